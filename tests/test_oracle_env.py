@@ -1,0 +1,40 @@
+"""CPU: the C oracle's env-level logic (PD, RFC, obs v2, termination, reward) against traces of the REFERENCE's own
+Python run over the same oracle physics (tools/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def load_expert(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, f"expert_{tag}.npz"))
+    ex = {k: z[k] for k in z.files}
+    shape_obs = np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+    return ex, shape_obs
+
+
+@pytest.mark.parametrize("tag,act", [("sway", "zero"), ("sway", "noise"), ("kick", "noise")])
+def test_env_trace_matches_reference_python(golden_dir, tag, act):
+    g = np.load(os.path.join(golden_dir, f"env_{tag}_{act}.npz"))
+    ex, so = load_expert(golden_dir, tag)
+    env = O.Env(O.Model(), ex, so)
+    obs0 = env.reset()
+    np.testing.assert_allclose(obs0, g["obs0"], rtol=0, atol=1e-9)
+    worst = 0.0
+    for t in range(len(g["reward"])):
+        obs, r, done, info = env.step(g["action"][t])
+        np.testing.assert_allclose(env.torque, g["torque"][t], rtol=1e-7, atol=1e-6, err_msg=f"torque t={t}")
+        np.testing.assert_allclose(env.d.qpos, g["qpos"][t], rtol=0, atol=1e-7, err_msg=f"qpos t={t}")
+        np.testing.assert_allclose(env.d.qvel, g["qvel"][t], rtol=0, atol=1e-5, err_msg=f"qvel t={t}")
+        np.testing.assert_allclose(obs, g["obs"][t], rtol=0, atol=1e-5, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(env.bquat, g["bquat"][t], atol=1e-8)
+        np.testing.assert_allclose(env.prev_bquat, g["prev_bquat"][t], atol=1e-8)
+        np.testing.assert_allclose(info["c_info"], g["c_info"][t], rtol=0, atol=1e-6, err_msg=f"c_info t={t}")
+        assert abs(r - g["reward"][t]) < 1e-6
+        assert abs(env.body_diff() - g["body_diff"][t]) < 1e-7
+        assert info["fail"] == bool(g["fail"][t]) and info["end"] == bool(g["end"][t])
+        assert abs(info["percent"] - g["percent"][t]) < 1e-12
+        worst = max(worst, np.abs(env.d.qpos - g["qpos"][t]).max())
+    assert worst < 1e-7

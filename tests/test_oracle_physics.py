@@ -1,0 +1,71 @@
+"""CPU: physical invariants the L0 restatement is held to in lieu of MuJoCo."""
+import os
+import tempfile
+
+import numpy as np
+
+from oracle import oracle as O
+
+
+def _random_state(m, rng, z=3.0):
+    q = m.qpos0.copy()
+    q[2] = z
+    q[3:7] = rng.normal(size=4)
+    q[3:7] /= np.linalg.norm(q[3:7])
+    q[7:] = rng.uniform(-0.6, 0.6, 69)
+    return q
+
+
+def test_total_mass_and_mass_matrix_spd():
+    m, d = O.Model(), O.Data()
+    assert abs(m.z["body_mass"].sum() - 80.29) < 0.05          # 80.3 kg at density 1000
+    d.qpos[:] = _random_state(m, np.random.default_rng(0))
+    O.forward(m, d)
+    M = d.M.reshape(75, 75)
+    assert np.abs(M - M.T).max() < 1e-12
+    assert np.linalg.eigvalsh(M).min() > 0.009                  # >= armature
+    assert abs(M[0, 0] - m.z["body_mass"].sum()) < 1e-9
+
+
+def test_free_fall_is_minus_g():
+    m, d = O.Model(), O.Data()
+    d.qpos[:] = _random_state(m, np.random.default_rng(1))
+    O.forward(m, d)
+    assert d.ncon == 0
+    assert abs(d.qacc[2] + 9.81) < 1e-9
+    assert np.abs(np.delete(d.qacc, 2)).max() < 1e-9
+
+
+def test_energy_and_momentum_conservation_contact_free():
+    z = dict(np.load(O.MODEL_NPZ))
+    z["timestep"] = np.float64(1e-5)
+    p = os.path.join(tempfile.mkdtemp(), "m.npz")
+    np.savez(p, **z)
+    m, d = O.Model(p), O.Data()
+    rng = np.random.default_rng(2)
+    d.qpos[:] = _random_state(m, rng)
+    d.qvel[:] = rng.normal(size=75)
+    e0, p0 = O.energy(m, d)
+    n = 1500
+    for _ in range(n):
+        O.step(m, d)
+    e1, p1 = O.energy(m, d)
+    assert abs(e1 - e0) / abs(e0) < 2e-6                       # C(q,v) consistent with M(q)
+    assert np.abs(p1[:2] - p0[:2]).max() < 1e-3
+    assert abs((p1[2] - p0[2]) - (-9.81 * z["body_mass"].sum() * n * 1e-5)) < 1e-3
+
+
+def test_resting_contact_supports_weight_without_deep_penetration():
+    import joblib  # noqa: F401  (not needed: qpos below is a plain array)
+    m, d = O.Model(), O.Data()
+    q = m.qpos0.copy()
+    q[2] = 0.97
+    q[3:7] = [0.7071068, 0.7071068, 0, 0]                      # Y-up rest pose -> Z-up world (base_rot)
+    d.qpos[:] = q
+    for _ in range(1800):
+        O.step(m, d)
+    assert d.ncon > 0
+    f = d.efc_force[:4 * d.ncon].sum()
+    assert abs(f - 9.81 * m.z["body_mass"].sum()) / (9.81 * 80.29) < 0.05
+    assert d.con_dist[:d.ncon].min() > -0.02
+    assert np.abs(d.qvel[:3]).max() < 0.05                     # undamped limp limbs may still jiggle; the root rests

@@ -1,0 +1,173 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by executing the REFERENCE's own Python (see tools/ref_harness.py).
+
+Runs only in the build container (needs /root/reference); the vectors it writes travel with the repo.
+  expert_<clip>.npz     inputs pose_aa/trans/beta/gender  ->  smpl_to_qpose + Humanoid.qpos_fk outputs
+                        (uhc/smpllib/smpl_mujoco.py:543-607, uhc/smpllib/torch_smpl_humanoid.py:155-261)
+  env_<clip>_<act>.npz  HumanoidEnv.reset/step + world_rfc_implicit_reward traces on the oracle physics
+                        (uhc/envs/humanoid_im.py, uhc/losses/reward_function.py:12-88)
+  ppo_small.npz         PolicyGaussian / Value / estimate_advantages / AgentPPO.update_policy / ZFilter traces
+                        (uhc/khrylib/rl/core/*, uhc/khrylib/rl/agents/agent_ppo.py, khrylib/utils/zfilter.py)
+  math_doctest.npz      the known-answer constants in uhc/utils/transformation.py doctests
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_harness as H  # noqa: E402
+
+OUT = os.path.join(H.ROOT, "tests", "golden")
+EXPERT_KEYS = ["qpos", "qvel", "wbpos", "wbquat", "bquat", "body_com", "bangvel", "ee_wpos", "ee_pos", "com", "rlinv",
+               "rlinv_local", "rangv"]
+
+
+def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train"):
+    from uhc.losses.reward_function import world_rfc_implicit_reward
+    seq = dl.get_sample_from_key(key, full_sample=False, fr_start=0)
+    seq = {k: (v[:nframes] if hasattr(v, "shape") and v.shape[:1] == (300,) or (hasattr(v, "shape") and len(v) > nframes) else v)
+           for k, v in seq.items()}
+    env = H.make_env(cfg, seq, mode=mode)
+    env.seed(seed)
+    ex = env.expert
+    np.savez_compressed(os.path.join(OUT, f"expert_{tag}.npz"), pose_aa=seq["pose_aa"][:, :72].copy(),
+                        trans=seq["trans"], beta=seq["beta"], gender=seq["gender"],
+                        height_lb=ex["height_lb"], length=ex["len"], **{k: ex[k] for k in EXPERT_KEYS})
+    rng = np.random.RandomState(seed)
+    obs0 = env.reset()
+    rec = {k: [] for k in ("action", "obs", "reward", "c_info", "fail", "end", "percent", "qpos", "qvel", "torque",
+                           "body_diff", "xpos", "bquat", "prev_bquat", "ncon")}
+    for t in range(nsteps):
+        if act_mode == "zero":
+            a = np.zeros(env.action_dim)
+        else:
+            a = rng.normal(0.0, 0.1, env.action_dim)
+            a[69:75] *= 0.3
+        ob, _, done, info = env.step(a.copy())
+        r, ci = world_rfc_implicit_reward(env, None, a, info)
+        rec["action"].append(a); rec["obs"].append(ob); rec["reward"].append(r); rec["c_info"].append(ci)
+        rec["fail"].append(bool(info["fail"])); rec["end"].append(bool(info["end"])); rec["percent"].append(info["percent"])
+        rec["qpos"].append(env.data.qpos.copy()); rec["qvel"].append(env.data.qvel.copy())
+        rec["torque"].append(np.array(env.curr_torque)); rec["body_diff"].append(env.calc_body_diff())
+        rec["xpos"].append(env.data.body_xpos[1:].copy()); rec["bquat"].append(env.bquat.copy())
+        rec["prev_bquat"].append(env.prev_bquat.copy()); rec["ncon"].append(env.data.ncon)
+        if info["end"]:
+            break
+    np.savez_compressed(os.path.join(OUT, f"env_{tag}_{act_mode}.npz"), obs0=obs0, expert=f"expert_{tag}.npz",
+                        **{k: np.array(v) for k, v in rec.items()})
+    print(tag, act_mode, "steps", len(rec["reward"]), "fails", int(np.sum(rec["fail"])), "mean r %.4f" % np.mean(rec["reward"]),
+          "max ncon", max(rec["ncon"]))
+
+
+def gen_ppo():
+    import torch
+    from uhc.khrylib.models.mlp import MLP
+    from uhc.khrylib.rl.core.policy_gaussian import PolicyGaussian
+    from uhc.khrylib.rl.core.critic import Value
+    from uhc.khrylib.rl.core.common import estimate_advantages
+    from uhc.khrylib.rl.agents.agent_ppo import AgentPPO
+    from uhc.khrylib.utils.zfilter import ZFilter
+
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(1)
+    rng = np.random.RandomState(1)
+    S, A, N, hs = 657, 105, 384, [96, 64, 48]
+
+    class Cfg:
+        policy_hsize, policy_htype, fix_std, log_std = hs, "gelu", True, -2.3
+
+    pol = PolicyGaussian(Cfg(), action_dim=A, state_dim=S)
+    val = Value(MLP(S, hs, "gelu"))
+    # obs normaliser trace
+    zf = ZFilter((S,), clip=5)
+    raw = rng.normal(0, 2.0, (40, S)) * rng.uniform(0.1, 3, S)
+    zout = np.array([zf(x) for x in raw])
+    states = rng.normal(0, 1, (N, S)).clip(-5, 5)
+    st = torch.tensor(states)
+    with torch.no_grad():
+        mean = pol.forward(st).loc.numpy()
+        actions_t = pol.select_action(st, False)
+        logp = pol.get_log_prob(st, actions_t).numpy()
+        values = val(st).numpy()
+    actions = actions_t.numpy()
+    rewards = rng.uniform(0, 1, N)
+    masks = (rng.uniform(0, 1, N) > 0.05).astype(np.float64)
+    masks[-1] = 0
+    adv, ret = estimate_advantages(torch.tensor(rewards)[:, None], torch.tensor(masks)[:, None], torch.tensor(values), 0.95, 0.95)
+    exps = (rng.uniform(0, 1, N) > 0.1).astype(np.float64)
+    p0 = {k: v.detach().numpy().copy() for k, v in pol.state_dict().items()}
+    v0 = {k: v.detach().numpy().copy() for k, v in val.state_dict().items()}
+
+    agent = AgentPPO.__new__(AgentPPO)
+    agent.policy_net, agent.value_net = pol, val
+    agent.optimizer_policy = torch.optim.Adam(pol.parameters(), lr=5e-5)
+    agent.optimizer_value = torch.optim.Adam(val.parameters(), lr=3e-4)
+    agent.clip_epsilon, agent.opt_num_epochs, agent.use_mini_batch = 0.2, 3, False
+    agent.policy_grad_clip = [(pol.parameters(), 40)]
+    agent.update_modules = [pol, val]
+    agent.value_opt_niter = 1
+    agent.update_policy(st, actions_t, ret, adv, torch.tensor(exps)[:, None])
+    p1 = {k: v.detach().numpy().copy() for k, v in pol.state_dict().items()}
+    v1 = {k: v.detach().numpy().copy() for k, v in val.state_dict().items()}
+    out = dict(hsize=np.array(hs), states=states, actions=actions, mean=mean, logp=logp, values=values, rewards=rewards,
+               masks=masks, advantages=adv.numpy(), returns=ret.numpy(), exps=exps, gamma=0.95, tau=0.95, clip_eps=0.2,
+               epochs=3, policy_lr=5e-5, value_lr=3e-4, grad_clip=40.0, z_raw=raw, z_out=zout, z_mean=zf.rs.mean,
+               z_std=zf.rs.std, z_n=zf.rs.n)
+    for k, v in p0.items():
+        out["p0." + k] = v
+    for k, v in p1.items():
+        out["p1." + k] = v
+    for k, v in v0.items():
+        out["v0." + k] = v
+    for k, v in v1.items():
+        out["v1." + k] = v
+    np.savez_compressed(os.path.join(OUT, "ppo_small.npz"), **out)
+    print("ppo_small: N", N, "adv mean/std", adv.mean().item(), adv.std().item())
+
+
+def gen_math():
+    from uhc.utils import transformation as T
+    from uhc.utils import math_utils as MU
+    rng = np.random.RandomState(3)
+    qs = rng.normal(size=(16, 4))
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    vs = rng.normal(size=(16, 3))
+    out = dict(
+        q=qs, v=vs,
+        about_axis=T.quaternion_about_axis(0.123, [1, 0, 0]),                     # transformation.py:350-351
+        mul_doctest=T.quaternion_multiply([4, 1, -2, 3], [8, -5, 6, 7]),          # transformation.py:1481-1483
+        euler_doctest=T.quaternion_from_euler(1, 2, 3, "ryxz"),                   # transformation.py:1237-1239
+        mul=np.array([T.quaternion_multiply(qs[i], qs[(i + 1) % 16]) for i in range(16)]),
+        inv=np.array([T.quaternion_inverse(q * 1.3) for q in qs]),
+        euler_rzyx=np.array([T.quaternion_from_euler(v[0], v[1], v[2], "rzyx") for v in vs]),
+        heading=np.array([MU.get_heading(q) for q in qs]),
+        heading_q=np.array([MU.get_heading_q(q) for q in qs]),
+        de_heading=np.array([MU.de_heading(q) for q in qs]),
+        rot_from_quat=np.array([T.rotation_from_quaternion(q) for q in qs]),
+        transform_vec=np.array([MU.transform_vec(v, q, "root") for v, q in zip(vs, qs)]),
+        quat_mul_vec=np.array([MU.quat_mul_vec(q, v) for v, q in zip(vs, qs)]),
+    )
+    np.savez_compressed(os.path.join(OUT, "math_doctest.npz"), **out)
+    print("math goldens ok", out["mul_doctest"])
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    H.install()
+    what = sys.argv[1:] or ["math", "env", "ppo"]
+    if "math" in what:
+        gen_math()
+    if "env" in what:
+        cfg = H.make_cfg()
+        from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
+        dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
+        gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 60, "zero")
+        gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 60, "noise")
+        gen_env(cfg, dl, "0-BioMotionLab_NTroje_rub008_0025_kicking1_poses", "kick", 70, 69, "noise")
+    if "ppo" in what:
+        gen_ppo()
+
+
+if __name__ == "__main__":
+    main()
