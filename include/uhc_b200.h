@@ -1,0 +1,86 @@
+/* uhc_b200.h -- C ABI of the B200 humanoid-imitation engine (libuhc_b200.so).
+ *
+ * The reference (ZhengyiLuo/UHC) exposes NO native interface: its boundary is duck-typed Python over mujoco-py.
+ * Each entry point below names the reference Python call it replaces (file:line under the reference tree); the
+ * ctypes binding a maintainer adds on the reference side is shown in INTEGRATION.md and implemented in
+ * uhc_b200/engine.py.  All functions return 0 on success, <0 on error (uhc_last_error() gives the text); nothing
+ * throws across the ABI.  A per-env solver/NaN failure is not an error: it sets that env's `fail` flag
+ * (mirrors the try/except at uhc/envs/humanoid_im.py:1207-1211).
+ * Pointers suffixed _dev are CUDA device pointers owned by the caller (e.g. torch tensors); _host are host pointers.
+ * One engine per GPU; calls are stream-ordered on the cudaStream_t passed as `stream`; an engine is not thread-safe.
+ */
+#ifndef UHC_B200_H
+#define UHC_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UHC_NB 24
+#define UHC_NQ 76
+#define UHC_NV 75
+#define UHC_NU 69
+#define UHC_OBS_DIM 657
+#define UHC_ACT_DIM 105
+#define UHC_EX_SIZE 508   /* expert frame record: qpos76 qvel75 wbpos72 wbquat96 bquat96 bangvel72 ee_wpos15 com3 pad3 */
+#define UHC_BODYF 20
+
+typedef struct UhcEngine UhcEngine;
+
+/* Flat humanoid model tables (built by uhc_b200/model.py from the compiled XML+STL model). Replaces the MuJoCo model
+ * object created by mujoco_py.load_model_from_xml at uhc/envs/humanoid_im.py:174 / mujoco_env.py:18. */
+typedef struct {
+    int nvert, nnbr;
+    const double *body_f;   /* [24][20] offset3 ipos3 mass inertia6 invweight bsphere4 diffw pad */
+    const double *dof_f;    /* [75][4]  armature kp kd torque_limit */
+    const double *hull;     /* [nvert][3] convex-hull vertices, body frame */
+    const int *hull_adr, *hull_num, *nbr, *nbradr;
+    const int *parent, *depth, *child_adr, *child, *body_sub_end, *dep, *madr, *dof_sub_end, *dof_body;
+    const short *rowadr; const unsigned char *colidx, *ent_row, *ent_col; const int *ee;
+    double dt, margin, mu, solref[2], solimp[5], gravz;
+} UhcModelHost;
+
+/* Task configuration: the cfg attributes HumanoidEnv / world_rfc_implicit_reward read
+ * (uhc/envs/humanoid_im.py:85-89,1138-1142,1228-1235; uhc/losses/reward_function.py:14-30). */
+typedef struct {
+    double base_rot[4], rfc_scale, rfc_lim, rfc_rate, body_diff_thresh;
+    int meta_pd, env_episode_len, trail_steps, newton_max_iter;
+    double w[5], k[5], newton_tol;
+} UhcEnvCfg;
+
+const char *uhc_last_error(void);
+
+/* precision: 32 (product) or 64 (fp64 debug build of the same kernels). */
+int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_envs, int device, int precision, UhcEngine **out);
+void uhc_engine_destroy(UhcEngine *e);
+int uhc_engine_set_cfg(UhcEngine *e, const UhcEnvCfg *cfg);
+
+/* Expert tables for C clips (replaces HumanoidEnv.load_expert's per-episode recompute, humanoid_im.py:182-215):
+ * frames_host = concatenated [sum(len)][UHC_EX_SIZE] doubles, shape_host = [C][17] (beta16, gender). */
+int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *frames_host, const double *shape_host);
+
+/* env.reset() for n envs (mujoco_env.py:95-104 + humanoid_im.py:1245-1299).  clip/start/len select the expert slice
+ * (dataset_amass_single.py:200-253); q/v override (may be NULL) = [n][76]/[n][75] floats on the device.
+ * obs_dev = [num_envs][657] (rows of the listed envs are written). */
+int uhc_env_reset(UhcEngine *e, int n, const int *env_ids_host, const int *clip_host, const int *start_host, const int *len_host,
+                  const float *qpos_dev, const float *qvel_dev, float *obs_dev, void *stream);
+
+/* env.step(a) for ALL envs (humanoid_im.py:1192-1243) fused with custom_reward (reward_function.py:12-88):
+ * actions_dev [E][105] -> obs_dev [E][657], reward_dev [E], cinfo_dev [E][5], fail/end [E] (int32), percent [E];
+ * torque_dev (optional) [E][15][69] = the per-substep torques (env.curr_torque). */
+int uhc_env_step(UhcEngine *e, const float *actions_dev, float *obs_dev, float *reward_dev, float *cinfo_dev, int *fail_dev,
+                 int *end_dev, float *percent_dev, float *torque_dev, void *stream);
+
+/* Host-buffer convenience used by the single-env facade and the end-to-end benchmark: copies in/out inside the call. */
+int uhc_env_step_host(UhcEngine *e, const float *actions_host, float *obs_host, float *reward_host, float *cinfo_host,
+                      int *fail_host, int *end_host, float *percent_host);
+
+/* parity hooks / fail_safe (humanoid_im.py:902-905): read or overwrite the simulator state of one env (host doubles). */
+int uhc_env_get_state(UhcEngine *e, int env, double *qpos76, double *qvel75, double *xpos72, double *bquat96, int *istate8);
+int uhc_env_set_state(UhcEngine *e, int env, const double *qpos76, const double *qvel75);
+int uhc_num_envs(const UhcEngine *e);
+int uhc_kernel_launches(const UhcEngine *e);   /* kernels launched by this engine so far (bench `gpu_launches`) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

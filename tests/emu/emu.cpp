@@ -1,0 +1,101 @@
+// emu.cpp -- TEST INFRASTRUCTURE: compiles the product kernel source (uhc_b200/csrc/sim_core.h, env_step.h) as a host
+// lane-loop emulation (-DUHC_EMU) so the warp-per-env algorithms can be checked against the oracle on a CPU-only box.
+// Never loaded by the product path (uhc_b200/engine.py only loads the CUDA library).
+#define UHC_EMU 1
+#include <vector>
+#include <cstring>
+#include "../../include/uhc_b200.h"
+#include "../../uhc_b200/csrc/env_step.h"
+
+using namespace uhc;
+
+template <class Real>
+struct Emu {
+    std::vector<Real> body_f, dof_f, hull, state, expert, shape;
+    std::vector<int> hull_adr, hull_num, nbr, nbradr, parent, depth, child_adr, child, body_sub_end, dep, madr, dof_sub_end, dof_body, ee, istate, clip_adr;
+    std::vector<short> rowadr; std::vector<unsigned char> colidx, ent_row, ent_col;
+    EngineView<Real> ev; Work<Real> w; int E;
+};
+
+template <class Real, class T> static void cp(std::vector<Real> &d, const T *s, size_t n) { d.resize(n); for (size_t i = 0; i < n; i++) d[i] = (Real)s[i]; }
+
+template <class Real>
+static void set_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) {
+    for (int i = 0; i < 4; i++) c.base_rot[i] = (Real)h->base_rot[i];
+    c.rfc_scale = (Real)h->rfc_scale; c.rfc_lim = (Real)h->rfc_lim; c.rfc_rate = (Real)h->rfc_rate; c.body_diff_thresh = (Real)h->body_diff_thresh;
+    c.meta_pd = h->meta_pd; c.env_episode_len = h->env_episode_len; c.trail_steps = h->trail_steps; c.newton_max_iter = h->newton_max_iter;
+    for (int i = 0; i < 5; i++) { c.w[i] = (Real)h->w[i]; c.k[i] = (Real)h->k[i]; }
+    c.newton_tol = (Real)h->newton_tol;
+}
+
+template <class Real>
+static Emu<Real> *create(const UhcModelHost *m, const UhcEnvCfg *cfg, int E) {
+    Emu<Real> *e = new Emu<Real>();
+    e->E = E;
+    cp(e->body_f, m->body_f, NB * BODYF); cp(e->dof_f, m->dof_f, NV * 4); cp(e->hull, m->hull, (size_t)m->nvert * 3);
+    cp(e->hull_adr, m->hull_adr, NB); cp(e->hull_num, m->hull_num, NB); cp(e->nbr, m->nbr, m->nnbr); cp(e->nbradr, m->nbradr, m->nvert + 1);
+    cp(e->parent, m->parent, NB); cp(e->depth, m->depth, NB); cp(e->child_adr, m->child_adr, NB + 1); cp(e->child, m->child, NB - 1);
+    cp(e->body_sub_end, m->body_sub_end, NB); cp(e->dep, m->dep, NV); cp(e->madr, m->madr, NV); cp(e->dof_sub_end, m->dof_sub_end, NV);
+    cp(e->dof_body, m->dof_body, NV); cp(e->ee, m->ee, 5);
+    cp(e->rowadr, m->rowadr, NV * 32); cp(e->colidx, m->colidx, NV * 32); cp(e->ent_row, m->ent_row, NNZ); cp(e->ent_col, m->ent_col, NNZ);
+    Model<Real> &M = e->ev.model;
+    M.body_f = e->body_f.data(); M.dof_f = e->dof_f.data(); M.hull = e->hull.data(); M.hull_adr = e->hull_adr.data(); M.hull_num = e->hull_num.data();
+    M.nbr = e->nbr.data(); M.nbradr = e->nbradr.data(); M.parent = e->parent.data(); M.depth = e->depth.data(); M.child_adr = e->child_adr.data();
+    M.child = e->child.data(); M.body_sub_end = e->body_sub_end.data(); M.dep = e->dep.data(); M.madr = e->madr.data(); M.dof_sub_end = e->dof_sub_end.data();
+    M.dof_body = e->dof_body.data(); M.rowadr = e->rowadr.data(); M.colidx = e->colidx.data(); M.ent_row = e->ent_row.data(); M.ent_col = e->ent_col.data();
+    M.ee = e->ee.data();
+    M.dt = (Real)m->dt; M.margin = (Real)m->margin; M.mu = (Real)m->mu; M.solref0 = (Real)m->solref[0]; M.solref1 = (Real)m->solref[1];
+    M.simp0 = (Real)m->solimp[0]; M.simp1 = (Real)m->solimp[1]; M.simp2 = (Real)m->solimp[2]; M.simp3 = (Real)m->solimp[3]; M.simp4 = (Real)m->solimp[4];
+    M.gravz = (Real)m->gravz;
+    set_cfg(e->ev.cfg, cfg);
+    e->state.assign((size_t)E * ST_SIZE, 0); e->istate.assign((size_t)E * SI_SIZE, 0);
+    e->ev.num_envs = E; e->ev.state = e->state.data(); e->ev.istate = e->istate.data();
+    return e;
+}
+
+template <class Real>
+static void load_clips(Emu<Real> *e, int nclips, const int *len, const double *frames, const double *shape) {
+    e->clip_adr.assign(nclips + 1, 0);
+    for (int i = 0; i < nclips; i++) e->clip_adr[i + 1] = e->clip_adr[i] + len[i];
+    cp(e->expert, frames, (size_t)e->clip_adr[nclips] * EX_SIZE); cp(e->shape, shape, (size_t)nclips * 17);
+    e->ev.expert = e->expert.data(); e->ev.clip_adr = e->clip_adr.data(); e->ev.clip_shape = e->shape.data();
+}
+
+extern "C" {
+void *emu_create(const UhcModelHost *m, const UhcEnvCfg *cfg, int E, int precision) {
+    return precision == 64 ? (void *)create<double>(m, cfg, E) : (void *)create<float>(m, cfg, E);
+}
+#define DISPATCH(h, prec, ...) do { if (prec == 64) { auto *e = (Emu<double> *)h; typedef double Real; (void)sizeof(Real); __VA_ARGS__; } else { auto *e = (Emu<float> *)h; typedef float Real; (void)sizeof(Real); __VA_ARGS__; } } while (0)
+void emu_destroy(void *h, int prec) { DISPATCH(h, prec, delete e); }
+void emu_load_clips(void *h, int prec, int nclips, const int *len, const double *frames, const double *shape) { DISPATCH(h, prec, load_clips(e, nclips, len, frames, shape)); }
+void emu_reset(void *h, int prec, int env, int clip, int start, int len, const double *qpos, const double *qvel, double *obs) {
+    DISPATCH(h, prec, {
+        std::vector<Real> q, v; if (qpos) cp(q, qpos, NQ); if (qvel) cp(v, qvel, NV);
+        env_reset_warp<Real, double>(e->ev, env, e->w, clip, start, len, qpos ? q.data() : nullptr, qvel ? v.data() : nullptr, obs);
+    });
+}
+int emu_step(void *h, int prec, int env, const double *action, double *obs, double *reward, double *cinfo, int *fail, int *end, double *percent, double *torque) {
+    int done = 0;
+    DISPATCH(h, prec, done = (env_step_warp<Real, double>(e->ev, env, e->w, action, obs, reward, cinfo, fail, end, percent, torque)));
+    return done;
+}
+void emu_get_state(void *h, int prec, int env, double *out, int *iout) {
+    DISPATCH(h, prec, { for (int i = 0; i < ST_SIZE; i++) out[i] = (double)e->state[(size_t)env * ST_SIZE + i]; for (int i = 0; i < SI_SIZE; i++) iout[i] = e->istate[(size_t)env * SI_SIZE + i]; });
+}
+// forward pass only on an arbitrary state: returns dense M, C, qacc, xpos for unit tests
+void emu_forward(void *h, int prec, const double *qpos, const double *qvel, const double *tau, const double *fapp, const double *aw, double *Msparse,
+                 double *Cout, double *qacc, double *xpos, int *ncon, int *iters) {
+    DISPATCH(h, prec, {
+        Work<Real> &w = e->w;
+        for (int i = 0; i < NQ; i++) w.q[i] = (Real)qpos[i];
+        for (int i = 0; i < NV; i++) { w.v[i] = (Real)qvel[i]; w.aw[i] = aw ? (Real)aw[i] : Real(0); }
+        for (int i = 0; i < NU; i++) w.tau[i] = (Real)tau[i];
+        Real fa[6]; for (int i = 0; i < 6; i++) fa[i] = (Real)fapp[i];
+        *iters = forward_dynamics(e->ev.model, e->ev.cfg, w, fa, true);
+        for (int i = 0; i < NNZ; i++) Msparse[i] = (double)w.M[i];
+        for (int i = 0; i < NV; i++) { Cout[i] = (double)w.C[i]; qacc[i] = (double)w.a[i]; }
+        for (int i = 0; i < 72; i++) xpos[i] = (double)(&w.xpos[0][0])[i];
+        *ncon = w.ncon;
+    });
+}
+}

@@ -1,0 +1,108 @@
+"""ctypes wrapper of the host emulation build of the product kernels (TEST INFRASTRUCTURE)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from uhc_b200.model import HumanoidModel
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libuhc_emu.so")
+ST = dict(Q=0, V=76, AW=152, C=228, XPOS=304, XQUAT=376, XIPOS=472, BQUAT=544, PBQUAT=640, M=736, SIZE=1960)
+EX_SIZE = 508
+
+
+class UhcEnvCfg(C.Structure):
+    _fields_ = [("base_rot", C.c_double * 4), ("rfc_scale", C.c_double), ("rfc_lim", C.c_double), ("rfc_rate", C.c_double),
+                ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
+                ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double)]
+
+
+def default_cfg(precision=32, **kw):
+    c = UhcEnvCfg()
+    c.base_rot = (C.c_double * 4)(0.7071, 0.7071, 0.0, 0.0)
+    c.rfc_scale, c.rfc_lim, c.rfc_rate, c.body_diff_thresh = 100.0, 100.0, 1.0, 0.5
+    c.meta_pd, c.env_episode_len, c.trail_steps = 1, 100000, 0
+    c.newton_max_iter = 20 if precision == 64 else 12
+    c.w = (C.c_double * 5)(0.3, 0.1, 0.45, 0.1, 0.05)
+    c.k = (C.c_double * 5)(2.0, 0.005, 5.0, 100.0, 1.0)
+    c.newton_tol = 1e-11 if precision == 64 else 1e-6
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def pack_expert(ex):
+    """expert dict (qpos, qvel, wbpos, wbquat, bquat, bangvel, ee_wpos, com) -> [T][508] record array."""
+    T = len(ex["qpos"])
+    out = np.zeros((T, EX_SIZE))
+    o = 0
+    for k, n in (("qpos", 76), ("qvel", 75), ("wbpos", 72), ("wbquat", 96), ("bquat", 96), ("bangvel", 72), ("ee_wpos", 15), ("com", 3)):
+        out[:, o:o + n] = np.asarray(ex[k]).reshape(T, n)
+        o += n
+    return out
+
+
+def build():
+    srcs = [os.path.join(_HERE, "emu.cpp"), os.path.join(_HERE, "..", "..", "uhc_b200", "csrc", "sim_core.h"),
+            os.path.join(_HERE, "..", "..", "uhc_b200", "csrc", "env_step.h")]
+    if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", _SO, srcs[0]])
+    return _SO
+
+
+def _p(a, t=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+class Emu:
+    def __init__(self, precision=64, num_envs=1, model=None, **cfg):
+        self.lib = C.CDLL(build())
+        self.lib.emu_create.restype = C.c_void_p
+        self.prec = precision
+        self.model = model or HumanoidModel()
+        self._ms = self.model.host_struct()
+        self._cfg = default_cfg(precision, **cfg)
+        self.h = C.c_void_p(self.lib.emu_create(C.byref(self._ms), C.byref(self._cfg), C.c_int(num_envs), C.c_int(precision)))
+
+    def load_clips(self, experts, shapes):
+        lens = np.array([len(e["qpos"]) for e in experts], np.int32)
+        frames = np.ascontiguousarray(np.concatenate([pack_expert(e) for e in experts]))
+        shp = np.ascontiguousarray(np.asarray(shapes, dtype=np.float64).reshape(len(experts), 17))
+        self.lens = lens
+        self.lib.emu_load_clips(self.h, self.prec, len(experts), _p(lens, C.c_int), _p(frames), _p(shp))
+
+    def reset(self, env=0, clip=0, start=0, length=None, qpos=None, qvel=None):
+        obs = np.zeros(657)
+        L = int(self.lens[clip]) if length is None else length
+        q = None if qpos is None else np.ascontiguousarray(qpos, dtype=np.float64)
+        v = None if qvel is None else np.ascontiguousarray(qvel, dtype=np.float64)
+        self.lib.emu_reset(self.h, self.prec, env, clip, start, L, _p(q), _p(v), _p(obs))
+        return obs
+
+    def step(self, action, env=0):
+        a = np.ascontiguousarray(action, dtype=np.float64)
+        obs, rew, ci, pct, tq = np.zeros(657), np.zeros(1), np.zeros(5), np.zeros(1), np.zeros((15, 69))
+        fail, end = C.c_int(0), C.c_int(0)
+        done = self.lib.emu_step(self.h, self.prec, env, _p(a), _p(obs), _p(rew), _p(ci), C.byref(fail), C.byref(end), _p(pct), _p(tq))
+        return obs, float(rew[0]), bool(done), {"fail": bool(fail.value), "end": bool(end.value), "percent": float(pct[0]), "c_info": ci, "torque": tq}
+
+    def state(self, env=0):
+        out, iout = np.zeros(ST["SIZE"]), np.zeros(8, np.int32)
+        self.lib.emu_get_state(self.h, self.prec, env, _p(out), _p(iout, C.c_int))
+        return out, iout
+
+    def forward(self, qpos, qvel, tau=None, fapp=None, aw=None):
+        tau = np.zeros(69) if tau is None else np.ascontiguousarray(tau, dtype=np.float64)
+        fapp = np.zeros(6) if fapp is None else np.ascontiguousarray(fapp, dtype=np.float64)
+        aw_ = None if aw is None else np.ascontiguousarray(aw, dtype=np.float64)
+        Ms, Cc, qa, xp = np.zeros(1221), np.zeros(75), np.zeros(75), np.zeros(72)
+        ncon, iters = C.c_int(0), C.c_int(0)
+        self.lib.emu_forward(self.h, self.prec, _p(np.ascontiguousarray(qpos, dtype=np.float64)), _p(np.ascontiguousarray(qvel, dtype=np.float64)),
+                             _p(tau), _p(fapp), _p(aw_), _p(Ms), _p(Cc), _p(qa), _p(xp), C.byref(ncon), C.byref(iters))
+        M = np.zeros((75, 75))
+        m = self.model
+        M[m.ent_row, m.ent_col] = Ms
+        M = M + M.T - np.diag(np.diag(M))
+        return dict(M=M, C=Cc, qacc=qa, xpos=xp.reshape(24, 3), ncon=ncon.value, iters=iters.value)

@@ -1,0 +1,144 @@
+// env_step.h -- one warp advances one humanoid environment by one 30 Hz control step (15 physics substeps) and runs the
+// imitation-task epilogue; also the reset path.  Shared by the CUDA kernels (step_kernel.cu) and the host emulation
+// (tests/emu).  Reference: uhc/envs/humanoid_im.py:1192-1243 (step), :1145-1190 (do_simulation), :1245-1299 (reset_model),
+// uhc/khrylib/rl/envs/common/mujoco_env.py:95-113 (reset / set_state).
+#pragma once
+#include "sim_core.h"
+
+namespace uhc {
+
+// everything a warp needs to find its environment's data
+template <class Real>
+struct EngineView {
+    Model<Real> model;
+    EnvCfg<Real> cfg;
+    int num_envs;
+    Real *state;            // [E][ST_SIZE]
+    int *istate;            // [E][SI_SIZE]
+    const Real *expert;     // [total_frames][EX_SIZE]
+    const int *clip_adr;    // [C+1] first frame of each clip in `expert`
+    const Real *clip_shape; // [C][17] beta[16], gender
+};
+
+template <class Real>
+UHC_DEV const Real *expert_frame(const EngineView<Real> &ev, int clip, int start, int len, int t) {  // humanoid_im.py:1322
+    int i = start + t; if (i > len - 1) i = len - 1;
+    return ev.expert + (size_t)(UHC_LDG(ev.clip_adr + clip) + i) * EX_SIZE;
+}
+
+template <class Real>
+UHC_DEV void load_state(const EngineView<Real> &ev, int env, Work<Real> &w) {
+    const Real *st = ev.state + (size_t)env * ST_SIZE;
+    LANES_BEGIN
+    for (int i = lane; i < NQ; i += 32) w.q[i] = st[ST_Q + i];
+    for (int i = lane; i < NV; i += 32) { w.v[i] = st[ST_V + i]; w.aw[i] = st[ST_AW + i]; w.C[i] = st[ST_C + i]; }
+    for (int i = lane; i < NNZ; i += 32) w.M[i] = st[ST_M + i];
+    LANES_END
+}
+template <class Real>
+UHC_DEV void store_state(const EngineView<Real> &ev, int env, const Work<Real> &w, const Real *bquat, const Real *pbquat) {
+    Real *st = ev.state + (size_t)env * ST_SIZE;
+    LANES_BEGIN
+    for (int i = lane; i < NQ; i += 32) st[ST_Q + i] = w.q[i];
+    for (int i = lane; i < NV; i += 32) { st[ST_V + i] = w.v[i]; st[ST_AW + i] = w.aw[i]; st[ST_C + i] = w.C[i]; }
+    for (int i = lane; i < NNZ; i += 32) st[ST_M + i] = w.M[i];
+    for (int i = lane; i < 72; i += 32) { st[ST_XPOS + i] = (&w.xpos[0][0])[i]; st[ST_XIPOS + i] = (&w.xipos[0][0])[i]; }
+    for (int i = lane; i < 96; i += 32) { st[ST_XQUAT + i] = (&w.xquat[0][0])[i]; st[ST_BQUAT + i] = bquat[i]; if (pbquat) st[ST_PBQUAT + i] = pbquat[i]; }
+    LANES_END
+}
+
+// reset one env onto frame 0 of (clip, start, len): state <- expert qpos/qvel (or the override), sim.forward(), obs.
+// bquat is left at the qpos0 value (identity quats) exactly as reset_model leaves it (humanoid_im.py:1277 runs before set_state).
+template <class Real, class ObsT>
+UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, int clip, int start, int len,
+                            const Real *qpos_override, const Real *qvel_override, ObsT *obs) {
+    const Real *e0 = expert_frame(ev, clip, start, len, 0);
+    LANES_BEGIN
+    for (int i = lane; i < NQ; i += 32) w.q[i] = qpos_override ? qpos_override[i] : e0[EX_QPOS + i];
+    for (int i = lane; i < NV; i += 32) { w.v[i] = qvel_override ? qvel_override[i] : e0[EX_QVEL + i]; w.aw[i] = 0; }
+    for (int i = lane; i < ACT_DIM; i += 32) w.act[i] = 0;
+    LANES_END
+    Real fapp[6] = {0, 0, 0, 0, 0, 0};
+    const int iters = forward_dynamics(ev.model, ev.cfg, w, fapp, false);
+    world_quat(ev.model, w.q, w);
+    int *is = ev.istate + (size_t)env * SI_SIZE;
+    Real *st = ev.state + (size_t)env * ST_SIZE;
+    LANES_BEGIN
+    for (int i = lane; i < 96; i += 32) { const Real v = (i & 3) == 0 ? Real(1) : Real(0); st[ST_BQUAT + i] = v; st[ST_PBQUAT + i] = v; }
+    if (lane == 0) { is[SI_CUR_T] = 0; is[SI_CLIP] = clip; is[SI_START] = start; is[SI_LEN] = len; is[SI_NEWTON] = iters; is[SI_NCON] = w.ncon; }
+    LANES_END
+    if (obs) obs_v2(ev.cfg, w, expert_frame(ev, clip, start, len, 1), ev.clip_shape + 17 * clip, obs);
+    Real *stq = ev.state + (size_t)env * ST_SIZE;
+    LANES_BEGIN
+    for (int i = lane; i < NQ; i += 32) stq[ST_Q + i] = w.q[i];
+    for (int i = lane; i < NV; i += 32) { stq[ST_V + i] = w.v[i]; stq[ST_AW + i] = 0; stq[ST_C + i] = w.C[i]; }
+    for (int i = lane; i < NNZ; i += 32) stq[ST_M + i] = w.M[i];
+    for (int i = lane; i < 72; i += 32) { stq[ST_XPOS + i] = (&w.xpos[0][0])[i]; stq[ST_XIPOS + i] = (&w.xipos[0][0])[i]; }
+    for (int i = lane; i < 96; i += 32) stq[ST_XQUAT + i] = (&w.xquat[0][0])[i];
+    LANES_END
+}
+
+// one control step.  out_* may be null.  Returns done; fills flags.
+template <class Real, class ObsT>
+UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, const ObsT *action, ObsT *obs, ObsT *reward,
+                          ObsT *cinfo_out, int *fail_out, int *end_out, ObsT *percent_out, ObsT *torque_out) {
+    int *is = ev.istate + (size_t)env * SI_SIZE;
+    Real *st = ev.state + (size_t)env * ST_SIZE;
+    const int clip = is[SI_CLIP], start = is[SI_START], len = is[SI_LEN];
+    int cur_t = is[SI_CUR_T];
+    load_state(ev, env, w);
+    LANES_BEGIN
+    for (int i = lane; i < ACT_DIM; i += 32) w.act[i] = (Real)action[i];
+    LANES_END
+    const Real *target = expert_frame(ev, clip, start, len, cur_t + 1) + EX_QPOS + 7;
+    int iters = 0, maxcon = 0;
+    for (int it = 0; it < NSUB; ++it) {
+        pd_torque(ev.model, ev.cfg, w, target, it);
+        if (torque_out) {
+            LANES_BEGIN
+            for (int j = lane; j < NU; j += 32) torque_out[it * NU + j] = (ObsT)w.tau[j];
+            LANES_END
+        }
+        Real fapp[6];
+        rfc_implicit(ev.cfg, w, fapp);
+        iters += forward_dynamics(ev.model, ev.cfg, w, fapp, true);
+        if (w.ncon > maxcon) maxcon = w.ncon;
+        if (it == NSUB - 1) world_quat(ev.model, w.q, w);  // pose of the last forward pass (what data.body_xquat holds)
+        integrate(ev.model, w);
+    }
+    cur_t += 1;
+    // body quats: prev <- stored, current from the new qpos (humanoid_im.py:1196, :1219)
+    Real *bq = st + ST_BQUAT, *pbq = st + ST_PBQUAT;
+    LANES_BEGIN
+    for (int i = lane; i < 96; i += 32) pbq[i] = bq[i];
+    LANES_END
+    body_quat(w, bq);
+    Real bd, rew, ci[5];
+    diff_and_reward(ev.model, ev.cfg, w, expert_frame(ev, clip, start, len, cur_t), bq, pbq, &bd, &rew, ci);
+    int fail = bd > ev.cfg.body_diff_thresh;
+    {   // a non-finite state can never pass "bd > thresh": flag it as a failure (mirrors the try/except at :1207-1211)
+        LVAR(int, bad);
+        LANES_BEGIN
+        int b = 0;
+        for (int i = lane; i < NQ; i += 32) if (!(w.q[i] == w.q[i]) || abs_(w.q[i]) > Real(1e6)) b = 1;
+        LV(bad) = b;
+        LANES_END
+        if (WBALLOT(bad)) fail = 1;
+    }
+    const int end = (cur_t >= ev.cfg.env_episode_len) || (cur_t + start >= len + ev.cfg.trail_steps - 1);
+    if (obs) obs_v2(ev.cfg, w, expert_frame(ev, clip, start, len, cur_t + 1), ev.clip_shape + 17 * clip, obs);
+    LANES_BEGIN
+    if (lane == 0) {
+        is[SI_CUR_T] = cur_t; is[SI_NEWTON] = iters; is[SI_NCON] = maxcon;
+        if (reward) *reward = (ObsT)rew;
+        if (fail_out) *fail_out = fail;
+        if (end_out) *end_out = end;
+        if (percent_out) *percent_out = (ObsT)((Real)cur_t / (Real)(len - 1));
+    }
+    if (cinfo_out && lane < 5) cinfo_out[lane] = (ObsT)ci[lane];
+    LANES_END
+    store_state(ev, env, w, bq, (const Real *)nullptr);
+    return fail || end;
+}
+
+}  // namespace uhc

@@ -1,0 +1,936 @@
+// sim_core.h -- the per-humanoid physics + imitation-task step, one WARP per environment.
+//
+// Product code (CUDA, sm_100a).  Everything in this header is written in an SPMD "phase" style:
+//     LANES_BEGIN ... per-lane code, no cross-lane dependency inside ... LANES_END   (= __syncwarp())
+// so that the very same source can also be compiled by g++ as a lane-loop emulation (tests/emu, -DUHC_EMU) and be
+// debugged on a CPU-only box.  The emulation is test infrastructure; the C-ABI library only ever launches the CUDA build.
+//
+// Algorithms (all world-aligned spatial vectors about the reference point O = root position):
+//   kinematics            level-synchronous tree pass, lane = body                         (a5: mj_kinematics)
+//   bias force C(q,v)     spatial recursive Newton-Euler, lane = body / lane = dof         (a5: mj_rne)
+//   mass matrix M         composite-rigid-body algorithm into a tree-sparse row-chain store (a5: mj_crb)
+//   stable PD             tree-sparse L^T D L of (M_stale + Kd dt), substitution             (a3: humanoid_im.py:1014-1076)
+//   floor contacts        plane / convex-hull support vertex + hull-graph neighbours        (a5: collision)
+//   constraint solve      primal Newton on the convex soft-constraint cost, Hessian = CRBA with contact-augmented
+//                         composite inertias, exact-direction + safeguarded 1-D Newton line search (a5: solver)
+//   integration           semi-implicit Euler, quaternion exponential map for the root      (a5: mj_Euler)
+//   epilogue              body quats, termination, observation v2, world_rfc_implicit reward (a6, a7, a10)
+// Reference behaviour being restated is cited next to each phase (file:line under the reference tree).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifndef UHC_EMU
+#include <cuda_runtime.h>
+#define UHC_DEV __device__ __forceinline__
+#define UHC_DEVNI __device__ __noinline__
+#define LANES_BEGIN { const int lane = (int)(threadIdx.x & 31);
+#define LANES_END } __syncwarp();
+#define LVAR(T, n) T n
+#define LV(n) n
+#define UHC_LDG(p) __ldg(p)
+#else
+#define UHC_DEV static inline
+#define UHC_DEVNI static
+#define LANES_BEGIN for (int lane = 0; lane < 32; ++lane) {
+#define LANES_END }
+#define LVAR(T, n) T n[32]
+#define LV(n) n[lane]
+#define UHC_LDG(p) (*(p))
+#endif
+
+namespace uhc {
+
+constexpr int NB = 24, NQ = 76, NV = 75, NU = 69, NSUB = 15;
+constexpr int OBS_DIM = 657, ACT_DIM = 105;
+constexpr int NNZ = 1221, NNZP = 1224;        // tree-sparse row-chain storage of M / H
+constexpr int NLOW = 39, NNZ_LOW = 420;       // dofs 0..38 (root, legs, torso, spine, chest): rows that contact Hessians touch
+constexpr int UPPER_BODY0 = 12;               // bodies >= Neck: arms, neck, head
+constexpr int MAXCON = 40;
+constexpr int MAXLEVEL = 8;
+constexpr int BODYF = 20;                     // floats per body in the model table
+// per-env state record in HBM (Real units)
+constexpr int ST_Q = 0, ST_V = 76, ST_AW = 152, ST_C = 228, ST_XPOS = 304, ST_XQUAT = 376, ST_XIPOS = 472,
+              ST_BQUAT = 544, ST_PBQUAT = 640, ST_M = 736, ST_SIZE = 1960;
+// per-env integer record
+constexpr int SI_CUR_T = 0, SI_CLIP = 1, SI_START = 2, SI_LEN = 3, SI_EPISODE = 4, SI_FLAGS = 5, SI_NEWTON = 6, SI_NCON = 7, SI_SIZE = 8;
+// expert frame record (Real units): qpos 76 | qvel 75 | wbpos 72 | wbquat 96 | bquat 96 | bangvel 72 | ee_wpos 15 | com 3 | pad
+constexpr int EX_QPOS = 0, EX_QVEL = 76, EX_WBPOS = 151, EX_WBQUAT = 223, EX_BQUAT = 319, EX_BANGVEL = 415, EX_EE = 487,
+              EX_COM = 502, EX_SIZE = 508;
+
+template <class Real>
+struct Model {
+    const Real *body_f;   // [NB][BODYF]: offset3 ipos3 mass inertia6(xx,yy,zz,xy,xz,yz) invw bsphere4 diffw pad
+    const Real *dof_f;    // [NV][4]: armature, kp, kd, torque_lim
+    const Real *hull;     // [nvert][3] body-local
+    const int *hull_adr, *hull_num, *nbr, *nbradr;
+    const int *parent, *depth, *child_adr, *child, *body_sub_end;
+    const int *dep, *madr, *dof_sub_end, *dof_body;
+    const short *rowadr;          // [NV][32]: madr[anc(k,s)]
+    const unsigned char *colidx;  // [NV][32]: anc(k,s)
+    const unsigned char *ent_row, *ent_col;  // [NNZ]
+    const int *ee;                // [5]
+    Real dt, margin, mu, solref0, solref1, simp0, simp1, simp2, simp3, simp4, gravz;
+};
+
+template <class Real>
+struct EnvCfg {
+    Real base_rot[4], rfc_scale, rfc_lim, rfc_rate, body_diff_thresh;
+    int meta_pd, env_episode_len, trail_steps, newton_max_iter;
+    Real w[5], k[5], newton_tol;
+};
+
+// per-environment working set (lives in shared memory on the GPU)
+template <class Real>
+struct Work {
+    Real q[NQ], v[NV + 1], aw[NV + 1], act[ACT_DIM + 3];
+    Real xpos[NB][3], xmat[NB][9], xipos[NB][3], xquat[NB][4];
+    Real S[NV][6];
+    Real Ic[NB][21];              // composite rigid inertia (first 10) during CRBA; composite contact matrix K (21) in Newton
+    Real M[NNZP], H[NNZP], Mt[NNZ_LOW], dinv[NV + 1];
+    Real C[NV + 1], fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
+    Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
+    Real scr[NV * 6 + 2];         // F_i = Ic * S_i scratch
+    // contacts
+    int cbody[MAXCON]; Real cr[MAXCON][3], cdist[MAXCON], cD[MAXCON], caref[MAXCON][4], cres[MAXCON][4], cjp[MAXCON][4];
+    int bcon_adr[NB + 1];
+    int ncon, upper_contact;
+};
+
+// ------------------------------------------------------------------------------------------------ scalar helpers
+UHC_DEV float rsqrt_(float x) { return 1.0f / sqrtf(x); }
+UHC_DEV double rsqrt_(double x) { return 1.0 / sqrt(x); }
+UHC_DEV void sincos_(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
+UHC_DEV void sincos_(double x, double *s, double *c) { *s = sin(x); *c = cos(x); }
+UHC_DEV float acos_(float x) { return acosf(x); }
+UHC_DEV double acos_(double x) { return acos(x); }
+UHC_DEV float exp_(float x) { return expf(x); }
+UHC_DEV double exp_(double x) { return exp(x); }
+UHC_DEV float abs_(float x) { return fabsf(x); }
+UHC_DEV double abs_(double x) { return fabs(x); }
+UHC_DEV float pow_(float x, float y) { return powf(x, y); }
+UHC_DEV double pow_(double x, double y) { return pow(x, y); }
+template <class R> UHC_DEV R min_(R a, R b) { return a < b ? a : b; }
+template <class R> UHC_DEV R max_(R a, R b) { return a > b ? a : b; }
+template <class R> UHC_DEV R clamp_(R x, R lo, R hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+template <class R> UHC_DEV void cross3(const R *a, const R *b, R *o) {
+    R x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+template <class R> UHC_DEV R dot3(const R *a, const R *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <class R> UHC_DEV R dot6(const R *a, const R *b) {
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+template <class R> UHC_DEV void qmul(const R *a, const R *b, R *o) {
+    R w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    R x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    R y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    R z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+    o[0] = w; o[1] = x; o[2] = y; o[3] = z;
+}
+template <class R> UHC_DEV void qinv(const R *q, R *o) {  // conj / |q|^2 (uhc/utils/transformation.py:1509)
+    R n = R(1) / (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    o[0] = q[0] * n; o[1] = -q[1] * n; o[2] = -q[2] * n; o[3] = -q[3] * n;
+}
+template <class R> UHC_DEV void q2mat(const R *q, R *m) {  // rotation of the normalised quaternion
+    R n = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    R s = R(2) / n;
+    R xx = s * q[1] * q[1], yy = s * q[2] * q[2], zz = s * q[3] * q[3];
+    R xy = s * q[1] * q[2], xz = s * q[1] * q[3], yz = s * q[2] * q[3];
+    R wx = s * q[0] * q[1], wy = s * q[0] * q[2], wz = s * q[0] * q[3];
+    m[0] = 1 - yy - zz; m[1] = xy - wz; m[2] = xz + wy;
+    m[3] = xy + wz; m[4] = 1 - xx - zz; m[5] = yz - wx;
+    m[6] = xz - wy; m[7] = yz + wx; m[8] = 1 - xx - yy;
+}
+template <class R> UHC_DEV void mtv(const R *m, const R *v, R *o) {  // m^T v
+    R a = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], b = m[1] * v[0] + m[4] * v[1] + m[7] * v[2],
+      c = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+    o[0] = a; o[1] = b; o[2] = c;
+}
+template <class R> UHC_DEV void mv3(const R *m, const R *v, R *o) {
+    R a = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], b = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+      c = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+    o[0] = a; o[1] = b; o[2] = c;
+}
+// rigid spatial inertia (10 params: m, h[3]=m*c, I_O{xx,yy,zz,xy,xz,yz}) times motion vector S=(a,b) -> force (n,f)
+template <class R> UHC_DEV void rigid_mul(const R *I, const R *S, R *F) {
+    const R *h = I + 1, *J = I + 4; const R *a = S, *b = S + 3;
+    R hb[3], ha[3];
+    cross3(h, b, hb); cross3(h, a, ha);
+    F[0] = J[0] * a[0] + J[3] * a[1] + J[4] * a[2] + hb[0];
+    F[1] = J[3] * a[0] + J[1] * a[1] + J[5] * a[2] + hb[1];
+    F[2] = J[4] * a[0] + J[5] * a[1] + J[2] * a[2] + hb[2];
+    F[3] = I[0] * b[0] - ha[0]; F[4] = I[0] * b[1] - ha[1]; F[5] = I[0] * b[2] - ha[2];
+}
+// packed symmetric 6x6 (21: row-major upper triangle) times vector
+UHC_DEV int sym6(int i, int j) { if (i > j) { int t = i; i = j; j = t; } return i * 6 - (i * (i - 1)) / 2 + (j - i); }
+template <class R> UHC_DEV void sym6_mul(const R *K, const R *x, R *y) {
+    for (int i = 0; i < 6; i++) { R s = 0; for (int j = 0; j < 6; j++) s += K[sym6(i, j)] * x[j]; y[i] = s; }
+}
+
+// ------------------------------------------------------------------------------------------------ warp reductions
+#ifndef UHC_EMU
+template <class R> UHC_DEV R warp_sum(R x) { for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o); return x; }
+template <class R> UHC_DEV R warp_max(R x) { for (int o = 16; o; o >>= 1) { R y = __shfl_xor_sync(0xffffffffu, x, o); x = x > y ? x : y; } return x; }
+template <class R> UHC_DEV void warp_argmin(R &x, int &i) {
+    for (int o = 16; o; o >>= 1) { R y = __shfl_xor_sync(0xffffffffu, x, o); int j = __shfl_xor_sync(0xffffffffu, i, o); if (y < x || (y == x && j < i)) { x = y; i = j; } }
+}
+#define WSUM(n) warp_sum(n)
+#define WMAX(n) warp_max(n)
+#define WARGMIN(x, i, ox, oi) { ox = x; oi = i; warp_argmin(ox, oi); }
+#define WBALLOT(n) __ballot_sync(0xffffffffu, (n) != 0)
+#else
+template <class R> static R emu_sum(const R *x) { R s = 0; for (int i = 0; i < 32; i++) s += x[i]; return s; }
+template <class R> static R emu_max(const R *x) { R s = x[0]; for (int i = 1; i < 32; i++) s = x[i] > s ? x[i] : s; return s; }
+#define WSUM(n) emu_sum(n)
+#define WMAX(n) emu_max(n)
+#define WARGMIN(x, i, ox, oi) { ox = x[0]; oi = i[0]; for (int l_ = 1; l_ < 32; l_++) if (x[l_] < ox || (x[l_] == ox && i[l_] < oi)) { ox = x[l_]; oi = i[l_]; } }
+static unsigned emu_ballot(const int *x) { unsigned m = 0; for (int i = 0; i < 32; i++) if (x[i]) m |= 1u << i; return m; }
+#define WBALLOT(n) emu_ballot(n)
+#endif
+UHC_DEV int popc_(unsigned x) { int c = 0; while (x) { x &= x - 1; c++; } return c; }
+
+// ================================================================================================ tree-sparse L^T D L
+// H is stored row-chain: row k holds H[k][anc(k,0..dep k)] at H[madr[k] ..]; after factorisation row k holds the
+// UNSCALED factor row (L[k][t] = H[k][t] * dinv[k]) and dinv[k] = 1 / D_k.  Pivots run from leaves to the root.
+template <class Real>
+UHC_DEV void ldl_factor(const Model<Real> &m, Real *H, Real *dinv, int k_hi, int k_lo) {
+    for (int k = k_hi; k >= k_lo; --k) {
+        const int d = UHC_LDG(m.dep + k);
+        const Real *Hk = H + UHC_LDG(m.madr + k);
+        const Real inv = Real(1) / Hk[d];
+        LANES_BEGIN
+        if (lane == 0) dinv[k] = inv;
+        if (lane < d) {
+            const Real w = Hk[lane] * inv;
+            const short *ra = m.rowadr + k * 32;
+            for (int s = lane; s < d; ++s) H[UHC_LDG(ra + s) + lane] -= Hk[s] * w;
+        }
+        LANES_END
+    }
+}
+// solves H x = b in place (b -> x) with the factor above
+template <class Real>
+UHC_DEV void ldl_solve(const Model<Real> &m, const Real *H, const Real *dinv, Real *b) {
+    for (int k = NV - 1; k >= 1; --k) {  // y = L^-T b : scatter row k onto its ancestors
+        const int d = UHC_LDG(m.dep + k);
+        const Real *Hk = H + UHC_LDG(m.madr + k);
+        const Real bk = b[k] * dinv[k];
+        LANES_BEGIN
+        if (lane < d) b[UHC_LDG(m.colidx + k * 32 + lane)] -= Hk[lane] * bk;
+        LANES_END
+    }
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) b[i] *= dinv[i];
+    LANES_END
+    for (int j = 0; j < NV - 1; ++j) {  // x = L^-1 z : push x[j] to every dof of its subtree
+        const int e = UHC_LDG(m.dof_sub_end + j), dj = UHC_LDG(m.dep + j);
+        const Real xj = b[j];
+        if (e <= j) continue;
+        LANES_BEGIN
+        for (int k = j + 1 + lane; k <= e; k += 32) b[k] -= H[UHC_LDG(m.madr + k) + dj] * dinv[k] * xj;
+        LANES_END
+    }
+}
+
+// ================================================================================================ kinematics + RNE
+// Forward pass over tree levels, lane = body: pose, motion subspaces S (about O = root position), spatial velocity V
+// and velocity-product acceleration A (gravity folded in as a base acceleration), then per-body rigid inertia and the
+// inertial wrench F = I A + V x* (I V).   MuJoCo semantics: SURVEY.md Appendix B (mj_kinematics / mj_comPos / mj_rne).
+template <class Real>
+UHC_DEV void kin_rne_forward(const Model<Real> &m, Work<Real> &w) {
+    for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
+        LANES_BEGIN
+        const int b = lane;
+        if (b < NB && UHC_LDG(m.depth + b) == lvl) {
+            const Real *bf = m.body_f + b * BODYF;
+            Real R[9], pos[3], V[6], A[6];
+            if (b == 0) {
+                Real qn[4] = {w.q[3], w.q[4], w.q[5], w.q[6]};
+                Real n = rsqrt_(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+                for (int i = 0; i < 4; i++) qn[i] *= n;
+                q2mat(qn, R);
+                pos[0] = w.q[0]; pos[1] = w.q[1]; pos[2] = w.q[2];
+                for (int k = 0; k < 3; k++) {  // translation dofs, world axes
+                    for (int i = 0; i < 6; i++) w.S[k][i] = 0;
+                    w.S[k][3 + k] = 1;
+                }
+                for (int k = 0; k < 3; k++) {  // rotation dofs: body-frame axes through O
+                    w.S[3 + k][0] = R[k]; w.S[3 + k][1] = R[3 + k]; w.S[3 + k][2] = R[6 + k];
+                    w.S[3 + k][3] = w.S[3 + k][4] = w.S[3 + k][5] = 0;
+                }
+                Real wl[3] = {w.v[3], w.v[4], w.v[5]}, ww[3], t[3];
+                mv3(R, wl, ww);
+                V[0] = ww[0]; V[1] = ww[1]; V[2] = ww[2]; V[3] = w.v[0]; V[4] = w.v[1]; V[5] = w.v[2];
+                cross3(ww, V + 3, t);  // spatial acceleration of the free body with qacc = 0 is (0, -w x v); minus gravity
+                A[0] = A[1] = A[2] = 0; A[3] = -t[0]; A[4] = -t[1]; A[5] = -t[2] - m.gravz;
+            } else {
+                const int p = UHC_LDG(m.parent + b);
+                const Real *Rp = w.xmat[p];
+                mv3(Rp, bf, pos);
+                for (int i = 0; i < 3; i++) pos[i] += w.xpos[p][i];
+                for (int i = 0; i < 9; i++) R[i] = Rp[i];
+                for (int i = 0; i < 6; i++) { V[i] = w.Vb[p][i]; A[i] = w.Ab[p][i]; }
+                const Real r[3] = {pos[0] - w.q[0], pos[1] - w.q[1], pos[2] - w.q[2]};
+                // three hinges z, y, x, each seen in the frame produced by the previous ones
+                for (int j = 0; j < 3; ++j) {
+                    const int dof = 6 + 3 * (b - 1) + j, col = 2 - j;
+                    Real ax[3] = {R[col], R[3 + col], R[6 + col]}, Sj[6], Sd[6], t[3];
+                    cross3(r, ax, t);
+                    Sj[0] = ax[0]; Sj[1] = ax[1]; Sj[2] = ax[2]; Sj[3] = t[0]; Sj[4] = t[1]; Sj[5] = t[2];
+                    cross3(V, Sj, Sd);              // Sdot = V x_m S = (w x a, w x b + v x a)
+                    cross3(V, Sj + 3, Sd + 3);
+                    cross3(V + 3, Sj, t);
+                    Sd[3] += t[0]; Sd[4] += t[1]; Sd[5] += t[2];
+                    const Real qd = w.v[dof];
+                    for (int i = 0; i < 6; i++) { w.S[dof][i] = Sj[i]; A[i] += Sd[i] * qd; V[i] += Sj[i] * qd; }
+                    Real sn, cs; sincos_(w.q[7 + 3 * (b - 1) + j], &sn, &cs);
+                    // R <- R * Rot(axis col, angle): rotate the two other columns
+                    const int c1 = (col + 1) % 3, c2 = (col + 2) % 3;
+                    for (int i = 0; i < 3; i++) {
+                        const Real u = R[3 * i + c1], v2 = R[3 * i + c2];
+                        R[3 * i + c1] = cs * u + sn * v2;
+                        R[3 * i + c2] = -sn * u + cs * v2;
+                    }
+                }
+            }
+            for (int i = 0; i < 3; i++) w.xpos[b][i] = pos[i];
+            for (int i = 0; i < 9; i++) w.xmat[b][i] = R[i];
+            for (int i = 0; i < 6; i++) { w.Vb[b][i] = V[i]; w.Ab[b][i] = A[i]; }
+            // rigid inertia about O in world axes, inertial wrench
+            Real cl[3], c[3], I[10], T[9];
+            mv3(R, bf + 3, cl);
+            for (int i = 0; i < 3; i++) { w.xipos[b][i] = pos[i] + cl[i]; c[i] = pos[i] + cl[i] - w.q[i]; }
+            const Real ms = bf[6];
+            const Real Il[9] = {bf[7], bf[10], bf[11], bf[10], bf[8], bf[12], bf[11], bf[12], bf[9]};
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) T[3 * i + j] = R[3 * i] * Il[j] + R[3 * i + 1] * Il[3 + j] + R[3 * i + 2] * Il[6 + j];
+            const Real cc = dot3(c, c);
+            Real Iw[6]; const int ii[6] = {0, 1, 2, 0, 0, 1}, jj[6] = {0, 1, 2, 1, 2, 2};
+            for (int e = 0; e < 6; e++) {
+                const int i = ii[e], j = jj[e];
+                Iw[e] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2] + ms * ((i == j ? cc : Real(0)) - c[i] * c[j]);
+            }
+            I[0] = ms; I[1] = ms * c[0]; I[2] = ms * c[1]; I[3] = ms * c[2];
+            for (int e = 0; e < 6; e++) I[4 + e] = Iw[e];
+            for (int e = 0; e < 10; e++) w.Ic[b][e] = I[e];
+            Real IA[6], IV[6], t[3], t2[3];
+            rigid_mul(I, A, IA); rigid_mul(I, V, IV);
+            cross3(V, IV, t); cross3(V + 3, IV + 3, t2);   // V x* F = (w x n + v x f, w x f)
+            IA[0] += t[0] + t2[0]; IA[1] += t[1] + t2[1]; IA[2] += t[2] + t2[2];
+            cross3(V, IV + 3, t);
+            IA[3] += t[0]; IA[4] += t[1]; IA[5] += t[2];
+            for (int i = 0; i < 6; i++) w.Fb[b][i] = IA[i];
+        }
+        LANES_END
+    }
+}
+
+// leaves -> root accumulation of n floats per body (parents gather their children), lane = body
+template <class Real>
+UHC_DEV void tree_gather(const Model<Real> &m, Real *X, int stride, int n) {
+    for (int lvl = MAXLEVEL - 1; lvl >= 0; --lvl) {
+        LANES_BEGIN
+        const int b = lane;
+        if (b < NB && UHC_LDG(m.depth + b) == lvl) {
+            const int c0 = UHC_LDG(m.child_adr + b), c1 = UHC_LDG(m.child_adr + b + 1);
+            for (int ci = c0; ci < c1; ++ci) {
+                const int c = UHC_LDG(m.child + ci);
+                for (int i = 0; i < n; i++) X[b * stride + i] += X[c * stride + i];
+            }
+        }
+        LANES_END
+    }
+}
+// per-body spatial vector  X_b = sum_{i on chain(b)} S_i x_i   (root -> leaves), lane = body
+template <class Real>
+UHC_DEV void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real (*X)[6]) {
+    for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
+        LANES_BEGIN
+        const int b = lane;
+        if (b < NB && UHC_LDG(m.depth + b) == lvl) {
+            Real V[6];
+            int d0, nd;
+            if (b == 0) { for (int i = 0; i < 6; i++) V[i] = 0; d0 = 0; nd = 6; }
+            else { const int p = UHC_LDG(m.parent + b); for (int i = 0; i < 6; i++) V[i] = X[p][i]; d0 = 6 + 3 * (b - 1); nd = 3; }
+            for (int j = 0; j < nd; ++j) { const Real xj = x[d0 + j]; for (int i = 0; i < 6; i++) V[i] += w.S[d0 + j][i] * xj; }
+            for (int i = 0; i < 6; i++) X[b][i] = V[i];
+        }
+        LANES_END
+    }
+}
+// y_i = S_i . Fsub[body(i)]  for all dofs, lane = dof
+template <class Real>
+UHC_DEV void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F)[6], Real *y, Real scale, const Real *add) {
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) {
+        const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
+        y[i] = scale * dot6(w.S[i], F[b]) + (add ? add[i] : Real(0));
+    }
+    LANES_END
+}
+
+// CRBA: composite inertias (in w.Ic, 10 params) -> tree-sparse M (+ armature)
+template <class Real>
+UHC_DEV void crba(const Model<Real> &m, Work<Real> &w) {
+    tree_gather(m, &w.Ic[0][0], 21, 10);
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) {
+        const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
+        rigid_mul(w.Ic[b], w.S[i], w.scr + 6 * i);
+    }
+    LANES_END
+    LANES_BEGIN
+    for (int e = lane; e < NNZ; e += 32) {
+        const int r = UHC_LDG(m.ent_row + e), c = UHC_LDG(m.ent_col + e);
+        Real val = dot6(w.S[c], w.scr + 6 * r);
+        if (r == c) val += UHC_LDG(m.dof_f + 4 * r);
+        w.M[e] = val;
+    }
+    LANES_END
+}
+
+// ================================================================================================ collision
+// Floor plane z = 0 against each body hull (oracle/uhc_oracle.c or_collide states the manifold rule).
+template <class Real>
+UHC_DEV void collide(const Model<Real> &m, Work<Real> &w) {
+    int ncon = 0, upper = 0;
+    for (int b = 0; b < NB; ++b) {
+        w.bcon_adr[b] = ncon;  // uniform value, every lane writes the same (benign)
+        const Real *bf = m.body_f + b * BODYF;
+        const Real *R = w.xmat[b];
+        const Real cz = w.xpos[b][2] + R[6] * bf[14] + R[7] * bf[15] + R[8] * bf[16];
+        if (cz - bf[17] > m.margin || ncon + 4 > MAXCON) continue;
+        const int adr = UHC_LDG(m.hull_adr + b), nvt = UHC_LDG(m.hull_num + b);
+        LVAR(Real, bz); LVAR(int, bi);
+        LANES_BEGIN
+        Real best = Real(1e30); int besti = 1 << 20;
+        for (int i = lane; i < nvt; i += 32) {
+            const Real *vv = m.hull + 3 * (adr + i);
+            const Real z = w.xpos[b][2] + R[6] * UHC_LDG(vv) + R[7] * UHC_LDG(vv + 1) + R[8] * UHC_LDG(vv + 2);
+            if (z < best) { best = z; besti = i; }
+        }
+        LV(bz) = best; LV(bi) = besti;
+        LANES_END
+        Real minz; int mini;
+        WARGMIN(bz, bi, minz, mini);
+        if (minz > m.margin) continue;
+        const int g = adr + mini, n0 = UHC_LDG(m.nbradr + g), nn = UHC_LDG(m.nbradr + g + 1) - n0;
+        LVAR(int, flag);
+        LANES_BEGIN
+        int f = 0;
+        if (lane < nn) {
+            const Real *vv = m.hull + 3 * (adr + UHC_LDG(m.nbr + n0 + lane));
+            const Real z = w.xpos[b][2] + R[6] * UHC_LDG(vv) + R[7] * UHC_LDG(vv + 1) + R[8] * UHC_LDG(vv + 2);
+            f = z <= m.margin;
+        }
+        LV(flag) = f;
+        LANES_END
+        unsigned mask = WBALLOT(flag);
+        int cand[4]; int nc = 0; cand[nc++] = mini;
+        while (mask && nc < 4) { int l = 0; while (!((mask >> l) & 1u)) l++; mask &= mask - 1; cand[nc++] = UHC_LDG(m.nbr + n0 + l); }
+        LANES_BEGIN
+        if (lane < nc) {
+            const Real *vv = m.hull + 3 * (adr + cand[lane]);
+            const Real v0 = UHC_LDG(vv), v1 = UHC_LDG(vv + 1), v2 = UHC_LDG(vv + 2);
+            const Real px = w.xpos[b][0] + R[0] * v0 + R[1] * v1 + R[2] * v2;
+            const Real py = w.xpos[b][1] + R[3] * v0 + R[4] * v1 + R[5] * v2;
+            const Real pz = w.xpos[b][2] + R[6] * v0 + R[7] * v1 + R[8] * v2;
+            const int c = ncon + lane;
+            w.cbody[c] = b; w.cdist[c] = pz;
+            w.cr[c][0] = px - w.q[0]; w.cr[c][1] = py - w.q[1]; w.cr[c][2] = Real(0.5) * pz - w.q[2];
+        }
+        LANES_END
+        ncon += nc;
+        if (b >= UPPER_BODY0) upper = 1;
+    }
+    w.bcon_adr[NB] = ncon;
+    w.ncon = ncon; w.upper_contact = upper;
+#ifndef UHC_EMU
+    __syncwarp();
+#endif
+}
+
+// pyramid edge directions d_e = n +- mu t  for n = +z, t1 = +y, t2 = -x
+template <class Real> UHC_DEV void edge_dir(int e, Real mu, Real *d) {
+    d[0] = e == 2 ? -mu : (e == 3 ? mu : Real(0));
+    d[1] = e == 0 ? mu : (e == 1 ? -mu : Real(0));
+    d[2] = 1;
+}
+
+// per-contact soft-constraint parameters (MuJoCo solref/solimp semantics), lane = contact
+template <class Real>
+UHC_DEV void constraint_setup(const Model<Real> &m, Work<Real> &w) {
+    const Real kk = Real(1) / (m.simp1 * m.simp1 * m.solref0 * m.solref0 * m.solref1 * m.solref1), bb = Real(2) / (m.simp1 * m.solref0);
+    LANES_BEGIN
+    for (int c = lane; c < w.ncon; c += 32) {
+        const int b = w.cbody[c];
+        const Real pos = w.cdist[c] - m.margin;
+        Real x = abs_(pos) / m.simp2; if (x > 1) x = 1;
+        Real y;
+        if (x < m.simp3) y = pow_(x / m.simp3, m.simp4) * m.simp3;
+        else y = 1 - pow_((1 - x) / (1 - m.simp3), m.simp4) * (1 - m.simp3);
+        const Real imp = m.simp0 + y * (m.simp1 - m.simp0);
+        Real R0 = (1 - imp) * UHC_LDG(m.body_f + b * BODYF + 13) * (1 + m.mu * m.mu) / imp;
+        if (R0 < Real(1e-15)) R0 = Real(1e-15);
+        w.cD[c] = Real(1) / (2 * m.mu * m.mu * R0);
+        Real u[3], t[3];
+        cross3(w.Vb[b], w.cr[c], t);
+        for (int i = 0; i < 3; i++) u[i] = w.Vb[b][3 + i] + t[i];
+        for (int e = 0; e < 4; e++) { Real d[3]; edge_dir(e, m.mu, d); w.caref[c][e] = -bb * dot3(d, u) - kk * imp * pos; }
+    }
+    LANES_END
+}
+
+// rows: out[c][e] = d_e . (point velocity of body spatial vector X at contact c), lane = contact
+template <class Real>
+UHC_DEV void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)[6], Real (*out)[4], const Real (*sub)[4]) {
+    LANES_BEGIN
+    for (int c = lane; c < w.ncon; c += 32) {
+        const int b = w.cbody[c]; Real u[3], t[3];
+        cross3(X[b], w.cr[c], t);
+        for (int i = 0; i < 3; i++) u[i] = X[b][3 + i] + t[i];
+        for (int e = 0; e < 4; e++) { Real d[3]; edge_dir(e, m.mu, d); out[c][e] = dot3(d, u) - (sub ? sub[c][e] : Real(0)); }
+    }
+    LANES_END
+}
+// body wrenches from per-row multipliers lam[c][e] (force on the body along d_e at the contact point), then subtree sums
+template <class Real, class F>
+UHC_DEV void contact_force(const Model<Real> &m, Work<Real> &w, F lam, Real (*Fo)[6]) {
+    LANES_BEGIN
+    const int b = lane;
+    if (b < NB) {
+        Real acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
+            Real f[3] = {0, 0, 0}, t[3];
+            for (int e = 0; e < 4; e++) { Real d[3]; edge_dir(e, m.mu, d); const Real l = lam(c, e); f[0] += l * d[0]; f[1] += l * d[1]; f[2] += l * d[2]; }
+            cross3(w.cr[c], f, t);
+            acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2]; acc[3] += f[0]; acc[4] += f[1]; acc[5] += f[2];
+        }
+        for (int i = 0; i < 6; i++) Fo[b][i] = acc[i];
+    }
+    LANES_END
+    tree_gather(m, &Fo[0][0], 6, 6);
+}
+
+// ================================================================================================ constraint solve
+// min_a 1/2 (a-a_s)^T M (a-a_s) + sum_rows 1/2 D min(0, J a - aref)^2 ; primal Newton, Hessian = M + J^T D_act J built as a
+// CRBA over contact-augmented composites, factorised tree-sparse (only the lower-body rows when no arm/head contact).
+template <class Real>
+UHC_DEV int newton_solve(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w) {
+    // cost of the two start candidates (warm start vs unconstrained)
+    Real cost[2];
+    for (int pass = 0; pass < 2; ++pass) {
+        const Real *x = pass ? w.as_ : w.aw;
+        tree_vel(m, w, x, w.Ab);
+        contact_rows(m, w, w.Ab, w.cjp, w.caref);
+        LVAR(Real, part);
+        if (pass == 0) {  // M aw via body wrenches: Ma = sum_b J_b^T I_b (J_b aw) ; composite-free O(n) pass
+            LANES_BEGIN
+            const int b = lane;
+            if (b < NB) {
+                // rigid inertia of body b alone = composite(b) - sum composite(children)
+                Real I[10];
+                for (int e = 0; e < 10; e++) I[e] = w.Ic[b][e];
+                for (int ci = UHC_LDG(m.child_adr + b); ci < UHC_LDG(m.child_adr + b + 1); ++ci) { const int c = UHC_LDG(m.child + ci); for (int e = 0; e < 10; e++) I[e] -= w.Ic[c][e]; }
+                rigid_mul(I, w.Ab[b], w.Fb[b]);
+            }
+            LANES_END
+            tree_gather(m, &w.Fb[0][0], 6, 6);
+            LANES_BEGIN
+            for (int i = lane; i < NV; i += 32) {
+                const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
+                w.Ma[i] = dot6(w.S[i], w.Fb[b]) + UHC_LDG(m.dof_f + 4 * i) * x[i];
+            }
+            LANES_END
+        }
+        LANES_BEGIN
+        Real s = 0;
+        if (pass == 0) for (int i = lane; i < NV; i += 32) s += Real(0.5) * (w.aw[i] - w.as_[i]) * (w.Ma[i] - w.fs[i]);
+        for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) { const Real r = w.cjp[c][e]; if (r < 0) s += Real(0.5) * w.cD[c] * r * r; }
+        LV(part) = s;
+        LANES_END
+        cost[pass] = WSUM(part);
+        if (pass == 0) {  // keep the warm-start residuals in cres
+            LANES_BEGIN
+            for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] = w.cjp[c][e];
+            LANES_END
+        }
+    }
+    const bool use_warm = cost[0] < cost[1];
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) { w.a[i] = use_warm ? w.aw[i] : w.as_[i]; if (!use_warm) w.Ma[i] = w.fs[i]; }
+    if (!use_warm) for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] = w.cjp[c][e];
+    LANES_END
+
+    Real scale = 0;  // sum of diag(M): gradient tolerance scale
+    {
+        LVAR(Real, part);
+        LANES_BEGIN
+        Real s = 0;
+        for (int i = lane; i < NV; i += 32) s += w.M[UHC_LDG(m.madr + i) + UHC_LDG(m.dep + i)];
+        LV(part) = s;
+        LANES_END
+        scale = WSUM(part);
+    }
+    int it = 0;
+    for (; it < cfg.newton_max_iter; ++it) {
+        // gradient g = M a - f_s + J^T D r_-
+        contact_force(m, w, [&](int c, int e) { const Real r = w.cres[c][e]; return r < 0 ? w.cD[c] * r : Real(0); }, w.Fb);
+        LVAR(Real, part);
+        LANES_BEGIN
+        Real s = 0;
+        for (int i = lane; i < NV; i += 32) {
+            const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
+            const Real gi = w.Ma[i] - w.fs[i] + dot6(w.S[i], w.Fb[b]);
+            w.g[i] = gi; w.p[i] = -gi; s += gi * gi;
+        }
+        LV(part) = s;
+        LANES_END
+        const Real gn = WSUM(part);
+        if (!(gn > cfg.newton_tol * cfg.newton_tol * scale * scale)) break;
+        // contact matrices K_b = sum_c X^T W X (own contacts), composites by gathering
+        LANES_BEGIN
+        const int b = lane;
+        if (b < NB) {
+            Real K[21];
+            for (int e = 0; e < 21; e++) K[e] = 0;
+            for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
+                Real W[6] = {0, 0, 0, 0, 0, 0};  // xx yy zz xy xz yz
+                for (int e = 0; e < 4; e++) if (w.cres[c][e] < 0) {
+                    Real d[3]; edge_dir(e, m.mu, d); const Real D = w.cD[c];
+                    W[0] += D * d[0] * d[0]; W[1] += D * d[1] * d[1]; W[2] += D * d[2] * d[2];
+                    W[3] += D * d[0] * d[1]; W[4] += D * d[0] * d[2]; W[5] += D * d[1] * d[2];
+                }
+                const Real Wm[9] = {W[0], W[3], W[4], W[3], W[1], W[5], W[4], W[5], W[2]};
+                const Real *r = w.cr[c];
+                // u = v + w x r = G w + v, G = -[r]x ; X = [G 1]
+                const Real G[9] = {0, r[2], -r[1], -r[2], 0, r[0], r[1], -r[0], 0};
+                Real WG[9], GtWG[9];
+                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) WG[3 * i + j] = Wm[3 * i] * G[j] + Wm[3 * i + 1] * G[3 + j] + Wm[3 * i + 2] * G[6 + j];
+                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) GtWG[3 * i + j] = G[i] * WG[j] + G[3 + i] * WG[3 + j] + G[6 + i] * WG[6 + j];
+                for (int i = 0; i < 3; i++) for (int j = i; j < 3; j++) { K[sym6(i, j)] += GtWG[3 * i + j]; K[sym6(3 + i, 3 + j)] += Wm[3 * i + j]; }
+                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) K[sym6(i, 3 + j)] += WG[3 * j + i];  // (G^T W)[i][j] = WG[j][i]
+            }
+            for (int e = 0; e < 21; e++) w.Ic[b][e] = K[e];
+        }
+        LANES_END
+        tree_gather(m, &w.Ic[0][0], 21, 21);
+        const int nrow = w.upper_contact ? NV : NLOW, nent = w.upper_contact ? NNZ : NNZ_LOW;
+        LANES_BEGIN
+        for (int i = lane; i < nrow; i += 32) { const int b = i < 6 ? 0 : 1 + (i - 6) / 3; sym6_mul(w.Ic[b], w.S[i], w.scr + 6 * i); }
+        LANES_END
+        LANES_BEGIN
+        for (int e = lane; e < nent; e += 32) {
+            const int r = UHC_LDG(m.ent_row + e), c = UHC_LDG(m.ent_col + e);
+            w.H[e] = (w.upper_contact ? w.M[e] : w.Mt[e]) + dot6(w.S[c], w.scr + 6 * r);
+        }
+        LANES_END
+        ldl_factor(m, w.H, w.dinv, nrow - 1, 1);
+        LANES_BEGIN
+        if (lane == 0) w.dinv[0] = Real(1) / w.H[0];
+        LANES_END
+        ldl_solve(m, w.H, w.dinv, w.p);
+        // J p, M p = -g - J^T D_act (J p)
+        tree_vel(m, w, w.p, w.Ab);
+        contact_rows(m, w, w.Ab, w.cjp, (const Real (*)[4]) nullptr);
+        contact_force(m, w, [&](int c, int e) { return w.cres[c][e] < 0 ? w.cD[c] * w.cjp[c][e] : Real(0); }, w.Fb);
+        LVAR(Real, pa); LVAR(Real, pb);
+        LANES_BEGIN
+        Real sA = 0, sB = 0;
+        for (int i = lane; i < NV; i += 32) {
+            const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
+            const Real mp = -w.g[i] - dot6(w.S[i], w.Fb[b]);
+            w.Mp[i] = mp; sA += (w.Ma[i] - w.fs[i]) * w.p[i]; sB += mp * w.p[i];
+        }
+        LV(pa) = sA; LV(pb) = sB;
+        LANES_END
+        const Real A0 = WSUM(pa), B0 = WSUM(pb);
+        // 1-D safeguarded Newton on f'(al) = A0 + al B0 + sum_rows D (r + al jp)_- jp   (piecewise linear, increasing)
+        Real lo = 0, hi = -1, al = 1;
+        for (int ls = 0; ls < 12; ++ls) {
+            LVAR(Real, d1); LVAR(Real, d2);
+            LANES_BEGIN
+            Real s1 = 0, s2 = 0;
+            for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) {
+                const Real r = w.cres[c][e] + al * w.cjp[c][e];
+                if (r < 0) { s1 += w.cD[c] * r * w.cjp[c][e]; s2 += w.cD[c] * w.cjp[c][e] * w.cjp[c][e]; }
+            }
+            LV(d1) = s1; LV(d2) = s2;
+            LANES_END
+            const Real f1 = A0 + al * B0 + WSUM(d1), f2 = B0 + WSUM(d2);
+            if (f1 > 0) hi = al; else lo = al;
+            if (abs_(f1) <= Real(1e-6) * abs_(A0) + Real(1e-30)) break;
+            Real nx = al - f1 / f2;
+            if (!(nx > lo) || (hi > 0 && !(nx < hi))) nx = hi > 0 ? Real(0.5) * (lo + hi) : 2 * al;
+            if (nx == al) break;
+            al = nx;
+        }
+        LANES_BEGIN
+        for (int i = lane; i < NV; i += 32) { w.a[i] += al * w.p[i]; w.Ma[i] += al * w.Mp[i]; }
+        for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] += al * w.cjp[c][e];
+        LANES_END
+    }
+    return it;
+}
+
+// ================================================================================================ one physics substep
+// mj_forward (position, velocity, actuation, acceleration, constraint) at the current (q, v), then semi-implicit Euler.
+// `tau` holds the 69 joint torques, fapp the 6 root residual forces.  Leaves M, C, xpos/xmat/xipos of THIS (pre-integration)
+// configuration in the work set -- the staleness MuJoCo exposes to the Python side (SURVEY.md section 7 "stale dynamics").
+template <class Real>
+UHC_DEV int forward_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const Real *fapp, bool have_tau) {
+    kin_rne_forward(m, w);
+    tree_gather(m, &w.Fb[0][0], 6, 6);
+    project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
+    crba(m, w);
+    collide(m, w);
+    // smooth acceleration a_s = M^-1 (tau + f_applied - C)
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) {
+        const Real f = (i < 6 ? fapp[i] : (have_tau ? w.tau[i - 6] : Real(0))) - w.C[i];
+        w.fs[i] = f; w.as_[i] = f;
+    }
+    for (int e = lane; e < NNZ; e += 32) w.H[e] = w.M[e];
+    LANES_END
+    ldl_factor(m, w.H, w.dinv, NV - 1, NLOW);
+    LANES_BEGIN
+    for (int e = lane; e < NNZ_LOW; e += 32) w.Mt[e] = w.H[e];  // lower rows after the arm/head Schur complement
+    LANES_END
+    ldl_factor(m, w.H, w.dinv, NLOW - 1, 1);
+    LANES_BEGIN
+    if (lane == 0) w.dinv[0] = Real(1) / w.H[0];
+    LANES_END
+    ldl_solve(m, w.H, w.dinv, w.as_);
+    int iters = 0;
+    if (w.ncon > 0) {
+        constraint_setup(m, w);
+        iters = newton_solve(m, cfg, w);
+    } else {
+        LANES_BEGIN
+        for (int i = lane; i < NV; i += 32) w.a[i] = w.as_[i];
+        LANES_END
+    }
+    return iters;
+}
+
+template <class Real>
+UHC_DEV void integrate(const Model<Real> &m, Work<Real> &w) {
+    const Real dt = m.dt;
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) { const Real vn = w.v[i] + dt * w.a[i]; w.v[i] = vn; w.aw[i] = w.a[i]; if (i >= 6) w.q[i + 1] += dt * vn; }
+    LANES_END
+    LANES_BEGIN
+    if (lane < 3) w.q[lane] += dt * w.v[lane];
+    if (lane == 3) {
+        const Real wx = w.v[3], wy = w.v[4], wz = w.v[5], n = sqrt(wx * wx + wy * wy + wz * wz), ang = n * dt;
+        Real dq[4] = {1, 0, 0, 0}, qn[4], qo[4] = {w.q[3], w.q[4], w.q[5], w.q[6]};
+        if (ang > Real(1e-30)) { Real sn, cs; sincos_(Real(0.5) * ang, &sn, &cs); const Real s = sn / n; dq[0] = cs; dq[1] = wx * s; dq[2] = wy * s; dq[3] = wz * s; }
+        qmul(qo, dq, qn);
+        const Real nn = rsqrt_(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+        for (int i = 0; i < 4; i++) w.q[3 + i] = qn[i] * nn;
+    }
+    LANES_END
+}
+
+// ================================================================================================ task layer
+template <class Real> UHC_DEV void heading_q(const Real *q, Real *hq) {  // uhc/utils/math_utils.py:134-139
+    const Real n = rsqrt_(q[0] * q[0] + q[3] * q[3]);
+    hq[0] = q[0] * n; hq[1] = 0; hq[2] = 0; hq[3] = q[3] * n;
+}
+template <class Real> UHC_DEV Real heading(const Real *q) {  // uhc/utils/math_utils.py:176-183
+    Real w = q[0], z = q[3]; if (z < 0) { w = -w; z = -z; }
+    return 2 * acos_(clamp_(w * rsqrt_(w * w + z * z), Real(-1), Real(1)));
+}
+template <class Real> UHC_DEV void remove_base_rot(const EnvCfg<Real> &cfg, const Real *q, Real *o) {  // humanoid_im.py:263
+    Real bi[4]; qinv(cfg.base_rot, bi); qmul(q, bi, o);
+}
+template <class Real> UHC_DEV void euler_zyx_quat(Real e0, Real e1, Real e2, Real *q) {  // quaternion_from_euler(.., "rzyx")
+    Real s0, c0, s1, c1, s2, c2;
+    sincos_(e0 * Real(0.5), &s0, &c0); sincos_(e1 * Real(0.5), &s1, &c1); sincos_(e2 * Real(0.5), &s2, &c2);
+    const Real qz[4] = {c0, 0, 0, s0}, qy[4] = {c1, 0, s1, 0}, qx[4] = {c2, s2, 0, 0}; Real t[4];
+    qmul(qz, qy, t); qmul(t, qx, q);
+}
+constexpr double PI_D = 3.14159265358979323846;
+
+// stable PD torque for substep `it` (humanoid_im.py:1033-1076 + :1014-1031): uses the M, C currently in the work set
+// (= previous forward pass) with the current q, v; leaves the clipped torques in w.tau (:1160).
+template <class Real>
+UHC_DEV void pd_torque(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const Real *target, int it) {
+    const Real dt = m.dt;
+    Real sp = 1, sd = 1;
+    if (cfg.meta_pd) { sp = clamp_(w.act[NU + 6 + it] + 1, Real(0), Real(10)); sd = clamp_(w.act[NU + 6 + it + NSUB] + 1, Real(0), Real(10)); }
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) {
+        Real rhs = -w.C[i];
+        if (i >= 6) {
+            const int j = i - 6; const Real qj = w.q[7 + j];
+            Real base = target[j];
+            while (base - qj > Real(PI_D)) base -= Real(2 * PI_D);
+            while (base - qj < -Real(PI_D)) base += Real(2 * PI_D);
+            const Real kp = UHC_LDG(m.dof_f + 4 * i + 1) * sp, kd = UHC_LDG(m.dof_f + 4 * i + 2) * sd;
+            const Real err = qj + w.v[i] * dt - (base + w.act[j]);
+            rhs += -kp * err - kd * w.v[i];
+            w.g[i] = err;  // stash
+        }
+        w.p[i] = rhs;
+    }
+    for (int e = lane; e < NNZ; e += 32) {
+        const int r = UHC_LDG(m.ent_row + e);
+        Real val = w.M[e];
+        if (r >= 6 && r == UHC_LDG(m.ent_col + e)) val += UHC_LDG(m.dof_f + 4 * r + 2) * sd * dt;
+        w.H[e] = val;
+    }
+    LANES_END
+    ldl_factor(m, w.H, w.dinv, NV - 1, 1);
+    LANES_BEGIN
+    if (lane == 0) w.dinv[0] = Real(1) / w.H[0];
+    LANES_END
+    ldl_solve(m, w.H, w.dinv, w.p);
+    LANES_BEGIN
+    for (int i = 6 + lane; i < NV; i += 32) {
+        const Real kp = UHC_LDG(m.dof_f + 4 * i + 1) * sp, kd = UHC_LDG(m.dof_f + 4 * i + 2) * sd, lim = UHC_LDG(m.dof_f + 4 * i + 3);
+        const Real t = -kp * w.g[i] - kd * (w.v[i] + w.p[i] * dt);
+        w.tau[i - 6] = clamp_(t, -lim, lim);
+    }
+    LANES_END
+}
+// implicit residual force: humanoid_im.py:1136-1143 (recomputed every substep from the current root quaternion)
+template <class Real>
+UHC_DEV void rfc_implicit(const EnvCfg<Real> &cfg, const Work<Real> &w, Real *fapp) {
+    Real crq[4], hq[4], R[9], vf[6], t[3];
+    for (int i = 0; i < 6; i++) vf[i] = w.act[NU + i] * cfg.rfc_scale * cfg.rfc_rate;
+    remove_base_rot(cfg, w.q + 3, crq); heading_q(crq, hq); q2mat(hq, R); mv3(R, vf, t);
+    vf[0] = t[0]; vf[1] = t[1]; vf[2] = t[2];
+    for (int i = 0; i < 6; i++) fapp[i] = clamp_(vf[i], -cfg.rfc_lim, cfg.rfc_lim);
+}
+
+// body quaternions from qpos (humanoid_im.py:925-947), lane = body
+template <class Real>
+UHC_DEV void body_quat(const Work<Real> &w, Real *out) {
+    LANES_BEGIN
+    const int b = lane;
+    if (b == 0) for (int i = 0; i < 4; i++) out[i] = w.q[3 + i];
+    else if (b < NB) euler_zyx_quat(w.q[7 + 3 * (b - 1)], w.q[8 + 3 * (b - 1)], w.q[9 + 3 * (b - 1)], out + 4 * b);
+    LANES_END
+}
+// world body quaternions by composing along each body's own chain (no cross-lane dependency), lane = body.
+// Matches the pose the last forward pass used (xquat is only consumed by the observation).
+template <class Real>
+UHC_DEV void world_quat(const Model<Real> &m, const Real *qfk, Work<Real> &w) {
+    LANES_BEGIN
+    const int b = lane;
+    if (b < NB) {
+        int chain[MAXLEVEL + 1], n = 0;
+        for (int a = b; a > 0; a = UHC_LDG(m.parent + a)) chain[n++] = a;
+        Real q[4] = {qfk[3], qfk[4], qfk[5], qfk[6]};
+        const Real nn = rsqrt_(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        for (int i = 0; i < 4; i++) q[i] *= nn;
+        for (int k = n - 1; k >= 0; --k) {
+            const int a = chain[k]; Real ql[4], t[4];
+            euler_zyx_quat(qfk[7 + 3 * (a - 1)], qfk[8 + 3 * (a - 1)], qfk[9 + 3 * (a - 1)], ql);
+            qmul(q, ql, t);
+            const Real n2 = rsqrt_(t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3]);
+            for (int i = 0; i < 4; i++) q[i] = t[i] * n2;
+        }
+        for (int i = 0; i < 4; i++) w.xquat[b][i] = q[i];
+    }
+    LANES_END
+}
+
+// observation v2 (humanoid_im.py:419-503, obs_coord "root"); ex1 = expert frame at cur_t + 1
+template <class Real, class OutT>
+UHC_DEV void obs_v2(const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *ex1, const Real *shape_obs, OutT *obs) {
+    Real crq[4], hq[4], hqi[4], trq[4], dh[4], ci[4], dq[4], Rq[9], Rc[9];
+    remove_base_rot(cfg, w.q + 3, crq); heading_q(crq, hq); qinv(hq, hqi);
+    remove_base_rot(cfg, ex1 + EX_QPOS + 3, trq);
+    qmul(hqi, crq, dh); qinv(crq, ci); qmul(trq, ci, dq);
+    q2mat(w.q + 3, Rq); q2mat(crq, Rc);
+    Real rel_h = heading(trq) - heading(crq);
+    if (rel_h > Real(PI_D)) rel_h -= Real(2 * PI_D);
+    if (rel_h < -Real(PI_D)) rel_h += Real(2 * PI_D);
+    LANES_BEGIN
+    if (lane < 4) obs[lane] = (OutT)hq[lane];
+    for (int i = lane; i < 74; i += 32) {
+        const Real tq = ex1[EX_QPOS + 2 + i];
+        Real cur, df;
+        if (i == 0) { cur = w.q[2]; df = tq - cur; }
+        else if (i < 5) { cur = dh[i - 1]; df = dq[i - 1]; }
+        else { cur = w.q[2 + i]; df = tq - cur; }
+        obs[4 + i] = (OutT)tq; obs[78 + i] = (OutT)cur; obs[152 + i] = (OutT)df;
+    }
+    if (lane == 0) {
+        Real t[3], t2[3];
+        mtv(Rq, w.v, t); mtv(Rc, t, t2);                                   // rotated twice (:425, :451)
+        obs[226] = (OutT)t2[0]; obs[227] = (OutT)t2[1]; obs[228] = (OutT)t2[2];
+        obs[301] = (OutT)rel_h;
+        const Real rp[3] = {trq[0] - w.q[0], trq[1] - w.q[1], trq[2] - w.q[2]};  // the kept bug (:466)
+        mtv(Rc, rp, t);
+        obs[302] = (OutT)t[0]; obs[303] = (OutT)t[1];
+    }
+    for (int i = 3 + lane; i < NV; i += 32) obs[226 + i] = (OutT)w.v[i];
+    if (lane < NB) {
+        const int b = lane; Real r[3], t[3];
+        for (int k = 0; k < 3; k++) r[k] = w.xpos[b][k] - w.q[k];
+        mtv(Rc, r, t);
+        for (int k = 0; k < 3; k++) obs[304 + 24 * k + b] = (OutT)t[k];
+        for (int k = 0; k < 3; k++) r[k] = ex1[EX_WBPOS + 3 * b + k] - w.xpos[b][k];
+        mtv(Rc, r, t);
+        for (int k = 0; k < 3; k++) obs[376 + 24 * k + b] = (OutT)t[k];
+        const bool use_t = (w.xquat[0][0] == 0);
+        const Real *cq = use_t ? ex1 + EX_WBQUAT + 4 * b : w.xquat[b];
+        Real o1[4], iq[4], o2[4];
+        qmul(hqi, cq, o1);
+        const Real nn = rsqrt_(cq[0] * cq[0] + cq[1] * cq[1] + cq[2] * cq[2] + cq[3] * cq[3]);  // inverse_batch: conj / |q|
+        iq[0] = cq[0] * nn; iq[1] = -cq[1] * nn; iq[2] = -cq[2] * nn; iq[3] = -cq[3] * nn;
+        qmul(iq, ex1 + EX_WBQUAT + 4 * b, o2);
+        for (int k = 0; k < 4; k++) { obs[448 + 4 * b + k] = (OutT)o1[k]; obs[544 + 4 * b + k] = (OutT)o2[k]; }
+    }
+    if (lane < 17) obs[640 + lane] = (OutT)shape_obs[lane];
+    LANES_END
+}
+
+template <class Real> UHC_DEV void rot_from_quat(const Real *q, Real *rv) {  // transformation.py:362-372
+    if (abs_(1 - q[0]) < Real(1e-6) || abs_(1 + q[0]) < Real(1e-6)) { rv[0] = rv[1] = rv[2] = 0; return; }
+    const Real ang = 2 * acos_(clamp_(q[0], Real(-1), Real(1)));
+    Real sn, cs; sincos_(ang * Real(0.5), &sn, &cs);
+    const Real ax[3] = {q[1] / sn, q[2] / sn, q[3] / sn};
+    const Real n = rsqrt_(dot3(ax, ax)) * ang;
+    rv[0] = ax[0] * n; rv[1] = ax[1] * n; rv[2] = ax[2] * n;
+}
+
+// termination metric (humanoid_im.py:1408-1415) and world_rfc_implicit reward (reward_function.py:12-88);
+// ext = expert frame at the NEW cur_t; bquat/pbquat = current / previous body quats
+template <class Real>
+UHC_DEV void diff_and_reward(const Model<Real> &m, const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *ext, const Real *bquat,
+                             const Real *pbquat, Real *body_diff, Real *reward, Real *cinfo) {
+    LVAR(Real, s_bd); LVAR(Real, s_n); LVAR(Real, s_pose); LVAR(Real, s_vel); LVAR(Real, s_ee);
+    const Real dtc = m.dt * NSUB;
+    LANES_BEGIN
+    Real bd = 0, nn = 0, pose = 0, vel = 0, ee = 0;
+    if (lane < NB) {
+        const int b = lane; const Real dw = UHC_LDG(m.body_f + b * BODYF + 18);
+        if (dw != 0) { Real dx[3]; for (int k = 0; k < 3; k++) dx[k] = (w.xpos[b][k] - ext[EX_WBPOS + 3 * b + k]) * dw; bd = sqrt(dot3(dx, dx)); nn = 1; }
+        Real iq[4], dq[4], rv[3];
+        qinv(ext + EX_BQUAT + 4 * b, iq); qmul(bquat + 4 * b, iq, dq);
+        const Real a = acos_(clamp_(dq[0], Real(-1), Real(1))) * (b == 0 ? Real(1) : dw);
+        pose = a * a;
+        qinv(pbquat + 4 * b, iq); qmul(bquat + 4 * b, iq, dq); rot_from_quat(dq, rv);
+        for (int k = 0; k < 3; k++) { const Real dv = (rv[k] / dtc - ext[EX_BANGVEL + 3 * b + k]) * dw; vel += dv * dv; }
+    }
+    if (lane < 5) { const int eb = UHC_LDG(m.ee + lane); for (int k = 0; k < 3; k++) { const Real x = w.xpos[eb][k] - ext[EX_EE + 3 * lane + k]; ee += x * x; } }
+    LV(s_bd) = bd; LV(s_n) = nn; LV(s_pose) = pose; LV(s_vel) = vel; LV(s_ee) = ee;
+    LANES_END
+    const Real bdsum = WSUM(s_bd), nsum = WSUM(s_n), pose2 = WSUM(s_pose), vel2 = WSUM(s_vel), ee2 = WSUM(s_ee);
+    *body_diff = bdsum / nsum;
+    Real com2 = 0, vf2 = 0;
+    for (int k = 0; k < 3; k++) { const Real x = w.xipos[0][k] - ext[EX_COM + k]; com2 += x * x; }
+    for (int i = 0; i < 6; i++) vf2 += w.act[NU + i] * w.act[NU + i];
+    cinfo[0] = exp_(-cfg.k[0] * pose2); cinfo[1] = exp_(-cfg.k[1] * vel2); cinfo[2] = exp_(-cfg.k[2] * ee2);
+    cinfo[3] = exp_(-cfg.k[3] * com2); cinfo[4] = exp_(-cfg.k[4] * vf2);
+    Real r = 0, ws = 0;
+    for (int i = 0; i < 5; i++) { r += cfg.w[i] * cinfo[i]; ws += cfg.w[i]; }
+    *reward = r / ws;
+}
+
+}  // namespace uhc

@@ -1,0 +1,154 @@
+"""Host-side model tables for the batched engine.
+
+Loads the compiled humanoid (uhc_b200/assets/smpl_neutral_model.npz, produced by tools/compile_model.py from the
+reference's humanoid_smpl_neutral_mesh.xml + STL hulls) and derives the topology tables the kernels index with:
+depth-first dof numbering (root 6 dofs, then 3 hinges z,y,x per body), the tree-sparse row-chain layout of the joint-space
+inertia matrix (row k stores M[k][anc(k,0..dep k)]), children lists, subtree ranges.
+Mirrors what SMPLConverter exposes to the reference env (uhc/smpllib/smpl_mujoco.py:259-281): kp/kd/torque-limit/diff-weight.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ASSET = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets", "smpl_neutral_model.npz")
+NB, NQ, NV, NU = 24, 76, 75, 69
+BODYF = 20
+
+
+class UhcModelHost(C.Structure):
+    """C mirror: include/uhc_b200.h `UhcModelHost`."""
+    _fields_ = [("nvert", C.c_int), ("nnbr", C.c_int),
+                ("body_f", C.POINTER(C.c_double)), ("dof_f", C.POINTER(C.c_double)), ("hull", C.POINTER(C.c_double)),
+                ("hull_adr", C.POINTER(C.c_int)), ("hull_num", C.POINTER(C.c_int)), ("nbr", C.POINTER(C.c_int)),
+                ("nbradr", C.POINTER(C.c_int)), ("parent", C.POINTER(C.c_int)), ("depth", C.POINTER(C.c_int)),
+                ("child_adr", C.POINTER(C.c_int)), ("child", C.POINTER(C.c_int)), ("body_sub_end", C.POINTER(C.c_int)),
+                ("dep", C.POINTER(C.c_int)), ("madr", C.POINTER(C.c_int)), ("dof_sub_end", C.POINTER(C.c_int)),
+                ("dof_body", C.POINTER(C.c_int)), ("rowadr", C.POINTER(C.c_short)), ("colidx", C.POINTER(C.c_ubyte)),
+                ("ent_row", C.POINTER(C.c_ubyte)), ("ent_col", C.POINTER(C.c_ubyte)), ("ee", C.POINTER(C.c_int)),
+                ("dt", C.c_double), ("margin", C.c_double), ("mu", C.c_double), ("solref", C.c_double * 2),
+                ("solimp", C.c_double * 5), ("gravz", C.c_double)]
+
+
+class HumanoidModel:
+    def __init__(self, npz=ASSET, scale=None):
+        z = np.load(npz)
+        self.z = {k: z[k] for k in z.files}
+        self.body_names = [str(n) for n in z["body_names"]]
+        self.parent = z["parent"].astype(np.int32)
+        offset, ipos, mass, inertia = (z[k].astype(np.float64).copy() for k in ("body_offset", "body_ipos", "body_mass", "body_inertia"))
+        hull = z["hull_vert"].astype(np.float64).copy()
+        invw = z["body_invweight0"][:, 0].astype(np.float64).copy()
+        self.hull_adr, self.hull_num = z["hull_vadr"].astype(np.int32), z["hull_vnum"].astype(np.int32)
+        if scale is not None:  # synthetic body-shape variant: per-body isotropic limb scale
+            s = np.asarray(scale, dtype=np.float64)
+            offset[1:] *= s[self.parent[1:], None]   # bone offsets live in the parent's frame
+            ipos *= s[:, None]
+            mass *= s ** 3
+            inertia *= (s ** 5)[:, None, None]
+            for b in range(NB):
+                hull[self.hull_adr[b]:self.hull_adr[b] + self.hull_num[b]] *= s[b]
+            invw = invw / s ** 3
+        self.offset, self.ipos, self.mass, self.inertia, self.hull, self.invw = offset, ipos, mass, inertia, hull, invw
+        self.diffw = z["diffw"].astype(np.float64)
+        self.jkp, self.jkd, self.torque_lim = (z[k].astype(np.float64) for k in ("jkp", "jkd", "torque_lim"))
+        self.armature = z["armature"].astype(np.float64)
+        self.ee = z["ee_body"].astype(np.int32)
+        self.nbr, self.nbradr = z["hull_nbr"].astype(np.int32), z["hull_nbradr"].astype(np.int32)
+        self.dt = float(z["timestep"])
+        self.margin, self.mu = float(z["margin"]), float(z["friction"])
+        self.solref, self.solimp, self.gravz = z["solref"], z["solimp"], float(z["gravity"][2])
+        self.qpos0 = np.zeros(NQ)
+        self.qpos0[:3] = z["body_gpos"][0]
+        self.qpos0[3] = 1.0
+        self.root_offset = z["body_gpos"][0].copy()  # mj_model.body_pos[1] in smpl_to_qpose (count_offset)
+        self._topology()
+        self._pack()
+
+    def _topology(self):
+        p = self.parent
+        self.depth = np.zeros(NB, np.int32)
+        for b in range(1, NB):
+            self.depth[b] = self.depth[p[b]] + 1
+        ch = [[c for c in range(NB) if p[c] == b] for b in range(NB)]
+        self.child_adr = np.concatenate([[0], np.cumsum([len(c) for c in ch])]).astype(np.int32)
+        self.child = np.array([c for cs in ch for c in cs], np.int32)
+        sub_end = np.arange(NB)
+        for b in range(NB - 1, 0, -1):
+            sub_end[p[b]] = max(sub_end[p[b]], sub_end[b])
+        self.body_sub_end = sub_end.astype(np.int32)
+        self.dof_body = np.array([0] * 6 + [1 + d // 3 for d in range(NU)], np.int32)
+        # ancestor chain (by depth) of every dof
+        chains = []
+        for k in range(NV):
+            b = self.dof_body[k]
+            if b == 0:
+                chains.append(list(range(k + 1)))
+                continue
+            bodies, a = [], b
+            while a > 0:
+                bodies.append(a)
+                a = p[a]
+            ch_k = list(range(6))
+            for a in reversed(bodies):
+                d0 = 6 + 3 * (a - 1)
+                ch_k += [d0, d0 + 1, d0 + 2] if a != b else list(range(d0, k + 1))
+            chains.append(ch_k)
+        self.dep = np.array([len(c) - 1 for c in chains], np.int32)
+        self.madr = np.concatenate([[0], np.cumsum(self.dep + 1)])[:-1].astype(np.int32)
+        self.nnz = int((self.dep + 1).sum())
+        assert self.nnz == 1221 and self.dep.max() == 29 and int((self.dep[:39] + 1).sum()) == 420, (self.nnz, self.dep.max())
+        self.rowadr = np.zeros((NV, 32), np.int16)
+        self.colidx = np.zeros((NV, 32), np.uint8)
+        ent_row, ent_col = [], []
+        for k, c in enumerate(chains):
+            for s, a in enumerate(c):
+                self.rowadr[k, s] = self.madr[a]
+                self.colidx[k, s] = a
+                ent_row.append(k)
+                ent_col.append(a)
+        self.ent_row, self.ent_col = np.array(ent_row, np.uint8), np.array(ent_col, np.uint8)
+        dse = np.zeros(NV, np.int32)
+        for k in range(NV):
+            b = self.dof_body[k]
+            dse[k] = NV - 1 if b == 0 else 6 + 3 * (self.body_sub_end[b] - 1) + 2
+        self.dof_sub_end = dse
+        self.chains = chains
+
+    def _pack(self):
+        bf = np.zeros((NB, BODYF))
+        bf[:, 0:3], bf[:, 3:6], bf[:, 6] = self.offset, self.ipos, self.mass
+        I = self.inertia
+        bf[:, 7:13] = np.stack([I[:, 0, 0], I[:, 1, 1], I[:, 2, 2], I[:, 0, 1], I[:, 0, 2], I[:, 1, 2]], 1)
+        bf[:, 13] = self.invw
+        for b in range(NB):  # bounding sphere of the hull about its vertex centroid
+            v = self.hull[self.hull_adr[b]:self.hull_adr[b] + self.hull_num[b]]
+            c = v.mean(0)
+            bf[b, 14:17], bf[b, 17] = c, np.linalg.norm(v - c, axis=1).max() * 1.0001 + 1e-6
+        bf[:, 18] = self.diffw
+        df = np.zeros((NV, 4))
+        df[:, 0] = self.armature
+        df[6:, 1], df[6:, 2], df[6:, 3] = self.jkp, self.jkd, self.torque_lim
+        self.body_f, self.dof_f = np.ascontiguousarray(bf), np.ascontiguousarray(df)
+
+    def host_struct(self):
+        """ctypes struct of host pointers for uhc_engine_create / the emulation (arrays kept alive on self)."""
+        h = UhcModelHost()
+        keep = self._keep = {}
+
+        def ptr(name, arr, ct):
+            a = np.ascontiguousarray(arr)
+            keep[name] = a
+            return a.ctypes.data_as(C.POINTER(ct))
+
+        h.nvert, h.nnbr = len(self.hull), len(self.nbr)
+        h.body_f, h.dof_f, h.hull = ptr("bf", self.body_f, C.c_double), ptr("df", self.dof_f, C.c_double), ptr("hull", self.hull, C.c_double)
+        for n in ("hull_adr", "hull_num", "nbr", "nbradr", "parent", "depth", "child_adr", "child", "body_sub_end", "dep",
+                  "madr", "dof_sub_end", "dof_body", "ee"):
+            setattr(h, n, ptr(n, getattr(self, n).astype(np.int32), C.c_int))
+        h.rowadr, h.colidx = ptr("rowadr", self.rowadr, C.c_short), ptr("colidx", self.colidx, C.c_ubyte)
+        h.ent_row, h.ent_col = ptr("er", self.ent_row, C.c_ubyte), ptr("ec", self.ent_col, C.c_ubyte)
+        h.dt, h.margin, h.mu, h.gravz = self.dt, self.margin, self.mu, self.gravz
+        h.solref = (C.c_double * 2)(*self.solref)
+        h.solimp = (C.c_double * 5)(*self.solimp)
+        return h
