@@ -1,0 +1,53 @@
+"""CPU: the product kernel source compiled as a host lane-loop emulation (tests/emu) against the oracle / goldens.
+This exercises every line of uhc_b200/csrc/sim_core.h + env_step.h without a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.emu.emu import Emu
+
+
+def test_forward_dynamics_matches_oracle_fp64():
+    om, d = O.Model(), O.Data()
+    e = Emu(64)
+    rng = np.random.default_rng(0)
+    for case in range(4):
+        q = om.qpos0.copy()
+        q[2] = 3.0 if case == 0 else rng.uniform(0.85, 0.95)
+        q[3:7] = [0.7071068, 0.7071068, 0, 0] + (rng.normal(size=4) * (1.0 if case == 0 else 0.05))
+        q[3:7] /= np.linalg.norm(q[3:7])
+        q[7:] = rng.uniform(-0.3, 0.3, 69)
+        v = rng.normal(size=75) * 0.5
+        tau, fapp = rng.normal(size=69) * 20, rng.normal(size=6) * 10
+        d.qpos[:], d.qvel[:], d.ctrl[:] = q, v, tau
+        d.qfrc_applied[:] = 0
+        d.qfrc_applied[:6] = fapp
+        d.qacc_warm[:] = 0
+        O.forward(om, d)
+        r = e.forward(q, v, tau, fapp)
+        assert np.abs(r["M"] - d.M.reshape(75, 75)).max() < 1e-11
+        assert np.abs(r["C"] - d.C).max() < 1e-9
+        assert np.abs(r["xpos"] - d.xpos.reshape(24, 3)).max() < 1e-13
+        assert r["ncon"] == d.ncon
+        assert np.abs(r["qacc"] - d.qacc).max() < 1e-6 * max(1.0, np.abs(d.qacc).max())
+
+
+@pytest.mark.parametrize("prec,tol_q,tol_o", [(64, 1e-11, 1e-9), (32, 1e-4, 2e-3)])
+def test_env_trace_matches_reference_golden(golden_dir, prec, tol_q, tol_o):
+    g = np.load(os.path.join(golden_dir, "env_sway_noise.npz"))
+    z = np.load(os.path.join(golden_dir, "expert_sway.npz"))
+    ex = {k: z[k] for k in z.files}
+    so = np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+    e = Emu(prec)
+    e.load_clips([ex], [so])
+    obs0 = e.reset()
+    assert np.abs(obs0 - g["obs0"]).max() < max(tol_o * 1e-2, 1e-12)
+    for t in range(35):
+        obs, r, done, info = e.step(g["action"][t])
+        st, _ = e.state()
+        assert np.abs(st[:76] - g["qpos"][t]).max() < tol_q, t
+        assert np.abs(obs - g["obs"][t]).max() < tol_o, t
+        assert abs(r - g["reward"][t]) < tol_o
+        assert info["fail"] == bool(g["fail"][t])

@@ -195,7 +195,7 @@ UHC_DEV int popc_(unsigned x) { int c = 0; while (x) { x &= x - 1; c++; } return
 // H is stored row-chain: row k holds H[k][anc(k,0..dep k)] at H[madr[k] ..]; after factorisation row k holds the
 // UNSCALED factor row (L[k][t] = H[k][t] * dinv[k]) and dinv[k] = 1 / D_k.  Pivots run from leaves to the root.
 template <class Real>
-UHC_DEV void ldl_factor(const Model<Real> &m, Real *H, Real *dinv, int k_hi, int k_lo) {
+UHC_DEVNI void ldl_factor(const Model<Real> &m, Real *H, Real *dinv, int k_hi, int k_lo) {
     for (int k = k_hi; k >= k_lo; --k) {
         const int d = UHC_LDG(m.dep + k);
         const Real *Hk = H + UHC_LDG(m.madr + k);
@@ -212,7 +212,7 @@ UHC_DEV void ldl_factor(const Model<Real> &m, Real *H, Real *dinv, int k_hi, int
 }
 // solves H x = b in place (b -> x) with the factor above
 template <class Real>
-UHC_DEV void ldl_solve(const Model<Real> &m, const Real *H, const Real *dinv, Real *b) {
+UHC_DEVNI void ldl_solve(const Model<Real> &m, const Real *H, const Real *dinv, Real *b) {
     for (int k = NV - 1; k >= 1; --k) {  // y = L^-T b : scatter row k onto its ancestors
         const int d = UHC_LDG(m.dep + k);
         const Real *Hk = H + UHC_LDG(m.madr + k);
@@ -239,7 +239,7 @@ UHC_DEV void ldl_solve(const Model<Real> &m, const Real *H, const Real *dinv, Re
 // and velocity-product acceleration A (gravity folded in as a base acceleration), then per-body rigid inertia and the
 // inertial wrench F = I A + V x* (I V).   MuJoCo semantics: SURVEY.md Appendix B (mj_kinematics / mj_comPos / mj_rne).
 template <class Real>
-UHC_DEV void kin_rne_forward(const Model<Real> &m, Work<Real> &w) {
+UHC_DEVNI void kin_rne_forward(const Model<Real> &m, Work<Real> &w) {
     for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
         LANES_BEGIN
         const int b = lane;
@@ -328,7 +328,7 @@ UHC_DEV void kin_rne_forward(const Model<Real> &m, Work<Real> &w) {
 
 // leaves -> root accumulation of n floats per body (parents gather their children), lane = body
 template <class Real>
-UHC_DEV void tree_gather(const Model<Real> &m, Real *X, int stride, int n) {
+UHC_DEVNI void tree_gather(const Model<Real> &m, Real *X, int stride, int n) {
     for (int lvl = MAXLEVEL - 1; lvl >= 0; --lvl) {
         LANES_BEGIN
         const int b = lane;
@@ -344,7 +344,7 @@ UHC_DEV void tree_gather(const Model<Real> &m, Real *X, int stride, int n) {
 }
 // per-body spatial vector  X_b = sum_{i on chain(b)} S_i x_i   (root -> leaves), lane = body
 template <class Real>
-UHC_DEV void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real (*X)[6]) {
+UHC_DEVNI void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real (*X)[6]) {
     for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
         LANES_BEGIN
         const int b = lane;
@@ -361,7 +361,7 @@ UHC_DEV void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real (
 }
 // y_i = S_i . Fsub[body(i)]  for all dofs, lane = dof
 template <class Real>
-UHC_DEV void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F)[6], Real *y, Real scale, const Real *add) {
+UHC_DEVNI void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F)[6], Real *y, Real scale, const Real *add) {
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) {
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
@@ -372,7 +372,7 @@ UHC_DEV void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F)[
 
 // CRBA: composite inertias (in w.Ic, 10 params) -> tree-sparse M (+ armature)
 template <class Real>
-UHC_DEV void crba(const Model<Real> &m, Work<Real> &w) {
+UHC_DEVNI void crba(const Model<Real> &m, Work<Real> &w) {
     tree_gather(m, &w.Ic[0][0], 21, 10);
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) {
@@ -393,7 +393,7 @@ UHC_DEV void crba(const Model<Real> &m, Work<Real> &w) {
 // ================================================================================================ collision
 // Floor plane z = 0 against each body hull (oracle/uhc_oracle.c or_collide states the manifold rule).
 template <class Real>
-UHC_DEV void collide(const Model<Real> &m, Work<Real> &w) {
+UHC_DEVNI void collide(const Model<Real> &m, Work<Real> &w) {
     int ncon = 0, upper = 0;
     for (int b = 0; b < NB; ++b) {
         w.bcon_adr[b] = ncon;  // uniform value, every lane writes the same (benign)
@@ -460,7 +460,7 @@ template <class Real> UHC_DEV void edge_dir(int e, Real mu, Real *d) {
 
 // per-contact soft-constraint parameters (MuJoCo solref/solimp semantics), lane = contact
 template <class Real>
-UHC_DEV void constraint_setup(const Model<Real> &m, Work<Real> &w) {
+UHC_DEVNI void constraint_setup(const Model<Real> &m, Work<Real> &w) {
     const Real kk = Real(1) / (m.simp1 * m.simp1 * m.solref0 * m.solref0 * m.solref1 * m.solref1), bb = Real(2) / (m.simp1 * m.solref0);
     LANES_BEGIN
     for (int c = lane; c < w.ncon; c += 32) {
@@ -484,7 +484,7 @@ UHC_DEV void constraint_setup(const Model<Real> &m, Work<Real> &w) {
 
 // rows: out[c][e] = d_e . (point velocity of body spatial vector X at contact c), lane = contact
 template <class Real>
-UHC_DEV void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)[6], Real (*out)[4], const Real (*sub)[4]) {
+UHC_DEVNI void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)[6], Real (*out)[4], const Real (*sub)[4]) {
     LANES_BEGIN
     for (int c = lane; c < w.ncon; c += 32) {
         const int b = w.cbody[c]; Real u[3], t[3];
@@ -517,7 +517,7 @@ UHC_DEV void contact_force(const Model<Real> &m, Work<Real> &w, F lam, Real (*Fo
 // min_a 1/2 (a-a_s)^T M (a-a_s) + sum_rows 1/2 D min(0, J a - aref)^2 ; primal Newton, Hessian = M + J^T D_act J built as a
 // CRBA over contact-augmented composites, factorised tree-sparse (only the lower-body rows when no arm/head contact).
 template <class Real>
-UHC_DEV int newton_solve(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w) {
+UHC_DEVNI int newton_solve(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w) {
     // cost of the two start candidates (warm start vs unconstrained)
     Real cost[2];
     for (int pass = 0; pass < 2; ++pass) {
@@ -679,7 +679,7 @@ UHC_DEV int newton_solve(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Rea
 // `tau` holds the 69 joint torques, fapp the 6 root residual forces.  Leaves M, C, xpos/xmat/xipos of THIS (pre-integration)
 // configuration in the work set -- the staleness MuJoCo exposes to the Python side (SURVEY.md section 7 "stale dynamics").
 template <class Real>
-UHC_DEV int forward_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const Real *fapp, bool have_tau) {
+UHC_DEVNI int forward_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const Real *fapp, bool have_tau) {
     kin_rne_forward(m, w);
     tree_gather(m, &w.Fb[0][0], 6, 6);
     project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
@@ -715,7 +715,7 @@ UHC_DEV int forward_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work
 }
 
 template <class Real>
-UHC_DEV void integrate(const Model<Real> &m, Work<Real> &w) {
+UHC_DEVNI void integrate(const Model<Real> &m, Work<Real> &w) {
     const Real dt = m.dt;
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) { const Real vn = w.v[i] + dt * w.a[i]; w.v[i] = vn; w.aw[i] = w.a[i]; if (i >= 6) w.q[i + 1] += dt * vn; }
@@ -756,7 +756,7 @@ constexpr double PI_D = 3.14159265358979323846;
 // stable PD torque for substep `it` (humanoid_im.py:1033-1076 + :1014-1031): uses the M, C currently in the work set
 // (= previous forward pass) with the current q, v; leaves the clipped torques in w.tau (:1160).
 template <class Real>
-UHC_DEV void pd_torque(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const Real *target, int it) {
+UHC_DEVNI void pd_torque(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const Real *target, int it) {
     const Real dt = m.dt;
     Real sp = 1, sd = 1;
     if (cfg.meta_pd) { sp = clamp_(w.act[NU + 6 + it] + 1, Real(0), Real(10)); sd = clamp_(w.act[NU + 6 + it + NSUB] + 1, Real(0), Real(10)); }
@@ -807,7 +807,7 @@ UHC_DEV void rfc_implicit(const EnvCfg<Real> &cfg, const Work<Real> &w, Real *fa
 
 // body quaternions from qpos (humanoid_im.py:925-947), lane = body
 template <class Real>
-UHC_DEV void body_quat(const Work<Real> &w, Real *out) {
+UHC_DEVNI void body_quat(const Work<Real> &w, Real *out) {
     LANES_BEGIN
     const int b = lane;
     if (b == 0) for (int i = 0; i < 4; i++) out[i] = w.q[3 + i];
@@ -817,7 +817,7 @@ UHC_DEV void body_quat(const Work<Real> &w, Real *out) {
 // world body quaternions by composing along each body's own chain (no cross-lane dependency), lane = body.
 // Matches the pose the last forward pass used (xquat is only consumed by the observation).
 template <class Real>
-UHC_DEV void world_quat(const Model<Real> &m, const Real *qfk, Work<Real> &w) {
+UHC_DEVNI void world_quat(const Model<Real> &m, const Real *qfk, Work<Real> &w) {
     LANES_BEGIN
     const int b = lane;
     if (b < NB) {
@@ -840,7 +840,7 @@ UHC_DEV void world_quat(const Model<Real> &m, const Real *qfk, Work<Real> &w) {
 
 // observation v2 (humanoid_im.py:419-503, obs_coord "root"); ex1 = expert frame at cur_t + 1
 template <class Real, class OutT>
-UHC_DEV void obs_v2(const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *ex1, const Real *shape_obs, OutT *obs) {
+UHC_DEVNI void obs_v2(const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *ex1, const Real *shape_obs, OutT *obs) {
     Real crq[4], hq[4], hqi[4], trq[4], dh[4], ci[4], dq[4], Rq[9], Rc[9];
     remove_base_rot(cfg, w.q + 3, crq); heading_q(crq, hq); qinv(hq, hqi);
     remove_base_rot(cfg, ex1 + EX_QPOS + 3, trq);
@@ -902,7 +902,7 @@ template <class Real> UHC_DEV void rot_from_quat(const Real *q, Real *rv) {  // 
 // termination metric (humanoid_im.py:1408-1415) and world_rfc_implicit reward (reward_function.py:12-88);
 // ext = expert frame at the NEW cur_t; bquat/pbquat = current / previous body quats
 template <class Real>
-UHC_DEV void diff_and_reward(const Model<Real> &m, const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *ext, const Real *bquat,
+UHC_DEVNI void diff_and_reward(const Model<Real> &m, const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *ext, const Real *bquat,
                              const Real *pbquat, Real *body_diff, Real *reward, Real *cinfo) {
     LVAR(Real, s_bd); LVAR(Real, s_n); LVAR(Real, s_pose); LVAR(Real, s_vel); LVAR(Real, s_ee);
     const Real dtc = m.dt * NSUB;

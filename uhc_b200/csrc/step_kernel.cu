@@ -1,0 +1,270 @@
+// step_kernel.cu -- CUDA kernels + C ABI (include/uhc_b200.h) for the batched humanoid env: one warp per environment,
+// working set in shared memory, state records in HBM.  sm_100a.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/uhc_b200.h"
+#include "env_step.h"
+
+using namespace uhc;
+
+static thread_local std::string g_err;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
+
+template <class Real, int EPB>
+__global__ void __launch_bounds__(32 * EPB)
+k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict__ obs, float *__restrict__ rew, float *__restrict__ cinfo,
+           int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, env = blockIdx.x * EPB + warp;
+    if (env >= ev.num_envs) return;
+    Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
+    env_step_warp<Real, float>(ev, env, w, act + (size_t)env * ACT_DIM, obs ? obs + (size_t)env * OBS_DIM : nullptr, rew ? rew + env : nullptr,
+                               cinfo ? cinfo + (size_t)env * 5 : nullptr, fail ? fail + env : nullptr, end ? end + env : nullptr,
+                               pct ? pct + env : nullptr, torque ? torque + (size_t)env * NSUB * NU : nullptr);
+}
+
+template <class Real, int EPB>
+__global__ void __launch_bounds__(32 * EPB)
+k_env_reset(EngineView<Real> ev, int n, const int *__restrict__ ids, const int *__restrict__ clip, const int *__restrict__ start,
+            const int *__restrict__ len, const float *__restrict__ qpos, const float *__restrict__ qvel, float *__restrict__ obs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, i = blockIdx.x * EPB + warp;
+    if (i >= n) return;
+    Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
+    const int env = ids[i];
+    // optional overrides arrive as float; stage them through the work set's scratch vectors
+    Real *qo = nullptr, *vo = nullptr;
+    if (qpos) { qo = w.scr; vo = w.scr + 80; const int lane = threadIdx.x & 31;
+        for (int k = lane; k < NQ; k += 32) qo[k] = (Real)qpos[(size_t)i * NQ + k];
+        for (int k = lane; k < NV; k += 32) vo[k] = qvel ? (Real)qvel[(size_t)i * NV + k] : Real(0);
+        __syncwarp(); }
+    env_reset_warp<Real, float>(ev, env, w, clip[i], start[i], len[i], qo, vo, obs ? obs + (size_t)env * OBS_DIM : nullptr);
+}
+
+struct UhcEngine {
+    int E, device, precision, launches;
+    std::vector<void *> allocs;
+    EngineView<float> evf; EngineView<double> evd;
+    void *d_expert = nullptr, *d_shape = nullptr; int *d_clip_adr = nullptr;
+    // staging for the host-buffer API
+    float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_cinfo = nullptr, *d_pct = nullptr; int *d_fail = nullptr, *d_end = nullptr;
+    int *d_ids = nullptr; int ids_cap = 0;
+};
+
+template <class T> static int dev_copy(UhcEngine *e, T **dst, const T *src, size_t n) {
+    CK(cudaMalloc((void **)dst, n * sizeof(T))); e->allocs.push_back(*dst);
+    CK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+template <class Real> static int dev_copy_real(UhcEngine *e, const Real **dst, const double *src, size_t n) {
+    std::vector<Real> tmp(n); for (size_t i = 0; i < n; i++) tmp[i] = (Real)src[i];
+    Real *d; if (dev_copy(e, &d, tmp.data(), n)) return -1; *dst = d; return 0;
+}
+template <class Real> static void fill_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) {
+    for (int i = 0; i < 4; i++) c.base_rot[i] = (Real)h->base_rot[i];
+    c.rfc_scale = (Real)h->rfc_scale; c.rfc_lim = (Real)h->rfc_lim; c.rfc_rate = (Real)h->rfc_rate; c.body_diff_thresh = (Real)h->body_diff_thresh;
+    c.meta_pd = h->meta_pd; c.env_episode_len = h->env_episode_len; c.trail_steps = h->trail_steps; c.newton_max_iter = h->newton_max_iter;
+    for (int i = 0; i < 5; i++) { c.w[i] = (Real)h->w[i]; c.k[i] = (Real)h->k[i]; }
+    c.newton_tol = (Real)h->newton_tol;
+}
+template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, const UhcModelHost *m, const UhcEnvCfg *cfg) {
+    Model<Real> &M = ev.model;
+    if (dev_copy_real<Real>(e, &M.body_f, m->body_f, NB * BODYF) || dev_copy_real<Real>(e, &M.dof_f, m->dof_f, NV * 4) ||
+        dev_copy_real<Real>(e, &M.hull, m->hull, (size_t)m->nvert * 3)) return -1;
+    int *p;
+#define CPI(field, n) do { if (dev_copy(e, &p, m->field, (size_t)(n))) return -1; M.field = p; } while (0)
+    CPI(hull_adr, NB); CPI(hull_num, NB); CPI(nbr, m->nnbr); CPI(nbradr, m->nvert + 1); CPI(parent, NB); CPI(depth, NB); CPI(child_adr, NB + 1);
+    CPI(child, NB - 1); CPI(body_sub_end, NB); CPI(dep, NV); CPI(madr, NV); CPI(dof_sub_end, NV); CPI(dof_body, NV); CPI(ee, 5);
+#undef CPI
+    short *ps; if (dev_copy(e, &ps, m->rowadr, (size_t)NV * 32)) return -1; M.rowadr = ps;
+    unsigned char *pc;
+    if (dev_copy(e, &pc, m->colidx, (size_t)NV * 32)) return -1; M.colidx = pc;
+    if (dev_copy(e, &pc, m->ent_row, (size_t)NNZ)) return -1; M.ent_row = pc;
+    if (dev_copy(e, &pc, m->ent_col, (size_t)NNZ)) return -1; M.ent_col = pc;
+    M.dt = (Real)m->dt; M.margin = (Real)m->margin; M.mu = (Real)m->mu; M.solref0 = (Real)m->solref[0]; M.solref1 = (Real)m->solref[1];
+    M.simp0 = (Real)m->solimp[0]; M.simp1 = (Real)m->solimp[1]; M.simp2 = (Real)m->solimp[2]; M.simp3 = (Real)m->solimp[3]; M.simp4 = (Real)m->solimp[4];
+    M.gravz = (Real)m->gravz;
+    fill_cfg(ev.cfg, cfg);
+    ev.num_envs = e->E;
+    Real *st; CK(cudaMalloc((void **)&st, (size_t)e->E * ST_SIZE * sizeof(Real))); e->allocs.push_back(st);
+    CK(cudaMemset(st, 0, (size_t)e->E * ST_SIZE * sizeof(Real)));
+    int *is; CK(cudaMalloc((void **)&is, (size_t)e->E * SI_SIZE * sizeof(int))); e->allocs.push_back(is);
+    CK(cudaMemset(is, 0, (size_t)e->E * SI_SIZE * sizeof(int)));
+    ev.state = st; ev.istate = is; ev.expert = nullptr; ev.clip_adr = nullptr; ev.clip_shape = nullptr;
+    return 0;
+}
+
+constexpr int EPB_F = 4, EPB_D = 2;  // environments (warps) per block
+
+extern "C" {
+
+const char *uhc_last_error(void) { return g_err.c_str(); }
+
+int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_envs, int device, int precision, UhcEngine **out) {
+    if (!model || !cfg || !out || num_envs <= 0 || (precision != 32 && precision != 64)) { g_err = "uhc_engine_create: bad argument"; return -2; }
+    CK(cudaSetDevice(device));
+    UhcEngine *e = new UhcEngine();
+    e->E = num_envs; e->device = device; e->precision = precision; e->launches = 0;
+    int rc = precision == 32 ? build_view<float>(e, e->evf, model, cfg) : build_view<double>(e, e->evd, model, cfg);
+    if (rc) { delete e; return rc; }
+    if (precision == 32) {
+        CK(cudaFuncSetAttribute(k_env_step<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_F * sizeof(Work<float>))));
+        CK(cudaFuncSetAttribute(k_env_reset<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_F * sizeof(Work<float>))));
+    } else {
+        CK(cudaFuncSetAttribute(k_env_step<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_D * sizeof(Work<double>))));
+        CK(cudaFuncSetAttribute(k_env_reset<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_D * sizeof(Work<double>))));
+    }
+    const size_t E = num_envs;
+    CK(cudaMalloc((void **)&e->d_act, E * ACT_DIM * 4)); CK(cudaMalloc((void **)&e->d_obs, E * OBS_DIM * 4)); CK(cudaMalloc((void **)&e->d_rew, E * 4));
+    CK(cudaMalloc((void **)&e->d_cinfo, E * 5 * 4)); CK(cudaMalloc((void **)&e->d_pct, E * 4)); CK(cudaMalloc((void **)&e->d_fail, E * 4)); CK(cudaMalloc((void **)&e->d_end, E * 4));
+    for (void *p : {(void *)e->d_act, (void *)e->d_obs, (void *)e->d_rew, (void *)e->d_cinfo, (void *)e->d_pct, (void *)e->d_fail, (void *)e->d_end}) e->allocs.push_back(p);
+    *out = e;
+    return 0;
+}
+
+void uhc_engine_destroy(UhcEngine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->d_expert) cudaFree(e->d_expert);
+    if (e->d_shape) cudaFree(e->d_shape);
+    if (e->d_clip_adr) cudaFree(e->d_clip_adr);
+    if (e->d_ids) cudaFree(e->d_ids);
+    delete e;
+}
+
+int uhc_engine_set_cfg(UhcEngine *e, const UhcEnvCfg *cfg) {
+    if (!e || !cfg) { g_err = "uhc_engine_set_cfg: null"; return -2; }
+    if (e->precision == 32) fill_cfg(e->evf.cfg, cfg); else fill_cfg(e->evd.cfg, cfg);
+    return 0;
+}
+
+int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *frames_host, const double *shape_host) {
+    if (!e || nclips <= 0 || !clip_len || !frames_host || !shape_host) { g_err = "uhc_load_clips: bad argument"; return -2; }
+    CK(cudaSetDevice(e->device));
+    std::vector<int> adr(nclips + 1, 0);
+    for (int i = 0; i < nclips; i++) { if (clip_len[i] < 2) { g_err = "uhc_load_clips: clip shorter than 2 frames"; return -2; } adr[i + 1] = adr[i] + clip_len[i]; }
+    const size_t nf = (size_t)adr[nclips] * EX_SIZE, ns = (size_t)nclips * 17;
+    if (e->d_expert) { cudaFree(e->d_expert); cudaFree(e->d_shape); cudaFree(e->d_clip_adr); e->d_expert = e->d_shape = nullptr; e->d_clip_adr = nullptr; }
+    CK(cudaMalloc((void **)&e->d_clip_adr, (nclips + 1) * sizeof(int)));
+    CK(cudaMemcpy(e->d_clip_adr, adr.data(), (nclips + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    if (e->precision == 32) {
+        std::vector<float> f(nf), s(ns);
+        for (size_t i = 0; i < nf; i++) f[i] = (float)frames_host[i];
+        for (size_t i = 0; i < ns; i++) s[i] = (float)shape_host[i];
+        CK(cudaMalloc(&e->d_expert, nf * 4)); CK(cudaMalloc(&e->d_shape, ns * 4));
+        CK(cudaMemcpy(e->d_expert, f.data(), nf * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(e->d_shape, s.data(), ns * 4, cudaMemcpyHostToDevice));
+        e->evf.expert = (const float *)e->d_expert; e->evf.clip_shape = (const float *)e->d_shape; e->evf.clip_adr = e->d_clip_adr;
+    } else {
+        CK(cudaMalloc(&e->d_expert, nf * 8)); CK(cudaMalloc(&e->d_shape, ns * 8));
+        CK(cudaMemcpy(e->d_expert, frames_host, nf * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(e->d_shape, shape_host, ns * 8, cudaMemcpyHostToDevice));
+        e->evd.expert = (const double *)e->d_expert; e->evd.clip_shape = (const double *)e->d_shape; e->evd.clip_adr = e->d_clip_adr;
+    }
+    return 0;
+}
+
+int uhc_env_reset(UhcEngine *e, int n, const int *env_ids_host, const int *clip_host, const int *start_host, const int *len_host,
+                  const float *qpos_dev, const float *qvel_dev, float *obs_dev, void *stream) {
+    if (!e || n <= 0 || !env_ids_host || !clip_host || !start_host || !len_host) { g_err = "uhc_env_reset: bad argument"; return -2; }
+    if (!e->d_expert) { g_err = "uhc_env_reset: no clips loaded"; return -3; }
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e->ids_cap < n) { if (e->d_ids) cudaFree(e->d_ids); CK(cudaMalloc((void **)&e->d_ids, (size_t)4 * n * sizeof(int))); e->ids_cap = n; }
+    for (int i = 0; i < n; i++) if (env_ids_host[i] < 0 || env_ids_host[i] >= e->E) { g_err = "uhc_env_reset: env id out of range"; return -2; }
+    CK(cudaMemcpyAsync(e->d_ids, env_ids_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_ids + n, clip_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_ids + 2 * n, start_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_ids + 3 * n, len_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (e->precision == 32)
+        k_env_reset<float, EPB_F><<<(n + EPB_F - 1) / EPB_F, 32 * EPB_F, EPB_F * sizeof(Work<float>), st>>>(e->evf, n, e->d_ids, e->d_ids + n, e->d_ids + 2 * n, e->d_ids + 3 * n, qpos_dev, qvel_dev, obs_dev);
+    else
+        k_env_reset<double, EPB_D><<<(n + EPB_D - 1) / EPB_D, 32 * EPB_D, EPB_D * sizeof(Work<double>), st>>>(e->evd, n, e->d_ids, e->d_ids + n, e->d_ids + 2 * n, e->d_ids + 3 * n, qpos_dev, qvel_dev, obs_dev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));  // the host id arrays may be reused by the caller
+    e->launches++;
+    return 0;
+}
+
+int uhc_env_step(UhcEngine *e, const float *actions_dev, float *obs_dev, float *reward_dev, float *cinfo_dev, int *fail_dev, int *end_dev,
+                 float *percent_dev, float *torque_dev, void *stream) {
+    if (!e || !actions_dev) { g_err = "uhc_env_step: bad argument"; return -2; }
+    if (!e->d_expert) { g_err = "uhc_env_step: no clips loaded"; return -3; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (e->precision == 32)
+        k_env_step<float, EPB_F><<<(e->E + EPB_F - 1) / EPB_F, 32 * EPB_F, EPB_F * sizeof(Work<float>), st>>>(e->evf, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev);
+    else
+        k_env_step<double, EPB_D><<<(e->E + EPB_D - 1) / EPB_D, 32 * EPB_D, EPB_D * sizeof(Work<double>), st>>>(e->evd, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev);
+    CK(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+int uhc_env_step_host(UhcEngine *e, const float *actions_host, float *obs_host, float *reward_host, float *cinfo_host, int *fail_host,
+                      int *end_host, float *percent_host) {
+    if (!e || !actions_host) { g_err = "uhc_env_step_host: bad argument"; return -2; }
+    CK(cudaSetDevice(e->device));
+    const size_t E = e->E;
+    CK(cudaMemcpyAsync(e->d_act, actions_host, E * ACT_DIM * 4, cudaMemcpyHostToDevice, 0));
+    int rc = uhc_env_step(e, e->d_act, e->d_obs, e->d_rew, e->d_cinfo, e->d_fail, e->d_end, e->d_pct, nullptr, nullptr);
+    if (rc) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, e->d_obs, E * OBS_DIM * 4, cudaMemcpyDeviceToHost, 0));
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, e->d_rew, E * 4, cudaMemcpyDeviceToHost, 0));
+    if (cinfo_host) CK(cudaMemcpyAsync(cinfo_host, e->d_cinfo, E * 5 * 4, cudaMemcpyDeviceToHost, 0));
+    if (fail_host) CK(cudaMemcpyAsync(fail_host, e->d_fail, E * 4, cudaMemcpyDeviceToHost, 0));
+    if (end_host) CK(cudaMemcpyAsync(end_host, e->d_end, E * 4, cudaMemcpyDeviceToHost, 0));
+    if (percent_host) CK(cudaMemcpyAsync(percent_host, e->d_pct, E * 4, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int uhc_env_get_state(UhcEngine *e, int env, double *qpos76, double *qvel75, double *xpos72, double *bquat96, int *istate8) {
+    if (!e || env < 0 || env >= e->E) { g_err = "uhc_env_get_state: bad argument"; return -2; }
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<double> st(ST_SIZE);
+    if (e->precision == 32) {
+        std::vector<float> f(ST_SIZE);
+        CK(cudaMemcpy(f.data(), e->evf.state + (size_t)env * ST_SIZE, ST_SIZE * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < ST_SIZE; i++) st[i] = f[i];
+    } else CK(cudaMemcpy(st.data(), e->evd.state + (size_t)env * ST_SIZE, ST_SIZE * 8, cudaMemcpyDeviceToHost));
+    if (qpos76) memcpy(qpos76, &st[ST_Q], NQ * 8);
+    if (qvel75) memcpy(qvel75, &st[ST_V], NV * 8);
+    if (xpos72) memcpy(xpos72, &st[ST_XPOS], 72 * 8);
+    if (bquat96) memcpy(bquat96, &st[ST_BQUAT], 96 * 8);
+    if (istate8) CK(cudaMemcpy(istate8, (e->precision == 32 ? e->evf.istate : e->evd.istate) + (size_t)env * SI_SIZE, SI_SIZE * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int uhc_env_set_state(UhcEngine *e, int env, const double *qpos76, const double *qvel75) {
+    // fail_safe (humanoid_im.py:902-905): overwrite qpos/qvel then run sim.forward(); implemented as a reset-with-override
+    if (!e || env < 0 || env >= e->E || !qpos76 || !qvel75) { g_err = "uhc_env_set_state: bad argument"; return -2; }
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());
+    int is[SI_SIZE];
+    int *isd = (e->precision == 32 ? e->evf.istate : e->evd.istate) + (size_t)env * SI_SIZE;
+    CK(cudaMemcpy(is, isd, sizeof is, cudaMemcpyDeviceToHost));
+    std::vector<float> q(NQ), v(NV);
+    for (int i = 0; i < NQ; i++) q[i] = (float)qpos76[i];
+    for (int i = 0; i < NV; i++) v[i] = (float)qvel75[i];
+    float *dq, *dv; CK(cudaMalloc((void **)&dq, NQ * 4)); CK(cudaMalloc((void **)&dv, NV * 4));
+    CK(cudaMemcpy(dq, q.data(), NQ * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dv, v.data(), NV * 4, cudaMemcpyHostToDevice));
+    // keep cur_t / bquat: save and restore around the reset kernel
+    std::vector<unsigned char> keep((size_t)192 * (e->precision == 32 ? 4 : 8));
+    const size_t rs = e->precision == 32 ? 4 : 8;
+    unsigned char *stb = (unsigned char *)(e->precision == 32 ? (void *)e->evf.state : (void *)e->evd.state) + ((size_t)env * ST_SIZE + ST_BQUAT) * rs;
+    CK(cudaMemcpy(keep.data(), stb, keep.size(), cudaMemcpyDeviceToHost));
+    int rc = uhc_env_reset(e, 1, &env, &is[SI_CLIP], &is[SI_START], &is[SI_LEN], dq, dv, nullptr, nullptr);
+    cudaFree(dq); cudaFree(dv);
+    if (rc) return rc;
+    CK(cudaMemcpy(stb, keep.data(), keep.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(isd, is, sizeof(int), cudaMemcpyHostToDevice));  // cur_t
+    return 0;
+}
+
+int uhc_num_envs(const UhcEngine *e) { return e ? e->E : -1; }
+int uhc_kernel_launches(const UhcEngine *e) { return e ? e->launches : -1; }
+
+}  // extern "C"
