@@ -22,7 +22,8 @@ struct EngineView {
 
 template <class Real>
 UHC_DEV const Real *expert_frame(const EngineView<Real> &ev, int clip, int start, int len, int t) {  // humanoid_im.py:1322
-    int i = start + t; if (i > len - 1) i = len - 1;
+    // the reference slices the clip to [start, start+len) and always runs with start_ind = 0 (dataset_amass_single.py:238-244)
+    const int i = start + (t < len - 1 ? t : len - 1);
     return ev.expert + (size_t)(UHC_LDG(ev.clip_adr + clip) + i) * EX_SIZE;
 }
 
@@ -125,7 +126,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
         LANES_END
         if (WBALLOT(bad)) fail = 1;
     }
-    const int end = (cur_t >= ev.cfg.env_episode_len) || (cur_t + start >= len + ev.cfg.trail_steps - 1);
+    const int end = (cur_t >= ev.cfg.env_episode_len) || (cur_t >= len + ev.cfg.trail_steps - 1);
     if (obs) obs_v2(ev.cfg, w, expert_frame(ev, clip, start, len, cur_t + 1), ev.clip_shape + 17 * clip, obs);
     LANES_BEGIN
     if (lane == 0) {
