@@ -1,0 +1,56 @@
+/* uhc_nn.h -- C ABI of the policy/value network, Gaussian head, observation normaliser, GAE and PPO-update kernels
+ * (part of libuhc_b200.so).  All pointers are CUDA device pointers owned by the caller (PyTorch tensors hold the weights --
+ * the checkpoint format of the reference is a torch state_dict, uhc/agents/agent_copycat.py:190-201); `stream` is a cudaStream_t.
+ * Return 0 on success, <0 on error (uhc_nn_last_error()).  Each entry cites the reference Python it replaces.
+ */
+#ifndef UHC_NN_H
+#define UHC_NN_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { UHC_ACT_NONE = 0, UHC_ACT_GELU = 1, UHC_ACT_TANH = 2, UHC_ACT_RELU = 3, UHC_ACT_SIGMOID = 4 };  /* mlp.py:9-16 */
+
+const char *uhc_nn_last_error(void);
+
+/* nn.Linear + activation (khrylib/models/mlp.py:24-27):  y[M][N] = act(x[M][K] W[N][K]^T + b[N]); z (optional) = pre-activation. */
+int uhc_linear_forward(const float *x, const float *W, const float *b, float *y, float *z_or_null, int M, int N, int K, int act, void *stream);
+/* autograd of the same layer: dx[M][K] = dz W ; dW[N][K] = dz^T x ; db[N] = colsum(dz).  dx may be NULL (first layer). */
+int uhc_linear_backward(const float *x, const float *W, const float *dz, float *dx_or_null, float *dW, float *db, int M, int N, int K, void *stream);
+int uhc_act_backward(const float *dh, const float *z, float *dz, long n, int act, void *stream);
+
+/* tensor-core forward of the same layer for the rollout path (tcgen05, bf16 operands, fp32 accumulate): see mlp_tcgen05.cu.
+ * x_bf16 [M][Kp], W_bf16 [N][Kp] with Kp a multiple of 64 (zero padded); y_bf16 [M][Np] (next layer's input) and/or y_f32 [M][N]. */
+int uhc_linear_forward_tc(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null,
+                          int M, int N, int Kp, int ldy_bf16, int act, void *stream);
+int uhc_f32_to_bf16_padded(const float *x, void *y_bf16, int M, int K, int Kp, void *stream);
+
+/* DiagGaussian (khrylib/rl/core/distributions.py:6-25, policy.py:12-23): sample a = mean + exp(log_std) eps (or the mean where
+ * mean_action[i] != 0), log-prob summed over the action dims. */
+int uhc_gaussian_sample(const float *mean, const float *log_std, const unsigned char *mean_action, float *action, float *logp, int M, int A,
+                        unsigned long long seed, unsigned long long step, void *stream);
+int uhc_gaussian_logprob(const float *mean, const float *log_std, const float *action, float *logp, int M, int A, void *stream);
+
+/* PPO clipped surrogate gradient wrt the mean head (agent_ppo.py:58-65; rows with exps == 0 are excluded, :45);
+ * inv_count = 1 / #selected rows; loss_acc (optional) accumulates the surrogate loss. */
+int uhc_ppo_policy_grad(const float *mean, const float *log_std, const float *action, const float *adv, const float *fixed_logp, const float *exps,
+                        float clip_eps, float inv_count, float *dmean, float *loss_acc, int M, int A, void *stream);
+/* value loss gradient (agent_pg.py:18-25): L = mean (v - returns)^2 */
+int uhc_value_grad(const float *v, const float *ret, float *dv, float *loss_acc, int M, void *stream);
+int uhc_sqsum(const float *x, long n, double *out_acc, void *stream);
+/* torch.optim.Adam step (agent_copycat.py:160-177) with optional clip_grad_norm_ scale from *sqnorm (agent_ppo.py:53-56). */
+int uhc_adam_step(float *p, const float *g, float *m, float *v, long n, float lr, float beta1, float beta2, float eps, int step,
+                  const double *sqnorm_or_null, float max_norm, void *stream);
+
+/* estimate_advantages (khrylib/rl/core/common.py:5-25) on a time-major [T][E] rollout; last_val = bootstrap V(s_T) or NULL (=0). */
+int uhc_gae(const float *rew, const float *mask, const float *val, const float *last_val, float gamma, float tau, float *adv, float *ret, int T, int E,
+            void *stream);
+int uhc_normalize_advantages(float *adv, long n, double *scratch2, void *stream);   /* (A - mean) / std_unbiased, common.py:22 */
+
+/* ZFilter (khrylib/utils/zfilter.py:7-73): stats = [n, mean[D], S[D]] doubles; update!=0 merges the batch first. y may be NULL. */
+int uhc_zfilter(const float *x, float *y, int M, int D, double *stats, float clip, int update, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,219 @@
+// mlp_tcgen05.cu -- tensor-core Linear(+bias+activation) for the rollout-time policy/value forward:
+//   y[M][N] = act(x[M][Kp] W[N][Kp]^T + b),  bf16 operands (K-major, zero padded to Kp % 64 == 0), fp32 accumulation in TMEM.
+// sm_100a only: TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring -> tcgen05.mma (one elected thread, UMMA 128x128x16,
+// cta_group::1) -> tcgen05.ld epilogue (bias + activation fused, bf16 and/or fp32 store).  Warp roles: 0 = TMA producer,
+// 1 = MMA issuer + TMEM allocator, 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/uhc_nn.h"
+
+namespace {
+constexpr int BM = 128, BN = 128, BK = 64, UK = 16, STAGES = 4;
+constexpr int STAGE_BYTES = (BM * BK + BN * BK) * 2;             // 32 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;    // + alignment slack + barriers
+thread_local std::string g_tc_err;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(cnt)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128B-swizzled operand tile: 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+    d |= (uint64_t)1 << 46;                 // descriptor version
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float act_f(float z, int act) {
+    switch (act) {
+    case UHC_ACT_GELU: return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
+    case UHC_ACT_TANH: return tanhf(z);
+    case UHC_ACT_RELU: return z > 0.f ? z : 0.f;
+    case UHC_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
+    }
+    return z;
+}
+
+__global__ void __launch_bounds__(192, 1)
+k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
+            __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, int M, int N, int Kp, int ldy, int act) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], tmem_full
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, nkb = Kp / BK;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB));
+        for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                const uint32_t a = smem_u32(smem + s * STAGE_BYTES), b = a + BM * BK * 2;
+                tma_load_2d(a, &mapA, full0 + 8 * s, kb * BK, m0);
+                tma_load_2d(b, &mapB, full0 + 8 * s, kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a = smem_u32(smem + s * STAGE_BYTES), b = a + BM * BK * 2;
+                const uint64_t ad = make_desc(a), bd = make_desc(b);
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k) umma_bf16(tmem, ad + (uint64_t)(k * UK * 2 >> 4), bd + (uint64_t)(k * UK * 2 >> 4), idesc, (kb | k) != 0);
+                umma_commit(empty0 + 8 * s);             // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tfull);                          // accumulator complete
+        }
+    } else {
+        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + 32 * q + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                           "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                const int nb = n0 + c * 32;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const int n = nb + j; v[j] = n < N ? act_f(__uint_as_float(r[j]) + (bias ? __ldg(bias + n) : 0.f), act) : 0.f; }
+                if (yf) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < N) yf[(size_t)row * N + nb + j] = v[j];
+                }
+                if (ybf && nb < ldy) {
+                    if (nb + 32 <= ldy) {
+                        uint4 *dst = (uint4 *)(ybf + (size_t)row * ldy + nb);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                            uint4 u; u.x = *(uint32_t *)&p0; u.y = *(uint32_t *)&p1; u.z = *(uint32_t *)&p2; u.w = *(uint32_t *)&p3;
+                            dst[j] = u;
+                        }
+                    } else {
+                        for (int j = 0; j < 32 && nb + j < ldy; ++j) ybf[(size_t)row * ldy + nb + j] = __float2bfloat16_rn(v[j]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+    }
+}
+
+__global__ void k_f32_to_bf16_padded(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, int M, int K, int Kp) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)M * Kp; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kp); const size_t r = i / Kp;
+        y[i] = __float2bfloat16_rn(k < K ? x[r * K + k] : 0.f);
+    }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                             const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeFn)p;
+    }
+    return fn;
+}
+int make_map(CUtensorMap *m, const void *base, int rows, int Kp) {  // row-major [rows][Kp] bf16, box 64 x 128, 128B swizzle
+    EncodeFn enc = get_encode();
+    if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return -1; }
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM}, estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return -1; }
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+const char *uhc_tc_last_error(void) { return g_tc_err.c_str(); }
+
+int uhc_f32_to_bf16_padded(const float *x, void *y_bf16, int M, int K, int Kp, void *stream) {
+    k_f32_to_bf16_padded<<<1184, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)y_bf16, M, K, Kp);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int uhc_linear_forward_tc(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null, int M, int N, int Kp,
+                          int ldy_bf16, int act, void *stream) {
+    if (Kp % BK != 0 || M <= 0 || N <= 0) { g_tc_err = "uhc_linear_forward_tc: Kp must be a positive multiple of 64"; return -2; }
+    if (y_bf16_or_null && (ldy_bf16 % 8 != 0)) { g_tc_err = "uhc_linear_forward_tc: ldy must be a multiple of 8"; return -2; }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute failed"; return -1; }
+        attr_set = true;
+    }
+    CUtensorMap ma, mb;
+    if (make_map(&ma, x_bf16, M, Kp) || make_map(&mb, W_bf16, N, Kp)) return -1;
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    k_linear_tc<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, M, N, Kp, ldy_bf16, act);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
+}

@@ -1,0 +1,277 @@
+"""Policy / value networks, Gaussian head, ZFilter, GAE and the PPO update on the hand-written kernels (include/uhc_nn.h).
+
+PyTorch tensors hold the parameters (so the reference's pickle checkpoint format -- a state_dict with the keys
+net.affine_layers.{i}.{weight,bias}, action_mean.*, action_log_std, value_head.* -- round-trips unchanged,
+uhc/agents/agent_copycat.py:190-201); every arithmetic op below is a kernel of libuhc_b200.so, not torch.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from .engine import load_library
+
+ACT = {"none": 0, "gelu": 1, "tanh": 2, "relu": 3, "sigmoid": 4}
+
+
+def _lib():
+    L = load_library()
+    if not getattr(L, "_nn_ready", False):
+        L.uhc_nn_last_error.restype = C.c_char_p
+        L.uhc_tc_last_error.restype = C.c_char_p
+        L._nn_ready = True
+    return L
+
+
+def _chk(rc):
+    if rc != 0:
+        L = _lib()
+        raise RuntimeError("uhc_nn: " + (L.uhc_nn_last_error().decode() or L.uhc_tc_last_error().decode()))
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+def _stream(t):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def linear_forward(x, W, b, act="none", save_z=False):
+    import torch
+    M, K = x.shape
+    N = W.shape[0]
+    y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    z = torch.empty_like(y) if save_z else None
+    _chk(_lib().uhc_linear_forward(_p(x), _p(W), _p(b), _p(y), _p(z), M, N, K, ACT[act], _stream(x)))
+    return (y, z) if save_z else y
+
+
+class MLPNet:
+    """MLP trunk + linear head (khrylib/models/mlp.py:5-27 with PolicyGaussian.action_mean or Value.value_head)."""
+
+    def __init__(self, in_dim, hsize, out_dim, htype="gelu", device="cuda", head_name="action_mean", seed=None):
+        import torch
+        self.torch, self.dims, self.htype, self.head_name = torch, [in_dim] + list(hsize) + [out_dim], htype, head_name
+        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        self.W, self.b = [], []
+        for i in range(len(self.dims) - 1):  # nn.Linear default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias
+            k = 1.0 / math.sqrt(self.dims[i])
+            w = (torch.rand(self.dims[i + 1], self.dims[i], generator=g) * 2 - 1) * k
+            bb = (torch.rand(self.dims[i + 1], generator=g) * 2 - 1) * k
+            if i == len(self.dims) - 2:  # policy_gaussian.py:20-21 / critic.py:12-13
+                w, bb = w * 0.1, bb * 0.0
+            self.W.append(w.to(device).float().contiguous())
+            self.b.append(bb.to(device).float().contiguous())
+        self.device = device
+        self._bf16 = None
+        self.opt = None
+
+    # ---- state_dict in the reference's key layout
+    def state_dict(self):
+        sd = {}
+        n = len(self.W)
+        for i in range(n - 1):
+            sd[f"net.affine_layers.{i}.weight"], sd[f"net.affine_layers.{i}.bias"] = self.W[i].detach().cpu(), self.b[i].detach().cpu()
+        sd[f"{self.head_name}.weight"], sd[f"{self.head_name}.bias"] = self.W[-1].detach().cpu(), self.b[-1].detach().cpu()
+        return sd
+
+    def load_state_dict(self, sd):
+        t = self.torch
+        n = len(self.W)
+        for i in range(n - 1):
+            self.W[i].copy_(t.as_tensor(np.asarray(sd[f"net.affine_layers.{i}.weight"]), dtype=t.float32))
+            self.b[i].copy_(t.as_tensor(np.asarray(sd[f"net.affine_layers.{i}.bias"]), dtype=t.float32))
+        self.W[-1].copy_(t.as_tensor(np.asarray(sd[f"{self.head_name}.weight"]), dtype=t.float32))
+        self.b[-1].copy_(t.as_tensor(np.asarray(sd[f"{self.head_name}.bias"]), dtype=t.float32))
+        self._bf16 = None
+
+    def params(self):
+        return [p for wb in zip(self.W, self.b) for p in wb]
+
+    # ---- fp32 path (training; exact-gelu, SIMT GEMM)
+    def forward(self, x, save=False):
+        h, saved = x, [x]
+        n = len(self.W)
+        zs = []
+        for i in range(n):
+            act = self.htype if i < n - 1 else "none"
+            if save and i < n - 1:
+                h, z = linear_forward(h, self.W[i], self.b[i], act, save_z=True)
+                zs.append(z)
+                saved.append(h)
+            else:
+                h = linear_forward(h, self.W[i], self.b[i], act)
+        return (h, (saved, zs)) if save else h
+
+    def backward(self, dy, ctx):
+        """dy: [M, out] gradient wrt the head output; returns grads in params() order."""
+        t = self.torch
+        saved, zs = ctx
+        n = len(self.W)
+        grads = [None] * (2 * n)
+        dz = dy.contiguous()
+        L = _lib()
+        for i in range(n - 1, -1, -1):
+            x = saved[i]
+            M, K = x.shape
+            N = self.W[i].shape[0]
+            dW, db = t.empty_like(self.W[i]), t.empty_like(self.b[i])
+            dx = t.empty(M, K, device=x.device, dtype=t.float32) if i > 0 else None
+            _chk(L.uhc_linear_backward(_p(x), _p(self.W[i]), _p(dz), _p(dx), _p(dW), _p(db), M, N, K, _stream(x)))
+            grads[2 * i], grads[2 * i + 1] = dW, db
+            if i > 0:
+                _chk(L.uhc_act_backward(_p(dx), _p(zs[i - 1]), _p(dx), C.c_long(dx.numel()), ACT[self.htype], _stream(x)))
+                dz = dx
+        return grads
+
+    # ---- tensor-core path (rollout): bf16 operands, fp32 accumulate, fused bias + activation
+    def _prep_bf16(self):
+        t = self.torch
+        Ws = []
+        for w in self.W:
+            N, K = w.shape
+            Kp = (K + 63) // 64 * 64
+            wb = t.zeros(N, Kp, device=w.device, dtype=t.bfloat16)
+            _chk(_lib().uhc_f32_to_bf16_padded(_p(w), _p(wb), N, K, Kp, _stream(w)))
+            Ws.append(wb)
+        self._bf16 = Ws
+
+    def invalidate_bf16(self):
+        self._bf16 = None
+
+    def forward_tc(self, x):
+        t = self.torch
+        if self._bf16 is None:
+            self._prep_bf16()
+        M, K = x.shape
+        Kp = self._bf16[0].shape[1]
+        key = (M, x.device)
+        if getattr(self, "_act_key", None) != key:  # activation buffers, zero padded once
+            self._acts = [t.zeros(M, w.shape[1], device=x.device, dtype=t.bfloat16) for w in self._bf16]
+            self._out = t.empty(M, self.dims[-1], device=x.device, dtype=t.float32)
+            self._act_key = key
+        L = _lib()
+        _chk(L.uhc_f32_to_bf16_padded(_p(x), _p(self._acts[0]), M, K, Kp, _stream(x)))
+        n = len(self.W)
+        for i in range(n):
+            last = i == n - 1
+            ybf = None if last else self._acts[i + 1]
+            _chk(L.uhc_linear_forward_tc(_p(self._acts[i]), _p(self._bf16[i]), _p(self.b[i]), _p(ybf), _p(self._out if last else None), M,
+                                         self.W[i].shape[0], self._bf16[i].shape[1], 0 if last else ybf.shape[1],
+                                         ACT["none" if last else self.htype], _stream(x)))
+        return self._out
+
+
+class Adam:
+    """torch.optim.Adam semantics (lr, betas (0.9, 0.999), eps 1e-8, no weight decay) on the fused kernel."""
+
+    def __init__(self, params, lr):
+        import torch
+        self.params, self.lr, self.step_n = params, lr, 0
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.sq = torch.zeros(1, device=params[0].device, dtype=torch.float64)
+
+    def step(self, grads, max_norm=None):
+        L = _lib()
+        self.step_n += 1
+        sq = None
+        if max_norm is not None:
+            self.sq.zero_()
+            for g in grads:
+                _chk(L.uhc_sqsum(_p(g), C.c_long(g.numel()), _p(self.sq), _stream(g)))
+            sq = self.sq
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            _chk(L.uhc_adam_step(_p(p), _p(g), _p(m), _p(v), C.c_long(p.numel()), C.c_float(self.lr), C.c_float(0.9), C.c_float(0.999),
+                                 C.c_float(1e-8), self.step_n, _p(sq), C.c_float(max_norm or 0.0), _stream(p)))
+
+
+class ZFilter:
+    """khrylib/utils/zfilter.py ZFilter on the device: stats = [n, mean[D], S[D]] (float64)."""
+
+    def __init__(self, dim, clip=5.0, device="cuda"):
+        import torch
+        self.dim, self.clip = dim, clip
+        self.stats = torch.zeros(1 + 2 * dim, device=device, dtype=torch.float64)
+
+    def __call__(self, x, update=True, out=None):
+        import torch
+        y = torch.empty_like(x) if out is None else out
+        _chk(_lib().uhc_zfilter(_p(x), _p(y), x.shape[0], self.dim, _p(self.stats), C.c_float(self.clip), int(update), _stream(x)))
+        return y
+
+    @property
+    def n(self):
+        return float(self.stats[0])
+
+    @property
+    def mean(self):
+        return self.stats[1:1 + self.dim].cpu().numpy()
+
+    @property
+    def std(self):
+        n = self.n
+        S = self.stats[1 + self.dim:].cpu().numpy()
+        return np.sqrt(S / (n - 1)) if n > 1 else np.abs(self.mean)
+
+    def load(self, n, mean, std):
+        import torch
+        var = np.asarray(std, dtype=np.float64) ** 2
+        s = np.concatenate([[float(n)], np.asarray(mean, dtype=np.float64), var * (max(n, 2) - 1)])
+        self.stats.copy_(torch.as_tensor(s))
+
+
+def gaussian_sample(mean, log_std, seed, step, mean_action=None):
+    import torch
+    M, A = mean.shape
+    a, lp = torch.empty_like(mean), torch.empty(M, device=mean.device, dtype=torch.float32)
+    _chk(_lib().uhc_gaussian_sample(_p(mean), _p(log_std), _p(mean_action), _p(a), _p(lp), M, A, C.c_ulonglong(seed), C.c_ulonglong(step), _stream(mean)))
+    return a, lp
+
+
+def gaussian_logprob(mean, log_std, action):
+    import torch
+    M, A = mean.shape
+    lp = torch.empty(M, device=mean.device, dtype=torch.float32)
+    _chk(_lib().uhc_gaussian_logprob(_p(mean), _p(log_std), _p(action), _p(lp), M, A, _stream(mean)))
+    return lp
+
+
+def gae(rewards, masks, values, last_values, gamma, tau, normalize=True):
+    """rewards/masks/values: [T, E] time-major.  Returns (advantages, returns), advantages normalised over the whole batch."""
+    import torch
+    T, E = rewards.shape
+    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    L = _lib()
+    _chk(L.uhc_gae(_p(rewards), _p(masks), _p(values), _p(last_values), C.c_float(gamma), C.c_float(tau), _p(adv), _p(ret), T, E, _stream(rewards)))
+    if normalize:
+        scratch = torch.zeros(2, device=rewards.device, dtype=torch.float64)
+        _chk(L.uhc_normalize_advantages(_p(adv), C.c_long(adv.numel()), _p(scratch), _stream(rewards)))
+    return adv, ret
+
+
+def ppo_update(policy, value, log_std, opt_p, opt_v, states, actions, returns, advantages, exps, clip_eps=0.2, epochs=10, grad_clip=40.0):
+    """AgentPPO.update_policy (agent_ppo.py:16-51), full batch: per epoch one value step then one clipped-surrogate policy step."""
+    import torch
+    L = _lib()
+    M, A = actions.shape
+    mean0 = policy.forward(states)
+    fixed = gaussian_logprob(mean0, log_std, actions)
+    count = float((exps != 0).sum().item())
+    losses = torch.zeros(2, device=states.device, dtype=torch.float32)
+    for _ in range(epochs):
+        v, ctx = value.forward(states, save=True)
+        dv = torch.empty_like(v)
+        losses.zero_()
+        _chk(L.uhc_value_grad(_p(v), _p(returns), _p(dv), _p(losses[1:]), M, _stream(states)))
+        opt_v.step(value.backward(dv, ctx))
+        mean, ctx = policy.forward(states, save=True)
+        dmean = torch.empty_like(mean)
+        _chk(L.uhc_ppo_policy_grad(_p(mean), _p(log_std), _p(actions), _p(advantages), _p(fixed), _p(exps), C.c_float(clip_eps),
+                                   C.c_float(1.0 / max(count, 1.0)), _p(dmean), _p(losses), M, A, _stream(states)))
+        opt_p.step(policy.backward(dmean, ctx), max_norm=grad_clip)
+    policy.invalidate_bf16()
+    value.invalidate_bf16()
+    return losses
