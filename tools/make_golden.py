@@ -107,7 +107,7 @@ def gen_ppo():
     agent.policy_grad_clip = [(pol.parameters(), 40)]
     agent.update_modules = [pol, val]
     agent.value_opt_niter = 1
-    agent.update_policy(st, actions_t, ret, adv, torch.tensor(exps)[:, None])
+    agent.update_policy(st, actions_t, ret, adv, torch.tensor(exps))
     p1 = {k: v.detach().numpy().copy() for k, v in pol.state_dict().items()}
     v1 = {k: v.detach().numpy().copy() for k, v in val.state_dict().items()}
     out = dict(hsize=np.array(hs), states=states, actions=actions, mean=mean, logp=logp, values=values, rewards=rewards,

@@ -271,7 +271,11 @@ def ppo_update(policy, value, log_std, opt_p, opt_v, states, actions, returns, a
         dmean = torch.empty_like(mean)
         _chk(L.uhc_ppo_policy_grad(_p(mean), _p(log_std), _p(actions), _p(advantages), _p(fixed), _p(exps), C.c_float(clip_eps),
                                    C.c_float(1.0 / max(count, 1.0)), _p(dmean), _p(losses), M, A, _stream(states)))
-        opt_p.step(policy.backward(dmean, ctx), max_norm=grad_clip)
+        # agent_copycat.py:93 passes `policy_net.parameters()` (a generator) as the clip list: clip_grad_norm_ exhausts it on the
+        # very first call, so the reference clips only the first policy step of a run.  Mirrored here.
+        first = not getattr(opt_p, "_clip_consumed", False)
+        opt_p._clip_consumed = True
+        opt_p.step(policy.backward(dmean, ctx), max_norm=grad_clip if (first and grad_clip) else None)
     policy.invalidate_bf16()
     value.invalidate_bf16()
     return losses
