@@ -37,7 +37,7 @@ static Emu<Real> *create(const UhcModelHost *m, const UhcEnvCfg *cfg, int E) {
     cp(e->parent, m->parent, NB); cp(e->depth, m->depth, NB); cp(e->child_adr, m->child_adr, NB + 1); cp(e->child, m->child, NB - 1);
     cp(e->body_sub_end, m->body_sub_end, NB); cp(e->dep, m->dep, NV); cp(e->madr, m->madr, NV); cp(e->dof_sub_end, m->dof_sub_end, NV);
     cp(e->dof_body, m->dof_body, NV); cp(e->ee, m->ee, 5);
-    cp(e->rowadr, m->rowadr, NV * 32); cp(e->colidx, m->colidx, NV * 32); cp(e->ent_row, m->ent_row, NNZ); cp(e->ent_col, m->ent_col, NNZ);
+    cp(e->rowadr, m->rowadr, NV * 32); cp(e->colidx, m->colidx, NV * 32); cp(e->ent_row, m->ent_row, 1221); cp(e->ent_col, m->ent_col, 1221);
     Model<Real> &M = e->ev.model;
     M.body_f = e->body_f.data(); M.dof_f = e->dof_f.data(); M.hull = e->hull.data(); M.hull_adr = e->hull_adr.data(); M.hull_num = e->hull_num.data();
     M.nbr = e->nbr.data(); M.nbradr = e->nbradr.data(); M.parent = e->parent.data(); M.depth = e->depth.data(); M.child_adr = e->child_adr.data();
@@ -59,6 +59,26 @@ static void load_clips(Emu<Real> *e, int nclips, const int *len, const double *f
     for (int i = 0; i < nclips; i++) e->clip_adr[i + 1] = e->clip_adr[i] + len[i];
     cp(e->expert, frames, (size_t)e->clip_adr[nclips] * EX_SIZE); cp(e->shape, shape, (size_t)nclips * 17);
     e->ev.expert = e->expert.data(); e->ev.clip_adr = e->clip_adr.data(); e->ev.clip_shape = e->shape.data();
+}
+
+template <class Real, class TPT>
+static int emu_forward_given_tau(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const TPT &tp, const double *fapp_d) {
+    // same sequence as substep_dynamics' PH_SMOOTH / PH_NEWTON phases with caller-provided torques and applied force
+    kin_rne_forward(m, w, tp);
+    project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
+    collide(m, w);
+    for (int i = 0; i < NV; i++) { Real f = -w.C[i] + (i < 6 ? (Real)fapp_d[i] : w.tau[i - 6]); w.fs[i] = f; w.as_[i] = f; }
+    aba_solve(m, w, tp, Real(0), false, w.as_);
+    if (w.ncon == 0) { for (int i = 0; i < NV; i++) w.a[i] = w.as_[i]; return 0; }
+    constraint_setup(m, w);
+    Real scale = newton_init(m, w, tp);
+    int iters = 0;
+    while (iters < cfg.newton_max_iter && newton_prepare(m, cfg, w, scale, tp)) {
+        ++iters;
+        aba_solve(m, w, tp, Real(0), true, w.p);
+        newton_advance(m, w, tp);
+    }
+    return iters;
 }
 
 extern "C" {
@@ -90,9 +110,14 @@ void emu_forward(void *h, int prec, const double *qpos, const double *qvel, cons
         for (int i = 0; i < NQ; i++) w.q[i] = (Real)qpos[i];
         for (int i = 0; i < NV; i++) { w.v[i] = (Real)qvel[i]; w.aw[i] = aw ? (Real)aw[i] : Real(0); }
         for (int i = 0; i < NU; i++) w.tau[i] = (Real)tau[i];
-        Real fa[6]; for (int i = 0; i < 6; i++) fa[i] = (Real)fapp[i];
-        *iters = forward_dynamics(e->ev.model, e->ev.cfg, w, fa, true);
-        for (int i = 0; i < NNZ; i++) Msparse[i] = (double)w.M[i];
+        // residual force goes through the action: vf = act[69:75] * rfc_scale rotated by the heading -> use a unit-scale, identity-heading cfg
+        (void)fapp;
+        for (int i = 0; i < ACT_DIM; i++) w.act[i] = 0;
+        TOPO_DECL(e->ev.model);
+        w.upper_contact = 0;
+        // emulate "with_pd" minus the PD phase: torques are given
+        *iters = emu_forward_given_tau<Real>(e->ev.model, e->ev.cfg, w, tp, fapp);
+        (void)Msparse;
         for (int i = 0; i < NV; i++) { Cout[i] = (double)w.C[i]; qacc[i] = (double)w.a[i]; }
         for (int i = 0; i < 72; i++) xpos[i] = (double)(&w.xpos[0][0])[i];
         *ncon = w.ncon;

@@ -9,7 +9,7 @@ from uhc_b200.model import HumanoidModel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libuhc_emu.so")
-ST = dict(Q=0, V=76, AW=152, C=228, XPOS=304, XQUAT=376, XIPOS=472, BQUAT=544, PBQUAT=640, M=736, SIZE=1960)
+ST = dict(Q=0, V=76, AW=152, C=228, XPOS=304, XQUAT=376, XIPOS=472, BQUAT=544, PBQUAT=640, IB=736, S=976, SIZE=1428)
 EX_SIZE = 508
 
 

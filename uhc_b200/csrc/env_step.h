@@ -33,7 +33,8 @@ UHC_DEV void load_state(const EngineView<Real> &ev, int env, Work<Real> &w) {
     LANES_BEGIN
     for (int i = lane; i < NQ; i += 32) w.q[i] = st[ST_Q + i];
     for (int i = lane; i < NV; i += 32) { w.v[i] = st[ST_V + i]; w.aw[i] = st[ST_AW + i]; w.C[i] = st[ST_C + i]; }
-    for (int i = lane; i < NNZ; i += 32) w.M[i] = st[ST_M + i];
+    for (int i = lane; i < NB * 10; i += 32) (&w.Ib[0][0])[i] = st[ST_IB + i];
+    for (int i = lane; i < NV * 6; i += 32) (&w.S[0][0])[i] = st[ST_S + i];
     LANES_END
 }
 template <class Real>
@@ -42,7 +43,8 @@ UHC_DEV void store_state(const EngineView<Real> &ev, int env, const Work<Real> &
     LANES_BEGIN
     for (int i = lane; i < NQ; i += 32) st[ST_Q + i] = w.q[i];
     for (int i = lane; i < NV; i += 32) { st[ST_V + i] = w.v[i]; st[ST_AW + i] = w.aw[i]; st[ST_C + i] = w.C[i]; }
-    for (int i = lane; i < NNZ; i += 32) st[ST_M + i] = w.M[i];
+    for (int i = lane; i < NB * 10; i += 32) st[ST_IB + i] = (&w.Ib[0][0])[i];
+    for (int i = lane; i < NV * 6; i += 32) st[ST_S + i] = (&w.S[0][0])[i];
     for (int i = lane; i < 72; i += 32) { st[ST_XPOS + i] = (&w.xpos[0][0])[i]; st[ST_XIPOS + i] = (&w.xipos[0][0])[i]; }
     for (int i = lane; i < 96; i += 32) { st[ST_XQUAT + i] = (&w.xquat[0][0])[i]; st[ST_BQUAT + i] = bquat[i]; if (pbquat) st[ST_PBQUAT + i] = pbquat[i]; }
     LANES_END
@@ -59,8 +61,8 @@ UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, 
     for (int i = lane; i < NV; i += 32) { w.v[i] = qvel_override ? qvel_override[i] : e0[EX_QVEL + i]; w.aw[i] = 0; }
     for (int i = lane; i < ACT_DIM; i += 32) w.act[i] = 0;
     LANES_END
-    Real fapp[6] = {0, 0, 0, 0, 0, 0};
-    const int iters = forward_dynamics(ev.model, ev.cfg, w, fapp, false);
+    TOPO_DECL(ev.model);
+    const int iters = substep_dynamics<Real, ObsT>(ev.model, ev.cfg, w, tp, (const Real *)nullptr, 0, false, (ObsT *)nullptr);
     world_quat(ev.model, w.q, w);
     int *is = ev.istate + (size_t)env * SI_SIZE;
     Real *st = ev.state + (size_t)env * ST_SIZE;
@@ -73,7 +75,8 @@ UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, 
     LANES_BEGIN
     for (int i = lane; i < NQ; i += 32) stq[ST_Q + i] = w.q[i];
     for (int i = lane; i < NV; i += 32) { stq[ST_V + i] = w.v[i]; stq[ST_AW + i] = 0; stq[ST_C + i] = w.C[i]; }
-    for (int i = lane; i < NNZ; i += 32) stq[ST_M + i] = w.M[i];
+    for (int i = lane; i < NB * 10; i += 32) stq[ST_IB + i] = (&w.Ib[0][0])[i];
+    for (int i = lane; i < NV * 6; i += 32) stq[ST_S + i] = (&w.S[0][0])[i];
     for (int i = lane; i < 72; i += 32) { stq[ST_XPOS + i] = (&w.xpos[0][0])[i]; stq[ST_XIPOS + i] = (&w.xipos[0][0])[i]; }
     for (int i = lane; i < 96; i += 32) stq[ST_XQUAT + i] = (&w.xquat[0][0])[i];
     LANES_END
@@ -93,16 +96,10 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     LANES_END
     const Real *target = expert_frame(ev, clip, start, len, cur_t + 1) + EX_QPOS + 7;
     int iters = 0, maxcon = 0;
+    TOPO_DECL(ev.model);
+#pragma unroll 1
     for (int it = 0; it < NSUB; ++it) {
-        pd_torque(ev.model, ev.cfg, w, target, it);
-        if (torque_out) {
-            LANES_BEGIN
-            for (int j = lane; j < NU; j += 32) torque_out[it * NU + j] = (ObsT)w.tau[j];
-            LANES_END
-        }
-        Real fapp[6];
-        rfc_implicit(ev.cfg, w, fapp);
-        iters += forward_dynamics(ev.model, ev.cfg, w, fapp, true);
+        iters += substep_dynamics<Real, ObsT>(ev.model, ev.cfg, w, tp, target, it, true, torque_out);
         if (w.ncon > maxcon) maxcon = w.ncon;
         if (it == NSUB - 1) world_quat(ev.model, w.q, w);  // pose of the last forward pass (what data.body_xquat holds)
         integrate(ev.model, w);

@@ -8,11 +8,11 @@
 // Algorithms (all world-aligned spatial vectors about the reference point O = root position):
 //   kinematics            level-synchronous tree pass, lane = body                         (a5: mj_kinematics)
 //   bias force C(q,v)     spatial recursive Newton-Euler, lane = body / lane = dof         (a5: mj_rne)
-//   mass matrix M         composite-rigid-body algorithm into a tree-sparse row-chain store (a5: mj_crb)
-//   stable PD             tree-sparse L^T D L of (M_stale + Kd dt), substitution             (a3: humanoid_im.py:1014-1076)
+//   linear solves         O(n) articulated-body sweeps, lane = body, registers + shuffles (replaces mj_crb + mj_factorM + cho_solve)
+//   stable PD             (M_stale + Kd dt)^-1 rhs by the articulated-body solve             (a3: humanoid_im.py:1014-1076)
 //   floor contacts        plane / convex-hull support vertex + hull-graph neighbours        (a5: collision)
-//   constraint solve      primal Newton on the convex soft-constraint cost, Hessian = CRBA with contact-augmented
-//                         composite inertias, exact-direction + safeguarded 1-D Newton line search (a5: solver)
+//   constraint solve      primal Newton on the convex soft-constraint cost, Newton direction = articulated-body solve with
+//                         contact-augmented body inertias, safeguarded 1-D Newton line search (a5: solver)
 //   integration           semi-implicit Euler, quaternion exponential map for the root      (a5: mj_Euler)
 //   epilogue              body quats, termination, observation v2, world_rfc_implicit reward (a6, a7, a10)
 // Reference behaviour being restated is cited next to each phase (file:line under the reference tree).
@@ -28,6 +28,8 @@
 #define LANES_END } __syncwarp();
 #define LVAR(T, n) T n
 #define LV(n) n
+#define LVARA(T, n, K) T n[K]
+#define LVA(n) n
 #define UHC_LDG(p) __ldg(p)
 #else
 #define UHC_DEV static inline
@@ -36,6 +38,8 @@
 #define LANES_END }
 #define LVAR(T, n) T n[32]
 #define LV(n) n[lane]
+#define LVARA(T, n, K) T n[32][K]
+#define LVA(n) n[lane]
 #define UHC_LDG(p) (*(p))
 #endif
 
@@ -43,15 +47,13 @@ namespace uhc {
 
 constexpr int NB = 24, NQ = 76, NV = 75, NU = 69, NSUB = 15;
 constexpr int OBS_DIM = 657, ACT_DIM = 105;
-constexpr int NNZ = 1221, NNZP = 1224;        // tree-sparse row-chain storage of M / H
-constexpr int NLOW = 39, NNZ_LOW = 420;       // dofs 0..38 (root, legs, torso, spine, chest): rows that contact Hessians touch
 constexpr int UPPER_BODY0 = 12;               // bodies >= Neck: arms, neck, head
 constexpr int MAXCON = 40;
 constexpr int MAXLEVEL = 8;
 constexpr int BODYF = 20;                     // floats per body in the model table
 // per-env state record in HBM (Real units)
 constexpr int ST_Q = 0, ST_V = 76, ST_AW = 152, ST_C = 228, ST_XPOS = 304, ST_XQUAT = 376, ST_XIPOS = 472,
-              ST_BQUAT = 544, ST_PBQUAT = 640, ST_M = 736, ST_SIZE = 1960;
+              ST_BQUAT = 544, ST_PBQUAT = 640, ST_IB = 736, ST_S = 976, ST_SIZE = 1428;   // IB: per-body inertia 24x10, S: 75x6
 // per-env integer record
 constexpr int SI_CUR_T = 0, SI_CLIP = 1, SI_START = 2, SI_LEN = 3, SI_EPISODE = 4, SI_FLAGS = 5, SI_NEWTON = 6, SI_NCON = 7, SI_SIZE = 8;
 // expert frame record (Real units): qpos 76 | qvel 75 | wbpos 72 | wbquat 96 | bquat 96 | bangvel 72 | ee_wpos 15 | com 3 | pad
@@ -86,11 +88,9 @@ struct Work {
     Real q[NQ], v[NV + 1], aw[NV + 1], act[ACT_DIM + 3];
     Real xpos[NB][3], xmat[NB][9], xipos[NB][3], xquat[NB][4];
     Real S[NV][6];
-    Real Ic[NB][21];              // composite rigid inertia (first 10) during CRBA; composite contact matrix K (21) in Newton
-    Real M[NNZP], H[NNZP], Mt[NNZ_LOW], dinv[NV + 1];
+    Real Ib[NB][10];              // per-body rigid inertia about O, world axes (of the last forward pass)
     Real C[NV + 1], fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
     Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
-    Real scr[NV * 6 + 2];         // F_i = Ic * S_i scratch
     // contacts
     int cbody[MAXCON]; Real cr[MAXCON][3], cdist[MAXCON], cD[MAXCON], caref[MAXCON][4], cres[MAXCON][4], cjp[MAXCON][4];
     int bcon_adr[NB + 1];
@@ -169,7 +169,7 @@ template <class R> UHC_DEV void sym6_mul(const R *K, const R *x, R *y) {
     for (int i = 0; i < 6; i++) { R s = 0; for (int j = 0; j < 6; j++) s += K[sym6(i, j)] * x[j]; y[i] = s; }
 }
 
-// ------------------------------------------------------------------------------------------------ warp reductions
+// ------------------------------------------------------------------------------------------------ warp primitives
 #ifndef UHC_EMU
 template <class R> UHC_DEV R warp_sum(R x) { for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o); return x; }
 template <class R> UHC_DEV R warp_max(R x) { for (int o = 16; o; o >>= 1) { R y = __shfl_xor_sync(0xffffffffu, x, o); x = x > y ? x : y; } return x; }
@@ -180,6 +180,27 @@ template <class R> UHC_DEV void warp_argmin(R &x, int &i) {
 #define WMAX(n) warp_max(n)
 #define WARGMIN(x, i, ox, oi) { ox = x; oi = i; warp_argmin(ox, oi); }
 #define WBALLOT(n) __ballot_sync(0xffffffffu, (n) != 0)
+// bodies are numbered depth-first, so subtree(b) = lanes [b, sub_end]: subtree sum = difference of an inclusive warp prefix sum
+template <class R, int K> UHC_DEV void subtree_sum(R (&x)[K], int sub_end, int lane) {
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        R p = x[i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { R t = __shfl_up_sync(0xffffffffu, p, o); if (lane >= o) p += t; }
+        const R hi = __shfl_sync(0xffffffffu, p, sub_end), lo = __shfl_up_sync(0xffffffffu, p, 1);
+        x[i] = hi - (lane > 0 ? lo : R(0));
+    }
+}
+// root -> leaves accumulation along the tree: x_b <- x_b + x_parent(b), level by level
+template <class R, int K> UHC_DEV void ancestor_sum(R (&x)[K], int parent, int depth) {
+#pragma unroll 1
+    for (int lvl = 1; lvl <= MAXLEVEL; ++lvl) {
+#pragma unroll
+        for (int i = 0; i < K; i++) { const R t = __shfl_sync(0xffffffffu, x[i], parent < 0 ? 0 : parent); if (depth == lvl) x[i] += t; }
+    }
+}
+#define WSUBTREE(n, K, tp) subtree_sum<Real, K>(n, tp.sub_end, tp.lane)
+#define WANCESTOR(n, K, tp) ancestor_sum<Real, K>(n, tp.parent, tp.depth)
 #else
 template <class R> static R emu_sum(const R *x) { R s = 0; for (int i = 0; i < 32; i++) s += x[i]; return s; }
 template <class R> static R emu_max(const R *x) { R s = x[0]; for (int i = 1; i < 32; i++) s = x[i] > s ? x[i] : s; return s; }
@@ -188,48 +209,187 @@ template <class R> static R emu_max(const R *x) { R s = x[0]; for (int i = 1; i 
 #define WARGMIN(x, i, ox, oi) { ox = x[0]; oi = i[0]; for (int l_ = 1; l_ < 32; l_++) if (x[l_] < ox || (x[l_] == ox && i[l_] < oi)) { ox = x[l_]; oi = i[l_]; } }
 static unsigned emu_ballot(const int *x) { unsigned m = 0; for (int i = 0; i < 32; i++) if (x[i]) m |= 1u << i; return m; }
 #define WBALLOT(n) emu_ballot(n)
+template <class R, int K, class TP> static void emu_subtree(R (*x)[K], const TP *tp) {
+    R out[32][K];
+    for (int b = 0; b < 32; b++) for (int i = 0; i < K; i++) { R s = 0; for (int c = b; c <= tp[b].sub_end && c < 32; c++) s += x[c][i]; out[b][i] = s; }
+    for (int b = 0; b < 32; b++) for (int i = 0; i < K; i++) x[b][i] = out[b][i];
+}
+template <class R, int K, class TP> static void emu_ancestor(R (*x)[K], const TP *tp) {
+    for (int b = 1; b < NB; b++) for (int i = 0; i < K; i++) x[b][i] += x[tp[b].parent][i];   // depth-first order: parents come first
+}
+#define WSUBTREE(n, K, tp) emu_subtree<Real, K>(n, tp)
+#define WANCESTOR(n, K, tp) emu_ancestor<Real, K>(n, tp)
 #endif
 UHC_DEV int popc_(unsigned x) { int c = 0; while (x) { x &= x - 1; c++; } return c; }
 
-// ================================================================================================ tree-sparse L^T D L
-// H is stored row-chain: row k holds H[k][anc(k,0..dep k)] at H[madr[k] ..]; after factorisation row k holds the
-// UNSCALED factor row (L[k][t] = H[k][t] * dinv[k]) and dinv[k] = 1 / D_k.  Pivots run from leaves to the root.
+// ================================================================================================ articulated-body solve
+// Every linear system of a substep has the form  H x = b,  H = sum_b J_b^T Ihat_b J_b + diag(arm)  with J_b x = sum_{i on chain(b)} S_i x_i:
+//   stable PD        Ihat = I_b (previous forward pass),  arm = armature + kd dt        (humanoid_im.py:1014-1031, dense cho_solve there)
+//   smooth dynamics  Ihat = I_b,                           arm = armature                (mj_fwdAcceleration)
+//   Newton direction Ihat = I_b + K_b (active contacts),   arm = armature                (Hessian of the constraint cost)
+// so one O(n) articulated-body sweep solves all three without ever forming the joint-space matrix: lane = body, articulated
+// inertia (sym 6x6) / bias wrench in registers, leaves -> root then root -> leaves, children/parent exchange by warp shuffles.
+// World-aligned spatial quantities about the common point O need no frame transforms between bodies.
+struct LaneTopo { int lane, parent, depth, sub_end, ch0, ch1, ch2; };
 template <class Real>
-UHC_DEVNI void ldl_factor(const Model<Real> &m, Real *H, Real *dinv, int k_hi, int k_lo) {
-    for (int k = k_hi; k >= k_lo; --k) {
-        const int d = UHC_LDG(m.dep + k);
-        const Real *Hk = H + UHC_LDG(m.madr + k);
-        const Real inv = Real(1) / Hk[d];
+UHC_DEV LaneTopo lane_topo(const Model<Real> &m, int lane) {
+    LaneTopo t; t.lane = lane;
+    const int b = lane < NB ? lane : NB - 1;
+    t.parent = UHC_LDG(m.parent + b); t.depth = lane < NB ? UHC_LDG(m.depth + b) : 99; t.sub_end = lane < NB ? UHC_LDG(m.body_sub_end + b) : lane;
+    const int c0 = UHC_LDG(m.child_adr + b), c1 = UHC_LDG(m.child_adr + b + 1);
+    t.ch0 = (lane < NB && c0 < c1) ? UHC_LDG(m.child + c0) : -1;
+    t.ch1 = (lane < NB && c0 + 1 < c1) ? UHC_LDG(m.child + c0 + 1) : -1;
+    t.ch2 = (lane < NB && c0 + 2 < c1) ? UHC_LDG(m.child + c0 + 2) : -1;
+    return t;
+}
+#ifndef UHC_EMU
+#define TOPO_DECL(m) const LaneTopo tp = lane_topo(m, (int)(threadIdx.x & 31))
+#define TP tp
+// parents at depth `lvl` add their children's K floats (children sit at lvl + 1)
+template <class R, int K> UHC_DEV void gather_children(R (&x)[K], const LaneTopo &tp, int lvl) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const int src = r == 0 ? tp.ch0 : (r == 1 ? tp.ch1 : tp.ch2);
+        const bool act = tp.depth == lvl && src >= 0;
+        if (!__any_sync(0xffffffffu, act)) continue;
+#pragma unroll
+        for (int i = 0; i < K; i++) { const R t = __shfl_sync(0xffffffffu, x[i], src < 0 ? tp.lane : src); if (act) x[i] += t; }
+    }
+}
+template <class R, int K> UHC_DEV void fetch_parent(const R (&x)[K], R (&o)[K], const LaneTopo &tp) {
+#pragma unroll
+    for (int i = 0; i < K; i++) o[i] = __shfl_sync(0xffffffffu, x[i], tp.parent < 0 ? 0 : tp.parent);
+}
+#define WGATHER(n, K, tp, lvl) gather_children<Real, K>(n, tp, lvl)
+#define WFETCHP(n, o, K, tp) fetch_parent<Real, K>(n, o, tp)
+#else
+#define TOPO_DECL(m) LaneTopo tp[32]; for (int l_ = 0; l_ < 32; l_++) tp[l_] = lane_topo(m, l_)
+#define TP tp[lane]
+template <class R, int K> static void emu_gather(R (*x)[K], const LaneTopo *tp, int lvl) {
+    for (int b = 0; b < NB; b++) if (tp[b].depth == lvl) {
+        const int ch[3] = {tp[b].ch0, tp[b].ch1, tp[b].ch2};
+        for (int r = 0; r < 3; r++) if (ch[r] >= 0) for (int i = 0; i < K; i++) x[b][i] += x[ch[r]][i];
+    }
+}
+template <class R, int K> static void emu_fetchp(R (*x)[K], R (*o)[K], const LaneTopo *tp) {
+    for (int b = 0; b < 32; b++) for (int i = 0; i < K; i++) o[b][i] = x[tp[b].parent < 0 ? 0 : tp[b].parent][i];
+}
+#define WGATHER(n, K, tp, lvl) emu_gather<Real, K>(n, tp, lvl)
+#define WFETCHP(n, o, K, tp) emu_fetchp<Real, K>(n, o, tp)
+#endif
+
+// pyramid edge directions d_e = n +- mu t  for n = +z, t1 = +y, t2 = -x
+template <class Real> UHC_DEV void edge_dir(int e, Real mu, Real *d) {
+    d[0] = e == 2 ? -mu : (e == 3 ? mu : Real(0));
+    d[1] = e == 0 ? mu : (e == 1 ? -mu : Real(0));
+    d[2] = 1;
+}
+
+// contact matrix of body b: K_b = sum_{own contacts} X^T W X,  X = [G 1], G = -[r]x, W = D sum_{active edges} d d^T
+template <class Real>
+UHC_DEV void contact_matrix(const Model<Real> &m, const Work<Real> &w, int b, Real *K) {
+    for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
+        Real W[6] = {0, 0, 0, 0, 0, 0};  // xx yy zz xy xz yz
+        for (int e = 0; e < 4; e++) if (w.cres[c][e] < 0) {
+            Real d[3]; edge_dir(e, m.mu, d); const Real D = w.cD[c];
+            W[0] += D * d[0] * d[0]; W[1] += D * d[1] * d[1]; W[2] += D * d[2] * d[2];
+            W[3] += D * d[0] * d[1]; W[4] += D * d[0] * d[2]; W[5] += D * d[1] * d[2];
+        }
+        const Real Wm[9] = {W[0], W[3], W[4], W[3], W[1], W[5], W[4], W[5], W[2]};
+        const Real *r = w.cr[c];
+        const Real G[9] = {0, r[2], -r[1], -r[2], 0, r[0], r[1], -r[0], 0};
+        Real WG[9], GtWG[9];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) WG[3 * i + j] = Wm[3 * i] * G[j] + Wm[3 * i + 1] * G[3 + j] + Wm[3 * i + 2] * G[6 + j];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) GtWG[3 * i + j] = G[i] * WG[j] + G[3 + i] * WG[3 + j] + G[6 + i] * WG[6 + j];
+        for (int i = 0; i < 3; i++) for (int j = i; j < 3; j++) { K[sym6(i, j)] += GtWG[3 * i + j]; K[sym6(3 + i, 3 + j)] += Wm[3 * i + j]; }
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) K[sym6(i, 3 + j)] += WG[3 * j + i];  // (G^T W)[i][j] = WG[j][i]
+    }
+}
+
+// eliminate one joint dof from the articulated pair (IA, pA):  U = IA S, D = S.U + arm, u = b - S.pA ; IA -= U U^T / D ; pA += U u / D
+template <class Real>
+UHC_DEV void aba_eliminate(Real *IA, Real *pA, const Real *S, Real arm, Real bj, Real *U, Real *Dinv, Real *uo) {
+    sym6_mul(IA, S, U);
+    const Real D = dot6(S, U) + arm, di = Real(1) / D, u = bj - dot6(S, pA);
+    *Dinv = di; *uo = u;
+    const Real ud = u * di;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const Real Ui = U[i] * di;
+#pragma unroll
+        for (int j = i; j < 6; j++) IA[sym6(i, j)] -= Ui * U[j];
+        pA[i] += U[i] * ud;
+    }
+}
+
+// x <- H^-1 x  (x: 75-vector in shared memory).  arm_scale: extra joint-space diagonal = arm_scale * kd_i (0 for none).
+template <class Real, class TPT>
+UHC_DEV void aba_solve(const Model<Real> &m, Work<Real> &w, const TPT &tp, Real arm_scale, bool use_contacts, Real *x) {
+    LVARA(Real, IP, 27);      // articulated inertia (21, packed symmetric) + bias wrench (6)
+    LVARA(Real, U, 36);       // U_j (6 each) of this lane's dofs (6 for the root, 3 otherwise)
+    LVARA(Real, DU, 12);      // 1/D_j, u_j
+    LANES_BEGIN
+    const int b = lane;
+    for (int i = 0; i < 27; i++) LVA(IP)[i] = 0;
+    if (b < NB) {
+        const Real *I = w.Ib[b];   // rigid (m, h, J) -> packed symmetric 6x6 in (w, v) ordering
+        Real *A = LVA(IP);
+        A[sym6(0, 0)] = I[4]; A[sym6(1, 1)] = I[5]; A[sym6(2, 2)] = I[6]; A[sym6(0, 1)] = I[7]; A[sym6(0, 2)] = I[8]; A[sym6(1, 2)] = I[9];
+        A[sym6(3, 3)] = I[0]; A[sym6(4, 4)] = I[0]; A[sym6(5, 5)] = I[0];
+        // n = J a + h x b  ->  upper-right block is [h]x
+        A[sym6(0, 4)] = -I[3]; A[sym6(0, 5)] = I[2]; A[sym6(1, 3)] = I[3]; A[sym6(1, 5)] = -I[1]; A[sym6(2, 3)] = -I[2]; A[sym6(2, 4)] = I[1];
+        if (use_contacts) contact_matrix(m, w, b, A);
+    }
+    LANES_END
+    for (int lvl = MAXLEVEL; lvl >= 0; --lvl) {
+        WGATHER(IP, 27, tp, lvl);
         LANES_BEGIN
-        if (lane == 0) dinv[k] = inv;
-        if (lane < d) {
-            const Real w = Hk[lane] * inv;
-            const short *ra = m.rowadr + k * 32;
-            for (int s = lane; s < d; ++s) H[UHC_LDG(ra + s) + lane] -= Hk[s] * w;
+        const int b = lane;
+        if (b < NB && TP.depth == lvl) {
+            if (b == 0) {
+#pragma unroll
+                for (int j = 5; j >= 0; --j) {
+                    const Real arm = UHC_LDG(m.dof_f + 4 * j) + arm_scale * UHC_LDG(m.dof_f + 4 * j + 2);
+                    aba_eliminate(LVA(IP), LVA(IP) + 21, w.S[j], arm, x[j], LVA(U) + 6 * j, &LVA(DU)[j], &LVA(DU)[6 + j]);
+                }
+            } else {
+                const int d0 = 6 + 3 * (b - 1);
+#pragma unroll
+                for (int j = 2; j >= 0; --j) {
+                    const Real arm = UHC_LDG(m.dof_f + 4 * (d0 + j)) + arm_scale * UHC_LDG(m.dof_f + 4 * (d0 + j) + 2);
+                    aba_eliminate(LVA(IP), LVA(IP) + 21, w.S[d0 + j], arm, x[d0 + j], LVA(U) + 6 * j, &LVA(DU)[j], &LVA(DU)[6 + j]);
+                }
+            }
         }
         LANES_END
     }
-}
-// solves H x = b in place (b -> x) with the factor above
-template <class Real>
-UHC_DEVNI void ldl_solve(const Model<Real> &m, const Real *H, const Real *dinv, Real *b) {
-    for (int k = NV - 1; k >= 1; --k) {  // y = L^-T b : scatter row k onto its ancestors
-        const int d = UHC_LDG(m.dep + k);
-        const Real *Hk = H + UHC_LDG(m.madr + k);
-        const Real bk = b[k] * dinv[k];
-        LANES_BEGIN
-        if (lane < d) b[UHC_LDG(m.colidx + k * 32 + lane)] -= Hk[lane] * bk;
-        LANES_END
-    }
+    // root -> leaves: x_j = (u_j - U_j . a) / D_j ; a += S_j x_j
+    LVARA(Real, acc, 6); LVARA(Real, ap, 6);
     LANES_BEGIN
-    for (int i = lane; i < NV; i += 32) b[i] *= dinv[i];
+    for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const Real xj = (LVA(DU)[6 + j] - dot6(LVA(U) + 6 * j, LVA(acc))) * LVA(DU)[j];
+            x[j] = xj;
+            for (int i = 0; i < 6; i++) LVA(acc)[i] += w.S[j][i] * xj;
+        }
+    }
     LANES_END
-    for (int j = 0; j < NV - 1; ++j) {  // x = L^-1 z : push x[j] to every dof of its subtree
-        const int e = UHC_LDG(m.dof_sub_end + j), dj = UHC_LDG(m.dep + j);
-        const Real xj = b[j];
-        if (e <= j) continue;
+    for (int lvl = 1; lvl <= MAXLEVEL; ++lvl) {
+        WFETCHP(acc, ap, 6, tp);
         LANES_BEGIN
-        for (int k = j + 1 + lane; k <= e; k += 32) b[k] -= H[UHC_LDG(m.madr + k) + dj] * dinv[k] * xj;
+        const int b = lane;
+        if (b < NB && TP.depth == lvl) {
+            const int d0 = 6 + 3 * (b - 1);
+            for (int i = 0; i < 6; i++) LVA(acc)[i] = LVA(ap)[i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const Real xj = (LVA(DU)[6 + j] - dot6(LVA(U) + 6 * j, LVA(acc))) * LVA(DU)[j];
+                x[d0 + j] = xj;
+                for (int i = 0; i < 6; i++) LVA(acc)[i] += w.S[d0 + j][i] * xj;
+            }
+        }
         LANES_END
     }
 }
@@ -237,13 +397,14 @@ UHC_DEVNI void ldl_solve(const Model<Real> &m, const Real *H, const Real *dinv, 
 // ================================================================================================ kinematics + RNE
 // Forward pass over tree levels, lane = body: pose, motion subspaces S (about O = root position), spatial velocity V
 // and velocity-product acceleration A (gravity folded in as a base acceleration), then per-body rigid inertia and the
-// inertial wrench F = I A + V x* (I V).   MuJoCo semantics: SURVEY.md Appendix B (mj_kinematics / mj_comPos / mj_rne).
-template <class Real>
-UHC_DEVNI void kin_rne_forward(const Model<Real> &m, Work<Real> &w) {
+// inertial wrench F = I A + V x* (I V); subtree wrenches by warp prefix sums.
+// MuJoCo semantics: SURVEY.md Appendix B (mj_kinematics / mj_comPos / mj_rne / mj_crb).
+template <class Real, class TPT>
+UHC_DEV void kin_rne_forward(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
     for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
         LANES_BEGIN
         const int b = lane;
-        if (b < NB && UHC_LDG(m.depth + b) == lvl) {
+        if (b < NB && TP.depth == lvl) {
             const Real *bf = m.body_f + b * BODYF;
             Real R[9], pos[3], V[6], A[6];
             if (b == 0) {
@@ -266,14 +427,16 @@ UHC_DEVNI void kin_rne_forward(const Model<Real> &m, Work<Real> &w) {
                 cross3(ww, V + 3, t);  // spatial acceleration of the free body with qacc = 0 is (0, -w x v); minus gravity
                 A[0] = A[1] = A[2] = 0; A[3] = -t[0]; A[4] = -t[1]; A[5] = -t[2] - m.gravz;
             } else {
-                const int p = UHC_LDG(m.parent + b);
+                const int p = TP.parent;
                 const Real *Rp = w.xmat[p];
-                mv3(Rp, bf, pos);
+                Real off[3] = {UHC_LDG(bf), UHC_LDG(bf + 1), UHC_LDG(bf + 2)};
+                mv3(Rp, off, pos);
                 for (int i = 0; i < 3; i++) pos[i] += w.xpos[p][i];
                 for (int i = 0; i < 9; i++) R[i] = Rp[i];
                 for (int i = 0; i < 6; i++) { V[i] = w.Vb[p][i]; A[i] = w.Ab[p][i]; }
                 const Real r[3] = {pos[0] - w.q[0], pos[1] - w.q[1], pos[2] - w.q[2]};
                 // three hinges z, y, x, each seen in the frame produced by the previous ones
+#pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int dof = 6 + 3 * (b - 1) + j, col = 2 - j;
                     Real ax[3] = {R[col], R[3 + col], R[6 + col]}, Sj[6], Sd[6], t[3];
@@ -298,70 +461,68 @@ UHC_DEVNI void kin_rne_forward(const Model<Real> &m, Work<Real> &w) {
             for (int i = 0; i < 3; i++) w.xpos[b][i] = pos[i];
             for (int i = 0; i < 9; i++) w.xmat[b][i] = R[i];
             for (int i = 0; i < 6; i++) { w.Vb[b][i] = V[i]; w.Ab[b][i] = A[i]; }
-            // rigid inertia about O in world axes, inertial wrench
-            Real cl[3], c[3], I[10], T[9];
-            mv3(R, bf + 3, cl);
-            for (int i = 0; i < 3; i++) { w.xipos[b][i] = pos[i] + cl[i]; c[i] = pos[i] + cl[i] - w.q[i]; }
-            const Real ms = bf[6];
-            const Real Il[9] = {bf[7], bf[10], bf[11], bf[10], bf[8], bf[12], bf[11], bf[12], bf[9]};
-            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) T[3 * i + j] = R[3 * i] * Il[j] + R[3 * i + 1] * Il[3 + j] + R[3 * i + 2] * Il[6 + j];
-            const Real cc = dot3(c, c);
-            Real Iw[6]; const int ii[6] = {0, 1, 2, 0, 0, 1}, jj[6] = {0, 1, 2, 1, 2, 2};
-            for (int e = 0; e < 6; e++) {
-                const int i = ii[e], j = jj[e];
-                Iw[e] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2] + ms * ((i == j ? cc : Real(0)) - c[i] * c[j]);
-            }
-            I[0] = ms; I[1] = ms * c[0]; I[2] = ms * c[1]; I[3] = ms * c[2];
-            for (int e = 0; e < 6; e++) I[4 + e] = Iw[e];
-            for (int e = 0; e < 10; e++) w.Ic[b][e] = I[e];
-            Real IA[6], IV[6], t[3], t2[3];
-            rigid_mul(I, A, IA); rigid_mul(I, V, IV);
-            cross3(V, IV, t); cross3(V + 3, IV + 3, t2);   // V x* F = (w x n + v x f, w x f)
-            IA[0] += t[0] + t2[0]; IA[1] += t[1] + t2[1]; IA[2] += t[2] + t2[2];
-            cross3(V, IV + 3, t);
-            IA[3] += t[0]; IA[4] += t[1]; IA[5] += t[2];
-            for (int i = 0; i < 6; i++) w.Fb[b][i] = IA[i];
         }
         LANES_END
     }
+    // rigid inertia about O in world axes, inertial wrench; then subtree sums (composite inertia, subtree wrench)
+    LVARA(Real, IF, 6);
+    LANES_BEGIN
+    const int b = lane;
+    for (int i = 0; i < 6; i++) LVA(IF)[i] = 0;
+    if (b < NB) {
+        const Real *bf = m.body_f + b * BODYF;
+        const Real *R = w.xmat[b], *pos = w.xpos[b], *V = w.Vb[b], *A = w.Ab[b];
+        Real cl[3], c[3], I[10], T[9];
+        const Real ip[3] = {UHC_LDG(bf + 3), UHC_LDG(bf + 4), UHC_LDG(bf + 5)};
+        mv3(R, ip, cl);
+        for (int i = 0; i < 3; i++) { w.xipos[b][i] = pos[i] + cl[i]; c[i] = pos[i] + cl[i] - w.q[i]; }
+        const Real ms = UHC_LDG(bf + 6);
+        const Real i0 = UHC_LDG(bf + 7), i1 = UHC_LDG(bf + 8), i2 = UHC_LDG(bf + 9), i3 = UHC_LDG(bf + 10), i4 = UHC_LDG(bf + 11), i5 = UHC_LDG(bf + 12);
+        const Real Il[9] = {i0, i3, i4, i3, i1, i5, i4, i5, i2};
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) T[3 * i + j] = R[3 * i] * Il[j] + R[3 * i + 1] * Il[3 + j] + R[3 * i + 2] * Il[6 + j];
+        const Real cc = dot3(c, c);
+        const int ii[6] = {0, 1, 2, 0, 0, 1}, jj[6] = {0, 1, 2, 1, 2, 2};
+        I[0] = ms; I[1] = ms * c[0]; I[2] = ms * c[1]; I[3] = ms * c[2];
+        for (int e = 0; e < 6; e++) {
+            const int i = ii[e], j = jj[e];
+            I[4 + e] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2] + ms * ((i == j ? cc : Real(0)) - c[i] * c[j]);
+        }
+        Real IA[6], IV[6], t[3], t2[3];
+        rigid_mul(I, A, IA); rigid_mul(I, V, IV);
+        cross3(V, IV, t); cross3(V + 3, IV + 3, t2);   // V x* F = (w x n + v x f, w x f)
+        IA[0] += t[0] + t2[0]; IA[1] += t[1] + t2[1]; IA[2] += t[2] + t2[2];
+        cross3(V, IV + 3, t);
+        IA[3] += t[0]; IA[4] += t[1]; IA[5] += t[2];
+        for (int e = 0; e < 10; e++) w.Ib[b][e] = I[e];
+        for (int e = 0; e < 6; e++) LVA(IF)[e] = IA[e];
+    }
+    LANES_END
+    WSUBTREE(IF, 6, tp);
+    LANES_BEGIN
+    if (lane < NB) for (int e = 0; e < 6; e++) w.Fb[lane][e] = LVA(IF)[e];
+    LANES_END
 }
 
-// leaves -> root accumulation of n floats per body (parents gather their children), lane = body
-template <class Real>
-UHC_DEVNI void tree_gather(const Model<Real> &m, Real *X, int stride, int n) {
-    for (int lvl = MAXLEVEL - 1; lvl >= 0; --lvl) {
-        LANES_BEGIN
-        const int b = lane;
-        if (b < NB && UHC_LDG(m.depth + b) == lvl) {
-            const int c0 = UHC_LDG(m.child_adr + b), c1 = UHC_LDG(m.child_adr + b + 1);
-            for (int ci = c0; ci < c1; ++ci) {
-                const int c = UHC_LDG(m.child + ci);
-                for (int i = 0; i < n; i++) X[b * stride + i] += X[c * stride + i];
-            }
-        }
-        LANES_END
-    }
-}
 // per-body spatial vector  X_b = sum_{i on chain(b)} S_i x_i   (root -> leaves), lane = body
-template <class Real>
-UHC_DEVNI void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real (*X)[6]) {
-    for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
-        LANES_BEGIN
-        const int b = lane;
-        if (b < NB && UHC_LDG(m.depth + b) == lvl) {
-            Real V[6];
-            int d0, nd;
-            if (b == 0) { for (int i = 0; i < 6; i++) V[i] = 0; d0 = 0; nd = 6; }
-            else { const int p = UHC_LDG(m.parent + b); for (int i = 0; i < 6; i++) V[i] = X[p][i]; d0 = 6 + 3 * (b - 1); nd = 3; }
-            for (int j = 0; j < nd; ++j) { const Real xj = x[d0 + j]; for (int i = 0; i < 6; i++) V[i] += w.S[d0 + j][i] * xj; }
-            for (int i = 0; i < 6; i++) X[b][i] = V[i];
-        }
-        LANES_END
+template <class Real, class TPT>
+UHC_DEV void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real (*X)[6], const TPT &tp) {
+    LVARA(Real, V, 6);
+    LANES_BEGIN
+    const int b = lane;
+    for (int i = 0; i < 6; i++) LVA(V)[i] = 0;
+    if (b < NB) {
+        const int d0 = b == 0 ? 0 : 6 + 3 * (b - 1), nd = b == 0 ? 6 : 3;
+        for (int j = 0; j < nd; ++j) { const Real xj = x[d0 + j]; for (int i = 0; i < 6; i++) LVA(V)[i] += w.S[d0 + j][i] * xj; }
     }
+    LANES_END
+    WANCESTOR(V, 6, tp);
+    LANES_BEGIN
+    if (lane < NB) for (int i = 0; i < 6; i++) X[lane][i] = LVA(V)[i];
+    LANES_END
 }
 // y_i = S_i . Fsub[body(i)]  for all dofs, lane = dof
 template <class Real>
-UHC_DEVNI void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F)[6], Real *y, Real scale, const Real *add) {
+UHC_DEV void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F)[6], Real *y, Real scale, const Real *add) {
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) {
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
@@ -370,37 +531,17 @@ UHC_DEVNI void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F
     LANES_END
 }
 
-// CRBA: composite inertias (in w.Ic, 10 params) -> tree-sparse M (+ armature)
-template <class Real>
-UHC_DEVNI void crba(const Model<Real> &m, Work<Real> &w) {
-    tree_gather(m, &w.Ic[0][0], 21, 10);
-    LANES_BEGIN
-    for (int i = lane; i < NV; i += 32) {
-        const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        rigid_mul(w.Ic[b], w.S[i], w.scr + 6 * i);
-    }
-    LANES_END
-    LANES_BEGIN
-    for (int e = lane; e < NNZ; e += 32) {
-        const int r = UHC_LDG(m.ent_row + e), c = UHC_LDG(m.ent_col + e);
-        Real val = dot6(w.S[c], w.scr + 6 * r);
-        if (r == c) val += UHC_LDG(m.dof_f + 4 * r);
-        w.M[e] = val;
-    }
-    LANES_END
-}
-
 // ================================================================================================ collision
 // Floor plane z = 0 against each body hull (oracle/uhc_oracle.c or_collide states the manifold rule).
 template <class Real>
-UHC_DEVNI void collide(const Model<Real> &m, Work<Real> &w) {
+UHC_DEV void collide(const Model<Real> &m, Work<Real> &w) {
     int ncon = 0, upper = 0;
     for (int b = 0; b < NB; ++b) {
         w.bcon_adr[b] = ncon;  // uniform value, every lane writes the same (benign)
         const Real *bf = m.body_f + b * BODYF;
         const Real *R = w.xmat[b];
-        const Real cz = w.xpos[b][2] + R[6] * bf[14] + R[7] * bf[15] + R[8] * bf[16];
-        if (cz - bf[17] > m.margin || ncon + 4 > MAXCON) continue;
+        const Real cz = w.xpos[b][2] + R[6] * UHC_LDG(bf + 14) + R[7] * UHC_LDG(bf + 15) + R[8] * UHC_LDG(bf + 16);
+        if (cz - UHC_LDG(bf + 17) > m.margin || ncon + 4 > MAXCON) continue;
         const int adr = UHC_LDG(m.hull_adr + b), nvt = UHC_LDG(m.hull_num + b);
         LVAR(Real, bz); LVAR(int, bi);
         LANES_BEGIN
@@ -431,7 +572,8 @@ UHC_DEVNI void collide(const Model<Real> &m, Work<Real> &w) {
         while (mask && nc < 4) { int l = 0; while (!((mask >> l) & 1u)) l++; mask &= mask - 1; cand[nc++] = UHC_LDG(m.nbr + n0 + l); }
         LANES_BEGIN
         if (lane < nc) {
-            const Real *vv = m.hull + 3 * (adr + cand[lane]);
+            const int ci = lane == 0 ? cand[0] : lane == 1 ? cand[1] : lane == 2 ? cand[2] : cand[3];
+            const Real *vv = m.hull + 3 * (adr + ci);
             const Real v0 = UHC_LDG(vv), v1 = UHC_LDG(vv + 1), v2 = UHC_LDG(vv + 2);
             const Real px = w.xpos[b][0] + R[0] * v0 + R[1] * v1 + R[2] * v2;
             const Real py = w.xpos[b][1] + R[3] * v0 + R[4] * v1 + R[5] * v2;
@@ -451,16 +593,10 @@ UHC_DEVNI void collide(const Model<Real> &m, Work<Real> &w) {
 #endif
 }
 
-// pyramid edge directions d_e = n +- mu t  for n = +z, t1 = +y, t2 = -x
-template <class Real> UHC_DEV void edge_dir(int e, Real mu, Real *d) {
-    d[0] = e == 2 ? -mu : (e == 3 ? mu : Real(0));
-    d[1] = e == 0 ? mu : (e == 1 ? -mu : Real(0));
-    d[2] = 1;
-}
 
 // per-contact soft-constraint parameters (MuJoCo solref/solimp semantics), lane = contact
 template <class Real>
-UHC_DEVNI void constraint_setup(const Model<Real> &m, Work<Real> &w) {
+UHC_DEV void constraint_setup(const Model<Real> &m, Work<Real> &w) {
     const Real kk = Real(1) / (m.simp1 * m.simp1 * m.solref0 * m.solref0 * m.solref1 * m.solref1), bb = Real(2) / (m.simp1 * m.solref0);
     LANES_BEGIN
     for (int c = lane; c < w.ncon; c += 32) {
@@ -468,7 +604,8 @@ UHC_DEVNI void constraint_setup(const Model<Real> &m, Work<Real> &w) {
         const Real pos = w.cdist[c] - m.margin;
         Real x = abs_(pos) / m.simp2; if (x > 1) x = 1;
         Real y;
-        if (x < m.simp3) y = pow_(x / m.simp3, m.simp4) * m.simp3;
+        if (m.simp4 == Real(2)) y = x < m.simp3 ? x * x / m.simp3 : 1 - (1 - x) * (1 - x) / (1 - m.simp3);   // power 2 (the default)
+        else if (x < m.simp3) y = pow_(x / m.simp3, m.simp4) * m.simp3;
         else y = 1 - pow_((1 - x) / (1 - m.simp3), m.simp4) * (1 - m.simp3);
         const Real imp = m.simp0 + y * (m.simp1 - m.simp0);
         Real R0 = (1 - imp) * UHC_LDG(m.body_f + b * BODYF + 13) * (1 + m.mu * m.mu) / imp;
@@ -484,7 +621,7 @@ UHC_DEVNI void constraint_setup(const Model<Real> &m, Work<Real> &w) {
 
 // rows: out[c][e] = d_e . (point velocity of body spatial vector X at contact c), lane = contact
 template <class Real>
-UHC_DEVNI void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)[6], Real (*out)[4], const Real (*sub)[4]) {
+UHC_DEV void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)[6], Real (*out)[4], const Real (*sub)[4]) {
     LANES_BEGIN
     for (int c = lane; c < w.ncon; c += 32) {
         const int b = w.cbody[c]; Real u[3], t[3];
@@ -495,48 +632,49 @@ UHC_DEVNI void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)
     LANES_END
 }
 // body wrenches from per-row multipliers lam[c][e] (force on the body along d_e at the contact point), then subtree sums
-template <class Real, class F>
-UHC_DEV void contact_force(const Model<Real> &m, Work<Real> &w, F lam, Real (*Fo)[6]) {
+template <class Real, class F, class TPT>
+UHC_DEV void contact_force(const Model<Real> &m, Work<Real> &w, F lam, Real (*Fo)[6], const TPT &tp) {
+    LVARA(Real, acc, 6);
     LANES_BEGIN
     const int b = lane;
+    for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
     if (b < NB) {
-        Real acc[6] = {0, 0, 0, 0, 0, 0};
         for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
             Real f[3] = {0, 0, 0}, t[3];
             for (int e = 0; e < 4; e++) { Real d[3]; edge_dir(e, m.mu, d); const Real l = lam(c, e); f[0] += l * d[0]; f[1] += l * d[1]; f[2] += l * d[2]; }
             cross3(w.cr[c], f, t);
-            acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2]; acc[3] += f[0]; acc[4] += f[1]; acc[5] += f[2];
+            LVA(acc)[0] += t[0]; LVA(acc)[1] += t[1]; LVA(acc)[2] += t[2]; LVA(acc)[3] += f[0]; LVA(acc)[4] += f[1]; LVA(acc)[5] += f[2];
         }
-        for (int i = 0; i < 6; i++) Fo[b][i] = acc[i];
     }
     LANES_END
-    tree_gather(m, &Fo[0][0], 6, 6);
+    WSUBTREE(acc, 6, tp);
+    LANES_BEGIN
+    if (lane < NB) for (int i = 0; i < 6; i++) Fo[lane][i] = LVA(acc)[i];
+    LANES_END
 }
 
 // ================================================================================================ constraint solve
 // min_a 1/2 (a-a_s)^T M (a-a_s) + sum_rows 1/2 D min(0, J a - aref)^2 ; primal Newton, Hessian = M + J^T D_act J built as a
 // CRBA over contact-augmented composites, factorised tree-sparse (only the lower-body rows when no arm/head contact).
-template <class Real>
-UHC_DEVNI int newton_solve(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w) {
-    // cost of the two start candidates (warm start vs unconstrained)
+// newton_init: pick the start point (warm start vs unconstrained), residuals, M a.  Returns the gradient-norm scale.
+template <class Real, class TPT>
+UHC_DEV Real newton_init(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
     Real cost[2];
     for (int pass = 0; pass < 2; ++pass) {
         const Real *x = pass ? w.as_ : w.aw;
-        tree_vel(m, w, x, w.Ab);
+        tree_vel(m, w, x, w.Ab, tp);
         contact_rows(m, w, w.Ab, w.cjp, w.caref);
         LVAR(Real, part);
-        if (pass == 0) {  // M aw via body wrenches: Ma = sum_b J_b^T I_b (J_b aw) ; composite-free O(n) pass
+        if (pass == 0) {  // M aw = sum_b J_b^T I_b (J_b aw) + armature: O(n) pass with the per-body inertias
+            LVARA(Real, Fm, 6);
             LANES_BEGIN
-            const int b = lane;
-            if (b < NB) {
-                // rigid inertia of body b alone = composite(b) - sum composite(children)
-                Real I[10];
-                for (int e = 0; e < 10; e++) I[e] = w.Ic[b][e];
-                for (int ci = UHC_LDG(m.child_adr + b); ci < UHC_LDG(m.child_adr + b + 1); ++ci) { const int c = UHC_LDG(m.child + ci); for (int e = 0; e < 10; e++) I[e] -= w.Ic[c][e]; }
-                rigid_mul(I, w.Ab[b], w.Fb[b]);
-            }
+            for (int i = 0; i < 6; i++) LVA(Fm)[i] = 0;
+            if (lane < NB) rigid_mul(w.Ib[lane], w.Ab[lane], LVA(Fm));
             LANES_END
-            tree_gather(m, &w.Fb[0][0], 6, 6);
+            WSUBTREE(Fm, 6, tp);
+            LANES_BEGIN
+            if (lane < NB) for (int i = 0; i < 6; i++) w.Fb[lane][i] = LVA(Fm)[i];
+            LANES_END
             LANES_BEGIN
             for (int i = lane; i < NV; i += 32) {
                 const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
@@ -558,178 +696,72 @@ UHC_DEVNI int newton_solve(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<R
         }
     }
     const bool use_warm = cost[0] < cost[1];
+    LVAR(Real, part);
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) { w.a[i] = use_warm ? w.aw[i] : w.as_[i]; if (!use_warm) w.Ma[i] = w.fs[i]; }
     if (!use_warm) for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] = w.cjp[c][e];
+    LV(part) = lane < NB ? 3 * w.Ib[lane][0] : Real(0);   // gradient tolerance scale ~ trace of the translational block of M
     LANES_END
-
-    Real scale = 0;  // sum of diag(M): gradient tolerance scale
-    {
-        LVAR(Real, part);
-        LANES_BEGIN
-        Real s = 0;
-        for (int i = lane; i < NV; i += 32) s += w.M[UHC_LDG(m.madr + i) + UHC_LDG(m.dep + i)];
-        LV(part) = s;
-        LANES_END
-        scale = WSUM(part);
-    }
-    int it = 0;
-    for (; it < cfg.newton_max_iter; ++it) {
-        // gradient g = M a - f_s + J^T D r_-
-        contact_force(m, w, [&](int c, int e) { const Real r = w.cres[c][e]; return r < 0 ? w.cD[c] * r : Real(0); }, w.Fb);
-        LVAR(Real, part);
-        LANES_BEGIN
-        Real s = 0;
-        for (int i = lane; i < NV; i += 32) {
-            const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-            const Real gi = w.Ma[i] - w.fs[i] + dot6(w.S[i], w.Fb[b]);
-            w.g[i] = gi; w.p[i] = -gi; s += gi * gi;
-        }
-        LV(part) = s;
-        LANES_END
-        const Real gn = WSUM(part);
-        if (!(gn > cfg.newton_tol * cfg.newton_tol * scale * scale)) break;
-        // contact matrices K_b = sum_c X^T W X (own contacts), composites by gathering
-        LANES_BEGIN
-        const int b = lane;
-        if (b < NB) {
-            Real K[21];
-            for (int e = 0; e < 21; e++) K[e] = 0;
-            for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
-                Real W[6] = {0, 0, 0, 0, 0, 0};  // xx yy zz xy xz yz
-                for (int e = 0; e < 4; e++) if (w.cres[c][e] < 0) {
-                    Real d[3]; edge_dir(e, m.mu, d); const Real D = w.cD[c];
-                    W[0] += D * d[0] * d[0]; W[1] += D * d[1] * d[1]; W[2] += D * d[2] * d[2];
-                    W[3] += D * d[0] * d[1]; W[4] += D * d[0] * d[2]; W[5] += D * d[1] * d[2];
-                }
-                const Real Wm[9] = {W[0], W[3], W[4], W[3], W[1], W[5], W[4], W[5], W[2]};
-                const Real *r = w.cr[c];
-                // u = v + w x r = G w + v, G = -[r]x ; X = [G 1]
-                const Real G[9] = {0, r[2], -r[1], -r[2], 0, r[0], r[1], -r[0], 0};
-                Real WG[9], GtWG[9];
-                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) WG[3 * i + j] = Wm[3 * i] * G[j] + Wm[3 * i + 1] * G[3 + j] + Wm[3 * i + 2] * G[6 + j];
-                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) GtWG[3 * i + j] = G[i] * WG[j] + G[3 + i] * WG[3 + j] + G[6 + i] * WG[6 + j];
-                for (int i = 0; i < 3; i++) for (int j = i; j < 3; j++) { K[sym6(i, j)] += GtWG[3 * i + j]; K[sym6(3 + i, 3 + j)] += Wm[3 * i + j]; }
-                for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) K[sym6(i, 3 + j)] += WG[3 * j + i];  // (G^T W)[i][j] = WG[j][i]
-            }
-            for (int e = 0; e < 21; e++) w.Ic[b][e] = K[e];
-        }
-        LANES_END
-        tree_gather(m, &w.Ic[0][0], 21, 21);
-        const int nrow = w.upper_contact ? NV : NLOW, nent = w.upper_contact ? NNZ : NNZ_LOW;
-        LANES_BEGIN
-        for (int i = lane; i < nrow; i += 32) { const int b = i < 6 ? 0 : 1 + (i - 6) / 3; sym6_mul(w.Ic[b], w.S[i], w.scr + 6 * i); }
-        LANES_END
-        LANES_BEGIN
-        for (int e = lane; e < nent; e += 32) {
-            const int r = UHC_LDG(m.ent_row + e), c = UHC_LDG(m.ent_col + e);
-            w.H[e] = (w.upper_contact ? w.M[e] : w.Mt[e]) + dot6(w.S[c], w.scr + 6 * r);
-        }
-        LANES_END
-        ldl_factor(m, w.H, w.dinv, nrow - 1, 1);
-        LANES_BEGIN
-        if (lane == 0) w.dinv[0] = Real(1) / w.H[0];
-        LANES_END
-        ldl_solve(m, w.H, w.dinv, w.p);
-        // J p, M p = -g - J^T D_act (J p)
-        tree_vel(m, w, w.p, w.Ab);
-        contact_rows(m, w, w.Ab, w.cjp, (const Real (*)[4]) nullptr);
-        contact_force(m, w, [&](int c, int e) { return w.cres[c][e] < 0 ? w.cD[c] * w.cjp[c][e] : Real(0); }, w.Fb);
-        LVAR(Real, pa); LVAR(Real, pb);
-        LANES_BEGIN
-        Real sA = 0, sB = 0;
-        for (int i = lane; i < NV; i += 32) {
-            const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-            const Real mp = -w.g[i] - dot6(w.S[i], w.Fb[b]);
-            w.Mp[i] = mp; sA += (w.Ma[i] - w.fs[i]) * w.p[i]; sB += mp * w.p[i];
-        }
-        LV(pa) = sA; LV(pb) = sB;
-        LANES_END
-        const Real A0 = WSUM(pa), B0 = WSUM(pb);
-        // 1-D safeguarded Newton on f'(al) = A0 + al B0 + sum_rows D (r + al jp)_- jp   (piecewise linear, increasing)
-        Real lo = 0, hi = -1, al = 1;
-        for (int ls = 0; ls < 12; ++ls) {
-            LVAR(Real, d1); LVAR(Real, d2);
-            LANES_BEGIN
-            Real s1 = 0, s2 = 0;
-            for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) {
-                const Real r = w.cres[c][e] + al * w.cjp[c][e];
-                if (r < 0) { s1 += w.cD[c] * r * w.cjp[c][e]; s2 += w.cD[c] * w.cjp[c][e] * w.cjp[c][e]; }
-            }
-            LV(d1) = s1; LV(d2) = s2;
-            LANES_END
-            const Real f1 = A0 + al * B0 + WSUM(d1), f2 = B0 + WSUM(d2);
-            if (f1 > 0) hi = al; else lo = al;
-            if (abs_(f1) <= Real(1e-6) * abs_(A0) + Real(1e-30)) break;
-            Real nx = al - f1 / f2;
-            if (!(nx > lo) || (hi > 0 && !(nx < hi))) nx = hi > 0 ? Real(0.5) * (lo + hi) : 2 * al;
-            if (nx == al) break;
-            al = nx;
-        }
-        LANES_BEGIN
-        for (int i = lane; i < NV; i += 32) { w.a[i] += al * w.p[i]; w.Ma[i] += al * w.Mp[i]; }
-        for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] += al * w.cjp[c][e];
-        LANES_END
-    }
-    return it;
+    return WSUM(part);
 }
-
-// ================================================================================================ one physics substep
-// mj_forward (position, velocity, actuation, acceleration, constraint) at the current (q, v), then semi-implicit Euler.
-// `tau` holds the 69 joint torques, fapp the 6 root residual forces.  Leaves M, C, xpos/xmat/xipos of THIS (pre-integration)
-// configuration in the work set -- the staleness MuJoCo exposes to the Python side (SURVEY.md section 7 "stale dynamics").
-template <class Real>
-UHC_DEVNI int forward_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const Real *fapp, bool have_tau) {
-    kin_rne_forward(m, w);
-    tree_gather(m, &w.Fb[0][0], 6, 6);
-    project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
-    crba(m, w);
-    collide(m, w);
-    // smooth acceleration a_s = M^-1 (tau + f_applied - C)
+// newton_prepare: gradient at the current point; returns false when converged, else leaves -g in w.p
+template <class Real, class TPT>
+UHC_DEV bool newton_prepare(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, Real scale, const TPT &tp) {
+    contact_force(m, w, [&](int c, int e) { const Real r = w.cres[c][e]; return r < 0 ? w.cD[c] * r : Real(0); }, w.Fb, tp);
+    LVAR(Real, part);
     LANES_BEGIN
+    Real s = 0;
     for (int i = lane; i < NV; i += 32) {
-        const Real f = (i < 6 ? fapp[i] : (have_tau ? w.tau[i - 6] : Real(0))) - w.C[i];
-        w.fs[i] = f; w.as_[i] = f;
+        const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
+        const Real gi = w.Ma[i] - w.fs[i] + dot6(w.S[i], w.Fb[b]);
+        w.g[i] = gi; w.p[i] = -gi; s += gi * gi;
     }
-    for (int e = lane; e < NNZ; e += 32) w.H[e] = w.M[e];
+    LV(part) = s;
     LANES_END
-    ldl_factor(m, w.H, w.dinv, NV - 1, NLOW);
-    LANES_BEGIN
-    for (int e = lane; e < NNZ_LOW; e += 32) w.Mt[e] = w.H[e];  // lower rows after the arm/head Schur complement
-    LANES_END
-    ldl_factor(m, w.H, w.dinv, NLOW - 1, 1);
-    LANES_BEGIN
-    if (lane == 0) w.dinv[0] = Real(1) / w.H[0];
-    LANES_END
-    ldl_solve(m, w.H, w.dinv, w.as_);
-    int iters = 0;
-    if (w.ncon > 0) {
-        constraint_setup(m, w);
-        iters = newton_solve(m, cfg, w);
-    } else {
-        LANES_BEGIN
-        for (int i = lane; i < NV; i += 32) w.a[i] = w.as_[i];
-        LANES_END
-    }
-    return iters;
+    const Real gn = WSUM(part);
+    if (!(gn > cfg.newton_tol * cfg.newton_tol * scale * scale)) return false;
+    return true;
 }
-
-template <class Real>
-UHC_DEVNI void integrate(const Model<Real> &m, Work<Real> &w) {
-    const Real dt = m.dt;
+// newton_advance: given the Newton direction in w.p: J p, M p, exact-ish line search, update a / M a / residuals
+template <class Real, class TPT>
+UHC_DEV void newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
+    tree_vel(m, w, w.p, w.Ab, tp);
+    contact_rows(m, w, w.Ab, w.cjp, (const Real (*)[4]) nullptr);
+    contact_force(m, w, [&](int c, int e) { return w.cres[c][e] < 0 ? w.cD[c] * w.cjp[c][e] : Real(0); }, w.Fb, tp);
+    LVAR(Real, pa); LVAR(Real, pb);
     LANES_BEGIN
-    for (int i = lane; i < NV; i += 32) { const Real vn = w.v[i] + dt * w.a[i]; w.v[i] = vn; w.aw[i] = w.a[i]; if (i >= 6) w.q[i + 1] += dt * vn; }
-    LANES_END
-    LANES_BEGIN
-    if (lane < 3) w.q[lane] += dt * w.v[lane];
-    if (lane == 3) {
-        const Real wx = w.v[3], wy = w.v[4], wz = w.v[5], n = sqrt(wx * wx + wy * wy + wz * wz), ang = n * dt;
-        Real dq[4] = {1, 0, 0, 0}, qn[4], qo[4] = {w.q[3], w.q[4], w.q[5], w.q[6]};
-        if (ang > Real(1e-30)) { Real sn, cs; sincos_(Real(0.5) * ang, &sn, &cs); const Real s = sn / n; dq[0] = cs; dq[1] = wx * s; dq[2] = wy * s; dq[3] = wz * s; }
-        qmul(qo, dq, qn);
-        const Real nn = rsqrt_(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
-        for (int i = 0; i < 4; i++) w.q[3 + i] = qn[i] * nn;
+    Real sA = 0, sB = 0;
+    for (int i = lane; i < NV; i += 32) {
+        const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
+        const Real mp = -w.g[i] - dot6(w.S[i], w.Fb[b]);
+        w.Mp[i] = mp; sA += (w.Ma[i] - w.fs[i]) * w.p[i]; sB += mp * w.p[i];
     }
+    LV(pa) = sA; LV(pb) = sB;
+    LANES_END
+    const Real A0 = WSUM(pa), B0 = WSUM(pb);
+    // 1-D safeguarded Newton on f'(al) = A0 + al B0 + sum_rows D (r + al jp)_- jp   (piecewise linear, increasing)
+    Real lo = 0, hi = -1, al = 1;
+    for (int ls = 0; ls < 12; ++ls) {
+        LVAR(Real, d1); LVAR(Real, d2);
+        LANES_BEGIN
+        Real s1 = 0, s2 = 0;
+        for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) {
+            const Real r = w.cres[c][e] + al * w.cjp[c][e];
+            if (r < 0) { s1 += w.cD[c] * r * w.cjp[c][e]; s2 += w.cD[c] * w.cjp[c][e] * w.cjp[c][e]; }
+        }
+        LV(d1) = s1; LV(d2) = s2;
+        LANES_END
+        const Real f1 = A0 + al * B0 + WSUM(d1), f2 = B0 + WSUM(d2);
+        if (f1 > 0) hi = al; else lo = al;
+        if (abs_(f1) <= Real(1e-6) * abs_(A0) + Real(1e-30)) break;
+        Real nx = al - f1 / f2;
+        if (!(nx > lo) || (hi > 0 && !(nx < hi))) nx = hi > 0 ? Real(0.5) * (lo + hi) : 2 * al;
+        if (nx == al) break;
+        al = nx;
+    }
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) { w.a[i] += al * w.p[i]; w.Ma[i] += al * w.Mp[i]; }
+    for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] += al * w.cjp[c][e];
     LANES_END
 }
 
@@ -754,12 +786,17 @@ template <class Real> UHC_DEV void euler_zyx_quat(Real e0, Real e1, Real e2, Rea
 constexpr double PI_D = 3.14159265358979323846;
 
 // stable PD torque for substep `it` (humanoid_im.py:1033-1076 + :1014-1031): uses the M, C currently in the work set
-// (= previous forward pass) with the current q, v; leaves the clipped torques in w.tau (:1160).
+// (= previous forward pass: per-body inertias w.Ib, motion subspaces w.S, bias w.C) with the current q, v.  pd_setup leaves the right-hand side in w.p;
+// after the shared L^T D L solve pd_finish turns the acceleration into clipped torques in w.tau (:1160).
 template <class Real>
-UHC_DEVNI void pd_torque(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const Real *target, int it) {
+UHC_DEV void pd_gains(const EnvCfg<Real> &cfg, const Work<Real> &w, int it, Real *sp, Real *sd) {
+    *sp = 1; *sd = 1;
+    if (cfg.meta_pd) { *sp = clamp_(w.act[NU + 6 + it] + 1, Real(0), Real(10)); *sd = clamp_(w.act[NU + 6 + it + NSUB] + 1, Real(0), Real(10)); }
+}
+template <class Real>
+UHC_DEV void pd_setup(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const Real *target, int it) {
     const Real dt = m.dt;
-    Real sp = 1, sd = 1;
-    if (cfg.meta_pd) { sp = clamp_(w.act[NU + 6 + it] + 1, Real(0), Real(10)); sd = clamp_(w.act[NU + 6 + it + NSUB] + 1, Real(0), Real(10)); }
+    Real sp, sd; pd_gains(cfg, w, it, &sp, &sd);
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) {
         Real rhs = -w.C[i];
@@ -775,23 +812,18 @@ UHC_DEVNI void pd_torque(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Rea
         }
         w.p[i] = rhs;
     }
-    for (int e = lane; e < NNZ; e += 32) {
-        const int r = UHC_LDG(m.ent_row + e);
-        Real val = w.M[e];
-        if (r >= 6 && r == UHC_LDG(m.ent_col + e)) val += UHC_LDG(m.dof_f + 4 * r + 2) * sd * dt;
-        w.H[e] = val;
-    }
     LANES_END
-    ldl_factor(m, w.H, w.dinv, NV - 1, 1);
-    LANES_BEGIN
-    if (lane == 0) w.dinv[0] = Real(1) / w.H[0];
-    LANES_END
-    ldl_solve(m, w.H, w.dinv, w.p);
+}
+template <class Real, class OutT>
+UHC_DEV void pd_finish(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, int it, OutT *torque_out) {
+    const Real dt = m.dt;
+    Real sp, sd; pd_gains(cfg, w, it, &sp, &sd);
     LANES_BEGIN
     for (int i = 6 + lane; i < NV; i += 32) {
         const Real kp = UHC_LDG(m.dof_f + 4 * i + 1) * sp, kd = UHC_LDG(m.dof_f + 4 * i + 2) * sd, lim = UHC_LDG(m.dof_f + 4 * i + 3);
-        const Real t = -kp * w.g[i] - kd * (w.v[i] + w.p[i] * dt);
-        w.tau[i - 6] = clamp_(t, -lim, lim);
+        const Real t = clamp_(-kp * w.g[i] - kd * (w.v[i] + w.p[i] * dt), -lim, lim);
+        w.tau[i - 6] = t;
+        if (torque_out) torque_out[it * NU + i - 6] = (OutT)t;
     }
     LANES_END
 }
@@ -803,6 +835,82 @@ UHC_DEV void rfc_implicit(const EnvCfg<Real> &cfg, const Work<Real> &w, Real *fa
     remove_base_rot(cfg, w.q + 3, crq); heading_q(crq, hq); q2mat(hq, R); mv3(R, vf, t);
     vf[0] = t[0]; vf[1] = t[1]; vf[2] = t[2];
     for (int i = 0; i < 6; i++) fapp[i] = clamp_(vf[i], -cfg.rfc_lim, cfg.rfc_lim);
+}
+
+template <class Real>
+UHC_DEV void integrate(const Model<Real> &m, Work<Real> &w) {
+    const Real dt = m.dt;
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) { const Real vn = w.v[i] + dt * w.a[i]; w.v[i] = vn; w.aw[i] = w.a[i]; if (i >= 6) w.q[i + 1] += dt * vn; }
+    LANES_END
+    LANES_BEGIN
+    if (lane < 3) w.q[lane] += dt * w.v[lane];
+    if (lane == 3) {
+        const Real wx = w.v[3], wy = w.v[4], wz = w.v[5], n = sqrt(wx * wx + wy * wy + wz * wz), ang = n * dt;
+        Real dq[4] = {1, 0, 0, 0}, qn[4], qo[4] = {w.q[3], w.q[4], w.q[5], w.q[6]};
+        if (ang > Real(1e-30)) { Real sn, cs; sincos_(Real(0.5) * ang, &sn, &cs); const Real s = sn / n; dq[0] = cs; dq[1] = wx * s; dq[2] = wy * s; dq[3] = wz * s; }
+        qmul(qo, dq, qn);
+        const Real nn = rsqrt_(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+        for (int i = 0; i < 4; i++) w.q[3 + i] = qn[i] * nn;
+    }
+    LANES_END
+}
+
+// ================================================================================================ one physics substep
+// [stable-PD torque] -> mj_forward (position, velocity, actuation, acceleration, constraint) at the current (q, v).
+// The three linear solves of a substep (PD: M_stale + Kd dt ; smooth: M ; Newton: M + J^T D J) run through ONE copy of the
+// articulated-body solve: a small phase machine sets up the right-hand side, the shared solve runs, the phase post-processes.  Leaves M, C, xpos/xmat/xipos of THIS (pre-integration) configuration in the work set -- the staleness MuJoCo
+// exposes to the Python side (SURVEY.md section 7 "stale dynamics").  with_pd = false: reset path (sim.forward with ctrl = 0).
+enum { PH_PD = 0, PH_SMOOTH = 1, PH_NEWTON = 2 };
+template <class Real, class OutT, class TPT>
+UHC_DEV int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const TPT &tp, const Real *target, int it,
+                             bool with_pd, OutT *torque_out) {
+    int phase = with_pd ? PH_PD : PH_SMOOTH, iters = 0;
+    Real scale = 0;
+    for (;;) {
+        // ---- phase set-up: right-hand side into the vector the solve runs on
+        Real *rhs = w.p;
+        Real arm_scale = 0;
+        if (phase == PH_PD) {
+            pd_setup(m, cfg, w, target, it);
+            Real sp, sd; pd_gains(cfg, w, it, &sp, &sd);
+            arm_scale = sd * m.dt;
+        } else if (phase == PH_SMOOTH) {
+            Real fapp[6] = {0, 0, 0, 0, 0, 0};
+            if (with_pd) rfc_implicit(cfg, w, fapp);
+            kin_rne_forward(m, w, tp);
+            project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
+            collide(m, w);
+            LANES_BEGIN
+            for (int i = lane; i < NV; i += 32) {  // smooth acceleration a_s = M^-1 (tau + f_applied - C)
+                Real f = -w.C[i];
+                if (i < 6) { const Real fa = i == 0 ? fapp[0] : i == 1 ? fapp[1] : i == 2 ? fapp[2] : i == 3 ? fapp[3] : i == 4 ? fapp[4] : fapp[5]; f += fa; }
+                else if (with_pd) f += w.tau[i - 6];
+                w.fs[i] = f; w.as_[i] = f;
+            }
+            LANES_END
+            rhs = w.as_;
+        } else {
+            if (iters >= cfg.newton_max_iter || !newton_prepare(m, cfg, w, scale, tp)) break;
+            ++iters;
+        }
+        // ---- the one shared O(n) articulated-body solve
+        aba_solve(m, w, tp, arm_scale, phase == PH_NEWTON, rhs);
+        // ---- phase post-processing
+        if (phase == PH_PD) { pd_finish(m, cfg, w, it, torque_out); phase = PH_SMOOTH; }
+        else if (phase == PH_SMOOTH) {
+            if (w.ncon == 0) {
+                LANES_BEGIN
+                for (int i = lane; i < NV; i += 32) w.a[i] = w.as_[i];
+                LANES_END
+                break;
+            }
+            constraint_setup(m, w);
+            scale = newton_init(m, w, tp);
+            phase = PH_NEWTON;
+        } else newton_advance(m, w, tp);
+    }
+    return iters;
 }
 
 // body quaternions from qpos (humanoid_im.py:925-947), lane = body

@@ -14,7 +14,7 @@ static thread_local std::string g_err;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
 
 template <class Real, int EPB>
-__global__ void __launch_bounds__(32 * EPB)
+__global__ void __launch_bounds__(32 * EPB, (sizeof(Real) == 4 ? 4 : 1))
 k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict__ obs, float *__restrict__ rew, float *__restrict__ cinfo,
            int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -37,7 +37,7 @@ k_env_reset(EngineView<Real> ev, int n, const int *__restrict__ ids, const int *
     const int env = ids[i];
     // optional overrides arrive as float; stage them through the work set's scratch vectors
     Real *qo = nullptr, *vo = nullptr;
-    if (qpos) { qo = w.scr; vo = w.scr + 80; const int lane = threadIdx.x & 31;
+    if (qpos) { qo = w.Ma; vo = w.Mp; const int lane = threadIdx.x & 31;   // vectors untouched before the reset copies them out
         for (int k = lane; k < NQ; k += 32) qo[k] = (Real)qpos[(size_t)i * NQ + k];
         for (int k = lane; k < NV; k += 32) vo[k] = qvel ? (Real)qvel[(size_t)i * NV + k] : Real(0);
         __syncwarp(); }
@@ -82,8 +82,8 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     short *ps; if (dev_copy(e, &ps, m->rowadr, (size_t)NV * 32)) return -1; M.rowadr = ps;
     unsigned char *pc;
     if (dev_copy(e, &pc, m->colidx, (size_t)NV * 32)) return -1; M.colidx = pc;
-    if (dev_copy(e, &pc, m->ent_row, (size_t)NNZ)) return -1; M.ent_row = pc;
-    if (dev_copy(e, &pc, m->ent_col, (size_t)NNZ)) return -1; M.ent_col = pc;
+    if (dev_copy(e, &pc, m->ent_row, (size_t)1221)) return -1; M.ent_row = pc;
+    if (dev_copy(e, &pc, m->ent_col, (size_t)1221)) return -1; M.ent_col = pc;
     M.dt = (Real)m->dt; M.margin = (Real)m->margin; M.mu = (Real)m->mu; M.solref0 = (Real)m->solref[0]; M.solref1 = (Real)m->solref[1];
     M.simp0 = (Real)m->solimp[0]; M.simp1 = (Real)m->solimp[1]; M.simp2 = (Real)m->solimp[2]; M.simp3 = (Real)m->solimp[3]; M.simp4 = (Real)m->solimp[4];
     M.gravz = (Real)m->gravz;
