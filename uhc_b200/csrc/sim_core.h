@@ -89,6 +89,7 @@ struct Work {
     Real xpos[NB][3], xmat[NB][9], xipos[NB][3], xquat[NB][4];
     Real S[NV][6];
     Real Ib[NB][10];              // per-body rigid inertia about O, world axes (of the last forward pass)
+    Real aU[NV][6], aDinv[NV + 1], au[NV + 1];   // articulated-body sweep: U_j = IA S_j, 1 / D_j, u_j
     Real C[NV + 1], fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
     Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
     // contacts
@@ -100,7 +101,20 @@ struct Work {
 // ------------------------------------------------------------------------------------------------ scalar helpers
 UHC_DEV float rsqrt_(float x) { return 1.0f / sqrtf(x); }
 UHC_DEV double rsqrt_(double x) { return 1.0 / sqrt(x); }
-UHC_DEV void sincos_(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
+// compact sin/cos (Cody-Waite reduction by pi/2, degree-7/8 minimax polynomials; |err| < 2e-7 for |x| < 1e3) -- joint angles and
+// half-angles only; keeps the hot loop free of libdevice's large-argument slow paths
+UHC_DEV void sincos_(float x, float *s, float *c) {
+    const float k = rintf(x * 0.63661977236758134f);
+    float r = fmaf(k, -1.5707962512969971f, x);
+    r = fmaf(k, -7.5497894158615964e-8f, r);
+    const float r2 = r * r;
+    const float sp = r * fmaf(r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), 1.0f);
+    const float cp = fmaf(r2, fmaf(r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f), -0.5f), 1.0f);
+    const int q = (int)k & 3;
+    const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+    *s = (q & 2) ? -ss : ss;
+    *c = ((q + 1) & 2) ? -cc : cc;
+}
 UHC_DEV void sincos_(double x, double *s, double *c) { *s = sin(x); *c = cos(x); }
 UHC_DEV float acos_(float x) { return acosf(x); }
 UHC_DEV double acos_(double x) { return acos(x); }
@@ -108,7 +122,7 @@ UHC_DEV float exp_(float x) { return expf(x); }
 UHC_DEV double exp_(double x) { return exp(x); }
 UHC_DEV float abs_(float x) { return fabsf(x); }
 UHC_DEV double abs_(double x) { return fabs(x); }
-UHC_DEV float pow_(float x, float y) { return powf(x, y); }
+UHC_DEV float pow_(float x, float y) { return exp2f(y * log2f(x)); }
 UHC_DEV double pow_(double x, double y) { return pow(x, y); }
 template <class R> UHC_DEV R min_(R a, R b) { return a < b ? a : b; }
 template <class R> UHC_DEV R max_(R a, R b) { return a > b ? a : b; }
@@ -166,7 +180,13 @@ template <class R> UHC_DEV void rigid_mul(const R *I, const R *S, R *F) {
 // packed symmetric 6x6 (21: row-major upper triangle) times vector
 UHC_DEV int sym6(int i, int j) { if (i > j) { int t = i; i = j; j = t; } return i * 6 - (i * (i - 1)) / 2 + (j - i); }
 template <class R> UHC_DEV void sym6_mul(const R *K, const R *x, R *y) {
-    for (int i = 0; i < 6; i++) { R s = 0; for (int j = 0; j < 6; j++) s += K[sym6(i, j)] * x[j]; y[i] = s; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        R s = 0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) s += K[sym6(i, j)] * x[j];
+        y[i] = s;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ warp primitives
@@ -247,7 +267,7 @@ UHC_DEV LaneTopo lane_topo(const Model<Real> &m, int lane) {
 #define TP tp
 // parents at depth `lvl` add their children's K floats (children sit at lvl + 1)
 template <class R, int K> UHC_DEV void gather_children(R (&x)[K], const LaneTopo &tp, int lvl) {
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 3; r++) {
         const int src = r == 0 ? tp.ch0 : (r == 1 ? tp.ch1 : tp.ch2);
         const bool act = tp.depth == lvl && src >= 0;
@@ -308,14 +328,18 @@ UHC_DEV void contact_matrix(const Model<Real> &m, const Work<Real> &w, int b, Re
 
 // eliminate one joint dof from the articulated pair (IA, pA):  U = IA S, D = S.U + arm, u = b - S.pA ; IA -= U U^T / D ; pA += U u / D
 template <class Real>
-UHC_DEV void aba_eliminate(Real *IA, Real *pA, const Real *S, Real arm, Real bj, Real *U, Real *Dinv, Real *uo) {
-    sym6_mul(IA, S, U);
-    const Real D = dot6(S, U) + arm, di = Real(1) / D, u = bj - dot6(S, pA);
+UHC_DEV void aba_eliminate(Real *IA, Real *pA, const Real *S, Real arm, Real bj, Real *Uout, Real *Dinv, Real *uo) {
+    Real U[6], Sv[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) Sv[i] = S[i];
+    sym6_mul(IA, Sv, U);
+    const Real D = dot6(Sv, U) + arm, di = Real(1) / D, u = bj - dot6(Sv, pA);
     *Dinv = di; *uo = u;
     const Real ud = u * di;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         const Real Ui = U[i] * di;
+        Uout[i] = U[i];
 #pragma unroll
         for (int j = i; j < 6; j++) IA[sym6(i, j)] -= Ui * U[j];
         pA[i] += U[i] * ud;
@@ -324,12 +348,11 @@ UHC_DEV void aba_eliminate(Real *IA, Real *pA, const Real *S, Real arm, Real bj,
 
 // x <- H^-1 x  (x: 75-vector in shared memory).  arm_scale: extra joint-space diagonal = arm_scale * kd_i (0 for none).
 template <class Real, class TPT>
-UHC_DEV void aba_solve(const Model<Real> &m, Work<Real> &w, const TPT &tp, Real arm_scale, bool use_contacts, Real *x) {
+UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, const TPT &tp, Real arm_scale, bool use_contacts, Real *x) {
     LVARA(Real, IP, 27);      // articulated inertia (21, packed symmetric) + bias wrench (6)
-    LVARA(Real, U, 36);       // U_j (6 each) of this lane's dofs (6 for the root, 3 otherwise)
-    LVARA(Real, DU, 12);      // 1/D_j, u_j
     LANES_BEGIN
     const int b = lane;
+#pragma unroll
     for (int i = 0; i < 27; i++) LVA(IP)[i] = 0;
     if (b < NB) {
         const Real *I = w.Ib[b];   // rigid (m, h, J) -> packed symmetric 6x6 in (w, v) ordering
@@ -341,24 +364,18 @@ UHC_DEV void aba_solve(const Model<Real> &m, Work<Real> &w, const TPT &tp, Real 
         if (use_contacts) contact_matrix(m, w, b, A);
     }
     LANES_END
+#pragma unroll 1
     for (int lvl = MAXLEVEL; lvl >= 0; --lvl) {
         WGATHER(IP, 27, tp, lvl);
         LANES_BEGIN
         const int b = lane;
         if (b < NB && TP.depth == lvl) {
-            if (b == 0) {
-#pragma unroll
-                for (int j = 5; j >= 0; --j) {
-                    const Real arm = UHC_LDG(m.dof_f + 4 * j) + arm_scale * UHC_LDG(m.dof_f + 4 * j + 2);
-                    aba_eliminate(LVA(IP), LVA(IP) + 21, w.S[j], arm, x[j], LVA(U) + 6 * j, &LVA(DU)[j], &LVA(DU)[6 + j]);
-                }
-            } else {
-                const int d0 = 6 + 3 * (b - 1);
-#pragma unroll
-                for (int j = 2; j >= 0; --j) {
-                    const Real arm = UHC_LDG(m.dof_f + 4 * (d0 + j)) + arm_scale * UHC_LDG(m.dof_f + 4 * (d0 + j) + 2);
-                    aba_eliminate(LVA(IP), LVA(IP) + 21, w.S[d0 + j], arm, x[d0 + j], LVA(U) + 6 * j, &LVA(DU)[j], &LVA(DU)[6 + j]);
-                }
+            const int d0 = b == 0 ? 0 : 6 + 3 * (b - 1), nd = b == 0 ? 6 : 3;
+#pragma unroll 1
+            for (int j = nd - 1; j >= 0; --j) {
+                const int dof = d0 + j;
+                const Real arm = UHC_LDG(m.dof_f + 4 * dof) + arm_scale * UHC_LDG(m.dof_f + 4 * dof + 2);
+                aba_eliminate(LVA(IP), LVA(IP) + 21, w.S[dof], arm, x[dof], w.aU[dof], &w.aDinv[dof], &w.au[dof]);
             }
         }
         LANES_END
@@ -366,28 +383,25 @@ UHC_DEV void aba_solve(const Model<Real> &m, Work<Real> &w, const TPT &tp, Real 
     // root -> leaves: x_j = (u_j - U_j . a) / D_j ; a += S_j x_j
     LVARA(Real, acc, 6); LVARA(Real, ap, 6);
     LANES_BEGIN
-    for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
-    if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            const Real xj = (LVA(DU)[6 + j] - dot6(LVA(U) + 6 * j, LVA(acc))) * LVA(DU)[j];
-            x[j] = xj;
-            for (int i = 0; i < 6; i++) LVA(acc)[i] += w.S[j][i] * xj;
-        }
-    }
+    for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
     LANES_END
-    for (int lvl = 1; lvl <= MAXLEVEL; ++lvl) {
+#pragma unroll 1
+    for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
         WFETCHP(acc, ap, 6, tp);
         LANES_BEGIN
         const int b = lane;
         if (b < NB && TP.depth == lvl) {
-            const int d0 = 6 + 3 * (b - 1);
-            for (int i = 0; i < 6; i++) LVA(acc)[i] = LVA(ap)[i];
+            const int d0 = b == 0 ? 0 : 6 + 3 * (b - 1), nd = b == 0 ? 6 : 3;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const Real xj = (LVA(DU)[6 + j] - dot6(LVA(U) + 6 * j, LVA(acc))) * LVA(DU)[j];
-                x[d0 + j] = xj;
-                for (int i = 0; i < 6; i++) LVA(acc)[i] += w.S[d0 + j][i] * xj;
+            for (int i = 0; i < 6; i++) LVA(acc)[i] = b == 0 ? Real(0) : LVA(ap)[i];
+#pragma unroll 1
+            for (int j = 0; j < nd; ++j) {
+                const int dof = d0 + j;
+                const Real xj = (w.au[dof] - dot6(w.aU[dof], LVA(acc))) * w.aDinv[dof];
+                x[dof] = xj;
+#pragma unroll
+                for (int i = 0; i < 6; i++) LVA(acc)[i] += w.S[dof][i] * xj;
             }
         }
         LANES_END
@@ -505,7 +519,7 @@ UHC_DEV void kin_rne_forward(const Model<Real> &m, Work<Real> &w, const TPT &tp)
 
 // per-body spatial vector  X_b = sum_{i on chain(b)} S_i x_i   (root -> leaves), lane = body
 template <class Real, class TPT>
-UHC_DEV void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real (*X)[6], const TPT &tp) {
+UHC_DEVNI void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real (*X)[6], const TPT &tp) {
     LVARA(Real, V, 6);
     LANES_BEGIN
     const int b = lane;
@@ -621,7 +635,7 @@ UHC_DEV void constraint_setup(const Model<Real> &m, Work<Real> &w) {
 
 // rows: out[c][e] = d_e . (point velocity of body spatial vector X at contact c), lane = contact
 template <class Real>
-UHC_DEV void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)[6], Real (*out)[4], const Real (*sub)[4]) {
+UHC_DEVNI void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)[6], Real (*out)[4], const Real (*sub)[4]) {
     LANES_BEGIN
     for (int c = lane; c < w.ncon; c += 32) {
         const int b = w.cbody[c]; Real u[3], t[3];
@@ -631,17 +645,25 @@ UHC_DEV void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)[6
     }
     LANES_END
 }
-// body wrenches from per-row multipliers lam[c][e] (force on the body along d_e at the contact point), then subtree sums
-template <class Real, class F, class TPT>
-UHC_DEV void contact_force(const Model<Real> &m, Work<Real> &w, F lam, Real (*Fo)[6], const TPT &tp) {
+// body wrenches from per-row multipliers (force on the body along d_e at the contact point), then subtree sums.
+// mode 0: lam = D r_-  (gradient term J^T D r_-) ; mode 1: lam = D [r<0] jp  (J^T D_act J p)
+template <class Real, class TPT>
+UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real (*Fo)[6], const TPT &tp) {
     LVARA(Real, acc, 6);
     LANES_BEGIN
     const int b = lane;
+#pragma unroll
     for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
     if (b < NB) {
         for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
             Real f[3] = {0, 0, 0}, t[3];
-            for (int e = 0; e < 4; e++) { Real d[3]; edge_dir(e, m.mu, d); const Real l = lam(c, e); f[0] += l * d[0]; f[1] += l * d[1]; f[2] += l * d[2]; }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                Real d[3]; edge_dir(e, m.mu, d);
+                const Real r = w.cres[c][e];
+                const Real l = r < 0 ? w.cD[c] * (mode ? w.cjp[c][e] : r) : Real(0);
+                f[0] += l * d[0]; f[1] += l * d[1]; f[2] += l * d[2];
+            }
             cross3(w.cr[c], f, t);
             LVA(acc)[0] += t[0]; LVA(acc)[1] += t[1]; LVA(acc)[2] += t[2]; LVA(acc)[3] += f[0]; LVA(acc)[4] += f[1]; LVA(acc)[5] += f[2];
         }
@@ -707,7 +729,7 @@ UHC_DEV Real newton_init(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
 // newton_prepare: gradient at the current point; returns false when converged, else leaves -g in w.p
 template <class Real, class TPT>
 UHC_DEV bool newton_prepare(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, Real scale, const TPT &tp) {
-    contact_force(m, w, [&](int c, int e) { const Real r = w.cres[c][e]; return r < 0 ? w.cD[c] * r : Real(0); }, w.Fb, tp);
+    contact_force(m, w, 0, w.Fb, tp);
     LVAR(Real, part);
     LANES_BEGIN
     Real s = 0;
@@ -727,7 +749,7 @@ template <class Real, class TPT>
 UHC_DEV void newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
     tree_vel(m, w, w.p, w.Ab, tp);
     contact_rows(m, w, w.Ab, w.cjp, (const Real (*)[4]) nullptr);
-    contact_force(m, w, [&](int c, int e) { return w.cres[c][e] < 0 ? w.cD[c] * w.cjp[c][e] : Real(0); }, w.Fb, tp);
+    contact_force(m, w, 1, w.Fb, tp);
     LVAR(Real, pa); LVAR(Real, pb);
     LANES_BEGIN
     Real sA = 0, sB = 0;
