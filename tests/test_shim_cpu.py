@@ -18,9 +18,8 @@ def test_config_defaults_and_schedules(tmp_path, monkeypatch):
     cfg.update_adaptive_params(10)
     assert cfg.adp_noise_rate == 1.0 and cfg.adp_policy_lr == 5e-5 and cfg.adp_log_std == -2.3
 
-    class A:
-        num_threads, no_log = 3, True
-    cfg.update(A())
+    import types
+    cfg.update(types.SimpleNamespace(num_threads=3, no_log=True))
     assert cfg.num_threads == 3 and cfg.no_log is True
     flags.debug = True
     assert flags.debug
