@@ -27,7 +27,7 @@ def default_cfg(precision=32, **kw):
     c.newton_max_iter = 20 if precision == 64 else 12
     c.w = (C.c_double * 5)(0.3, 0.1, 0.45, 0.1, 0.05)
     c.k = (C.c_double * 5)(2.0, 0.005, 5.0, 100.0, 1.0)
-    c.newton_tol = 1e-11 if precision == 64 else 1e-6
+    c.newton_tol = 1e-11 if precision == 64 else 1e-5
     for k, v in kw.items():
         setattr(c, k, v)
     return c

@@ -30,6 +30,7 @@
 #define LV(n) n
 #define LVARA(T, n, K) T n[K]
 #define LVA(n) n
+#define LV_ARR(n, c) n[c]
 #define UHC_LDG(p) __ldg(p)
 #else
 #define UHC_DEV static inline
@@ -40,6 +41,7 @@
 #define LV(n) n[lane]
 #define LVARA(T, n, K) T n[32][K]
 #define LVA(n) n[lane]
+#define LV_ARR(n, c) n[lane][c]
 #define UHC_LDG(p) (*(p))
 #endif
 
@@ -50,6 +52,7 @@ constexpr int OBS_DIM = 657, ACT_DIM = 105;
 constexpr int UPPER_BODY0 = 12;               // bodies >= Neck: arms, neck, head
 constexpr int MAXCON = 40;
 constexpr int MAXLEVEL = 8;
+constexpr int LVL_G = 5;                      // max bodies per tree level (lane groups of 6 lanes in the articulated-body solve)
 constexpr int BODYF = 20;                     // floats per body in the model table
 // per-env state record in HBM (Real units)
 constexpr int ST_Q = 0, ST_V = 76, ST_AW = 152, ST_C = 228, ST_XPOS = 304, ST_XQUAT = 376, ST_XIPOS = 472,
@@ -72,6 +75,8 @@ struct Model {
     const unsigned char *colidx;  // [NV][32]: anc(k,s)
     const unsigned char *ent_row, *ent_col;  // [NNZ]
     const int *ee;                // [5]
+    const int *lvl_tab;           // [MAXLEVEL+1][LVL_G][5]: body, parent's group, groups of <=3 children (-1 = none)
+    const int *lvl_pack;          // [MAXLEVEL+1][LVL_G]: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15
     Real dt, margin, mu, solref0, solref1, simp0, simp1, simp2, simp3, simp4, gravz;
 };
 
@@ -89,7 +94,7 @@ struct Work {
     Real xpos[NB][3], xmat[NB][9], xipos[NB][3], xquat[NB][4];
     Real S[NV][6];
     Real Ib[NB][10];              // per-body rigid inertia about O, world axes (of the last forward pass)
-    Real aU[NV][6], aDinv[NV + 1], au[NV + 1];   // articulated-body sweep: U_j = IA S_j, 1 / D_j, u_j
+    Real aU[NV][6], aDinv[NV + 1], au[NV + 1], aArm[NV + 1];   // articulated-body sweep: U_j = IA S_j, 1 / D_j, u_j, joint-space diagonal
     Real C[NV + 1], fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
     Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
     // contacts
@@ -282,6 +287,10 @@ template <class R, int K> UHC_DEV void fetch_parent(const R (&x)[K], R (&o)[K], 
 }
 #define WGATHER(n, K, tp, lvl) gather_children<Real, K>(n, tp, lvl)
 #define WFETCHP(n, o, K, tp) fetch_parent<Real, K>(n, o, tp)
+// dst[i] = src[i] of lane SRCL (a per-lane expression), i < K ; WANY: warp-wide OR of a per-lane flag
+#define WSHFL(dst, src, K, SRCL) { const int lane = (int)(threadIdx.x & 31); const int s_ = (SRCL); (void)lane; _Pragma("unroll") for (int i_ = 0; i_ < K; i_++) dst[i_] = __shfl_sync(0xffffffffu, src[i_], s_); }
+#define WSHFL1(dst, src, SRCL) { const int lane = (int)(threadIdx.x & 31); (void)lane; dst = __shfl_sync(0xffffffffu, src, (SRCL)); }
+#define WANY(flag) __any_sync(0xffffffffu, flag)
 #else
 #define TOPO_DECL(m) LaneTopo tp[32]; for (int l_ = 0; l_ < 32; l_++) tp[l_] = lane_topo(m, l_)
 #define TP tp[lane]
@@ -296,6 +305,10 @@ template <class R, int K> static void emu_fetchp(R (*x)[K], R (*o)[K], const Lan
 }
 #define WGATHER(n, K, tp, lvl) emu_gather<Real, K>(n, tp, lvl)
 #define WFETCHP(n, o, K, tp) emu_fetchp<Real, K>(n, o, tp)
+#define WSHFL(dst, src, K, SRCL) { Real t_[32][K]; for (int l_ = 0; l_ < 32; l_++) for (int i_ = 0; i_ < K; i_++) t_[l_][i_] = src[l_][i_]; \
+    for (int lane = 0; lane < 32; lane++) { const int s_ = (SRCL); for (int i_ = 0; i_ < K; i_++) dst[lane][i_] = t_[s_][i_]; } }
+#define WSHFL1(dst, src, SRCL) { Real t_[32]; for (int l_ = 0; l_ < 32; l_++) t_[l_] = src[l_]; for (int lane = 0; lane < 32; lane++) dst = t_[(SRCL)]; }
+#define WANY(flag) emu_ballot(flag)
 #endif
 
 // pyramid edge directions d_e = n +- mu t  for n = +z, t1 = +y, t2 = -x
@@ -305,105 +318,150 @@ template <class Real> UHC_DEV void edge_dir(int e, Real mu, Real *d) {
     d[2] = 1;
 }
 
-// contact matrix of body b: K_b = sum_{own contacts} X^T W X,  X = [G 1], G = -[r]x, W = D sum_{active edges} d d^T
+// row r of the contact matrix of body b: K_b = sum_{own contacts} X^T W X,  X = [G 1], G = -[r]x, W = D sum_{active edges} d d^T
 template <class Real>
-UHC_DEV void contact_matrix(const Model<Real> &m, const Work<Real> &w, int b, Real *K) {
+UHC_DEV void contact_matrix_row(const Model<Real> &m, const Work<Real> &w, int b, int r, Real *row) {
     for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
         Real W[6] = {0, 0, 0, 0, 0, 0};  // xx yy zz xy xz yz
+#pragma unroll
         for (int e = 0; e < 4; e++) if (w.cres[c][e] < 0) {
             Real d[3]; edge_dir(e, m.mu, d); const Real D = w.cD[c];
             W[0] += D * d[0] * d[0]; W[1] += D * d[1] * d[1]; W[2] += D * d[2] * d[2];
             W[3] += D * d[0] * d[1]; W[4] += D * d[0] * d[2]; W[5] += D * d[1] * d[2];
         }
-        const Real Wm[9] = {W[0], W[3], W[4], W[3], W[1], W[5], W[4], W[5], W[2]};
-        const Real *r = w.cr[c];
-        const Real G[9] = {0, r[2], -r[1], -r[2], 0, r[0], r[1], -r[0], 0};
-        Real WG[9], GtWG[9];
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) WG[3 * i + j] = Wm[3 * i] * G[j] + Wm[3 * i + 1] * G[3 + j] + Wm[3 * i + 2] * G[6 + j];
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) GtWG[3 * i + j] = G[i] * WG[j] + G[3 + i] * WG[3 + j] + G[6 + i] * WG[6 + j];
-        for (int i = 0; i < 3; i++) for (int j = i; j < 3; j++) { K[sym6(i, j)] += GtWG[3 * i + j]; K[sym6(3 + i, 3 + j)] += Wm[3 * i + j]; }
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) K[sym6(i, 3 + j)] += WG[3 * j + i];  // (G^T W)[i][j] = WG[j][i]
+        const Real *p = w.cr[c];
+        // columns of X: angular k -> e_k x p ... X maps (w, v) to v + w x p, so X e_k(angular) = e_k x p, X e_k(linear) = e_k
+        Real Xc[6][3] = {{0, -p[2], p[1]}, {p[2], 0, -p[0]}, {-p[1], p[0], 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        Real xr[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 6; k++) if (k == r) { xr[0] = Xc[k][0]; xr[1] = Xc[k][1]; xr[2] = Xc[k][2]; }
+        const Real v[3] = {W[0] * xr[0] + W[3] * xr[1] + W[4] * xr[2], W[3] * xr[0] + W[1] * xr[1] + W[5] * xr[2], W[4] * xr[0] + W[5] * xr[1] + W[2] * xr[2]};
+#pragma unroll
+        for (int k = 0; k < 6; k++) row[k] += v[0] * Xc[k][0] + v[1] * Xc[k][1] + v[2] * Xc[k][2];
     }
 }
-
-// eliminate one joint dof from the articulated pair (IA, pA):  U = IA S, D = S.U + arm, u = b - S.pA ; IA -= U U^T / D ; pA += U u / D
+// row r of the 6x6 spatial inertia of a rigid body (m, h = m c, J about O), (w, v) ordering:  [[J, [h]x], [-[h]x, m 1]]
 template <class Real>
-UHC_DEV void aba_eliminate(Real *IA, Real *pA, const Real *S, Real arm, Real bj, Real *Uout, Real *Dinv, Real *uo) {
-    Real U[6], Sv[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) Sv[i] = S[i];
-    sym6_mul(IA, Sv, U);
-    const Real D = dot6(Sv, U) + arm, di = Real(1) / D, u = bj - dot6(Sv, pA);
-    *Dinv = di; *uo = u;
-    const Real ud = u * di;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        const Real Ui = U[i] * di;
-        Uout[i] = U[i];
-#pragma unroll
-        for (int j = i; j < 6; j++) IA[sym6(i, j)] -= Ui * U[j];
-        pA[i] += U[i] * ud;
+UHC_DEV void rigid_row(const Real *I, int r, Real *row) {
+    const int q = r < 3 ? r : r - 3, q1 = q == 2 ? 0 : q + 1, q2 = q == 0 ? 2 : q - 1;
+    // [h]x row q: column q1 -> -h[q2], column q2 -> +h[q1], column q -> 0
+    const Real hx1 = -I[1 + q2], hx2 = I[1 + q1];
+    const Real c0 = q1 == 0 ? hx1 : (q2 == 0 ? hx2 : Real(0)), c1 = q1 == 1 ? hx1 : (q2 == 1 ? hx2 : Real(0)), c2 = q1 == 2 ? hx1 : (q2 == 2 ? hx2 : Real(0));
+    if (r < 3) {   // J row q from the packed (xx yy zz xy xz yz): diagonal 4+q, off-diagonal (i,j) at 6+i+j
+        const Real d = I[4 + q], o1 = I[6 + q + q1], o2 = I[6 + q + q2];
+        row[0] = q == 0 ? d : (q1 == 0 ? o1 : o2); row[1] = q == 1 ? d : (q1 == 1 ? o1 : o2); row[2] = q == 2 ? d : (q1 == 2 ? o1 : o2);
+        row[3] = c0; row[4] = c1; row[5] = c2;
+    } else {
+        const Real ms = I[0];
+        row[0] = -c0; row[1] = -c1; row[2] = -c2; row[3] = q == 0 ? ms : Real(0); row[4] = q == 1 ? ms : Real(0); row[5] = q == 2 ? ms : Real(0);
     }
 }
 
 // x <- H^-1 x  (x: 75-vector in shared memory).  arm_scale: extra joint-space diagonal = arm_scale * kd_i (0 for none).
-template <class Real, class TPT>
-UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, const TPT &tp, Real arm_scale, bool use_contacts, Real *x) {
-    LVARA(Real, IP, 27);      // articulated inertia (21, packed symmetric) + bias wrench (6)
+// Lane layout: the <= 5 bodies of one tree level are processed together, 6 lanes per body (lane = 6 g + r owns ROW r of that
+// body's articulated inertia; the bias wrench is replicated in the group).  Leaves -> root eliminates the joint dofs
+// (U = IA S, D = S.U + arm, u = b - S.pA ; IA -= U U^T / D ; pA += U u / D), root -> leaves back-substitutes.
+template <class Real>
+UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bool use_contacts, Real *x) {
+    LVARA(Real, row, 6); LVARA(Real, pA, 6); LVARA(Real, crow, 6); LVARA(Real, cpA, 6); LVARA(Real, trow, 6); LVARA(Real, tpA, 6);
+    LVARA(Real, Uf, 6);
+    LVARA(Real, Sv, 6);
+    LVAR(Real, Ur); LVAR(int, body); LVAR(int, src); LVAR(int, act); LVAR(int, gbase); LVAR(int, rr); LVAR(int, ent);
     LANES_BEGIN
-    const int b = lane;
-#pragma unroll
-    for (int i = 0; i < 27; i++) LVA(IP)[i] = 0;
-    if (b < NB) {
-        const Real *I = w.Ib[b];   // rigid (m, h, J) -> packed symmetric 6x6 in (w, v) ordering
-        Real *A = LVA(IP);
-        A[sym6(0, 0)] = I[4]; A[sym6(1, 1)] = I[5]; A[sym6(2, 2)] = I[6]; A[sym6(0, 1)] = I[7]; A[sym6(0, 2)] = I[8]; A[sym6(1, 2)] = I[9];
-        A[sym6(3, 3)] = I[0]; A[sym6(4, 4)] = I[0]; A[sym6(5, 5)] = I[0];
-        // n = J a + h x b  ->  upper-right block is [h]x
-        A[sym6(0, 4)] = -I[3]; A[sym6(0, 5)] = I[2]; A[sym6(1, 3)] = I[3]; A[sym6(1, 5)] = -I[1]; A[sym6(2, 3)] = -I[2]; A[sym6(2, 4)] = I[1];
-        if (use_contacts) contact_matrix(m, w, b, A);
-    }
+    for (int i = 0; i < 6; i++) { LVA(crow)[i] = 0; LVA(cpA)[i] = 0; }
+    const int g = lane / 6;
+    LV(gbase) = g < LVL_G ? 6 * g : 24; LV(rr) = lane - 6 * g;
+    for (int i = lane; i < NV; i += 32) w.aArm[i] = UHC_LDG(m.dof_f + 4 * i) + arm_scale * UHC_LDG(m.dof_f + 4 * i + 2);
     LANES_END
 #pragma unroll 1
     for (int lvl = MAXLEVEL; lvl >= 0; --lvl) {
-        WGATHER(IP, 27, tp, lvl);
         LANES_BEGIN
-        const int b = lane;
-        if (b < NB && TP.depth == lvl) {
-            const int d0 = b == 0 ? 0 : 6 + 3 * (b - 1), nd = b == 0 ? 6 : 3;
-#pragma unroll 1
-            for (int j = nd - 1; j >= 0; --j) {
-                const int dof = d0 + j;
-                const Real arm = UHC_LDG(m.dof_f + 4 * dof) + arm_scale * UHC_LDG(m.dof_f + 4 * dof + 2);
-                aba_eliminate(LVA(IP), LVA(IP) + 21, w.S[dof], arm, x[dof], w.aU[dof], &w.aDinv[dof], &w.au[dof]);
-            }
+        const int g = lane / 6, r = LV(rr);
+        const int e = g < LVL_G ? UHC_LDG(m.lvl_pack + lvl * LVL_G + g) : 0;
+        const int b = (e & 63) - 1;
+        LV(ent) = e; LV(body) = b;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { LVA(row)[i] = 0; LVA(pA)[i] = 0; }
+        if (b >= 0) {
+            rigid_row(w.Ib[b], r, LVA(row));
+            if (use_contacts) contact_matrix_row(m, w, b, r, LVA(row));
         }
         LANES_END
-    }
-    // root -> leaves: x_j = (u_j - U_j . a) / D_j ; a += S_j x_j
-    LVARA(Real, acc, 6); LVARA(Real, ap, 6);
-    LANES_BEGIN
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {  // children of this level's bodies (they sit one level deeper, results in crow / cpA)
+            LANES_BEGIN
+            const int cg = ((LV(ent) >> (9 + 3 * k)) & 7) - 1;
+            LV(act) = cg >= 0; LV(src) = cg >= 0 ? cg * 6 + LV(rr) : lane;
+            LANES_END
+            if (!WANY(act)) continue;
+            WSHFL(trow, crow, 6, LV(src));
+            WSHFL(tpA, cpA, 6, LV(src));
+            LANES_BEGIN
+            if (LV(act)) for (int i = 0; i < 6; i++) { LVA(row)[i] += LVA(trow)[i]; LVA(pA)[i] += LVA(tpA)[i]; }
+            LANES_END
+        }
+        const int nd = lvl == 0 ? 6 : 3;
+#pragma unroll 1
+        for (int j = nd - 1; j >= 0; --j) {
+            LANES_BEGIN
+            Real u = 0;
+            const int b = LV(body), dof = b <= 0 ? j : 3 + 3 * b + j;
+            const Real *S = w.S[dof];
 #pragma unroll
-    for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
+            for (int c = 0; c < 6; c++) { const Real sc = b >= 0 ? S[c] : Real(0); LVA(Sv)[c] = sc; u += LVA(row)[c] * sc; }
+            LV(Ur) = u;
+            LANES_END
+#pragma unroll
+            for (int c = 0; c < 6; c++) { WSHFL1(LV_ARR(Uf, c), Ur, LV(gbase) + c); }
+            LANES_BEGIN
+            const int b = LV(body);
+            if (b >= 0) {
+                const int dof = b == 0 ? j : 3 + 3 * b + j;
+                Real D = w.aArm[dof], sp = 0;       // joint-space diagonal (armature + arm_scale kd)
+#pragma unroll
+                for (int c = 0; c < 6; c++) { D += LVA(Sv)[c] * LVA(Uf)[c]; sp += LVA(Sv)[c] * LVA(pA)[c]; }
+                const Real di = Real(1) / D, u = x[dof] - sp, ud = u * di, Urd = LV(Ur) * di;
+#pragma unroll
+                for (int c = 0; c < 6; c++) { LVA(row)[c] -= Urd * LVA(Uf)[c]; LVA(pA)[c] += LVA(Uf)[c] * ud; }
+                w.aU[dof][LV(rr)] = LV(Ur);
+                if (LV(rr) == 0) { w.aDinv[dof] = di; w.au[dof] = u; }
+            }
+            LANES_END
+        }
+        LANES_BEGIN
+        for (int i = 0; i < 6; i++) { LVA(crow)[i] = LVA(row)[i]; LVA(cpA)[i] = LVA(pA)[i]; }
+        LANES_END
+    }
+    // root -> leaves: x_j = (u_j - U_j . a) / D_j ; a += S_j x_j   (a replicated in the 6 lanes of a group)
+    LVARA(Real, acc, 6); LVARA(Real, pacc, 6);
+    LANES_BEGIN
+    for (int i = 0; i < 6; i++) LVA(pacc)[i] = 0;
     LANES_END
 #pragma unroll 1
     for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
-        WFETCHP(acc, ap, 6, tp);
         LANES_BEGIN
-        const int b = lane;
-        if (b < NB && TP.depth == lvl) {
+        const int g = lane / 6;
+        const int e = g < LVL_G ? UHC_LDG(m.lvl_pack + lvl * LVL_G + g) : 0;
+        const int b = (e & 63) - 1;
+        LV(body) = b;
+        LV(src) = (b >= 0 && lvl > 0) ? ((e >> 6) & 7) * 6 : lane;
+        LANES_END
+        WSHFL(acc, pacc, 6, LV(src));
+        LANES_BEGIN
+        const int b = LV(body);
+        if (b >= 0) {
             const int d0 = b == 0 ? 0 : 6 + 3 * (b - 1), nd = b == 0 ? 6 : 3;
-#pragma unroll
-            for (int i = 0; i < 6; i++) LVA(acc)[i] = b == 0 ? Real(0) : LVA(ap)[i];
+            if (b == 0) for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
 #pragma unroll 1
             for (int j = 0; j < nd; ++j) {
                 const int dof = d0 + j;
                 const Real xj = (w.au[dof] - dot6(w.aU[dof], LVA(acc))) * w.aDinv[dof];
-                x[dof] = xj;
+                if (LV(rr) == 0) x[dof] = xj;
 #pragma unroll
                 for (int i = 0; i < 6; i++) LVA(acc)[i] += w.S[dof][i] * xj;
             }
         }
+        for (int i = 0; i < 6; i++) LVA(pacc)[i] = LVA(acc)[i];
         LANES_END
     }
 }
@@ -824,9 +882,12 @@ UHC_DEV void pd_setup(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> 
         Real rhs = -w.C[i];
         if (i >= 6) {
             const int j = i - 6; const Real qj = w.q[7 + j];
+            // humanoid_im.py:1041-1045 (while base - q > pi: base -= 2 pi ; while base - q < -pi: base += 2 pi) in closed form --
+            // a loop on a non-finite state would never terminate
             Real base = target[j];
-            while (base - qj > Real(PI_D)) base -= Real(2 * PI_D);
-            while (base - qj < -Real(PI_D)) base += Real(2 * PI_D);
+            const Real dlt = base - qj;
+            if (dlt > Real(PI_D)) base -= Real(2 * PI_D) * ceil((dlt - Real(PI_D)) / Real(2 * PI_D));
+            else if (dlt < -Real(PI_D)) base += Real(2 * PI_D) * ceil((-Real(PI_D) - dlt) / Real(2 * PI_D));
             const Real kp = UHC_LDG(m.dof_f + 4 * i + 1) * sp, kd = UHC_LDG(m.dof_f + 4 * i + 2) * sd;
             const Real err = qj + w.v[i] * dt - (base + w.act[j]);
             rhs += -kp * err - kd * w.v[i];
@@ -917,7 +978,7 @@ UHC_DEV int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work
             ++iters;
         }
         // ---- the one shared O(n) articulated-body solve
-        aba_solve(m, w, tp, arm_scale, phase == PH_NEWTON, rhs);
+        aba_solve(m, w, arm_scale, phase == PH_NEWTON, rhs);
         // ---- phase post-processing
         if (phase == PH_PD) { pd_finish(m, cfg, w, it, torque_out); phase = PH_SMOOTH; }
         else if (phase == PH_SMOOTH) {

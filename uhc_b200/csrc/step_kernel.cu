@@ -77,7 +77,7 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     int *p;
 #define CPI(field, n) do { if (dev_copy(e, &p, m->field, (size_t)(n))) return -1; M.field = p; } while (0)
     CPI(hull_adr, NB); CPI(hull_num, NB); CPI(nbr, m->nnbr); CPI(nbradr, m->nvert + 1); CPI(parent, NB); CPI(depth, NB); CPI(child_adr, NB + 1);
-    CPI(child, NB - 1); CPI(body_sub_end, NB); CPI(dep, NV); CPI(madr, NV); CPI(dof_sub_end, NV); CPI(dof_body, NV); CPI(ee, 5);
+    CPI(child, NB - 1); CPI(body_sub_end, NB); CPI(dep, NV); CPI(madr, NV); CPI(dof_sub_end, NV); CPI(dof_body, NV); CPI(ee, 5); CPI(lvl_tab, (MAXLEVEL + 1) * LVL_G * 5); CPI(lvl_pack, (MAXLEVEL + 1) * LVL_G);
 #undef CPI
     short *ps; if (dev_copy(e, &ps, m->rowadr, (size_t)NV * 32)) return -1; M.rowadr = ps;
     unsigned char *pc;

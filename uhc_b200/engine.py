@@ -31,7 +31,7 @@ def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0,
     c.rfc_scale, c.rfc_lim, c.rfc_rate, c.body_diff_thresh = rfc_scale, rfc_lim, rfc_rate, body_diff_thresh
     c.meta_pd, c.env_episode_len, c.trail_steps = int(meta_pd), int(env_episode_len), int(trail_steps)
     c.newton_max_iter = newton_max_iter or (20 if precision == 64 else 12)
-    c.newton_tol = newton_tol or (1e-11 if precision == 64 else 1e-6)
+    c.newton_tol = newton_tol or (1e-11 if precision == 64 else 1e-5)
     c.w, c.k = (C.c_double * 5)(*w), (C.c_double * 5)(*k)
     return c
 

@@ -26,6 +26,7 @@ class UhcModelHost(C.Structure):
                 ("dep", C.POINTER(C.c_int)), ("madr", C.POINTER(C.c_int)), ("dof_sub_end", C.POINTER(C.c_int)),
                 ("dof_body", C.POINTER(C.c_int)), ("rowadr", C.POINTER(C.c_short)), ("colidx", C.POINTER(C.c_ubyte)),
                 ("ent_row", C.POINTER(C.c_ubyte)), ("ent_col", C.POINTER(C.c_ubyte)), ("ee", C.POINTER(C.c_int)),
+                ("lvl_tab", C.POINTER(C.c_int)), ("lvl_pack", C.POINTER(C.c_int)),
                 ("dt", C.c_double), ("margin", C.c_double), ("mu", C.c_double), ("solref", C.c_double * 2),
                 ("solimp", C.c_double * 5), ("gravz", C.c_double)]
 
@@ -77,6 +78,21 @@ class HumanoidModel:
         for b in range(NB - 1, 0, -1):
             sub_end[p[b]] = max(sub_end[p[b]], sub_end[b])
         self.body_sub_end = sub_end.astype(np.int32)
+        # per tree level: the bodies of that level as lane groups (<= 5), with the group index of the parent and of <= 3 children
+        nlev = int(self.depth.max()) + 1
+        assert nlev <= 9
+        groups = [[b for b in range(NB) if self.depth[b] == L] for L in range(9)]
+        assert max(len(g) for g in groups) <= 5 and max(len(c) for c in ch) <= 3
+        grp = {b: g.index(b) for g in groups for b in g}
+        tab = -np.ones((9, 5, 5), np.int32)
+        for L, g in enumerate(groups):
+            for gi, b in enumerate(g):
+                tab[L, gi, 0] = b
+                tab[L, gi, 1] = grp[p[b]] if b > 0 else 0
+                for k, c in enumerate(ch[b]):
+                    tab[L, gi, 2 + k] = grp[c]
+        self.lvl_tab = np.ascontiguousarray(tab.reshape(-1))
+        self.lvl_pack = np.ascontiguousarray(((tab[:, :, 0] + 1) | (np.maximum(tab[:, :, 1], 0) << 6) | ((tab[:, :, 2] + 1) << 9) | ((tab[:, :, 3] + 1) << 12) | ((tab[:, :, 4] + 1) << 15)).astype(np.int32).reshape(-1))
         self.dof_body = np.array([0] * 6 + [1 + d // 3 for d in range(NU)], np.int32)
         # ancestor chain (by depth) of every dof
         chains = []
@@ -144,7 +160,7 @@ class HumanoidModel:
         h.nvert, h.nnbr = len(self.hull), len(self.nbr)
         h.body_f, h.dof_f, h.hull = ptr("bf", self.body_f, C.c_double), ptr("df", self.dof_f, C.c_double), ptr("hull", self.hull, C.c_double)
         for n in ("hull_adr", "hull_num", "nbr", "nbradr", "parent", "depth", "child_adr", "child", "body_sub_end", "dep",
-                  "madr", "dof_sub_end", "dof_body", "ee"):
+                  "madr", "dof_sub_end", "dof_body", "ee", "lvl_tab", "lvl_pack"):
             setattr(h, n, ptr(n, getattr(self, n).astype(np.int32), C.c_int))
         h.rowadr, h.colidx = ptr("rowadr", self.rowadr, C.c_short), ptr("colidx", self.colidx, C.c_ubyte)
         h.ent_row, h.ent_col = ptr("er", self.ent_row, C.c_ubyte), ptr("ec", self.ent_col, C.c_ubyte)
