@@ -153,9 +153,9 @@ def run_gpu(args):
     raw_step = agent.engine.step
     cur = [0]
 
-    def timed_step(a, torque_out=None):
+    def timed_step(a, torque_out=None, reward_out=None):
         kev[cur[0]][0].record()
-        out = raw_step(a, torque_out)
+        out = raw_step(a, torque_out, reward_out)
         kev[cur[0]][1].record()
         return out
     agent.engine.step = timed_step
@@ -230,7 +230,7 @@ def run_gpu(args):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=total_ms / K, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload_config(world),
                 roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                              kernel="k_env_step<float,4>", kernel_ms=kern_ms, kernel_share_of_step=kern_ms / (total_ms / K),
+                              kernel="k_env_step<float,7>", kernel_ms=kern_ms, kernel_share_of_step=kern_ms / (total_ms / K),
                               peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                               note="algorithmic bytes 6396 B/env-step (SURVEY 8d); the step is latency/ALU bound, not HBM bound -- see DESIGN.md"),
                 e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=E * (657 + 105) * 4, d2h_bytes_per_step=E * (105 + 657 + 1 + 5 + 1 + 1 + 1) * 4, steps=Ke),

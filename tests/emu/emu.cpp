@@ -68,8 +68,7 @@ static int emu_forward_given_tau(const Model<Real> &m, const EnvCfg<Real> &cfg, 
     project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
     collide(m, w);
     for (int i = 0; i < NV; i++) { Real f = -w.C[i] + (i < 6 ? (Real)fapp_d[i] : w.tau[i - 6]); w.fs[i] = f; w.as_[i] = f; }
-    aba_solve(m, w, Real(0), false, w.as_);
-    if (w.ncon == 0) { for (int i = 0; i < NV; i++) w.a[i] = w.as_[i]; return 0; }
+    if (w.ncon == 0) { aba_solve(m, w, Real(0), false, w.as_); for (int i = 0; i < NV; i++) w.a[i] = w.as_[i]; return 0; }
     constraint_setup(m, w);
     Real scale = newton_init(m, w, tp);
     int iters = 0;

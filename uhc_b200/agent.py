@@ -83,6 +83,7 @@ class BatchedAgent:
         self.ep_len = torch.zeros(num_envs, device=self.dev)
         self.ep_ret = torch.zeros(num_envs, device=self.dev)
         self.nn_launches = 0
+        self._notdone = torch.zeros(num_envs, device=self.dev, dtype=torch.bool)
 
     # ---- env.reset for a subset with freshly sampled clip slices
     def reset_envs(self, ids=None):
@@ -91,11 +92,12 @@ class BatchedAgent:
         self.obs = self.engine.reset(ids, clip, start, length)
         return self.obs
 
-    def policy_step(self, obs, update_filter=True, mean_action=None, use_tc=True):
-        """running_state -> policy -> sample.  Returns (normalised state, action, logp)."""
-        s = self.running_state(obs, update=update_filter)
+    def policy_step(self, obs, update_filter=True, mean_action=None, use_tc=True, out_state=None, out_action=None, out_logp=None):
+        """running_state -> policy -> sample.  Returns (normalised state, action, logp); the out_* tensors (rows of the rollout
+        buffer) are written in place by the kernels."""
+        s = self.running_state(obs, update=update_filter, out=out_state)
         mean = self.policy.forward_tc(s) if use_tc else self.policy.forward(s)
-        a, lp = nn.gaussian_sample(mean, self.log_std, self.seed * 1000003 + self.rank, self.global_step, mean_action)
+        a, lp = nn.gaussian_sample(mean, self.log_std, self.seed * 1000003 + self.rank, self.global_step, mean_action, out_action, out_logp)
         self.nn_launches += (3 if update_filter else 1) + (1 + len(self.policy.W) if use_tc else len(self.policy.W)) + 1
         return s, a, lp
 
@@ -105,15 +107,16 @@ class BatchedAgent:
         mean_action = None
         if self.noise_rate < 1.0:
             mean_action = (t.rand(self.E, device=self.dev) < (1.0 - self.noise_rate)).to(t.uint8)
-        s, a, lp = self.policy_step(self.obs, True, mean_action, use_tc)
-        buf.states[k].copy_(s)
-        buf.actions[k].copy_(a)
-        buf.logp[k].copy_(lp)
-        buf.exps[k].fill_(1.0) if mean_action is None else buf.exps[k].copy_(1.0 - mean_action.float())
-        obs, rew, cinfo, fail, end, pct = self.engine.step(a)
+        s, a, lp = self.policy_step(self.obs, True, mean_action, use_tc, buf.states[k], buf.actions[k], buf.logp[k])
+        if mean_action is not None:
+            buf.exps[k].copy_(1.0 - mean_action.float())
+        elif not getattr(buf, "_exps_ones", False):
+            buf.exps.fill_(1.0)
+            buf._exps_ones = True
+        obs, rew, cinfo, fail, end, pct = self.engine.step(a, reward_out=buf.rewards[k])
         done = (fail | end) != 0
-        buf.rewards[k].copy_(rew)
-        buf.masks[k].copy_((~done).float())
+        t.logical_not(done, out=self._notdone)
+        buf.masks[k].copy_(self._notdone)
         self.ep_len += 1
         self.ep_ret += rew
         self.global_step += 1

@@ -736,50 +736,29 @@ UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real
 // ================================================================================================ constraint solve
 // min_a 1/2 (a-a_s)^T M (a-a_s) + sum_rows 1/2 D min(0, J a - aref)^2 ; primal Newton, Hessian = M + J^T D_act J built as a
 // CRBA over contact-augmented composites, factorised tree-sparse (only the lower-body rows when no arm/head contact).
-// newton_init: pick the start point (warm start vs unconstrained), residuals, M a.  Returns the gradient-norm scale.
+// newton_init: start from the warm start (previous qacc, as MuJoCo's warmstart): residuals J a - aref and M a by O(n) passes.
+// The problem is strictly convex, so the minimiser does not depend on the start; starting from the warm start makes the
+// unconstrained solve a_s = M^-1 f_s unnecessary whenever contacts are present.  Returns the gradient-norm scale.
 template <class Real, class TPT>
 UHC_DEV Real newton_init(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
-    Real cost[2];
-    for (int pass = 0; pass < 2; ++pass) {
-        const Real *x = pass ? w.as_ : w.aw;
-        tree_vel(m, w, x, w.Ab, tp);
-        contact_rows(m, w, w.Ab, w.cjp, w.caref);
-        LVAR(Real, part);
-        if (pass == 0) {  // M aw = sum_b J_b^T I_b (J_b aw) + armature: O(n) pass with the per-body inertias
-            LVARA(Real, Fm, 6);
-            LANES_BEGIN
-            for (int i = 0; i < 6; i++) LVA(Fm)[i] = 0;
-            if (lane < NB) rigid_mul(w.Ib[lane], w.Ab[lane], LVA(Fm));
-            LANES_END
-            WSUBTREE(Fm, 6, tp);
-            LANES_BEGIN
-            if (lane < NB) for (int i = 0; i < 6; i++) w.Fb[lane][i] = LVA(Fm)[i];
-            LANES_END
-            LANES_BEGIN
-            for (int i = lane; i < NV; i += 32) {
-                const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-                w.Ma[i] = dot6(w.S[i], w.Fb[b]) + UHC_LDG(m.dof_f + 4 * i) * x[i];
-            }
-            LANES_END
-        }
-        LANES_BEGIN
-        Real s = 0;
-        if (pass == 0) for (int i = lane; i < NV; i += 32) s += Real(0.5) * (w.aw[i] - w.as_[i]) * (w.Ma[i] - w.fs[i]);
-        for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) { const Real r = w.cjp[c][e]; if (r < 0) s += Real(0.5) * w.cD[c] * r * r; }
-        LV(part) = s;
-        LANES_END
-        cost[pass] = WSUM(part);
-        if (pass == 0) {  // keep the warm-start residuals in cres
-            LANES_BEGIN
-            for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] = w.cjp[c][e];
-            LANES_END
-        }
-    }
-    const bool use_warm = cost[0] < cost[1];
+    tree_vel(m, w, w.aw, w.Ab, tp);
+    contact_rows(m, w, w.Ab, w.cres, w.caref);
+    LVARA(Real, Fm, 6);
+    LANES_BEGIN
+    for (int i = 0; i < 6; i++) LVA(Fm)[i] = 0;
+    if (lane < NB) rigid_mul(w.Ib[lane], w.Ab[lane], LVA(Fm));
+    LANES_END
+    WSUBTREE(Fm, 6, tp);
+    LANES_BEGIN
+    if (lane < NB) for (int i = 0; i < 6; i++) w.Fb[lane][i] = LVA(Fm)[i];
+    LANES_END
     LVAR(Real, part);
     LANES_BEGIN
-    for (int i = lane; i < NV; i += 32) { w.a[i] = use_warm ? w.aw[i] : w.as_[i]; if (!use_warm) w.Ma[i] = w.fs[i]; }
-    if (!use_warm) for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] = w.cjp[c][e];
+    for (int i = lane; i < NV; i += 32) {
+        const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
+        w.Ma[i] = dot6(w.S[i], w.Fb[b]) + UHC_LDG(m.dof_f + 4 * i) * w.aw[i];
+        w.a[i] = w.aw[i];
+    }
     LV(part) = lane < NB ? 3 * w.Ib[lane][0] : Real(0);   // gradient tolerance scale ~ trace of the translational block of M
     LANES_END
     return WSUM(part);
@@ -977,8 +956,9 @@ UHC_DEV int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work
             if (iters >= cfg.newton_max_iter || !newton_prepare(m, cfg, w, scale, tp)) break;
             ++iters;
         }
-        // ---- the one shared O(n) articulated-body solve
-        aba_solve(m, w, arm_scale, phase == PH_NEWTON, rhs);
+        // ---- the one shared O(n) articulated-body solve (not needed for the smooth phase when contacts are present:
+        //      Newton starts from the warm start and only needs f_s, not a_s = M^-1 f_s)
+        if (!(phase == PH_SMOOTH && w.ncon > 0)) aba_solve(m, w, arm_scale, phase == PH_NEWTON, rhs);
         // ---- phase post-processing
         if (phase == PH_PD) { pd_finish(m, cfg, w, it, torque_out); phase = PH_SMOOTH; }
         else if (phase == PH_SMOOTH) {

@@ -142,16 +142,17 @@ class Engine:
                                     C.c_void_p(self.obs.data_ptr()), self._stream()))
         return self.obs
 
-    def step(self, actions, torque_out=None):
+    def step(self, actions, torque_out=None, reward_out=None):
         """env.step(a) + custom_reward for all envs.  actions: float32 cuda tensor [E,105].  Returns views of the engine's
         output tensors (obs, reward, cinfo, fail, end, percent)."""
         t = self.torch
         assert actions.is_cuda and actions.dtype == t.float32 and actions.is_contiguous() and tuple(actions.shape) == (self.E, ACT_DIM)
-        _chk(self.lib.uhc_env_step(self.h, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()), C.c_void_p(self.reward.data_ptr()),
+        rew = self.reward if reward_out is None else reward_out
+        _chk(self.lib.uhc_env_step(self.h, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()), C.c_void_p(rew.data_ptr()),
                                    C.c_void_p(self.cinfo.data_ptr()), C.c_void_p(self.fail.data_ptr()), C.c_void_p(self.end.data_ptr()),
                                    C.c_void_p(self.percent.data_ptr()), C.c_void_p(torque_out.data_ptr() if torque_out is not None else None),
                                    self._stream()))
-        return self.obs, self.reward, self.cinfo, self.fail, self.end, self.percent
+        return self.obs, rew, self.cinfo, self.fail, self.end, self.percent
 
     def step_host(self, actions, obs=None, reward=None, cinfo=None, fail=None, end=None, percent=None):
         """Host-buffer entry (H2D of actions and D2H of every requested output inside the call)."""

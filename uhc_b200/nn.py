@@ -223,10 +223,11 @@ class ZFilter:
         self.stats.copy_(torch.as_tensor(s))
 
 
-def gaussian_sample(mean, log_std, seed, step, mean_action=None):
+def gaussian_sample(mean, log_std, seed, step, mean_action=None, out_action=None, out_logp=None):
     import torch
     M, A = mean.shape
-    a, lp = torch.empty_like(mean), torch.empty(M, device=mean.device, dtype=torch.float32)
+    a = torch.empty_like(mean) if out_action is None else out_action
+    lp = torch.empty(M, device=mean.device, dtype=torch.float32) if out_logp is None else out_logp
     _chk(_lib().uhc_gaussian_sample(_p(mean), _p(log_std), _p(mean_action), _p(a), _p(lp), M, A, C.c_ulonglong(seed), C.c_ulonglong(step), _stream(mean)))
     return a, lp
 
