@@ -200,7 +200,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
         agent.engine.step_host(act_h.numpy(), obs_h.numpy(), rew_h, ci_h, fail_h, end_h, pct_h)
         done = np.nonzero(fail_h | end_h)[0]
-        if len(done):
+        if len(done) and not agent.auto_reset:
             agent.reset_envs(done.astype(np.int32))
             torch.cuda.synchronize()
             obs_h[torch.as_tensor(done)] = agent.obs[torch.as_tensor(done, device=agent.dev)].cpu()

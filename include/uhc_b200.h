@@ -47,6 +47,10 @@ typedef struct {
     double base_rot[4], rfc_scale, rfc_lim, rfc_rate, body_diff_thresh;
     int meta_pd, env_episode_len, trail_steps, newton_max_iter;
     double w[5], k[5], newton_tol;
+    /* in-kernel re-seeding of finished episodes (agent_copycat.py:503-512 + dataset_amass_single.py:172-253): when auto_reset != 0,
+     * an env whose step ends its episode samples a new (clip, start) slice and is reset inside uhc_env_step; obs = reset obs. */
+    int auto_reset, t_min, t_max, reserved;
+    unsigned long long reset_seed;
 } UhcEnvCfg;
 
 const char *uhc_last_error(void);

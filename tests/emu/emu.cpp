@@ -26,6 +26,7 @@ static void set_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) {
     c.meta_pd = h->meta_pd; c.env_episode_len = h->env_episode_len; c.trail_steps = h->trail_steps; c.newton_max_iter = h->newton_max_iter;
     for (int i = 0; i < 5; i++) { c.w[i] = (Real)h->w[i]; c.k[i] = (Real)h->k[i]; }
     c.newton_tol = (Real)h->newton_tol;
+    c.auto_reset = 0; c.t_min = h->t_min; c.t_max = h->t_max; c.reset_seed = h->reset_seed; c.num_clips = 0;
 }
 
 template <class Real>

@@ -51,6 +51,7 @@ class RolloutBuffer:
         self.rewards, self.masks, self.exps, self.logp = (torch.empty(T, E, **f) for _ in range(4))
         self.last_obs = torch.empty(E, OBS_DIM, **f)
         self.last_alive = torch.empty(E, **f)
+        self.fails = torch.zeros(T, E, device=device, dtype=torch.int32)
 
     # TrajBatch-compatible flat views (khrylib/rl/core/trajbatch.py)
     def flat(self, name):
@@ -68,7 +69,9 @@ class BatchedAgent:
         self.dev = torch.device("cuda", device)
         torch.cuda.set_device(self.dev)
         self.E, self.seed, self.rank, self.world = num_envs, seed, rank, world
-        self.engine = Engine(num_envs, model=model, device=device, precision=precision, **env_cfg)
+        self.auto_reset = bool(env_cfg.pop("auto_reset", True))
+        self.engine = Engine(num_envs, model=model, device=device, precision=precision, auto_reset=int(self.auto_reset), t_min=t_min, t_max=t_max,
+                             reset_seed=seed * 7919 + rank * 104729 + 1, **env_cfg)
         self.engine.load_clips(clips, shapes)
         self.sampler = ClipSampler(self.engine.clip_len, t_min, t_max, seed=seed * 9973 + rank)
         self.policy = nn.MLPNet(OBS_DIM, policy_hsize, ACT_DIM, htype, device=self.dev, head_name="action_mean", seed=seed)
@@ -117,19 +120,13 @@ class BatchedAgent:
         done = (fail | end) != 0
         t.logical_not(done, out=self._notdone)
         buf.masks[k].copy_(self._notdone)
-        self.ep_len += 1
-        self.ep_ret += rew
         self.global_step += 1
+        buf.fails[k].copy_(fail)
+        if self.auto_reset:
+            return            # finished episodes were re-seeded inside the step kernel (no host round trip)
         ids = done.nonzero().flatten()
-        if ids.numel():                       # host round trip only when an episode ended
-            idc = ids.cpu().numpy().astype(np.int32)
-            st = getattr(self, "_ep_stats", None)
-            if st is not None:
-                st[0] += float(self.ep_len[ids].sum()); st[1] += float(self.ep_ret[ids].sum())
-                st[2] += int(fail[ids].sum()); st[3] += len(idc)
-            self.ep_len[ids] = 0
-            self.ep_ret[ids] = 0
-            self.reset_envs(idc)
+        if ids.numel():
+            self.reset_envs(ids.cpu().numpy().astype(np.int32))
 
     def sample(self, T, buf=None, use_tc=True):
         """agent.sample(): T lock-step control steps of all envs.  Returns (buffer, log)."""
@@ -138,14 +135,27 @@ class BatchedAgent:
             self.reset_envs()
         buf = buf or RolloutBuffer(T, self.E, self.dev)
         t0 = time.time()
-        self._ep_stats = [0.0, 0.0, 0, 0]
+        len0, ret0 = self.ep_len.clone(), self.ep_ret.clone()
         for k in range(T):
             self.step_once(buf, k, use_tc)
-        ep_done_len, ep_done_ret, n_fail, n_eps = self._ep_stats
         buf.last_obs.copy_(self.obs)
-        log = dict(num_steps=T * self.E, num_episodes=n_eps, avg_episode_len=ep_done_len / max(n_eps, 1),
-                   avg_episode_reward=ep_done_ret / max(n_eps, 1), fail_rate=n_fail / max(n_eps, 1),
-                   avg_reward=float(buf.rewards[:T].mean()), sample_time=time.time() - t0)
+        # episode statistics from the buffer (one sync at the end of the rollout): segment the [T][E] masks per env
+        m, r = buf.masks[:T], buf.rewards[:T]
+        done = m == 0
+        n_eps = int(done.sum())
+        run_len = t.zeros(self.E, device=self.dev); run_ret = t.zeros(self.E, device=self.dev)
+        run_len += len0; run_ret += ret0
+        tot_len = t.zeros((), device=self.dev); tot_ret = t.zeros((), device=self.dev)
+        for k in range(T):
+            run_len += 1; run_ret += r[k]
+            d = done[k]
+            tot_len += (run_len * d).sum(); tot_ret += (run_ret * d).sum()
+            run_len *= ~d; run_ret *= ~d
+        self.ep_len, self.ep_ret = run_len, run_ret
+        n_fail = int(((buf.fails[:T] != 0) & done).sum())
+        log = dict(num_steps=T * self.E, num_episodes=n_eps, avg_episode_len=float(tot_len) / max(n_eps, 1),
+                   avg_episode_reward=float(tot_ret) / max(n_eps, 1), fail_rate=n_fail / max(n_eps, 1),
+                   avg_reward=float(r.mean()), sample_time=time.time() - t0)
         return buf, log
 
     def update_params(self, buf):

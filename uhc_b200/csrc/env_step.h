@@ -18,6 +18,7 @@ struct EngineView {
     const Real *expert;     // [total_frames][EX_SIZE]
     const int *clip_adr;    // [C+1] first frame of each clip in `expert`
     const Real *clip_shape; // [C][17] beta[16], gender
+    const float *clip_cdf;  // [C] cumulative sampling weights (len // t_max + 1 copies per clip, sample_keys of the reference)
 };
 
 template <class Real>
@@ -25,6 +26,25 @@ UHC_DEV const Real *expert_frame(const EngineView<Real> &ev, int clip, int start
     // the reference slices the clip to [start, start+len) and always runs with start_ind = 0 (dataset_amass_single.py:238-244)
     const int i = start + (t < len - 1 ? t : len - 1);
     return ev.expert + (size_t)(UHC_LDG(ev.clip_adr + clip) + i) * EX_SIZE;
+}
+
+UHC_DEV unsigned long long mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+// DatasetAMASSSingle.sample_seq / get_sample_from_key (dataset_amass_single.py:172-253): clip ~ sample_keys (uniform over
+// len // t_max + 1 copies per clip), start ~ U{0 .. len - t_min - 1}, slice length min(t_max, len - start)
+template <class Real>
+UHC_DEV void sample_clip(const EngineView<Real> &ev, int env, int episode, int *clip, int *start, int *len) {
+    const unsigned long long h = mix64(ev.cfg.reset_seed ^ mix64((unsigned long long)env * 0x100000001B3ull + (unsigned long long)episode));
+    const float u1 = (float)(h >> 40) * (1.0f / 16777216.0f), u2 = (float)(h & 0xFFFFFF) * (1.0f / 16777216.0f);
+    int lo = 0, hi = ev.cfg.num_clips - 1;
+    const float target = u1 * UHC_LDG(ev.clip_cdf + hi);
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (UHC_LDG(ev.clip_cdf + mid) > target) hi = mid; else lo = mid + 1; }
+    const int L = UHC_LDG(ev.clip_adr + lo + 1) - UHC_LDG(ev.clip_adr + lo);
+    int span = L - ev.cfg.t_min; if (span < 1) span = 1;
+    int st = (int)(u2 * (float)span); if (st > span - 1) st = span - 1;
+    int ln = L - st; if (ev.cfg.t_max > 0 && ln > ev.cfg.t_max) ln = ev.cfg.t_max;
+    *clip = lo; *start = st; *len = ln;
 }
 
 template <class Real>
@@ -136,6 +156,15 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     if (cinfo_out && lane < 5) cinfo_out[lane] = (ObsT)ci[lane];
     LANES_END
     store_state(ev, env, w, bq, (const Real *)nullptr);
+    if (ev.cfg.auto_reset && (fail || end)) {   // re-seed the finished episode in place: the next observation is the reset observation
+        int nclip, nstart, nlen;
+        const int episode = is[SI_EPISODE] + 1;
+        sample_clip(ev, env, episode, &nclip, &nstart, &nlen);
+        env_reset_warp<Real, ObsT>(ev, env, w, nclip, nstart, nlen, (const Real *)nullptr, (const Real *)nullptr, obs);
+        LANES_BEGIN
+        if (lane == 0) is[SI_EPISODE] = episode;
+        LANES_END
+    }
     return fail || end;
 }
 

@@ -85,6 +85,8 @@ struct EnvCfg {
     Real base_rot[4], rfc_scale, rfc_lim, rfc_rate, body_diff_thresh;
     int meta_pd, env_episode_len, trail_steps, newton_max_iter;
     Real w[5], k[5], newton_tol;
+    int auto_reset, t_min, t_max, num_clips;      // in-kernel re-seeding of finished episodes (dataset_amass_single.py:172-253)
+    unsigned long long reset_seed;
 };
 
 // per-environment working set (lives in shared memory on the GPU)
@@ -925,7 +927,7 @@ UHC_DEV void integrate(const Model<Real> &m, Work<Real> &w) {
 // exposes to the Python side (SURVEY.md section 7 "stale dynamics").  with_pd = false: reset path (sim.forward with ctrl = 0).
 enum { PH_PD = 0, PH_SMOOTH = 1, PH_NEWTON = 2 };
 template <class Real, class OutT, class TPT>
-UHC_DEV int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const TPT &tp, const Real *target, int it,
+UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const TPT &tp, const Real *target, int it,
                              bool with_pd, OutT *torque_out) {
     int phase = with_pd ? PH_PD : PH_SMOOTH, iters = 0;
     Real scale = 0;

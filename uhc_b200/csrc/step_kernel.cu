@@ -48,7 +48,7 @@ struct UhcEngine {
     int E, device, precision, launches;
     std::vector<void *> allocs;
     EngineView<float> evf; EngineView<double> evd;
-    void *d_expert = nullptr, *d_shape = nullptr; int *d_clip_adr = nullptr;
+    void *d_expert = nullptr, *d_shape = nullptr; int *d_clip_adr = nullptr; float *d_clip_cdf = nullptr; int num_clips = 0;
     // staging for the host-buffer API
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_cinfo = nullptr, *d_pct = nullptr; int *d_fail = nullptr, *d_end = nullptr;
     int *d_ids = nullptr; int ids_cap = 0;
@@ -69,6 +69,7 @@ template <class Real> static void fill_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) 
     c.meta_pd = h->meta_pd; c.env_episode_len = h->env_episode_len; c.trail_steps = h->trail_steps; c.newton_max_iter = h->newton_max_iter;
     for (int i = 0; i < 5; i++) { c.w[i] = (Real)h->w[i]; c.k[i] = (Real)h->k[i]; }
     c.newton_tol = (Real)h->newton_tol;
+    c.auto_reset = h->auto_reset; c.t_min = h->t_min; c.t_max = h->t_max; c.reset_seed = h->reset_seed;
 }
 template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, const UhcModelHost *m, const UhcEnvCfg *cfg) {
     Model<Real> &M = ev.model;
@@ -132,13 +133,14 @@ void uhc_engine_destroy(UhcEngine *e) {
     if (e->d_expert) cudaFree(e->d_expert);
     if (e->d_shape) cudaFree(e->d_shape);
     if (e->d_clip_adr) cudaFree(e->d_clip_adr);
+    if (e->d_clip_cdf) cudaFree(e->d_clip_cdf);
     if (e->d_ids) cudaFree(e->d_ids);
     delete e;
 }
 
 int uhc_engine_set_cfg(UhcEngine *e, const UhcEnvCfg *cfg) {
     if (!e || !cfg) { g_err = "uhc_engine_set_cfg: null"; return -2; }
-    if (e->precision == 32) fill_cfg(e->evf.cfg, cfg); else fill_cfg(e->evd.cfg, cfg);
+    if (e->precision == 32) { fill_cfg(e->evf.cfg, cfg); e->evf.cfg.num_clips = e->num_clips; } else { fill_cfg(e->evd.cfg, cfg); e->evd.cfg.num_clips = e->num_clips; }
     return 0;
 }
 
@@ -148,9 +150,18 @@ int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *
     std::vector<int> adr(nclips + 1, 0);
     for (int i = 0; i < nclips; i++) { if (clip_len[i] < 2) { g_err = "uhc_load_clips: clip shorter than 2 frames"; return -2; } adr[i + 1] = adr[i] + clip_len[i]; }
     const size_t nf = (size_t)adr[nclips] * EX_SIZE, ns = (size_t)nclips * 17;
-    if (e->d_expert) { cudaFree(e->d_expert); cudaFree(e->d_shape); cudaFree(e->d_clip_adr); e->d_expert = e->d_shape = nullptr; e->d_clip_adr = nullptr; }
+    if (e->d_expert) { cudaFree(e->d_expert); cudaFree(e->d_shape); cudaFree(e->d_clip_adr); cudaFree(e->d_clip_cdf); e->d_expert = e->d_shape = nullptr; e->d_clip_adr = nullptr; e->d_clip_cdf = nullptr; }
     CK(cudaMalloc((void **)&e->d_clip_adr, (nclips + 1) * sizeof(int)));
     CK(cudaMemcpy(e->d_clip_adr, adr.data(), (nclips + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    {   // sampling weights: len // t_max + 1 copies per clip (sample_keys, dataset_amass_single.py:138-142)
+        const int tmax = e->precision == 32 ? e->evf.cfg.t_max : e->evd.cfg.t_max;
+        std::vector<float> cdf(nclips); float acc = 0.f;
+        for (int i = 0; i < nclips; i++) { acc += (float)(tmax > 0 ? clip_len[i] / tmax + 1 : 1); cdf[i] = acc; }
+        CK(cudaMalloc((void **)&e->d_clip_cdf, nclips * sizeof(float)));
+        CK(cudaMemcpy(e->d_clip_cdf, cdf.data(), nclips * sizeof(float), cudaMemcpyHostToDevice));
+        e->num_clips = nclips;
+        e->evf.clip_cdf = e->d_clip_cdf; e->evd.clip_cdf = e->d_clip_cdf; e->evf.cfg.num_clips = nclips; e->evd.cfg.num_clips = nclips;
+    }
     if (e->precision == 32) {
         std::vector<float> f(nf), s(ns);
         for (size_t i = 0; i < nf; i++) f[i] = (float)frames_host[i];

@@ -19,12 +19,13 @@ EXPERT_FIELDS = (("qpos", 76), ("qvel", 75), ("wbpos", 72), ("wbquat", 96), ("bq
 class UhcEnvCfg(C.Structure):
     _fields_ = [("base_rot", C.c_double * 4), ("rfc_scale", C.c_double), ("rfc_lim", C.c_double), ("rfc_rate", C.c_double),
                 ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
-                ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double)]
+                ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double),
+                ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reserved", C.c_int), ("reset_seed", C.c_ulonglong)]
 
 
 def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0, rfc_lim=100.0, rfc_rate=1.0, body_diff_thresh=0.5,
              meta_pd=1, env_episode_len=100000, trail_steps=0, w=(0.3, 0.1, 0.45, 0.1, 0.05), k=(2.0, 0.005, 5.0, 100.0, 1.0),
-             newton_max_iter=None, newton_tol=None):
+             newton_max_iter=None, newton_tol=None, auto_reset=0, t_min=5, t_max=300, reset_seed=1):
     """Defaults = config/release/uhc_implicit_shape.yml + copycat_config.py defaults of the reference."""
     c = UhcEnvCfg()
     c.base_rot = (C.c_double * 4)(*base_rot)
@@ -33,6 +34,7 @@ def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0,
     c.newton_max_iter = newton_max_iter or (20 if precision == 64 else 12)
     c.newton_tol = newton_tol or (1e-11 if precision == 64 else 1e-5)
     c.w, c.k = (C.c_double * 5)(*w), (C.c_double * 5)(*k)
+    c.auto_reset, c.t_min, c.t_max, c.reset_seed = int(auto_reset), int(t_min), int(t_max), int(reset_seed)
     return c
 
 
@@ -83,6 +85,7 @@ class Engine:
         self.E, self.device, self.precision = int(num_envs), int(device), precision
         self.model = model or HumanoidModel()
         self._ms = self.model.host_struct()
+        self._cfg_kw = dict(cfg)
         self._cfg = make_cfg(precision, **cfg)
         h = C.c_void_p()
         _chk(self.lib.uhc_engine_create(C.byref(self._ms), C.byref(self._cfg), C.c_int(self.E), C.c_int(self.device), C.c_int(precision), C.byref(h)))
@@ -109,7 +112,8 @@ class Engine:
             pass
 
     def set_cfg(self, **cfg):
-        self._cfg = make_cfg(self.precision, **cfg)
+        self._cfg_kw = dict(getattr(self, "_cfg_kw", {}), **cfg)
+        self._cfg = make_cfg(self.precision, **self._cfg_kw)
         _chk(self.lib.uhc_engine_set_cfg(self.h, C.byref(self._cfg)))
 
     def load_clips(self, experts, shapes=None):
