@@ -99,32 +99,51 @@ def workload_config(n):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms from before the warm-up; stop(t0, t1) keeps the samples whose
+    timestamp falls inside the timed region [t0, t1] (wall clock), or the nearest ones when the region is shorter than a sample."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, device):
         self.f = tempfile.NamedTemporaryFile("w+", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.p.terminate()
         self.p.wait()
         self.f.seek(0)
-        rows = [r.strip().split(", ") for r in self.f.read().strip().splitlines() if r.strip()]
-        sm = [float(r[0]) for r in rows if len(r) >= 7]
+        import datetime
+        rows = []
+        for line in self.f.read().strip().splitlines():
+            r = [x.strip() for x in line.split(",")]
+            if len(r) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(r[1]), float(r[2]), float(r[3]), r[4:8]))
+            except Exception:
+                continue
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
+        sel = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        where = "inside the timed region"
+        if not sel:
+            mid = 0.5 * ((t0 or rows[-1][0]) + (t1 or rows[-1][0]))
+            sel = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            where = "nearest to the timed region (region shorter than the sampling period)"
         reasons = set()
-        for r in rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.strip().lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows else None,
-                "power_w_max": max((float(r[2]) for r in rows if len(r) >= 7), default=None), "samples": len(sm), "reasons": sorted(reasons)}
+        for r in sel:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([r[1] for r in sel])), "sm_max_mhz": sel[0][2], "power_w_max": max(r[3] for r in sel),
+                "samples": len(sel), "where": where, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -142,6 +161,7 @@ def run_gpu(args):
     agent.reset_envs()
     buf = RolloutBuffer(max(K, 4), E, agent.dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=agent.dev)
+    clocks = ClockSampler(local) if rank == 0 else None
     for k in range(W):
         agent.step_once(buf, k % buf.T)
     torch.cuda.synchronize()
@@ -160,8 +180,8 @@ def run_gpu(args):
         return out
     agent.engine.step = timed_step
     l0, n0 = agent.engine.kernel_launches, agent.nn_launches
-    clocks = ClockSampler(local) if rank == 0 else None
     torch.cuda.synchronize()
+    t_wall0 = time.time()
     for k in range(K):
         flush.fill_(k & 0xFF)                       # L2 flush, outside the timed region
         cur[0] = k
@@ -171,7 +191,8 @@ def run_gpu(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clk = clocks.stop() if clocks else None
+    t_wall1 = time.time()
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
     agent.engine.step = raw_step
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / K
