@@ -24,6 +24,14 @@ int uhc_act_backward(const float *dh, const float *z, float *dz, long n, int act
 int uhc_linear_forward_tc(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null,
                           int M, int N, int Kp, int ldy_bf16, int act, void *stream);
 int uhc_f32_to_bf16_padded(const float *x, void *y_bf16, int M, int K, int Kp, void *stream);
+/* training variants on the tensor cores (bf16 operands, fp32 accumulate; autograd of nn.Linear + activation):
+ *   forward that also stores the pre-activation z (fp32) ; dX = dZ W and dW = dZ^T X are plain calls of uhc_linear_forward_tc on
+ *   transposed bf16 copies ; uhc_dact_bf16 fuses dz = dh * act'(z) -> bf16 dz, bf16 dz^T and the bias gradient. */
+int uhc_linear_forward_tc_train(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null, float *z_f32,
+                                int M, int N, int Kp, int ldy_bf16, int act, void *stream);
+int uhc_transpose_bf16(const void *in, void *out, int R, int C, int ld_in, int ld_out, void *stream);
+int uhc_dact_bf16(const float *dh, const float *z_or_null, void *dz_bf16, void *dzT_bf16, float *db_or_null, int M, int N, int ld_dz, int ld_dzT, int act,
+                  void *stream);
 
 /* DiagGaussian (khrylib/rl/core/distributions.py:6-25, policy.py:12-23): sample a = mean + exp(log_std) eps (or the mean where
  * mean_action[i] != 0), log-prob summed over the action dims. */

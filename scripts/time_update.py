@@ -12,12 +12,13 @@ x = torch.randn(N, 657, device="cuda").clamp(-5, 5)
 a = torch.randn(N, 105, device="cuda") * 0.1
 adv = torch.randn(N, device="cuda"); ret = torch.rand(N, device="cuda"); exps = torch.ones(N, device="cuda")
 op, ov = nn.Adam(pol.params(), 5e-5), nn.Adam(val.params(), 3e-4)
-nn.ppo_update(pol, val, log_std, op, ov, x, a, ret, adv, exps, epochs=1)
-torch.cuda.synchronize(); t0 = time.time()
-nn.ppo_update(pol, val, log_std, op, ov, x, a, ret, adv, exps, epochs=epochs)
-torch.cuda.synchronize(); dt = (time.time() - t0) / epochs
 flop = 6 * (4024530 + 3971073) * N
-print(f"N={N} per-epoch {dt*1e3:.1f} ms  -> {flop/dt/1e12:.1f} TFLOP/s effective (fp32 SIMT GEMM); 10 epochs = {dt*10:.2f} s")
+for tc in (False, True):
+    nn.ppo_update(pol, val, log_std, op, ov, x, a, ret, adv, exps, epochs=1, use_tc=tc)
+    torch.cuda.synchronize(); t0 = time.time()
+    nn.ppo_update(pol, val, log_std, op, ov, x, a, ret, adv, exps, epochs=epochs, use_tc=tc)
+    torch.cuda.synchronize(); dt = (time.time() - t0) / epochs
+    print(f"N={N} use_tc={tc} per-epoch {dt*1e3:.1f} ms  -> {flop/dt/1e12:.1f} TFLOP/s effective; 10 epochs = {dt*10:.2f} s")
 # tensor-core forward throughput
 for M in (4096, 32768):
     xs = x[:M].contiguous(); pol.forward_tc(xs); torch.cuda.synchronize()

@@ -63,7 +63,7 @@ class BatchedAgent:
     def __init__(self, num_envs, clips, shapes=None, device=0, seed=1, precision=32, policy_hsize=(2048, 1024, 512),
                  value_hsize=(2048, 1024, 512), htype="gelu", log_std=-2.3, policy_lr=5e-5, value_lr=3e-4, gamma=0.95, tau=0.95,
                  clip_epsilon=0.2, num_optim_epoch=10, grad_clip=40.0, t_min=5, t_max=300, noise_rate=1.0, rank=0, world=1,
-                 grad_sync=None, model=None, **env_cfg):
+                 grad_sync=None, model=None, update_tc=True, **env_cfg):
         import torch
         self.torch = torch
         self.dev = torch.device("cuda", device)
@@ -80,7 +80,7 @@ class BatchedAgent:
         self.running_state = nn.ZFilter(OBS_DIM, clip=5.0, device=self.dev)
         self.opt_p, self.opt_v = nn.Adam(self.policy.params(), policy_lr), nn.Adam(self.value.params(), value_lr)
         self.gamma, self.tau, self.clip_epsilon, self.epochs, self.grad_clip = gamma, tau, clip_epsilon, num_optim_epoch, grad_clip
-        self.noise_rate, self.grad_sync = noise_rate, grad_sync
+        self.noise_rate, self.grad_sync, self.update_tc = noise_rate, grad_sync, update_tc
         self.global_step = 0
         self.obs = None
         self.ep_len = torch.zeros(num_envs, device=self.dev)
@@ -170,7 +170,7 @@ class BatchedAgent:
         if self.grad_sync is not None:
             self._wrap_sync()
         losses = nn.ppo_update(self.policy, self.value, self.log_std, self.opt_p, self.opt_v, states, buf.flat("actions"), ret.reshape(-1),
-                               adv.reshape(-1), buf.flat("exps"), self.clip_epsilon, self.epochs, self.grad_clip)
+                               adv.reshape(-1), buf.flat("exps"), self.clip_epsilon, self.epochs, self.grad_clip, use_tc=self.update_tc)
         t.cuda.synchronize()
         return dict(update_time=time.time() - t0, surr_loss=float(losses[0]), value_loss=float(losses[1]))
 

@@ -60,7 +60,7 @@ __device__ __forceinline__ float act_f(float z, int act) {
 
 __global__ void __launch_bounds__(192, 1)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
-            __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, int M, int N, int Kp, int ldy, int act) {
+            __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], tmem_full
@@ -132,7 +132,12 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 const int nb = n0 + c * 32;
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { const int n = nb + j; v[j] = n < N ? act_f(__uint_as_float(r[j]) + (bias ? __ldg(bias + n) : 0.f), act) : 0.f; }
+                for (int j = 0; j < 32; ++j) {
+                    const int n = nb + j;
+                    const float z = n < N ? __uint_as_float(r[j]) + (bias ? __ldg(bias + n) : 0.f) : 0.f;
+                    if (zf && n < N) zf[(size_t)row * N + n] = z;       // pre-activation (for the backward pass)
+                    v[j] = n < N ? act_f(z, act) : 0.f;
+                }
                 if (yf) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (nb + j < N) yf[(size_t)row * N + nb + j] = v[j];
@@ -169,6 +174,52 @@ __global__ void k_f32_to_bf16_padded(const float *__restrict__ x, __nv_bfloat16 
     }
 }
 
+
+__device__ __forceinline__ float act_b(float z, int act) {
+    switch (act) {
+    case UHC_ACT_GELU: return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+    case UHC_ACT_TANH: { float t = tanhf(z); return 1.0f - t * t; }
+    case UHC_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case UHC_ACT_SIGMOID: { float s = 1.0f / (1.0f + expf(-z)); return s * (1.0f - s); }
+    }
+    return 1.f;
+}
+// out[c][r] = in[r][c]  (bf16, 64x64 tiles through shared memory); rows r >= R of `in` read as zero so out is zero padded to ld_out
+__global__ void k_transpose_bf16(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ out, int R, int Cc, int ld_in, int ld_out) {
+    __shared__ __nv_bfloat16 t[64][66];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    for (int i = threadIdx.y; i < 64; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        t[i][threadIdx.x] = (r < R && c < Cc) ? in[(size_t)r * ld_in + c] : __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 64; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < Cc && r < ld_out) out[(size_t)c * ld_out + r] = t[threadIdx.x][i];
+    }
+}
+// dz = dh * act'(z): writes dz (bf16, [M][ld_dz]) and its transpose ([N][ld_dzT], zero padded in M) and accumulates column sums (bias grads)
+__global__ void k_dact_bf16(const float *__restrict__ dh, const float *__restrict__ z, __nv_bfloat16 *__restrict__ dz, __nv_bfloat16 *__restrict__ dzT,
+                            float *__restrict__ db, int M, int N, int ld_dz, int ld_dzT, int act) {
+    __shared__ float t[64][65];
+    const int n0 = blockIdx.x * 64, m0 = blockIdx.y * 64;
+    float colsum = 0.f;
+    for (int i = threadIdx.y; i < 64; i += 8) {
+        const int m = m0 + i, n = n0 + threadIdx.x;
+        float v = 0.f;
+        if (m < M && n < N) { v = dh[(size_t)m * N + n]; if (z) v *= act_b(z[(size_t)m * N + n], act); }
+        t[i][threadIdx.x] = v;
+        colsum += v;
+        if (dz && m < M && n < ld_dz) dz[(size_t)m * ld_dz + n] = __float2bfloat16_rn(v);
+    }
+    if (db && n0 + threadIdx.x < N) atomicAdd(db + n0 + threadIdx.x, colsum);
+    __syncthreads();
+    if (dzT) for (int i = threadIdx.y; i < 64; i += 8) {
+        const int n = n0 + i, m = m0 + threadIdx.x;
+        if (n < N && m < ld_dzT) dzT[(size_t)n * ld_dzT + m] = __float2bfloat16_rn(t[threadIdx.x][i]);
+    }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                              const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeFn get_encode() {
@@ -199,8 +250,8 @@ int uhc_f32_to_bf16_padded(const float *x, void *y_bf16, int M, int K, int Kp, v
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int uhc_linear_forward_tc(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null, int M, int N, int Kp,
-                          int ldy_bf16, int act, void *stream) {
+static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null, float *z_f32_or_null,
+                          int M, int N, int Kp, int ldy_bf16, int act, void *stream) {
     if (Kp % BK != 0 || M <= 0 || N <= 0) { g_tc_err = "uhc_linear_forward_tc: Kp must be a positive multiple of 64"; return -2; }
     if (y_bf16_or_null && (ldy_bf16 % 8 != 0)) { g_tc_err = "uhc_linear_forward_tc: ldy must be a multiple of 8"; return -2; }
     static bool attr_set = false;
@@ -211,9 +262,30 @@ int uhc_linear_forward_tc(const void *x_bf16, const void *W_bf16, const float *b
     CUtensorMap ma, mb;
     if (make_map(&ma, x_bf16, M, Kp) || make_map(&mb, W_bf16, N, Kp)) return -1;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    k_linear_tc<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, M, N, Kp, ldy_bf16, act);
+    k_linear_tc<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
     return 0;
+}
+
+int uhc_linear_forward_tc(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null, int M, int N, int Kp,
+                          int ldy_bf16, int act, void *stream) {
+    return linear_tc_impl(x_bf16, W_bf16, b, y_bf16_or_null, y_f32_or_null, nullptr, M, N, Kp, ldy_bf16, act, stream);
+}
+int uhc_linear_forward_tc_train(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null, float *z_f32,
+                                int M, int N, int Kp, int ldy_bf16, int act, void *stream) {
+    return linear_tc_impl(x_bf16, W_bf16, b, y_bf16_or_null, y_f32_or_null, z_f32, M, N, Kp, ldy_bf16, act, stream);
+}
+int uhc_transpose_bf16(const void *in, void *out, int R, int Cc, int ld_in, int ld_out, void *stream) {
+    dim3 grid((Cc + 63) / 64, (R + 63) / 64);
+    k_transpose_bf16<<<grid, dim3(64, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, R, Cc, ld_in, ld_out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+int uhc_dact_bf16(const float *dh, const float *z_or_null, void *dz_bf16, void *dzT_bf16, float *db_or_null, int M, int N, int ld_dz, int ld_dzT, int act,
+                  void *stream) {
+    if (db_or_null) cudaMemsetAsync(db_or_null, 0, N * sizeof(float), (cudaStream_t)stream);
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    k_dact_bf16<<<grid, dim3(64, 8), 0, (cudaStream_t)stream>>>(dh, z_or_null, (__nv_bfloat16 *)dz_bf16, (__nv_bfloat16 *)dzT_bf16, db_or_null, M, N, ld_dz, ld_dzT, act);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 }

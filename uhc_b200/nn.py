@@ -164,6 +164,92 @@ class MLPNet:
         return self._out
 
 
+def _buf(cache, key, shape, dtype, device, zero=True):
+    import torch
+    t = cache.get(key)
+    if t is None or tuple(t.shape) != tuple(shape):
+        t = (torch.zeros if zero else torch.empty)(*shape, device=device, dtype=dtype)
+        cache[key] = t
+    return t
+
+
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
+class TCTrainer:
+    """Tensor-core (tcgen05, bf16 operands / fp32 accumulate) forward + backward of an MLPNet for the PPO update:
+    forward stores bf16 activations and fp32 pre-activations; dX = dZ W and dW = dZ^T X run on the same TN GEMM kernel using
+    transposed bf16 copies; dz = dh * act'(z), its transpose and the bias gradient come from one fused kernel."""
+
+    def __init__(self, net):
+        self.net, self.cache = net, {}
+
+    def prepare_input(self, x):
+        import torch
+        M, K = x.shape
+        Kp, Mp = _pad64(K), _pad64(M)
+        xb = _buf(self.cache, "xb", (M, Kp), torch.bfloat16, x.device)
+        _chk(_lib().uhc_f32_to_bf16_padded(_p(x), _p(xb), M, K, Kp, _stream(x)))
+        xT = _buf(self.cache, "xT", (K, Mp), torch.bfloat16, x.device)
+        _chk(_lib().uhc_transpose_bf16(_p(xb), _p(xT), M, K, Kp, Mp, _stream(x)))
+        return xb, xT
+
+    def forward(self, xb):
+        import torch
+        net, L = self.net, _lib()
+        if net._bf16 is None:
+            net._prep_bf16()
+        M = xb.shape[0]
+        acts, zs = [xb], []
+        n = len(net.W)
+        out = _buf(self.cache, "out", (M, net.dims[-1]), torch.float32, xb.device, zero=False)
+        for i in range(n):
+            last = i == n - 1
+            N = net.W[i].shape[0]
+            ybf = None if last else _buf(self.cache, f"a{i}", (M, _pad64(N)), torch.bfloat16, xb.device)
+            z = None if last else _buf(self.cache, f"z{i}", (M, N), torch.float32, xb.device, zero=False)
+            _chk(L.uhc_linear_forward_tc_train(_p(acts[i]), _p(net._bf16[i]), _p(net.b[i]), _p(ybf), _p(out if last else None), _p(z), M, N,
+                                               net._bf16[i].shape[1], 0 if last else ybf.shape[1], ACT["none" if last else net.htype], _stream(xb)))
+            if not last:
+                acts.append(ybf)
+                zs.append(z)
+        return out, (acts, zs)
+
+    def backward(self, dy, ctx, xT):
+        import torch
+        net, L = self.net, _lib()
+        acts, zs = ctx
+        n = len(net.W)
+        M = dy.shape[0]
+        Mp = _pad64(M)
+        dev = dy.device
+        grads = [None] * (2 * n)
+        dh = dy.contiguous()
+        for i in range(n - 1, -1, -1):
+            N, K = net.W[i].shape
+            Np = _pad64(N)
+            dz = _buf(self.cache, f"dz{i}", (M, Np), torch.bfloat16, dev)
+            dzT = _buf(self.cache, f"dzT{i}", (N, Mp), torch.bfloat16, dev)
+            db = torch.empty_like(net.b[i])
+            _chk(L.uhc_dact_bf16(_p(dh), _p(zs[i] if i < n - 1 else None), _p(dz), _p(dzT), _p(db), M, N, Np, Mp, ACT[net.htype], _stream(dy)))
+            if i == 0:
+                hT = xT
+            else:
+                hT = _buf(self.cache, f"hT{i}", (K, Mp), torch.bfloat16, dev)
+                _chk(L.uhc_transpose_bf16(_p(acts[i]), _p(hT), M, K, acts[i].shape[1], Mp, _stream(dy)))
+            dW = torch.empty_like(net.W[i])
+            _chk(L.uhc_linear_forward_tc(_p(dzT), _p(hT), None, None, _p(dW), N, K, Mp, 0, 0, _stream(dy)))      # dW = dz^T h
+            grads[2 * i], grads[2 * i + 1] = dW, db
+            if i > 0:
+                WT = _buf(self.cache, f"WT{i}", (K, Np), torch.bfloat16, dev)
+                _chk(L.uhc_transpose_bf16(_p(net._bf16[i]), _p(WT), N, K, net._bf16[i].shape[1], Np, _stream(dy)))
+                dhp = _buf(self.cache, f"dh{i}", (M, K), torch.float32, dev, zero=False)
+                _chk(L.uhc_linear_forward_tc(_p(dz), _p(WT), None, None, _p(dhp), M, K, Np, 0, 0, _stream(dy)))    # dh_prev = dz W
+                dh = dhp
+        return grads
+
+
 class Adam:
     """torch.optim.Adam semantics (lr, betas (0.9, 0.999), eps 1e-8, no weight decay) on the fused kernel."""
 
@@ -253,22 +339,39 @@ def gae(rewards, masks, values, last_values, gamma, tau, normalize=True):
     return adv, ret
 
 
-def ppo_update(policy, value, log_std, opt_p, opt_v, states, actions, returns, advantages, exps, clip_eps=0.2, epochs=10, grad_clip=40.0):
-    """AgentPPO.update_policy (agent_ppo.py:16-51), full batch: per epoch one value step then one clipped-surrogate policy step."""
+def ppo_update(policy, value, log_std, opt_p, opt_v, states, actions, returns, advantages, exps, clip_eps=0.2, epochs=10, grad_clip=40.0,
+               use_tc=False):
+    """AgentPPO.update_policy (agent_ppo.py:16-51), full batch: per epoch one value step then one clipped-surrogate policy step.
+    use_tc=False: fp32 SIMT GEMMs (parity path); use_tc=True: tcgen05 bf16/fp32-accumulate GEMMs for forward, dX and dW."""
     import torch
     L = _lib()
     M, A = actions.shape
-    mean0 = policy.forward(states)
+    if use_tc:
+        tp = getattr(policy, "_tc_trainer", None) or TCTrainer(policy)
+        tv = getattr(value, "_tc_trainer", None) or TCTrainer(value)
+        policy._tc_trainer, value._tc_trainer = tp, tv
+        xb, xT = tp.prepare_input(states)
+        tv.cache["xb"], tv.cache["xT"] = xb, xT
+        mean0 = tp.forward(xb)[0].clone()
+    else:
+        mean0 = policy.forward(states)
     fixed = gaussian_logprob(mean0, log_std, actions)
     count = float((exps != 0).sum().item())
     losses = torch.zeros(2, device=states.device, dtype=torch.float32)
     for _ in range(epochs):
-        v, ctx = value.forward(states, save=True)
+        if use_tc:
+            v, ctx = tv.forward(xb)
+        else:
+            v, ctx = value.forward(states, save=True)
         dv = torch.empty_like(v)
         losses.zero_()
         _chk(L.uhc_value_grad(_p(v), _p(returns), _p(dv), _p(losses[1:]), M, _stream(states)))
-        opt_v.step(value.backward(dv, ctx))
-        mean, ctx = policy.forward(states, save=True)
+        opt_v.step(tv.backward(dv, ctx, xT) if use_tc else value.backward(dv, ctx))
+        if use_tc:
+            value.invalidate_bf16()
+            mean, ctx = tp.forward(xb)
+        else:
+            mean, ctx = policy.forward(states, save=True)
         dmean = torch.empty_like(mean)
         _chk(L.uhc_ppo_policy_grad(_p(mean), _p(log_std), _p(actions), _p(advantages), _p(fixed), _p(exps), C.c_float(clip_eps),
                                    C.c_float(1.0 / max(count, 1.0)), _p(dmean), _p(losses), M, A, _stream(states)))
@@ -276,7 +379,9 @@ def ppo_update(policy, value, log_std, opt_p, opt_v, states, actions, returns, a
         # very first call, so the reference clips only the first policy step of a run.  Mirrored here.
         first = not getattr(opt_p, "_clip_consumed", False)
         opt_p._clip_consumed = True
-        opt_p.step(policy.backward(dmean, ctx), max_norm=grad_clip if (first and grad_clip) else None)
+        opt_p.step(tp.backward(dmean, ctx, xT) if use_tc else policy.backward(dmean, ctx), max_norm=grad_clip if (first and grad_clip) else None)
+        if use_tc:
+            policy.invalidate_bf16()
     policy.invalidate_bf16()
     value.invalidate_bf16()
     return losses
