@@ -39,6 +39,7 @@ typedef struct {
     const int *lvl_tab;     /* [9][5][5] per tree level and lane group: body, parent's group, groups of up to 3 children (-1 none) */
     const int *lvl_pack;    /* [9][5] the same, packed: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15 */
     double dt, margin, mu, solref[2], solimp[5], gravz;
+    int nshape;             /* number of body-shape variants: body_f = [nshape][24][20], hull = [nshape][nvert][3] (same topology / hull graph) */
 } UhcModelHost;
 
 /* Task configuration: the cfg attributes HumanoidEnv / world_rfc_implicit_reward read
@@ -63,6 +64,9 @@ int uhc_engine_set_cfg(UhcEngine *e, const UhcEnvCfg *cfg);
 /* Expert tables for C clips (replaces HumanoidEnv.load_expert's per-episode recompute, humanoid_im.py:182-215):
  * frames_host = concatenated [sum(len)][UHC_EX_SIZE] doubles, shape_host = [C][17] (beta16, gender). */
 int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *frames_host, const double *shape_host);
+/* body-shape variant of every clip (index into the model's shape variants); the reference rebuilds the robot per clip from
+ * its beta/gender (humanoid_im.py:154-180).  Call after uhc_load_clips; default = variant 0 for every clip. */
+int uhc_set_clip_models(UhcEngine *e, int nclips, const int *clip_model);
 
 /* env.reset() for n envs (mujoco_env.py:95-104 + humanoid_im.py:1245-1299).  clip/start/len select the expert slice
  * (dataset_amass_single.py:200-253); q/v override (may be NULL) = [n][76]/[n][75] floats on the device.

@@ -60,9 +60,14 @@ def _p(a, t=C.c_double):
 
 
 class Model:
-    def __init__(self, npz=MODEL_NPZ):
-        z = np.load(npz)
-        self.z = {k: z[k] for k in z.files}
+    def __init__(self, npz=MODEL_NPZ, tables=None):
+        """tables: optional dict overriding body_offset / body_mass / body_ipos / body_inertia / body_invweight0 / hull_vert
+        (a body-shape variant with the same topology)."""
+        z0 = np.load(npz)
+        z = {k: z0[k] for k in z0.files}
+        if tables:
+            z.update(tables)
+        self.z = dict(z)
         f = lambda k: np.ascontiguousarray(z[k], dtype=np.float64)
         i = lambda k: np.ascontiguousarray(z[k], dtype=np.int32)
         self._keep = [i("parent"), f("body_offset"), f("body_mass"), f("body_ipos"), f("body_inertia"),

@@ -105,3 +105,42 @@ def test_batched_envs_match_oracle_on_seeded_inputs(golden_dir):
             assert bool(f[e]) == info["fail"]
     assert worst_q < 1e-4 and worst_r < 1e-4, (worst_q, worst_r)
     eng.close()
+
+
+def test_mixed_body_shapes_match_oracle(golden_dir):
+    """BASELINE configs[3]: envs with different body shapes in one batch (per-clip model variant, synthetic limb scaling
+    U[0.85, 1.15] since the SMPL files are licence-gated) against the oracle built from the same scaled tables."""
+    import torch
+    from oracle import oracle as O
+    from uhc_b200 import motion_lib
+    from uhc_b200.engine import Engine
+    from uhc_b200.model import HumanoidModel
+    z = np.load(os.path.join(golden_dir, "expert_sway.npz"))
+    pose = np.concatenate([z["pose_aa"][:, :66], np.zeros((len(z["pose_aa"]), 6))], 1)
+    rng = np.random.RandomState(4)
+    hm0 = HumanoidModel()
+    hm1 = HumanoidModel(scale=rng.uniform(0.85, 1.15, 24))
+    assert abs(hm1.mass.sum() - hm0.mass.sum()) > 0.5 and np.abs(hm1.invw - hm0.invw).max() > 1e-4
+    exs = [motion_lib.make_expert(pose, z["trans"], m) for m in (hm0, hm1)]
+    so = np.concatenate([z["beta"][0], [z["gender"][0]]])
+    E, T = 8, 8
+    eng = Engine(E, hm0, variants=[hm0, hm1])
+    eng.load_clips(exs, [so, so], clip_models=[0, 1])
+    clip = (np.arange(E) % 2).astype(np.int32)
+    obs = eng.reset(np.arange(E, dtype=np.int32), clip, 0, None).cpu().numpy().copy()
+    oms = [O.Model(), O.Model(tables=dict(body_offset=hm1.offset, body_mass=hm1.mass, body_ipos=hm1.ipos, body_inertia=hm1.inertia,
+                                          body_invweight0=np.stack([hm1.invw, np.zeros(24)], 1), hull_vert=hm1.hull))]
+    oes = [O.Env(oms[c], exs[c], so) for c in (0, 1)]
+    for c in (0, 1):
+        assert np.abs(oes[c].reset() - obs[c]).max() < 1e-4
+    assert np.abs(obs[0] - obs[1]).max() > 1e-3                       # the two shapes really differ
+    acts = rng.normal(0, 0.1, (T, 105)).astype(np.float32)
+    for t in range(T):
+        o, r, ci, f, en, p = eng.step(torch.tensor(np.tile(acts[t], (E, 1)), device="cuda"))
+        r = r.cpu().numpy()
+        for c in (0, 1):
+            _, ro, _, info = oes[c].step(acts[t].astype(np.float64))
+            for e in (c, c + 2, c + 6):
+                assert np.abs(eng.get_state(e)["qpos"] - oes[c].d.qpos).max() < 1e-4
+                assert abs(r[e] - ro) < 1e-4
+    eng.close()

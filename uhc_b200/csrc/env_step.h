@@ -18,6 +18,7 @@ struct EngineView {
     const Real *expert;     // [total_frames][EX_SIZE]
     const int *clip_adr;    // [C+1] first frame of each clip in `expert`
     const Real *clip_shape; // [C][17] beta[16], gender
+    const int *clip_model;  // [C] body-shape (model variant) of each clip: the reference rebuilds the robot per clip (humanoid_im.py:154-180)
     const float *clip_cdf;  // [C] cumulative sampling weights (len // t_max + 1 copies per clip, sample_keys of the reference)
 };
 
@@ -45,6 +46,16 @@ UHC_DEV void sample_clip(const EngineView<Real> &ev, int env, int episode, int *
     int st = (int)(u2 * (float)span); if (st > span - 1) st = span - 1;
     int ln = L - st; if (ev.cfg.t_max > 0 && ln > ev.cfg.t_max) ln = ev.cfg.t_max;
     *clip = lo; *start = st; *len = ln;
+}
+
+// model tables of the body shape a clip was recorded with
+template <class Real>
+UHC_DEV Model<Real> model_for_clip(const EngineView<Real> &ev, int clip) {
+    Model<Real> m = ev.model;
+    const int sh = ev.clip_model ? UHC_LDG(ev.clip_model + clip) : 0;
+    m.body_f += (size_t)sh * NB * BODYF;
+    m.hull += (size_t)sh * m.nvert * 3;
+    return m;
 }
 
 template <class Real>
@@ -81,9 +92,10 @@ UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, 
     for (int i = lane; i < NV; i += 32) { w.v[i] = qvel_override ? qvel_override[i] : e0[EX_QVEL + i]; w.aw[i] = 0; }
     for (int i = lane; i < ACT_DIM; i += 32) w.act[i] = 0;
     LANES_END
-    TOPO_DECL(ev.model);
-    const int iters = substep_dynamics<Real, ObsT>(ev.model, ev.cfg, w, tp, (const Real *)nullptr, 0, false, (ObsT *)nullptr);
-    world_quat(ev.model, w.q, w);
+    const Model<Real> mdl = model_for_clip(ev, clip);
+    TOPO_DECL(mdl);
+    const int iters = substep_dynamics<Real, ObsT>(mdl, ev.cfg, w, tp, (const Real *)nullptr, 0, false, (ObsT *)nullptr);
+    world_quat(mdl, w.q, w);
     int *is = ev.istate + (size_t)env * SI_SIZE;
     Real *st = ev.state + (size_t)env * ST_SIZE;
     LANES_BEGIN
@@ -116,13 +128,14 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     LANES_END
     const Real *target = expert_frame(ev, clip, start, len, cur_t + 1) + EX_QPOS + 7;
     int iters = 0, maxcon = 0;
-    TOPO_DECL(ev.model);
+    const Model<Real> mdl = model_for_clip(ev, clip);
+    TOPO_DECL(mdl);
 #pragma unroll 1
     for (int it = 0; it < NSUB; ++it) {
-        iters += substep_dynamics<Real, ObsT>(ev.model, ev.cfg, w, tp, target, it, true, torque_out);
+        iters += substep_dynamics<Real, ObsT>(mdl, ev.cfg, w, tp, target, it, true, torque_out);
         if (w.ncon > maxcon) maxcon = w.ncon;
-        if (it == NSUB - 1) world_quat(ev.model, w.q, w);  // pose of the last forward pass (what data.body_xquat holds)
-        integrate(ev.model, w);
+        if (it == NSUB - 1) world_quat(mdl, w.q, w);  // pose of the last forward pass (what data.body_xquat holds)
+        integrate(mdl, w);
     }
     cur_t += 1;
     // body quats: prev <- stored, current from the new qpos (humanoid_im.py:1196, :1219)
@@ -132,7 +145,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     LANES_END
     body_quat(w, bq);
     Real bd, rew, ci[5];
-    diff_and_reward(ev.model, ev.cfg, w, expert_frame(ev, clip, start, len, cur_t), bq, pbq, &bd, &rew, ci);
+    diff_and_reward(mdl, ev.cfg, w, expert_frame(ev, clip, start, len, cur_t), bq, pbq, &bd, &rew, ci);
     int fail = bd > ev.cfg.body_diff_thresh;
     {   // a non-finite state can never pass "bd > thresh": flag it as a failure (mirrors the try/except at :1207-1211)
         LVAR(int, bad);

@@ -78,6 +78,7 @@ struct Model {
     const int *lvl_tab;           // [MAXLEVEL+1][LVL_G][5]: body, parent's group, groups of <=3 children (-1 = none)
     const int *lvl_pack;          // [MAXLEVEL+1][LVL_G]: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15
     Real dt, margin, mu, solref0, solref1, simp0, simp1, simp2, simp3, simp4, gravz;
+    int nshape, nvert;            // body_f / hull hold `nshape` consecutive shape variants ([nshape][NB][BODYF], [nshape][nvert][3])
 };
 
 template <class Real>

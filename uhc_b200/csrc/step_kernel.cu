@@ -48,6 +48,7 @@ struct UhcEngine {
     int E, device, precision, launches;
     std::vector<void *> allocs;
     EngineView<float> evf; EngineView<double> evd;
+    int *d_clip_model = nullptr; int nshape = 1;
     void *d_expert = nullptr, *d_shape = nullptr; int *d_clip_adr = nullptr; float *d_clip_cdf = nullptr; int num_clips = 0;
     // staging for the host-buffer API
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_cinfo = nullptr, *d_pct = nullptr; int *d_fail = nullptr, *d_end = nullptr;
@@ -73,8 +74,10 @@ template <class Real> static void fill_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) 
 }
 template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, const UhcModelHost *m, const UhcEnvCfg *cfg) {
     Model<Real> &M = ev.model;
-    if (dev_copy_real<Real>(e, &M.body_f, m->body_f, NB * BODYF) || dev_copy_real<Real>(e, &M.dof_f, m->dof_f, NV * 4) ||
-        dev_copy_real<Real>(e, &M.hull, m->hull, (size_t)m->nvert * 3)) return -1;
+    const int nshape = m->nshape > 0 ? m->nshape : 1;
+    if (dev_copy_real<Real>(e, &M.body_f, m->body_f, (size_t)nshape * NB * BODYF) || dev_copy_real<Real>(e, &M.dof_f, m->dof_f, NV * 4) ||
+        dev_copy_real<Real>(e, &M.hull, m->hull, (size_t)nshape * m->nvert * 3)) return -1;
+    M.nshape = nshape; M.nvert = m->nvert;
     int *p;
 #define CPI(field, n) do { if (dev_copy(e, &p, m->field, (size_t)(n))) return -1; M.field = p; } while (0)
     CPI(hull_adr, NB); CPI(hull_num, NB); CPI(nbr, m->nnbr); CPI(nbradr, m->nvert + 1); CPI(parent, NB); CPI(depth, NB); CPI(child_adr, NB + 1);
@@ -94,7 +97,7 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     CK(cudaMemset(st, 0, (size_t)e->E * ST_SIZE * sizeof(Real)));
     int *is; CK(cudaMalloc((void **)&is, (size_t)e->E * SI_SIZE * sizeof(int))); e->allocs.push_back(is);
     CK(cudaMemset(is, 0, (size_t)e->E * SI_SIZE * sizeof(int)));
-    ev.state = st; ev.istate = is; ev.expert = nullptr; ev.clip_adr = nullptr; ev.clip_shape = nullptr;
+    ev.state = st; ev.istate = is; ev.expert = nullptr; ev.clip_adr = nullptr; ev.clip_shape = nullptr; ev.clip_model = nullptr; ev.clip_cdf = nullptr;
     return 0;
 }
 
@@ -108,7 +111,7 @@ int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_e
     if (!model || !cfg || !out || num_envs <= 0 || (precision != 32 && precision != 64)) { g_err = "uhc_engine_create: bad argument"; return -2; }
     CK(cudaSetDevice(device));
     UhcEngine *e = new UhcEngine();
-    e->E = num_envs; e->device = device; e->precision = precision; e->launches = 0;
+    e->E = num_envs; e->device = device; e->precision = precision; e->launches = 0; e->nshape = model->nshape > 0 ? model->nshape : 1;
     int rc = precision == 32 ? build_view<float>(e, e->evf, model, cfg) : build_view<double>(e, e->evd, model, cfg);
     if (rc) { delete e; return rc; }
     if (precision == 32) {
@@ -134,6 +137,7 @@ void uhc_engine_destroy(UhcEngine *e) {
     if (e->d_shape) cudaFree(e->d_shape);
     if (e->d_clip_adr) cudaFree(e->d_clip_adr);
     if (e->d_clip_cdf) cudaFree(e->d_clip_cdf);
+    if (e->d_clip_model) cudaFree(e->d_clip_model);
     if (e->d_ids) cudaFree(e->d_ids);
     delete e;
 }
@@ -161,6 +165,8 @@ int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *
         CK(cudaMemcpy(e->d_clip_cdf, cdf.data(), nclips * sizeof(float), cudaMemcpyHostToDevice));
         e->num_clips = nclips;
         e->evf.clip_cdf = e->d_clip_cdf; e->evd.clip_cdf = e->d_clip_cdf; e->evf.cfg.num_clips = nclips; e->evd.cfg.num_clips = nclips;
+        if (e->d_clip_model) { cudaFree(e->d_clip_model); e->d_clip_model = nullptr; }
+        e->evf.clip_model = nullptr; e->evd.clip_model = nullptr;
     }
     if (e->precision == 32) {
         std::vector<float> f(nf), s(ns);
@@ -174,6 +180,17 @@ int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *
         CK(cudaMemcpy(e->d_expert, frames_host, nf * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(e->d_shape, shape_host, ns * 8, cudaMemcpyHostToDevice));
         e->evd.expert = (const double *)e->d_expert; e->evd.clip_shape = (const double *)e->d_shape; e->evd.clip_adr = e->d_clip_adr;
     }
+    return 0;
+}
+
+int uhc_set_clip_models(UhcEngine *e, int nclips, const int *clip_model) {
+    if (!e || !clip_model || nclips != e->num_clips) { g_err = "uhc_set_clip_models: call after uhc_load_clips with one entry per clip"; return -2; }
+    for (int i = 0; i < nclips; i++) if (clip_model[i] < 0 || clip_model[i] >= e->nshape) { g_err = "uhc_set_clip_models: shape index out of range"; return -2; }
+    CK(cudaSetDevice(e->device));
+    if (e->d_clip_model) cudaFree(e->d_clip_model);
+    CK(cudaMalloc((void **)&e->d_clip_model, nclips * sizeof(int)));
+    CK(cudaMemcpy(e->d_clip_model, clip_model, nclips * sizeof(int), cudaMemcpyHostToDevice));
+    e->evf.clip_model = e->d_clip_model; e->evd.clip_model = e->d_clip_model;
     return 0;
 }
 

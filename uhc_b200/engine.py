@@ -76,7 +76,7 @@ def _ip(a):
 class Engine:
     """E environments on one GPU.  Mirrors HumanoidEnv.reset/step (+ the agent's custom_reward) for all envs at once."""
 
-    def __init__(self, num_envs, model=None, device=0, precision=32, **cfg):
+    def __init__(self, num_envs, model=None, device=0, precision=32, variants=None, **cfg):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError("uhc_b200.Engine needs a CUDA device (no CPU fallback)")
@@ -84,7 +84,8 @@ class Engine:
         self.lib = load_library()
         self.E, self.device, self.precision = int(num_envs), int(device), precision
         self.model = model or HumanoidModel()
-        self._ms = self.model.host_struct()
+        self.variants = variants
+        self._ms = self.model.host_struct(variants)
         self._cfg_kw = dict(cfg)
         self._cfg = make_cfg(precision, **cfg)
         h = C.c_void_p()
@@ -116,7 +117,7 @@ class Engine:
         self._cfg = make_cfg(self.precision, **self._cfg_kw)
         _chk(self.lib.uhc_engine_set_cfg(self.h, C.byref(self._cfg)))
 
-    def load_clips(self, experts, shapes=None):
+    def load_clips(self, experts, shapes=None, clip_models=None):
         """experts: list of dicts with the fields of Humanoid.qpos_fk (torch_smpl_humanoid.py:234-260); shapes: [C][17]."""
         lens = np.array([len(e["qpos"]) for e in experts], np.int32)
         frames = np.ascontiguousarray(np.concatenate([pack_expert(e) for e in experts]))
@@ -125,6 +126,8 @@ class Engine:
         _chk(self.lib.uhc_load_clips(self.h, C.c_int(len(experts)), _ip(lens), frames.ctypes.data_as(C.POINTER(C.c_double)),
                                      shp.ctypes.data_as(C.POINTER(C.c_double))))
         self.clip_len = lens
+        if clip_models is not None:
+            _chk(self.lib.uhc_set_clip_models(self.h, C.c_int(len(experts)), _ip(clip_models)))
 
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)

@@ -28,7 +28,7 @@ class UhcModelHost(C.Structure):
                 ("ent_row", C.POINTER(C.c_ubyte)), ("ent_col", C.POINTER(C.c_ubyte)), ("ee", C.POINTER(C.c_int)),
                 ("lvl_tab", C.POINTER(C.c_int)), ("lvl_pack", C.POINTER(C.c_int)),
                 ("dt", C.c_double), ("margin", C.c_double), ("mu", C.c_double), ("solref", C.c_double * 2),
-                ("solimp", C.c_double * 5), ("gravz", C.c_double)]
+                ("solimp", C.c_double * 5), ("gravz", C.c_double), ("nshape", C.c_int)]
 
 
 class HumanoidModel:
@@ -49,7 +49,7 @@ class HumanoidModel:
             inertia *= (s ** 5)[:, None, None]
             for b in range(NB):
                 hull[self.hull_adr[b]:self.hull_adr[b] + self.hull_num[b]] *= s[b]
-            invw = invw / s ** 3
+            invw = None          # recomputed below from the scaled mass properties
         self.offset, self.ipos, self.mass, self.inertia, self.hull, self.invw = offset, ipos, mass, inertia, hull, invw
         self.diffw = z["diffw"].astype(np.float64)
         self.jkp, self.jkd, self.torque_lim = (z[k].astype(np.float64) for k in ("jkp", "jkd", "torque_lim"))
@@ -64,6 +64,8 @@ class HumanoidModel:
         self.qpos0[3] = 1.0
         self.root_offset = z["body_gpos"][0].copy()  # mj_model.body_pos[1] in smpl_to_qpose (count_offset)
         self._topology()
+        if self.invw is None:
+            self.invw = self._invweight0()
         self._pack()
 
     def _topology(self):
@@ -131,6 +133,34 @@ class HumanoidModel:
         self.dof_sub_end = dse
         self.chains = chains
 
+    def _invweight0(self):
+        """body_invweight0 (translational): trace(Jv M^-1 Jv^T) / 3 at qpos0 (rest pose, all rotations identity) -- tools/compile_model.py."""
+        p = self.parent
+        gpos = np.zeros((NB, 3))
+        gpos[0] = self.z["body_gpos"][0]
+        for b in range(1, NB):
+            gpos[b] = gpos[p[b]] + self.offset[b]
+        axes = np.eye(3)[[2, 1, 0]]
+        xipos = gpos + self.ipos
+        Jv, Jw = np.zeros((NB, 3, NV)), np.zeros((NB, 3, NV))
+        for b in range(NB):
+            Jv[b, :, 0:3] = np.eye(3)
+            for k in range(3):
+                Jw[b, :, 3 + k] = np.eye(3)[k]
+                Jv[b, :, 3 + k] = np.cross(np.eye(3)[k], xipos[b] - gpos[0])
+            a = b
+            while a > 0:
+                for k in range(3):
+                    d = 6 + 3 * (a - 1) + k
+                    Jw[b, :, d] = axes[k]
+                    Jv[b, :, d] = np.cross(axes[k], xipos[b] - gpos[a])
+                a = p[a]
+        M = np.diag(self.armature)
+        for b in range(NB):
+            M += self.mass[b] * Jv[b].T @ Jv[b] + Jw[b].T @ self.inertia[b] @ Jw[b]
+        Minv = np.linalg.inv(M)
+        return np.array([np.trace(Jv[b] @ Minv @ Jv[b].T) / 3 for b in range(NB)])
+
     def _pack(self):
         bf = np.zeros((NB, BODYF))
         bf[:, 0:3], bf[:, 3:6], bf[:, 6] = self.offset, self.ipos, self.mass
@@ -147,10 +177,15 @@ class HumanoidModel:
         df[6:, 1], df[6:, 2], df[6:, 3] = self.jkp, self.jkd, self.torque_lim
         self.body_f, self.dof_f = np.ascontiguousarray(bf), np.ascontiguousarray(df)
 
-    def host_struct(self):
-        """ctypes struct of host pointers for uhc_engine_create / the emulation (arrays kept alive on self)."""
+    def host_struct(self, variants=None):
+        """ctypes struct of host pointers for uhc_engine_create / the emulation (arrays kept alive on self).
+        variants: optional list of HumanoidModel shape variants (same topology); variant 0 must be `self`."""
         h = UhcModelHost()
         keep = self._keep = {}
+        models = variants or [self]
+        assert models[0] is self and all(len(m.hull) == len(self.hull) for m in models)
+        body_f = np.concatenate([m.body_f for m in models])
+        hull = np.concatenate([m.hull for m in models])
 
         def ptr(name, arr, ct):
             a = np.ascontiguousarray(arr)
@@ -158,7 +193,8 @@ class HumanoidModel:
             return a.ctypes.data_as(C.POINTER(ct))
 
         h.nvert, h.nnbr = len(self.hull), len(self.nbr)
-        h.body_f, h.dof_f, h.hull = ptr("bf", self.body_f, C.c_double), ptr("df", self.dof_f, C.c_double), ptr("hull", self.hull, C.c_double)
+        h.body_f, h.dof_f, h.hull = ptr("bf", body_f, C.c_double), ptr("df", self.dof_f, C.c_double), ptr("hull", hull, C.c_double)
+        h.nshape = len(models)
         for n in ("hull_adr", "hull_num", "nbr", "nbradr", "parent", "depth", "child_adr", "child", "body_sub_end", "dep",
                   "madr", "dof_sub_end", "dof_body", "ee", "lvl_tab", "lvl_pack"):
             setattr(h, n, ptr(n, getattr(self, n).astype(np.int32), C.c_int))
