@@ -63,16 +63,16 @@ class BatchedAgent:
     def __init__(self, num_envs, clips, shapes=None, device=0, seed=1, precision=32, policy_hsize=(2048, 1024, 512),
                  value_hsize=(2048, 1024, 512), htype="gelu", log_std=-2.3, policy_lr=5e-5, value_lr=3e-4, gamma=0.95, tau=0.95,
                  clip_epsilon=0.2, num_optim_epoch=10, grad_clip=40.0, t_min=5, t_max=300, noise_rate=1.0, rank=0, world=1,
-                 grad_sync=None, model=None, update_tc=True, **env_cfg):
+                 grad_sync=None, model=None, update_tc=True, variants=None, clip_models=None, **env_cfg):
         import torch
         self.torch = torch
         self.dev = torch.device("cuda", device)
         torch.cuda.set_device(self.dev)
         self.E, self.seed, self.rank, self.world = num_envs, seed, rank, world
         self.auto_reset = bool(env_cfg.pop("auto_reset", True))
-        self.engine = Engine(num_envs, model=model, device=device, precision=precision, auto_reset=int(self.auto_reset), t_min=t_min, t_max=t_max,
+        self.engine = Engine(num_envs, model=model, device=device, precision=precision, variants=variants, auto_reset=int(self.auto_reset), t_min=t_min, t_max=t_max,
                              reset_seed=seed * 7919 + rank * 104729 + 1, **env_cfg)
-        self.engine.load_clips(clips, shapes)
+        self.engine.load_clips(clips, shapes, clip_models)   # clip_models: body-shape variant per clip (the reference rebuilds the robot per clip)
         self.sampler = ClipSampler(self.engine.clip_len, t_min, t_max, seed=seed * 9973 + rank)
         self.policy = nn.MLPNet(OBS_DIM, policy_hsize, ACT_DIM, htype, device=self.dev, head_name="action_mean", seed=seed)
         self.value = nn.MLPNet(OBS_DIM, value_hsize, 1, htype, device=self.dev, head_name="value_head", seed=seed + 1)
