@@ -1,7 +1,7 @@
 // mlp_tcgen05.cu -- tensor-core Linear(+bias+activation) for the rollout-time policy/value forward:
 //   y[M][N] = act(x[M][Kp] W[N][Kp]^T + b),  bf16 operands (K-major, zero padded to Kp % 64 == 0), fp32 accumulation in TMEM.
 // sm_100a only: TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring -> tcgen05.mma (one elected thread, UMMA 128x128x16,
-// cta_group::1) -> tcgen05.ld epilogue (bias + activation fused, bf16 and/or fp32 store).  Warp roles: 0 = TMA producer,
+// cta_group::1, 128 TMEM columns per CTA, 2 CTAs/SM) -> tcgen05.ld epilogue (bias + activation fused, bf16 and/or fp32 store).  Warp roles: 0 = TMA producer,
 // 1 = MMA issuer + TMEM allocator, 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -11,7 +11,7 @@
 #include "../../include/uhc_nn.h"
 
 namespace {
-constexpr int BM = 128, BN = 128, BK = 64, UK = 16, STAGES = 4;
+constexpr int BM = 128, BN = 128, BK = 64, UK = 16, STAGES = 3;   // 3 stages x 32 KB -> two CTAs per SM: one CTA's epilogue overlaps the other's MMAs
 constexpr int STAGE_BYTES = (BM * BK + BN * BK) * 2;             // 32 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;    // + alignment slack + barriers
 thread_local std::string g_tc_err;
@@ -58,7 +58,7 @@ __device__ __forceinline__ float act_f(float z, int act) {
     return z;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
             __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act) {
     extern __shared__ uint8_t smem_raw[];
