@@ -144,3 +144,37 @@ def test_mixed_body_shapes_match_oracle(golden_dir):
                 assert np.abs(eng.get_state(e)["qpos"] - oes[c].d.qpos).max() < 1e-4
                 assert abs(r[e] - ro) < 1e-4
     eng.close()
+
+
+@pytest.mark.parametrize("kind", ["sitting", "airborne"])
+def test_varying_contact_counts_match_oracle(kind):
+    """BASELINE configs[4]-style synthetic clips (root lowered to a sitting height -> many body/floor contacts; hops -> none):
+    contact counts from 0 to >20 per env, engine vs oracle on the same seeded actions until the first termination."""
+    import torch
+    from oracle import oracle as O
+    from uhc_b200 import motion_lib
+    from uhc_b200.engine import Engine
+    ex = motion_lib.synthetic_clip(60, np.random.default_rng(5), kind=kind)
+    eng = Engine(4)
+    eng.load_clips([ex], None)
+    obs = eng.reset().cpu().numpy().copy()
+    oe = O.Env(O.Model(), ex, np.zeros(17))
+    assert np.abs(oe.reset() - obs[0]).max() < 1e-4
+    rng = np.random.RandomState(2)
+    maxcon, steps = 0, 0
+    for t in range(40):
+        a = rng.normal(0, 0.1, 105).astype(np.float32)
+        o, r, ci, f, en, p = eng.step(torch.tensor(np.tile(a, (4, 1)), device="cuda"))
+        _, ro, done, info = oe.step(a.astype(np.float64))
+        st = eng.get_state(1)
+        maxcon = max(maxcon, st["ncon"], oe.d.ncon)
+        assert oe.d.ncon <= 40, "oracle contact count exceeds the kernel's capacity: raise MAXCON"
+        assert np.abs(st["qpos"] - oe.d.qpos).max() < 1e-3, (t, np.abs(st["qpos"] - oe.d.qpos).max())
+        assert bool(f[1]) == info["fail"]
+        steps += 1
+        if info["fail"] or info["end"]:
+            break
+    assert steps >= 3
+    if kind == "sitting":
+        assert maxcon >= 12
+    eng.close()
