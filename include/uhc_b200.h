@@ -34,8 +34,8 @@ typedef struct {
     const double *dof_f;    /* [75][4]  armature kp kd torque_limit */
     const double *hull;     /* [nvert][3] convex-hull vertices, body frame */
     const int *hull_adr, *hull_num, *nbr, *nbradr;
-    const int *parent, *depth, *child_adr, *child, *body_sub_end, *dep, *madr, *dof_sub_end, *dof_body;
-    const short *rowadr; const unsigned char *colidx, *ent_row, *ent_col; const int *ee;
+    const int *parent, *depth, *child_adr, *child, *body_sub_end;   /* kinematic tree, bodies numbered depth-first */
+    const int *ee;          /* [5] end-effector bodies of the reward (smpl_parser.py:228) */
     const int *lvl_tab;     /* [9][5][5] per tree level and lane group: body, parent's group, groups of up to 3 children (-1 none) */
     const int *lvl_pack;    /* [9][5] the same, packed: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15 */
     double dt, margin, mu, solref[2], solimp[5], gravz;

@@ -12,8 +12,7 @@ using namespace uhc;
 template <class Real>
 struct Emu {
     std::vector<Real> body_f, dof_f, hull, state, expert, shape;
-    std::vector<int> lvl_tab, lvl_pack, hull_adr, hull_num, nbr, nbradr, parent, depth, child_adr, child, body_sub_end, dep, madr, dof_sub_end, dof_body, ee, istate, clip_adr;
-    std::vector<short> rowadr; std::vector<unsigned char> colidx, ent_row, ent_col;
+    std::vector<int> lvl_tab, lvl_pack, hull_adr, hull_num, nbr, nbradr, parent, depth, child_adr, child, body_sub_end, ee, istate, clip_adr;
     EngineView<Real> ev; Work<Real> w; int E;
 };
 
@@ -36,14 +35,11 @@ static Emu<Real> *create(const UhcModelHost *m, const UhcEnvCfg *cfg, int E) {
     cp(e->body_f, m->body_f, NB * BODYF); cp(e->dof_f, m->dof_f, NV * 4); cp(e->hull, m->hull, (size_t)m->nvert * 3);
     cp(e->hull_adr, m->hull_adr, NB); cp(e->hull_num, m->hull_num, NB); cp(e->nbr, m->nbr, m->nnbr); cp(e->nbradr, m->nbradr, m->nvert + 1);
     cp(e->parent, m->parent, NB); cp(e->depth, m->depth, NB); cp(e->child_adr, m->child_adr, NB + 1); cp(e->child, m->child, NB - 1);
-    cp(e->body_sub_end, m->body_sub_end, NB); cp(e->dep, m->dep, NV); cp(e->madr, m->madr, NV); cp(e->dof_sub_end, m->dof_sub_end, NV);
-    cp(e->dof_body, m->dof_body, NV); cp(e->ee, m->ee, 5); cp(e->lvl_tab, m->lvl_tab, (MAXLEVEL + 1) * LVL_G * 5); cp(e->lvl_pack, m->lvl_pack, (MAXLEVEL + 1) * LVL_G);
-    cp(e->rowadr, m->rowadr, NV * 32); cp(e->colidx, m->colidx, NV * 32); cp(e->ent_row, m->ent_row, 1221); cp(e->ent_col, m->ent_col, 1221);
+    cp(e->body_sub_end, m->body_sub_end, NB); cp(e->ee, m->ee, 5); cp(e->lvl_tab, m->lvl_tab, (MAXLEVEL + 1) * LVL_G * 5); cp(e->lvl_pack, m->lvl_pack, (MAXLEVEL + 1) * LVL_G);
     Model<Real> &M = e->ev.model;
     M.body_f = e->body_f.data(); M.dof_f = e->dof_f.data(); M.hull = e->hull.data(); M.hull_adr = e->hull_adr.data(); M.hull_num = e->hull_num.data();
     M.nbr = e->nbr.data(); M.nbradr = e->nbradr.data(); M.parent = e->parent.data(); M.depth = e->depth.data(); M.child_adr = e->child_adr.data();
-    M.child = e->child.data(); M.body_sub_end = e->body_sub_end.data(); M.dep = e->dep.data(); M.madr = e->madr.data(); M.dof_sub_end = e->dof_sub_end.data();
-    M.dof_body = e->dof_body.data(); M.rowadr = e->rowadr.data(); M.colidx = e->colidx.data(); M.ent_row = e->ent_row.data(); M.ent_col = e->ent_col.data();
+    M.child = e->child.data(); M.body_sub_end = e->body_sub_end.data();
     M.ee = e->ee.data(); M.lvl_tab = e->lvl_tab.data(); M.lvl_pack = e->lvl_pack.data();
     M.dt = (Real)m->dt; M.margin = (Real)m->margin; M.mu = (Real)m->mu; M.solref0 = (Real)m->solref[0]; M.solref1 = (Real)m->solref[1];
     M.simp0 = (Real)m->solimp[0]; M.simp1 = (Real)m->solimp[1]; M.simp2 = (Real)m->solimp[2]; M.simp3 = (Real)m->solimp[3]; M.simp4 = (Real)m->solimp[4];
@@ -105,7 +101,7 @@ void emu_get_state(void *h, int prec, int env, double *out, int *iout) {
 }
 // forward pass only on an arbitrary state: returns dense M, C, qacc, xpos for unit tests
 void emu_forward(void *h, int prec, const double *qpos, const double *qvel, const double *tau, const double *fapp, const double *aw, double *Msparse,
-                 double *Cout, double *qacc, double *xpos, int *ncon, int *iters) {
+                 double *Cout, double *qacc, double *xpos, int *ncon, int *iters) {   // Msparse: unused (no joint-space matrix exists)
     DISPATCH(h, prec, {
         Work<Real> &w = e->w;
         for (int i = 0; i < NQ; i++) w.q[i] = (Real)qpos[i];

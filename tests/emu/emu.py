@@ -102,8 +102,4 @@ class Emu:
         ncon, iters = C.c_int(0), C.c_int(0)
         self.lib.emu_forward(self.h, self.prec, _p(np.ascontiguousarray(qpos, dtype=np.float64)), _p(np.ascontiguousarray(qvel, dtype=np.float64)),
                              _p(tau), _p(fapp), _p(aw_), _p(Ms), _p(Cc), _p(qa), _p(xp), C.byref(ncon), C.byref(iters))
-        M = np.zeros((75, 75))
-        m = self.model
-        M[m.ent_row, m.ent_col] = Ms
-        M = M + M.T - np.diag(np.diag(M))
-        return dict(M=M, C=Cc, qacc=qa, xpos=xp.reshape(24, 3), ncon=ncon.value, iters=iters.value)
+        return dict(C=Cc, qacc=qa, xpos=xp.reshape(24, 3), ncon=ncon.value, iters=iters.value)

@@ -70,10 +70,6 @@ struct Model {
     const Real *hull;     // [nvert][3] body-local
     const int *hull_adr, *hull_num, *nbr, *nbradr;
     const int *parent, *depth, *child_adr, *child, *body_sub_end;
-    const int *dep, *madr, *dof_sub_end, *dof_body;
-    const short *rowadr;          // [NV][32]: madr[anc(k,s)]
-    const unsigned char *colidx;  // [NV][32]: anc(k,s)
-    const unsigned char *ent_row, *ent_col;  // [NNZ]
     const int *ee;                // [5]
     const int *lvl_tab;           // [MAXLEVEL+1][LVL_G][5]: body, parent's group, groups of <=3 children (-1 = none)
     const int *lvl_pack;          // [MAXLEVEL+1][LVL_G]: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15

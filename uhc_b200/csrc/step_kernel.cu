@@ -81,13 +81,8 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     int *p;
 #define CPI(field, n) do { if (dev_copy(e, &p, m->field, (size_t)(n))) return -1; M.field = p; } while (0)
     CPI(hull_adr, NB); CPI(hull_num, NB); CPI(nbr, m->nnbr); CPI(nbradr, m->nvert + 1); CPI(parent, NB); CPI(depth, NB); CPI(child_adr, NB + 1);
-    CPI(child, NB - 1); CPI(body_sub_end, NB); CPI(dep, NV); CPI(madr, NV); CPI(dof_sub_end, NV); CPI(dof_body, NV); CPI(ee, 5); CPI(lvl_tab, (MAXLEVEL + 1) * LVL_G * 5); CPI(lvl_pack, (MAXLEVEL + 1) * LVL_G);
+    CPI(child, NB - 1); CPI(body_sub_end, NB); CPI(ee, 5); CPI(lvl_tab, (MAXLEVEL + 1) * LVL_G * 5); CPI(lvl_pack, (MAXLEVEL + 1) * LVL_G);
 #undef CPI
-    short *ps; if (dev_copy(e, &ps, m->rowadr, (size_t)NV * 32)) return -1; M.rowadr = ps;
-    unsigned char *pc;
-    if (dev_copy(e, &pc, m->colidx, (size_t)NV * 32)) return -1; M.colidx = pc;
-    if (dev_copy(e, &pc, m->ent_row, (size_t)1221)) return -1; M.ent_row = pc;
-    if (dev_copy(e, &pc, m->ent_col, (size_t)1221)) return -1; M.ent_col = pc;
     M.dt = (Real)m->dt; M.margin = (Real)m->margin; M.mu = (Real)m->mu; M.solref0 = (Real)m->solref[0]; M.solref1 = (Real)m->solref[1];
     M.simp0 = (Real)m->solimp[0]; M.simp1 = (Real)m->solimp[1]; M.simp2 = (Real)m->solimp[2]; M.simp3 = (Real)m->solimp[3]; M.simp4 = (Real)m->solimp[4];
     M.gravz = (Real)m->gravz;

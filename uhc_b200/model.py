@@ -2,8 +2,8 @@
 
 Loads the compiled humanoid (uhc_b200/assets/smpl_neutral_model.npz, produced by tools/compile_model.py from the
 reference's humanoid_smpl_neutral_mesh.xml + STL hulls) and derives the topology tables the kernels index with:
-depth-first dof numbering (root 6 dofs, then 3 hinges z,y,x per body), the tree-sparse row-chain layout of the joint-space
-inertia matrix (row k stores M[k][anc(k,0..dep k)]), children lists, subtree ranges.
+depth-first dof numbering (root 6 dofs, then 3 hinges z,y,x per body), children lists, subtree ranges, and the per-tree-level
+lane-group table of the articulated-body solve.
 Mirrors what SMPLConverter exposes to the reference env (uhc/smpllib/smpl_mujoco.py:259-281): kp/kd/torque-limit/diff-weight.
 """
 import ctypes as C
@@ -23,9 +23,7 @@ class UhcModelHost(C.Structure):
                 ("hull_adr", C.POINTER(C.c_int)), ("hull_num", C.POINTER(C.c_int)), ("nbr", C.POINTER(C.c_int)),
                 ("nbradr", C.POINTER(C.c_int)), ("parent", C.POINTER(C.c_int)), ("depth", C.POINTER(C.c_int)),
                 ("child_adr", C.POINTER(C.c_int)), ("child", C.POINTER(C.c_int)), ("body_sub_end", C.POINTER(C.c_int)),
-                ("dep", C.POINTER(C.c_int)), ("madr", C.POINTER(C.c_int)), ("dof_sub_end", C.POINTER(C.c_int)),
-                ("dof_body", C.POINTER(C.c_int)), ("rowadr", C.POINTER(C.c_short)), ("colidx", C.POINTER(C.c_ubyte)),
-                ("ent_row", C.POINTER(C.c_ubyte)), ("ent_col", C.POINTER(C.c_ubyte)), ("ee", C.POINTER(C.c_int)),
+                ("ee", C.POINTER(C.c_int)),
                 ("lvl_tab", C.POINTER(C.c_int)), ("lvl_pack", C.POINTER(C.c_int)),
                 ("dt", C.c_double), ("margin", C.c_double), ("mu", C.c_double), ("solref", C.c_double * 2),
                 ("solimp", C.c_double * 5), ("gravz", C.c_double), ("nshape", C.c_int)]
@@ -96,42 +94,6 @@ class HumanoidModel:
         self.lvl_tab = np.ascontiguousarray(tab.reshape(-1))
         self.lvl_pack = np.ascontiguousarray(((tab[:, :, 0] + 1) | (np.maximum(tab[:, :, 1], 0) << 6) | ((tab[:, :, 2] + 1) << 9) | ((tab[:, :, 3] + 1) << 12) | ((tab[:, :, 4] + 1) << 15)).astype(np.int32).reshape(-1))
         self.dof_body = np.array([0] * 6 + [1 + d // 3 for d in range(NU)], np.int32)
-        # ancestor chain (by depth) of every dof
-        chains = []
-        for k in range(NV):
-            b = self.dof_body[k]
-            if b == 0:
-                chains.append(list(range(k + 1)))
-                continue
-            bodies, a = [], b
-            while a > 0:
-                bodies.append(a)
-                a = p[a]
-            ch_k = list(range(6))
-            for a in reversed(bodies):
-                d0 = 6 + 3 * (a - 1)
-                ch_k += [d0, d0 + 1, d0 + 2] if a != b else list(range(d0, k + 1))
-            chains.append(ch_k)
-        self.dep = np.array([len(c) - 1 for c in chains], np.int32)
-        self.madr = np.concatenate([[0], np.cumsum(self.dep + 1)])[:-1].astype(np.int32)
-        self.nnz = int((self.dep + 1).sum())
-        assert self.nnz == 1221 and self.dep.max() == 29 and int((self.dep[:39] + 1).sum()) == 420, (self.nnz, self.dep.max())
-        self.rowadr = np.zeros((NV, 32), np.int16)
-        self.colidx = np.zeros((NV, 32), np.uint8)
-        ent_row, ent_col = [], []
-        for k, c in enumerate(chains):
-            for s, a in enumerate(c):
-                self.rowadr[k, s] = self.madr[a]
-                self.colidx[k, s] = a
-                ent_row.append(k)
-                ent_col.append(a)
-        self.ent_row, self.ent_col = np.array(ent_row, np.uint8), np.array(ent_col, np.uint8)
-        dse = np.zeros(NV, np.int32)
-        for k in range(NV):
-            b = self.dof_body[k]
-            dse[k] = NV - 1 if b == 0 else 6 + 3 * (self.body_sub_end[b] - 1) + 2
-        self.dof_sub_end = dse
-        self.chains = chains
 
     def _invweight0(self):
         """body_invweight0 (translational): trace(Jv M^-1 Jv^T) / 3 at qpos0 (rest pose, all rotations identity) -- tools/compile_model.py."""
@@ -195,11 +157,8 @@ class HumanoidModel:
         h.nvert, h.nnbr = len(self.hull), len(self.nbr)
         h.body_f, h.dof_f, h.hull = ptr("bf", body_f, C.c_double), ptr("df", self.dof_f, C.c_double), ptr("hull", hull, C.c_double)
         h.nshape = len(models)
-        for n in ("hull_adr", "hull_num", "nbr", "nbradr", "parent", "depth", "child_adr", "child", "body_sub_end", "dep",
-                  "madr", "dof_sub_end", "dof_body", "ee", "lvl_tab", "lvl_pack"):
+        for n in ("hull_adr", "hull_num", "nbr", "nbradr", "parent", "depth", "child_adr", "child", "body_sub_end", "ee", "lvl_tab", "lvl_pack"):
             setattr(h, n, ptr(n, getattr(self, n).astype(np.int32), C.c_int))
-        h.rowadr, h.colidx = ptr("rowadr", self.rowadr, C.c_short), ptr("colidx", self.colidx, C.c_ubyte)
-        h.ent_row, h.ent_col = ptr("er", self.ent_row, C.c_ubyte), ptr("ec", self.ent_col, C.c_ubyte)
         h.dt, h.margin, h.mu, h.gravz = self.dt, self.margin, self.mu, self.gravz
         h.solref = (C.c_double * 2)(*self.solref)
         h.solimp = (C.c_double * 5)(*self.solimp)
