@@ -60,13 +60,15 @@ __device__ __forceinline__ float act_f(float z, int act) {
 
 __global__ void __launch_bounds__(192, 2)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
-            __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act) {
+            __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act, int ksplit) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], tmem_full
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, nkb = Kp / BK;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // split-K (gridDim.z slices of the reduction, fp32 atomic accumulation into yf): used for dW = dZ^T X whose output has few tiles
+    const int nkb_all = Kp / BK, kb0 = (int)(((long)nkb_all * blockIdx.z) / ksplit), nkb = (int)(((long)nkb_all * (blockIdx.z + 1)) / ksplit) - kb0;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
 
     if (warp == 0 && lane == 0) {
@@ -92,8 +94,8 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
                 const uint32_t a = smem_u32(smem + s * STAGE_BYTES), b = a + BM * BK * 2;
-                tma_load_2d(a, &mapA, full0 + 8 * s, kb * BK, m0);
-                tma_load_2d(b, &mapB, full0 + 8 * s, kb * BK, n0);
+                tma_load_2d(a, &mapA, full0 + 8 * s, (kb0 + kb) * BK, m0);
+                tma_load_2d(b, &mapB, full0 + 8 * s, (kb0 + kb) * BK, n0);
             }
         }
     } else if (warp == 1) {
@@ -134,13 +136,18 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = nb + j;
-                    const float z = n < N ? __uint_as_float(r[j]) + (bias ? __ldg(bias + n) : 0.f) : 0.f;
+                    const float z = n < N ? __uint_as_float(r[j]) + ((bias && blockIdx.z == 0) ? __ldg(bias + n) : 0.f) : 0.f;
                     if (zf && n < N) zf[(size_t)row * N + n] = z;       // pre-activation (for the backward pass)
                     v[j] = n < N ? act_f(z, act) : 0.f;
                 }
                 if (yf) {
+                    if (ksplit > 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < N) yf[(size_t)row * N + nb + j] = v[j];
+                        for (int j = 0; j < 32; ++j) if (nb + j < N) atomicAdd(yf + (size_t)row * N + nb + j, v[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (nb + j < N) yf[(size_t)row * N + nb + j] = v[j];
+                    }
                 }
                 if (ybf && nb < ldy) {
                     if (nb + 32 <= ldy) {
@@ -261,8 +268,17 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
     }
     CUtensorMap ma, mb;
     if (make_map(&ma, x_bf16, M, Kp) || make_map(&mb, W_bf16, N, Kp)) return -1;
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-    k_linear_tc<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act);
+    // split the reduction when the output has too few tiles to fill the GPU (only legal for a plain fp32 accumulate output)
+    const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM), nkb = Kp / BK;
+    int ksplit = 1;
+    if (!y_bf16_or_null && !z_f32_or_null && act == UHC_ACT_NONE && y_f32_or_null && tiles < 148 && nkb >= 32) {
+        ksplit = (296 + tiles - 1) / tiles;
+        if (ksplit > nkb / 8) ksplit = nkb / 8;
+        if (ksplit < 1) ksplit = 1;
+        if (ksplit > 1 && cudaMemsetAsync(y_f32_or_null, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "memset failed"; return -1; }
+    }
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, ksplit);
+    k_linear_tc<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act, ksplit);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
     return 0;
