@@ -16,7 +16,7 @@ def build(force=False, verbose=False):
     deps = srcs + [os.path.join(csrc, d) for d in DEPS] + [os.path.abspath(__file__)]
     if not force and os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in deps if os.path.exists(d)):
         return SO
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("UHC_NVCC_EXTRA", "").split()
     cmd = ["nvcc"] + flags + ["-o", SO] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:

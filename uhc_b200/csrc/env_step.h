@@ -132,7 +132,12 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     TOPO_DECL(mdl);
 #pragma unroll 1
     for (int it = 0; it < NSUB; ++it) {
-        iters += substep_dynamics<Real, ObsT>(mdl, ev.cfg, w, tp, target, it, true, torque_out);
+#ifndef UHC_SYNC_PERIOD
+#define UHC_SYNC_PERIOD 1
+#endif
+        const bool sync_now = (it % UHC_SYNC_PERIOD) == 0;
+        UHC_CTA_SYNC(sync_now);
+        iters += substep_dynamics<Real, ObsT>(mdl, ev.cfg, w, tp, target, it, true, torque_out, sync_now);
         if (w.ncon > maxcon) maxcon = w.ncon;
         if (it == NSUB - 1) world_quat(mdl, w.q, w);  // pose of the last forward pass (what data.body_xquat holds)
         integrate(mdl, w);

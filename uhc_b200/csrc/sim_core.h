@@ -91,9 +91,10 @@ template <class Real>
 struct Work {
     Real q[NQ], v[NV + 1], aw[NV + 1], act[ACT_DIM + 3];
     Real xpos[NB][3], xmat[NB][9], xipos[NB][3], xquat[NB][4];
-    Real S[NV][6];
+    alignas(16) Real S[NV][6];
     Real Ib[NB][10];              // per-body rigid inertia about O, world axes (of the last forward pass)
-    Real aU[NV][6], aDinv[NV + 1], au[NV + 1], aArm[NV + 1];   // articulated-body sweep: U_j = IA S_j, 1 / D_j, u_j, joint-space diagonal
+    alignas(16) Real aU[NV][6];   // articulated-body sweep: columns of  U D^-1  per 3-dof block (U = IA S, D = S^T U + arm)
+    Real au[NV + 1];                // D^-1 u per block
     Real C[NV + 1], fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
     Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
     // contacts
@@ -103,6 +104,15 @@ struct Work {
 };
 
 // ------------------------------------------------------------------------------------------------ scalar helpers
+// reciprocal: hardware approximation + one Newton step on the GPU (within 1 ulp; no slow-path branch), exact division elsewhere
+UHC_DEV float rcp_(float x) {
+#if defined(__CUDA_ARCH__)
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+    return 1.0f / x;
+#endif
+}
+UHC_DEV double rcp_(double x) { return 1.0 / x; }
 UHC_DEV float rsqrt_(float x) { return 1.0f / sqrtf(x); }
 UHC_DEV double rsqrt_(double x) { return 1.0 / sqrt(x); }
 // compact sin/cos (Cody-Waite reduction by pi/2, degree-7/8 minimax polynomials; |err| < 2e-7 for |x| < 1e3) -- joint angles and
@@ -192,6 +202,30 @@ template <class R> UHC_DEV void sym6_mul(const R *K, const R *x, R *y) {
         y[i] = s;
     }
 }
+
+// ------------------------------------------------------------------------------------------------ packed pairs
+// Two Reals handled by one instruction where the hardware has it: sm_100 issues fp32 pairs as FFMA2 / FMUL2 / FADD2 and loads
+// them from shared memory as one 64-bit access; doubles (and the host emulation) fall back to component-wise arithmetic.
+template <class R> struct alignas(2 * sizeof(R)) Pr { R x, y; };
+template <class R> UHC_DEV Pr<R> pbc(R s) { Pr<R> r; r.x = s; r.y = s; return r; }
+template <class R> UHC_DEV Pr<R> pfma(Pr<R> a, Pr<R> b, Pr<R> c) { Pr<R> r; r.x = a.x * b.x + c.x; r.y = a.y * b.y + c.y; return r; }
+template <class R> UHC_DEV Pr<R> pmul(Pr<R> a, Pr<R> b) { Pr<R> r; r.x = a.x * b.x; r.y = a.y * b.y; return r; }
+template <class R> UHC_DEV Pr<R> padd(Pr<R> a, Pr<R> b) { Pr<R> r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+template <> UHC_DEV Pr<float> pfma<float>(Pr<float> a, Pr<float> b, Pr<float> c) {
+    const float2 t = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y)); Pr<float> r; r.x = t.x; r.y = t.y; return r;
+}
+template <> UHC_DEV Pr<float> pmul<float>(Pr<float> a, Pr<float> b) {
+    const float2 t = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); Pr<float> r; r.x = t.x; r.y = t.y; return r;
+}
+template <> UHC_DEV Pr<float> padd<float>(Pr<float> a, Pr<float> b) {
+    const float2 t = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); Pr<float> r; r.x = t.x; r.y = t.y; return r;
+}
+#endif
+// 6-vectors as three pairs
+template <class R> UHC_DEV R pdot6(const Pr<R> *a, const Pr<R> *b) { Pr<R> t = pmul(a[0], b[0]); t = pfma(a[1], b[1], t); t = pfma(a[2], b[2], t); return t.x + t.y; }
+template <class R> UHC_DEV void paxpy6(R s, const Pr<R> *x, Pr<R> *y) { const Pr<R> ss = pbc(s); y[0] = pfma(ss, x[0], y[0]); y[1] = pfma(ss, x[1], y[1]); y[2] = pfma(ss, x[2], y[2]); }
+template <class R> UHC_DEV const Pr<R> *as_pairs(const R *p) { return reinterpret_cast<const Pr<R> *>(p); }
 
 // ------------------------------------------------------------------------------------------------ warp primitives
 #ifndef UHC_EMU
@@ -358,109 +392,130 @@ UHC_DEV void rigid_row(const Real *I, int r, Real *row) {
 
 // x <- H^-1 x  (x: 75-vector in shared memory).  arm_scale: extra joint-space diagonal = arm_scale * kd_i (0 for none).
 // Lane layout: the <= 5 bodies of one tree level are processed together, 6 lanes per body (lane = 6 g + r owns ROW r of that
-// body's articulated inertia; the bias wrench is replicated in the group).  Leaves -> root eliminates the joint dofs
-// (U = IA S, D = S.U + arm, u = b - S.pA ; IA -= U U^T / D ; pA += U u / D), root -> leaves back-substitutes.
+// body's articulated inertia; the bias wrench is replicated in the group).  A body's three hinge dofs (the root: its rotation
+// block, then its translation block) are eliminated as ONE 3x3 block:
+//   leaves -> root:  U = IA S (6x3), D = S^T U + arm (3x3), u = b - S^T pA ;  IA -= U D^-1 U^T ;  pA += U D^-1 u
+//   root -> leaves:  x = D^-1 u - (U D^-1)^T a_parent ;  a = a_parent + S x
+// so only  U D^-1  and  D^-1 u  are kept for the back-substitution.
 template <class Real>
 UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bool use_contacts, Real *x) {
-    LVARA(Real, row, 6); LVARA(Real, pA, 6); LVARA(Real, crow, 6); LVARA(Real, cpA, 6); LVARA(Real, trow, 6); LVARA(Real, tpA, 6);
-    LVARA(Real, Uf, 6);
-    LVARA(Real, Sv, 6);
-    LVAR(Real, Ur); LVAR(int, body); LVAR(int, src); LVAR(int, act); LVAR(int, gbase); LVAR(int, rr); LVAR(int, ent);
+    typedef Pr<Real> P;
+    LVARA(P, row, 3); LVARA(P, pA, 3); LVARA(P, nrow, 3); LVARA(P, npA, 3); LVARA(Real, trow, 6); LVARA(Real, tpA, 6);
+    LVARA(Real, Ur, 3); LVARA(Real, armv, 3);
+    LVAR(int, body); LVAR(int, src); LVAR(int, act); LVAR(int, rr); LVAR(int, ent); LVAR(int, entn);
     LANES_BEGIN
-    for (int i = 0; i < 6; i++) { LVA(crow)[i] = 0; LVA(cpA)[i] = 0; }
-    const int g = lane / 6;
-    LV(gbase) = g < LVL_G ? 6 * g : 24; LV(rr) = lane - 6 * g;
-    for (int i = lane; i < NV; i += 32) w.aArm[i] = UHC_LDG(m.dof_f + 4 * i) + arm_scale * UHC_LDG(m.dof_f + 4 * i + 2);
+    for (int i = 0; i < 3; i++) { LVA(row)[i] = pbc(Real(0)); LVA(pA)[i] = pbc(Real(0)); }
+    LV(rr) = lane - 6 * (lane / 6);
+    LV(entn) = lane < 6 * LVL_G ? UHC_LDG(m.lvl_pack + MAXLEVEL * LVL_G + lane / 6) : 0;
     LANES_END
 #pragma unroll 1
     for (int lvl = MAXLEVEL; lvl >= 0; --lvl) {
         LANES_BEGIN
         const int g = lane / 6, r = LV(rr);
-        const int e = g < LVL_G ? UHC_LDG(m.lvl_pack + lvl * LVL_G + g) : 0;
+        const int e = LV(entn);            // this level's table entry was fetched one level ahead
+        LV(entn) = (g < LVL_G && lvl > 0) ? UHC_LDG(m.lvl_pack + (lvl - 1) * LVL_G + g) : 0;
         const int b = (e & 63) - 1;
         LV(ent) = e; LV(body) = b;
-#pragma unroll
-        for (int i = 0; i < 6; i++) { LVA(row)[i] = 0; LVA(pA)[i] = 0; }
+        Real ri[6] = {0, 0, 0, 0, 0, 0};
         if (b >= 0) {
-            rigid_row(w.Ib[b], r, LVA(row));
-            if (use_contacts) contact_matrix_row(m, w, b, r, LVA(row));
+            rigid_row(w.Ib[b], r, ri);
+            if (use_contacts) contact_matrix_row(m, w, b, r, ri);
         }
+        for (int i = 0; i < 3; i++) { LVA(nrow)[i].x = ri[2 * i]; LVA(nrow)[i].y = ri[2 * i + 1]; LVA(npA)[i] = pbc(Real(0)); }
         LANES_END
 #pragma unroll 1
-        for (int k = 0; k < 3; ++k) {  // children of this level's bodies (they sit one level deeper, results in crow / cpA)
+        for (int k = 0; k < 3; ++k) {  // children of this level's bodies: they sit one level deeper, their results are still in row / pA
             LANES_BEGIN
             const int cg = ((LV(ent) >> (9 + 3 * k)) & 7) - 1;
             LV(act) = cg >= 0; LV(src) = cg >= 0 ? cg * 6 + LV(rr) : lane;
+            for (int i = 0; i < 3; i++) { LVA(trow)[2 * i] = LVA(row)[i].x; LVA(trow)[2 * i + 1] = LVA(row)[i].y; LVA(tpA)[2 * i] = LVA(pA)[i].x; LVA(tpA)[2 * i + 1] = LVA(pA)[i].y; }
             LANES_END
             if (!WANY(act)) continue;
-            WSHFL(trow, crow, 6, LV(src));
-            WSHFL(tpA, cpA, 6, LV(src));
+            WSHFL(trow, trow, 6, LV(src));
+            WSHFL(tpA, tpA, 6, LV(src));
             LANES_BEGIN
-            if (LV(act)) for (int i = 0; i < 6; i++) { LVA(row)[i] += LVA(trow)[i]; LVA(pA)[i] += LVA(tpA)[i]; }
-            LANES_END
-        }
-        const int nd = lvl == 0 ? 6 : 3;
-#pragma unroll 1
-        for (int j = nd - 1; j >= 0; --j) {
-            LANES_BEGIN
-            Real u = 0;
-            const int b = LV(body), dof = b <= 0 ? j : 3 + 3 * b + j;
-            const Real *S = w.S[dof];
-#pragma unroll
-            for (int c = 0; c < 6; c++) { const Real sc = b >= 0 ? S[c] : Real(0); LVA(Sv)[c] = sc; u += LVA(row)[c] * sc; }
-            LV(Ur) = u;
-            LANES_END
-#pragma unroll
-            for (int c = 0; c < 6; c++) { WSHFL1(LV_ARR(Uf, c), Ur, LV(gbase) + c); }
-            LANES_BEGIN
-            const int b = LV(body);
-            if (b >= 0) {
-                const int dof = b == 0 ? j : 3 + 3 * b + j;
-                Real D = w.aArm[dof], sp = 0;       // joint-space diagonal (armature + arm_scale kd)
-#pragma unroll
-                for (int c = 0; c < 6; c++) { D += LVA(Sv)[c] * LVA(Uf)[c]; sp += LVA(Sv)[c] * LVA(pA)[c]; }
-                const Real di = Real(1) / D, u = x[dof] - sp, ud = u * di, Urd = LV(Ur) * di;
-#pragma unroll
-                for (int c = 0; c < 6; c++) { LVA(row)[c] -= Urd * LVA(Uf)[c]; LVA(pA)[c] += LVA(Uf)[c] * ud; }
-                w.aU[dof][LV(rr)] = LV(Ur);
-                if (LV(rr) == 0) { w.aDinv[dof] = di; w.au[dof] = u; }
+            if (LV(act)) for (int i = 0; i < 3; i++) {
+                P a, c; a.x = LVA(trow)[2 * i]; a.y = LVA(trow)[2 * i + 1]; c.x = LVA(tpA)[2 * i]; c.y = LVA(tpA)[2 * i + 1];
+                LVA(nrow)[i] = padd(LVA(nrow)[i], a); LVA(npA)[i] = padd(LVA(npA)[i], c);
             }
             LANES_END
         }
         LANES_BEGIN
-        for (int i = 0; i < 6; i++) { LVA(crow)[i] = LVA(row)[i]; LVA(cpA)[i] = LVA(pA)[i]; }
+        for (int i = 0; i < 3; i++) { LVA(row)[i] = LVA(nrow)[i]; LVA(pA)[i] = LVA(npA)[i]; }
         LANES_END
+#pragma unroll 1
+        for (int blk = lvl == 0 ? 1 : 0; blk >= 0; --blk) {
+            LANES_BEGIN   // this lane's entries of U = IA S
+            const int b = LV(body), d0 = b <= 0 ? 3 * blk : 3 + 3 * b;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const Real u = pdot6(LVA(row), as_pairs(w.S[d0 + k]));
+                LVA(Ur)[k] = u;
+                if (b >= 0) w.aU[d0 + k][LV(rr)] = u;
+                LVA(armv)[k] = UHC_LDG(m.dof_f + 4 * (d0 + k)) + arm_scale * UHC_LDG(m.dof_f + 4 * (d0 + k) + 2);   // joint-space diagonal
+            }
+            LANES_END
+            LANES_BEGIN
+            const int b = LV(body), d0 = b <= 0 ? 3 * blk : 3 + 3 * b, r = LV(rr);
+            P U0[3], U1[3], U2[3];
+            const P *S0 = as_pairs(w.S[d0]), *S1 = as_pairs(w.S[d0 + 1]), *S2 = as_pairs(w.S[d0 + 2]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) { U0[i] = as_pairs(w.aU[d0])[i]; U1[i] = as_pairs(w.aU[d0 + 1])[i]; U2[i] = as_pairs(w.aU[d0 + 2])[i]; }
+            // D = S^T U + arm (symmetric), u = b - S^T pA
+            const Real D00 = pdot6(S0, U0) + LVA(armv)[0], D11 = pdot6(S1, U1) + LVA(armv)[1], D22 = pdot6(S2, U2) + LVA(armv)[2];
+            const Real D01 = pdot6(S0, U1), D02 = pdot6(S0, U2), D12 = pdot6(S1, U2);
+            const Real u0 = x[d0] - pdot6(S0, LVA(pA)), u1 = x[d0 + 1] - pdot6(S1, LVA(pA)), u2 = x[d0 + 2] - pdot6(S2, LVA(pA));
+            // inverse by the adjugate (D is symmetric positive definite and small)
+            const Real c00 = D11 * D22 - D12 * D12, c01 = D02 * D12 - D01 * D22, c02 = D01 * D12 - D02 * D11;
+            const Real c11 = D00 * D22 - D02 * D02, c12 = D01 * D02 - D00 * D12, c22 = D00 * D11 - D01 * D01;
+            const Real id = rcp_(D00 * c00 + D01 * c01 + D02 * c02);
+            const Real i00 = c00 * id, i01 = c01 * id, i02 = c02 * id, i11 = c11 * id, i12 = c12 * id, i22 = c22 * id;
+            const Real a0 = LVA(Ur)[0], a1 = LVA(Ur)[1], a2 = LVA(Ur)[2];
+            const Real W0 = a0 * i00 + a1 * i01 + a2 * i02, W1 = a0 * i01 + a1 * i11 + a2 * i12, W2 = a0 * i02 + a1 * i12 + a2 * i22;   // row r of U D^-1
+            const Real v0 = u0 * i00 + u1 * i01 + u2 * i02, v1 = u0 * i01 + u1 * i11 + u2 * i12, v2 = u0 * i02 + u1 * i12 + u2 * i22;   // D^-1 u
+            paxpy6(-W0, U0, LVA(row)); paxpy6(-W1, U1, LVA(row)); paxpy6(-W2, U2, LVA(row));
+            paxpy6(v0, U0, LVA(pA)); paxpy6(v1, U1, LVA(pA)); paxpy6(v2, U2, LVA(pA));
+            LVA(Ur)[0] = W0; LVA(Ur)[1] = W1; LVA(Ur)[2] = W2;
+            if (b >= 0 && r < 3) w.au[d0 + r] = r == 0 ? v0 : (r == 1 ? v1 : v2);
+            LANES_END
+            LANES_BEGIN   // U D^-1 replaces U (after every lane of the group has read U)
+            const int b = LV(body), d0 = b <= 0 ? 3 * blk : 3 + 3 * b;
+            if (b >= 0) { w.aU[d0][LV(rr)] = LVA(Ur)[0]; w.aU[d0 + 1][LV(rr)] = LVA(Ur)[1]; w.aU[d0 + 2][LV(rr)] = LVA(Ur)[2]; }
+            LANES_END
+        }
     }
-    // root -> leaves: x_j = (u_j - U_j . a) / D_j ; a += S_j x_j   (a replicated in the 6 lanes of a group)
+    // root -> leaves (the spatial acceleration a is replicated in the 6 lanes of a group)
     LVARA(Real, acc, 6); LVARA(Real, pacc, 6);
     LANES_BEGIN
     for (int i = 0; i < 6; i++) LVA(pacc)[i] = 0;
+    LV(entn) = lane < 6 * LVL_G ? UHC_LDG(m.lvl_pack + lane / 6) : 0;
     LANES_END
 #pragma unroll 1
     for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
         LANES_BEGIN
         const int g = lane / 6;
-        const int e = g < LVL_G ? UHC_LDG(m.lvl_pack + lvl * LVL_G + g) : 0;
+        const int e = LV(entn);
+        LV(entn) = (g < LVL_G && lvl < MAXLEVEL) ? UHC_LDG(m.lvl_pack + (lvl + 1) * LVL_G + g) : 0;
         const int b = (e & 63) - 1;
         LV(body) = b;
         LV(src) = (b >= 0 && lvl > 0) ? ((e >> 6) & 7) * 6 : lane;
         LANES_END
         WSHFL(acc, pacc, 6, LV(src));
         LANES_BEGIN
-        const int b = LV(body);
+        const int b = LV(body), r = LV(rr);
+        P a[3];
+        for (int i = 0; i < 3; i++) { a[i].x = b == 0 ? Real(0) : LVA(acc)[2 * i]; a[i].y = b == 0 ? Real(0) : LVA(acc)[2 * i + 1]; }
         if (b >= 0) {
-            const int d0 = b == 0 ? 0 : 6 + 3 * (b - 1), nd = b == 0 ? 6 : 3;
-            if (b == 0) for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
 #pragma unroll 1
-            for (int j = 0; j < nd; ++j) {
-                const int dof = d0 + j;
-                const Real xj = (w.au[dof] - dot6(w.aU[dof], LVA(acc))) * w.aDinv[dof];
-                if (LV(rr) == 0) x[dof] = xj;
-#pragma unroll
-                for (int i = 0; i < 6; i++) LVA(acc)[i] += w.S[dof][i] * xj;
+            for (int blk = 0; blk < (b == 0 ? 2 : 1); ++blk) {
+                const int d0 = b == 0 ? 3 * blk : 3 + 3 * b;
+                const Real x0 = w.au[d0] - pdot6(as_pairs(w.aU[d0]), a), x1 = w.au[d0 + 1] - pdot6(as_pairs(w.aU[d0 + 1]), a),
+                           x2 = w.au[d0 + 2] - pdot6(as_pairs(w.aU[d0 + 2]), a);
+                if (r < 3) x[d0 + r] = r == 0 ? x0 : (r == 1 ? x1 : x2);
+                paxpy6(x0, as_pairs(w.S[d0]), a); paxpy6(x1, as_pairs(w.S[d0 + 1]), a); paxpy6(x2, as_pairs(w.S[d0 + 2]), a);
             }
         }
-        for (int i = 0; i < 6; i++) LVA(pacc)[i] = LVA(acc)[i];
+        for (int i = 0; i < 3; i++) { LVA(pacc)[2 * i] = a[i].x; LVA(pacc)[2 * i + 1] = a[i].y; }
         LANES_END
     }
 }
@@ -923,10 +978,18 @@ UHC_DEV void integrate(const Model<Real> &m, Work<Real> &w) {
 // articulated-body solve: a small phase machine sets up the right-hand side, the shared solve runs, the phase post-processes.  Leaves M, C, xpos/xmat/xipos of THIS (pre-integration) configuration in the work set -- the staleness MuJoCo
 // exposes to the Python side (SURVEY.md section 7 "stale dynamics").  with_pd = false: reset path (sim.forward with ctrl = 0).
 enum { PH_PD = 0, PH_SMOOTH = 1, PH_NEWTON = 2 };
+// The warps of a CTA are re-aligned at points every warp passes exactly once per substep: they then run the same code at
+// the same time and share instruction-cache lines (the per-substep code is ~3x the 32 KB instruction cache).
+#if !defined(UHC_EMU) && !defined(UHC_NO_CTA_SYNC)
+#define UHC_CTA_SYNC(on) do { if (on) __syncthreads(); } while (0)
+#else
+#define UHC_CTA_SYNC(on) do { (void)(on); } while (0)
+#endif
 template <class Real, class OutT, class TPT>
 UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const TPT &tp, const Real *target, int it,
-                             bool with_pd, OutT *torque_out) {
+                             bool with_pd, OutT *torque_out, bool cta_sync = false) {
     int phase = with_pd ? PH_PD : PH_SMOOTH, iters = 0;
+    bool done = false;
     Real scale = 0;
     for (;;) {
         // ---- phase set-up: right-hand side into the vector the solve runs on
@@ -952,23 +1015,26 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
             LANES_END
             rhs = w.as_;
         } else {
-            if (iters >= cfg.newton_max_iter || !newton_prepare(m, cfg, w, scale, tp)) break;
+            // (aligning the Newton iterations across the CTA as well was measured: the waiting costs more than it saves)
+            if (done || iters >= cfg.newton_max_iter || !newton_prepare(m, cfg, w, scale, tp)) break;
             ++iters;
         }
         // ---- the one shared O(n) articulated-body solve (not needed for the smooth phase when contacts are present:
         //      Newton starts from the warm start and only needs f_s, not a_s = M^-1 f_s)
         if (!(phase == PH_SMOOTH && w.ncon > 0)) aba_solve(m, w, arm_scale, phase == PH_NEWTON, rhs);
         // ---- phase post-processing
-        if (phase == PH_PD) { pd_finish(m, cfg, w, it, torque_out); phase = PH_SMOOTH; }
+        if (phase == PH_PD) { pd_finish(m, cfg, w, it, torque_out); phase = PH_SMOOTH; UHC_CTA_SYNC(cta_sync); }
         else if (phase == PH_SMOOTH) {
+            UHC_CTA_SYNC(cta_sync);
             if (w.ncon == 0) {
                 LANES_BEGIN
                 for (int i = lane; i < NV; i += 32) w.a[i] = w.as_[i];
                 LANES_END
-                break;
+                done = true;
+            } else {
+                constraint_setup(m, w);
+                scale = newton_init(m, w, tp);
             }
-            constraint_setup(m, w);
-            scale = newton_init(m, w, tp);
             phase = PH_NEWTON;
         } else newton_advance(m, w, tp);
     }

@@ -14,7 +14,7 @@ static thread_local std::string g_err;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
 
 template <class Real, int EPB>
-__global__ void __launch_bounds__(32 * EPB, (sizeof(Real) == 4 ? 2 : 1))
+__global__ void __launch_bounds__(32 * EPB, (sizeof(Real) == 4 && EPB <= 7 ? 2 : 1))
 k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict__ obs, float *__restrict__ rew, float *__restrict__ cinfo,
            int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -96,7 +96,10 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     return 0;
 }
 
-constexpr int EPB_F = 7, EPB_D = 2;  // environments (warps) per block
+#ifndef UHC_EPB_F
+#define UHC_EPB_F 7
+#endif
+constexpr int EPB_F = UHC_EPB_F, EPB_D = 2;  // environments (warps) per block
 
 extern "C" {
 
