@@ -31,7 +31,9 @@
 #define LVARA(T, n, K) T n[K]
 #define LVA(n) n
 #define LV_ARR(n, c) n[c]
+#define LV_ALL(n) n
 #define UHC_LDG(p) __ldg(p)
+#define UHC_LDT(p) (*(p))   /* small per-model tables (dof_f, lvl_pack): staged in shared memory by the step kernel */
 #else
 #define UHC_DEV static inline
 #define UHC_DEVNI static
@@ -42,7 +44,9 @@
 #define LVARA(T, n, K) T n[32][K]
 #define LVA(n) n[lane]
 #define LV_ARR(n, c) n[lane][c]
+#define LV_ALL(n) n
 #define UHC_LDG(p) (*(p))
+#define UHC_LDT(p) (*(p))
 #endif
 
 namespace uhc {
@@ -238,6 +242,8 @@ template <class R> UHC_DEV void warp_argmin(R &x, int &i) {
 #define WMAX(n) warp_max(n)
 #define WARGMIN(x, i, ox, oi) { ox = x; oi = i; warp_argmin(ox, oi); }
 #define WBALLOT(n) __ballot_sync(0xffffffffu, (n) != 0)
+UHC_DEV int warp_excl_scan(int x, int lane) { int p = x; for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, p, o); if (lane >= o) p += t; } return p - x; }
+#define WEXSCAN(dst, src) { dst = warp_excl_scan(src, (int)(threadIdx.x & 31)); }
 // bodies are numbered depth-first, so subtree(b) = lanes [b, sub_end]: subtree sum = difference of an inclusive warp prefix sum
 template <class R, int K> UHC_DEV void subtree_sum(R (&x)[K], int sub_end, int lane) {
 #pragma unroll
@@ -267,6 +273,7 @@ template <class R> static R emu_max(const R *x) { R s = x[0]; for (int i = 1; i 
 #define WARGMIN(x, i, ox, oi) { ox = x[0]; oi = i[0]; for (int l_ = 1; l_ < 32; l_++) if (x[l_] < ox || (x[l_] == ox && i[l_] < oi)) { ox = x[l_]; oi = i[l_]; } }
 static unsigned emu_ballot(const int *x) { unsigned m = 0; for (int i = 0; i < 32; i++) if (x[i]) m |= 1u << i; return m; }
 #define WBALLOT(n) emu_ballot(n)
+#define WEXSCAN(dst, src) { int run_ = 0; for (int l_ = 0; l_ < 32; l_++) { const int t_ = src[l_]; dst[l_] = run_; run_ += t_; } }
 template <class R, int K, class TP> static void emu_subtree(R (*x)[K], const TP *tp) {
     R out[32][K];
     for (int b = 0; b < 32; b++) for (int i = 0; i < K; i++) { R s = 0; for (int c = b; c <= tp[b].sub_end && c < 32; c++) s += x[c][i]; out[b][i] = s; }
@@ -406,14 +413,14 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
     LANES_BEGIN
     for (int i = 0; i < 3; i++) { LVA(row)[i] = pbc(Real(0)); LVA(pA)[i] = pbc(Real(0)); }
     LV(rr) = lane - 6 * (lane / 6);
-    LV(entn) = lane < 6 * LVL_G ? UHC_LDG(m.lvl_pack + MAXLEVEL * LVL_G + lane / 6) : 0;
+    LV(entn) = lane < 6 * LVL_G ? UHC_LDT(m.lvl_pack + MAXLEVEL * LVL_G + lane / 6) : 0;
     LANES_END
 #pragma unroll 1
     for (int lvl = MAXLEVEL; lvl >= 0; --lvl) {
         LANES_BEGIN
         const int g = lane / 6, r = LV(rr);
         const int e = LV(entn);            // this level's table entry was fetched one level ahead
-        LV(entn) = (g < LVL_G && lvl > 0) ? UHC_LDG(m.lvl_pack + (lvl - 1) * LVL_G + g) : 0;
+        LV(entn) = (g < LVL_G && lvl > 0) ? UHC_LDT(m.lvl_pack + (lvl - 1) * LVL_G + g) : 0;
         const int b = (e & 63) - 1;
         LV(ent) = e; LV(body) = b;
         Real ri[6] = {0, 0, 0, 0, 0, 0};
@@ -452,7 +459,7 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
                 const Real u = pdot6(LVA(row), as_pairs(w.S[d0 + k]));
                 LVA(Ur)[k] = u;
                 if (b >= 0) w.aU[d0 + k][LV(rr)] = u;
-                LVA(armv)[k] = UHC_LDG(m.dof_f + 4 * (d0 + k)) + arm_scale * UHC_LDG(m.dof_f + 4 * (d0 + k) + 2);   // joint-space diagonal
+                LVA(armv)[k] = UHC_LDT(m.dof_f + 4 * (d0 + k)) + arm_scale * UHC_LDT(m.dof_f + 4 * (d0 + k) + 2);   // joint-space diagonal
             }
             LANES_END
             LANES_BEGIN
@@ -488,14 +495,14 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
     LVARA(Real, acc, 6); LVARA(Real, pacc, 6);
     LANES_BEGIN
     for (int i = 0; i < 6; i++) LVA(pacc)[i] = 0;
-    LV(entn) = lane < 6 * LVL_G ? UHC_LDG(m.lvl_pack + lane / 6) : 0;
+    LV(entn) = lane < 6 * LVL_G ? UHC_LDT(m.lvl_pack + lane / 6) : 0;
     LANES_END
 #pragma unroll 1
     for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
         LANES_BEGIN
         const int g = lane / 6;
         const int e = LV(entn);
-        LV(entn) = (g < LVL_G && lvl < MAXLEVEL) ? UHC_LDG(m.lvl_pack + (lvl + 1) * LVL_G + g) : 0;
+        LV(entn) = (g < LVL_G && lvl < MAXLEVEL) ? UHC_LDT(m.lvl_pack + (lvl + 1) * LVL_G + g) : 0;
         const int b = (e & 63) - 1;
         LV(body) = b;
         LV(src) = (b >= 0 && lvl > 0) ? ((e >> 6) & 7) * 6 : lane;
@@ -661,13 +668,24 @@ UHC_DEV void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F)[
 // Floor plane z = 0 against each body hull (oracle/uhc_oracle.c or_collide states the manifold rule).
 template <class Real>
 UHC_DEV void collide(const Model<Real> &m, Work<Real> &w) {
+    // broad phase for all bodies at once (lane = body): bounding sphere against the plane
+    LVAR(int, near); LVAR(int, cnt); LVAR(int, adr0);
+    LANES_BEGIN
+    int f = 0;
+    if (lane < NB) {
+        const Real *bf = m.body_f + lane * BODYF; const Real *R = w.xmat[lane];
+        const Real cz = w.xpos[lane][2] + R[6] * UHC_LDG(bf + 14) + R[7] * UHC_LDG(bf + 15) + R[8] * UHC_LDG(bf + 16);
+        f = !(cz - UHC_LDG(bf + 17) > m.margin);
+    }
+    LV(near) = f; LV(cnt) = 0;
+    LANES_END
+    unsigned cand_b = WBALLOT(near);
     int ncon = 0, upper = 0;
-    for (int b = 0; b < NB; ++b) {
-        w.bcon_adr[b] = ncon;  // uniform value, every lane writes the same (benign)
-        const Real *bf = m.body_f + b * BODYF;
+    while (cand_b) {     // candidate bodies in ascending order
+        int b = 0; while (!((cand_b >> b) & 1u)) b++;
+        cand_b &= cand_b - 1;
+        if (ncon + 4 > MAXCON) continue;
         const Real *R = w.xmat[b];
-        const Real cz = w.xpos[b][2] + R[6] * UHC_LDG(bf + 14) + R[7] * UHC_LDG(bf + 15) + R[8] * UHC_LDG(bf + 16);
-        if (cz - UHC_LDG(bf + 17) > m.margin || ncon + 4 > MAXCON) continue;
         const int adr = UHC_LDG(m.hull_adr + b), nvt = UHC_LDG(m.hull_num + b);
         LVAR(Real, bz); LVAR(int, bi);
         LANES_BEGIN
@@ -708,11 +726,16 @@ UHC_DEV void collide(const Model<Real> &m, Work<Real> &w) {
             w.cbody[c] = b; w.cdist[c] = pz;
             w.cr[c][0] = px - w.q[0]; w.cr[c][1] = py - w.q[1]; w.cr[c][2] = Real(0.5) * pz - w.q[2];
         }
+        if (lane == b) LV(cnt) = nc;
         LANES_END
         ncon += nc;
         if (b >= UPPER_BODY0) upper = 1;
     }
-    w.bcon_adr[NB] = ncon;
+    // contact ranges per body: exclusive prefix sum of the per-body counts (lane = body)
+    WEXSCAN(LV_ALL(adr0), LV_ALL(cnt));
+    LANES_BEGIN
+    if (lane <= NB) w.bcon_adr[lane] = LV(adr0);
+    LANES_END
     w.ncon = ncon; w.upper_contact = upper;
 #ifndef UHC_EMU
     __syncwarp();
@@ -810,7 +833,7 @@ UHC_DEV Real newton_init(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) {
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        w.Ma[i] = dot6(w.S[i], w.Fb[b]) + UHC_LDG(m.dof_f + 4 * i) * w.aw[i];
+        w.Ma[i] = dot6(w.S[i], w.Fb[b]) + UHC_LDT(m.dof_f + 4 * i) * w.aw[i];
         w.a[i] = w.aw[i];
     }
     LV(part) = lane < NB ? 3 * w.Ib[lane][0] : Real(0);   // gradient tolerance scale ~ trace of the translational block of M
@@ -921,7 +944,7 @@ UHC_DEV void pd_setup(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> 
             const Real dlt = base - qj;
             if (dlt > Real(PI_D)) base -= Real(2 * PI_D) * ceil((dlt - Real(PI_D)) / Real(2 * PI_D));
             else if (dlt < -Real(PI_D)) base += Real(2 * PI_D) * ceil((-Real(PI_D) - dlt) / Real(2 * PI_D));
-            const Real kp = UHC_LDG(m.dof_f + 4 * i + 1) * sp, kd = UHC_LDG(m.dof_f + 4 * i + 2) * sd;
+            const Real kp = UHC_LDT(m.dof_f + 4 * i + 1) * sp, kd = UHC_LDT(m.dof_f + 4 * i + 2) * sd;
             const Real err = qj + w.v[i] * dt - (base + w.act[j]);
             rhs += -kp * err - kd * w.v[i];
             w.g[i] = err;  // stash
@@ -936,7 +959,7 @@ UHC_DEV void pd_finish(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real>
     Real sp, sd; pd_gains(cfg, w, it, &sp, &sd);
     LANES_BEGIN
     for (int i = 6 + lane; i < NV; i += 32) {
-        const Real kp = UHC_LDG(m.dof_f + 4 * i + 1) * sp, kd = UHC_LDG(m.dof_f + 4 * i + 2) * sd, lim = UHC_LDG(m.dof_f + 4 * i + 3);
+        const Real kp = UHC_LDT(m.dof_f + 4 * i + 1) * sp, kd = UHC_LDT(m.dof_f + 4 * i + 2) * sd, lim = UHC_LDT(m.dof_f + 4 * i + 3);
         const Real t = clamp_(-kp * w.g[i] - kd * (w.v[i] + w.p[i] * dt), -lim, lim);
         w.tau[i - 6] = t;
         if (torque_out) torque_out[it * NU + i - 6] = (OutT)t;

@@ -19,6 +19,13 @@ k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict
            int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, env = blockIdx.x * EPB + warp;
+    // the small per-model tables every solve walks (joint gains / armature, tree-level table) are staged once per CTA
+    Real *s_dof = reinterpret_cast<Real *>(smem + EPB * sizeof(Work<Real>));
+    int *s_lvl = reinterpret_cast<int *>(s_dof + NV * 4);
+    for (int i = threadIdx.x; i < NV * 4; i += blockDim.x) s_dof[i] = ev.model.dof_f[i];
+    for (int i = threadIdx.x; i < (MAXLEVEL + 1) * LVL_G; i += blockDim.x) s_lvl[i] = ev.model.lvl_pack[i];
+    __syncthreads();
+    ev.model.dof_f = s_dof; ev.model.lvl_pack = s_lvl;
     if (env >= ev.num_envs) return;
     Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
     env_step_warp<Real, float>(ev, env, w, act + (size_t)env * ACT_DIM, obs ? obs + (size_t)env * OBS_DIM : nullptr, rew ? rew + env : nullptr,
@@ -99,7 +106,8 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
 #ifndef UHC_EPB_F
 #define UHC_EPB_F 7
 #endif
-constexpr int EPB_F = UHC_EPB_F, EPB_D = 2;  // environments (warps) per block
+constexpr int EPB_F = UHC_EPB_F, EPB_D = 2;
+template <class Real, int EPB> constexpr size_t step_smem() { return EPB * sizeof(Work<Real>) + NV * 4 * sizeof(Real) + (MAXLEVEL + 1) * LVL_G * sizeof(int); }  // environments (warps) per block
 
 extern "C" {
 
@@ -113,10 +121,10 @@ int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_e
     int rc = precision == 32 ? build_view<float>(e, e->evf, model, cfg) : build_view<double>(e, e->evd, model, cfg);
     if (rc) { delete e; return rc; }
     if (precision == 32) {
-        CK(cudaFuncSetAttribute(k_env_step<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_F * sizeof(Work<float>))));
+        CK(cudaFuncSetAttribute(k_env_step<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<float, EPB_F>()));
         CK(cudaFuncSetAttribute(k_env_reset<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_F * sizeof(Work<float>))));
     } else {
-        CK(cudaFuncSetAttribute(k_env_step<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_D * sizeof(Work<double>))));
+        CK(cudaFuncSetAttribute(k_env_step<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<double, EPB_D>()));
         CK(cudaFuncSetAttribute(k_env_reset<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_D * sizeof(Work<double>))));
     }
     const size_t E = num_envs;
@@ -220,9 +228,9 @@ int uhc_env_step(UhcEngine *e, const float *actions_dev, float *obs_dev, float *
     if (!e->d_expert) { g_err = "uhc_env_step: no clips loaded"; return -3; }
     cudaStream_t st = (cudaStream_t)stream;
     if (e->precision == 32)
-        k_env_step<float, EPB_F><<<(e->E + EPB_F - 1) / EPB_F, 32 * EPB_F, EPB_F * sizeof(Work<float>), st>>>(e->evf, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev);
+        k_env_step<float, EPB_F><<<(e->E + EPB_F - 1) / EPB_F, 32 * EPB_F, step_smem<float, EPB_F>(), st>>>(e->evf, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev);
     else
-        k_env_step<double, EPB_D><<<(e->E + EPB_D - 1) / EPB_D, 32 * EPB_D, EPB_D * sizeof(Work<double>), st>>>(e->evd, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev);
+        k_env_step<double, EPB_D><<<(e->E + EPB_D - 1) / EPB_D, 32 * EPB_D, step_smem<double, EPB_D>(), st>>>(e->evd, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev);
     CK(cudaGetLastError());
     e->launches++;
     return 0;
