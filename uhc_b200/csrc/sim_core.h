@@ -358,43 +358,35 @@ template <class Real> UHC_DEV void edge_dir(int e, Real mu, Real *d) {
     d[2] = 1;
 }
 
-// row r of the contact matrix of body b: K_b = sum_{own contacts} X^T W X,  X = [G 1], G = -[r]x, W = D sum_{active edges} d d^T
+// Row r of a body's 6x6 matrices, (w, v) ordering.  The lane's row is described by the unit vector u = e_(r mod 3) and
+// ang = (r < 3), so that every lane runs the same arithmetic (no per-row branches or select chains).
+// Contact matrix of body b:  K_b = sum_{own contacts} X^T W X,  X = [-[p]x 1] (point velocity = v + w x p),
+// W = D sum_{active edges} d d^T with pyramid edges d = (+-mu or 0, +-mu or 0, 1)  ->  W_xy = 0.
+// Row r of X^T W X = [p x (W xr), W xr] with xr = column r of X = (ang ? u x p : u).
 template <class Real>
-UHC_DEV void contact_matrix_row(const Model<Real> &m, const Work<Real> &w, int b, int r, Real *row) {
+UHC_DEV void contact_matrix_row(const Model<Real> &m, const Work<Real> &w, int b, const Real *u, bool ang, Real *row) {
+    const Real mu = m.mu, mu2 = mu * mu;
     for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
-        Real W[6] = {0, 0, 0, 0, 0, 0};  // xx yy zz xy xz yz
-#pragma unroll
-        for (int e = 0; e < 4; e++) if (w.cres[c][e] < 0) {
-            Real d[3]; edge_dir(e, m.mu, d); const Real D = w.cD[c];
-            W[0] += D * d[0] * d[0]; W[1] += D * d[1] * d[1]; W[2] += D * d[2] * d[2];
-            W[3] += D * d[0] * d[1]; W[4] += D * d[0] * d[2]; W[5] += D * d[1] * d[2];
-        }
+        const Real D = w.cD[c];
+        const Real a0 = w.cres[c][0] < 0 ? D : Real(0), a1 = w.cres[c][1] < 0 ? D : Real(0), a2 = w.cres[c][2] < 0 ? D : Real(0), a3 = w.cres[c][3] < 0 ? D : Real(0);
+        const Real Wxx = mu2 * (a2 + a3), Wyy = mu2 * (a0 + a1), Wzz = (a0 + a1) + (a2 + a3), Wxz = mu * (a3 - a2), Wyz = mu * (a0 - a1);
         const Real *p = w.cr[c];
-        // columns of X: angular k -> e_k x p ... X maps (w, v) to v + w x p, so X e_k(angular) = e_k x p, X e_k(linear) = e_k
-        Real Xc[6][3] = {{0, -p[2], p[1]}, {p[2], 0, -p[0]}, {-p[1], p[0], 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-        Real xr[3] = {0, 0, 0};
-#pragma unroll
-        for (int k = 0; k < 6; k++) if (k == r) { xr[0] = Xc[k][0]; xr[1] = Xc[k][1]; xr[2] = Xc[k][2]; }
-        const Real v[3] = {W[0] * xr[0] + W[3] * xr[1] + W[4] * xr[2], W[3] * xr[0] + W[1] * xr[1] + W[5] * xr[2], W[4] * xr[0] + W[5] * xr[1] + W[2] * xr[2]};
-#pragma unroll
-        for (int k = 0; k < 6; k++) row[k] += v[0] * Xc[k][0] + v[1] * Xc[k][1] + v[2] * Xc[k][2];
+        Real t[3], xr[3], v[3], pv[3];
+        cross3(u, p, t);
+        xr[0] = ang ? t[0] : u[0]; xr[1] = ang ? t[1] : u[1]; xr[2] = ang ? t[2] : u[2];
+        v[0] = Wxx * xr[0] + Wxz * xr[2]; v[1] = Wyy * xr[1] + Wyz * xr[2]; v[2] = Wxz * xr[0] + Wyz * xr[1] + Wzz * xr[2];
+        cross3(p, v, pv);
+        row[0] += pv[0]; row[1] += pv[1]; row[2] += pv[2]; row[3] += v[0]; row[4] += v[1]; row[5] += v[2];
     }
 }
-// row r of the 6x6 spatial inertia of a rigid body (m, h = m c, J about O), (w, v) ordering:  [[J, [h]x], [-[h]x, m 1]]
+// Rigid spatial inertia (m, h = m c, J about O):  [[J, [h]x], [-[h]x, m 1]].  Angular row q: [J u, u x h]; linear row q: [h x u, m u].
 template <class Real>
-UHC_DEV void rigid_row(const Real *I, int r, Real *row) {
-    const int q = r < 3 ? r : r - 3, q1 = q == 2 ? 0 : q + 1, q2 = q == 0 ? 2 : q - 1;
-    // [h]x row q: column q1 -> -h[q2], column q2 -> +h[q1], column q -> 0
-    const Real hx1 = -I[1 + q2], hx2 = I[1 + q1];
-    const Real c0 = q1 == 0 ? hx1 : (q2 == 0 ? hx2 : Real(0)), c1 = q1 == 1 ? hx1 : (q2 == 1 ? hx2 : Real(0)), c2 = q1 == 2 ? hx1 : (q2 == 2 ? hx2 : Real(0));
-    if (r < 3) {   // J row q from the packed (xx yy zz xy xz yz): diagonal 4+q, off-diagonal (i,j) at 6+i+j
-        const Real d = I[4 + q], o1 = I[6 + q + q1], o2 = I[6 + q + q2];
-        row[0] = q == 0 ? d : (q1 == 0 ? o1 : o2); row[1] = q == 1 ? d : (q1 == 1 ? o1 : o2); row[2] = q == 2 ? d : (q1 == 2 ? o1 : o2);
-        row[3] = c0; row[4] = c1; row[5] = c2;
-    } else {
-        const Real ms = I[0];
-        row[0] = -c0; row[1] = -c1; row[2] = -c2; row[3] = q == 0 ? ms : Real(0); row[4] = q == 1 ? ms : Real(0); row[5] = q == 2 ? ms : Real(0);
-    }
+UHC_DEV void rigid_row(const Real *I, const Real *u, bool ang, Real *row) {
+    const Real *h = I + 1;
+    const Real Ju0 = I[4] * u[0] + I[7] * u[1] + I[8] * u[2], Ju1 = I[7] * u[0] + I[5] * u[1] + I[9] * u[2], Ju2 = I[8] * u[0] + I[9] * u[1] + I[6] * u[2];
+    Real t[3]; cross3(u, h, t);
+    row[0] = ang ? Ju0 : -t[0]; row[1] = ang ? Ju1 : -t[1]; row[2] = ang ? Ju2 : -t[2];
+    row[3] = ang ? t[0] : I[0] * u[0]; row[4] = ang ? t[1] : I[0] * u[1]; row[5] = ang ? t[2] : I[0] * u[2];
 }
 
 // x <- H^-1 x  (x: 75-vector in shared memory).  arm_scale: extra joint-space diagonal = arm_scale * kd_i (0 for none).
@@ -425,8 +417,10 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
         LV(ent) = e; LV(body) = b;
         Real ri[6] = {0, 0, 0, 0, 0, 0};
         if (b >= 0) {
-            rigid_row(w.Ib[b], r, ri);
-            if (use_contacts) contact_matrix_row(m, w, b, r, ri);
+            const int q = r < 3 ? r : r - 3;
+            const Real u[3] = {q == 0 ? Real(1) : Real(0), q == 1 ? Real(1) : Real(0), q == 2 ? Real(1) : Real(0)};
+            rigid_row(w.Ib[b], u, r < 3, ri);
+            if (use_contacts) contact_matrix_row(m, w, b, u, r < 3, ri);
         }
         for (int i = 0; i < 3; i++) { LVA(nrow)[i].x = ri[2 * i]; LVA(nrow)[i].y = ri[2 * i + 1]; LVA(npA)[i] = pbc(Real(0)); }
         LANES_END
