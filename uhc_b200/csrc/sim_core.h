@@ -100,7 +100,7 @@ struct Work {
     alignas(16) Real aU[NV][6];   // articulated-body sweep: columns of  U D^-1  per 3-dof block (U = IA S, D = S^T U + arm)
     Real au[NV + 1];                // D^-1 u per block
     Real C[NV + 1], fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
-    Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
+    alignas(16) Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
     // contacts
     int cbody[MAXCON]; Real cr[MAXCON][3], cdist[MAXCON], cD[MAXCON], caref[MAXCON][4], cres[MAXCON][4], cjp[MAXCON][4];
     int bcon_adr[NB + 1];
@@ -636,11 +636,12 @@ UHC_DEVNI void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real
     LVARA(Real, V, 6);
     LANES_BEGIN
     const int b = lane;
-    for (int i = 0; i < 6; i++) LVA(V)[i] = 0;
+    Pr<Real> Vp[3] = {pbc(Real(0)), pbc(Real(0)), pbc(Real(0))};
     if (b < NB) {
         const int d0 = b == 0 ? 0 : 6 + 3 * (b - 1), nd = b == 0 ? 6 : 3;
-        for (int j = 0; j < nd; ++j) { const Real xj = x[d0 + j]; for (int i = 0; i < 6; i++) LVA(V)[i] += w.S[d0 + j][i] * xj; }
+        for (int j = 0; j < nd; ++j) paxpy6(x[d0 + j], as_pairs(w.S[d0 + j]), Vp);
     }
+    for (int i = 0; i < 3; i++) { LVA(V)[2 * i] = Vp[i].x; LVA(V)[2 * i + 1] = Vp[i].y; }
     LANES_END
     WANCESTOR(V, 6, tp);
     LANES_BEGIN
@@ -653,7 +654,7 @@ UHC_DEV void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F)[
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) {
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        y[i] = scale * dot6(w.S[i], F[b]) + (add ? add[i] : Real(0));
+        y[i] = scale * pdot6(as_pairs(w.S[i]), as_pairs(F[b])) + (add ? add[i] : Real(0));
     }
     LANES_END
 }
@@ -785,14 +786,13 @@ UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real
     for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
     if (b < NB) {
         for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
-            Real f[3] = {0, 0, 0}, t[3];
+            // multipliers of the four pyramid edges d = (0, mu, 1), (0, -mu, 1), (-mu, 0, 1), (mu, 0, 1); force = sum_e l_e d_e
+            const Real D = w.cD[c];
+            Real l[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                Real d[3]; edge_dir(e, m.mu, d);
-                const Real r = w.cres[c][e];
-                const Real l = r < 0 ? w.cD[c] * (mode ? w.cjp[c][e] : r) : Real(0);
-                f[0] += l * d[0]; f[1] += l * d[1]; f[2] += l * d[2];
-            }
+            for (int e = 0; e < 4; e++) { const Real r = w.cres[c][e]; l[e] = r < 0 ? D * (mode ? w.cjp[c][e] : r) : Real(0); }
+            const Real f[3] = {m.mu * (l[3] - l[2]), m.mu * (l[0] - l[1]), (l[0] + l[1]) + (l[2] + l[3])};
+            Real t[3];
             cross3(w.cr[c], f, t);
             LVA(acc)[0] += t[0]; LVA(acc)[1] += t[1]; LVA(acc)[2] += t[2]; LVA(acc)[3] += f[0]; LVA(acc)[4] += f[1]; LVA(acc)[5] += f[2];
         }
@@ -827,7 +827,7 @@ UHC_DEV Real newton_init(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) {
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        w.Ma[i] = dot6(w.S[i], w.Fb[b]) + UHC_LDT(m.dof_f + 4 * i) * w.aw[i];
+        w.Ma[i] = pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b])) + UHC_LDT(m.dof_f + 4 * i) * w.aw[i];
         w.a[i] = w.aw[i];
     }
     LV(part) = lane < NB ? 3 * w.Ib[lane][0] : Real(0);   // gradient tolerance scale ~ trace of the translational block of M
@@ -843,7 +843,7 @@ UHC_DEV bool newton_prepare(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<
     Real s = 0;
     for (int i = lane; i < NV; i += 32) {
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        const Real gi = w.Ma[i] - w.fs[i] + dot6(w.S[i], w.Fb[b]);
+        const Real gi = w.Ma[i] - w.fs[i] + pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b]));
         w.g[i] = gi; w.p[i] = -gi; s += gi * gi;
     }
     LV(part) = s;
@@ -863,7 +863,7 @@ UHC_DEV void newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp) 
     Real sA = 0, sB = 0;
     for (int i = lane; i < NV; i += 32) {
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        const Real mp = -w.g[i] - dot6(w.S[i], w.Fb[b]);
+        const Real mp = -w.g[i] - pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b]));
         w.Mp[i] = mp; sA += (w.Ma[i] - w.fs[i]) * w.p[i]; sB += mp * w.p[i];
     }
     LV(pa) = sA; LV(pb) = sB;
