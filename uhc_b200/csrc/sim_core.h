@@ -264,6 +264,16 @@ template <class R, int K> UHC_DEV void ancestor_sum(R (&x)[K], int parent, int d
     }
 }
 #define WSUBTREE(n, K, tp) subtree_sum<Real, K>(n, tp.sub_end, tp.lane)
+template <class R, int K> UHC_DEV void prefix_sum(R (&x)[K], int lane) {   // inclusive, over the 32 lanes
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        R p = x[i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const R t = __shfl_up_sync(0xffffffffu, p, o); if (lane >= o) p += t; }
+        x[i] = p;
+    }
+}
+#define WPREFIX(n, K) prefix_sum<Real, K>(n, (int)(threadIdx.x & 31))
 #define WANCESTOR(n, K, tp) ancestor_sum<Real, K>(n, tp.parent, tp.depth)
 #else
 template <class R> static R emu_sum(const R *x) { R s = 0; for (int i = 0; i < 32; i++) s += x[i]; return s; }
@@ -283,6 +293,7 @@ template <class R, int K, class TP> static void emu_ancestor(R (*x)[K], const TP
     for (int b = 1; b < NB; b++) for (int i = 0; i < K; i++) x[b][i] += x[tp[b].parent][i];   // depth-first order: parents come first
 }
 #define WSUBTREE(n, K, tp) emu_subtree<Real, K>(n, tp)
+#define WPREFIX(n, K) { for (int l_ = 1; l_ < 32; l_++) for (int i_ = 0; i_ < K; i_++) n[l_][i_] += n[l_ - 1][i_]; }
 #define WANCESTOR(n, K, tp) emu_ancestor<Real, K>(n, tp)
 #endif
 UHC_DEV int popc_(unsigned x) { int c = 0; while (x) { x &= x - 1; c++; } return c; }
@@ -777,15 +788,18 @@ UHC_DEVNI void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)
 }
 // body wrenches from per-row multipliers (force on the body along d_e at the contact point), then subtree sums.
 // mode 0: lam = D r_-  (gradient term J^T D r_-) ; mode 1: lam = D [r<0] jp  (J^T D_act J p)
+// lane = contact: wrench of each contact about O; contacts are ordered by body and bodies depth-first, so the wrench of
+// subtree(b) is a contiguous range of contacts = a difference of two inclusive prefix sums (second 32-chunk only when needed).
 template <class Real, class TPT>
 UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real (*Fo)[6], const TPT &tp) {
-    LVARA(Real, acc, 6);
-    LANES_BEGIN
-    const int b = lane;
-#pragma unroll
-    for (int i = 0; i < 6; i++) LVA(acc)[i] = 0;
-    if (b < NB) {
-        for (int c = w.bcon_adr[b]; c < w.bcon_adr[b + 1]; ++c) {
+    LVARA(Real, P0, 6); LVARA(Real, P1, 6); LVARA(Real, lo, 6); LVARA(Real, hi, 6); LVAR(int, jlo); LVAR(int, jhi);
+    const int nchunk = w.ncon > 32 ? 2 : 1;
+    for (int k = 0; k < nchunk; ++k) {
+        LVARA(Real, F, 6);
+        LANES_BEGIN
+        const int c = 32 * k + lane;
+        for (int i = 0; i < 6; i++) LVA(F)[i] = 0;
+        if (c < w.ncon) {
             // multipliers of the four pyramid edges d = (0, mu, 1), (0, -mu, 1), (-mu, 0, 1), (mu, 0, 1); force = sum_e l_e d_e
             const Real D = w.cD[c];
             Real l[4];
@@ -794,13 +808,41 @@ UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real
             const Real f[3] = {m.mu * (l[3] - l[2]), m.mu * (l[0] - l[1]), (l[0] + l[1]) + (l[2] + l[3])};
             Real t[3];
             cross3(w.cr[c], f, t);
-            LVA(acc)[0] += t[0]; LVA(acc)[1] += t[1]; LVA(acc)[2] += t[2]; LVA(acc)[3] += f[0]; LVA(acc)[4] += f[1]; LVA(acc)[5] += f[2];
+            LVA(F)[0] = t[0]; LVA(F)[1] = t[1]; LVA(F)[2] = t[2]; LVA(F)[3] = f[0]; LVA(F)[4] = f[1]; LVA(F)[5] = f[2];
         }
+        LANES_END
+        WPREFIX(F, 6);
+        if (k == 0) { LANES_BEGIN for (int i = 0; i < 6; i++) { LVA(P0)[i] = LVA(F)[i]; LVA(P1)[i] = 0; } LANES_END }
+        else { LANES_BEGIN for (int i = 0; i < 6; i++) LVA(P1)[i] = LVA(F)[i]; LANES_END }
+    }
+    // lane = body: subtree(b) owns contacts [bcon_adr[b], bcon_adr[sub_end(b) + 1])
+    LANES_BEGIN
+    const int b = lane < NB ? lane : NB - 1;
+    LV(jlo) = w.bcon_adr[b] - 1; LV(jhi) = w.bcon_adr[TP.sub_end < NB ? TP.sub_end + 1 : NB] - 1;
+    if (lane >= NB) { LV(jlo) = -1; LV(jhi) = -1; }
+    LANES_END
+    WSHFL(lo, P0, 6, (LV(jlo) < 0 ? 0 : LV(jlo)) & 31);
+    WSHFL(hi, P0, 6, (LV(jhi) < 0 ? 0 : LV(jhi)) & 31);
+    LANES_BEGIN
+    for (int i = 0; i < 6; i++) {
+        if (LV(jlo) < 0) LVA(lo)[i] = 0;
+        if (LV(jhi) < 0) LVA(hi)[i] = 0;
     }
     LANES_END
-    WSUBTREE(acc, 6, tp);
+    if (nchunk == 2) {      // indices >= 32 live in the second chunk: P(j) = total of chunk 0 + P1(j - 32)
+        LVARA(Real, t0, 6); LVARA(Real, a, 6); LVARA(Real, c2, 6);
+        WSHFL(t0, P0, 6, 31);
+        WSHFL(a, P1, 6, (LV(jlo) < 0 ? 0 : LV(jlo)) & 31);
+        WSHFL(c2, P1, 6, (LV(jhi) < 0 ? 0 : LV(jhi)) & 31);
+        LANES_BEGIN
+        for (int i = 0; i < 6; i++) {
+            if (LV(jlo) >= 32) LVA(lo)[i] = LVA(t0)[i] + LVA(a)[i];
+            if (LV(jhi) >= 32) LVA(hi)[i] = LVA(t0)[i] + LVA(c2)[i];
+        }
+        LANES_END
+    }
     LANES_BEGIN
-    if (lane < NB) for (int i = 0; i < 6; i++) Fo[lane][i] = LVA(acc)[i];
+    if (lane < NB) for (int i = 0; i < 6; i++) Fo[lane][i] = LVA(hi)[i] - LVA(lo)[i];
     LANES_END
 }
 
