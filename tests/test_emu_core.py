@@ -33,6 +33,24 @@ def test_forward_dynamics_matches_oracle_fp64():
         assert np.abs(r["qacc"] - d.qacc).max() < 1e-6 * max(1.0, np.abs(d.qacc).max())
 
 
+def test_forward_dynamics_many_contacts_fp64():
+    """Leaning far forward close to the floor: 33..40 contacts, i.e. the second 32-contact chunk of the wrench prefix sums."""
+    om, d = O.Model(), O.Data()
+    e = Emu(64)
+    q = om.qpos0.copy()
+    q[2] = 0.16
+    a = np.deg2rad(40.0) / 2
+    q[3:7] = [np.cos(a), 0, np.sin(a), 0]
+    v = np.random.default_rng(3).normal(size=75) * 0.3
+    d.qpos[:], d.qvel[:], d.ctrl[:] = q, v, 0
+    d.qfrc_applied[:] = 0
+    d.qacc_warm[:] = 0
+    O.forward(om, d)
+    r = e.forward(q, v, np.zeros(69), np.zeros(6))
+    assert 32 < d.ncon <= 40 and r["ncon"] == d.ncon
+    assert np.abs(r["qacc"] - d.qacc).max() < 1e-6 * max(1.0, np.abs(d.qacc).max())
+
+
 @pytest.mark.parametrize("prec,tol_q,tol_o", [(64, 1e-11, 1e-9), (32, 1e-4, 2e-3)])
 def test_env_trace_matches_reference_golden(golden_dir, prec, tol_q, tol_o):
     g = np.load(os.path.join(golden_dir, "env_sway_noise.npz"))

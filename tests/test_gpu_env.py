@@ -178,3 +178,34 @@ def test_varying_contact_counts_match_oracle(kind):
     if kind == "sitting":
         assert maxcon >= 12
     eng.close()
+
+
+def test_more_than_32_contacts_match_oracle():
+    """Leaning far forward close to the floor (36 contacts): exercises the second chunk of the contact-wrench prefix sums."""
+    import torch
+    from oracle import oracle as O
+    from uhc_b200 import motion_lib
+    from uhc_b200.engine import Engine
+    ex = motion_lib.synthetic_clip(20, np.random.default_rng(5), kind="sitting")
+    q = ex["qpos"][0].copy()
+    q[7:] = 0
+    q[2] = 0.16
+    a = np.deg2rad(40.0) / 2
+    q[3:7] = [np.cos(a), 0, np.sin(a), 0]
+    eng = Engine(2, body_diff_thresh=100.0)
+    eng.load_clips([ex], None)
+    eng.reset(qpos=np.tile(q, (2, 1)), qvel=np.zeros((2, 75)))
+    oe = O.Env(O.Model(), ex, np.zeros(17), body_diff_thresh=100.0)
+    oe.reset(q, np.zeros(75))
+    assert 32 < oe.d.ncon <= 40 and eng.get_state(1)["ncon"] == oe.d.ncon
+    big = 0
+    for t in range(3):
+        act = np.zeros(105, np.float32)
+        eng.step(torch.tensor(np.tile(act, (2, 1)), device="cuda"))
+        oe.step(act.astype(np.float64))
+        if oe.d.ncon > 40:
+            break
+        st = eng.get_state(1)
+        big = max(big, st["ncon"])
+        assert np.abs(st["qpos"] - oe.d.qpos).max() < 1e-3, (t, np.abs(st["qpos"] - oe.d.qpos).max())
+    eng.close()

@@ -33,7 +33,12 @@
 #define LV_ARR(n, c) n[c]
 #define LV_ALL(n) n
 #define UHC_LDG(p) __ldg(p)
-#define UHC_LDT(p) (*(p))   /* small per-model tables (dof_f, lvl_pack): staged in shared memory by the step kernel */
+// small per-model tables (dof_f, lvl_pack): the kernels stage them in shared memory and point the Model at the copies, so the
+// device reads them with shared-space loads (32-bit addressing, no generic-pointer arithmetic)
+__device__ __forceinline__ float uhc_lds(const float *p) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p))); return v; }
+__device__ __forceinline__ double uhc_lds(const double *p) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p))); return v; }
+__device__ __forceinline__ int uhc_lds(const int *p) { int v; asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p))); return v; }
+#define UHC_LDT(p) uhc_lds(p)
 #else
 #define UHC_DEV static inline
 #define UHC_DEVNI static
@@ -411,12 +416,14 @@ template <class Real>
 UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bool use_contacts, Real *x) {
     typedef Pr<Real> P;
     LVARA(P, row, 3); LVARA(P, pA, 3); LVARA(P, nrow, 3); LVARA(P, npA, 3); LVARA(Real, trow, 6); LVARA(Real, tpA, 6);
-    LVARA(Real, Ur, 3); LVARA(Real, armv, 3);
+    LVARA(Real, Ur, 3);
+    Real *arm = w.Mp;     // joint-space diagonal (armature + arm_scale kd); Mp is only live inside newton_advance
     LVAR(int, body); LVAR(int, src); LVAR(int, act); LVAR(int, rr); LVAR(int, ent); LVAR(int, entn);
     LANES_BEGIN
     for (int i = 0; i < 3; i++) { LVA(row)[i] = pbc(Real(0)); LVA(pA)[i] = pbc(Real(0)); }
     LV(rr) = lane - 6 * (lane / 6);
     LV(entn) = lane < 6 * LVL_G ? UHC_LDT(m.lvl_pack + MAXLEVEL * LVL_G + lane / 6) : 0;
+    for (int i = lane; i < NV; i += 32) arm[i] = UHC_LDT(m.dof_f + 4 * i) + arm_scale * UHC_LDT(m.dof_f + 4 * i + 2);   // joint-space diagonal
     LANES_END
 #pragma unroll 1
     for (int lvl = MAXLEVEL; lvl >= 0; --lvl) {
@@ -464,7 +471,6 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
                 const Real u = pdot6(LVA(row), as_pairs(w.S[d0 + k]));
                 LVA(Ur)[k] = u;
                 if (b >= 0) w.aU[d0 + k][LV(rr)] = u;
-                LVA(armv)[k] = UHC_LDT(m.dof_f + 4 * (d0 + k)) + arm_scale * UHC_LDT(m.dof_f + 4 * (d0 + k) + 2);   // joint-space diagonal
             }
             LANES_END
             LANES_BEGIN
@@ -474,7 +480,7 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
 #pragma unroll
             for (int i = 0; i < 3; i++) { U0[i] = as_pairs(w.aU[d0])[i]; U1[i] = as_pairs(w.aU[d0 + 1])[i]; U2[i] = as_pairs(w.aU[d0 + 2])[i]; }
             // D = S^T U + arm (symmetric), u = b - S^T pA
-            const Real D00 = pdot6(S0, U0) + LVA(armv)[0], D11 = pdot6(S1, U1) + LVA(armv)[1], D22 = pdot6(S2, U2) + LVA(armv)[2];
+            const Real D00 = pdot6(S0, U0) + arm[d0], D11 = pdot6(S1, U1) + arm[d0 + 1], D22 = pdot6(S2, U2) + arm[d0 + 2];
             const Real D01 = pdot6(S0, U1), D02 = pdot6(S0, U2), D12 = pdot6(S1, U2);
             const Real u0 = x[d0] - pdot6(S0, LVA(pA)), u1 = x[d0 + 1] - pdot6(S1, LVA(pA)), u2 = x[d0 + 2] - pdot6(S2, LVA(pA));
             // inverse by the adjugate (D is symmetric positive definite and small)

@@ -13,19 +13,25 @@ using namespace uhc;
 static thread_local std::string g_err;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { g_err = std::string(#x) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
 
+// the small per-model tables every solve walks (joint gains / armature, tree-level table) are staged once per CTA behind the
+// EPB work sets; the Model is pointed at the copies (sim_core.h reads them with shared-space loads)
 template <class Real, int EPB>
-__global__ void __launch_bounds__(32 * EPB, (sizeof(Real) == 4 && EPB <= 7 ? 2 : 1))
-k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict__ obs, float *__restrict__ rew, float *__restrict__ cinfo,
-           int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, env = blockIdx.x * EPB + warp;
-    // the small per-model tables every solve walks (joint gains / armature, tree-level table) are staged once per CTA
+__device__ __forceinline__ void stage_tables(EngineView<Real> &ev, unsigned char *smem) {
     Real *s_dof = reinterpret_cast<Real *>(smem + EPB * sizeof(Work<Real>));
     int *s_lvl = reinterpret_cast<int *>(s_dof + NV * 4);
     for (int i = threadIdx.x; i < NV * 4; i += blockDim.x) s_dof[i] = ev.model.dof_f[i];
     for (int i = threadIdx.x; i < (MAXLEVEL + 1) * LVL_G; i += blockDim.x) s_lvl[i] = ev.model.lvl_pack[i];
     __syncthreads();
     ev.model.dof_f = s_dof; ev.model.lvl_pack = s_lvl;
+}
+
+template <class Real, int EPB>
+__global__ void __launch_bounds__(32 * EPB, (sizeof(Real) == 4 && EPB <= 7 ? 2 : 1))
+k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict__ obs, float *__restrict__ rew, float *__restrict__ cinfo,
+           int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, env = blockIdx.x * EPB + warp;
+    stage_tables<Real, EPB>(ev, smem);
     if (env >= ev.num_envs) return;
     Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
     env_step_warp<Real, float>(ev, env, w, act + (size_t)env * ACT_DIM, obs ? obs + (size_t)env * OBS_DIM : nullptr, rew ? rew + env : nullptr,
@@ -39,6 +45,7 @@ k_env_reset(EngineView<Real> ev, int n, const int *__restrict__ ids, const int *
             const int *__restrict__ len, const float *__restrict__ qpos, const float *__restrict__ qvel, float *__restrict__ obs) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, i = blockIdx.x * EPB + warp;
+    stage_tables<Real, EPB>(ev, smem);
     if (i >= n) return;
     Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
     const int env = ids[i];
@@ -122,10 +129,10 @@ int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_e
     if (rc) { delete e; return rc; }
     if (precision == 32) {
         CK(cudaFuncSetAttribute(k_env_step<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<float, EPB_F>()));
-        CK(cudaFuncSetAttribute(k_env_reset<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_F * sizeof(Work<float>))));
+        CK(cudaFuncSetAttribute(k_env_reset<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<float, EPB_F>()));
     } else {
         CK(cudaFuncSetAttribute(k_env_step<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<double, EPB_D>()));
-        CK(cudaFuncSetAttribute(k_env_reset<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(EPB_D * sizeof(Work<double>))));
+        CK(cudaFuncSetAttribute(k_env_reset<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<double, EPB_D>()));
     }
     const size_t E = num_envs;
     CK(cudaMalloc((void **)&e->d_act, E * ACT_DIM * 4)); CK(cudaMalloc((void **)&e->d_obs, E * OBS_DIM * 4)); CK(cudaMalloc((void **)&e->d_rew, E * 4));
@@ -213,9 +220,9 @@ int uhc_env_reset(UhcEngine *e, int n, const int *env_ids_host, const int *clip_
     CK(cudaMemcpyAsync(e->d_ids + 2 * n, start_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->d_ids + 3 * n, len_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
     if (e->precision == 32)
-        k_env_reset<float, EPB_F><<<(n + EPB_F - 1) / EPB_F, 32 * EPB_F, EPB_F * sizeof(Work<float>), st>>>(e->evf, n, e->d_ids, e->d_ids + n, e->d_ids + 2 * n, e->d_ids + 3 * n, qpos_dev, qvel_dev, obs_dev);
+        k_env_reset<float, EPB_F><<<(n + EPB_F - 1) / EPB_F, 32 * EPB_F, step_smem<float, EPB_F>(), st>>>(e->evf, n, e->d_ids, e->d_ids + n, e->d_ids + 2 * n, e->d_ids + 3 * n, qpos_dev, qvel_dev, obs_dev);
     else
-        k_env_reset<double, EPB_D><<<(n + EPB_D - 1) / EPB_D, 32 * EPB_D, EPB_D * sizeof(Work<double>), st>>>(e->evd, n, e->d_ids, e->d_ids + n, e->d_ids + 2 * n, e->d_ids + 3 * n, qpos_dev, qvel_dev, obs_dev);
+        k_env_reset<double, EPB_D><<<(n + EPB_D - 1) / EPB_D, 32 * EPB_D, step_smem<double, EPB_D>(), st>>>(e->evd, n, e->d_ids, e->d_ids + n, e->d_ids + 2 * n, e->d_ids + 3 * n, qpos_dev, qvel_dev, obs_dev);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));  // the host id arrays may be reused by the caller
     e->launches++;
