@@ -132,12 +132,8 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     TOPO_DECL(mdl);
 #pragma unroll 1
     for (int it = 0; it < NSUB; ++it) {
-#ifndef UHC_SYNC_PERIOD
-#define UHC_SYNC_PERIOD 1
-#endif
-        const bool sync_now = (it % UHC_SYNC_PERIOD) == 0;
-        UHC_CTA_SYNC(sync_now);
-        iters += substep_dynamics<Real, ObsT>(mdl, ev.cfg, w, tp, target, it, true, torque_out, sync_now);
+        UHC_CTA_SYNC(true);   // see substep_dynamics: the CTA's warps run each substep's straight-line code together
+        iters += substep_dynamics<Real, ObsT>(mdl, ev.cfg, w, tp, target, it, true, torque_out, true);
         if (w.ncon > maxcon) maxcon = w.ncon;
         if (it == NSUB - 1) world_quat(mdl, w.q, w);  // pose of the last forward pass (what data.body_xquat holds)
         integrate(mdl, w);

@@ -81,7 +81,7 @@ struct Model {
     const int *parent, *depth, *child_adr, *child, *body_sub_end;
     const int *ee;                // [5]
     const int *lvl_tab;           // [MAXLEVEL+1][LVL_G][5]: body, parent's group, groups of <=3 children (-1 = none)
-    const int *lvl_pack;          // [MAXLEVEL+1][LVL_G]: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15
+    const int *lvl_pack;          // [MAXLEVEL+1][LVL_G]: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15 | nslot<<18 (max children per body on the level, same in all entries of a level)
     Real dt, margin, mu, solref0, solref1, simp0, simp1, simp2, simp3, simp4, gravz;
     int nshape, nvert;            // body_f / hull hold `nshape` consecutive shape variants ([nshape][NB][BODYF], [nshape][nvert][3])
 };
@@ -442,14 +442,14 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
         }
         for (int i = 0; i < 3; i++) { LVA(nrow)[i].x = ri[2 * i]; LVA(nrow)[i].y = ri[2 * i + 1]; LVA(npA)[i] = pbc(Real(0)); }
         LANES_END
+        const int nslot = (UHC_LDT(m.lvl_pack + lvl * LVL_G) >> 18) & 3;   // uniform: most children any body of this level has
 #pragma unroll 1
-        for (int k = 0; k < 3; ++k) {  // children of this level's bodies: they sit one level deeper, their results are still in row / pA
+        for (int k = 0; k < nslot; ++k) {  // children of this level's bodies: they sit one level deeper, their results are still in row / pA
             LANES_BEGIN
             const int cg = ((LV(ent) >> (9 + 3 * k)) & 7) - 1;
             LV(act) = cg >= 0; LV(src) = cg >= 0 ? cg * 6 + LV(rr) : lane;
             for (int i = 0; i < 3; i++) { LVA(trow)[2 * i] = LVA(row)[i].x; LVA(trow)[2 * i + 1] = LVA(row)[i].y; LVA(tpA)[2 * i] = LVA(pA)[i].x; LVA(tpA)[2 * i + 1] = LVA(pA)[i].y; }
             LANES_END
-            if (!WANY(act)) continue;
             WSHFL(trow, trow, 6, LV(src));
             WSHFL(tpA, tpA, 6, LV(src));
             LANES_BEGIN
@@ -494,7 +494,7 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
             paxpy6(-W0, U0, LVA(row)); paxpy6(-W1, U1, LVA(row)); paxpy6(-W2, U2, LVA(row));
             paxpy6(v0, U0, LVA(pA)); paxpy6(v1, U1, LVA(pA)); paxpy6(v2, U2, LVA(pA));
             LVA(Ur)[0] = W0; LVA(Ur)[1] = W1; LVA(Ur)[2] = W2;
-            if (b >= 0 && r < 3) w.au[d0 + r] = r == 0 ? v0 : (r == 1 ? v1 : v2);
+            if (b >= 0 && r == 0) { w.au[d0] = v0; w.au[d0 + 1] = v1; w.au[d0 + 2] = v2; }
             LANES_END
             LANES_BEGIN   // U D^-1 replaces U (after every lane of the group has read U)
             const int b = LV(body), d0 = b <= 0 ? 3 * blk : 3 + 3 * b;
@@ -529,7 +529,7 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
                 const int d0 = b == 0 ? 3 * blk : 3 + 3 * b;
                 const Real x0 = w.au[d0] - pdot6(as_pairs(w.aU[d0]), a), x1 = w.au[d0 + 1] - pdot6(as_pairs(w.aU[d0 + 1]), a),
                            x2 = w.au[d0 + 2] - pdot6(as_pairs(w.aU[d0 + 2]), a);
-                if (r < 3) x[d0 + r] = r == 0 ? x0 : (r == 1 ? x1 : x2);
+                if (r == 0) { x[d0] = x0; x[d0 + 1] = x1; x[d0 + 2] = x2; }
                 paxpy6(x0, as_pairs(w.S[d0]), a); paxpy6(x1, as_pairs(w.S[d0 + 1]), a); paxpy6(x2, as_pairs(w.S[d0 + 2]), a);
             }
         }
@@ -1045,6 +1045,8 @@ UHC_DEV void integrate(const Model<Real> &m, Work<Real> &w) {
 enum { PH_PD = 0, PH_SMOOTH = 1, PH_NEWTON = 2 };
 // The warps of a CTA are re-aligned at points every warp passes exactly once per substep: they then run the same code at
 // the same time and share instruction-cache lines (the per-substep code is ~3x the 32 KB instruction cache).
+// Measured (E = 4096): whole-CTA alignment 1.25 M env-steps/s, groups of 4 / 3 / 2 warps 1.23 / 1.20 / 1.16 M, none 0.95 M;
+// every 2nd / 3rd substep only 1.06 / 1.00 M; aligning each Newton iteration too 1.06 M.
 #if !defined(UHC_EMU) && !defined(UHC_NO_CTA_SYNC)
 #define UHC_CTA_SYNC(on) do { if (on) __syncthreads(); } while (0)
 #else

@@ -6,6 +6,9 @@
 #include <string>
 #include <vector>
 #include "../../include/uhc_b200.h"
+#ifndef UHC_EPB_F
+#define UHC_EPB_F 7
+#endif
 #include "env_step.h"
 
 using namespace uhc;
@@ -110,9 +113,6 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     return 0;
 }
 
-#ifndef UHC_EPB_F
-#define UHC_EPB_F 7
-#endif
 constexpr int EPB_F = UHC_EPB_F, EPB_D = 2;
 template <class Real, int EPB> constexpr size_t step_smem() { return EPB * sizeof(Work<Real>) + NV * 4 * sizeof(Real) + (MAXLEVEL + 1) * LVL_G * sizeof(int); }  // environments (warps) per block
 

@@ -92,7 +92,9 @@ class HumanoidModel:
                 for k, c in enumerate(ch[b]):
                     tab[L, gi, 2 + k] = grp[c]
         self.lvl_tab = np.ascontiguousarray(tab.reshape(-1))
-        self.lvl_pack = np.ascontiguousarray(((tab[:, :, 0] + 1) | (np.maximum(tab[:, :, 1], 0) << 6) | ((tab[:, :, 2] + 1) << 9) | ((tab[:, :, 3] + 1) << 12) | ((tab[:, :, 4] + 1) << 15)).astype(np.int32).reshape(-1))
+        nslot = (tab[:, :, 2:5] >= 0).sum(axis=2).max(axis=1)          # most children any body of the level has (uniform per level)
+        self.lvl_pack = np.ascontiguousarray(((tab[:, :, 0] + 1) | (np.maximum(tab[:, :, 1], 0) << 6) | ((tab[:, :, 2] + 1) << 9) | ((tab[:, :, 3] + 1) << 12) | ((tab[:, :, 4] + 1) << 15)
+                                              | (nslot[:, None] << 18)).astype(np.int32).reshape(-1))
         self.dof_body = np.array([0] * 6 + [1 + d // 3 for d in range(NU)], np.int32)
 
     def _invweight0(self):
