@@ -525,7 +525,7 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
         for (int i = 0; i < 3; i++) { a[i].x = b == 0 ? Real(0) : LVA(acc)[2 * i]; a[i].y = b == 0 ? Real(0) : LVA(acc)[2 * i + 1]; }
         if (b >= 0) {
 #pragma unroll 1
-            for (int blk = 0; blk < (b == 0 ? 2 : 1); ++blk) {
+            for (int blk = 0; blk < (lvl == 0 ? 2 : 1); ++blk) {   // uniform trip count (only the root sits on level 0)
                 const int d0 = b == 0 ? 3 * blk : 3 + 3 * b;
                 const Real x0 = w.au[d0] - pdot6(as_pairs(w.aU[d0]), a), x1 = w.au[d0 + 1] - pdot6(as_pairs(w.aU[d0 + 1]), a),
                            x2 = w.au[d0 + 2] - pdot6(as_pairs(w.aU[d0 + 2]), a);
