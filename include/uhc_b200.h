@@ -36,8 +36,10 @@ typedef struct {
     const int *hull_adr, *hull_num, *nbr, *nbradr;
     const int *parent, *depth, *child_adr, *child, *body_sub_end;   /* kinematic tree, bodies numbered depth-first */
     const int *ee;          /* [5] end-effector bodies of the reward (smpl_parser.py:228) */
-    const int *lvl_tab;     /* [9][5][5] per tree level and lane group: body, parent's group, groups of up to 3 children (-1 none) */
-    const int *lvl_pack;    /* [9][5] the same, packed: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15 */
+    const int *lvl_tab;     /* [9][5][5] elimination tree of the joint-space solve, hung from the tree's centre body (7 levels for SMPL): per level
+                               and lane group: body, parent's group, groups of up to 3 children (-1 none) */
+    const int *lvl_pack;    /* [9][5] the same, packed: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15 | max children on the level<<18
+                               | (first dof of the connecting joint / 3)<<20 | joint crossed backwards<<25 | number of levels<<26 */
     double dt, margin, mu, solref[2], solimp[5], gravz;
     int nshape;             /* number of body-shape variants: body_f = [nshape][24][20], hull = [nshape][nvert][3] (same topology / hull graph) */
 } UhcModelHost;

@@ -81,7 +81,8 @@ struct Model {
     const int *parent, *depth, *child_adr, *child, *body_sub_end;
     const int *ee;                // [5]
     const int *lvl_tab;           // [MAXLEVEL+1][LVL_G][5]: body, parent's group, groups of <=3 children (-1 = none)
-    const int *lvl_pack;          // [MAXLEVEL+1][LVL_G]: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15 | nslot<<18 (max children per body on the level, same in all entries of a level)
+    const int *lvl_pack;          // elimination tree of the solve (hung from the tree's centre), [MAXLEVEL+1][LVL_G]: (body+1) | pgrp<<6 | (cg0+1)<<9 | (cg1+1)<<12 | (cg2+1)<<15
+                                  //   | nslot<<18 (max children per body on the level) | (first dof / 3)<<20 | reversed<<25 | nlevels<<26
     Real dt, margin, mu, solref0, solref1, simp0, simp1, simp2, simp3, simp4, gravz;
     int nshape, nvert;            // body_f / hull hold `nshape` consecutive shape variants ([nshape][NB][BODYF], [nshape][nvert][3])
 };
@@ -100,10 +101,10 @@ template <class Real>
 struct Work {
     Real q[NQ], v[NV + 1], aw[NV + 1], act[ACT_DIM + 3];
     Real xpos[NB][3], xmat[NB][9], xipos[NB][3], xquat[NB][4];
-    alignas(16) Real S[NV][6];
+    alignas(16) Real S[NV + 6][6];   // motion subspaces; rows NV.. are the unit vectors of the solve's virtual dofs
     Real Ib[NB][10];              // per-body rigid inertia about O, world axes (of the last forward pass)
-    alignas(16) Real aU[NV][6];   // articulated-body sweep: columns of  U D^-1  per 3-dof block (U = IA S, D = S^T U + arm)
-    Real au[NV + 1];                // D^-1 u per block
+    alignas(16) Real aU[NV + 6][6];   // articulated-body sweep: columns of  U D^-1  per 3-dof block (U = IA S, D = S^T U + arm)
+    Real au[NV + 6];                // D^-1 u per block
     Real C[NV + 1], fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
     alignas(16) Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
     // contacts
@@ -406,11 +407,18 @@ UHC_DEV void rigid_row(const Real *I, const Real *u, bool ang, Real *row) {
 }
 
 // x <- H^-1 x  (x: 75-vector in shared memory).  arm_scale: extra joint-space diagonal = arm_scale * kd_i (0 for none).
-// Lane layout: the <= 5 bodies of one tree level are processed together, 6 lanes per body (lane = 6 g + r owns ROW r of that
-// body's articulated inertia; the bias wrench is replicated in the group).  A body's three hinge dofs (the root: its rotation
-// block, then its translation block) are eliminated as ONE 3x3 block:
-//   leaves -> root:  U = IA S (6x3), D = S^T U + arm (3x3), u = b - S^T pA ;  IA -= U D^-1 U^T ;  pA += U D^-1 u
-//   root -> leaves:  x = D^-1 u - (U D^-1)^T a_parent ;  a = a_parent + S x
+//
+// H = sum_b J_b^T IA_b J_b + diag(arm) is the matrix of a TREE of bodies coupled by joints; the tree can be eliminated towards any
+// of its bodies.  The level table (Model::lvl_pack, built by uhc_b200/model.py) hangs it from its centre (Spine for SMPL): 7 levels of
+// <= 5 bodies instead of the 9 of the kinematic tree.  A joint on the path centre -> Pelvis is crossed against its kinematic
+// direction: with y = -qacc_j it reads a_child = a_parent + S_j y like every other joint, so its right-hand side and solution
+// just change sign.  The free joint (no armature) turns into the wrench  S_0^-T b_0  applied to the Pelvis body, and the centre
+// body is solved for its own spatial acceleration through six virtual dofs NV .. NV+5 with unit motion vectors.
+//
+// Lane layout: the <= 5 bodies of one level are processed together, 6 lanes per body (lane = 6 g + r owns ROW r of that body's
+// articulated inertia; the bias wrench is replicated in the group).  The three dofs of a body's joint are eliminated as ONE block:
+//   leaves -> centre:  U = IA S (6x3), D = S^T U + arm (3x3), u = b - S^T pA ;  IA -= U D^-1 U^T ;  pA += U D^-1 u
+//   centre -> leaves:  y = D^-1 u - (U D^-1)^T a_parent ;  a = a_parent + S y
 // so only  U D^-1  and  D^-1 u  are kept for the back-substitution.
 template <class Real>
 UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bool use_contacts, Real *x) {
@@ -419,28 +427,34 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
     LVARA(Real, Ur, 3);
     Real *arm = w.Mp;     // joint-space diagonal (armature + arm_scale kd); Mp is only live inside newton_advance
     LVAR(int, body); LVAR(int, src); LVAR(int, act); LVAR(int, rr); LVAR(int, ent); LVAR(int, entn);
+    const int nlvl = (UHC_LDT(m.lvl_pack) >> 26) & 15;
     LANES_BEGIN
     for (int i = 0; i < 3; i++) { LVA(row)[i] = pbc(Real(0)); LVA(pA)[i] = pbc(Real(0)); }
     LV(rr) = lane - 6 * (lane / 6);
-    LV(entn) = lane < 6 * LVL_G ? UHC_LDT(m.lvl_pack + MAXLEVEL * LVL_G + lane / 6) : 0;
+    LV(entn) = lane < 6 * LVL_G ? UHC_LDT(m.lvl_pack + (nlvl - 1) * LVL_G + lane / 6) : 0;
     for (int i = lane; i < NV; i += 32) arm[i] = UHC_LDT(m.dof_f + 4 * i) + arm_scale * UHC_LDT(m.dof_f + 4 * i + 2);   // joint-space diagonal
+    if (lane < 6) for (int c = 0; c < 6; c++) w.S[NV + lane][c] = c == lane ? Real(1) : Real(0);                       // virtual dofs of the centre body
     LANES_END
 #pragma unroll 1
-    for (int lvl = MAXLEVEL; lvl >= 0; --lvl) {
+    for (int lvl = nlvl - 1; lvl >= 0; --lvl) {
         LANES_BEGIN
         const int g = lane / 6, r = LV(rr);
         const int e = LV(entn);            // this level's table entry was fetched one level ahead
         LV(entn) = (g < LVL_G && lvl > 0) ? UHC_LDT(m.lvl_pack + (lvl - 1) * LVL_G + g) : 0;
         const int b = (e & 63) - 1;
         LV(ent) = e; LV(body) = b;
-        Real ri[6] = {0, 0, 0, 0, 0, 0};
+        Real ri[6] = {0, 0, 0, 0, 0, 0}, pi[6] = {0, 0, 0, 0, 0, 0};
         if (b >= 0) {
             const int q = r < 3 ? r : r - 3;
             const Real u[3] = {q == 0 ? Real(1) : Real(0), q == 1 ? Real(1) : Real(0), q == 2 ? Real(1) : Real(0)};
             rigid_row(w.Ib[b], u, r < 3, ri);
             if (use_contacts) contact_matrix_row(m, w, b, u, r < 3, ri);
+            if (b == 0) {   // the free joint's right-hand side is a wrench on the Pelvis: bias = -S_0^-T b_0 (S_0 = [0 R; 1 0] is orthogonal)
+                const Real b3 = x[3], b4 = x[4], b5 = x[5];
+                for (int i = 0; i < 3; i++) { pi[i] = -(w.S[3][i] * b3 + w.S[4][i] * b4 + w.S[5][i] * b5); pi[3 + i] = -x[i]; }
+            }
         }
-        for (int i = 0; i < 3; i++) { LVA(nrow)[i].x = ri[2 * i]; LVA(nrow)[i].y = ri[2 * i + 1]; LVA(npA)[i] = pbc(Real(0)); }
+        for (int i = 0; i < 3; i++) { LVA(nrow)[i].x = ri[2 * i]; LVA(nrow)[i].y = ri[2 * i + 1]; LVA(npA)[i].x = pi[2 * i]; LVA(npA)[i].y = pi[2 * i + 1]; }
         LANES_END
         const int nslot = (UHC_LDT(m.lvl_pack + lvl * LVL_G) >> 18) & 3;   // uniform: most children any body of this level has
 #pragma unroll 1
@@ -463,9 +477,9 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
         for (int i = 0; i < 3; i++) { LVA(row)[i] = LVA(nrow)[i]; LVA(pA)[i] = LVA(npA)[i]; }
         LANES_END
 #pragma unroll 1
-        for (int blk = lvl == 0 ? 1 : 0; blk >= 0; --blk) {
+        for (int blk = lvl == 0 ? 1 : 0; blk >= 0; --blk) {   // the centre body (level 0) has two blocks of virtual dofs
             LANES_BEGIN   // this lane's entries of U = IA S
-            const int b = LV(body), d0 = b <= 0 ? 3 * blk : 3 + 3 * b;
+            const int b = LV(body), d0 = 3 * ((LV(ent) >> 20) & 31) + 3 * blk;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const Real u = pdot6(LVA(row), as_pairs(w.S[d0 + k]));
@@ -474,15 +488,19 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
             }
             LANES_END
             LANES_BEGIN
-            const int b = LV(body), d0 = b <= 0 ? 3 * blk : 3 + 3 * b, r = LV(rr);
+            const int b = LV(body), d0 = 3 * ((LV(ent) >> 20) & 31) + 3 * blk, r = LV(rr);
+            const bool real_dofs = d0 < NV;                              // virtual dofs: no armature, zero right-hand side
+            const Real sg = ((LV(ent) >> 25) & 1) ? Real(-1) : Real(1);   // joint crossed against its kinematic direction
             P U0[3], U1[3], U2[3];
             const P *S0 = as_pairs(w.S[d0]), *S1 = as_pairs(w.S[d0 + 1]), *S2 = as_pairs(w.S[d0 + 2]);
 #pragma unroll
             for (int i = 0; i < 3; i++) { U0[i] = as_pairs(w.aU[d0])[i]; U1[i] = as_pairs(w.aU[d0 + 1])[i]; U2[i] = as_pairs(w.aU[d0 + 2])[i]; }
             // D = S^T U + arm (symmetric), u = b - S^T pA
-            const Real D00 = pdot6(S0, U0) + arm[d0], D11 = pdot6(S1, U1) + arm[d0 + 1], D22 = pdot6(S2, U2) + arm[d0 + 2];
+            const Real D00 = pdot6(S0, U0) + (real_dofs ? arm[d0] : Real(0)), D11 = pdot6(S1, U1) + (real_dofs ? arm[d0 + 1] : Real(0)),
+                       D22 = pdot6(S2, U2) + (real_dofs ? arm[d0 + 2] : Real(0));
             const Real D01 = pdot6(S0, U1), D02 = pdot6(S0, U2), D12 = pdot6(S1, U2);
-            const Real u0 = x[d0] - pdot6(S0, LVA(pA)), u1 = x[d0 + 1] - pdot6(S1, LVA(pA)), u2 = x[d0 + 2] - pdot6(S2, LVA(pA));
+            const Real u0 = (real_dofs ? sg * x[d0] : Real(0)) - pdot6(S0, LVA(pA)), u1 = (real_dofs ? sg * x[d0 + 1] : Real(0)) - pdot6(S1, LVA(pA)),
+                       u2 = (real_dofs ? sg * x[d0 + 2] : Real(0)) - pdot6(S2, LVA(pA));
             // inverse by the adjugate (D is symmetric positive definite and small)
             const Real c00 = D11 * D22 - D12 * D12, c01 = D02 * D12 - D01 * D22, c02 = D01 * D12 - D02 * D11;
             const Real c11 = D00 * D22 - D02 * D02, c12 = D01 * D02 - D00 * D12, c22 = D00 * D11 - D01 * D01;
@@ -497,40 +515,45 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
             if (b >= 0 && r == 0) { w.au[d0] = v0; w.au[d0 + 1] = v1; w.au[d0 + 2] = v2; }
             LANES_END
             LANES_BEGIN   // U D^-1 replaces U (after every lane of the group has read U)
-            const int b = LV(body), d0 = b <= 0 ? 3 * blk : 3 + 3 * b;
+            const int b = LV(body), d0 = 3 * ((LV(ent) >> 20) & 31) + 3 * blk;
             if (b >= 0) { w.aU[d0][LV(rr)] = LVA(Ur)[0]; w.aU[d0 + 1][LV(rr)] = LVA(Ur)[1]; w.aU[d0 + 2][LV(rr)] = LVA(Ur)[2]; }
             LANES_END
         }
     }
-    // root -> leaves (the spatial acceleration a is replicated in the 6 lanes of a group)
+    // centre -> leaves (the spatial acceleration a is replicated in the 6 lanes of a group)
     LVARA(Real, acc, 6); LVARA(Real, pacc, 6);
     LANES_BEGIN
     for (int i = 0; i < 6; i++) LVA(pacc)[i] = 0;
     LV(entn) = lane < 6 * LVL_G ? UHC_LDT(m.lvl_pack + lane / 6) : 0;
     LANES_END
 #pragma unroll 1
-    for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
+    for (int lvl = 0; lvl < nlvl; ++lvl) {
         LANES_BEGIN
         const int g = lane / 6;
         const int e = LV(entn);
-        LV(entn) = (g < LVL_G && lvl < MAXLEVEL) ? UHC_LDT(m.lvl_pack + (lvl + 1) * LVL_G + g) : 0;
+        LV(entn) = (g < LVL_G && lvl + 1 < nlvl) ? UHC_LDT(m.lvl_pack + (lvl + 1) * LVL_G + g) : 0;
         const int b = (e & 63) - 1;
-        LV(body) = b;
+        LV(body) = b; LV(ent) = e;
         LV(src) = (b >= 0 && lvl > 0) ? ((e >> 6) & 7) * 6 : lane;
         LANES_END
         WSHFL(acc, pacc, 6, LV(src));
         LANES_BEGIN
         const int b = LV(body), r = LV(rr);
         P a[3];
-        for (int i = 0; i < 3; i++) { a[i].x = b == 0 ? Real(0) : LVA(acc)[2 * i]; a[i].y = b == 0 ? Real(0) : LVA(acc)[2 * i + 1]; }
+        for (int i = 0; i < 3; i++) { a[i].x = lvl == 0 ? Real(0) : LVA(acc)[2 * i]; a[i].y = lvl == 0 ? Real(0) : LVA(acc)[2 * i + 1]; }
         if (b >= 0) {
+            const Real sg = ((LV(ent) >> 25) & 1) ? Real(-1) : Real(1);
 #pragma unroll 1
-            for (int blk = 0; blk < (lvl == 0 ? 2 : 1); ++blk) {   // uniform trip count (only the root sits on level 0)
-                const int d0 = b == 0 ? 3 * blk : 3 + 3 * b;
+            for (int blk = 0; blk < (lvl == 0 ? 2 : 1); ++blk) {   // uniform trip count (only the centre body sits on level 0)
+                const int d0 = 3 * ((LV(ent) >> 20) & 31) + 3 * blk;
                 const Real x0 = w.au[d0] - pdot6(as_pairs(w.aU[d0]), a), x1 = w.au[d0 + 1] - pdot6(as_pairs(w.aU[d0 + 1]), a),
                            x2 = w.au[d0 + 2] - pdot6(as_pairs(w.aU[d0 + 2]), a);
-                if (r == 0) { x[d0] = x0; x[d0 + 1] = x1; x[d0 + 2] = x2; }
+                if (r == 0 && d0 < NV) { x[d0] = sg * x0; x[d0 + 1] = sg * x1; x[d0 + 2] = sg * x2; }
                 paxpy6(x0, as_pairs(w.S[d0]), a); paxpy6(x1, as_pairs(w.S[d0 + 1]), a); paxpy6(x2, as_pairs(w.S[d0 + 2]), a);
+            }
+            if (b == 0 && r == 0) {   // free-joint accelerations from the Pelvis spatial acceleration: qacc_0 = S_0^-1 a = S_0^T a
+                x[0] = a[1].y; x[1] = a[2].x; x[2] = a[2].y;
+                for (int k = 0; k < 3; k++) x[3 + k] = w.S[3 + k][0] * a[0].x + w.S[3 + k][1] * a[0].y + w.S[3 + k][2] * a[1].x;
             }
         }
         for (int i = 0; i < 3; i++) { LVA(pacc)[2 * i] = a[i].x; LVA(pacc)[2 * i + 1] = a[i].y; }

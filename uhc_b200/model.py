@@ -78,23 +78,47 @@ class HumanoidModel:
         for b in range(NB - 1, 0, -1):
             sub_end[p[b]] = max(sub_end[p[b]], sub_end[b])
         self.body_sub_end = sub_end.astype(np.int32)
-        # per tree level: the bodies of that level as lane groups (<= 5), with the group index of the parent and of <= 3 children
-        nlev = int(self.depth.max()) + 1
-        assert nlev <= 9
-        groups = [[b for b in range(NB) if self.depth[b] == L] for L in range(9)]
-        assert max(len(g) for g in groups) <= 5 and max(len(c) for c in ch) <= 3
+        # Elimination tree of the articulated-body solve.  The joint-space matrix only needs A tree of bodies and joints, not the
+        # kinematic root: hanging the same tree from its centre (Spine2 for SMPL) gives 7 levels of <= 5 bodies instead of 9.
+        # Joints on the path centre -> Pelvis are traversed against their kinematic direction (sign bit); the Pelvis free joint
+        # becomes an external wrench on the Pelvis body (its armature must be 0) and the centre body carries 6 virtual dofs.
+        # Per level and lane group (<= 5): body, parent's group, groups of <= 3 children, joint block (first dof / 3), sign.
+        nbrs = [[c for c in range(NB) if p[c] == b] + ([int(p[b])] if b > 0 else []) for b in range(NB)]
+
+        def hang(root):
+            par, dep, order = {root: -1}, {root: 0}, [root]
+            for b in order:
+                for c in sorted(nbrs[b]):
+                    if c not in par:
+                        par[c], dep[c] = b, dep[b] + 1
+                        order.append(c)
+            return par, dep
+        root = min(range(NB), key=lambda r: (max(hang(r)[1].values()), r))
+        par2, dep2 = hang(root)
+        nlev = max(dep2.values()) + 1
+        ch2 = [[c for c in range(NB) if par2[c] == b] for b in range(NB)]
+        groups = [[b for b in range(NB) if dep2[b] == L] for L in range(9)]
+        assert nlev <= 9 and max(len(g) for g in groups) <= 5 and max(len(c) for c in ch2) <= 3
+        assert np.all(self.armature[:6] == 0), "the solve re-roots the tree: the free joint must have no armature"
         grp = {b: g.index(b) for g in groups for b in g}
-        tab = -np.ones((9, 5, 5), np.int32)
+        tab = -np.ones((9, 5, 7), np.int32)
         for L, g in enumerate(groups):
             for gi, b in enumerate(g):
                 tab[L, gi, 0] = b
-                tab[L, gi, 1] = grp[p[b]] if b > 0 else 0
-                for k, c in enumerate(ch[b]):
+                tab[L, gi, 1] = grp[par2[b]] if par2[b] >= 0 else 0
+                for k, c in enumerate(ch2[b]):
                     tab[L, gi, 2 + k] = grp[c]
-        self.lvl_tab = np.ascontiguousarray(tab.reshape(-1))
+                if par2[b] < 0:
+                    tab[L, gi, 5], tab[L, gi, 6] = NV // 3, 0            # virtual dofs NV .. NV+5 of the centre body
+                elif p[b] == par2[b]:
+                    tab[L, gi, 5], tab[L, gi, 6] = 1 + b, 0              # own joint: dofs 3 + 3 b ..
+                else:
+                    tab[L, gi, 5], tab[L, gi, 6] = 1 + par2[b], 1        # the tree parent's joint, traversed backwards
+        self.solve_root, self.solve_levels = root, nlev
+        self.lvl_tab = np.ascontiguousarray(tab[:, :, :5].reshape(-1))
         nslot = (tab[:, :, 2:5] >= 0).sum(axis=2).max(axis=1)          # most children any body of the level has (uniform per level)
         self.lvl_pack = np.ascontiguousarray(((tab[:, :, 0] + 1) | (np.maximum(tab[:, :, 1], 0) << 6) | ((tab[:, :, 2] + 1) << 9) | ((tab[:, :, 3] + 1) << 12) | ((tab[:, :, 4] + 1) << 15)
-                                              | (nslot[:, None] << 18)).astype(np.int32).reshape(-1))
+                                              | (nslot[:, None] << 18) | (np.maximum(tab[:, :, 5], 0) << 20) | (np.maximum(tab[:, :, 6], 0) << 25) | (nlev << 26)).astype(np.int32).reshape(-1))
         self.dof_body = np.array([0] * 6 + [1 + d // 3 for d in range(NU)], np.int32)
 
     def _invweight0(self):
