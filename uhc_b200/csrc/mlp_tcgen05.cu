@@ -58,6 +58,25 @@ __device__ __forceinline__ float act_f(float z, int act) {
     return z;
 }
 
+// one warp writes its 32 x 32 block (thread = row, vals = that row's 32 columns) to dst[row0 + rr][col0 + lane], rows in order
+__device__ __forceinline__ void stage_store(float *stg, float *__restrict__ dst, const float (&vals)[32], int row0, int col0, int M, int N, int lane, bool atomic) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = vals[j];
+    __syncwarp();
+    const int n = col0 + lane;
+    if (n < N) {
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+            const int grow = row0 + rr;
+            if (grow < M) {
+                const float x = stg[rr * 33 + lane];
+                if (atomic) atomicAdd(dst + (size_t)grow * N + n, x); else dst[(size_t)grow * N + n] = x;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(192, 2)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
             __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act, int ksplit) {
@@ -130,38 +149,34 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                            "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                const int nb = n0 + c * 32;
-                float v[32];
+            // fp32 outputs leave through a warp-private 32 x 33 staging tile in the (now idle) operand ring so that every store
+            // instruction writes one full 128-byte row segment instead of 32 scattered words
+            const int nb = n0 + c * 32;
+            float *stg = reinterpret_cast<float *>(smem) + q * (32 * 33);
+            float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = nb + j;
-                    const float z = n < N ? __uint_as_float(r[j]) + ((bias && blockIdx.z == 0) ? __ldg(bias + n) : 0.f) : 0.f;
-                    if (zf && n < N) zf[(size_t)row * N + n] = z;       // pre-activation (for the backward pass)
-                    v[j] = n < N ? act_f(z, act) : 0.f;
-                }
-                if (yf) {
-                    if (ksplit > 1) {
+            for (int j = 0; j < 32; ++j) {
+                const int n = nb + j;
+                v[j] = (row < M && n < N) ? __uint_as_float(r[j]) + ((bias && blockIdx.z == 0) ? __ldg(bias + n) : 0.f) : 0.f;
+            }
+            if (zf) stage_store(stg, zf, v, m0 + 32 * q, nb, M, N, lane, false);       // pre-activation (for the backward pass)
+            if (act != UHC_ACT_NONE) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (nb + j < N) atomicAdd(yf + (size_t)row * N + nb + j, v[j]);
-                    } else {
+                for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? act_f(v[j], act) : 0.f;
+            }
+            if (yf) stage_store(stg, yf, v, m0 + 32 * q, nb, M, N, lane, ksplit > 1);
+            if (ybf && nb < ldy && row < M) {
+                if (nb + 32 <= ldy) {
+                    uint4 *dst = (uint4 *)(ybf + (size_t)row * ldy + nb);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (nb + j < N) yf[(size_t)row * N + nb + j] = v[j];
+                    for (int j = 0; j < 4; ++j) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                        uint4 u; u.x = *(uint32_t *)&p0; u.y = *(uint32_t *)&p1; u.z = *(uint32_t *)&p2; u.w = *(uint32_t *)&p3;
+                        dst[j] = u;
                     }
-                }
-                if (ybf && nb < ldy) {
-                    if (nb + 32 <= ldy) {
-                        uint4 *dst = (uint4 *)(ybf + (size_t)row * ldy + nb);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                            uint4 u; u.x = *(uint32_t *)&p0; u.y = *(uint32_t *)&p1; u.z = *(uint32_t *)&p2; u.w = *(uint32_t *)&p3;
-                            dst[j] = u;
-                        }
-                    } else {
-                        for (int j = 0; j < 32 && nb + j < ldy; ++j) ybf[(size_t)row * ldy + nb + j] = __float2bfloat16_rn(v[j]);
-                    }
+                } else {
+                    for (int j = 0; j < 32 && nb + j < ldy; ++j) ybf[(size_t)row * ldy + nb + j] = __float2bfloat16_rn(v[j]);
                 }
             }
         }
