@@ -48,9 +48,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, i.e. below the bf16 / fp32 noise of this path) on the fast exp / rcp units:
+// the epilogue is instruction-latency bound, and erff() alone costs more than the tile's tensor-core time
+__device__ __forceinline__ float gelu_fast(float z) {
+    const float x = fabsf(z) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+    const float e = 1.0f - poly * __expf(-x * x);            // erf(|z| / sqrt 2)
+    return 0.5f * z + 0.5f * fabsf(z) * e;                  // 0.5 z (1 + sign(z) e)
+}
 __device__ __forceinline__ float act_f(float z, int act) {
     switch (act) {
-    case UHC_ACT_GELU: return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
+    case UHC_ACT_GELU: return gelu_fast(z);
     case UHC_ACT_TANH: return tanhf(z);
     case UHC_ACT_RELU: return z > 0.f ? z : 0.f;
     case UHC_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
@@ -152,15 +161,18 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             // fp32 outputs leave through a warp-private 32 x 33 staging tile in the (now idle) operand ring so that every store
             // instruction writes one full 128-byte row segment instead of 32 scattered words
             const int nb = n0 + c * 32;
-            float *stg = reinterpret_cast<float *>(smem) + q * (32 * 33);
+            float *stg = reinterpret_cast<float *>(smem) + q * (33 * 33);
             float v[32];
+            __syncwarp();
+            stg[32 * 33 + lane] = (bias && blockIdx.z == 0 && nb + lane < N) ? __ldg(bias + nb + lane) : 0.f;   // this chunk's 32 biases, read back as broadcasts
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = nb + j;
-                v[j] = (row < M && n < N) ? __uint_as_float(r[j]) + ((bias && blockIdx.z == 0) ? __ldg(bias + n) : 0.f) : 0.f;
-            }
+            for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? __uint_as_float(r[j]) + stg[32 * 33 + j] : 0.f;
             if (zf) stage_store(stg, zf, v, m0 + 32 * q, nb, M, N, lane, false);       // pre-activation (for the backward pass)
-            if (act != UHC_ACT_NONE) {
+            if (act == UHC_ACT_GELU) {        // act(0) = 0 for every supported activation except sigmoid, so padded entries stay 0
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            } else if (act != UHC_ACT_NONE) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? act_f(v[j], act) : 0.f;
             }
