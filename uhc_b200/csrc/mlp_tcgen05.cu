@@ -13,6 +13,7 @@
 namespace {
 constexpr int BM = 128, BN = 128, BK = 64, UK = 16, STAGES = 3;   // 3 stages x 32 KB -> two CTAs per SM: one CTA's epilogue overlaps the other's MMAs
 constexpr int STAGE_BYTES = (BM * BK + BN * BK) * 2;             // 32 KB
+constexpr int NTHREADS = 320;                                    // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue (two per TMEM lane quarter, half the columns each)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;    // + alignment slack + barriers
 thread_local std::string g_tc_err;
 
@@ -86,7 +87,7 @@ __device__ __forceinline__ void stage_store(float *stg, float *__restrict__ dst,
     }
 }
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(NTHREADS, 2)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
             __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act, int ksplit) {
     extern __shared__ uint8_t smem_raw[];
@@ -144,30 +145,30 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
     } else {
         const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                // which half of the tile's columns this warp drains
         mbar_wait(tfull, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + 32 * q + lane;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
+        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+            float v[32];
             const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32);
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-                           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-                           "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                         : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+                           "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]),
+                           "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
                          : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]) :: "memory");   // (operands: the loaded registers may not be read before the wait)
             // fp32 outputs leave through a warp-private 32 x 33 staging tile in the (now idle) operand ring so that every store
             // instruction writes one full 128-byte row segment instead of 32 scattered words
             const int nb = n0 + c * 32;
-            float *stg = reinterpret_cast<float *>(smem) + q * (33 * 33);
-            float v[32];
+            float *stg = reinterpret_cast<float *>(smem) + (warp - 2) * (33 * 33);
             __syncwarp();
             stg[32 * 33 + lane] = (bias && blockIdx.z == 0 && nb + lane < N) ? __ldg(bias + nb + lane) : 0.f;   // this chunk's 32 biases, read back as broadcasts
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? __uint_as_float(r[j]) + stg[32 * 33 + j] : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? v[j] + stg[32 * 33 + j] : 0.f;
             if (zf) stage_store(stg, zf, v, m0 + 32 * q, nb, M, N, lane, false);       // pre-activation (for the backward pass)
             if (act == UHC_ACT_GELU) {        // act(0) = 0 for every supported activation except sigmoid, so padded entries stay 0
 #pragma unroll
@@ -305,7 +306,7 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
         if (ksplit > 1 && cudaMemsetAsync(y_f32_or_null, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "memset failed"; return -1; }
     }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, ksplit);
-    k_linear_tc<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act, ksplit);
+    k_linear_tc<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act, ksplit);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
     return 0;
