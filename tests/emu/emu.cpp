@@ -40,7 +40,7 @@ static Emu<Real> *create(const UhcModelHost *m, const UhcEnvCfg *cfg, int E) {
     M.body_f = e->body_f.data(); M.dof_f = e->dof_f.data(); M.hull = e->hull.data(); M.hull_adr = e->hull_adr.data(); M.hull_num = e->hull_num.data();
     M.nbr = e->nbr.data(); M.nbradr = e->nbradr.data(); M.parent = e->parent.data(); M.depth = e->depth.data(); M.child_adr = e->child_adr.data();
     M.child = e->child.data(); M.body_sub_end = e->body_sub_end.data();
-    M.ee = e->ee.data(); M.lvl_tab = e->lvl_tab.data(); M.lvl_pack = e->lvl_pack.data();
+    M.ee = e->ee.data(); M.lvl_tab = e->lvl_tab.data(); M.lvl_pack = e->lvl_pack.data(); M.topo_s = nullptr;
     M.dt = (Real)m->dt; M.margin = (Real)m->margin; M.mu = (Real)m->mu; M.solref0 = (Real)m->solref[0]; M.solref1 = (Real)m->solref[1];
     M.simp0 = (Real)m->solimp[0]; M.simp1 = (Real)m->solimp[1]; M.simp2 = (Real)m->solimp[2]; M.simp3 = (Real)m->solimp[3]; M.simp4 = (Real)m->solimp[4];
     M.gravz = (Real)m->gravz; M.nshape = 1; M.nvert = m->nvert;

@@ -92,9 +92,12 @@ UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, 
     for (int i = lane; i < NV; i += 32) { w.v[i] = qvel_override ? qvel_override[i] : e0[EX_QVEL + i]; w.aw[i] = 0; }
     for (int i = lane; i < ACT_DIM; i += 32) w.act[i] = 0;
     LANES_END
-    const Model<Real> mdl = model_for_clip(ev, clip);
+    LANES_BEGIN
+    if (lane == 0) { w.mdl = model_for_clip(ev, clip); w.cfg = ev.cfg; }
+    LANES_END
+    const Model<Real> &mdl = w.mdl;
     TOPO_DECL(mdl);
-    const int iters = substep_dynamics<Real, ObsT>(mdl, ev.cfg, w, tp, (const Real *)nullptr, 0, false, (ObsT *)nullptr);
+    const int iters = substep_dynamics<Real, ObsT>(mdl, w.cfg, w, tp, (const Real *)nullptr, 0, false, (ObsT *)nullptr);
     world_quat(mdl, w.q, w);
     int *is = ev.istate + (size_t)env * SI_SIZE;
     Real *st = ev.state + (size_t)env * ST_SIZE;
@@ -102,7 +105,7 @@ UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, 
     for (int i = lane; i < 96; i += 32) { const Real v = (i & 3) == 0 ? Real(1) : Real(0); st[ST_BQUAT + i] = v; st[ST_PBQUAT + i] = v; }
     if (lane == 0) { is[SI_CUR_T] = 0; is[SI_CLIP] = clip; is[SI_START] = start; is[SI_LEN] = len; is[SI_NEWTON] = iters; is[SI_NCON] = w.ncon; }
     LANES_END
-    if (obs) obs_v2(ev.cfg, w, expert_frame(ev, clip, start, len, 1), ev.clip_shape + 17 * clip, obs);
+    if (obs) obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, 1), ev.clip_shape + 17 * clip, obs);
     Real *stq = ev.state + (size_t)env * ST_SIZE;
     LANES_BEGIN
     for (int i = lane; i < NQ; i += 32) stq[ST_Q + i] = w.q[i];
@@ -128,12 +131,15 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     LANES_END
     const Real *target = expert_frame(ev, clip, start, len, cur_t + 1) + EX_QPOS + 7;
     int iters = 0, maxcon = 0;
-    const Model<Real> mdl = model_for_clip(ev, clip);
+    LANES_BEGIN
+    if (lane == 0) { w.mdl = model_for_clip(ev, clip); w.cfg = ev.cfg; }
+    LANES_END
+    const Model<Real> &mdl = w.mdl;
     TOPO_DECL(mdl);
 #pragma unroll 1
     for (int it = 0; it < NSUB; ++it) {
         UHC_CTA_SYNC(true);   // see substep_dynamics: the CTA's warps run each substep's straight-line code together
-        iters += substep_dynamics<Real, ObsT>(mdl, ev.cfg, w, tp, target, it, true, torque_out, true);
+        iters += substep_dynamics<Real, ObsT>(mdl, w.cfg, w, tp, target, it, true, torque_out, true);
         if (w.ncon > maxcon) maxcon = w.ncon;
         if (it == NSUB - 1) world_quat(mdl, w.q, w);  // pose of the last forward pass (what data.body_xquat holds)
         integrate(mdl, w);
@@ -146,7 +152,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     LANES_END
     body_quat(w, bq);
     Real bd, rew, ci[5];
-    diff_and_reward(mdl, ev.cfg, w, expert_frame(ev, clip, start, len, cur_t), bq, pbq, &bd, &rew, ci);
+    diff_and_reward(mdl, w.cfg, w, expert_frame(ev, clip, start, len, cur_t), bq, pbq, &bd, &rew, ci);
     int fail = bd > ev.cfg.body_diff_thresh;
     {   // a non-finite state can never pass "bd > thresh": flag it as a failure (mirrors the try/except at :1207-1211)
         LVAR(int, bad);
@@ -158,7 +164,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
         if (WBALLOT(bad)) fail = 1;
     }
     const int end = (cur_t >= ev.cfg.env_episode_len) || (cur_t >= len + ev.cfg.trail_steps - 1);
-    if (obs) obs_v2(ev.cfg, w, expert_frame(ev, clip, start, len, cur_t + 1), ev.clip_shape + 17 * clip, obs);
+    if (obs) obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, cur_t + 1), ev.clip_shape + 17 * clip, obs);
     LANES_BEGIN
     if (lane == 0) {
         is[SI_CUR_T] = cur_t; is[SI_NEWTON] = iters; is[SI_NCON] = maxcon;

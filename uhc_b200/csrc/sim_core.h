@@ -85,6 +85,7 @@ struct Model {
                                   //   | nslot<<18 (max children per body on the level) | (first dof / 3)<<20 | reversed<<25 | nlevels<<26
     Real dt, margin, mu, solref0, solref1, simp0, simp1, simp2, simp3, simp4, gravz;
     int nshape, nvert;            // body_f / hull hold `nshape` consecutive shape variants ([nshape][NB][BODYF], [nshape][nvert][3])
+    const void *topo_s;           // device: LaneTopo[32] staged in shared memory by the kernels (per-lane tree links); unused on the host
 };
 
 template <class Real>
@@ -111,6 +112,10 @@ struct Work {
     int cbody[MAXCON]; Real cr[MAXCON][3], cdist[MAXCON], cD[MAXCON], caref[MAXCON][4], cres[MAXCON][4], cjp[MAXCON][4];
     int bcon_adr[NB + 1];
     int ncon, upper_contact;
+    // this env's model view (shape variant) and config: kept here so that the non-inlined phases read them from shared memory
+    // instead of a per-thread local-memory copy
+    alignas(8) Model<Real> mdl;
+    alignas(8) EnvCfg<Real> cfg;
 };
 
 // ------------------------------------------------------------------------------------------------ scalar helpers
@@ -325,7 +330,8 @@ UHC_DEV LaneTopo lane_topo(const Model<Real> &m, int lane) {
     return t;
 }
 #ifndef UHC_EMU
-#define TOPO_DECL(m) const LaneTopo tp = lane_topo(m, (int)(threadIdx.x & 31))
+// the per-lane tree links live in shared memory (staged once per CTA): functions take them by reference without a local-memory copy
+#define TOPO_DECL(m) const LaneTopo &tp = reinterpret_cast<const LaneTopo *>((m).topo_s)[threadIdx.x & 31]
 #define TP tp
 // parents at depth `lvl` add their children's K floats (children sit at lvl + 1)
 template <class R, int K> UHC_DEV void gather_children(R (&x)[K], const LaneTopo &tp, int lvl) {

@@ -24,8 +24,10 @@ __device__ __forceinline__ void stage_tables(EngineView<Real> &ev, unsigned char
     int *s_lvl = reinterpret_cast<int *>(s_dof + NV * 4);
     for (int i = threadIdx.x; i < NV * 4; i += blockDim.x) s_dof[i] = ev.model.dof_f[i];
     for (int i = threadIdx.x; i < (MAXLEVEL + 1) * LVL_G; i += blockDim.x) s_lvl[i] = ev.model.lvl_pack[i];
+    LaneTopo *s_topo = reinterpret_cast<LaneTopo *>(s_lvl + (MAXLEVEL + 1) * LVL_G);
+    if (threadIdx.x < 32) s_topo[threadIdx.x] = lane_topo(ev.model, (int)threadIdx.x);
     __syncthreads();
-    ev.model.dof_f = s_dof; ev.model.lvl_pack = s_lvl;
+    ev.model.dof_f = s_dof; ev.model.lvl_pack = s_lvl; ev.model.topo_s = s_topo;
 }
 
 template <class Real, int EPB>
@@ -94,7 +96,7 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     const int nshape = m->nshape > 0 ? m->nshape : 1;
     if (dev_copy_real<Real>(e, &M.body_f, m->body_f, (size_t)nshape * NB * BODYF) || dev_copy_real<Real>(e, &M.dof_f, m->dof_f, NV * 4) ||
         dev_copy_real<Real>(e, &M.hull, m->hull, (size_t)nshape * m->nvert * 3)) return -1;
-    M.nshape = nshape; M.nvert = m->nvert;
+    M.nshape = nshape; M.nvert = m->nvert; M.topo_s = nullptr;
     int *p;
 #define CPI(field, n) do { if (dev_copy(e, &p, m->field, (size_t)(n))) return -1; M.field = p; } while (0)
     CPI(hull_adr, NB); CPI(hull_num, NB); CPI(nbr, m->nnbr); CPI(nbradr, m->nvert + 1); CPI(parent, NB); CPI(depth, NB); CPI(child_adr, NB + 1);
@@ -114,7 +116,7 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
 }
 
 constexpr int EPB_F = UHC_EPB_F, EPB_D = 2;
-template <class Real, int EPB> constexpr size_t step_smem() { return EPB * sizeof(Work<Real>) + NV * 4 * sizeof(Real) + (MAXLEVEL + 1) * LVL_G * sizeof(int); }  // environments (warps) per block
+template <class Real, int EPB> constexpr size_t step_smem() { return EPB * sizeof(Work<Real>) + NV * 4 * sizeof(Real) + (MAXLEVEL + 1) * LVL_G * sizeof(int) + 32 * sizeof(LaneTopo); }  // environments (warps) per block
 
 extern "C" {
 
