@@ -26,6 +26,7 @@
 #define UHC_DEVNI __device__ __noinline__
 #define LANES_BEGIN { const int lane = (int)(threadIdx.x & 31);
 #define LANES_END } __syncwarp();
+#define LANES_END_R }                /* block that exchanged nothing through shared memory: no warp barrier needed */
 #define LVAR(T, n) T n
 #define LV(n) n
 #define LVARA(T, n, K) T n[K]
@@ -44,6 +45,7 @@ __device__ __forceinline__ int uhc_lds(const int *p) { int v; asm("ld.shared.s32
 #define UHC_DEVNI static
 #define LANES_BEGIN for (int lane = 0; lane < 32; ++lane) {
 #define LANES_END }
+#define LANES_END_R }
 #define LVAR(T, n) T n[32]
 #define LV(n) n[lane]
 #define LVARA(T, n, K) T n[32][K]
@@ -461,7 +463,7 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
             }
         }
         for (int i = 0; i < 3; i++) { LVA(nrow)[i].x = ri[2 * i]; LVA(nrow)[i].y = ri[2 * i + 1]; LVA(npA)[i].x = pi[2 * i]; LVA(npA)[i].y = pi[2 * i + 1]; }
-        LANES_END
+        LANES_END_R
         const int nslot = (UHC_LDT(m.lvl_pack + lvl * LVL_G) >> 18) & 3;   // uniform: most children any body of this level has
 #pragma unroll 1
         for (int k = 0; k < nslot; ++k) {  // children of this level's bodies: they sit one level deeper, their results are still in row / pA
@@ -469,7 +471,7 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
             const int cg = ((LV(ent) >> (9 + 3 * k)) & 7) - 1;
             LV(act) = cg >= 0; LV(src) = cg >= 0 ? cg * 6 + LV(rr) : lane;
             for (int i = 0; i < 3; i++) { LVA(trow)[2 * i] = LVA(row)[i].x; LVA(trow)[2 * i + 1] = LVA(row)[i].y; LVA(tpA)[2 * i] = LVA(pA)[i].x; LVA(tpA)[2 * i + 1] = LVA(pA)[i].y; }
-            LANES_END
+            LANES_END_R
             WSHFL(trow, trow, 6, LV(src));
             WSHFL(tpA, tpA, 6, LV(src));
             LANES_BEGIN
@@ -477,11 +479,11 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
                 P a, c; a.x = LVA(trow)[2 * i]; a.y = LVA(trow)[2 * i + 1]; c.x = LVA(tpA)[2 * i]; c.y = LVA(tpA)[2 * i + 1];
                 LVA(nrow)[i] = padd(LVA(nrow)[i], a); LVA(npA)[i] = padd(LVA(npA)[i], c);
             }
-            LANES_END
+            LANES_END_R
         }
         LANES_BEGIN
         for (int i = 0; i < 3; i++) { LVA(row)[i] = LVA(nrow)[i]; LVA(pA)[i] = LVA(npA)[i]; }
-        LANES_END
+        LANES_END_R
 #pragma unroll 1
         for (int blk = lvl == 0 ? 1 : 0; blk >= 0; --blk) {   // the centre body (level 0) has two blocks of virtual dofs
             LANES_BEGIN   // this lane's entries of U = IA S
@@ -541,7 +543,7 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
         const int b = (e & 63) - 1;
         LV(body) = b; LV(ent) = e;
         LV(src) = (b >= 0 && lvl > 0) ? ((e >> 6) & 7) * 6 : lane;
-        LANES_END
+        LANES_END_R
         WSHFL(acc, pacc, 6, LV(src));
         LANES_BEGIN
         const int b = LV(body), r = LV(rr);
@@ -688,7 +690,7 @@ UHC_DEVNI void tree_vel(const Model<Real> &m, Work<Real> &w, const Real *x, Real
         for (int j = 0; j < nd; ++j) paxpy6(x[d0 + j], as_pairs(w.S[d0 + j]), Vp);
     }
     for (int i = 0; i < 3; i++) { LVA(V)[2 * i] = Vp[i].x; LVA(V)[2 * i + 1] = Vp[i].y; }
-    LANES_END
+    LANES_END_R
     WANCESTOR(V, 6, tp);
     LANES_BEGIN
     if (lane < NB) for (int i = 0; i < 6; i++) X[lane][i] = LVA(V)[i];
@@ -845,17 +847,17 @@ UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real
             cross3(w.cr[c], f, t);
             LVA(F)[0] = t[0]; LVA(F)[1] = t[1]; LVA(F)[2] = t[2]; LVA(F)[3] = f[0]; LVA(F)[4] = f[1]; LVA(F)[5] = f[2];
         }
-        LANES_END
+        LANES_END_R
         WPREFIX(F, 6);
-        if (k == 0) { LANES_BEGIN for (int i = 0; i < 6; i++) { LVA(P0)[i] = LVA(F)[i]; LVA(P1)[i] = 0; } LANES_END }
-        else { LANES_BEGIN for (int i = 0; i < 6; i++) LVA(P1)[i] = LVA(F)[i]; LANES_END }
+        if (k == 0) { LANES_BEGIN for (int i = 0; i < 6; i++) { LVA(P0)[i] = LVA(F)[i]; LVA(P1)[i] = 0; } LANES_END_R }
+        else { LANES_BEGIN for (int i = 0; i < 6; i++) LVA(P1)[i] = LVA(F)[i]; LANES_END_R }
     }
     // lane = body: subtree(b) owns contacts [bcon_adr[b], bcon_adr[sub_end(b) + 1])
     LANES_BEGIN
     const int b = lane < NB ? lane : NB - 1;
     LV(jlo) = w.bcon_adr[b] - 1; LV(jhi) = w.bcon_adr[TP.sub_end < NB ? TP.sub_end + 1 : NB] - 1;
     if (lane >= NB) { LV(jlo) = -1; LV(jhi) = -1; }
-    LANES_END
+    LANES_END_R
     WSHFL(lo, P0, 6, (LV(jlo) < 0 ? 0 : LV(jlo)) & 31);
     WSHFL(hi, P0, 6, (LV(jhi) < 0 ? 0 : LV(jhi)) & 31);
     LANES_BEGIN
@@ -863,7 +865,7 @@ UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real
         if (LV(jlo) < 0) LVA(lo)[i] = 0;
         if (LV(jhi) < 0) LVA(hi)[i] = 0;
     }
-    LANES_END
+    LANES_END_R
     if (nchunk == 2) {      // indices >= 32 live in the second chunk: P(j) = total of chunk 0 + P1(j - 32)
         LVARA(Real, t0, 6); LVARA(Real, a, 6); LVARA(Real, c2, 6);
         WSHFL(t0, P0, 6, 31);
