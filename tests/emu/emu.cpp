@@ -64,7 +64,7 @@ static int emu_forward_given_tau(const Model<Real> &m, const EnvCfg<Real> &cfg, 
     // same sequence as substep_dynamics' PH_SMOOTH / PH_NEWTON phases with caller-provided torques and applied force
     kin_rne_forward(m, w, tp);
     project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
-    collide(m, w);
+    collide(m, w, tp);
     for (int i = 0; i < NV; i++) { Real f = -w.C[i] + (i < 6 ? (Real)fapp_d[i] : w.tau[i - 6]); w.fs[i] = f; w.as_[i] = f; }
     if (w.ncon == 0) { aba_solve(m, w, Real(0), false, w.as_); for (int i = 0; i < NV; i++) w.a[i] = w.as_[i]; return 0; }
     constraint_setup(m, w);

@@ -319,7 +319,7 @@ UHC_DEV int popc_(unsigned x) { int c = 0; while (x) { x &= x - 1; c++; } return
 // so one O(n) articulated-body sweep solves all three without ever forming the joint-space matrix: lane = body, articulated
 // inertia (sym 6x6) / bias wrench in registers, leaves -> root then root -> leaves, children/parent exchange by warp shuffles.
 // World-aligned spatial quantities about the common point O need no frame transforms between bodies.
-struct LaneTopo { int lane, parent, depth, sub_end, ch0, ch1, ch2; };
+struct LaneTopo { int lane, parent, depth, sub_end, ch0, ch1, ch2, hadr, hnum; };   // lane = body: tree links, hull vertex range
 template <class Real>
 UHC_DEV LaneTopo lane_topo(const Model<Real> &m, int lane) {
     LaneTopo t; t.lane = lane;
@@ -329,12 +329,14 @@ UHC_DEV LaneTopo lane_topo(const Model<Real> &m, int lane) {
     t.ch0 = (lane < NB && c0 < c1) ? UHC_LDG(m.child + c0) : -1;
     t.ch1 = (lane < NB && c0 + 1 < c1) ? UHC_LDG(m.child + c0 + 1) : -1;
     t.ch2 = (lane < NB && c0 + 2 < c1) ? UHC_LDG(m.child + c0 + 2) : -1;
+    t.hadr = UHC_LDG(m.hull_adr + b); t.hnum = lane < NB ? UHC_LDG(m.hull_num + b) : 0;
     return t;
 }
 #ifndef UHC_EMU
 // the per-lane tree links live in shared memory (staged once per CTA): functions take them by reference without a local-memory copy
 #define TOPO_DECL(m) const LaneTopo &tp = reinterpret_cast<const LaneTopo *>((m).topo_s)[threadIdx.x & 31]
 #define TP tp
+#define TP_OF(m, tp, b) (reinterpret_cast<const LaneTopo *>((m).topo_s)[b])
 // parents at depth `lvl` add their children's K floats (children sit at lvl + 1)
 template <class R, int K> UHC_DEV void gather_children(R (&x)[K], const LaneTopo &tp, int lvl) {
 #pragma unroll 1
@@ -359,6 +361,7 @@ template <class R, int K> UHC_DEV void fetch_parent(const R (&x)[K], R (&o)[K], 
 #else
 #define TOPO_DECL(m) LaneTopo tp[32]; for (int l_ = 0; l_ < 32; l_++) tp[l_] = lane_topo(m, l_)
 #define TP tp[lane]
+#define TP_OF(m, tp, b) (tp[b])
 template <class R, int K> static void emu_gather(R (*x)[K], const LaneTopo *tp, int lvl) {
     for (int b = 0; b < NB; b++) if (tp[b].depth == lvl) {
         const int ch[3] = {tp[b].ch0, tp[b].ch1, tp[b].ch2};
@@ -576,12 +579,22 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
 // MuJoCo semantics: SURVEY.md Appendix B (mj_kinematics / mj_comPos / mj_rne / mj_crb).
 template <class Real, class TPT>
 UHC_DEV void kin_rne_forward(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
+    // joint-angle sines / cosines of every body in one lane = body pass (the level loop below only has a few lanes active per level)
+    LVARA(Real, sc, 6);
+    LANES_BEGIN
+    const int b = lane;
+    for (int j = 0; j < 3; ++j) {
+        Real sn = 0, cs = 1;
+        if (b >= 1 && b < NB) sincos_(w.q[7 + 3 * (b - 1) + j], &sn, &cs);
+        LVA(sc)[2 * j] = sn; LVA(sc)[2 * j + 1] = cs;
+    }
+    LANES_END_R
     for (int lvl = 0; lvl <= MAXLEVEL; ++lvl) {
         LANES_BEGIN
         const int b = lane;
         if (b < NB && TP.depth == lvl) {
             const Real *bf = m.body_f + b * BODYF;
-            Real R[9], pos[3], V[6], A[6];
+            Real R[9], pos[3]; alignas(16) Real V[6], A[6];
             if (b == 0) {
                 Real qn[4] = {w.q[3], w.q[4], w.q[5], w.q[6]};
                 Real n = rsqrt_(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
@@ -614,7 +627,7 @@ UHC_DEV void kin_rne_forward(const Model<Real> &m, Work<Real> &w, const TPT &tp)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int dof = 6 + 3 * (b - 1) + j, col = 2 - j;
-                    Real ax[3] = {R[col], R[3 + col], R[6 + col]}, Sj[6], Sd[6], t[3];
+                    Real ax[3] = {R[col], R[3 + col], R[6 + col]}, t[3]; alignas(16) Real Sj[6], Sd[6];
                     cross3(r, ax, t);
                     Sj[0] = ax[0]; Sj[1] = ax[1]; Sj[2] = ax[2]; Sj[3] = t[0]; Sj[4] = t[1]; Sj[5] = t[2];
                     cross3(V, Sj, Sd);              // Sdot = V x_m S = (w x a, w x b + v x a)
@@ -622,8 +635,10 @@ UHC_DEV void kin_rne_forward(const Model<Real> &m, Work<Real> &w, const TPT &tp)
                     cross3(V + 3, Sj, t);
                     Sd[3] += t[0]; Sd[4] += t[1]; Sd[5] += t[2];
                     const Real qd = w.v[dof];
-                    for (int i = 0; i < 6; i++) { w.S[dof][i] = Sj[i]; A[i] += Sd[i] * qd; V[i] += Sj[i] * qd; }
-                    Real sn, cs; sincos_(w.q[7 + 3 * (b - 1) + j], &sn, &cs);
+                    for (int i = 0; i < 6; i++) w.S[dof][i] = Sj[i];
+                    paxpy6(qd, reinterpret_cast<const Pr<Real> *>(Sd), reinterpret_cast<Pr<Real> *>(A));
+                    paxpy6(qd, reinterpret_cast<const Pr<Real> *>(Sj), reinterpret_cast<Pr<Real> *>(V));
+                    const Real sn = LVA(sc)[2 * j], cs = LVA(sc)[2 * j + 1];
                     // R <- R * Rot(axis col, angle): rotate the two other columns
                     const int c1 = (col + 1) % 3, c2 = (col + 2) % 3;
                     for (int i = 0; i < 3; i++) {
@@ -709,8 +724,8 @@ UHC_DEV void project_force(const Model<Real> &m, Work<Real> &w, const Real (*F)[
 
 // ================================================================================================ collision
 // Floor plane z = 0 against each body hull (oracle/uhc_oracle.c or_collide states the manifold rule).
-template <class Real>
-UHC_DEV void collide(const Model<Real> &m, Work<Real> &w) {
+template <class Real, class TPT>
+UHC_DEV void collide(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
     // broad phase for all bodies at once (lane = body): bounding sphere against the plane
     LVAR(int, near); LVAR(int, cnt); LVAR(int, adr0);
     LANES_BEGIN
@@ -721,7 +736,7 @@ UHC_DEV void collide(const Model<Real> &m, Work<Real> &w) {
         f = !(cz - UHC_LDG(bf + 17) > m.margin);
     }
     LV(near) = f; LV(cnt) = 0;
-    LANES_END
+    LANES_END_R
     unsigned cand_b = WBALLOT(near);
     int ncon = 0, upper = 0;
     while (cand_b) {     // candidate bodies in ascending order
@@ -729,45 +744,53 @@ UHC_DEV void collide(const Model<Real> &m, Work<Real> &w) {
         cand_b &= cand_b - 1;
         if (ncon + 4 > MAXCON) continue;
         const Real *R = w.xmat[b];
-        const int adr = UHC_LDG(m.hull_adr + b), nvt = UHC_LDG(m.hull_num + b);
-        LVAR(Real, bz); LVAR(int, bi);
+        const int adr = TP_OF(m, tp, b).hadr, nvt = TP_OF(m, tp, b).hnum;
+        // deepest hull vertex: every lane keeps its best vertex (height, index, body-frame coordinates)
+        LVAR(Real, bz); LVAR(int, bi); LVARA(Real, bv, 3); LVARA(Real, nv, 3);
         LANES_BEGIN
-        Real best = Real(1e30); int besti = 1 << 20;
+        Real best = Real(1e30); int besti = 1 << 20; Real b0 = 0, b1 = 0, b2 = 0;
         for (int i = lane; i < nvt; i += 32) {
             const Real *vv = m.hull + 3 * (adr + i);
-            const Real z = w.xpos[b][2] + R[6] * UHC_LDG(vv) + R[7] * UHC_LDG(vv + 1) + R[8] * UHC_LDG(vv + 2);
-            if (z < best) { best = z; besti = i; }
+            const Real v0 = UHC_LDG(vv), v1 = UHC_LDG(vv + 1), v2 = UHC_LDG(vv + 2);
+            const Real z = w.xpos[b][2] + R[6] * v0 + R[7] * v1 + R[8] * v2;
+            if (z < best) { best = z; besti = i; b0 = v0; b1 = v1; b2 = v2; }
         }
-        LV(bz) = best; LV(bi) = besti;
-        LANES_END
+        LV(bz) = best; LV(bi) = besti; LVA(bv)[0] = b0; LVA(bv)[1] = b1; LVA(bv)[2] = b2;
+        LANES_END_R
         Real minz; int mini;
         WARGMIN(bz, bi, minz, mini);
         if (minz > m.margin) continue;
+        // its hull-graph neighbours (lane = neighbour): the ones within the margin join the manifold, first three in list order
         const int g = adr + mini, n0 = UHC_LDG(m.nbradr + g), nn = UHC_LDG(m.nbradr + g + 1) - n0;
         LVAR(int, flag);
         LANES_BEGIN
         int f = 0;
         if (lane < nn) {
             const Real *vv = m.hull + 3 * (adr + UHC_LDG(m.nbr + n0 + lane));
-            const Real z = w.xpos[b][2] + R[6] * UHC_LDG(vv) + R[7] * UHC_LDG(vv + 1) + R[8] * UHC_LDG(vv + 2);
+            const Real v0 = UHC_LDG(vv), v1 = UHC_LDG(vv + 1), v2 = UHC_LDG(vv + 2);
+            const Real z = w.xpos[b][2] + R[6] * v0 + R[7] * v1 + R[8] * v2;
             f = z <= m.margin;
+            LVA(nv)[0] = v0; LVA(nv)[1] = v1; LVA(nv)[2] = v2;
         }
         LV(flag) = f;
-        LANES_END
-        unsigned mask = WBALLOT(flag);
-        int cand[4]; int nc = 0; cand[nc++] = mini;
-        while (mask && nc < 4) { int l = 0; while (!((mask >> l) & 1u)) l++; mask &= mask - 1; cand[nc++] = UHC_LDG(m.nbr + n0 + l); }
+        LANES_END_R
+        const unsigned mask = WBALLOT(flag);
+        int nsel = 0; for (unsigned t = mask; t && nsel < 3; t &= t - 1) nsel++;
+        const int nc = 1 + nsel;
         LANES_BEGIN
-        if (lane < nc) {
-            const int ci = lane == 0 ? cand[0] : lane == 1 ? cand[1] : lane == 2 ? cand[2] : cand[3];
-            const Real *vv = m.hull + 3 * (adr + ci);
-            const Real v0 = UHC_LDG(vv), v1 = UHC_LDG(vv + 1), v2 = UHC_LDG(vv + 2);
-            const Real px = w.xpos[b][0] + R[0] * v0 + R[1] * v1 + R[2] * v2;
-            const Real py = w.xpos[b][1] + R[3] * v0 + R[4] * v1 + R[5] * v2;
-            const Real pz = w.xpos[b][2] + R[6] * v0 + R[7] * v1 + R[8] * v2;
-            const int c = ncon + lane;
-            w.cbody[c] = b; w.cdist[c] = pz;
-            w.cr[c][0] = px - w.q[0]; w.cr[c][1] = py - w.q[1]; w.cr[c][2] = Real(0.5) * pz - w.q[2];
+        // slot 0: the deepest vertex (held by lane mini mod 32); slots 1..: flagged neighbours in lane order
+        int below = 0; for (unsigned t = mask & ((1u << lane) - 1u); t; t &= t - 1) below++;
+        const bool is_nb = ((mask >> lane) & 1u) && below < 3, is_min = lane == (mini & 31);
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0 ? is_min : is_nb) {
+                const Real v0 = pass == 0 ? LVA(bv)[0] : LVA(nv)[0], v1 = pass == 0 ? LVA(bv)[1] : LVA(nv)[1], v2 = pass == 0 ? LVA(bv)[2] : LVA(nv)[2];
+                const Real px = w.xpos[b][0] + R[0] * v0 + R[1] * v1 + R[2] * v2;
+                const Real py = w.xpos[b][1] + R[3] * v0 + R[4] * v1 + R[5] * v2;
+                const Real pz = w.xpos[b][2] + R[6] * v0 + R[7] * v1 + R[8] * v2;
+                const int c = ncon + (pass == 0 ? 0 : 1 + below);
+                w.cbody[c] = b; w.cdist[c] = pz;
+                w.cr[c][0] = px - w.q[0]; w.cr[c][1] = py - w.q[1]; w.cr[c][2] = Real(0.5) * pz - w.q[2];
+            }
         }
         if (lane == b) LV(cnt) = nc;
         LANES_END
@@ -1102,7 +1125,7 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
             if (with_pd) rfc_implicit(cfg, w, fapp);
             kin_rne_forward(m, w, tp);
             project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
-            collide(m, w);
+            collide(m, w, tp);
             LANES_BEGIN
             for (int i = lane; i < NV; i += 32) {  // smooth acceleration a_s = M^-1 (tau + f_applied - C)
                 Real f = -w.C[i];
