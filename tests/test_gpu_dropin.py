@@ -77,5 +77,11 @@ def test_single_env_facade_matches_engine_and_oracle(tmp_path, monkeypatch, gold
         assert r == 1.0 and done == do and info["fail"] == io["fail"] and abs(info["percent"] - io["percent"]) < 1e-6
         assert np.abs(ob - oo).max() < 2e-3 and abs(cr - ro) < 1e-3 and np.abs(ci - io["c_info"]).max() < 2e-3
         assert abs(env.calc_body_diff() - oe.body_diff()) < 1e-4
+        # getters of the reference surface (humanoid_im.py:910-965, :1198): end effectors, Pelvis COM, previous body quats
+        assert np.abs(env.get_com() - oe.d.xipos[:3]).max() < 1e-4
+        ee = env.get_ee_pos(None).reshape(5, 3)
+        assert np.abs(ee - oe.d.xpos.reshape(24, 3)[env.model_tables.ee]).max() < 1e-4
+        assert env.get_ee_pos("heading").shape == (15,) and env.prev_bquat.shape == (96,)
+        assert np.abs(env.data.qpos - oe.d.qpos).max() < 1e-4 and len(env.model.actuator_names) == 69
     env.fail_safe()
     assert np.abs(env.get_humanoid_qpos() - env.get_expert_qpos()).max() < 1e-6

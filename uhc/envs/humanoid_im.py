@@ -26,6 +26,43 @@ class _RobotShim:
         raise NotImplementedError("the B200 engine has no MuJoCo XML to export; rendering is out of scope")
 
 
+class _ModelShim:
+    """The few mujoco_py model attributes the agent / reward code reads (agent_copycat.py:139, humanoid_im.py:917)."""
+
+    def __init__(self, tables):
+        self.body_names = list(tables.body_names)
+        self._body_name2id = {n: i for i, n in enumerate(self.body_names)}
+        self.actuator_names = [f"{b}_{ax}" for b in self.body_names[1:] for ax in "zyx"]   # three hinges z, y, x per non-root body
+
+
+class _DataShim:
+    """data.qpos / data.qvel / data.body_xpos views of the engine state (read-only copies)."""
+
+    def __init__(self, env):
+        self._env = env
+
+    qpos = property(lambda self: self._env.engine.get_state(0)["qpos"])
+    qvel = property(lambda self: self._env.engine.get_state(0)["qvel"])
+    body_xpos = property(lambda self: self._env.engine.get_state(0)["xpos"])
+
+
+def _quat_rot(q):
+    w, x, y, z = np.asarray(q, dtype=np.float64) / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _transform_vec(v, q, trans="root"):
+    """uhc/utils/math_utils.py:103-115."""
+    q = np.asarray(q, dtype=np.float64).copy()
+    if trans == "heading":
+        q[1] = q[2] = 0.0
+    else:
+        assert trans == "root"
+    return _quat_rot(q).T.dot(v)
+
+
 class HumanoidEnv:
     def __init__(self, cfg, init_expert, data_specs, mode="train", no_root=False, device=0, precision=32):
         import torch
@@ -45,6 +82,8 @@ class HumanoidEnv:
         self.action_space, self.observation_space = _Space(ACT_DIM), _Space(OBS_DIM)
         self.body_diffw, self.jpos_diffw = self.model_tables.diffw[1:], self.model_tables.diffw[:, None]
         self.smpl_robot, self.np_random = _RobotShim(), np.random.RandomState(0)
+        self.model, self.data, self.converter = _ModelShim(self.model_tables), _DataShim(self), None
+        self.prev_bquat = None
         self.cur_t, self.start_ind, self.end_reward, self.rfc_rate = 0, 0, 0.0, 1.0
         self.last_reward, self.last_cinfo = 0.0, np.zeros(5)
         self._act = torch.zeros(1, ACT_DIM, device=self.engine.obs.device)
@@ -74,9 +113,11 @@ class HumanoidEnv:
             qpos[7:] += self.np_random.normal(0.0, self.cc_cfg.env_init_noise, 69)
         obs = self.engine.reset([0], 0, 0, None, qpos=qpos[None] if qpos is not None else None,
                                 qvel=self.expert["qvel"][:1] if qpos is not None else None)
+        self.prev_bquat = None            # humanoid_im.py:95 / :1198: set at the start of each step
         return obs[0].double().cpu().numpy()
 
     def step(self, a):
+        self.prev_bquat = self.get_body_quat().copy()
         self._act.copy_(self.torch.as_tensor(np.asarray(a, dtype=np.float32)).reshape(1, ACT_DIM))
         obs, rew, cinfo, fail, end, pct = self.engine.step(self._act)
         self.cur_t += 1
@@ -108,6 +149,29 @@ class HumanoidEnv:
 
     def get_body_quat(self):
         return self.engine.get_state(0)["bquat"]
+
+    @property
+    def bquat(self):
+        return self.get_body_quat()
+
+    def get_ee_pos(self, transform):
+        """humanoid_im.py:910-923: the five end effectors, world frame or relative to the root in its root / heading frame."""
+        st = self.engine.get_state(0)
+        out = []
+        for b in self.model_tables.ee:
+            v = st["xpos"][int(b)].copy()
+            if transform is not None:
+                v = _transform_vec(v - st["qpos"][:3], st["qpos"][3:7], transform)
+            out.append(v)
+        return np.concatenate(out)
+
+    def get_com(self):
+        """humanoid_im.py:962-965: data.get_body_xipos("Pelvis")."""
+        st = self.engine.get_state(0)
+        return st["xpos"][0] + _quat_rot(st["qpos"][3:7]).dot(self.model_tables.ipos[0])
+
+    def render(self, *a, **k):
+        raise NotImplementedError("rendering needs MuJoCo; the B200 engine has no viewer")
 
     def calc_body_diff(self):
         cur = self.engine.get_state(0)["xpos"]
