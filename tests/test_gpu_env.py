@@ -209,3 +209,31 @@ def test_more_than_32_contacts_match_oracle():
         big = max(big, st["ncon"])
         assert np.abs(st["qpos"] - oe.d.qpos).max() < 1e-3, (t, np.abs(st["qpos"] - oe.d.qpos).max())
     eng.close()
+
+
+def test_work_sorted_slots_do_not_change_results(golden_dir, monkeypatch):
+    """The step kernel assigns environments to warps by the previous step's solver iterations (k_order_envs); outputs are indexed
+    by environment id, so a run with the identity assignment must give bit-identical results."""
+    import torch
+    from uhc_b200.engine import Engine
+    z = np.load(os.path.join(golden_dir, "expert_kick.npz"))
+    ex = {k: z[k] for k in z.files}
+    so = np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+    E = 96
+    rng = np.random.RandomState(3)
+    starts = rng.randint(0, 30, E).astype(np.int32)
+    acts = [torch.tensor(rng.normal(0, 0.3, (E, 105)), dtype=torch.float32, device="cuda") for _ in range(4)]
+    outs = []
+    for sort in ("1", "0"):
+        monkeypatch.setenv("UHC_SORT_ENVS", sort)
+        eng = Engine(E)
+        eng.load_clips([ex], [so])
+        eng.reset(start=starts)
+        rec = []
+        for a in acts:
+            o, r, ci, f, en, p = eng.step(a)
+            rec.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), f.cpu().numpy().copy()))
+        outs.append(rec)
+        eng.close()
+    for (o1, r1, f1), (o0, r0, f0) in zip(*outs):
+        assert np.array_equal(o1, o0) and np.array_equal(r1, r0) and np.array_equal(f1, f0)

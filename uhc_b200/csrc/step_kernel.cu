@@ -2,6 +2,7 @@
 // working set in shared memory, state records in HBM.  sm_100a.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -33,15 +34,30 @@ __device__ __forceinline__ void stage_tables(EngineView<Real> &ev, unsigned char
 template <class Real, int EPB>
 __global__ void __launch_bounds__(32 * EPB, (sizeof(Real) == 4 && EPB <= 7 ? 2 : 1))
 k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict__ obs, float *__restrict__ rew, float *__restrict__ cinfo,
-           int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque) {
+           int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque, const int *__restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, env = blockIdx.x * EPB + warp;
+    const int warp = threadIdx.x >> 5, slot = blockIdx.x * EPB + warp;
     stage_tables<Real, EPB>(ev, smem);
-    if (env >= ev.num_envs) return;
+    if (slot >= ev.num_envs) return;
+    // the warps of a CTA wait for each other every substep: `order` groups environments that needed a similar number of solver
+    // iterations in the previous step into the same CTA (k_order_envs), outputs stay indexed by the environment id
+    const int env = order ? order[slot] : slot;
     Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
     env_step_warp<Real, float>(ev, env, w, act + (size_t)env * ACT_DIM, obs ? obs + (size_t)env * OBS_DIM : nullptr, rew ? rew + env : nullptr,
                                cinfo ? cinfo + (size_t)env * 5 : nullptr, fail ? fail + env : nullptr, end ? end + env : nullptr,
                                pct ? pct + env : nullptr, torque ? torque + (size_t)env * NSUB * NU : nullptr);
+}
+
+// counting sort of the environments by the Newton iterations of their previous step (one block)
+__global__ void __launch_bounds__(1024) k_order_envs(const int *__restrict__ istate, int E, int *__restrict__ order) {
+    __shared__ int hist[64], base[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) { int k = istate[(size_t)i * SI_SIZE + SI_NEWTON]; k = k < 0 ? 0 : (k > 63 ? 63 : k); atomicAdd(&hist[k], 1); }
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int k = 0; k < 64; k++) { base[k] = run; run += hist[k]; } }
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) { int k = istate[(size_t)i * SI_SIZE + SI_NEWTON]; k = k < 0 ? 0 : (k > 63 ? 63 : k); order[atomicAdd(&base[k], 1)] = i; }
 }
 
 template <class Real, int EPB>
@@ -72,6 +88,7 @@ struct UhcEngine {
     // staging for the host-buffer API
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_cinfo = nullptr, *d_pct = nullptr; int *d_fail = nullptr, *d_end = nullptr;
     int *d_ids = nullptr; int ids_cap = 0;
+    int *d_order = nullptr;   // warp slot -> environment (work-sorted each step), null = identity
 };
 
 template <class T> static int dev_copy(UhcEngine *e, T **dst, const T *src, size_t n) {
@@ -129,6 +146,10 @@ int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_e
     e->E = num_envs; e->device = device; e->precision = precision; e->launches = 0; e->nshape = model->nshape > 0 ? model->nshape : 1;
     int rc = precision == 32 ? build_view<float>(e, e->evf, model, cfg) : build_view<double>(e, e->evd, model, cfg);
     if (rc) { delete e; return rc; }
+    {   // work-sorted warp slots (UHC_SORT_ENVS=0 keeps the identity mapping)
+        const char *se = getenv("UHC_SORT_ENVS");
+        if (!(se && se[0] == '0') && num_envs > 2 * EPB_F) { CK(cudaMalloc((void **)&e->d_order, (size_t)num_envs * sizeof(int))); e->allocs.push_back(e->d_order); }
+    }
     if (precision == 32) {
         CK(cudaFuncSetAttribute(k_env_step<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<float, EPB_F>()));
         CK(cudaFuncSetAttribute(k_env_reset<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<float, EPB_F>()));
@@ -236,10 +257,11 @@ int uhc_env_step(UhcEngine *e, const float *actions_dev, float *obs_dev, float *
     if (!e || !actions_dev) { g_err = "uhc_env_step: bad argument"; return -2; }
     if (!e->d_expert) { g_err = "uhc_env_step: no clips loaded"; return -3; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (e->d_order) { k_order_envs<<<1, 1024, 0, st>>>(e->precision == 32 ? e->evf.istate : e->evd.istate, e->E, e->d_order); e->launches++; }
     if (e->precision == 32)
-        k_env_step<float, EPB_F><<<(e->E + EPB_F - 1) / EPB_F, 32 * EPB_F, step_smem<float, EPB_F>(), st>>>(e->evf, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev);
+        k_env_step<float, EPB_F><<<(e->E + EPB_F - 1) / EPB_F, 32 * EPB_F, step_smem<float, EPB_F>(), st>>>(e->evf, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev, e->d_order);
     else
-        k_env_step<double, EPB_D><<<(e->E + EPB_D - 1) / EPB_D, 32 * EPB_D, step_smem<double, EPB_D>(), st>>>(e->evd, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev);
+        k_env_step<double, EPB_D><<<(e->E + EPB_D - 1) / EPB_D, 32 * EPB_D, step_smem<double, EPB_D>(), st>>>(e->evd, actions_dev, obs_dev, reward_dev, cinfo_dev, fail_dev, end_dev, percent_dev, torque_dev, e->d_order);
     CK(cudaGetLastError());
     e->launches++;
     return 0;
