@@ -146,9 +146,10 @@ int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_e
     e->E = num_envs; e->device = device; e->precision = precision; e->launches = 0; e->nshape = model->nshape > 0 ? model->nshape : 1;
     int rc = precision == 32 ? build_view<float>(e, e->evf, model, cfg) : build_view<double>(e, e->evd, model, cfg);
     if (rc) { delete e; return rc; }
-    {   // work-sorted warp slots (UHC_SORT_ENVS=0 keeps the identity mapping)
+    {   // work-sorted warp slots: opt-in (UHC_SORT_ENVS=1).  Measured at 4096 envs: 1.52 M env-steps/s sorted vs 1.57 M with the identity
+        // mapping -- the previous step's iteration total does not predict the per-substep imbalance well enough to pay for itself
         const char *se = getenv("UHC_SORT_ENVS");
-        if (!(se && se[0] == '0') && num_envs > 2 * EPB_F) { CK(cudaMalloc((void **)&e->d_order, (size_t)num_envs * sizeof(int))); e->allocs.push_back(e->d_order); }
+        if (se && se[0] == '1' && num_envs > 2 * EPB_F) { CK(cudaMalloc((void **)&e->d_order, (size_t)num_envs * sizeof(int))); e->allocs.push_back(e->d_order); }
     }
     if (precision == 32) {
         CK(cudaFuncSetAttribute(k_env_step<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<float, EPB_F>()));
