@@ -210,9 +210,18 @@ __global__ void k_f32_to_bf16_padded(const float *__restrict__ x, __nv_bfloat16 
 }
 
 
+// d/dz gelu(z) = Phi(z) + z phi(z), Phi through the same A&S erf as gelu_fast (shares the exp)
+__device__ __forceinline__ float dgelu_fast(float z) {
+    const float x = fabsf(z) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+    const float ex = __expf(-x * x);                       // exp(-z^2 / 2)
+    const float e = 1.0f - poly * ex;                      // erf(|z| / sqrt 2)
+    return 0.5f + copysignf(0.5f * e, z) + z * 0.3989422804014327f * ex;
+}
 __device__ __forceinline__ float act_b(float z, int act) {
     switch (act) {
-    case UHC_ACT_GELU: return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+    case UHC_ACT_GELU: return dgelu_fast(z);
     case UHC_ACT_TANH: { float t = tanhf(z); return 1.0f - t * t; }
     case UHC_ACT_RELU: return z > 0.f ? 1.f : 0.f;
     case UHC_ACT_SIGMOID: { float s = 1.0f / (1.0f + expf(-z)); return s * (1.0f - s); }
@@ -231,6 +240,74 @@ __global__ void k_transpose_bf16(const __nv_bfloat16 *__restrict__ in, __nv_bflo
     for (int i = threadIdx.y; i < 64; i += 8) {
         const int c = c0 + i, r = r0 + threadIdx.x;
         if (c < Cc && r < ld_out) out[(size_t)c * ld_out + r] = t[threadIdx.x][i];
+    }
+}
+// vectorised variants (4 elements per thread along the contiguous dimension, all loads of a thread issued before use): used when the
+// row lengths are multiples of 4
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+    uint2 u; u.x = *(uint32_t *)&p0; u.y = *(uint32_t *)&p1; return u;
+}
+__global__ void __launch_bounds__(256) k_transpose_bf16_v4(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ out, int R, int Cc, int ld_in, int ld_out) {
+    __shared__ float t[64][65];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    uint2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 16 * k, c = c0 + 4 * tx;
+        v[k] = (r < R && c < Cc) ? *reinterpret_cast<const uint2 *>(in + (size_t)r * ld_in + c) : make_uint2(0u, 0u);   // Cc % 4 == 0: a group is all in or all out
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 a = *(__nv_bfloat162 *)&v[k].x, b = *(__nv_bfloat162 *)&v[k].y;
+        float *row = t[ty + 16 * k] + 4 * tx;
+        row[0] = __low2float(a); row[1] = __high2float(a); row[2] = __low2float(b); row[3] = __high2float(b);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 16 * k, r = r0 + 4 * tx;
+        if (c < Cc && r < ld_out)
+            *reinterpret_cast<uint2 *>(out + (size_t)c * ld_out + r) = pack_bf16x4(t[4 * tx][ty + 16 * k], t[4 * tx + 1][ty + 16 * k], t[4 * tx + 2][ty + 16 * k], t[4 * tx + 3][ty + 16 * k]);
+    }
+}
+__global__ void __launch_bounds__(256) k_dact_bf16_v4(const float *__restrict__ dh, const float *__restrict__ z, __nv_bfloat16 *__restrict__ dz, __nv_bfloat16 *__restrict__ dzT,
+                                                     float *__restrict__ db, int M, int N, int ld_dz, int ld_dzT, int act) {
+    __shared__ float t[64][65];
+    __shared__ float cs[64];
+    const int n0 = blockIdx.x * 64, m0 = blockIdx.y * 64, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    if (threadIdx.x < 64) cs[threadIdx.x] = 0.f;
+    float4 g[4], zz[4];
+    const int n = n0 + 4 * tx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int m = m0 + ty + 16 * k;
+        const bool in = m < M && n < N;
+        g[k] = in ? *reinterpret_cast<const float4 *>(dh + (size_t)m * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        zz[k] = (in && z) ? *reinterpret_cast<const float4 *>(z + (size_t)m * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int m = m0 + ty + 16 * k;
+        float4 v = g[k];
+        if (z) { v.x *= act_b(zz[k].x, act); v.y *= act_b(zz[k].y, act); v.z *= act_b(zz[k].z, act); v.w *= act_b(zz[k].w, act); }
+        float *row = t[ty + 16 * k] + 4 * tx;
+        row[0] = v.x; row[1] = v.y; row[2] = v.z; row[3] = v.w;
+        c0 += v.x; c1 += v.y; c2 += v.z; c3 += v.w;
+        if (dz && m < M && n < ld_dz) *reinterpret_cast<uint2 *>(dz + (size_t)m * ld_dz + n) = pack_bf16x4(v.x, v.y, v.z, v.w);
+    }
+    if (db) { atomicAdd(&cs[4 * tx], c0); atomicAdd(&cs[4 * tx + 1], c1); atomicAdd(&cs[4 * tx + 2], c2); atomicAdd(&cs[4 * tx + 3], c3); }
+    __syncthreads();
+    if (db && threadIdx.x < 64 && n0 + threadIdx.x < N) atomicAdd(db + n0 + threadIdx.x, cs[threadIdx.x]);
+    if (dzT) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int nn = n0 + ty + 16 * k, m = m0 + 4 * tx;
+            if (nn < N && m < ld_dzT)
+                *reinterpret_cast<uint2 *>(dzT + (size_t)nn * ld_dzT + m) = pack_bf16x4(t[4 * tx][ty + 16 * k], t[4 * tx + 1][ty + 16 * k], t[4 * tx + 2][ty + 16 * k], t[4 * tx + 3][ty + 16 * k]);
+        }
     }
 }
 // dz = dh * act'(z): writes dz (bf16, [M][ld_dz]) and its transpose ([N][ld_dzT], zero padded in M) and accumulates column sums (bias grads)
@@ -322,14 +399,20 @@ int uhc_linear_forward_tc_train(const void *x_bf16, const void *W_bf16, const fl
 }
 int uhc_transpose_bf16(const void *in, void *out, int R, int Cc, int ld_in, int ld_out, void *stream) {
     dim3 grid((Cc + 63) / 64, (R + 63) / 64);
-    k_transpose_bf16<<<grid, dim3(64, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, R, Cc, ld_in, ld_out);
+    if (Cc % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && ((uintptr_t)in & 7) == 0 && ((uintptr_t)out & 7) == 0)
+        k_transpose_bf16_v4<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, R, Cc, ld_in, ld_out);
+    else
+        k_transpose_bf16<<<grid, dim3(64, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)in, (__nv_bfloat16 *)out, R, Cc, ld_in, ld_out);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 int uhc_dact_bf16(const float *dh, const float *z_or_null, void *dz_bf16, void *dzT_bf16, float *db_or_null, int M, int N, int ld_dz, int ld_dzT, int act,
                   void *stream) {
     if (db_or_null) cudaMemsetAsync(db_or_null, 0, N * sizeof(float), (cudaStream_t)stream);
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    k_dact_bf16<<<grid, dim3(64, 8), 0, (cudaStream_t)stream>>>(dh, z_or_null, (__nv_bfloat16 *)dz_bf16, (__nv_bfloat16 *)dzT_bf16, db_or_null, M, N, ld_dz, ld_dzT, act);
+    const bool v4 = N % 4 == 0 && (!dz_bf16 || (ld_dz % 4 == 0 && ((uintptr_t)dz_bf16 & 7) == 0)) && (!dzT_bf16 || (ld_dzT % 4 == 0 && ((uintptr_t)dzT_bf16 & 7) == 0)) &&
+                    ((uintptr_t)dh & 15) == 0 && (!z_or_null || ((uintptr_t)z_or_null & 15) == 0);
+    if (v4) k_dact_bf16_v4<<<grid, 256, 0, (cudaStream_t)stream>>>(dh, z_or_null, (__nv_bfloat16 *)dz_bf16, (__nv_bfloat16 *)dzT_bf16, db_or_null, M, N, ld_dz, ld_dzT, act);
+    else k_dact_bf16<<<grid, dim3(64, 8), 0, (cudaStream_t)stream>>>(dh, z_or_null, (__nv_bfloat16 *)dz_bf16, (__nv_bfloat16 *)dzT_bf16, db_or_null, M, N, ld_dz, ld_dzT, act);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 }
