@@ -8,7 +8,8 @@
 // Algorithms (all world-aligned spatial vectors about the reference point O = root position):
 //   kinematics            level-synchronous tree pass, lane = body                         (a5: mj_kinematics)
 //   bias force C(q,v)     spatial recursive Newton-Euler, lane = body / lane = dof         (a5: mj_rne)
-//   linear solves         O(n) articulated-body sweeps, lane = body, registers + shuffles (replaces mj_crb + mj_factorM + cho_solve)
+//   linear solves         O(n) articulated-body sweeps over a centre-rooted 7-level tree, 6 lanes per body, 3x3 block
+//                         elimination, packed fp32 pairs (replaces mj_crb + mj_factorM + cho_solve)
 //   stable PD             (M_stale + Kd dt)^-1 rhs by the articulated-body solve             (a3: humanoid_im.py:1014-1076)
 //   floor contacts        plane / convex-hull support vertex + hull-graph neighbours        (a5: collision)
 //   constraint solve      primal Newton on the convex soft-constraint cost, Newton direction = articulated-body solve with
@@ -907,8 +908,8 @@ UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real
 }
 
 // ================================================================================================ constraint solve
-// min_a 1/2 (a-a_s)^T M (a-a_s) + sum_rows 1/2 D min(0, J a - aref)^2 ; primal Newton, Hessian = M + J^T D_act J built as a
-// CRBA over contact-augmented composites, factorised tree-sparse (only the lower-body rows when no arm/head contact).
+// min_a 1/2 (a-a_s)^T M (a-a_s) + sum_rows 1/2 D min(0, J a - aref)^2 ; primal Newton.  The Hessian M + J^T D_act J is never formed:
+// the Newton direction is one articulated-body solve with contact-augmented body inertias (aba_solve, use_contacts).
 // newton_init: start from the warm start (previous qacc, as MuJoCo's warmstart): residuals J a - aref and M a by O(n) passes.
 // The problem is strictly convex, so the minimiser does not depend on the start; starting from the warm start makes the
 // unconstrained solve a_s = M^-1 f_s unnecessary whenever contacts are present.  Returns the gradient-norm scale.
@@ -1019,7 +1020,7 @@ constexpr double PI_D = 3.14159265358979323846;
 
 // stable PD torque for substep `it` (humanoid_im.py:1033-1076 + :1014-1031): uses the M, C currently in the work set
 // (= previous forward pass: per-body inertias w.Ib, motion subspaces w.S, bias w.C) with the current q, v.  pd_setup leaves the right-hand side in w.p;
-// after the shared L^T D L solve pd_finish turns the acceleration into clipped torques in w.tau (:1160).
+// after the shared articulated-body solve pd_finish turns the acceleration into clipped torques in w.tau (:1160).
 template <class Real>
 UHC_DEV void pd_gains(const EnvCfg<Real> &cfg, const Work<Real> &w, int it, Real *sp, Real *sd) {
     *sp = 1; *sd = 1;
