@@ -76,7 +76,7 @@ class Emu:
 
     def reset(self, env=0, clip=0, start=0, length=None, qpos=None, qvel=None):
         obs = np.zeros(657)
-        L = int(self.lens[clip]) if length is None else length
+        L = int(self.lens[clip]) - start if length is None else length      # Engine.reset: the rest of the clip from `start`
         q = None if qpos is None else np.ascontiguousarray(qpos, dtype=np.float64)
         v = None if qvel is None else np.ascontiguousarray(qvel, dtype=np.float64)
         self.lib.emu_reset(self.h, self.prec, env, clip, start, L, _p(q), _p(v), _p(obs))

@@ -237,3 +237,62 @@ def test_work_sorted_slots_do_not_change_results(golden_dir, monkeypatch):
         eng.close()
     for (o1, r1, f1), (o0, r0, f0) in zip(*outs):
         assert np.array_equal(o1, o0) and np.array_equal(r1, r0) and np.array_equal(f1, f0)
+
+
+def test_ragged_clips_partial_resets_and_clip_end(golden_dir):
+    """Edge cases of the batched surface: an env count that does not fill the last CTA (13), clips of very different lengths
+    (3 .. ~70 frames), slices with explicit (start, length), re-seeding a SUBSET of
+    envs leaves the others untouched, and the `end` flag / percent at the clip end agree with the oracle env."""
+    import torch
+    from oracle import oracle as O
+    from uhc_b200.engine import Engine
+    ex, so = _expert(golden_dir, "sway")
+    keys = ("qpos", "qvel", "wbpos", "wbquat", "bquat", "bangvel", "ee_wpos", "com")
+    Tm = len(ex["qpos"])
+    cuts = [(0, 3), (5, 9), (20, Tm - 20)]                              # (first frame, length) of three clips cut from the golden motion
+    assert Tm - 20 > 55
+    clips = [{k: ex[k][a:a + n] for k in keys} for a, n in cuts]
+    E = 13
+    eng = Engine(E)
+    eng.load_clips(clips, [so] * len(clips))
+    clip = np.array([0, 1, 2] * 4 + [1], np.int32)
+    start = np.array([0, 2, 10, 1, 0, 30, 0, 4, 50, 0, 1, 0, 3], np.int32)
+    length = np.array([cuts[c][1] - s for c, s in zip(clip, start)], np.int32)
+    obs = eng.reset(clip=clip, start=start, length=length).cpu().numpy().copy()
+    om = O.Model()
+    envs = []
+    for e in range(E):
+        sl = {k: clips[clip[e]][k][start[e]:start[e] + length[e]] for k in keys}
+        oe = O.Env(om, sl, so)
+        assert np.abs(oe.reset() - obs[e]).max() < 1e-4, e
+        envs.append(oe)
+    rng = np.random.RandomState(11)
+    alive = np.ones(E, bool)
+    for t in range(8):
+        a = rng.normal(0, 0.05, (E, 105)).astype(np.float32)
+        o, r, ci, f, en, p = eng.step(torch.tensor(a, device="cuda"))
+        f, en, p = f.cpu().numpy(), en.cpu().numpy(), p.cpu().numpy()
+        for e in range(E):
+            if not alive[e]:
+                continue
+            _, ro, done, info = envs[e].step(a[e].astype(np.float64))
+            assert bool(f[e]) == info["fail"] and bool(en[e]) == info["end"], (t, e)
+            assert abs(p[e] - info["percent"]) < 1e-6
+            assert np.abs(eng.get_state(e)["qpos"] - envs[e].d.qpos).max() < 3e-3   # fp32 vs fp64 across contact switches mid-motion
+            if done:
+                alive[e] = False
+        if t == 3:                                                       # re-seed three envs in the middle of the others' episodes
+            ids = np.array([1, 6, 12], np.int32)
+            before = {e: eng.get_state(e)["qpos"].copy() for e in range(E) if e not in ids}
+            eng.reset(ids, clip=np.array([2, 2, 0], np.int32), start=np.array([0, 40, 0], np.int32))
+            for e, q in before.items():
+                assert np.array_equal(eng.get_state(e)["qpos"], q)
+            for e, (c, s) in zip(ids, ((2, 0), (2, 40), (0, 0))):
+                sl = {k: clips[c][k][s:] for k in keys}
+                envs[e] = O.Env(om, sl, so)
+                assert np.abs(envs[e].reset() - eng.obs[e].cpu().numpy()).max() < 1e-4
+                alive[e] = True
+    assert (~alive).sum() >= 3                                           # the 3-frame and 9-frame clips ended on the way
+    with pytest.raises(RuntimeError):                                    # a slice that leaves its clip is an argument error, not a silent read
+        eng.reset(np.array([0], np.int32), clip=np.array([1], np.int32), start=np.array([5], np.int32), length=np.array([9], np.int32))
+    eng.close()

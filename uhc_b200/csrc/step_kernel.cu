@@ -89,6 +89,7 @@ struct UhcEngine {
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_cinfo = nullptr, *d_pct = nullptr; int *d_fail = nullptr, *d_end = nullptr;
     int *d_ids = nullptr; int ids_cap = 0;
     int *d_order = nullptr;   // warp slot -> environment (work-sorted each step), null = identity
+    std::vector<int> clip_len_h;   // host copy of the clip lengths (argument validation)
 };
 
 template <class T> static int dev_copy(UhcEngine *e, T **dst, const T *src, size_t n) {
@@ -200,7 +201,7 @@ int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *
         for (int i = 0; i < nclips; i++) { acc += (float)(tmax > 0 ? clip_len[i] / tmax + 1 : 1); cdf[i] = acc; }
         CK(cudaMalloc((void **)&e->d_clip_cdf, nclips * sizeof(float)));
         CK(cudaMemcpy(e->d_clip_cdf, cdf.data(), nclips * sizeof(float), cudaMemcpyHostToDevice));
-        e->num_clips = nclips;
+        e->num_clips = nclips; e->clip_len_h.assign(clip_len, clip_len + nclips);
         e->evf.clip_cdf = e->d_clip_cdf; e->evd.clip_cdf = e->d_clip_cdf; e->evf.cfg.num_clips = nclips; e->evd.cfg.num_clips = nclips;
         if (e->d_clip_model) { cudaFree(e->d_clip_model); e->d_clip_model = nullptr; }
         e->evf.clip_model = nullptr; e->evd.clip_model = nullptr;
@@ -238,7 +239,12 @@ int uhc_env_reset(UhcEngine *e, int n, const int *env_ids_host, const int *clip_
     CK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (e->ids_cap < n) { if (e->d_ids) cudaFree(e->d_ids); CK(cudaMalloc((void **)&e->d_ids, (size_t)4 * n * sizeof(int))); e->ids_cap = n; }
-    for (int i = 0; i < n; i++) if (env_ids_host[i] < 0 || env_ids_host[i] >= e->E) { g_err = "uhc_env_reset: env id out of range"; return -2; }
+    for (int i = 0; i < n; i++) {
+        if (env_ids_host[i] < 0 || env_ids_host[i] >= e->E) { g_err = "uhc_env_reset: env id out of range"; return -2; }
+        const int c = clip_host[i];
+        if (c < 0 || c >= e->num_clips) { g_err = "uhc_env_reset: clip index out of range"; return -2; }
+        if (start_host[i] < 0 || len_host[i] < 1 || start_host[i] + len_host[i] > e->clip_len_h[c]) { g_err = "uhc_env_reset: (start, length) outside the clip"; return -2; }
+    }
     CK(cudaMemcpyAsync(e->d_ids, env_ids_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->d_ids + n, clip_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->d_ids + 2 * n, start_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
