@@ -11,7 +11,13 @@
 #include "../../include/uhc_nn.h"
 
 namespace {
-constexpr int BM = 128, BN = 128, BK = 64, UK = 16, STAGES = 3;   // 3 stages x 32 KB -> two CTAs per SM: one CTA's epilogue overlaps the other's MMAs
+#ifndef UHC_TC_BN
+#define UHC_TC_BN 128
+#endif
+#ifndef UHC_TC_STAGES
+#define UHC_TC_STAGES 3
+#endif
+constexpr int BM = 128, BN = UHC_TC_BN, BK = 64, UK = 16, STAGES = UHC_TC_STAGES;   // 3 stages x 32 KB -> two CTAs per SM: one CTA's epilogue overlaps the other's MMAs
 constexpr int STAGE_BYTES = (BM * BK + BN * BK) * 2;             // 32 KB
 constexpr int NTHREADS = 320;                                    // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue (two per TMEM lane quarter, half the columns each)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;    // + alignment slack + barriers
@@ -87,7 +93,7 @@ __device__ __forceinline__ void stage_store(float *stg, float *__restrict__ dst,
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, STAGES * STAGE_BYTES <= 100 * 1024 ? 2 : 1)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
             __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act, int ksplit) {
     extern __shared__ uint8_t smem_raw[];
@@ -342,11 +348,11 @@ EncodeFn get_encode() {
     }
     return fn;
 }
-int make_map(CUtensorMap *m, const void *base, int rows, int Kp) {  // row-major [rows][Kp] bf16, box 64 x 128, 128B swizzle
+int make_map(CUtensorMap *m, const void *base, int rows, int Kp, int box_rows = BM) {  // row-major [rows][Kp] bf16, box 64 x 128, 128B swizzle
     EncodeFn enc = get_encode();
     if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return -1; }
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM}, estr[2] = {1, 1};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows}, estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return -1; }
@@ -372,7 +378,7 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
         attr_set = true;
     }
     CUtensorMap ma, mb;
-    if (make_map(&ma, x_bf16, M, Kp) || make_map(&mb, W_bf16, N, Kp)) return -1;
+    if (make_map(&ma, x_bf16, M, Kp, BM) || make_map(&mb, W_bf16, N, Kp, BN)) return -1;
     // split the reduction when the output has too few tiles to fill the GPU (only legal for a plain fp32 accumulate output)
     const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM), nkb = Kp / BK;
     int ksplit = 1;
