@@ -1101,7 +1101,8 @@ enum { PH_PD = 0, PH_SMOOTH = 1, PH_NEWTON = 2 };
 // The warps of a CTA are re-aligned at points every warp passes exactly once per substep: they then run the same code at
 // the same time and share instruction-cache lines (the per-substep code is ~3x the 32 KB instruction cache).
 // Measured (E = 4096): whole-CTA alignment 1.25 M env-steps/s, groups of 4 / 3 / 2 warps 1.23 / 1.20 / 1.16 M, none 0.95 M;
-// every 2nd / 3rd substep only 1.06 / 1.00 M; aligning each Newton iteration too 1.06 M.
+// every 2nd / 3rd substep only 1.06 / 1.00 M; aligning each Newton iteration too 1.06 M.  Re-measured on the final kernel (1.57 M):
+// without the barrier before the Newton phase 1.53 M, without the one at the substep start 1.57 M (neutral), without both 1.52 M.
 #if !defined(UHC_EMU) && !defined(UHC_NO_CTA_SYNC)
 #define UHC_CTA_SYNC(on) do { if (on) __syncthreads(); } while (0)
 #else
