@@ -51,6 +51,42 @@ def test_forward_dynamics_many_contacts_fp64():
     assert np.abs(r["qacc"] - d.qacc).max() < 1e-6 * max(1.0, np.abs(d.qacc).max())
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_forward_dynamics_random_contact_states_fp64(seed):
+    """Seeded random poses from standing to crouching / leaning (0 .. ~30 contacts), random velocities, torques, applied root wrench and
+    warm start: the O(n) kernel pipeline (spatial RNE, centre-rooted block articulated-body solves, prefix-sum contact wrenches, Newton)
+    must land on the oracle's dense solution."""
+    om, d = O.Model(), O.Data()
+    e = Emu(64)
+    rng = np.random.default_rng(100 + seed)
+    ncons = []
+    for case in range(5):
+        q = om.qpos0.copy()
+        q[2] = rng.uniform(0.25, 0.95)
+        tilt = rng.normal(size=3) * rng.uniform(0.0, 0.6)
+        ang = np.linalg.norm(tilt) + 1e-12
+        dq = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * tilt / ang])
+        b = np.array([0.7071068, 0.7071068, 0.0, 0.0])
+        q[3:7] = [dq[0] * b[0] - dq[1:] @ b[1:], *(dq[0] * b[1:] + b[0] * dq[1:] + np.cross(dq[1:], b[1:]))]
+        q[3:7] /= np.linalg.norm(q[3:7])
+        q[7:] = rng.uniform(-0.6, 0.6, 69)
+        v = rng.normal(size=75) * rng.uniform(0.0, 1.5)
+        tau, fapp, aw = rng.normal(size=69) * 30, rng.normal(size=6) * 20, rng.normal(size=75) * 5
+        d.qpos[:], d.qvel[:], d.ctrl[:] = q, v, tau
+        d.qfrc_applied[:] = 0
+        d.qfrc_applied[:6] = fapp
+        d.qacc_warm[:] = aw
+        O.forward(om, d)
+        if d.ncon > 40:
+            continue
+        r = e.forward(q, v, tau, fapp, aw)
+        ncons.append(d.ncon)
+        assert r["ncon"] == d.ncon
+        assert np.abs(r["C"] - d.C).max() < 1e-8 * max(1.0, np.abs(d.C).max())
+        assert np.abs(r["qacc"] - d.qacc).max() < 2e-6 * max(1.0, np.abs(d.qacc).max()), (case, d.ncon, np.abs(r["qacc"] - d.qacc).max())
+    assert len(ncons) >= 3
+
+
 @pytest.mark.parametrize("prec,tol_q,tol_o", [(64, 1e-11, 1e-9), (32, 1e-4, 2e-3)])
 def test_env_trace_matches_reference_golden(golden_dir, prec, tol_q, tol_o):
     g = np.load(os.path.join(golden_dir, "env_sway_noise.npz"))
