@@ -69,3 +69,33 @@ def test_resting_contact_supports_weight_without_deep_penetration():
     assert abs(f - 9.81 * m.z["body_mass"].sum()) / (9.81 * 80.29) < 0.05
     assert d.con_dist[:d.ncon].min() > -0.02
     assert np.abs(d.qvel[:3]).max() < 0.05                     # undamped limp limbs may still jiggle; the root rests
+
+
+def test_contact_solution_is_consistent_with_its_forces():
+    """At the converged constraint solution the constraint force M (a - a_smooth) equals J^T f with f >= 0.  Without exposing J this is
+    checked on the root translation rows, where J^T f is the plain sum of the pyramid-edge forces f_e d_e over all contacts
+    (edges d = (0, mu, 1), (0, -mu, 1), (-mu, 0, 1), (mu, 0, 1) in the floor frame), and on the sign of every row force."""
+    m, d = O.Model(), O.Data()
+    mu = float(m.z["friction"])
+    rng = np.random.default_rng(42)
+    seen = 0
+    for case in range(12):
+        q = m.qpos0.copy()
+        q[2] = rng.uniform(0.3, 0.93)
+        q[3:7] = np.array([0.7071068, 0.7071068, 0, 0]) + rng.normal(size=4) * 0.1
+        q[3:7] /= np.linalg.norm(q[3:7])
+        q[7:] = rng.uniform(-0.5, 0.5, 69)
+        d.qpos[:], d.qvel[:], d.ctrl[:] = q, rng.normal(size=75) * 0.5, rng.normal(size=69) * 20
+        d.qfrc_applied[:] = 0
+        d.qacc_warm[:] = 0
+        O.forward(m, d)
+        if d.ncon == 0:
+            continue
+        seen += 1
+        f = d.efc_force[:4 * d.ncon].reshape(d.ncon, 4)
+        assert f.min() >= 0.0
+        total = np.array([mu * (f[:, 3] - f[:, 2]).sum(), mu * (f[:, 0] - f[:, 1]).sum(), f.sum()])
+        lhs = (d.M.reshape(75, 75) @ (d.qacc - d.qacc_smooth))[:3]
+        assert np.abs(lhs - total).max() < 1e-6 * max(1.0, np.abs(total).max()), (case, lhs, total)
+        assert total[2] > 0                                       # the floor only pushes
+    assert seen >= 5
