@@ -58,13 +58,36 @@ def _cpu_worker(args):
     return n, time.time() - t0
 
 
+def usable_cores():
+    """host threads this process may actually use: min(os.cpu_count, scheduler affinity, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read().split()[0])
+                    n = min(n, max(1, q // period))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def cpu_baseline(budget_s=12.0, cores=None):
     """The reference's per-env CPU path restated (oracle/uhc_oracle.c: PD + 15 substeps + obs + reward), one process per
     host core, bounded sample."""
     import multiprocessing as mp
     from oracle import oracle as O
     O.build()
-    cores = cores or os.cpu_count() or 1
+    cores = cores or usable_cores()
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, [(i + 1, budget_s) for i in range(cores)])
