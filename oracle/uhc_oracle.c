@@ -309,7 +309,7 @@ static int brk_cmp(const void *x, const void *y) { double a = ((const Brk *)x)->
    solved to machine precision by exact Newton with an exact (sorted-breakpoint) line search. */
 static void or_constraint_solve(const OrModel *m, OrData *d) {
     static double J[MAXROW][NV], Jv[3][NV], Jw[3][NV], H[NV*NV];
-    double aref[MAXROW], D[MAXROW], r[MAXROW], jp[MAXROW];
+    double aref[MAXROW], D[MAXROW], r[MAXROW];
     int nrow = 0;
     const double t1[3] = {0, 1, 0}, t2[3] = {-1, 0, 0}; /* contact frame of normal (0,0,1) */
     const double mu = m->mu, dmin = m->solimp[0], dmax = m->solimp[1], width = m->solimp[2], mid = m->solimp[3], power = m->solimp[4];
@@ -364,7 +364,7 @@ static void or_constraint_solve(const OrModel *m, OrData *d) {
         for (int i = 0; i < NV; i++) { double s = 0; for (int j = 0; j < NV; j++) s += d->M[i*NV+j]*p[j]; A += Ma[i]*p[i]; B += s*p[i]; }
         Brk brk[MAXROW]; int nb = 0;
         for (int k = 0; k < nrow; k++) {
-            double s = 0; for (int i = 0; i < NV; i++) s += J[k][i]*p[i]; jp[k] = s;
+            double s = 0; for (int i = 0; i < NV; i++) s += J[k][i]*p[i];
             if (r[k] < 0) { A += D[k]*r[k]*s; B += D[k]*s*s; }
             if (s != 0) { double al = -r[k]/s; if (al > 0) { int act = r[k] < 0; brk[nb].a = al; brk[nb].dA = (act ? -1 : 1)*D[k]*r[k]*s; brk[nb].dB = (act ? -1 : 1)*D[k]*s*s; nb++; } }
         }
