@@ -31,8 +31,16 @@ __device__ __forceinline__ void stage_tables(EngineView<Real> &ev, unsigned char
     ev.model.dof_f = s_dof; ev.model.lvl_pack = s_lvl; ev.model.topo_s = s_topo;
 }
 
+#ifndef UHC_MIN_CTAS
+#define UHC_MIN_CTAS 2
+#endif
+#ifdef UHC_MAXNREG     /* experiment knob: cap registers without changing the CTA shape */
+#define UHC_STEP_BOUNDS(EPB, Real) __maxnreg__(UHC_MAXNREG)
+#else
+#define UHC_STEP_BOUNDS(EPB, Real) __launch_bounds__(32 * EPB, (sizeof(Real) == 4 && EPB <= 7 ? UHC_MIN_CTAS : 1))
+#endif
 template <class Real, int EPB>
-__global__ void __launch_bounds__(32 * EPB, (sizeof(Real) == 4 && EPB <= 7 ? 2 : 1))
+__global__ void UHC_STEP_BOUNDS(EPB, Real)
 k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict__ obs, float *__restrict__ rew, float *__restrict__ cinfo,
            int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque, const int *__restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem[];

@@ -11,7 +11,7 @@ import numpy as np
 from .model import HumanoidModel, UhcModelHost
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libuhc_b200.so")
+_SO = os.environ.get("UHC_B200_SO") or os.path.join(_HERE, "libuhc_b200.so")   # override: scratch builds of kernel variants
 OBS_DIM, ACT_DIM, NQ, NV, NU, EX_SIZE = 657, 105, 76, 75, 69, 508
 EXPERT_FIELDS = (("qpos", 76), ("qvel", 75), ("wbpos", 72), ("wbquat", 96), ("bquat", 96), ("bangvel", 72), ("ee_wpos", 15), ("com", 3))
 
