@@ -70,6 +70,13 @@ int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *
  * its beta/gender (humanoid_im.py:154-180).  Call after uhc_load_clips; default = variant 0 for every clip. */
 int uhc_set_clip_models(UhcEngine *e, int nclips, const int *clip_model);
 
+/* Clip sampling weights of the in-kernel re-seeding.  Default (weights_host == NULL, and after every uhc_load_clips) = the
+ * sample_keys rule used when no success history exists (len // t_max + 1 copies per clip, dataset_amass_single.py:138-142,180-182).
+ * The training loop of the reference passes its per-clip success history instead (agent_copycat.py:511-517): with probability
+ * sampling_freq the clip is drawn from exp(-ewma(success)/temp), else uniformly (dataset_amass_single.py:183-186, math_utils.py:25-29);
+ * the caller folds both into one weight per clip: w = sampling_freq * p_fail + (1 - sampling_freq) / C. */
+int uhc_set_clip_weights(UhcEngine *e, int nclips, const float *weights_host);
+
 /* env.reset() for n envs (mujoco_env.py:95-104 + humanoid_im.py:1245-1299).  clip/start/len select the expert slice
  * (dataset_amass_single.py:200-253); q/v override (may be NULL) = [n][76]/[n][75] floats on the device.
  * obs_dev = [num_envs][657] (rows of the listed envs are written). */
@@ -89,6 +96,14 @@ int uhc_env_step_host(UhcEngine *e, const float *actions_host, float *obs_host, 
 /* parity hooks / fail_safe (humanoid_im.py:902-905): read or overwrite the simulator state of one env (host doubles). */
 int uhc_env_get_state(UhcEngine *e, int env, double *qpos76, double *qvel75, double *xpos72, double *bquat96, int *istate8);
 int uhc_env_set_state(UhcEngine *e, int env, const double *qpos76, const double *qvel75);
+/* the same for n envs with one launch and one copy: out_host = [n][319] doubles (qpos76 qvel75 xpos72 bquat96), istate_host = [n][8]
+ * (cur_t, clip, start, len, episode, flags (bit 0: contact overflow), newton iterations, max contacts); set: qpos [n][76], qvel [n][75]. */
+int uhc_env_get_state_batch(UhcEngine *e, int n, const int *env_ids_host, double *out_host, int *istate_host);
+int uhc_env_set_state_batch(UhcEngine *e, int n, const int *env_ids_host, const double *qpos_host, const double *qvel_host);
+/* device counters: out4[0] = env-steps FAILED because a body's floor contacts did not fit the per-env contact capacity (40; MuJoCo's
+ * generated models allocate nconmax 500, skeleton_mesh.py:46 -- such a step sets fail instead of continuing on a truncated contact
+ * set), out4[1] = env-steps skipped because the env record was stale (clip table reloaded) or never reset (outputs: fail = end = 1). */
+int uhc_engine_counters(UhcEngine *e, int *out4);
 int uhc_num_envs(const UhcEngine *e);
 int uhc_kernel_launches(const UhcEngine *e);   /* kernels launched by this engine so far (bench `gpu_launches`) */
 

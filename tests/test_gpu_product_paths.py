@@ -1,0 +1,318 @@
+"""GPU parity of the paths the PRODUCT runs by default: in-kernel re-seeding of finished episodes
+(auto_reset), the device clip sampler against DatasetAMASSSingle.sample_seq statistics, a 4096-env launch sampled against the
+oracle, contact-capacity overflow, stale env records after a clip-table reload, and ppo_update(use_tc=True) against a khrylib
+golden at the production network sizes."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+KEYS = ("qpos", "qvel", "wbpos", "wbquat", "bquat", "bangvel", "ee_wpos", "com")
+
+
+def _expert(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, f"expert_{tag}.npz"))
+    ex = {k: z[k] for k in z.files}
+    return ex, np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+
+
+def _slice(ex, a, n):
+    return {k: ex[k][a:a + n] for k in KEYS}
+
+
+def test_auto_reset_matches_oracle_reset_and_following_steps(golden_dir):
+    """auto_reset = 1 (what bench.py and BatchedAgent run): every env that fails or reaches its clip end is re-seeded INSIDE the step
+    kernel.  After each in-kernel reset the (clip, start, len) the device sampler drew is read back; the observation returned by that
+    step must be the oracle's reset observation on exactly that slice, the slice must obey the reference's rule
+    (start in [0, L - t_min), len = min(t_max, L - start), dataset_amass_single.py:234-238), and the episode that follows must track
+    the oracle env step by step."""
+    import torch
+    from oracle import oracle as O
+    from uhc_b200.engine import Engine
+    sway, so = _expert(golden_dir, "sway")
+    kick, sk = _expert(golden_dir, "kick")
+    cuts = [(sway, 0, 30), (sway, 30, 17), (sway, 50, 40), (kick, 0, 24), (kick, 20, 50), (kick, 5, 9)]
+    clips = [_slice(e, a, n) for e, a, n in cuts]
+    shapes = [so, so, so, sk, sk, sk]
+    t_min, t_max, E, T = 4, 12, 256, 40
+    eng = Engine(E, auto_reset=1, t_min=t_min, t_max=t_max, reset_seed=77)
+    eng.load_clips(clips, shapes)
+    rng = np.random.RandomState(5)
+    clip0 = rng.randint(0, len(clips), E).astype(np.int32)
+    eng.reset(np.arange(E, dtype=np.int32), clip0, 0, np.minimum(eng.clip_len[clip0], t_max).astype(np.int32))
+    om = O.Model()
+    tracked = {}                                # env -> oracle env of its CURRENT episode (only episodes that began with an in-kernel reset)
+    prev_ep = eng.get_states()["episode"].copy()
+    n_reset_checked = n_steps_checked = 0
+    worst_reset = worst_q = 0.0
+    for t in range(T):
+        a = rng.normal(0, 0.25 if t % 7 else 0.8, (E, 105)).astype(np.float32)     # occasional violent actions: failures as well as clip ends
+        a[:, 69:75] *= 0.3
+        obs, rew, ci, fail, end, pct = eng.step(torch.tensor(a, device="cuda"))
+        obs, fail, end, rew = obs.cpu().numpy(), fail.cpu().numpy(), end.cpu().numpy(), rew.cpu().numpy()
+        st = eng.get_states()
+        for e, oe in list(tracked.items()):     # episodes under comparison: the step just taken
+            _, ro, done, info = oe.step(a[e].astype(np.float64))
+            assert bool(fail[e]) == info["fail"] and bool(end[e]) == info["end"], (t, e)
+            assert abs(ro - rew[e]) < 2e-3, (t, e, ro, rew[e])
+            if done:
+                del tracked[e]                  # its in-kernel re-seeding is checked below like any other
+            else:
+                worst_q = max(worst_q, np.abs(st["qpos"][e] - oe.d.qpos).max())
+                n_steps_checked += 1
+        done = (fail | end) != 0
+        assert (st["episode"] == prev_ep + done).all()                              # exactly the finished episodes were re-seeded
+        for e in np.nonzero(done)[0]:
+            c, s, ln = int(st["clip"][e]), int(st["start"][e]), int(st["len"][e])
+            L = int(eng.clip_len[c])
+            assert 0 <= s < max(L - t_min, 1) and ln == min(t_max, L - s) and st["cur_t"][e] == 0, (e, c, s, ln, L)
+            if len(tracked) < 48 or e in tracked:
+                oe = O.Env(om, {k: clips[c][k][s:s + ln] for k in KEYS}, shapes[c])
+                o0 = oe.reset()
+                worst_reset = max(worst_reset, np.abs(o0 - obs[e]).max())
+                assert np.abs(st["qpos"][e] - oe.d.qpos).max() < 1e-5
+                tracked[e] = oe
+                n_reset_checked += 1
+        prev_ep = st["episode"].copy()
+    assert n_reset_checked >= 60 and n_steps_checked >= 150, (n_reset_checked, n_steps_checked)
+    assert worst_reset < 1e-4 and worst_q < 1e-3, (worst_reset, worst_q)
+    assert eng.counters["invalid_env_steps"] == 0
+    eng.close()
+
+
+def test_device_clip_sampler_matches_reference_sampler_statistics(golden_dir):
+    """>= 10 000 in-kernel re-seedings against DatasetAMASSSingle.sample_seq on the same clip lengths (golden: 40 000 draws of the
+    unmodified reference, tools/make_golden.py gen_sampler): clip histogram by chi-square, start ~ U[0, L - t_min) by mean / range.
+    (a) no success history = sample_keys rule; (b) the training loop's failure-weighted mixture through uhc_set_clip_weights."""
+    import torch
+    from uhc_b200 import motion_lib
+    from uhc_b200.agent import failure_weights
+    from uhc_b200.engine import Engine
+    g = np.load(os.path.join(golden_dir, "sampler_hist.npz"))
+    lens, t_min, t_max = g["lens"], int(g["t_min"]), int(g["t_max"])
+    rng = np.random.default_rng(1)
+    clips = [motion_lib.synthetic_clip(int(L), rng) for L in lens]
+    E = 4096
+    for tag in ("a", "b"):
+        # env_episode_len = 1: every episode ends after one step, so every step re-seeds every env
+        eng = Engine(E, auto_reset=1, t_min=t_min, t_max=t_max, reset_seed=1234 + ord(tag), env_episode_len=1)
+        eng.load_clips(clips, None)
+        if tag == "b":
+            succ = g["freq_succ"]
+            eng.set_clip_weights(failure_weights([list(map(float, r)) for r in succ], sampling_temp=0.2, sampling_freq=0.5))
+        eng.reset(np.arange(E, dtype=np.int32), np.zeros(E, np.int32), 0, np.full(E, t_max, np.int32))
+        a = torch.zeros(E, 105, device="cuda")
+        hist = np.zeros(len(lens)); ssum = np.zeros(len(lens)); smax = np.zeros(len(lens), np.int64); n = 0
+        for t in range(4):
+            _, _, _, fail, end, _ = eng.step(a)
+            assert ((fail | end) != 0).all()
+            st = eng.get_states()
+            hist += np.bincount(st["clip"], minlength=len(lens))
+            for c in range(len(lens)):
+                sel = st["clip"] == c
+                ssum[c] += st["start"][sel].sum(); smax[c] = max(smax[c], st["start"][sel].max(initial=0))
+            assert (st["len"] == np.minimum(t_max, lens[st["clip"]] - st["start"])).all()
+            n += E
+        assert n >= 10000
+        ref = g[f"{tag}.clip_hist"].astype(np.float64)
+        p = ref / ref.sum()
+        # two-sample chi-square (reference draws are a sample too): sum (k1 o - k2 r)^2 / (o + r), 9 dof, 99.9 % quantile = 27.9
+        k1, k2 = np.sqrt(ref.sum() / n), np.sqrt(n / ref.sum())
+        chi2 = (((k1 * hist - k2 * ref) ** 2) / (hist + ref)).sum()
+        assert chi2 < 27.9, (tag, chi2, hist / n, p)
+        span = np.maximum(lens - t_min, 1)
+        mean_start = ssum / np.maximum(hist, 1)
+        assert (smax < span).all() and (smax >= span - 1 - np.ceil(12 * span / np.maximum(hist, 1))).all(), (smax, span)
+        # uniform on {0..span-1}: mean (span-1)/2, sd of the mean = span / sqrt(12 n_c)
+        z = (mean_start - (span - 1) / 2) / (span / np.sqrt(12 * np.maximum(hist, 1)))
+        assert np.abs(z).max() < 4.5, z
+        assert np.abs(g[f"{tag}.start_mean"] - (span - 1) / 2).max() < 0.05 * span.max()        # the reference draws follow the same law
+        eng.close()
+
+
+def test_4096_env_launch_sampled_against_oracle(golden_dir):
+    """The production launch shape (4096 envs = 586 CTAs, two residency rounds per SM): 64 envs spread over the grid are compared
+    with the oracle env for 10 steps; every env gets its own start frame and seeded action stream."""
+    import torch
+    from oracle import oracle as O
+    from uhc_b200.engine import Engine
+    ex, so = _expert(golden_dir, "sway")
+    E, T = 4096, 10
+    rng = np.random.RandomState(21)
+    starts = rng.randint(0, 70, E).astype(np.int32)
+    eng = Engine(E)
+    eng.load_clips([ex], [so])
+    obs = eng.reset(start=starts).cpu().numpy().copy()
+    ids = np.unique(np.concatenate([rng.choice(E, 60, replace=False), [0, 6, 7, E - 1]])).astype(np.int32)   # CTA edges included
+    om = O.Model()
+    envs = []
+    for e in ids:
+        oe = O.Env(om, {k: ex[k][starts[e]:] for k in KEYS}, so)
+        assert np.abs(oe.reset() - obs[e]).max() < 1e-4
+        envs.append(oe)
+    worst_q = worst_o = worst_r = 0.0
+    alive = np.ones(len(ids), bool)
+    for t in range(T):
+        a = rng.normal(0, 0.1, (E, 105)).astype(np.float32)
+        a[:, 69:75] *= 0.3
+        o, r, ci, f, en, p = eng.step(torch.tensor(a, device="cuda"))
+        o, r, f, en = o.cpu().numpy(), r.cpu().numpy(), f.cpu().numpy(), en.cpu().numpy()
+        assert np.isfinite(o).all() and np.isfinite(r).all()
+        st = eng.get_states(ids)
+        for i, e in enumerate(ids):
+            if not alive[i]:
+                continue
+            oo, ro, done, info = envs[i].step(a[e].astype(np.float64))
+            assert bool(f[e]) == info["fail"] and bool(en[e]) == info["end"]
+            worst_q = max(worst_q, np.abs(st["qpos"][i] - envs[i].d.qpos).max())
+            worst_r = max(worst_r, abs(ro - r[e]))
+            if not done:
+                worst_o = max(worst_o, np.abs(oo - o[e]).max())
+            alive[i] = not done
+    assert worst_q < 1e-3 and worst_r < 1e-3 and worst_o < 5e-3, (worst_q, worst_r, worst_o)
+    assert alive.sum() >= 48
+    eng.close()
+
+
+def test_contact_capacity_overflow_is_flagged_not_truncated():
+    """A humanoid lying flat on the floor touches it with more hull vertices than the per-env contact capacity (40; the oracle
+    holds 96, MuJoCo's generated models 500).  The kernel must not continue on a silently truncated contact set: the step reports
+    fail, sets flag bit 0 of the env record and counts the event; an env below the capacity in the same batch is unaffected."""
+    import torch
+    from oracle import oracle as O
+    from uhc_b200 import motion_lib
+    from uhc_b200.engine import Engine
+    ex = motion_lib.synthetic_clip(20, np.random.default_rng(5), kind="sitting")
+    q = ex["qpos"][0].copy()
+    q[7:] = 0
+    lying = q.copy()
+    lying[2] = 0.08
+    lying[3:7] = [1, 0, 0, 0]                              # identity root rotation: the Y-up SMPL rest pose lies flat in the Z-up world
+    oe = O.Env(O.Model(), ex, np.zeros(17), body_diff_thresh=100.0)
+    oe.reset(lying, np.zeros(75))
+    assert oe.d.ncon > 60, oe.d.ncon                        # the case really exceeds the kernel's capacity (87 contacts at this pose)
+    eng = Engine(3, body_diff_thresh=100.0)
+    eng.load_clips([ex], None)
+    qs = np.stack([lying, ex["qpos"][0], lying])
+    eng.reset(qpos=qs, qvel=np.zeros((3, 75)))
+    c0 = eng.counters["contact_overflow_steps"]
+    _, _, _, fail, end, _ = eng.step(torch.zeros(3, 105, device="cuda"))
+    fail = fail.cpu().numpy()
+    st = eng.get_states()
+    assert fail[0] == 1 and fail[2] == 1 and fail[1] == 0
+    assert (st["flags"] & 1).tolist() == [1, 0, 1]
+    assert eng.counters["contact_overflow_steps"] == c0 + 2
+    oe1 = O.Env(O.Model(), ex, np.zeros(17), body_diff_thresh=100.0)
+    oe1.reset(ex["qpos"][0], np.zeros(75))
+    oe1.step(np.zeros(105))
+    assert np.abs(st["qpos"][1] - oe1.d.qpos).max() < 1e-4
+    eng.close()
+
+
+def test_stale_env_records_after_clip_table_reload_are_skipped(golden_dir):
+    """eval_policy loads a SMALLER clip table and resets only some envs; the others keep clip indices of the old
+    table.  uhc_load_clips invalidates every record and the step kernel skips invalid ones (fail = end = 1, zero obs, counted)
+    instead of reading frames past the new table."""
+    import torch
+    from uhc_b200.engine import Engine
+    sway, so = _expert(golden_dir, "sway")
+    kick, sk = _expert(golden_dir, "kick")
+    many = [_slice(sway, 5 * i, 30) for i in range(10)] + [_slice(kick, 3 * i, 30) for i in range(10)]
+    E = 23                                                # three full CTAs + a partial one
+    eng = Engine(E)
+    eng.load_clips(many, [so] * 10 + [sk] * 10)
+    eng.reset(np.arange(E, dtype=np.int32), (np.arange(E) % 20).astype(np.int32), 0, None)
+    a = torch.zeros(E, 105, device="cuda")
+    _, _, _, fail, end, _ = eng.step(a)
+    assert eng.counters["invalid_env_steps"] == 0
+    eng.load_clips([_slice(kick, 0, 12)], [sk])           # one short clip: every old record is stale now
+    ids = np.array([0, 3, 8, 15, 22], np.int32)
+    obs = eng.reset(ids, np.zeros(5, np.int32), 0, None).cpu().numpy().copy()
+    for k in range(3):
+        o, r, ci, fail, end, pct = eng.step(a)
+        o, fail, end, r = o.cpu().numpy(), fail.cpu().numpy(), end.cpu().numpy(), r.cpu().numpy()
+        stale = np.setdiff1d(np.arange(E), ids)
+        assert (fail[stale] == 1).all() and (end[stale] == 1).all() and (o[stale] == 0).all() and (r[stale] == 0).all()
+        assert (fail[ids] == 0).all() and np.isfinite(o[ids]).all() and (np.abs(o[ids]).sum(1) > 0).all()
+        assert (o[0] == o[15]).all()                       # same slice, same actions: bit-identical next to skipped warps
+    assert eng.counters["invalid_env_steps"] == 3 * (E - len(ids))
+    st = eng.get_states(ids)
+    assert (st["cur_t"] == 3).all()
+    eng.close()
+
+
+def _ppo_real_inputs(N=8192, S=657, A=105, hs=(2048, 1024, 512), seed=11):
+    """bit-identical copy of tools/make_golden.py ppo_real_inputs (numpy / torch CPU generators only)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    dims = [S] + list(hs)
+
+    def net(out_dim):
+        Ws, bs = [], []
+        d = dims + [out_dim]
+        for i in range(len(d) - 1):
+            k = 1.0 / np.sqrt(d[i])
+            W = (torch.rand(d[i + 1], d[i], generator=g, dtype=torch.float64) * 2 - 1) * k
+            b = (torch.rand(d[i + 1], generator=g, dtype=torch.float64) * 2 - 1) * k
+            if i == len(d) - 2:
+                W, b = W * 0.1, b * 0.0
+            Ws.append(W.float()); bs.append(b.float())
+        return Ws, bs
+    pol, val = net(A), net(1)
+    rng = np.random.RandomState(seed)
+    states = rng.normal(0, 1, (N, S)).clip(-5, 5).astype(np.float32)
+    actions = rng.normal(0, 0.15, (N, A)).astype(np.float32)
+    returns = rng.uniform(0, 8, N).astype(np.float32)
+    adv = rng.normal(0, 1, N)
+    adv = ((adv - adv.mean()) / adv.std()).astype(np.float32)
+    exps = (rng.uniform(0, 1, N) > 0.1).astype(np.float32)
+    probe = rng.normal(0, 1, (256, S)).clip(-5, 5).astype(np.float32)
+    return pol, val, states, actions, returns, adv, exps, probe
+
+
+@pytest.mark.parametrize("use_tc", [True, False])
+def test_ppo_update_at_production_sizes_matches_khrylib(golden_dir, use_tc):
+    """ppo_update (use_tc=True is what BatchedAgent.update_params runs) against AgentPPO.update_policy of the unmodified reference in
+    fp64 (tools/make_golden.py gen_ppo_real): nets 657-2048-1024-512-{105,1}, N = 8192 rows, 3 epochs (value step, then clipped
+    surrogate step with the first-step grad-norm clip), Adam.  Compared: the change of the policy mean / value on a 256-row probe batch
+    and 4096 sampled entries of every parameter tensor.
+    Tolerances: Adam's first steps are ~lr * sign(g), so entries whose gradient is near zero may legitimately differ by a whole step;
+    the bound is therefore on the MEAN deviation relative to the mean update size: 2 % for the fp32 SIMT path, 10 % for the tensor-core
+    path (bf16 operands, fp32 accumulate), and on the probe outputs 2 % / 8 % of the mean output change."""
+    import torch
+    from uhc_b200 import nn
+    g = np.load(os.path.join(golden_dir, "ppo_real.npz"))
+    (pW, pb), (vW, vb), states, actions, returns, adv, exps, probe = _ppo_real_inputs()
+    dev = "cuda"
+    pol = nn.MLPNet(657, (2048, 1024, 512), 105, "gelu", device=dev, head_name="action_mean", seed=1)
+    val = nn.MLPNet(657, (2048, 1024, 512), 1, "gelu", device=dev, head_name="value_head", seed=2)
+    for net, Ws, bs in ((pol, pW, pb), (val, vW, vb)):
+        for i in range(4):
+            net.W[i].copy_(Ws[i]); net.b[i].copy_(bs[i])
+        net.invalidate_bf16()
+    pr = torch.tensor(probe, device=dev)
+    mean0, v0 = pol.forward(pr).cpu().numpy().astype(np.float64), val.forward(pr).cpu().numpy().astype(np.float64)
+    assert np.abs(mean0 - g["mean0"]).max() < 2e-5 and np.abs(v0 - g["v0"]).max() < 2e-5          # same initial nets as the golden
+    log_std = torch.full((105,), -2.3, device=dev)
+    opt_p, opt_v = nn.Adam(pol.params(), 5e-5), nn.Adam(val.params(), 3e-4)
+    t = lambda x: torch.tensor(x, device=dev)
+    nn.ppo_update(pol, val, log_std, opt_p, opt_v, t(states), t(actions), t(returns), t(adv), t(exps), 0.2, 3, 40.0, use_tc=use_tc)
+    mean1, v1 = pol.forward(pr).cpu().numpy().astype(np.float64), val.forward(pr).cpu().numpy().astype(np.float64)
+    tol_out, tol_par = (0.08, 0.10) if use_tc else (0.02, 0.02)
+    for name, ours, ref0, ref1 in (("mean", mean1 - mean0, g["mean0"], g["mean1"]), ("value", v1 - v0, g["v0"], g["v1"])):
+        dref = ref1 - ref0
+        rel = np.abs(ours - dref).mean() / np.abs(dref).mean()
+        assert rel < tol_out, (name, use_tc, rel)
+    for tag, net in (("p", pol), ("v", val)):
+        for i in range(4):
+            W1 = net.W[i].detach().cpu().numpy().reshape(-1).astype(np.float64)
+            idx = g[f"{tag}.W{i}.idx"]
+            dours, dref = W1[idx] - g[f"{tag}.W{i}.old"], g[f"{tag}.W{i}.new"] - g[f"{tag}.W{i}.old"]
+            rel = np.abs(dours - dref).mean() / np.abs(dref).mean()
+            assert rel < tol_par, (tag, "W", i, use_tc, rel)
+            b1 = net.b[i].detach().cpu().numpy().astype(np.float64)
+            dours, dref = b1 - g[f"{tag}.b{i}.old"], g[f"{tag}.b{i}.new"] - g[f"{tag}.b{i}.old"]
+            if np.abs(dref).mean() > 0:
+                rel = np.abs(dours - dref).mean() / np.abs(dref).mean()
+                assert rel < max(tol_par, 0.05) * (2 if i == 3 else 1), (tag, "b", i, use_tc, rel)

@@ -126,6 +126,123 @@ def gen_ppo():
     print("ppo_small: N", N, "adv mean/std", adv.mean().item(), adv.std().item())
 
 
+def ppo_real_inputs(N=8192, S=657, A=105, hs=(2048, 1024, 512), seed=11):
+    """Seeded inputs of the real-size PPO parity case, regenerated identically by tests/test_gpu_product_paths.py (numpy and torch CPU
+    generators only): initial weights (nn.Linear rule, head x0.1 / bias 0), states, actions, returns, advantages, exps."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    dims = [S] + list(hs)
+
+    def net(out_dim):
+        Ws, bs = [], []
+        d = dims + [out_dim]
+        for i in range(len(d) - 1):
+            k = 1.0 / np.sqrt(d[i])
+            W = (torch.rand(d[i + 1], d[i], generator=g, dtype=torch.float64) * 2 - 1) * k
+            b = (torch.rand(d[i + 1], generator=g, dtype=torch.float64) * 2 - 1) * k
+            if i == len(d) - 2:
+                W, b = W * 0.1, b * 0.0
+            Ws.append(W.float().double()); bs.append(b.float().double())      # exactly representable in fp32
+        return Ws, bs
+    pol, val = net(A), net(1)
+    rng = np.random.RandomState(seed)
+    states = rng.normal(0, 1, (N, S)).clip(-5, 5).astype(np.float32).astype(np.float64)
+    actions = rng.normal(0, 0.15, (N, A)).astype(np.float32).astype(np.float64)
+    returns = rng.uniform(0, 8, N).astype(np.float32).astype(np.float64)
+    adv = rng.normal(0, 1, N)
+    adv = ((adv - adv.mean()) / adv.std()).astype(np.float32).astype(np.float64)
+    exps = (rng.uniform(0, 1, N) > 0.1).astype(np.float64)
+    probe = rng.normal(0, 1, (256, S)).clip(-5, 5).astype(np.float32).astype(np.float64)
+    return pol, val, states, actions, returns, adv, exps, probe
+
+
+def gen_ppo_real():
+    """AgentPPO.update_policy (agent_ppo.py:16-51) at the production sizes 657-2048-1024-512-{105,1}, N = 8192, 3 epochs, fp64 on the CPU.
+    The inputs are seeded (ppo_real_inputs); the golden keeps the policy / value outputs on a 256-row probe batch before and after the
+    update and 4096 sampled entries of every parameter tensor after the update."""
+    import torch
+    from uhc.khrylib.models.mlp import MLP
+    from uhc.khrylib.rl.core.policy_gaussian import PolicyGaussian
+    from uhc.khrylib.rl.core.critic import Value
+    from uhc.khrylib.rl.agents.agent_ppo import AgentPPO
+    torch.set_default_dtype(torch.float64)
+    torch.set_num_threads(os.cpu_count() or 1)
+    (pW, pb), (vW, vb), states, actions, returns, adv, exps, probe = ppo_real_inputs()
+    hs = [2048, 1024, 512]
+
+    class Cfg:
+        policy_hsize, policy_htype, fix_std, log_std = hs, "gelu", True, -2.3
+
+    pol = PolicyGaussian(Cfg(), action_dim=105, state_dim=657)
+    val = Value(MLP(657, hs, "gelu"))
+
+    def load(net, Ws, bs, head):
+        sd = net.state_dict()
+        for i in range(3):
+            sd[f"net.affine_layers.{i}.weight"] = Ws[i]; sd[f"net.affine_layers.{i}.bias"] = bs[i]
+        sd[f"{head}.weight"], sd[f"{head}.bias"] = Ws[3], bs[3]
+        net.load_state_dict(sd)
+    load(pol, pW, pb, "action_mean"); load(val, vW, vb, "value_head")
+    st, pr = torch.tensor(states), torch.tensor(probe)
+    with torch.no_grad():
+        mean0, v0 = pol.forward(pr).loc.numpy().copy(), val(pr).numpy().copy()
+    agent = AgentPPO.__new__(AgentPPO)
+    agent.policy_net, agent.value_net = pol, val
+    agent.optimizer_policy = torch.optim.Adam(pol.parameters(), lr=5e-5)
+    agent.optimizer_value = torch.optim.Adam(val.parameters(), lr=3e-4)
+    agent.clip_epsilon, agent.opt_num_epochs, agent.use_mini_batch = 0.2, 3, False
+    agent.policy_grad_clip = [(pol.parameters(), 40)]
+    agent.update_modules = [pol, val]
+    agent.value_opt_niter = 1
+    agent.update_policy(st, torch.tensor(actions), torch.tensor(returns)[:, None], torch.tensor(adv)[:, None], torch.tensor(exps))
+    with torch.no_grad():
+        mean1, v1 = pol.forward(pr).loc.numpy().copy(), val(pr).numpy().copy()
+    out = dict(N=8192, epochs=3, seed=11, mean0=mean0, v0=v0, mean1=mean1, v1=v1)
+    rs = np.random.RandomState(5)
+    for tag, net, W0, b0, head in (("p", pol, pW, pb, "action_mean"), ("v", val, vW, vb, "value_head")):
+        sd = net.state_dict()
+        for i in range(4):
+            kw = f"net.affine_layers.{i}.weight" if i < 3 else f"{head}.weight"
+            kb = f"net.affine_layers.{i}.bias" if i < 3 else f"{head}.bias"
+            W1, b1 = sd[kw].numpy().reshape(-1), sd[kb].numpy().reshape(-1)
+            idx = rs.randint(0, W1.size, 4096)
+            out[f"{tag}.W{i}.idx"], out[f"{tag}.W{i}.new"], out[f"{tag}.W{i}.old"] = idx, W1[idx], W0[i].numpy().reshape(-1)[idx]
+            out[f"{tag}.b{i}.new"], out[f"{tag}.b{i}.old"] = b1, b0[i].numpy()
+    np.savez_compressed(os.path.join(OUT, "ppo_real.npz"), **out)
+    print("ppo_real: |dmean| %.3e |dv| %.3e" % (np.abs(mean1 - mean0).mean(), np.abs(v1 - v0).mean()))
+
+
+def gen_sampler(cfg):
+    """DatasetAMASSSingle.sample_seq (dataset_amass_single.py:172-253) draw statistics on take5_test_small: (a) no success history
+    (sample_keys rule), (b) the training loop's call with a success history (failure-weighted mixture)."""
+    import random
+    from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
+    out = {}
+    for tag, t_min, t_max in (("a", 15, 60), ("b", 15, 60)):
+        cfg.data_specs["t_min"], cfg.data_specs["t_max"] = t_min, t_max
+        dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
+        keys = list(dl.data_keys)
+        lens = np.array([dl.data["pose_aa"][k].shape[0] for k in keys])
+        np.random.seed(3); random.seed(3)
+        freq = None
+        if tag == "b":   # synthetic per-clip success histories [success, fr_start] as agent_copycat.py:561 records them
+            rs = np.random.RandomState(9)
+            freq = {k: [[float(rs.uniform() < p), 0] for _ in range(30)] for k, p in zip(keys, np.linspace(0.1, 0.95, len(keys)))}
+            out["freq_succ"] = np.array([[r[0] for r in freq[k]] for k in keys])
+        n = 40000
+        clip, start, length = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        for i in range(n):
+            s = dl.sample_seq(freq_dict=freq, full_sample=False, sampling_temp=0.2, sampling_freq=0.5)
+            clip[i], start[i], length[i] = keys.index(dl.curr_key), dl.fr_start, dl.fr_end - dl.fr_start
+        out[f"{tag}.clip_hist"] = np.bincount(clip, minlength=len(keys))
+        out[f"{tag}.start_mean"] = np.array([start[clip == c].mean() for c in range(len(keys))])
+        out[f"{tag}.start_max"] = np.array([start[clip == c].max() for c in range(len(keys))])
+        out[f"{tag}.len_ok"] = np.array(all(length[i] == min(t_max, lens[clip[i]] - start[i]) for i in range(n)))
+        out["lens"], out["t_min"], out["t_max"], out["n"] = lens, t_min, t_max, n
+        print("sampler", tag, out[f"{tag}.clip_hist"], out[f"{tag}.len_ok"])
+    np.savez_compressed(os.path.join(OUT, "sampler_hist.npz"), **out)
+
+
 def gen_math():
     from uhc.utils import transformation as T
     from uhc.utils import math_utils as MU
@@ -167,6 +284,10 @@ def main():
         gen_env(cfg, dl, "0-BioMotionLab_NTroje_rub008_0025_kicking1_poses", "kick", 70, 69, "noise")
     if "ppo" in what:
         gen_ppo()
+    if "ppo_real" in what:
+        gen_ppo_real()
+    if "sampler" in what:
+        gen_sampler(H.make_cfg())
 
 
 if __name__ == "__main__":

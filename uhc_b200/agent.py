@@ -16,6 +16,25 @@ from . import nn
 from .engine import ACT_DIM, OBS_DIM, Engine
 
 
+def ewma(x, alpha=0.05):
+    """uhc/utils/math_utils.py:25-29"""
+    avg = float(x[0])
+    for i in x[1:]:
+        avg = alpha * float(i) + (1 - alpha) * avg
+    return avg
+
+
+def failure_weights(success_hist, sampling_temp=0.2, sampling_freq=0.5):
+    """Per-clip sampling weights of the training loop (DatasetAMASSSingle.sample_seq with freq_dict, dataset_amass_single.py:183-186):
+    with probability sampling_freq the clip is drawn from p ~ exp(-ewma(success history) / temp) (0 for an empty history), else
+    uniformly over the clips.  success_hist: one list of 0/1 outcomes per clip (freq_dict[k][:, 0] == 1).  Returns the mixture
+    weights w = sampling_freq * p + (1 - sampling_freq) / C for uhc_set_clip_weights."""
+    s = np.array([ewma(np.asarray(h, dtype=np.float64) == 1) if len(h) > 0 else 0.0 for h in success_hist])
+    p = np.exp(-s / sampling_temp)
+    p = p / p.sum()
+    return (sampling_freq * p + (1.0 - sampling_freq) / len(p)).astype(np.float32)
+
+
 class ClipSampler:
     """DatasetAMASSSingle.sample_seq / get_sample_from_key (dataset_amass_single.py:172-253): uniform clip choice (or
     failure-weighted when freq stats are given), start ~ U[0, len - t_min), slice length min(t_max, len - start)."""

@@ -20,7 +20,34 @@ struct EngineView {
     const Real *clip_shape; // [C][17] beta[16], gender
     const int *clip_model;  // [C] body-shape (model variant) of each clip: the reference rebuilds the robot per clip (humanoid_im.py:154-180)
     const float *clip_cdf;  // [C] cumulative sampling weights (len // t_max + 1 copies per clip, sample_keys of the reference)
+    int *counters;          // [4] device counters: 0 = env-steps failed because a body's contacts did not fit MAXCON, 1 = env-steps skipped on an invalid env record
 };
+
+// an env record the step kernel can run: a clip of the CURRENT clip table and at least two frames (uhc_load_clips invalidates every
+// record; never-reset envs have len = 0)
+template <class Real>
+UHC_DEV bool env_record_valid(const EngineView<Real> &ev, int env) {
+    const int *is = ev.istate + (size_t)env * SI_SIZE;
+    const int clip = is[SI_CLIP], len = is[SI_LEN];
+    return len >= 2 && clip >= 0 && clip < ev.cfg.num_clips;
+}
+// outputs of an env that cannot be stepped: fail = end = 1, zero observation / reward (the caller must reset it)
+template <class Real, class ObsT>
+UHC_DEV void env_step_invalid(const EngineView<Real> &ev, ObsT *obs, ObsT *reward, ObsT *cinfo_out, int *fail_out, int *end_out, ObsT *percent_out) {
+    LANES_BEGIN
+    if (obs) for (int i = lane; i < OBS_DIM; i += 32) obs[i] = (ObsT)0;
+    if (cinfo_out && lane < 5) cinfo_out[lane] = (ObsT)0;
+    if (lane == 0) {
+        if (reward) *reward = (ObsT)0;
+        if (fail_out) *fail_out = 1;
+        if (end_out) *end_out = 1;
+        if (percent_out) *percent_out = (ObsT)0;
+#ifndef UHC_EMU
+        if (ev.counters) atomicAdd(ev.counters + 1, 1);
+#endif
+    }
+    LANES_END
+}
 
 template <class Real>
 UHC_DEV const Real *expert_frame(const EngineView<Real> &ev, int clip, int start, int len, int t) {  // humanoid_im.py:1322
@@ -93,7 +120,7 @@ UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, 
     for (int i = lane; i < ACT_DIM; i += 32) w.act[i] = 0;
     LANES_END
     LANES_BEGIN
-    if (lane == 0) { w.mdl = model_for_clip(ev, clip); w.cfg = ev.cfg; }
+    if (lane == 0) { w.mdl = model_for_clip(ev, clip); w.cfg = ev.cfg; w.con_overflow = 0; }
     LANES_END
     const Model<Real> &mdl = w.mdl;
     TOPO_DECL(mdl);
@@ -132,7 +159,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     const Real *target = expert_frame(ev, clip, start, len, cur_t + 1) + EX_QPOS + 7;
     int iters = 0, maxcon = 0;
     LANES_BEGIN
-    if (lane == 0) { w.mdl = model_for_clip(ev, clip); w.cfg = ev.cfg; }
+    if (lane == 0) { w.mdl = model_for_clip(ev, clip); w.cfg = ev.cfg; w.con_overflow = 0; }
     LANES_END
     const Model<Real> &mdl = w.mdl;
     TOPO_DECL(mdl);
@@ -163,11 +190,17 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
         LANES_END
         if (WBALLOT(bad)) fail = 1;
     }
+    // contacts that did not fit the work set: the episode is failed (and counted), never continued on a truncated contact set
+    const int overflow = w.con_overflow;
+    if (overflow) fail = 1;
     const int end = (cur_t >= ev.cfg.env_episode_len) || (cur_t >= len + ev.cfg.trail_steps - 1);
     if (obs) obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, cur_t + 1), ev.clip_shape + 17 * clip, obs);
     LANES_BEGIN
     if (lane == 0) {
-        is[SI_CUR_T] = cur_t; is[SI_NEWTON] = iters; is[SI_NCON] = maxcon;
+        is[SI_CUR_T] = cur_t; is[SI_NEWTON] = iters; is[SI_NCON] = maxcon; is[SI_FLAGS] = overflow ? 1 : 0;
+#ifndef UHC_EMU
+        if (overflow && ev.counters) atomicAdd(ev.counters, 1);
+#endif
         if (reward) *reward = (ObsT)rew;
         if (fail_out) *fail_out = fail;
         if (end_out) *end_out = end;

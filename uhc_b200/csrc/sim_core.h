@@ -115,6 +115,8 @@ struct Work {
     int cbody[MAXCON]; Real cr[MAXCON][3], cdist[MAXCON], cD[MAXCON], caref[MAXCON][4], cres[MAXCON][4], cjp[MAXCON][4];
     int bcon_adr[NB + 1];
     int ncon, upper_contact;
+    int con_overflow;             // a candidate body's contacts did not fit MAXCON in some substep of this step (the env is failed, never silently truncated)
+    int sync_threads;             // threads taking part in the CTA-level substep alignment barrier (32 x warps that own a valid env)
     // this env's model view (shape variant) and config: kept here so that the non-inlined phases read them from shared memory
     // instead of a per-thread local-memory copy
     alignas(8) Model<Real> mdl;
@@ -743,7 +745,7 @@ UHC_DEV void collide(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
     while (cand_b) {     // candidate bodies in ascending order
         int b = 0; while (!((cand_b >> b) & 1u)) b++;
         cand_b &= cand_b - 1;
-        if (ncon + 4 > MAXCON) continue;
+        if (ncon + 4 > MAXCON) { w.con_overflow = 1; continue; }   // flagged: env_step_warp turns it into fail (SI_FLAGS bit 0)
         const Real *R = w.xmat[b];
         const int adr = TP_OF(m, tp, b).hadr, nvt = TP_OF(m, tp, b).hnum;
         // deepest hull vertex: every lane keeps its best vertex (height, index, body-frame coordinates)
@@ -1103,8 +1105,10 @@ enum { PH_PD = 0, PH_SMOOTH = 1, PH_NEWTON = 2 };
 // Measured (E = 4096): whole-CTA alignment 1.25 M env-steps/s, groups of 4 / 3 / 2 warps 1.23 / 1.20 / 1.16 M, none 0.95 M;
 // every 2nd / 3rd substep only 1.06 / 1.00 M; aligning each Newton iteration too 1.06 M.  Re-measured on the final kernel (1.57 M):
 // without the barrier before the Newton phase 1.53 M, without the one at the substep start 1.57 M (neutral), without both 1.52 M.
+// The barrier is a NAMED barrier with an explicit thread count (w.sync_threads = 32 x the warps of the CTA that own a valid
+// environment): warps without work leave the kernel before the substep loop and are simply not counted.
 #if !defined(UHC_EMU) && !defined(UHC_NO_CTA_SYNC)
-#define UHC_CTA_SYNC(on) do { if (on) __syncthreads(); } while (0)
+#define UHC_CTA_SYNC(on) do { if (on) asm volatile("bar.sync 1, %0;" :: "r"(w.sync_threads) : "memory"); } while (0)
 #else
 #define UHC_CTA_SYNC(on) do { (void)(on); } while (0)
 #endif

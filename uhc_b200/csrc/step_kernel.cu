@@ -44,13 +44,24 @@ __global__ void UHC_STEP_BOUNDS(EPB, Real)
 k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict__ obs, float *__restrict__ rew, float *__restrict__ cinfo,
            int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque, const int *__restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_nvalid;
     const int warp = threadIdx.x >> 5, slot = blockIdx.x * EPB + warp;
+    if (threadIdx.x == 0) s_nvalid = 0;
     stage_tables<Real, EPB>(ev, smem);
-    if (slot >= ev.num_envs) return;
     // the warps of a CTA wait for each other every substep: `order` groups environments that needed a similar number of solver
     // iterations in the previous step into the same CTA (k_order_envs), outputs stay indexed by the environment id
-    const int env = order ? order[slot] : slot;
+    const int env = slot < ev.num_envs ? (order ? order[slot] : slot) : -1;
+    const bool valid = env >= 0 && env_record_valid(ev, env);
+    if (valid && (threadIdx.x & 31) == 0) atomicAdd(&s_nvalid, 1);
+    __syncthreads();
+    if (!valid) {   // no work (grid tail) or a stale / never-reset env record: flagged outputs, and the warp is not counted in the substep barrier
+        if (env >= 0) env_step_invalid<Real, float>(ev, obs ? obs + (size_t)env * OBS_DIM : nullptr, rew ? rew + env : nullptr, cinfo ? cinfo + (size_t)env * 5 : nullptr,
+                                                    fail ? fail + env : nullptr, end ? end + env : nullptr, pct ? pct + env : nullptr);
+        return;
+    }
     Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
+    if ((threadIdx.x & 31) == 0) w.sync_threads = 32 * s_nvalid;
+    __syncwarp();
     env_step_warp<Real, float>(ev, env, w, act + (size_t)env * ACT_DIM, obs ? obs + (size_t)env * OBS_DIM : nullptr, rew ? rew + env : nullptr,
                                cinfo ? cinfo + (size_t)env * 5 : nullptr, fail ? fail + env : nullptr, end ? end + env : nullptr,
                                pct ? pct + env : nullptr, torque ? torque + (size_t)env * NSUB * NU : nullptr);
@@ -87,6 +98,29 @@ k_env_reset(EngineView<Real> ev, int n, const int *__restrict__ ids, const int *
     env_reset_warp<Real, float>(ev, env, w, clip[i], start[i], len[i], qo, vo, obs ? obs + (size_t)env * OBS_DIM : nullptr);
 }
 
+// parity / evaluation hook: gather q, v, xpos, bquat (+ the integer record) of the listed envs into one staging array
+template <class Real>
+__global__ void k_gather_state(const Real *__restrict__ state, const int *__restrict__ istate, const int *__restrict__ ids, int n, double *__restrict__ out, int *__restrict__ iout) {
+    const int i = blockIdx.x; if (i >= n) return;
+    const int env = ids[i];
+    const Real *st = state + (size_t)env * ST_SIZE;
+    double *o = out + (size_t)i * 319;
+    for (int k = threadIdx.x; k < NQ; k += blockDim.x) o[k] = (double)st[ST_Q + k];
+    for (int k = threadIdx.x; k < NV; k += blockDim.x) o[76 + k] = (double)st[ST_V + k];
+    for (int k = threadIdx.x; k < 72; k += blockDim.x) o[151 + k] = (double)st[ST_XPOS + k];
+    for (int k = threadIdx.x; k < 96; k += blockDim.x) o[223 + k] = (double)st[ST_BQUAT + k];
+    if (threadIdx.x < SI_SIZE) iout[(size_t)i * SI_SIZE + threadIdx.x] = istate[(size_t)env * SI_SIZE + threadIdx.x];
+}
+// set_state keeps cur_t and the body quaternions of the env (humanoid_im.py:902-905 only overwrites qpos / qvel)
+template <class Real>
+__global__ void k_save_restore_bquat(Real *__restrict__ state, int *__restrict__ istate, const int *__restrict__ ids, int n, Real *__restrict__ keep, int *__restrict__ keep_t, int restore) {
+    const int i = blockIdx.x; if (i >= n) return;
+    const int env = ids[i];
+    Real *st = state + (size_t)env * ST_SIZE + ST_BQUAT;
+    for (int k = threadIdx.x; k < 192; k += blockDim.x) { if (restore) st[k] = keep[(size_t)i * 192 + k]; else keep[(size_t)i * 192 + k] = st[k]; }
+    if (threadIdx.x == 0) { if (restore) istate[(size_t)env * SI_SIZE + SI_CUR_T] = keep_t[i]; else keep_t[i] = istate[(size_t)env * SI_SIZE + SI_CUR_T]; }
+}
+
 struct UhcEngine {
     int E, device, precision, launches;
     std::vector<void *> allocs;
@@ -96,6 +130,11 @@ struct UhcEngine {
     // staging for the host-buffer API
     float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_cinfo = nullptr, *d_pct = nullptr; int *d_fail = nullptr, *d_end = nullptr;
     int *d_ids = nullptr; int ids_cap = 0;
+    int *h_ids = nullptr;                 // pinned host staging of the reset arguments (ids, clip, start, len)
+    cudaEvent_t ids_done = nullptr;       // the last reset kernel that read d_ids has been enqueued before this event
+    float *d_qv = nullptr; int qv_cap = 0; void *d_keep = nullptr; int *d_keep_t = nullptr;   // set_state staging: [n][76+75] floats, kept bquat / cur_t
+    double *d_gather = nullptr; int *d_gather_i = nullptr; int gather_cap = 0;
+    std::vector<float> clip_w;            // clip sampling weights behind clip_cdf (uhc_set_clip_weights), empty = sample_keys rule
     int *d_order = nullptr;   // warp slot -> environment (work-sorted each step), null = identity
     std::vector<int> clip_len_h;   // host copy of the clip lengths (argument validation)
 };
@@ -137,6 +176,8 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     CK(cudaMemset(st, 0, (size_t)e->E * ST_SIZE * sizeof(Real)));
     int *is; CK(cudaMalloc((void **)&is, (size_t)e->E * SI_SIZE * sizeof(int))); e->allocs.push_back(is);
     CK(cudaMemset(is, 0, (size_t)e->E * SI_SIZE * sizeof(int)));
+    int *cn; CK(cudaMalloc((void **)&cn, 4 * sizeof(int))); e->allocs.push_back(cn); CK(cudaMemset(cn, 0, 4 * sizeof(int)));
+    ev.counters = cn;
     ev.state = st; ev.istate = is; ev.expert = nullptr; ev.clip_adr = nullptr; ev.clip_shape = nullptr; ev.clip_model = nullptr; ev.clip_cdf = nullptr;
     return 0;
 }
@@ -185,35 +226,60 @@ void uhc_engine_destroy(UhcEngine *e) {
     if (e->d_clip_cdf) cudaFree(e->d_clip_cdf);
     if (e->d_clip_model) cudaFree(e->d_clip_model);
     if (e->d_ids) cudaFree(e->d_ids);
+    if (e->h_ids) cudaFreeHost(e->h_ids);
+    if (e->ids_done) cudaEventDestroy(e->ids_done);
+    if (e->d_qv) cudaFree(e->d_qv);
+    if (e->d_keep) cudaFree(e->d_keep);
+    if (e->d_keep_t) cudaFree(e->d_keep_t);
+    if (e->d_gather) cudaFree(e->d_gather);
+    if (e->d_gather_i) cudaFree(e->d_gather_i);
     delete e;
+}
+
+// cumulative clip sampling weights: explicit weights (uhc_set_clip_weights) or the sample_keys rule of the reference
+// (len // t_max + 1 copies per clip, dataset_amass_single.py:138-142)
+static int upload_clip_cdf(UhcEngine *e) {
+    const int nclips = e->num_clips;
+    if (nclips <= 0) return 0;
+    const int tmax = e->precision == 32 ? e->evf.cfg.t_max : e->evd.cfg.t_max;
+    std::vector<float> cdf(nclips); double acc = 0.0;
+    for (int i = 0; i < nclips; i++) {
+        acc += e->clip_w.empty() ? (double)(tmax > 0 ? e->clip_len_h[i] / tmax + 1 : 1) : (double)e->clip_w[i];
+        cdf[i] = (float)acc;
+    }
+    if (!e->d_clip_cdf) CK(cudaMalloc((void **)&e->d_clip_cdf, nclips * sizeof(float)));
+    CK(cudaMemcpy(e->d_clip_cdf, cdf.data(), nclips * sizeof(float), cudaMemcpyHostToDevice));
+    e->evf.clip_cdf = e->d_clip_cdf; e->evd.clip_cdf = e->d_clip_cdf;
+    return 0;
 }
 
 int uhc_engine_set_cfg(UhcEngine *e, const UhcEnvCfg *cfg) {
     if (!e || !cfg) { g_err = "uhc_engine_set_cfg: null"; return -2; }
+    CK(cudaSetDevice(e->device));
+    const int old_tmax = e->precision == 32 ? e->evf.cfg.t_max : e->evd.cfg.t_max;
     if (e->precision == 32) { fill_cfg(e->evf.cfg, cfg); e->evf.cfg.num_clips = e->num_clips; } else { fill_cfg(e->evd.cfg, cfg); e->evd.cfg.num_clips = e->num_clips; }
+    if (cfg->t_max != old_tmax && e->clip_w.empty()) { CK(cudaDeviceSynchronize()); return upload_clip_cdf(e); }   // the sample_keys weights depend on t_max
     return 0;
 }
 
 int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *frames_host, const double *shape_host) {
     if (!e || nclips <= 0 || !clip_len || !frames_host || !shape_host) { g_err = "uhc_load_clips: bad argument"; return -2; }
     CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());
     std::vector<int> adr(nclips + 1, 0);
     for (int i = 0; i < nclips; i++) { if (clip_len[i] < 2) { g_err = "uhc_load_clips: clip shorter than 2 frames"; return -2; } adr[i + 1] = adr[i] + clip_len[i]; }
     const size_t nf = (size_t)adr[nclips] * EX_SIZE, ns = (size_t)nclips * 17;
     if (e->d_expert) { cudaFree(e->d_expert); cudaFree(e->d_shape); cudaFree(e->d_clip_adr); cudaFree(e->d_clip_cdf); e->d_expert = e->d_shape = nullptr; e->d_clip_adr = nullptr; e->d_clip_cdf = nullptr; }
     CK(cudaMalloc((void **)&e->d_clip_adr, (nclips + 1) * sizeof(int)));
     CK(cudaMemcpy(e->d_clip_adr, adr.data(), (nclips + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    {   // sampling weights: len // t_max + 1 copies per clip (sample_keys, dataset_amass_single.py:138-142)
-        const int tmax = e->precision == 32 ? e->evf.cfg.t_max : e->evd.cfg.t_max;
-        std::vector<float> cdf(nclips); float acc = 0.f;
-        for (int i = 0; i < nclips; i++) { acc += (float)(tmax > 0 ? clip_len[i] / tmax + 1 : 1); cdf[i] = acc; }
-        CK(cudaMalloc((void **)&e->d_clip_cdf, nclips * sizeof(float)));
-        CK(cudaMemcpy(e->d_clip_cdf, cdf.data(), nclips * sizeof(float), cudaMemcpyHostToDevice));
-        e->num_clips = nclips; e->clip_len_h.assign(clip_len, clip_len + nclips);
-        e->evf.clip_cdf = e->d_clip_cdf; e->evd.clip_cdf = e->d_clip_cdf; e->evf.cfg.num_clips = nclips; e->evd.cfg.num_clips = nclips;
-        if (e->d_clip_model) { cudaFree(e->d_clip_model); e->d_clip_model = nullptr; }
-        e->evf.clip_model = nullptr; e->evd.clip_model = nullptr;
-    }
+    e->num_clips = nclips; e->clip_len_h.assign(clip_len, clip_len + nclips); e->clip_w.clear();
+    e->evf.cfg.num_clips = nclips; e->evd.cfg.num_clips = nclips;
+    if (upload_clip_cdf(e)) return -1;
+    if (e->d_clip_model) { cudaFree(e->d_clip_model); e->d_clip_model = nullptr; }
+    e->evf.clip_model = nullptr; e->evd.clip_model = nullptr;
+    // every env record points into the OLD clip table: invalidate them all (len = 0); the step kernel skips (and flags) an env
+    // until uhc_env_reset gives it a slice of the new table
+    CK(cudaMemset(e->precision == 32 ? e->evf.istate : e->evd.istate, 0, (size_t)e->E * SI_SIZE * sizeof(int)));
     if (e->precision == 32) {
         std::vector<float> f(nf), s(ns);
         for (size_t i = 0; i < nf; i++) f[i] = (float)frames_host[i];
@@ -227,6 +293,19 @@ int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *
         e->evd.expert = (const double *)e->d_expert; e->evd.clip_shape = (const double *)e->d_shape; e->evd.clip_adr = e->d_clip_adr;
     }
     return 0;
+}
+
+int uhc_set_clip_weights(UhcEngine *e, int nclips, const float *weights_host) {
+    if (!e || nclips != e->num_clips) { g_err = "uhc_set_clip_weights: call after uhc_load_clips with one weight per clip"; return -2; }
+    CK(cudaSetDevice(e->device));
+    if (!weights_host) e->clip_w.clear();
+    else {
+        double tot = 0; for (int i = 0; i < nclips; i++) { if (!(weights_host[i] >= 0.f)) { g_err = "uhc_set_clip_weights: negative / NaN weight"; return -2; } tot += weights_host[i]; }
+        if (!(tot > 0)) { g_err = "uhc_set_clip_weights: all weights are zero"; return -2; }
+        e->clip_w.assign(weights_host, weights_host + nclips);
+    }
+    CK(cudaDeviceSynchronize());
+    return upload_clip_cdf(e);
 }
 
 int uhc_set_clip_models(UhcEngine *e, int nclips, const int *clip_model) {
@@ -246,23 +325,32 @@ int uhc_env_reset(UhcEngine *e, int n, const int *env_ids_host, const int *clip_
     if (!e->d_expert) { g_err = "uhc_env_reset: no clips loaded"; return -3; }
     CK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (e->ids_cap < n) { if (e->d_ids) cudaFree(e->d_ids); CK(cudaMalloc((void **)&e->d_ids, (size_t)4 * n * sizeof(int))); e->ids_cap = n; }
     for (int i = 0; i < n; i++) {
         if (env_ids_host[i] < 0 || env_ids_host[i] >= e->E) { g_err = "uhc_env_reset: env id out of range"; return -2; }
         const int c = clip_host[i];
         if (c < 0 || c >= e->num_clips) { g_err = "uhc_env_reset: clip index out of range"; return -2; }
         if (start_host[i] < 0 || len_host[i] < 1 || start_host[i] + len_host[i] > e->clip_len_h[c]) { g_err = "uhc_env_reset: (start, length) outside the clip"; return -2; }
     }
-    CK(cudaMemcpyAsync(e->d_ids, env_ids_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_ids + n, clip_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_ids + 2 * n, start_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_ids + 3 * n, len_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    // the arguments travel through a pinned staging buffer owned by the engine, so the caller's arrays are free on return and the
+    // call stays asynchronous: the only wait is for the PREVIOUS reset's kernel to have consumed the staging buffer
+    if (!e->ids_done) CK(cudaEventCreateWithFlags(&e->ids_done, cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(e->ids_done));
+    if (e->ids_cap < n) {
+        if (e->d_ids) cudaFree(e->d_ids);
+        if (e->h_ids) cudaFreeHost(e->h_ids);
+        const int cap = n > 256 ? n : 256;
+        CK(cudaMalloc((void **)&e->d_ids, (size_t)4 * cap * sizeof(int))); CK(cudaHostAlloc((void **)&e->h_ids, (size_t)4 * cap * sizeof(int), cudaHostAllocDefault));
+        e->ids_cap = cap;
+    }
+    memcpy(e->h_ids, env_ids_host, n * sizeof(int)); memcpy(e->h_ids + n, clip_host, n * sizeof(int));
+    memcpy(e->h_ids + 2 * n, start_host, n * sizeof(int)); memcpy(e->h_ids + 3 * n, len_host, n * sizeof(int));
+    CK(cudaMemcpyAsync(e->d_ids, e->h_ids, (size_t)4 * n * sizeof(int), cudaMemcpyHostToDevice, st));
     if (e->precision == 32)
         k_env_reset<float, EPB_F><<<(n + EPB_F - 1) / EPB_F, 32 * EPB_F, step_smem<float, EPB_F>(), st>>>(e->evf, n, e->d_ids, e->d_ids + n, e->d_ids + 2 * n, e->d_ids + 3 * n, qpos_dev, qvel_dev, obs_dev);
     else
         k_env_reset<double, EPB_D><<<(n + EPB_D - 1) / EPB_D, 32 * EPB_D, step_smem<double, EPB_D>(), st>>>(e->evd, n, e->d_ids, e->d_ids + n, e->d_ids + 2 * n, e->d_ids + 3 * n, qpos_dev, qvel_dev, obs_dev);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));  // the host id arrays may be reused by the caller
+    CK(cudaEventRecord(e->ids_done, st));
     e->launches++;
     return 0;
 }
@@ -271,6 +359,7 @@ int uhc_env_step(UhcEngine *e, const float *actions_dev, float *obs_dev, float *
                  float *percent_dev, float *torque_dev, void *stream) {
     if (!e || !actions_dev) { g_err = "uhc_env_step: bad argument"; return -2; }
     if (!e->d_expert) { g_err = "uhc_env_step: no clips loaded"; return -3; }
+    CK(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (e->d_order) { k_order_envs<<<1, 1024, 0, st>>>(e->precision == 32 ? e->evf.istate : e->evd.istate, e->E, e->d_order); e->launches++; }
     if (e->precision == 32)
@@ -300,47 +389,89 @@ int uhc_env_step_host(UhcEngine *e, const float *actions_host, float *obs_host, 
     return 0;
 }
 
-int uhc_env_get_state(UhcEngine *e, int env, double *qpos76, double *qvel75, double *xpos72, double *bquat96, int *istate8) {
-    if (!e || env < 0 || env >= e->E) { g_err = "uhc_env_get_state: bad argument"; return -2; }
+// state of n envs in one gather kernel + one copy: out = [n][319] doubles (qpos76 qvel75 xpos72 bquat96), iout = [n][8]
+int uhc_env_get_state_batch(UhcEngine *e, int n, const int *env_ids_host, double *out_host, int *istate_host) {
+    if (!e || n <= 0 || !env_ids_host || !out_host) { g_err = "uhc_env_get_state_batch: bad argument"; return -2; }
+    for (int i = 0; i < n; i++) if (env_ids_host[i] < 0 || env_ids_host[i] >= e->E) { g_err = "uhc_env_get_state_batch: env id out of range"; return -2; }
     CK(cudaSetDevice(e->device));
     CK(cudaDeviceSynchronize());
-    std::vector<double> st(ST_SIZE);
-    if (e->precision == 32) {
-        std::vector<float> f(ST_SIZE);
-        CK(cudaMemcpy(f.data(), e->evf.state + (size_t)env * ST_SIZE, ST_SIZE * 4, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < ST_SIZE; i++) st[i] = f[i];
-    } else CK(cudaMemcpy(st.data(), e->evd.state + (size_t)env * ST_SIZE, ST_SIZE * 8, cudaMemcpyDeviceToHost));
-    if (qpos76) memcpy(qpos76, &st[ST_Q], NQ * 8);
-    if (qvel75) memcpy(qvel75, &st[ST_V], NV * 8);
-    if (xpos72) memcpy(xpos72, &st[ST_XPOS], 72 * 8);
-    if (bquat96) memcpy(bquat96, &st[ST_BQUAT], 96 * 8);
-    if (istate8) CK(cudaMemcpy(istate8, (e->precision == 32 ? e->evf.istate : e->evd.istate) + (size_t)env * SI_SIZE, SI_SIZE * 4, cudaMemcpyDeviceToHost));
+    if (e->gather_cap < n) {
+        if (e->d_gather) { cudaFree(e->d_gather); cudaFree(e->d_gather_i); }
+        CK(cudaMalloc((void **)&e->d_gather, (size_t)n * 319 * sizeof(double))); CK(cudaMalloc((void **)&e->d_gather_i, (size_t)n * (SI_SIZE + 1) * sizeof(int)));
+        e->gather_cap = n;
+    }
+    int *d_idl = e->d_gather_i + (size_t)n * SI_SIZE;
+    CK(cudaMemcpy(d_idl, env_ids_host, n * sizeof(int), cudaMemcpyHostToDevice));
+    if (e->precision == 32) k_gather_state<float><<<n, 128>>>(e->evf.state, e->evf.istate, d_idl, n, e->d_gather, e->d_gather_i);
+    else k_gather_state<double><<<n, 128>>>(e->evd.state, e->evd.istate, d_idl, n, e->d_gather, e->d_gather_i);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out_host, e->d_gather, (size_t)n * 319 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (istate_host) CK(cudaMemcpy(istate_host, e->d_gather_i, (size_t)n * SI_SIZE * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int uhc_env_get_state(UhcEngine *e, int env, double *qpos76, double *qvel75, double *xpos72, double *bquat96, int *istate8) {
+    if (!e || env < 0 || env >= e->E) { g_err = "uhc_env_get_state: bad argument"; return -2; }
+    double out[319]; int is[SI_SIZE];
+    int rc = uhc_env_get_state_batch(e, 1, &env, out, is);
+    if (rc) return rc;
+    if (qpos76) memcpy(qpos76, out, NQ * 8);
+    if (qvel75) memcpy(qvel75, out + 76, NV * 8);
+    if (xpos72) memcpy(xpos72, out + 151, 72 * 8);
+    if (bquat96) memcpy(bquat96, out + 223, 96 * 8);
+    if (istate8) memcpy(istate8, is, sizeof is);
+    return 0;
+}
+
+// fail_safe (humanoid_im.py:902-905) for n envs at once: overwrite qpos/qvel, run sim.forward(), keep cur_t and the body quats.
+// One reset-with-override launch for all of them; no allocation in the steady state.
+int uhc_env_set_state_batch(UhcEngine *e, int n, const int *env_ids_host, const double *qpos_host, const double *qvel_host) {
+    if (!e || n <= 0 || !env_ids_host || !qpos_host || !qvel_host) { g_err = "uhc_env_set_state_batch: bad argument"; return -2; }
+    for (int i = 0; i < n; i++) if (env_ids_host[i] < 0 || env_ids_host[i] >= e->E) { g_err = "uhc_env_set_state_batch: env id out of range"; return -2; }
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());
+    const size_t rs = e->precision == 32 ? 4 : 8;
+    if (e->qv_cap < n) {
+        if (e->d_qv) { cudaFree(e->d_qv); cudaFree(e->d_keep); cudaFree(e->d_keep_t); }
+        CK(cudaMalloc((void **)&e->d_qv, (size_t)n * (NQ + NV) * 4)); CK(cudaMalloc(&e->d_keep, (size_t)n * 192 * 8)); CK(cudaMalloc((void **)&e->d_keep_t, (size_t)n * 2 * sizeof(int)));
+        e->qv_cap = n;
+    }
+    (void)rs;
+    std::vector<float> qv((size_t)n * (NQ + NV));
+    for (int i = 0; i < n; i++) { for (int k = 0; k < NQ; k++) qv[(size_t)i * NQ + k] = (float)qpos_host[(size_t)i * NQ + k]; for (int k = 0; k < NV; k++) qv[(size_t)n * NQ + (size_t)i * NV + k] = (float)qvel_host[(size_t)i * NV + k]; }
+    CK(cudaMemcpy(e->d_qv, qv.data(), qv.size() * 4, cudaMemcpyHostToDevice));
+    std::vector<int> is((size_t)n * SI_SIZE), clip(n), start(n), len(n);
+    std::vector<double> tmp((size_t)n * 319);
+    int rc = uhc_env_get_state_batch(e, n, env_ids_host, tmp.data(), is.data());
+    if (rc) return rc;
+    for (int i = 0; i < n; i++) {
+        clip[i] = is[(size_t)i * SI_SIZE + SI_CLIP]; start[i] = is[(size_t)i * SI_SIZE + SI_START]; len[i] = is[(size_t)i * SI_SIZE + SI_LEN];
+        if (len[i] < 2 || clip[i] < 0 || clip[i] >= e->num_clips) { g_err = "uhc_env_set_state_batch: env has no valid episode (reset it first)"; return -2; }
+    }
+    int *d_idl = e->d_keep_t + n;
+    CK(cudaMemcpy(d_idl, env_ids_host, n * sizeof(int), cudaMemcpyHostToDevice));
+    if (e->precision == 32) k_save_restore_bquat<float><<<n, 64>>>(e->evf.state, e->evf.istate, d_idl, n, (float *)e->d_keep, e->d_keep_t, 0);
+    else k_save_restore_bquat<double><<<n, 64>>>(e->evd.state, e->evd.istate, d_idl, n, (double *)e->d_keep, e->d_keep_t, 0);
+    rc = uhc_env_reset(e, n, env_ids_host, clip.data(), start.data(), len.data(), e->d_qv, e->d_qv + (size_t)n * NQ, nullptr, nullptr);
+    if (rc) return rc;
+    if (e->precision == 32) k_save_restore_bquat<float><<<n, 64>>>(e->evf.state, e->evf.istate, d_idl, n, (float *)e->d_keep, e->d_keep_t, 1);
+    else k_save_restore_bquat<double><<<n, 64>>>(e->evd.state, e->evd.istate, d_idl, n, (double *)e->d_keep, e->d_keep_t, 1);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
     return 0;
 }
 
 int uhc_env_set_state(UhcEngine *e, int env, const double *qpos76, const double *qvel75) {
-    // fail_safe (humanoid_im.py:902-905): overwrite qpos/qvel then run sim.forward(); implemented as a reset-with-override
-    if (!e || env < 0 || env >= e->E || !qpos76 || !qvel75) { g_err = "uhc_env_set_state: bad argument"; return -2; }
+    return uhc_env_set_state_batch(e, 1, &env, qpos76, qvel75);
+}
+
+// device counters: out[0] = env-steps failed because a body's contacts did not fit the work set (MAXCON), out[1] = env-steps
+// skipped on an invalid (stale / never reset) env record
+int uhc_engine_counters(UhcEngine *e, int *out4) {
+    if (!e || !out4) { g_err = "uhc_engine_counters: bad argument"; return -2; }
     CK(cudaSetDevice(e->device));
     CK(cudaDeviceSynchronize());
-    int is[SI_SIZE];
-    int *isd = (e->precision == 32 ? e->evf.istate : e->evd.istate) + (size_t)env * SI_SIZE;
-    CK(cudaMemcpy(is, isd, sizeof is, cudaMemcpyDeviceToHost));
-    std::vector<float> q(NQ), v(NV);
-    for (int i = 0; i < NQ; i++) q[i] = (float)qpos76[i];
-    for (int i = 0; i < NV; i++) v[i] = (float)qvel75[i];
-    float *dq, *dv; CK(cudaMalloc((void **)&dq, NQ * 4)); CK(cudaMalloc((void **)&dv, NV * 4));
-    CK(cudaMemcpy(dq, q.data(), NQ * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dv, v.data(), NV * 4, cudaMemcpyHostToDevice));
-    // keep cur_t / bquat: save and restore around the reset kernel
-    std::vector<unsigned char> keep((size_t)192 * (e->precision == 32 ? 4 : 8));
-    const size_t rs = e->precision == 32 ? 4 : 8;
-    unsigned char *stb = (unsigned char *)(e->precision == 32 ? (void *)e->evf.state : (void *)e->evd.state) + ((size_t)env * ST_SIZE + ST_BQUAT) * rs;
-    CK(cudaMemcpy(keep.data(), stb, keep.size(), cudaMemcpyDeviceToHost));
-    int rc = uhc_env_reset(e, 1, &env, &is[SI_CLIP], &is[SI_START], &is[SI_LEN], dq, dv, nullptr, nullptr);
-    cudaFree(dq); cudaFree(dv);
-    if (rc) return rc;
-    CK(cudaMemcpy(stb, keep.data(), keep.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(isd, is, sizeof(int), cudaMemcpyHostToDevice));  // cur_t
+    CK(cudaMemcpy(out4, e->precision == 32 ? e->evf.counters : e->evd.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
 

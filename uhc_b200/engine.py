@@ -181,9 +181,38 @@ class Engine:
         return dict(qpos=q, qvel=v, xpos=xp.reshape(24, 3), bquat=bq, cur_t=int(ist[0]), clip=int(ist[1]), start=int(ist[2]), len=int(ist[3]),
                     newton_iters=int(ist[6]), ncon=int(ist[7]))
 
+    def get_states(self, env_ids=None):
+        """state of many envs with one gather launch + one copy (evaluation / parity hook): dict of arrays [n, ...]."""
+        ids = np.arange(self.E, dtype=np.int32) if env_ids is None else np.ascontiguousarray(env_ids, dtype=np.int32)
+        n = len(ids)
+        out, ist = np.zeros((n, 319)), np.zeros((n, 8), np.int32)
+        _chk(self.lib.uhc_env_get_state_batch(self.h, C.c_int(n), _ip(ids), out.ctypes.data_as(C.POINTER(C.c_double)), ist.ctypes.data_as(C.POINTER(C.c_int))))
+        return dict(qpos=out[:, :76], qvel=out[:, 76:151], xpos=out[:, 151:223].reshape(n, 24, 3), bquat=out[:, 223:319], cur_t=ist[:, 0], clip=ist[:, 1],
+                    start=ist[:, 2], len=ist[:, 3], episode=ist[:, 4], flags=ist[:, 5], newton_iters=ist[:, 6], ncon=ist[:, 7])
+
     def set_state(self, env, qpos, qvel):
-        q, v = np.ascontiguousarray(qpos, np.float64), np.ascontiguousarray(qvel, np.float64)
-        _chk(self.lib.uhc_env_set_state(self.h, C.c_int(env), q.ctypes.data_as(C.POINTER(C.c_double)), v.ctypes.data_as(C.POINTER(C.c_double))))
+        self.set_states([env], np.asarray(qpos)[None], np.asarray(qvel)[None])
+
+    def set_states(self, env_ids, qpos, qvel):
+        """fail_safe for many envs at once (humanoid_im.py:902-905): one reset-with-override launch."""
+        ids = np.ascontiguousarray(env_ids, dtype=np.int32)
+        q = np.ascontiguousarray(qpos, np.float64).reshape(len(ids), NQ)
+        v = np.ascontiguousarray(qvel, np.float64).reshape(len(ids), NV)
+        _chk(self.lib.uhc_env_set_state_batch(self.h, C.c_int(len(ids)), _ip(ids), q.ctypes.data_as(C.POINTER(C.c_double)), v.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def set_clip_weights(self, weights=None):
+        """sampling weights of the in-kernel re-seeding (None = the reference's sample_keys rule)."""
+        if weights is None:
+            _chk(self.lib.uhc_set_clip_weights(self.h, C.c_int(len(self.clip_len)), None))
+        else:
+            w = np.ascontiguousarray(weights, dtype=np.float32)
+            _chk(self.lib.uhc_set_clip_weights(self.h, C.c_int(len(w)), w.ctypes.data_as(C.POINTER(C.c_float))))
+
+    @property
+    def counters(self):
+        out = np.zeros(4, np.int32)
+        _chk(self.lib.uhc_engine_counters(self.h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        return dict(contact_overflow_steps=int(out[0]), invalid_env_steps=int(out[1]))
 
     @property
     def kernel_launches(self):
