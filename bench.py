@@ -3,7 +3,7 @@
 
 A "step" is one lock-step control step of every environment: observation normaliser -> policy MLP forward (tcgen05) ->
 Gaussian sample -> fused physics(15 substeps)+task kernel -> transition written to the HBM rollout buffer -> re-seeding of
-finished episodes.  Workload at N=1 = BASELINE.json configs[1]: 4096 SMPL-neutral humanoids imitating one AMASS-shaped clip,
+finished episodes; the whole step is one call of the C-ABI loop (uhc_rollout) = one CUDA-graph launch.  Workload at N=1 = BASELINE.json configs[1]: 4096 SMPL-neutral humanoids imitating one AMASS-shaped clip,
 policy rollout only.  N>1: weak scaling, 4096 envs per GPU, no data-path collective (the rollout has none).
 
   python bench.py --gpus 1 --steps 20 --warmup 3
@@ -37,25 +37,64 @@ def make_clip(seed=1):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
+REF_ENVS_PER_CORE = 32                 # bounded sample: every host process owns this many oracle envs; one "step" steps each of them once
+_REF_POLICY = None
+
+
+def _ref_policy():
+    """The bench policy (same seeded initial weights as the GPU arm) evaluated the way the reference does: torch fp64 on the CPU
+    (scripts/train_uhc.py:80-81 sets float64; khrylib/rl/core/policy_gaussian.py:26-31)."""
+    global _REF_POLICY
+    if _REF_POLICY is None:
+        import torch
+        from uhc_b200 import nn
+        net = nn.MLPNet(657, (2048, 1024, 512), 105, "gelu", device="cpu", head_name="action_mean", seed=1)
+        _REF_POLICY = ([w.double() for w in net.W], [b.double() for b in net.b])
+    return _REF_POLICY
+
+
 def _cpu_worker(args):
-    seed, budget_s = args
+    """One host process: REF_ENVS_PER_CORE oracle envs; per step ZFilter -> policy MLP (fp64) -> Gaussian sample -> env.step + reward,
+    finished episodes re-seeded (start ~ U[0, L - t_min)).  Runs `warmup` untimed and `steps` timed steps; returns the timed wall."""
+    import torch
+    seed, steps, warmup, nenv = args
+    torch.set_num_threads(1)
     from oracle import oracle as O
     ex, shape = make_clip()
     rng = np.random.RandomState(seed)
-    env = O.Env(O.Model(), ex, shape)
-    env.reset()
-    n, t0 = 0, time.time()
-    while time.time() - t0 < budget_s:
-        a = rng.normal(0, 0.1, 105)
-        a[69:75] *= 0.3
-        _, _, done, _ = env.step(a)
-        n += 1
-        if done:
-            s = rng.randint(0, CLIP_FRAMES - 5)
-            sl = {k: np.asarray(ex[k])[s:] for k in ("qpos", "qvel", "wbpos", "wbquat", "bquat", "bangvel", "ee_wpos", "com")}
-            env.load_expert(sl, shape)
-            env.reset()
-    return n, time.time() - t0
+    keys = ("qpos", "qvel", "wbpos", "wbquat", "bquat", "bangvel", "ee_wpos", "com")
+    om = O.Model()
+
+    def seeded():
+        s = rng.randint(0, CLIP_FRAMES - 5)
+        return {k: np.asarray(ex[k])[s:s + 300] for k in keys}
+    envs = [O.Env(om, seeded(), shape) for _ in range(nenv)]
+    obs = np.stack([e.reset() for e in envs])
+    Ws, bs = _ref_policy()
+    n, mean, S = 0.0, np.zeros(657), np.zeros(657)
+    t0 = None
+    for it in range(warmup + steps):
+        if it == warmup:
+            t0 = time.perf_counter()
+        nb, mb = float(len(obs)), obs.mean(0)                       # ZFilter, batched Chan merge (zfilter.py:7-73), clip 5
+        Sb = ((obs - mb) ** 2).sum(0)
+        d = mb - mean
+        tot = n + nb
+        mean, S, n = mean + d * nb / tot, S + Sb + d * d * n * nb / tot, tot
+        std = np.sqrt(S / (n - 1)) if n > 1 else np.abs(mean)
+        h = torch.from_numpy(np.clip((obs - mean) / (std + 1e-8), -5, 5))
+        for i, (W, b) in enumerate(zip(Ws, bs)):
+            h = h @ W.T + b
+            if i < len(Ws) - 1:
+                h = torch.nn.functional.gelu(h)
+        act = h.numpy() + np.exp(-2.3) * rng.standard_normal((len(obs), 105))
+        for j, e in enumerate(envs):
+            o, _, done, _ = e.step(act[j])
+            if done:
+                e.load_expert(seeded(), shape)
+                o = e.reset()
+            obs[j] = o
+    return nenv * steps, time.perf_counter() - t0
 
 
 def usable_cores():
@@ -81,21 +120,25 @@ def usable_cores():
     return max(1, n)
 
 
-def cpu_baseline(budget_s=12.0, cores=None):
-    """The reference's per-env CPU path restated (oracle/uhc_oracle.c: PD + 15 substeps + obs + reward), one process per
-    host core, bounded sample."""
+def cpu_baseline(steps=8, warmup=1, cores=None, envs_per_core=REF_ENVS_PER_CORE):
+    """The reference's CPU path restated (oracle/uhc_oracle.c: PD + 15 substeps + obs + reward; the policy in torch fp64 as the
+    reference runs it), one process per usable host core, on a bounded sample of the bench workload: cores x envs_per_core envs, `steps`
+    lock-step control steps.  Returns throughput and the MEASURED wall time per step of that sample."""
     import multiprocessing as mp
     from oracle import oracle as O
     O.build()
+    _ref_policy()
     cores = cores or usable_cores()
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(i + 1, budget_s) for i in range(cores)])
-    steps = sum(r[0] for r in res)
+        res = pool.map(_cpu_worker, [(i + 1, steps, warmup, envs_per_core) for i in range(cores)])
+    env_steps = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
-    return dict(value=steps / wall, unit=UNIT, cores=cores, kind="port",
-                sample=f"{steps} env-steps of the same workload (noise actions, re-seeded on termination) in {wall:.1f} s on {cores} processes; "
-                       "fp64 C restatement of the MuJoCo+Python path, NOT MuJoCo itself")
+    return dict(value=env_steps / wall, unit=UNIT, cores=cores, kind="port", sample_envs=cores * envs_per_core, sample_steps=steps,
+                ms_per_sample_step=1e3 * wall / steps,
+                sample=f"{cores * envs_per_core} envs ({envs_per_core} per process, {cores} processes) x {steps} control steps of the same workload = {env_steps} env-steps "
+                       f"in {wall:.2f} s: fp64 obs normaliser + 657-2048-1024-512-105 policy (torch fp64, same initial weights) + fp64 C restatement of the "
+                       "MuJoCo+Python step (oracle/, NOT MuJoCo itself), episodes re-seeded on termination")
 
 
 def run_reference(args):
@@ -103,11 +146,13 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.time()
-    per = max(2.0, min(20.0, 6.0 * (args.steps + args.warmup) / 23.0))
-    cb = cpu_baseline(budget_s=per)
+    cb = cpu_baseline(steps=args.steps, warmup=args.warmup)
+    cfg = workload_config(args.gpus)
+    cfg["reference_sample"] = (f"each reference step = one control step of {cb['sample_envs']} envs ({REF_ENVS_PER_CORE} per host process), a bounded sample of the "
+                               f"{ENVS_PER_GPU * args.gpus}-env workload; ms_per_step is the measured wall time of that sample step")
     line = dict(impl="reference", metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * ENVS_PER_GPU * args.gpus / cb["value"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                data="synthetic", config=workload_config(args.gpus), cpu_baseline=cb,
+                ms_per_step=cb["ms_per_sample_step"], higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=cfg, cpu_baseline=cb,
                 e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), wall_s=time.time() - t0)
     print(json.dumps(line))
 
@@ -171,6 +216,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -182,86 +228,92 @@ def run_gpu(args):
     E, K, W = ENVS_PER_GPU, args.steps, max(args.warmup, 3)
     agent = BatchedAgent(E, [ex], [shape], device=local, seed=1, rank=rank, world=world)
     agent.reset_envs()
-    buf = RolloutBuffer(max(K, 4), E, agent.dev)
+    L, h = agent.engine.lib, agent.engine.h
+    R = max(1, min(K, 32))                               # buffer rows in use: one CUDA graph (and one pair of kernel events) per row
+    buf = RolloutBuffer(R, E, agent.dev)
+    if L.uhc_rollout_time_env_step(h, C.c_int(R)) != 0:  # CUDA events around k_env_step, recorded on the launching stream inside the graph
+        raise RuntimeError("uhc_rollout_time_env_step failed")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=agent.dev)
     clocks = ClockSampler(local) if rank == 0 else None
-    for k in range(W):
-        agent.step_once(buf, k % buf.T)
+    for k in range(max(W, R)):                           # warm-up: every row's graph is captured and instantiated here, outside the timed region
+        agent.rollout(buf, 1, k % R)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    # per-kernel timing of the dominant kernel: wrap engine.step
-    raw_step = agent.engine.step
-    cur = [0]
-
-    def timed_step(a, torque_out=None, reward_out=None):
-        kev[cur[0]][0].record()
-        out = raw_step(a, torque_out, reward_out)
-        kev[cur[0]][1].record()
-        return out
-    agent.engine.step = timed_step
     l0, n0 = agent.engine.kernel_launches, agent.nn_launches
+    per_step = L.uhc_rollout_launches_per_step(h)
     torch.cuda.synchronize()
     t_wall0 = time.time()
     for k in range(K):
-        flush.fill_(k & 0xFF)                       # L2 flush, outside the timed region
-        cur[0] = k
+        flush.fill_(k & 0xFF)                            # L2 flush, outside the timed region
         ev[k][0].record()
-        agent.step_once(buf, k % buf.T)
+        agent.rollout(buf, 1, k % R)                     # ONE control step of all envs: uhc_rollout -> one CUDA-graph launch
         ev[k][1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()
     clk = clocks.stop(t_wall0, t_wall1) if clocks else None
-    agent.engine.step = raw_step
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / K
-    launches = (agent.engine.kernel_launches - l0) + (agent.nn_launches - n0)
+    ms = C.c_float(0)
+    kms, kern_src = [], "CUDA events around k_env_step recorded inside the timed graph replays (external event-record nodes on the launching stream)"
+    for r in range(R):
+        if L.uhc_rollout_env_step_ms(h, C.c_int(r), C.byref(ms)) != 0:
+            kms = None
+            break
+        kms.append(ms.value)
+    if kms is None:
+        # fallback: the same steps launched as plain stream launches (identical kernels), events around k_env_step on that stream
+        kern_src = "CUDA events around k_env_step in an extra pass of plain stream launches of the same step (graph event nodes unreadable on this driver)"
+        kms = []
+        for k in range(R):
+            flush.fill_(k & 0xFF)
+            agent.rollout(buf, 1, k % R, use_graph=False)
+        torch.cuda.synchronize()
+        for r in range(R):
+            if L.uhc_rollout_env_step_ms(h, C.c_int(r), C.byref(ms)) != 0:
+                L.uhc_rollout_last_error.restype = C.c_char_p
+                raise RuntimeError("uhc_rollout_env_step_ms failed: " + L.uhc_rollout_last_error().decode())
+            kms.append(ms.value)
+    kern_ms = float(np.mean(kms))
+    launches = per_step * K
     tt = torch.tensor([total_ms], device=agent.dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms = float(tt.item())
     value = E * world * K / (total_ms * 1e-3)
 
-    # end to end through the host-buffer API: obs (pinned host) -> device policy -> actions to host -> uhc_env_step_host -> obs/reward to host
+    # end to end through host buffers: the step's input (the observations) comes from pinned host memory, the step runs through the public
+    # call (BatchedAgent.rollout -> uhc_rollout), and its results (next obs, actions, reward, mask, fail) are read back to the host; one sync per step
     Ke = max(3, min(K, 20))
-    obs_h = torch.empty(E, 657, dtype=torch.float32).pin_memory()
-    act_h = torch.empty(E, 105, dtype=torch.float32).pin_memory()
-    rew_h, pct_h = np.empty(E, np.float32), np.empty(E, np.float32)
-    ci_h, fail_h, end_h = np.empty((E, 5), np.float32), np.empty(E, np.int32), np.empty(E, np.int32)
+    pin = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype).pin_memory()
+    obs_h, act_h, rew_h, mask_h, fail_h = pin(E, 657), pin(E, 105), pin(E), pin(E), pin(E, dtype=torch.int32)
     obs_h.copy_(agent.obs)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+
     def e2e_step():
-        od = obs_h.to(agent.dev, non_blocking=True)
-        _, a, _ = agent.policy_step(od, True, None, True)
-        act_h.copy_(a, non_blocking=True)
+        agent.obs.copy_(obs_h, non_blocking=True)
+        agent.rollout(buf, 1, 0)
+        obs_h.copy_(agent.obs, non_blocking=True); act_h.copy_(buf.actions[0], non_blocking=True); rew_h.copy_(buf.rewards[0], non_blocking=True)
+        mask_h.copy_(buf.masks[0], non_blocking=True); fail_h.copy_(buf.fails[0], non_blocking=True)
         torch.cuda.synchronize()
-        agent.engine.step_host(act_h.numpy(), obs_h.numpy(), rew_h, ci_h, fail_h, end_h, pct_h)
-        done = np.nonzero(fail_h | end_h)[0]
-        if len(done) and not agent.auto_reset:
-            agent.reset_envs(done.astype(np.int32))
-            torch.cuda.synchronize()
-            obs_h[torch.as_tensor(done)] = agent.obs[torch.as_tensor(done, device=agent.dev)].cpu()
-    for _ in range(min(W, 3)):      # untimed warm-up of the host path (staging buffers, page faults)
+    for _ in range(3):
         e2e_step()
-    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for k in range(Ke):
         e2e_step()
-    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=agent.dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = E * world * Ke / float(te.item())
+    counters = agent.engine.counters
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks = {}
     try:
@@ -270,24 +322,147 @@ def run_gpu(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = BYTES_PER_ENV_STEP * E / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "env_step_traffic.json")
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r02_env_step_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("how")
         except Exception:
             pass
-    cb = cpu_baseline(budget_s=10.0) if world == 1 else None
+    cb = cpu_baseline(steps=6, warmup=1) if world == 1 else None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=total_ms / K, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload_config(world),
-                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                              kernel="k_env_step<float,7>", kernel_ms=kern_ms, kernel_share_of_step=kern_ms / (total_ms / K),
+                roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
+                              kernel="k_env_step<float>", kernel_ms=kern_ms, kernel_ms_source=kern_src, kernel_share_of_step=kern_ms / (total_ms / K),
                               peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                              note="algorithmic bytes 6396 B/env-step (SURVEY 8d); the step is latency/ALU bound, not HBM bound -- see DESIGN.md"),
-                e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=E * (657 + 105) * 4, d2h_bytes_per_step=E * (105 + 657 + 1 + 5 + 1 + 1 + 1) * 4, steps=Ke),
-                gpu_launches=launches, clocks=clk)
+                              note="algorithmic bytes 6396 B/env-step (SURVEY 8d); the step is latency/issue bound, not HBM bound -- see DESIGN.md"),
+                e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=E * 657 * 4, d2h_bytes_per_step=E * (657 + 105 + 1 + 1 + 1) * 4, steps=Ke,
+                         path="pinned host obs -> device, BatchedAgent.rollout (uhc_rollout, 1 step), next obs / action / reward / mask / fail -> pinned host, one sync"),
+                gpu_launches=launches, launches_per_step=per_step, step_driver="uhc_rollout: one CUDA-graph launch per control step",
+                env_counters=counters, clocks=clk)
     if cb:
         line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ train workload (BASELINE configs 3-5)
+TAKE5_LENS = (320, 375, 146, 236, 121, 170, 137, 69, 209, 189)     # clip lengths of sample_data/amass_copycat_take5_test_small.pkl
+TRAIN_T, TRAIN_EPOCHS = 32, 10
+
+
+def make_train_clips(world):
+    """N = 1: BASELINE configs[2] -- ten AMASS-shaped clips with the lengths of take5_test_small, one body shape.
+    N > 1: configs[3]/[4] -- 24 clips in the issue-class proportions of amass_copycat_occlusion_v2 (normal / sitting / airborne ~ 54 / 33 / 13 %,
+    SURVEY.md section 8d) and three synthetic body-shape variants (limb scaling; the SMPL files are licence-gated)."""
+    from uhc_b200 import motion_lib
+    from uhc_b200.model import HumanoidModel, NB
+    rng = np.random.default_rng(7)
+    if world == 1:
+        clips = [motion_lib.synthetic_clip(L, rng) for L in TAKE5_LENS]
+        return clips, [np.zeros(17) for _ in clips], None, None, None
+    kinds = ["normal"] * 13 + ["sitting"] * 8 + ["airborne"] * 3
+    clips = [motion_lib.synthetic_clip(int(rng.integers(60, 300)), rng, kind=k) for k in kinds]
+    base = HumanoidModel()
+    variants = [base] + [HumanoidModel(scale=np.full(NB, sc)) for sc in (0.92, 1.08)]
+    clip_models = [i % 3 for i in range(len(clips))]
+    shapes = [np.concatenate([np.full(16, 0.1 * m), [0.0]]) for m in clip_models]
+    return clips, shapes, base, variants, clip_models
+
+
+def run_train(args):
+    """`--workload train`: one "step" = one full PPO iteration on every GPU: T = 32 lock-step control steps of 4096 envs per GPU (uhc_rollout),
+    V(s) + GAE + advantage normalisation, 10 epochs of (value step, clipped-surrogate policy step) on the tensor-core path, with the
+    gradient all-reduce (the design's only collective) INSIDE the timed region."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    from uhc_b200.agent import BatchedAgent, RolloutBuffer
+    clips, shapes, base, variants, clip_models = make_train_clips(world)
+    E, K, W, T = ENVS_PER_GPU, args.steps, max(args.warmup, 3), TRAIN_T
+    agent = BatchedAgent(E, clips, shapes, device=local, seed=1, rank=rank, world=world, model=base, variants=variants, clip_models=clip_models,
+                         num_optim_epoch=TRAIN_EPOCHS, t_min=15, t_max=300)
+    agent.reset_envs()
+    buf = RolloutBuffer(T, E, agent.dev)
+    clocks = ClockSampler(local) if rank == 0 else None
+    for _ in range(W):
+        agent.sample(T, buf); agent.update_params(buf)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
+    phases = dict(gae_ms=0.0, epochs_ms=0.0, allreduce_ms=0.0, allreduce_bytes=0, allreduce_calls=0)
+    l0 = agent.engine.kernel_launches
+    t_wall0 = time.time()
+    ev[0].record()
+    for k in range(K):
+        agent.rollout(buf, T)
+        buf.last_obs.copy_(agent.obs)
+        ev[2 * k + 1].record()
+        out = agent.update_params(buf)
+        ev[2 * k + 2].record()
+        for key in phases:
+            phases[key] += out.get(key, 0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.time()
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+    total_ms = ev[0].elapsed_time(ev[2 * K])
+    sample_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(K)) / K
+    update_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(K)) / K
+    tt = torch.tensor([total_ms], device=agent.dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    value = E * world * T * K / (total_ms * 1e-3)
+    # identical parameters and observation normaliser on every rank (the tail of the gradient all-reduce keeps them in lock-step)
+    chk = torch.stack([agent.policy.flat.double().sum(), agent.value.flat.double().sum(), agent.running_state.stats.sum()])
+    same = True
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(lo, hi))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    N = T * E
+    npar = agent.policy.flat.numel() + agent.value.flat.numel()
+    flops_update = TRAIN_EPOCHS * 6.0 * (sum(w.numel() for w in agent.policy.W) + sum(w.numel() for w in agent.value.W)) * N
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    ach = flops_update / (phases["epochs_ms"] / K * 1e-3) / 1e12
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=total_ms / K, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32 physics / bf16 tensor-core operands, fp32 accumulate + fp32 master weights", data="synthetic",
+                config={"workload": f"full PPO train loop, {E} envs per GPU x T={T} control steps per iteration (N = {N} transitions per GPU), GAE + {TRAIN_EPOCHS} full-batch epochs "
+                                    "(value step + clipped-surrogate policy step, Adam), 657-2048-1024-512-{105,1} gelu nets, "
+                                    + ("10 AMASS-shaped clips with the take5_test_small lengths (BASELINE configs[2])" if world == 1 else
+                                       "24 synthetic clips in the occlusion_v2 class mix (normal/sitting/airborne), 3 body-shape variants (BASELINE configs[3]/[4] shapes)"),
+                        "envs_per_gpu": E, "global_envs": E * world, "global_batch": N * world,
+                        "parallelism": f"env-sharded x{world}; per optimisation step one all-reduce of each net's flat fp32 gradient tensor (NCCL), overlapped with the other net's backward; "
+                                       "advantage / ZFilter statistics ride in its tail; nothing else crosses GPUs",
+                        "l2": "not flushed: every iteration streams a 1.3 GB rollout buffer (inputs larger than L2)"},
+                phases=dict(sample_ms=sample_ms, update_ms=update_ms, gae_ms=phases["gae_ms"] / K, epochs_ms=phases["epochs_ms"] / K,
+                            allreduce_ms_per_iter=phases["allreduce_ms"] / K, allreduce_bytes_per_iter=phases["allreduce_bytes"] / K,
+                            allreduce_calls_per_iter=phases["allreduce_calls"] / K,
+                            allreduce_busbw_GBps=(phases["allreduce_bytes"] * 2 * (world - 1) / world / (phases["allreduce_ms"] * 1e-3) / 1e9) if phases["allreduce_ms"] > 0 else None),
+                replicas_identical=same, parameters=npar,
+                roofline=dict(bound="tensor", kernel="k_linear_tc (forward, dX, dW of both nets)", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                              peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 TFLOP/s",
+                              note="6 x parameters x N flop per epoch over the measured time of the 10 epochs (includes the activation-gradient / transpose / Adam kernels)"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=16,
+                         note="the training iteration has no host inputs (observations, rollout buffer and weights are device resident); the host reads back the two loss scalars"),
+                gpu_launches=(agent.engine.kernel_launches - l0), clocks=clk)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -299,9 +474,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rollout", choices=["rollout", "train"],
+                    help="rollout (default, the headline: BASELINE configs[1]) or train (configs[2] at N=1, configs[3]/[4] shapes at N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_gpu(args)
 

@@ -104,6 +104,9 @@ int uhc_env_set_state_batch(UhcEngine *e, int n, const int *env_ids_host, const 
  * generated models allocate nconmax 500, skeleton_mesh.py:46 -- such a step sets fail instead of continuing on a truncated contact
  * set), out4[1] = env-steps skipped because the env record was stale (clip table reloaded) or never reset (outputs: fail = end = 1). */
 int uhc_engine_counters(UhcEngine *e, int *out4);
+/* device array [E][2] written by every uhc_env_step: clip index of the episode that ended in that step (-1 = none) and its completed
+ * fraction `percent` as float bits -- what the reference appends to its per-clip success history (agent_copycat.py:561). */
+const int *uhc_episode_log_dev(const UhcEngine *e);
 int uhc_num_envs(const UhcEngine *e);
 int uhc_kernel_launches(const UhcEngine *e);   /* kernels launched by this engine so far (bench `gpu_launches`) */
 

@@ -43,8 +43,13 @@ int uhc_gaussian_logprob(const float *mean, const float *log_std, const float *a
  * inv_count = 1 / #selected rows; loss_acc (optional) accumulates the surrogate loss. */
 int uhc_ppo_policy_grad(const float *mean, const float *log_std, const float *action, const float *adv, const float *fixed_logp, const float *exps,
                         float clip_eps, float inv_count, float *dmean, float *loss_acc, int M, int A, void *stream);
-/* value loss gradient (agent_pg.py:18-25): L = mean (v - returns)^2 */
+/* the same with 1 / #selected rows of the GLOBAL batch read from device memory (env-sharded multi-GPU update: the count arrives with the
+ * gradient all-reduce, no host round trip) */
+int uhc_ppo_policy_grad_dev(const float *mean, const float *log_std, const float *action, const float *adv, const float *fixed_logp, const float *exps,
+                            float clip_eps, const float *inv_count_dev, float *dmean, float *loss_acc, int M, int A, void *stream);
+/* value loss gradient (agent_pg.py:18-25): L = mean (v - returns)^2 ; _n: M_total = rows of the global batch (shard gradients then sum to the mean) */
 int uhc_value_grad(const float *v, const float *ret, float *dv, float *loss_acc, int M, void *stream);
+int uhc_value_grad_n(const float *v, const float *ret, float *dv, float *loss_acc, int M, long M_total, void *stream);
 int uhc_sqsum(const float *x, long n, double *out_acc, void *stream);
 /* torch.optim.Adam step (agent_copycat.py:160-177) with optional clip_grad_norm_ scale from *sqnorm (agent_ppo.py:53-56). */
 int uhc_adam_step(float *p, const float *g, float *m, float *v, long n, float lr, float beta1, float beta2, float eps, int step,
@@ -54,6 +59,9 @@ int uhc_adam_step(float *p, const float *g, float *m, float *v, long n, float lr
 int uhc_gae(const float *rew, const float *mask, const float *val, const float *last_val, float gamma, float tau, float *adv, float *ret, int T, int E,
             void *stream);
 int uhc_normalize_advantages(float *adv, long n, double *scratch2, void *stream);   /* (A - mean) / std_unbiased, common.py:22 */
+/* the two halves of it for a batch sharded over GPUs: local (sum, sum sq) -> [ride the gradient all-reduce] -> normalise with global moments / count */
+int uhc_adv_moments(const float *adv, long n, double *out2, void *stream);
+int uhc_adv_normalize(float *adv, long n, const double *mom2_dev, const double *ntotal_dev, void *stream);
 
 /* ZFilter (khrylib/utils/zfilter.py:7-73): stats = [n, mean[D], S[D]] doubles; update!=0 merges the batch first. y may be NULL. */
 int uhc_zfilter(const float *x, float *y, int M, int D, double *stats, float clip, int update, void *stream);

@@ -45,7 +45,7 @@ static Emu<Real> *create(const UhcModelHost *m, const UhcEnvCfg *cfg, int E) {
     M.simp0 = (Real)m->solimp[0]; M.simp1 = (Real)m->solimp[1]; M.simp2 = (Real)m->solimp[2]; M.simp3 = (Real)m->solimp[3]; M.simp4 = (Real)m->solimp[4];
     M.gravz = (Real)m->gravz; M.nshape = 1; M.nvert = m->nvert;
     set_cfg(e->ev.cfg, cfg);
-    e->ev.clip_model = nullptr; e->ev.clip_cdf = nullptr; e->ev.counters = nullptr;
+    e->ev.clip_model = nullptr; e->ev.clip_cdf = nullptr; e->ev.counters = nullptr; e->ev.ep_log = nullptr;
     e->state.assign((size_t)E * ST_SIZE, 0); e->istate.assign((size_t)E * SI_SIZE, 0);
     e->ev.num_envs = E; e->ev.state = e->state.data(); e->ev.istate = e->istate.data();
     return e;

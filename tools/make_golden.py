@@ -243,6 +243,25 @@ def gen_sampler(cfg):
     np.savez_compressed(os.path.join(OUT, "sampler_hist.npz"), **out)
 
 
+def gen_metrics():
+    """smpl_eval.compute_metrics / p_mpjpe (uhc/smpllib/smpl_eval.py:24-123) on seeded inputs."""
+    from uhc.smpllib.smpl_eval import compute_metrics
+    rng = np.random.RandomState(8)
+    out = {}
+    for tag, T in (("a", 40), ("b", 7)):
+        gt = rng.normal(0, 0.3, (T, 76)); gt[:, 3:7] = rng.normal(size=(T, 4)); gt[:, 3:7] /= np.linalg.norm(gt[:, 3:7], axis=1, keepdims=True)
+        pred = gt + rng.normal(0, 0.02, (T, 76)); pred[:, 3:7] /= np.linalg.norm(pred[:, 3:7], axis=1, keepdims=True)
+        gj = rng.normal(0, 0.5, (T, 72)); pj = gj + rng.normal(0, 0.03, (T, 72))
+        res = {"pred": pred, "gt": gt, "pred_jpos": pj, "gt_jpos": gj, "percent": 1.0 if tag == "a" else 0.6, "fail_safe": False}
+        m = compute_metrics(res)
+        for k, v in res.items():
+            out[f"{tag}.in.{k}"] = np.asarray(v)
+        for k, v in m.items():
+            out[f"{tag}.out.{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+    print("metrics golden:", {k: np.mean(v) for k, v in m.items()})
+
+
 def gen_math():
     from uhc.utils import transformation as T
     from uhc.utils import math_utils as MU
@@ -286,6 +305,8 @@ def main():
         gen_ppo()
     if "ppo_real" in what:
         gen_ppo_real()
+    if "metrics" in what:
+        gen_metrics()
     if "sampler" in what:
         gen_sampler(H.make_cfg())
 

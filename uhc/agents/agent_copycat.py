@@ -75,6 +75,11 @@ class AgentCopycat:
             sync = make_nccl_grad_sync(world)
         assert cfg.obs_v == 2 and cfg.actor_type == "gauss" and cfg.reward_id in reward_func, \
             "the B200 engine implements obs_v 2 / gauss actor / world_rfc_implicit (SURVEY.md section 8f lists the other variants as next)"
+        # variants the batched engine does not implement must not be accepted silently
+        assert cfg.fix_std, "log_std is not a trained parameter in this engine (fix_std: true in every released config)"
+        assert cfg.get("env_term_body", "body") == "body", "env_term_body: only 'body' (calc_body_diff) is implemented"
+        assert cfg.residual_force and cfg.get("residual_force_mode", "implicit") == "implicit", "only the implicit residual force is implemented"
+        assert float(cfg.get("env_init_noise", 0.0)) == 0.0, "env_init_noise > 0 is not implemented"
         self.agent = BatchedAgent(
             self.num_envs, self.data_loader.experts, self.data_loader.shapes, device=dev_index, seed=cfg.seed, policy_hsize=cfg.policy_hsize,
             value_hsize=cfg.value_hsize, htype=cfg.policy_htype, log_std=cfg.log_std, policy_lr=cfg.policy_lr, value_lr=cfg.value_lr,
@@ -110,9 +115,29 @@ class AgentCopycat:
     def sample(self, min_batch_size=None):
         T = self.horizon if min_batch_size is None else max(2, int(math.ceil(min_batch_size / self.num_envs)))
         buf, log = self.agent.sample(T)
+        self._update_freq_dict(buf)
         log = _Log(log)
         log.update(avg_c_reward=log["avg_reward"], avg_episode_c_reward=log["avg_episode_reward"])
         return _Batch(buf), log
+
+    def _update_freq_dict(self, buf):
+        """per-clip success history from the episodes that ended in this rollout ([percent, fr_start] per episode, agent_copycat.py:561,
+        590-603, capped at max_freq entries), then the device sampler's weights (dataset_amass_single.py:183-186)."""
+        clip = buf.ep_clip.cpu().numpy().reshape(-1)
+        pct = buf.ep_pct.cpu().numpy().reshape(-1)
+        sel = clip >= 0
+        keys = self.data_loader.data_keys
+        for c, p in zip(clip[sel], pct[sel]):
+            self.freq_dict[keys[c]].append([float(p), 0])
+        self.freq_dict = {k: v[-self.max_freq:] for k, v in self.freq_dict.items()}
+        self._push_clip_weights()
+
+    def _push_clip_weights(self):
+        from uhc_b200.agent import failure_weights
+        cfg = self.cfg
+        hist = [[r[0] for r in self.freq_dict[k]] for k in self.data_loader.data_keys]
+        if any(len(h) for h in hist):
+            self.agent.engine.set_clip_weights(failure_weights(hist, cfg.get("sampling_temp", 0.2), cfg.get("sampling_freq", 0.5)))
 
     def update_params(self, batch):
         return self.agent.update_params(batch.buf)["update_time"]
@@ -149,25 +174,32 @@ class AgentCopycat:
 
     # ---------------------------------------------------------------- evaluation (:354-494), batched: one env per clip
     def eval_policy(self, epoch=0, dump=False):
+        """eval_policy / eval_seq (agent_copycat.py:354-494) for every clip at once: env i imitates clip c0 + i from frame 0 with the
+        deterministic policy; per step ONE batched state read (uhc_env_get_state_batch) feeds the reference's metrics
+        (smpl_eval.compute_metrics: mpjpe / pa-mpjpe / accel / vel / root distance, restated in uhc_b200/metrics.py); fail_safe re-seats a
+        failed humanoid on the expert pose with one batched set_state (humanoid_im.py:902-905)."""
         import torch
+        from uhc_b200.metrics import compute_metrics
         cfg = self.cfg
         res_dicts = []
+        eng = self.agent.engine
+        E = self.num_envs
         for loader in self.test_data_loaders:
-            ag = self.agent if loader is self.data_loader else None
-            eng = self.agent.engine
             n = loader.get_len()
             if loader is not self.data_loader:
-                eng.load_clips(loader.experts, loader.shapes)
-            E = self.num_envs
+                eng.load_clips(loader.experts, loader.shapes)      # invalidates every env record: only the envs reset below are stepped
+            eng.set_cfg(**self._env_cfg(test=True))
             res = {}
             for c0 in range(0, n, E):
                 ids = np.arange(min(E, n - c0), dtype=np.int32)
                 clips = (c0 + ids).astype(np.int32)
-                eng.set_cfg(**self._env_cfg(test=True))
+                if len(ids) < E:                                   # idle envs: park them on clip c0 so every record is valid (their outputs are ignored)
+                    eng.reset(np.arange(len(ids), E, dtype=np.int32), np.full(E - len(ids), c0, np.int32), 0, None)
                 obs = eng.reset(ids, clips, 0, None)
                 lens = eng.clip_len[clips]
                 alive = np.ones(len(ids), bool); fail_any = np.zeros(len(ids), bool)
-                rsum, jerr, rdist, cnt = (np.zeros(len(ids)) for _ in range(4))
+                rsum = np.zeros(len(ids)); last_t = np.zeros(len(ids), np.int64)
+                traj = [dict(pred=[], pred_jpos=[], t=[]) for _ in ids]
                 det = torch.ones(E, dtype=torch.uint8, device=obs.device)
                 for t in range(int(lens.max()) - 1):
                     s = self.running_state(obs, update=False)
@@ -175,38 +207,45 @@ class AgentCopycat:
                     a, _ = nn.gaussian_sample(mean, self.agent.log_std, 0, 0, det)
                     obs, rew, ci, fail, end, pct = eng.step(a)
                     f, e, r = fail.cpu().numpy()[ids] != 0, end.cpu().numpy()[ids] != 0, rew.cpu().numpy()[ids]
-                    for i in np.nonzero(alive)[0]:
-                        st = eng.get_state(int(i)) if (t % 10 == 0 or f[i] or e[i]) else None
-                        if st is not None:
-                            ex = loader.experts[clips[i]]
-                            tt = min(st["cur_t"], ex["len"] - 1)
-                            jerr[i] += np.linalg.norm(st["xpos"] - ex["wbpos"][tt].reshape(24, 3), axis=1).mean() * 1000
-                            rdist[i] += np.linalg.norm(st["qpos"][:3] - ex["qpos"][tt][:3]); cnt[i] += 1
-                        rsum[i] += r[i]
-                        if f[i]:
-                            fail_any[i] = True
-                            if cfg.fail_safe:
-                                ex = loader.experts[clips[i]]
-                                tt = min(t + 1, ex["len"] - 1)
-                                eng.set_state(int(i), ex["qpos"][tt], ex["qvel"][tt])
-                            else:
-                                alive[i] = False
-                        if e[i]:
-                            alive[i] = False
+                    live = np.nonzero(alive)[0]
+                    st = eng.get_states(ids[live])
+                    for j, i in enumerate(live):
+                        traj[i]["pred"].append(st["qpos"][j].copy()); traj[i]["pred_jpos"].append(st["xpos"][j].reshape(-1).copy()); traj[i]["t"].append(int(st["cur_t"][j]))
+                        last_t[i] = st["cur_t"][j]
+                    rsum[live] += r[live]
+                    failed = live[f[live]]
+                    fail_any[failed] = True
+                    if len(failed):
+                        if cfg.fail_safe:
+                            tt = [min(int(last_t[i]), loader.experts[clips[i]]["len"] - 1) for i in failed]
+                            eng.set_states(ids[failed], np.stack([loader.experts[clips[i]]["qpos"][k] for i, k in zip(failed, tt)]),
+                                           np.stack([loader.experts[clips[i]]["qvel"][k] for i, k in zip(failed, tt)]))
+                        else:
+                            alive[failed] = False
+                    alive[live[e[live]]] = False
                     if not alive.any():
                         break
                 for i in ids:
                     k = loader.data_keys[c0 + i]
-                    res[k] = {"succ": [not fail_any[i]], "reward": rsum[i] / max(lens[i] - 1, 1), "mpjpe_g": jerr[i] / max(cnt[i], 1),
-                              "root_dist": rdist[i] / max(cnt[i], 1), "percent": 1.0}
-                    if k in self.freq_dict:
-                        self.freq_dict[k] += [[res[k]["succ"][0], 0]] * (1 if res[k]["succ"][0] else 3)
-                        self.freq_dict[k] = self.freq_dict[k][-self.max_freq:]
+                    ex = loader.experts[clips[i]]
+                    tt = np.minimum(np.array(traj[i]["t"], dtype=np.int64), ex["len"] - 1)
+                    percent = float(last_t[i]) / float(max(lens[i] - 1, 1))
+                    r_i = {"pred": np.array(traj[i]["pred"]), "gt": np.asarray(ex["qpos"])[tt], "pred_jpos": np.array(traj[i]["pred_jpos"]),
+                           "gt_jpos": np.asarray(ex["wbpos"])[tt], "percent": 1.0 if (percent >= 1.0 and not fail_any[i]) else min(percent, 0.999),
+                           "fail_safe": bool(fail_any[i] and cfg.fail_safe)}
+                    m = compute_metrics(r_i) if len(tt) >= 3 else {"succ": np.array([False])}
+                    m["succ"] = np.array([bool(m["succ"][0]) and not fail_any[i]])
+                    m["reward"] = rsum[i] / max(lens[i] - 1, 1)
+                    m["percent"] = percent
+                    res[k] = m
+                    if k in self.freq_dict:      # eval outcome feeds the failure-weighted sampler like a training episode ([percent, fr_start])
+                        self.freq_dict[k] = (self.freq_dict[k] + [[1.0 if m["succ"][0] else min(percent, 0.999), 0]])[-self.max_freq:]
             if loader is not self.data_loader:
                 eng.load_clips(self.data_loader.experts, self.data_loader.shapes)
             eng.set_cfg(**self._env_cfg(test=False))
             self.agent.obs = None
-            metrics = {m: float(np.mean([np.mean(r[m]) for r in res.values()])) for m in ("succ", "reward", "mpjpe_g", "root_dist")}
+            names = ("succ", "reward", "mpjpe", "mpjpe_g", "pa_mpjpe", "accel_dist", "vel_dist", "root_dist")
+            metrics = {m: float(np.mean([np.mean(r[m]) for r in res.values() if m in r])) if any(m in r for r in res.values()) else float("nan") for m in names}
             coverage = int(round(metrics["succ"] * n))
             self.logger.info(f"Coverage {loader.name} of {coverage} out of {n} | " + " \t".join(f"{k}: {v:.3f}" for k, v in metrics.items()))
             metrics.update(mean_coverage=coverage / n, num_coverage=coverage, all_coverage=n)
@@ -215,6 +254,7 @@ class AgentCopycat:
             if dump:
                 path = osp.join(cfg.output_dir, f"{epoch}_{loader.name}_coverage_full.pkl")
                 joblib.dump(res, path)
+        self._push_clip_weights()
         return res_dicts
 
     def _env_cfg(self, test):
@@ -235,10 +275,14 @@ class AgentCopycat:
 
     # ---------------------------------------------------------------- checkpoints (:190-260)
     def save_checkpoint(self, epoch):
+        """pickle {"policy_dict", "value_dict", "running_state": ZFilter} (agent_copycat.py:190-201).  Multi-GPU: every rank holds identical
+        weights and running_state (uhc_b200/agent.py update_params), so rank 0 alone writes the file."""
         cfg = self.cfg
         path = "%s/iter_%04d.p" % (cfg.model_dir, epoch + 1)
-        pickle.dump(self.agent.state_dicts(), open(path, "wb"))
-        joblib.dump(self.freq_dict, osp.join(cfg.result_dir, "freq_dict.pt"))
+        if int(os.environ.get("RANK", "0")) == 0:
+            with open(path, "wb") as f:
+                pickle.dump(self.agent.state_dicts(), f)
+            joblib.dump(self.freq_dict, osp.join(cfg.result_dir, "freq_dict.pt"))
         return path
 
     def load_checkpoint(self, epoch):

@@ -6,14 +6,22 @@ by E device-resident environments stepped in lock-step: per control step one obs
 in HBM.  Episode semantics follow Appendix C of SURVEY.md: an env that fails or reaches the end of its clip slice gets
 mask 0 and is re-seeded with a freshly sampled (clip, start) slice (dataset_amass_single.py:172-253); rollouts cut mid-episode
 are bootstrapped with V(s_T) (the reference never truncates, so this is the one semantic addition, documented in DESIGN.md).
-Multi-GPU: envs are sharded, one process per GPU; `grad_sync` all-reduces the flat gradients once per optimisation step.
+Multi-GPU: envs are sharded, one process per GPU; the flat gradient tensor of each net is all-reduced once per optimisation step
+(nn.GradComm, overlapped with the other net's backward); nothing else crosses GPUs.
 """
+import ctypes as C
 import time
 
 import numpy as np
 
 from . import nn
 from .engine import ACT_DIM, OBS_DIM, Engine
+
+
+class UhcRolloutBuf(C.Structure):
+    """include/uhc_rollout.h UhcRolloutBuf"""
+    _fields_ = [(k, C.c_void_p) for k in ("states", "actions", "rewards", "masks", "exps", "logp", "fails", "obs_cur", "ep_clip", "ep_pct")] + \
+               [("T_cap", C.c_int), ("reserved", C.c_int)]
 
 
 def ewma(x, alpha=0.05):
@@ -71,6 +79,15 @@ class RolloutBuffer:
         self.last_obs = torch.empty(E, OBS_DIM, **f)
         self.last_alive = torch.empty(E, **f)
         self.fails = torch.zeros(T, E, device=device, dtype=torch.int32)
+        self.ep_clip = torch.full((T, E), -1, device=device, dtype=torch.int32)      # clip of the episode that ended at (t, e), -1 = none
+        self.ep_pct = torch.zeros(T, E, **f)                                         # its completed fraction (info["percent"])
+
+    def c_struct(self, obs_cur):
+        b = UhcRolloutBuf()
+        for k in ("states", "actions", "rewards", "masks", "exps", "logp", "fails", "ep_clip", "ep_pct"):
+            setattr(b, k, getattr(self, k).data_ptr())
+        b.obs_cur, b.T_cap = obs_cur.data_ptr(), self.T
+        return b
 
     # TrajBatch-compatible flat views (khrylib/rl/core/trajbatch.py)
     def flat(self, name):
@@ -97,7 +114,8 @@ class BatchedAgent:
         self.value = nn.MLPNet(OBS_DIM, value_hsize, 1, htype, device=self.dev, head_name="value_head", seed=seed + 1)
         self.log_std = torch.full((ACT_DIM,), float(log_std), device=self.dev, dtype=torch.float32)
         self.running_state = nn.ZFilter(OBS_DIM, clip=5.0, device=self.dev)
-        self.opt_p, self.opt_v = nn.Adam(self.policy.params(), policy_lr), nn.Adam(self.value.params(), value_lr)
+        self.opt_p, self.opt_v = nn.Adam(self.policy.params(), policy_lr, net=self.policy), nn.Adam(self.value.params(), value_lr, net=self.value)
+        self.comm = nn.GradComm(world)
         self.gamma, self.tau, self.clip_epsilon, self.epochs, self.grad_clip = gamma, tau, clip_epsilon, num_optim_epoch, grad_clip
         self.noise_rate, self.grad_sync, self.update_tc = noise_rate, grad_sync, update_tc
         self.global_step = 0
@@ -147,16 +165,45 @@ class BatchedAgent:
         if ids.numel():
             self.reset_envs(ids.cpu().numpy().astype(np.int32))
 
-    def sample(self, T, buf=None, use_tc=True):
-        """agent.sample(): T lock-step control steps of all envs.  Returns (buffer, log)."""
+    def rollout(self, buf, T, row0=0, use_graph=True):
+        """T control steps through the C-side loop (uhc_rollout, include/uhc_rollout.h): the same kernels as step_once, enqueued from C and
+        replayed as one CUDA graph.  Needs auto_reset (finished episodes are re-seeded inside the step kernel)."""
+        assert self.auto_reset, "uhc_rollout re-seeds finished episodes in the step kernel: build the agent with auto_reset=True"
+        L = self.engine.lib
+        if not getattr(self, "_ro_ready", False):
+            L.uhc_rollout_last_error.restype = C.c_char_p
+            self._ro_ready = True
+        if self.policy._bf16 is None or getattr(self, "_mlp_c", None) is None:
+            self._mlp_c = nn.mlp_struct(self.policy)
+        if getattr(self, "_ro_step", None) != self.global_step:
+            L.uhc_rollout_set_step(self.engine.h, C.c_ulonglong(self.global_step))
+        bs = buf.c_struct(self.obs)
+        st = C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+        rc = L.uhc_rollout(self.engine.h, C.c_int(T), C.c_int(row0), C.byref(self._mlp_c), C.c_void_p(self.log_std.data_ptr()),
+                           C.c_void_p(self.running_state.stats.data_ptr()), C.c_float(self.running_state.clip), C.c_int(1),
+                           C.c_ulonglong(self.seed * 1000003 + self.rank), C.c_float(self.noise_rate), C.byref(bs), C.c_int(int(use_graph)), st)
+        if rc != 0:
+            raise RuntimeError("uhc_rollout: " + L.uhc_rollout_last_error().decode())
+        self.global_step += T
+        self._ro_step = self.global_step
+        self.nn_launches += T * (L.uhc_rollout_launches_per_step(self.engine.h) - 1)      # the env-step launch is counted by the engine
+
+    def sample(self, T, buf=None, use_tc=True, c_loop=None):
+        """agent.sample(): T lock-step control steps of all envs.  Returns (buffer, log).  c_loop (default: whenever auto_reset is on):
+        the loop runs behind the C ABI as one CUDA graph; otherwise the Python loop over step_once (identical kernels and results)."""
         t = self.torch
         if self.obs is None:
             self.reset_envs()
         buf = buf or RolloutBuffer(T, self.E, self.dev)
         t0 = time.time()
         len0, ret0 = self.ep_len.clone(), self.ep_ret.clone()
-        for k in range(T):
-            self.step_once(buf, k, use_tc)
+        if c_loop is None:
+            c_loop = self.auto_reset and use_tc
+        if c_loop:
+            self.rollout(buf, T)
+        else:
+            for k in range(T):
+                self.step_once(buf, k, use_tc)
         buf.last_obs.copy_(self.obs)
         # episode statistics from the buffer (one sync at the end of the rollout): segment the [T][E] masks per env
         m, r = buf.masks[:T], buf.rewards[:T]
@@ -178,33 +225,78 @@ class BatchedAgent:
         return buf, log
 
     def update_params(self, buf):
-        """AgentPG.update_params (agent_pg.py:39-56): V(s), GAE (+bootstrap), advantage normalisation, PPO epochs."""
+        """AgentPG.update_params (agent_pg.py:39-56): V(s), GAE (+bootstrap), advantage normalisation, PPO epochs -- all on the
+        tensor-core path.  Multi-GPU (envs sharded by rank): the ONLY collective is the all-reduce of the flat gradient tensors; the
+        global-batch statistics the reference's full-batch semantics need (advantage sum / sum of squares / count, the number of
+        selected rows, the ZFilter increments of every rank) ride in the tail of the first one."""
         t = self.torch
-        t0 = time.time()
+        L = nn._lib()
+        ev = [t.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
         T, E = buf.T, buf.E
+        N = T * E
         states = buf.flat("states")
-        values = self.value.forward(states).reshape(T, E)
-        last_v = self.value.forward(self.running_state(buf.last_obs, update=False)).reshape(E)
-        adv, ret = nn.gae(buf.rewards, buf.masks, values, last_v, self.gamma, self.tau, normalize=True)
-        if self.grad_sync is not None:
-            self._wrap_sync()
-        losses = nn.ppo_update(self.policy, self.value, self.log_std, self.opt_p, self.opt_v, states, buf.flat("actions"), ret.reshape(-1),
-                               adv.reshape(-1), buf.flat("exps"), self.clip_epsilon, self.epochs, self.grad_clip, use_tc=self.update_tc)
+        if not self.update_tc:               # fp32 SIMT parity path (single GPU)
+            t0 = time.time()
+            values = self.value.forward(states).reshape(T, E)
+            last_v = self.value.forward(self.running_state(buf.last_obs, update=False)).reshape(E)
+            adv, ret = nn.gae(buf.rewards, buf.masks, values, last_v, self.gamma, self.tau, normalize=True)
+            losses = nn.ppo_update(self.policy, self.value, self.log_std, self.opt_p, self.opt_v, states, buf.flat("actions"), ret.reshape(-1),
+                                   adv.reshape(-1), buf.flat("exps"), self.clip_epsilon, self.epochs, self.grad_clip, use_tc=False)
+            t.cuda.synchronize()
+            self._mlp_c = None
+            return dict(update_time=time.time() - t0, surr_loss=float(losses[0]), value_loss=float(losses[1]))
+        tp = getattr(self.policy, "_tc_trainer", None) or nn.TCTrainer(self.policy)
+        tv = getattr(self.value, "_tc_trainer", None) or nn.TCTrainer(self.value)
+        self.policy._tc_trainer, self.value._tc_trainer = tp, tv
+        xb, xT = tp.prepare_input(states)
+        tv.cache["xb"], tv.cache["xT"] = xb, xT
+        v0, ctx0 = tv.forward(xb)                                                   # V(s): GAE input and epoch 0's value forward
+        last_v = self.value.forward_tc(self.running_state(buf.last_obs, update=False)).reshape(E)
+        adv, ret = nn.gae(buf.rewards, buf.masks, v0.reshape(T, E), last_v, self.gamma, self.tau, normalize=False)
+        adv, ret, exps = adv.reshape(-1), ret.reshape(-1), buf.flat("exps")
+        mom = t.zeros(2, device=self.dev, dtype=t.float64)
+        nn._chk(L.uhc_adv_moments(nn._p(adv), C.c_long(N), nn._p(mom), nn._stream(adv)))
+        cnt = (exps != 0).sum().to(t.float64).reshape(1)
+        inv_count = t.zeros(1, device=self.dev, dtype=t.float32)
+        after = None
+        if self.world <= 1:
+            nn._chk(L.uhc_adv_normalize(nn._p(adv), C.c_long(N), nn._p(mom), None, nn._stream(adv)))
+            inv_count.copy_(1.0 / t.clamp(cnt, min=1.0))
+        else:
+            D = OBS_DIM
+            zs = self.running_state.stats
+            if getattr(self, "_z_sync", None) is None:                               # fresh agent: every rank starts from empty statistics
+                self._z_sync = t.zeros_like(zs)                                      # additive form of the statistics every rank agreed on last
+            d = t.cat([mom, t.full((1,), float(N), device=self.dev, dtype=t.float64), cnt, nn.zfilter_to_sums(zs, D) - self._z_sync])
+            hi, lo = nn.split_double(d)
+            tail = self.value.gfull[self.value.nflat:]
+            tail.zero_()
+            nd = d.numel()
+            tail[:nd].copy_(hi); tail[nd:2 * nd].copy_(lo)
+            ntot = t.zeros(1, device=self.dev, dtype=t.float64)
+
+            def after(tail_r):
+                g = nn.join_double(tail_r[:nd], tail_r[nd:2 * nd])                   # summed over the ranks by the gradient all-reduce
+                ntot.copy_(g[2:3])
+                gm = g[0:2].contiguous()
+                nn._chk(L.uhc_adv_normalize(nn._p(adv), C.c_long(N), nn._p(gm), nn._p(ntot), nn._stream(adv)))
+                inv_count.copy_(1.0 / t.clamp(g[3:4], min=1.0))
+                self._z_sync = self._z_sync + g[4:]
+                zs.copy_(nn.zfilter_from_sums(self._z_sync, D))                     # every rank now holds the same running_state
+        ev[1].record()
+        losses = nn.ppo_epochs_tc(self.policy, self.value, self.log_std, self.opt_p, self.opt_v, xb, xT, buf.flat("actions"), ret, adv, exps,
+                                  self.clip_epsilon, self.epochs, self.grad_clip, comm=self.comm, first_value=(v0, ctx0), after_first_reduce=after,
+                                  inv_count_dev=inv_count, world=self.world)
+        ev[2].record()
         t.cuda.synchronize()
-        return dict(update_time=time.time() - t0, surr_loss=float(losses[0]), value_loss=float(losses[1]))
-
-    def _wrap_sync(self):
-        """one all-reduce of the flat gradient buffer per optimisation step."""
-        if getattr(self, "_sync_wrapped", False):
-            return
-        sync = self.grad_sync
-        for opt in (self.opt_p, self.opt_v):
-            raw = opt.step
-
-            def stepper(grads, max_norm=None, _raw=raw):
-                _raw(sync(grads), max_norm=max_norm)
-            opt.step = stepper
-        self._sync_wrapped = True
+        self._mlp_c = None
+        out = dict(update_time=1e-3 * ev[0].elapsed_time(ev[2]), gae_ms=ev[0].elapsed_time(ev[1]), epochs_ms=ev[1].elapsed_time(ev[2]),
+                   surr_loss=float(losses[0]), value_loss=float(losses[1]))
+        if self.world > 1:
+            out.update(allreduce_ms=self.comm.pop_ms(), allreduce_bytes=self.comm.bytes, allreduce_calls=self.comm.calls)
+            self.comm.bytes = self.comm.calls = 0
+        return out
 
     def optimize_policy(self, T):
         buf, log = self.sample(T)
@@ -215,8 +307,13 @@ class BatchedAgent:
     def state_dicts(self):
         pd = self.policy.state_dict()
         pd["action_log_std"] = self.log_std.detach().cpu().reshape(1, -1)
+        # `running_state` in the reference's wire format: a ZFilter object (agent_copycat.py:194-200 pickles the object itself and
+        # load_checkpoint assigns it back, :249-260), filled from the device statistics
+        from uhc.khrylib.utils.zfilter import ZFilter as HostZFilter
+        st = self.running_state.stats.cpu().numpy()
+        D = self.running_state.dim
         return {"policy_dict": pd, "value_dict": self.value.state_dict(),
-                "running_state": {"n": self.running_state.n, "mean": self.running_state.mean, "std": self.running_state.std, "clip": 5.0}}
+                "running_state": HostZFilter.from_stats(st[0], st[1:1 + D], st[1 + D:], clip=self.running_state.clip)}
 
     def load_state_dicts(self, cp):
         t = self.torch
@@ -226,10 +323,12 @@ class BatchedAgent:
             self.log_std.copy_(t.as_tensor(np.asarray(cp["policy_dict"]["action_log_std"]), dtype=t.float32).reshape(-1))
         rs = cp.get("running_state")
         if rs is not None:
-            if isinstance(rs, dict):
+            if isinstance(rs, dict):          # round-1 checkpoints of this repo
                 self.running_state.load(rs["n"], rs["mean"], rs["std"])
-            else:  # a pickled khrylib ZFilter
-                self.running_state.load(rs.rs.n, rs.rs.mean, rs.rs.std)
+            else:                             # a pickled khrylib ZFilter (reference checkpoints and this repo's)
+                self.running_state.load_sums(rs.rs._n, rs.rs._M, rs.rs._S)
+            # a loaded normaliser is common to every rank: the cross-rank merge (update_params) only exchanges what is added from here on
+            self._z_sync = nn.zfilter_to_sums(self.running_state.stats, self.running_state.dim).clone()
 
 
 def make_nccl_grad_sync(world):

@@ -20,6 +20,8 @@ struct EngineView {
     const Real *clip_shape; // [C][17] beta[16], gender
     const int *clip_model;  // [C] body-shape (model variant) of each clip: the reference rebuilds the robot per clip (humanoid_im.py:154-180)
     const float *clip_cdf;  // [C] cumulative sampling weights (len // t_max + 1 copies per clip, sample_keys of the reference)
+    int *ep_log;            // [E][2] per env: clip index of the episode that ended in the last step (-1: none ended) and its completed fraction (float bits)
+                            //   -- the training loop's per-clip success history (agent_copycat.py:561) is built from it
     int *counters;          // [4] device counters: 0 = env-steps failed because a body's contacts did not fit MAXCON, 1 = env-steps skipped on an invalid env record
 };
 
@@ -205,6 +207,15 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
         if (fail_out) *fail_out = fail;
         if (end_out) *end_out = end;
         if (percent_out) *percent_out = (ObsT)((Real)cur_t / (Real)(len - 1));
+        if (ev.ep_log) {
+            const float pctf = (float)((Real)cur_t / (Real)(len - 1));
+            ev.ep_log[2 * env] = (fail || end) ? clip : -1;
+#ifndef UHC_EMU
+            ev.ep_log[2 * env + 1] = __float_as_int(pctf);
+#else
+            union { float f; int i; } cv; cv.f = pctf; ev.ep_log[2 * env + 1] = cv.i;
+#endif
+        }
     }
     if (cinfo_out && lane < 5) cinfo_out[lane] = (ObsT)ci[lane];
     LANES_END

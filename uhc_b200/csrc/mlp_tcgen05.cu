@@ -372,10 +372,11 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
                           int M, int N, int Kp, int ldy_bf16, int act, void *stream) {
     if (Kp % BK != 0 || M <= 0 || N <= 0) { g_tc_err = "uhc_linear_forward_tc: Kp must be a positive multiple of 64"; return -2; }
     if (y_bf16_or_null && (ldy_bf16 % 8 != 0)) { g_tc_err = "uhc_linear_forward_tc: ldy must be a multiple of 8"; return -2; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};   // per device: the attribute belongs to the function on the CURRENT device
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         if (cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute failed"; return -1; }
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     CUtensorMap ma, mb;
     if (make_map(&ma, x_bf16, M, Kp, BM) || make_map(&mb, W_bf16, N, Kp, BN)) return -1;
@@ -413,7 +414,7 @@ int uhc_transpose_bf16(const void *in, void *out, int R, int Cc, int ld_in, int 
 }
 int uhc_dact_bf16(const float *dh, const float *z_or_null, void *dz_bf16, void *dzT_bf16, float *db_or_null, int M, int N, int ld_dz, int ld_dzT, int act,
                   void *stream) {
-    if (db_or_null) cudaMemsetAsync(db_or_null, 0, N * sizeof(float), (cudaStream_t)stream);
+    if (db_or_null && cudaMemsetAsync(db_or_null, 0, N * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "uhc_dact_bf16: memset failed"; return -1; }
     dim3 grid((N + 63) / 64, (M + 63) / 64);
     const bool v4 = N % 4 == 0 && (!dz_bf16 || (ld_dz % 4 == 0 && ((uintptr_t)dz_bf16 & 7) == 0)) && (!dzT_bf16 || (ld_dzT % 4 == 0 && ((uintptr_t)dzT_bf16 & 7) == 0)) &&
                     ((uintptr_t)dh & 15) == 0 && (!z_or_null || ((uintptr_t)z_or_null & 15) == 0);

@@ -169,9 +169,10 @@ __global__ void k_gauss_logprob(const float *__restrict__ mean, const float *__r
 // Writes dL/dmean [M][A] (zero rows where exps == 0) and accumulates the loss and the selected-row count.
 __global__ void k_ppo_grad(const float *__restrict__ mean, const float *__restrict__ log_std, const float *__restrict__ action,
                            const float *__restrict__ adv, const float *__restrict__ fixed_logp, const float *__restrict__ exps, float clip_eps,
-                           float inv_count, float *__restrict__ dmean, float *__restrict__ loss_acc, int M, int A) {
+                           float inv_count, float *__restrict__ dmean, float *__restrict__ loss_acc, int M, int A, const float *__restrict__ inv_count_dev) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
+    if (inv_count_dev) inv_count = *inv_count_dev;   // 1 / #selected rows of the GLOBAL batch, produced on the device (multi-GPU: after the all-reduce)
     const bool sel = exps[row] != 0.f;
     float lp = 0.f;
     for (int d = lane; d < A; d += 32) {
@@ -190,9 +191,9 @@ __global__ void k_ppo_grad(const float *__restrict__ mean, const float *__restri
     if (lane == 0 && sel && loss_acc) atomicAdd(loss_acc, -fminf(s1, s2) * inv_count);
 }
 // value loss (agent_pg.py:18-25): L = mean (v - ret)^2 ; dv = 2 (v - ret) / M
-__global__ void k_value_grad(const float *__restrict__ v, const float *__restrict__ ret, float *__restrict__ dv, float *__restrict__ loss_acc, int M) {
-    float s = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) { const float d = v[i] - ret[i]; dv[i] = 2.f * d / M; s += d * d / M; }
+__global__ void k_value_grad(const float *__restrict__ v, const float *__restrict__ ret, float *__restrict__ dv, float *__restrict__ loss_acc, int M, float Mtot) {
+    float s = 0.f;   // Mtot: rows of the GLOBAL batch (= M on one GPU): the gradients of the shards then SUM to the full-batch mean gradient
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) { const float d = v[i] - ret[i]; dv[i] = 2.f * d / Mtot; s += d * d / Mtot; }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0 && loss_acc) atomicAdd(loss_acc, s);
 }
@@ -241,8 +242,9 @@ __global__ void k_moments(const float *__restrict__ x, size_t n, double *__restr
     for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
     if ((threadIdx.x & 31) == 0) { atomicAdd(out2, s); atomicAdd(out2 + 1, q); }
 }
-__global__ void k_normalize(float *__restrict__ x, size_t n, const double *__restrict__ mom) {
-    const double mean = mom[0] / (double)n, var = (mom[1] - (double)n * mean * mean) / (double)(n - 1);
+__global__ void k_normalize(float *__restrict__ x, size_t n, const double *__restrict__ mom, const double *__restrict__ ntot_dev) {
+    const double N = ntot_dev ? *ntot_dev : (double)n;    // elements behind the moments (the global batch when they were all-reduced)
+    const double mean = mom[0] / N, var = (mom[1] - N * mean * mean) / (N - 1.0);
     const float mu = (float)mean, inv = (float)(1.0 / sqrt(var));
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = (x[i] - mu) * inv;
 }
@@ -306,11 +308,20 @@ int uhc_gaussian_logprob(const float *mean, const float *log_std, const float *a
 }
 int uhc_ppo_policy_grad(const float *mean, const float *log_std, const float *action, const float *adv, const float *fixed_logp, const float *exps,
                         float clip_eps, float inv_count, float *dmean, float *loss_acc, int M, int A, void *stream) {
-    k_ppo_grad<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(mean, log_std, action, adv, fixed_logp, exps, clip_eps, inv_count, dmean, loss_acc, M, A);
+    k_ppo_grad<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(mean, log_std, action, adv, fixed_logp, exps, clip_eps, inv_count, dmean, loss_acc, M, A, nullptr);
+    CKN(cudaGetLastError()); return 0;
+}
+int uhc_ppo_policy_grad_dev(const float *mean, const float *log_std, const float *action, const float *adv, const float *fixed_logp, const float *exps,
+                            float clip_eps, const float *inv_count_dev, float *dmean, float *loss_acc, int M, int A, void *stream) {
+    if (!inv_count_dev) { g_nn_err = "uhc_ppo_policy_grad_dev: inv_count_dev is null"; return -2; }
+    k_ppo_grad<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(mean, log_std, action, adv, fixed_logp, exps, clip_eps, 0.f, dmean, loss_acc, M, A, inv_count_dev);
     CKN(cudaGetLastError()); return 0;
 }
 int uhc_value_grad(const float *v, const float *ret, float *dv, float *loss_acc, int M, void *stream) {
-    k_value_grad<<<592, 256, 0, (cudaStream_t)stream>>>(v, ret, dv, loss_acc, M); CKN(cudaGetLastError()); return 0;
+    k_value_grad<<<592, 256, 0, (cudaStream_t)stream>>>(v, ret, dv, loss_acc, M, (float)M); CKN(cudaGetLastError()); return 0;
+}
+int uhc_value_grad_n(const float *v, const float *ret, float *dv, float *loss_acc, int M, long M_total, void *stream) {
+    k_value_grad<<<592, 256, 0, (cudaStream_t)stream>>>(v, ret, dv, loss_acc, M, (float)M_total); CKN(cudaGetLastError()); return 0;
 }
 int uhc_sqsum(const float *x, long n, double *out_acc, void *stream) {
     k_sqsum<<<592, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, out_acc); CKN(cudaGetLastError()); return 0;
@@ -329,7 +340,19 @@ int uhc_normalize_advantages(float *adv, long n, double *scratch2, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     CKN(cudaMemsetAsync(scratch2, 0, 2 * sizeof(double), st));
     k_moments<<<592, 256, 0, st>>>(adv, (size_t)n, scratch2); CKN(cudaGetLastError());
-    k_normalize<<<592, 256, 0, st>>>(adv, (size_t)n, scratch2); CKN(cudaGetLastError());
+    k_normalize<<<592, 256, 0, st>>>(adv, (size_t)n, scratch2, nullptr); CKN(cudaGetLastError());
+    return 0;
+}
+// the two halves of the same normalisation, for a batch sharded over GPUs: local (sum, sum of squares) -> [all-reduce] -> normalise with
+// the global moments and the global element count (both read from device memory: no host round trip between the collective and the kernel)
+int uhc_adv_moments(const float *adv, long n, double *out2, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CKN(cudaMemsetAsync(out2, 0, 2 * sizeof(double), st));
+    k_moments<<<592, 256, 0, st>>>(adv, (size_t)n, out2); CKN(cudaGetLastError());
+    return 0;
+}
+int uhc_adv_normalize(float *adv, long n, const double *mom2_dev, const double *ntotal_dev, void *stream) {
+    k_normalize<<<592, 256, 0, (cudaStream_t)stream>>>(adv, (size_t)n, mom2_dev, ntotal_dev); CKN(cudaGetLastError());
     return 0;
 }
 int uhc_zfilter(const float *x, float *y, int M, int D, double *stats, float clip, int update, void *stream) {

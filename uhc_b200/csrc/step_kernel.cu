@@ -178,6 +178,8 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     CK(cudaMemset(is, 0, (size_t)e->E * SI_SIZE * sizeof(int)));
     int *cn; CK(cudaMalloc((void **)&cn, 4 * sizeof(int))); e->allocs.push_back(cn); CK(cudaMemset(cn, 0, 4 * sizeof(int)));
     ev.counters = cn;
+    int *el; CK(cudaMalloc((void **)&el, (size_t)e->E * 2 * sizeof(int))); e->allocs.push_back(el); CK(cudaMemset(el, 0xFF, (size_t)e->E * 2 * sizeof(int)));
+    ev.ep_log = el;
     ev.state = st; ev.istate = is; ev.expert = nullptr; ev.clip_adr = nullptr; ev.clip_shape = nullptr; ev.clip_model = nullptr; ev.clip_cdf = nullptr;
     return 0;
 }
@@ -475,6 +477,7 @@ int uhc_engine_counters(UhcEngine *e, int *out4) {
     return 0;
 }
 
+const int *uhc_episode_log_dev(const UhcEngine *e) { return e ? (e->precision == 32 ? e->evf.ep_log : e->evd.ep_log) : nullptr; }
 int uhc_num_envs(const UhcEngine *e) { return e ? e->E : -1; }
 int uhc_kernel_launches(const UhcEngine *e) { return e ? e->launches : -1; }
 

@@ -48,6 +48,11 @@ def linear_forward(x, W, b, act="none", save_z=False):
     return (y, z) if save_z else y
 
 
+class ParamList(list):
+    """params() of an MLPNet: a plain list that remembers its net (so an optimiser built from it can work on the flat tensors)"""
+    net = None
+
+
 class MLPNet:
     """MLP trunk + linear head (khrylib/models/mlp.py:5-27 with PolicyGaussian.action_mean or Value.value_head)."""
 
@@ -55,6 +60,17 @@ class MLPNet:
         import torch
         self.torch, self.dims, self.htype, self.head_name = torch, [in_dim] + list(hsize) + [out_dim], htype, head_name
         g = torch.Generator().manual_seed(seed) if seed is not None else None
+        # ONE flat fp32 tensor holds every parameter (each tensor starts on a 256-byte boundary), W[i] / b[i] are views of it; the
+        # gradients live in an identically laid out flat tensor (`gflat`) with a small tail for the scalar statistics that ride the
+        # gradient all-reduce -- so Adam is one launch per net and the collective needs no flatten / copy.
+        offs, o = [], 0
+        for i in range(len(self.dims) - 1):
+            nW, nb = self.dims[i + 1] * self.dims[i], self.dims[i + 1]
+            offs.append((o, nW)); o += (nW + 63) // 64 * 64
+            offs.append((o, nb)); o += (nb + 63) // 64 * 64
+        self._offs, self.nflat = offs, o
+        self.flat = torch.zeros(o, device=device, dtype=torch.float32)
+        self._gfull = None
         self.W, self.b = [], []
         for i in range(len(self.dims) - 1):  # nn.Linear default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias
             k = 1.0 / math.sqrt(self.dims[i])
@@ -62,8 +78,11 @@ class MLPNet:
             bb = (torch.rand(self.dims[i + 1], generator=g) * 2 - 1) * k
             if i == len(self.dims) - 2:  # policy_gaussian.py:20-21 / critic.py:12-13
                 w, bb = w * 0.1, bb * 0.0
-            self.W.append(w.to(device).float().contiguous())
-            self.b.append(bb.to(device).float().contiguous())
+            (ow, nw), (ob, nb) = offs[2 * i], offs[2 * i + 1]
+            W, B = self.flat[ow:ow + nw].view(self.dims[i + 1], self.dims[i]), self.flat[ob:ob + nb]
+            W.copy_(w.float()); B.copy_(bb.float())
+            self.W.append(W)
+            self.b.append(B)
         self.device = device
         self._bf16 = None
         self.opt = None
@@ -88,7 +107,29 @@ class MLPNet:
         self._bf16 = None
 
     def params(self):
-        return [p for wb in zip(self.W, self.b) for p in wb]
+        out = ParamList(p for wb in zip(self.W, self.b) for p in wb)
+        out.net = self
+        return out
+
+    GRAD_TAIL = 4096            # floats after the gradients in the flat gradient tensor (statistics riding the all-reduce)
+
+    @property
+    def gfull(self):
+        """flat gradients + tail, allocated on first use"""
+        if self._gfull is None:
+            self._gfull = self.torch.zeros(self.nflat + self.GRAD_TAIL, device=self.flat.device, dtype=self.torch.float32)
+        return self._gfull
+
+    @property
+    def gflat(self):
+        return self.gfull[:self.nflat]
+
+    def grad_views(self):
+        """gradient tensors (views of gflat) in params() order"""
+        g, out = self.gflat, []
+        for (o, n), p in zip(self._offs, self.params()):
+            out.append(g[o:o + n].view_as(p))
+        return out
 
     # ---- fp32 path (training; exact-gelu, SIMT GEMM)
     def forward(self, x, save=False):
@@ -128,15 +169,17 @@ class MLPNet:
 
     # ---- tensor-core path (rollout): bf16 operands, fp32 accumulate, fused bias + activation
     def _prep_bf16(self):
+        """bf16 K-padded copies of the weights for the tensor-core kernels; the tensors keep their addresses across refreshes (the
+        rollout's CUDA graph holds the pointers)."""
         t = self.torch
-        Ws = []
-        for w in self.W:
+        store = getattr(self, "_bf16_store", None)
+        if store is None:
+            store = [t.zeros(w.shape[0], (w.shape[1] + 63) // 64 * 64, device=w.device, dtype=t.bfloat16) for w in self.W]
+            self._bf16_store = store
+        for w, wb in zip(self.W, store):
             N, K = w.shape
-            Kp = (K + 63) // 64 * 64
-            wb = t.zeros(N, Kp, device=w.device, dtype=t.bfloat16)
-            _chk(_lib().uhc_f32_to_bf16_padded(_p(w), _p(wb), N, K, Kp, _stream(w)))
-            Ws.append(wb)
-        self._bf16 = Ws
+            _chk(_lib().uhc_f32_to_bf16_padded(_p(w), _p(wb), N, K, wb.shape[1], _stream(w)))
+        self._bf16 = store
 
     def invalidate_bf16(self):
         self._bf16 = None
@@ -162,6 +205,27 @@ class MLPNet:
                                          self.W[i].shape[0], self._bf16[i].shape[1], 0 if last else ybf.shape[1],
                                          ACT["none" if last else self.htype], _stream(x)))
         return self._out
+
+
+class UhcMlp(C.Structure):
+    """include/uhc_rollout.h UhcMlp"""
+    _fields_ = [("nlayers", C.c_int), ("act", C.c_int), ("dims", C.c_int * 10), ("kp", C.c_int * 8), ("W_bf16", C.c_void_p * 8), ("bias", C.c_void_p * 8)]
+
+
+def mlp_struct(net):
+    """UhcMlp view of an MLPNet's current bf16 weights (rebuilt after every optimiser step: _prep_bf16 allocates new tensors)."""
+    if net._bf16 is None:
+        net._prep_bf16()
+    m = UhcMlp()
+    m.nlayers, m.act = len(net.W), ACT[net.htype]
+    for i, d in enumerate(net.dims):
+        m.dims[i] = d
+    for i, (wb, b) in enumerate(zip(net._bf16, net.b)):
+        m.kp[i] = wb.shape[1]
+        m.W_bf16[i] = wb.data_ptr()
+        m.bias[i] = b.data_ptr()
+    m._keep = (list(net._bf16), list(net.b))
+    return m
 
 
 def _buf(cache, key, shape, dtype, device, zero=True):
@@ -224,45 +288,63 @@ class TCTrainer:
         M = dy.shape[0]
         Mp = _pad64(M)
         dev = dy.device
-        grads = [None] * (2 * n)
+        grads = net.grad_views()     # dW / db are written straight into the flat gradient tensor the optimiser and the all-reduce use
         dh = dy.contiguous()
         for i in range(n - 1, -1, -1):
             N, K = net.W[i].shape
             Np = _pad64(N)
             dz = _buf(self.cache, f"dz{i}", (M, Np), torch.bfloat16, dev)
             dzT = _buf(self.cache, f"dzT{i}", (N, Mp), torch.bfloat16, dev)
-            db = torch.empty_like(net.b[i])
+            db = grads[2 * i + 1]
             _chk(L.uhc_dact_bf16(_p(dh), _p(zs[i] if i < n - 1 else None), _p(dz), _p(dzT), _p(db), M, N, Np, Mp, ACT[net.htype], _stream(dy)))
             if i == 0:
                 hT = xT
             else:
                 hT = _buf(self.cache, f"hT{i}", (K, Mp), torch.bfloat16, dev)
                 _chk(L.uhc_transpose_bf16(_p(acts[i]), _p(hT), M, K, acts[i].shape[1], Mp, _stream(dy)))
-            dW = torch.empty_like(net.W[i])
+            dW = grads[2 * i]
             _chk(L.uhc_linear_forward_tc(_p(dzT), _p(hT), None, None, _p(dW), N, K, Mp, 0, 0, _stream(dy)))      # dW = dz^T h
-            grads[2 * i], grads[2 * i + 1] = dW, db
             if i > 0:
                 WT = _buf(self.cache, f"WT{i}", (K, Np), torch.bfloat16, dev)
                 _chk(L.uhc_transpose_bf16(_p(net._bf16[i]), _p(WT), N, K, net._bf16[i].shape[1], Np, _stream(dy)))
                 dhp = _buf(self.cache, f"dh{i}", (M, K), torch.float32, dev, zero=False)
                 _chk(L.uhc_linear_forward_tc(_p(dz), _p(WT), None, None, _p(dhp), M, K, Np, 0, 0, _stream(dy)))    # dh_prev = dz W
                 dh = dhp
-        return grads
+        return net.gflat
 
 
 class Adam:
     """torch.optim.Adam semantics (lr, betas (0.9, 0.999), eps 1e-8, no weight decay) on the fused kernel."""
 
-    def __init__(self, params, lr):
+    def __init__(self, params, lr, net=None):
+        """net: the MLPNet whose flat parameter tensor `params` are views of -- then step() on the net's flat gradient tensor is ONE
+        fused launch (plus one norm reduction when clipping) instead of one per tensor."""
         import torch
-        self.params, self.lr, self.step_n = params, lr, 0
-        self.m = [torch.zeros_like(p) for p in params]
-        self.v = [torch.zeros_like(p) for p in params]
+        net = net if net is not None else getattr(params, "net", None)
+        self.params, self.lr, self.step_n, self.net = params, lr, 0, net
+        if net is not None:
+            self.mflat, self.vflat = torch.zeros_like(net.flat), torch.zeros_like(net.flat)
+            self.m = [self.mflat[o:o + n].view_as(p) for (o, n), p in zip(net._offs, params)]
+            self.v = [self.vflat[o:o + n].view_as(p) for (o, n), p in zip(net._offs, params)]
+        else:
+            self.m = [torch.zeros_like(p) for p in params]
+            self.v = [torch.zeros_like(p) for p in params]
         self.sq = torch.zeros(1, device=params[0].device, dtype=torch.float64)
 
     def step(self, grads, max_norm=None):
         L = _lib()
         self.step_n += 1
+        if self.net is not None and not isinstance(grads, (list, tuple)):     # flat gradient tensor (padding elements are zero and stay zero)
+            g, p = grads, self.net.flat
+            assert g.numel() == p.numel() and g.is_contiguous()
+            sq = None
+            if max_norm is not None:
+                self.sq.zero_()
+                _chk(L.uhc_sqsum(_p(g), C.c_long(g.numel()), _p(self.sq), _stream(g)))
+                sq = self.sq
+            _chk(L.uhc_adam_step(_p(p), _p(g), _p(self.mflat), _p(self.vflat), C.c_long(p.numel()), C.c_float(self.lr), C.c_float(0.9), C.c_float(0.999),
+                                 C.c_float(1e-8), self.step_n, _p(sq), C.c_float(max_norm or 0.0), _stream(p)))
+            return
         sq = None
         if max_norm is not None:
             self.sq.zero_()
@@ -302,6 +384,12 @@ class ZFilter:
         S = self.stats[1 + self.dim:].cpu().numpy()
         return np.sqrt(S / (n - 1)) if n > 1 else np.abs(self.mean)
 
+    def load_sums(self, n, mean, S):
+        """exact restore from a RunningStat's (n, mean, sum of squared deviations)"""
+        import torch
+        s = np.concatenate([[float(n)], np.asarray(mean, dtype=np.float64).reshape(-1), np.asarray(S, dtype=np.float64).reshape(-1)])
+        self.stats.copy_(torch.as_tensor(s))
+
     def load(self, n, mean, std):
         import torch
         var = np.asarray(std, dtype=np.float64) ** 2
@@ -339,49 +427,163 @@ def gae(rewards, masks, values, last_values, gamma, tau, normalize=True):
     return adv, ret
 
 
-def ppo_update(policy, value, log_std, opt_p, opt_v, states, actions, returns, advantages, exps, clip_eps=0.2, epochs=10, grad_clip=40.0,
-               use_tc=False):
-    """AgentPPO.update_policy (agent_ppo.py:16-51), full batch: per epoch one value step then one clipped-surrogate policy step.
-    use_tc=False: fp32 SIMT GEMMs (parity path); use_tc=True: tcgen05 bf16/fp32-accumulate GEMMs for forward, dX and dW."""
+class GradComm:
+    """The one collective of the design: all-reduce(sum) of a net's flat gradient tensor, enqueued on a side
+    stream so it overlaps the OTHER net's forward / backward; the compute stream only waits right before the optimiser step.
+    Gradients arrive pre-scaled (the loss kernels divide by the GLOBAL batch size), so no division follows the collective."""
+
+    def __init__(self, world):
+        import torch
+        self.world, self.torch = world, torch
+        self.stream = torch.cuda.Stream() if (world > 1 and torch.cuda.is_available()) else None
+        self.bytes, self.calls = 0, 0
+        self.events = []
+
+    def start(self, t):
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        torch = self.torch
+        self.bytes += t.numel() * t.element_size(); self.calls += 1
+        if self.stream is None:                      # CPU / gloo (tests)
+            dist.all_reduce(t)
+            return
+        ready = torch.cuda.current_stream().record_event()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(t)
+            e1.record()
+            self.events.append((e0, e1))
+        return e1
+
+    def wait(self, done=None):
+        """make the compute stream wait for one collective (its completion event) or for everything enqueued so far"""
+        if self.world > 1 and self.stream is not None:
+            if done is not None:
+                self.torch.cuda.current_stream().wait_event(done)
+            else:
+                self.torch.cuda.current_stream().wait_stream(self.stream)
+
+    def pop_ms(self):
+        ms = sum(a.elapsed_time(b) for a, b in self.events)
+        self.events = []
+        return ms
+
+
+def split_double(x):
+    """double tensor -> (hi, lo) float32 pair with hi + lo == x to ~1e-14 relative: lets fp64 statistics ride an fp32 all-reduce."""
     import torch
-    L = _lib()
-    M, A = actions.shape
+    hi = x.to(torch.float32)
+    lo = (x - hi.to(torch.float64)).to(torch.float32)
+    return hi, lo
+
+
+def join_double(hi, lo):
+    import torch
+    return hi.to(torch.float64) + lo.to(torch.float64)
+
+
+def zfilter_to_sums(stats, D):
+    """(n, mean, S) -> additive form (n, sum, sum of squares)"""
+    import torch
+    n, mean, S = stats[0:1], stats[1:1 + D], stats[1 + D:]
+    return torch.cat([n, n * mean, S + n * mean * mean])
+
+
+def zfilter_from_sums(sums, D):
+    import torch
+    n, s1, s2 = sums[0:1], sums[1:1 + D], sums[1 + D:]
+    mean = s1 / torch.clamp(n, min=1.0)
+    return torch.cat([n, mean, torch.clamp(s2 - n * mean * mean, min=0.0)])
+
+
+def ppo_update(policy, value, log_std, opt_p, opt_v, states, actions, returns, advantages, exps, clip_eps=0.2, epochs=10, grad_clip=40.0,
+               use_tc=False, comm=None):
+    """AgentPPO.update_policy (agent_ppo.py:16-51), full batch: per epoch one value step then one clipped-surrogate policy step.
+    use_tc=False: fp32 SIMT GEMMs (parity path); use_tc=True: tcgen05 bf16/fp32-accumulate GEMMs for forward, dX and dW (production)."""
     if use_tc:
         tp = getattr(policy, "_tc_trainer", None) or TCTrainer(policy)
         tv = getattr(value, "_tc_trainer", None) or TCTrainer(value)
         policy._tc_trainer, value._tc_trainer = tp, tv
         xb, xT = tp.prepare_input(states)
         tv.cache["xb"], tv.cache["xT"] = xb, xT
-        mean0 = tp.forward(xb)[0].clone()
-    else:
-        mean0 = policy.forward(states)
-    fixed = gaussian_logprob(mean0, log_std, actions)
-    count = float((exps != 0).sum().item())
-    losses = torch.zeros(2, device=states.device, dtype=torch.float32)
-    for _ in range(epochs):
-        if use_tc:
-            v, ctx = tv.forward(xb)
-        else:
-            v, ctx = value.forward(states, save=True)
-        dv = torch.empty_like(v)
+        return ppo_epochs_tc(policy, value, log_std, opt_p, opt_v, xb, xT, actions, returns, advantages, exps, clip_eps, epochs, grad_clip, comm=comm)
+    return _ppo_update_fp32(policy, value, log_std, opt_p, opt_v, states, actions, returns, advantages, exps, clip_eps, epochs, grad_clip)
+
+
+def ppo_epochs_tc(policy, value, log_std, opt_p, opt_v, xb, xT, actions, returns, advantages, exps, clip_eps=0.2, epochs=10, grad_clip=40.0,
+                  comm=None, first_value=None, after_first_reduce=None, inv_count_dev=None, world=1):
+    """The production update on the tensor-core path.  Per epoch: value forward/backward -> its flat gradient starts its all-reduce on the
+    side stream -> policy forward / clipped-surrogate gradient / backward run meanwhile -> the policy gradient starts its all-reduce ->
+    value Adam (waits for its collective) -> policy Adam.  The two nets are independent inside an epoch, so this order gives the
+    reference's result (value step, then policy step, agent_ppo.py:46-51).
+    first_value: (v, ctx) of a value forward already done on xb with the current weights (the V(s) GAE needed) -- reused for epoch 0.
+    after_first_reduce(tail): called once the FIRST collective (value gradients + the statistics tail) is ordered before the compute
+    stream: finalises everything that needs global statistics (advantage normalisation, ZFilter merge, the global row count)."""
+    import torch
+    L = _lib()
+    tp, tv = policy._tc_trainer, value._tc_trainer
+    M, A = actions.shape
+    dev = actions.device
+    first_policy = tp.forward(xb)                                  # old-policy mean: the fixed log-probs AND epoch 0's forward (same weights)
+    fixed = gaussian_logprob(first_policy[0], log_std, actions)
+    if inv_count_dev is None:
+        inv_count_dev = (1.0 / torch.clamp((exps != 0).sum().to(torch.float32), min=1.0)).reshape(1)
+    losses = torch.zeros(2, device=dev, dtype=torch.float32)
+    comm = comm or GradComm(1)
+    for ep in range(epochs):
+        v, ctx = first_value if (ep == 0 and first_value is not None) else tv.forward(xb)
+        dv = _buf(tv.cache, "dv", tuple(v.shape), torch.float32, dev, zero=False)
         losses.zero_()
-        _chk(L.uhc_value_grad(_p(v), _p(returns), _p(dv), _p(losses[1:]), M, _stream(states)))
-        opt_v.step(tv.backward(dv, ctx, xT) if use_tc else value.backward(dv, ctx))
-        if use_tc:
-            value.invalidate_bf16()
-            mean, ctx = tp.forward(xb)
-        else:
-            mean, ctx = policy.forward(states, save=True)
-        dmean = torch.empty_like(mean)
-        _chk(L.uhc_ppo_policy_grad(_p(mean), _p(log_std), _p(actions), _p(advantages), _p(fixed), _p(exps), C.c_float(clip_eps),
-                                   C.c_float(1.0 / max(count, 1.0)), _p(dmean), _p(losses), M, A, _stream(states)))
+        _chk(L.uhc_value_grad_n(_p(v), _p(returns), _p(dv), _p(losses[1:]), M, C.c_long(M * world), _stream(dv)))
+        gv = tv.backward(dv, ctx, xT)
+        with_tail = ep == 0 and after_first_reduce is not None
+        v_done = comm.start(value.gfull if with_tail else gv)
+        if with_tail:                                              # the global statistics are needed before the first policy gradient
+            comm.wait(v_done)
+            after_first_reduce(value.gfull[value.nflat:])
+        mean, ctx = first_policy if ep == 0 else tp.forward(xb)
+        dmean = _buf(tp.cache, "dmean", tuple(mean.shape), torch.float32, dev, zero=False)
+        _chk(L.uhc_ppo_policy_grad_dev(_p(mean), _p(log_std), _p(actions), _p(advantages), _p(fixed), _p(exps), C.c_float(clip_eps),
+                                       _p(inv_count_dev), _p(dmean), _p(losses), M, A, _stream(dmean)))
+        gp = tp.backward(dmean, ctx, xT)
+        p_done = comm.start(gp)
+        comm.wait(v_done)                                          # value step first, as the reference; the policy collective is still in flight
+        opt_v.step(gv)
+        value.invalidate_bf16()
+        comm.wait(p_done)
         # agent_copycat.py:93 passes `policy_net.parameters()` (a generator) as the clip list: clip_grad_norm_ exhausts it on the
         # very first call, so the reference clips only the first policy step of a run.  Mirrored here.
         first = not getattr(opt_p, "_clip_consumed", False)
         opt_p._clip_consumed = True
-        opt_p.step(tp.backward(dmean, ctx, xT) if use_tc else policy.backward(dmean, ctx), max_norm=grad_clip if (first and grad_clip) else None)
-        if use_tc:
-            policy.invalidate_bf16()
+        opt_p.step(gp, max_norm=grad_clip if (first and grad_clip) else None)
+        policy.invalidate_bf16()
+    return losses
+
+
+def _ppo_update_fp32(policy, value, log_std, opt_p, opt_v, states, actions, returns, advantages, exps, clip_eps=0.2, epochs=10, grad_clip=40.0):
+    import torch
+    L = _lib()
+    M, A = actions.shape
+    mean0 = policy.forward(states)
+    fixed = gaussian_logprob(mean0, log_std, actions)
+    count = float((exps != 0).sum().item())
+    losses = torch.zeros(2, device=states.device, dtype=torch.float32)
+    for _ in range(epochs):
+        v, ctx = value.forward(states, save=True)
+        dv = torch.empty_like(v)
+        losses.zero_()
+        _chk(L.uhc_value_grad(_p(v), _p(returns), _p(dv), _p(losses[1:]), M, _stream(states)))
+        opt_v.step(value.backward(dv, ctx))
+        mean, ctx = policy.forward(states, save=True)
+        dmean = torch.empty_like(mean)
+        _chk(L.uhc_ppo_policy_grad(_p(mean), _p(log_std), _p(actions), _p(advantages), _p(fixed), _p(exps), C.c_float(clip_eps),
+                                   C.c_float(1.0 / max(count, 1.0)), _p(dmean), _p(losses), M, A, _stream(states)))
+        first = not getattr(opt_p, "_clip_consumed", False)
+        opt_p._clip_consumed = True
+        opt_p.step(policy.backward(dmean, ctx), max_norm=grad_clip if (first and grad_clip) else None)
     policy.invalidate_bf16()
     value.invalidate_bf16()
     return losses
