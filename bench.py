@@ -330,7 +330,7 @@ def run_gpu(args):
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("how")
         except Exception:
             pass
-    cb = cpu_baseline(steps=6, warmup=1) if world == 1 else None
+    cb = cpu_baseline(steps=6, warmup=1) if (world == 1 and not os.environ.get("UHC_BENCH_SKIP_CPU")) else None   # (skipped under ncu)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=total_ms / K, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=workload_config(world),
                 roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,

@@ -73,7 +73,7 @@ static int emu_forward_given_tau(const Model<Real> &m, const EnvCfg<Real> &cfg, 
     while (iters < cfg.newton_max_iter && newton_prepare(m, cfg, w, scale, tp)) {
         ++iters;
         aba_solve(m, w, Real(0), true, w.p);
-        newton_advance(m, w, tp);
+        if (newton_advance(m, w, tp)) break;
     }
     return iters;
 }

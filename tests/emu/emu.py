@@ -9,7 +9,7 @@ from uhc_b200.model import HumanoidModel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libuhc_emu.so")
-ST = dict(Q=0, V=76, AW=152, C=228, XPOS=304, XQUAT=376, XIPOS=472, BQUAT=544, PBQUAT=640, IB=736, S=976, SIZE=1428)
+ST = dict(Q=0, V=76, AW=152, C=228, IB=304, S=544, XPOS=996, XQUAT=1068, XIPOS=1164, BQUAT=1236, PBQUAT=1332, SIZE=1428)
 EX_SIZE = 508
 
 

@@ -269,15 +269,16 @@ class BatchedAgent:
             if getattr(self, "_z_sync", None) is None:                               # fresh agent: every rank starts from empty statistics
                 self._z_sync = t.zeros_like(zs)                                      # additive form of the statistics every rank agreed on last
             d = t.cat([mom, t.full((1,), float(N), device=self.dev, dtype=t.float64), cnt, nn.zfilter_to_sums(zs, D) - self._z_sync])
-            hi, lo = nn.split_double(d)
+            planes = nn.split_double(d)                                              # [5, nd] exact fixed-point digits (fp32)
             tail = self.value.gfull[self.value.nflat:]
             tail.zero_()
             nd = d.numel()
-            tail[:nd].copy_(hi); tail[nd:2 * nd].copy_(lo)
+            assert planes.numel() <= tail.numel()
+            tail[:planes.numel()].copy_(planes.reshape(-1))
             ntot = t.zeros(1, device=self.dev, dtype=t.float64)
 
             def after(tail_r):
-                g = nn.join_double(tail_r[:nd], tail_r[nd:2 * nd])                   # summed over the ranks by the gradient all-reduce
+                g = nn.join_double(tail_r[:nn.SPLIT_CHUNKS * nd].reshape(nn.SPLIT_CHUNKS, nd))   # summed over the ranks by the gradient all-reduce
                 ntot.copy_(g[2:3])
                 gm = g[0:2].contiguous()
                 nn._chk(L.uhc_adv_normalize(nn._p(adv), C.c_long(N), nn._p(gm), nn._p(ntot), nn._stream(adv)))

@@ -87,27 +87,67 @@ UHC_DEV Model<Real> model_for_clip(const EngineView<Real> &ev, int clip) {
     return m;
 }
 
+// ---- state record <-> work set.  GPU: the head block (q v aw C Ib S, ST_BLOCK Reals) travels as ONE bulk-async copy (TMA engine:
+// cp.async.bulk global -> shared completing on this warp's mbarrier; shared -> global as a bulk group), the pose arrays as 16-byte
+// vector stores.  Host emulation: plain copies.
+#ifndef UHC_EMU
+UHC_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 template <class Real>
-UHC_DEV void load_state(const EngineView<Real> &ev, int env, Work<Real> &w) {
+UHC_DEV void state_mbar_init(Work<Real> &w) {
+    if ((threadIdx.x & 31) == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&w.mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+}
+// 16-byte vector copy of n Reals (n * sizeof(Real) a multiple of 16, both sides 16-byte aligned), all lanes
+template <class Real>
+UHC_DEV void copy16(Real *dst, const Real *src, int n) {
+    const int nv = n * (int)sizeof(Real) / 16;
+    for (int i = threadIdx.x & 31; i < nv; i += 32) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+}
+#endif
+template <class Real>
+UHC_DEV void load_state(const EngineView<Real> &ev, int env, Work<Real> &w, int parity) {
     const Real *st = ev.state + (size_t)env * ST_SIZE;
-    LANES_BEGIN
-    for (int i = lane; i < NQ; i += 32) w.q[i] = st[ST_Q + i];
-    for (int i = lane; i < NV; i += 32) { w.v[i] = st[ST_V + i]; w.aw[i] = st[ST_AW + i]; w.C[i] = st[ST_C + i]; }
-    for (int i = lane; i < NB * 10; i += 32) (&w.Ib[0][0])[i] = st[ST_IB + i];
-    for (int i = lane; i < NV * 6; i += 32) (&w.S[0][0])[i] = st[ST_S + i];
-    LANES_END
+#ifndef UHC_EMU
+    constexpr unsigned BYTES = ST_BLOCK * sizeof(Real);
+    static_assert(BYTES % 16 == 0 && (ST_SIZE * sizeof(Real)) % 16 == 0, "bulk copies need 16-byte granularity");
+    const unsigned mb = smem_u32(&w.mbar);
+    if ((threadIdx.x & 31) == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(w.q)), "l"(st), "r"(BYTES), "r"(mb) : "memory");
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+    }
+    __syncwarp();
+#else
+    (void)parity;
+    for (int i = 0; i < ST_BLOCK; i++) w.q[i] = st[i];       // q v aw C Ib S are contiguous in Work exactly as in the record
+#endif
 }
 template <class Real>
-UHC_DEV void store_state(const EngineView<Real> &ev, int env, const Work<Real> &w, const Real *bquat, const Real *pbquat) {
+UHC_DEV void store_state(const EngineView<Real> &ev, int env, Work<Real> &w) {
     Real *st = ev.state + (size_t)env * ST_SIZE;
-    LANES_BEGIN
-    for (int i = lane; i < NQ; i += 32) st[ST_Q + i] = w.q[i];
-    for (int i = lane; i < NV; i += 32) { st[ST_V + i] = w.v[i]; st[ST_AW + i] = w.aw[i]; st[ST_C + i] = w.C[i]; }
-    for (int i = lane; i < NB * 10; i += 32) st[ST_IB + i] = (&w.Ib[0][0])[i];
-    for (int i = lane; i < NV * 6; i += 32) st[ST_S + i] = (&w.S[0][0])[i];
-    for (int i = lane; i < 72; i += 32) { st[ST_XPOS + i] = (&w.xpos[0][0])[i]; st[ST_XIPOS + i] = (&w.xipos[0][0])[i]; }
-    for (int i = lane; i < 96; i += 32) { st[ST_XQUAT + i] = (&w.xquat[0][0])[i]; st[ST_BQUAT + i] = bquat[i]; if (pbquat) st[ST_PBQUAT + i] = pbquat[i]; }
-    LANES_END
+#ifndef UHC_EMU
+    constexpr unsigned BYTES = ST_BLOCK * sizeof(Real);
+    __syncwarp();
+    copy16(st + ST_XPOS, &w.xpos[0][0], 72); copy16(st + ST_XIPOS, &w.xipos[0][0], 72); copy16(st + ST_XQUAT, &w.xquat[0][0], 96);
+    if ((threadIdx.x & 31) == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the warp's generic-proxy writes to the head block -> visible to the async proxy
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(st), "r"(smem_u32(w.q)), "r"(BYTES) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");         // complete (not just read): the record may be re-read / re-written right after (in-kernel reset)
+    }
+    __syncwarp();
+#else
+    for (int i = 0; i < ST_BLOCK; i++) st[i] = w.q[i];
+    for (int i = 0; i < 72; i++) { st[ST_XPOS + i] = (&w.xpos[0][0])[i]; st[ST_XIPOS + i] = (&w.xipos[0][0])[i]; }
+    for (int i = 0; i < 96; i++) st[ST_XQUAT + i] = (&w.xquat[0][0])[i];
+#endif
 }
 
 // reset one env onto frame 0 of (clip, start, len): state <- expert qpos/qvel (or the override), sim.forward(), obs.
@@ -135,15 +175,10 @@ UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, 
     if (lane == 0) { is[SI_CUR_T] = 0; is[SI_CLIP] = clip; is[SI_START] = start; is[SI_LEN] = len; is[SI_NEWTON] = iters; is[SI_NCON] = w.ncon; }
     LANES_END
     if (obs) obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, 1), ev.clip_shape + 17 * clip, obs);
-    Real *stq = ev.state + (size_t)env * ST_SIZE;
     LANES_BEGIN
-    for (int i = lane; i < NQ; i += 32) stq[ST_Q + i] = w.q[i];
-    for (int i = lane; i < NV; i += 32) { stq[ST_V + i] = w.v[i]; stq[ST_AW + i] = 0; stq[ST_C + i] = w.C[i]; }
-    for (int i = lane; i < NB * 10; i += 32) stq[ST_IB + i] = (&w.Ib[0][0])[i];
-    for (int i = lane; i < NV * 6; i += 32) stq[ST_S + i] = (&w.S[0][0])[i];
-    for (int i = lane; i < 72; i += 32) { stq[ST_XPOS + i] = (&w.xpos[0][0])[i]; stq[ST_XIPOS + i] = (&w.xipos[0][0])[i]; }
-    for (int i = lane; i < 96; i += 32) stq[ST_XQUAT + i] = (&w.xquat[0][0])[i];
+    for (int i = lane; i < NV; i += 32) w.aw[i] = 0;
     LANES_END
+    store_state(ev, env, w);
 }
 
 // one control step.  out_* may be null.  Returns done; fills flags.
@@ -154,7 +189,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     Real *st = ev.state + (size_t)env * ST_SIZE;
     const int clip = is[SI_CLIP], start = is[SI_START], len = is[SI_LEN];
     int cur_t = is[SI_CUR_T];
-    load_state(ev, env, w);
+    load_state(ev, env, w, 0);     // the warp's mbarrier completes exactly one phase per kernel launch
     LANES_BEGIN
     for (int i = lane; i < ACT_DIM; i += 32) w.act[i] = (Real)action[i];
     LANES_END
@@ -219,7 +254,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     }
     if (cinfo_out && lane < 5) cinfo_out[lane] = (ObsT)ci[lane];
     LANES_END
-    store_state(ev, env, w, bq, (const Real *)nullptr);
+    store_state(ev, env, w);
     if (ev.cfg.auto_reset && (fail || end)) {   // re-seed the finished episode in place: the next observation is the reset observation
         int nclip, nstart, nlen;
         const int episode = is[SI_EPISODE] + 1;

@@ -67,8 +67,10 @@ constexpr int MAXLEVEL = 8;
 constexpr int LVL_G = 5;                      // max bodies per tree level (lane groups of 6 lanes in the articulated-body solve)
 constexpr int BODYF = 20;                     // floats per body in the model table
 // per-env state record in HBM (Real units)
-constexpr int ST_Q = 0, ST_V = 76, ST_AW = 152, ST_C = 228, ST_XPOS = 304, ST_XQUAT = 376, ST_XIPOS = 472,
-              ST_BQUAT = 544, ST_PBQUAT = 640, ST_IB = 736, ST_S = 976, ST_SIZE = 1428;   // IB: per-body inertia 24x10, S: 75x6
+// The first ST_BLOCK Reals mirror the head of the shared-memory work set (q v aw C Ib S) byte for byte, so the step kernel moves them with
+// ONE bulk-async (TMA) copy in and one out; every field starts on a 16-byte boundary (vector stores for the rest).
+constexpr int ST_Q = 0, ST_V = 76, ST_AW = 152, ST_C = 228, ST_IB = 304, ST_S = 544, ST_BLOCK = 996,   // IB: per-body inertia 24x10, S: 75x6 (+2 pad)
+              ST_XPOS = 996, ST_XQUAT = 1068, ST_XIPOS = 1164, ST_BQUAT = 1236, ST_PBQUAT = 1332, ST_SIZE = 1428;
 // per-env integer record
 constexpr int SI_CUR_T = 0, SI_CLIP = 1, SI_START = 2, SI_LEN = 3, SI_EPISODE = 4, SI_FLAGS = 5, SI_NEWTON = 6, SI_NCON = 7, SI_SIZE = 8;
 // expert frame record (Real units): qpos 76 | qvel 75 | wbpos 72 | wbquat 96 | bquat 96 | bangvel 72 | ee_wpos 15 | com 3 | pad
@@ -103,19 +105,23 @@ struct EnvCfg {
 // per-environment working set (lives in shared memory on the GPU)
 template <class Real>
 struct Work {
-    Real q[NQ], v[NV + 1], aw[NV + 1], act[ACT_DIM + 3];
-    Real xpos[NB][3], xmat[NB][9], xipos[NB][3], xquat[NB][4];
-    alignas(16) Real S[NV + 6][6];   // motion subspaces; rows NV.. are the unit vectors of the solve's virtual dofs
+    // ---- head: the persistent simulator state, laid out exactly like the first ST_BLOCK Reals of the HBM record (bulk-async copy in / out)
+    alignas(16) Real q[NQ]; Real v[NV + 1], aw[NV + 1], C[NV + 1];
     Real Ib[NB][10];              // per-body rigid inertia about O, world axes (of the last forward pass)
+    alignas(16) Real S[NV + 6][6];   // motion subspaces; rows NV.. are the unit vectors of the solve's virtual dofs
+    // ---- derived pose (vector stores to the record), the rest of the working set
+    alignas(16) Real xpos[NB][3]; Real xipos[NB][3], xquat[NB][4], xmat[NB][9];
+    Real act[ACT_DIM + 3];
     alignas(16) Real aU[NV + 6][6];   // articulated-body sweep: columns of  U D^-1  per 3-dof block (U = IA S, D = S^T U + arm)
     Real au[NV + 6];                // D^-1 u per block
-    Real C[NV + 1], fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
+    Real fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
     alignas(16) Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
     // contacts
     int cbody[MAXCON]; Real cr[MAXCON][3], cdist[MAXCON], cD[MAXCON], caref[MAXCON][4], cres[MAXCON][4], cjp[MAXCON][4];
     int bcon_adr[NB + 1];
     int ncon, upper_contact;
     int con_overflow;             // a candidate body's contacts did not fit MAXCON in some substep of this step (the env is failed, never silently truncated)
+    alignas(8) unsigned long long mbar;   // mbarrier of this warp's bulk-async state load
     int sync_threads;             // threads taking part in the CTA-level substep alignment barrier (32 x warps that own a valid env)
     // this env's model view (shape variant) and config: kept here so that the non-inlined phases read them from shared memory
     // instead of a per-thread local-memory copy
@@ -958,8 +964,11 @@ UHC_DEV bool newton_prepare(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<
     return true;
 }
 // newton_advance: given the Newton direction in w.p: J p, M p, exact-ish line search, update a / M a / residuals
+// Returns true when the step was an exact Newton step: the full step (al = 1) zeroed the directional derivative and no constraint row
+// changed its active state on the way -- the cost is then quadratic along the whole step, the new point is its minimiser and the
+// gradient there is zero up to rounding, so the caller can stop without paying another gradient evaluation just to confirm it.
 template <class Real, class TPT>
-UHC_DEV void newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
+UHC_DEV bool newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
     tree_vel(m, w, w.p, w.Ab, tp);
     contact_rows(m, w, w.Ab, w.cjp, (const Real (*)[4]) nullptr);
     contact_force(m, w, 1, w.Fb, tp);
@@ -976,19 +985,21 @@ UHC_DEV void newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp) 
     const Real A0 = WSUM(pa), B0 = WSUM(pb);
     // 1-D safeguarded Newton on f'(al) = A0 + al B0 + sum_rows D (r + al jp)_- jp   (piecewise linear, increasing)
     Real lo = 0, hi = -1, al = 1;
+    bool exact = false;
     for (int ls = 0; ls < 12; ++ls) {
-        LVAR(Real, d1); LVAR(Real, d2);
+        LVAR(Real, d1); LVAR(Real, d2); LVAR(int, chg);
         LANES_BEGIN
-        Real s1 = 0, s2 = 0;
+        Real s1 = 0, s2 = 0; int ch = 0;
         for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) {
-            const Real r = w.cres[c][e] + al * w.cjp[c][e];
+            const Real r0 = w.cres[c][e], r = r0 + al * w.cjp[c][e];
             if (r < 0) { s1 += w.cD[c] * r * w.cjp[c][e]; s2 += w.cD[c] * w.cjp[c][e] * w.cjp[c][e]; }
+            ch |= (r0 < 0) != (r < 0);
         }
-        LV(d1) = s1; LV(d2) = s2;
+        LV(d1) = s1; LV(d2) = s2; LV(chg) = ch;
         LANES_END
         const Real f1 = A0 + al * B0 + WSUM(d1), f2 = B0 + WSUM(d2);
         if (f1 > 0) hi = al; else lo = al;
-        if (abs_(f1) <= Real(1e-6) * abs_(A0) + Real(1e-30)) break;
+        if (abs_(f1) <= Real(1e-6) * abs_(A0) + Real(1e-30)) { exact = ls == 0 && !WBALLOT(chg); break; }
         Real nx = al - f1 / f2;
         if (!(nx > lo) || (hi > 0 && !(nx < hi))) nx = hi > 0 ? Real(0.5) * (lo + hi) : 2 * al;
         if (nx == al) break;
@@ -998,6 +1009,7 @@ UHC_DEV void newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp) 
     for (int i = lane; i < NV; i += 32) { w.a[i] += al * w.p[i]; w.Ma[i] += al * w.Mp[i]; }
     for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] += al * w.cjp[c][e];
     LANES_END
+    return exact;
 }
 
 // ================================================================================================ task layer
@@ -1163,7 +1175,7 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
                 scale = newton_init(m, w, tp);
             }
             phase = PH_NEWTON;
-        } else newton_advance(m, w, tp);
+        } else if (newton_advance(m, w, tp)) done = true;
     }
     return iters;
 }

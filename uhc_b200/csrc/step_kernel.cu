@@ -61,7 +61,7 @@ k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict
     }
     Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
     if ((threadIdx.x & 31) == 0) w.sync_threads = 32 * s_nvalid;
-    __syncwarp();
+    state_mbar_init(w);            // mbarrier of this warp's bulk-async (TMA) state load
     env_step_warp<Real, float>(ev, env, w, act + (size_t)env * ACT_DIM, obs ? obs + (size_t)env * OBS_DIM : nullptr, rew ? rew + env : nullptr,
                                cinfo ? cinfo + (size_t)env * 5 : nullptr, fail ? fail + env : nullptr, end ? end + env : nullptr,
                                pct ? pct + env : nullptr, torque ? torque + (size_t)env * NSUB * NU : nullptr);

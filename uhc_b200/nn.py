@@ -111,7 +111,7 @@ class MLPNet:
         out.net = self
         return out
 
-    GRAD_TAIL = 4096            # floats after the gradients in the flat gradient tensor (statistics riding the all-reduce)
+    GRAD_TAIL = 8192            # floats after the gradients in the flat gradient tensor (statistics riding the all-reduce)
 
     @property
     def gfull(self):
@@ -472,17 +472,30 @@ class GradComm:
         return ms
 
 
+SPLIT_CHUNKS, SPLIT_BITS, SPLIT_TOP = 5, 18, 60
+
+
 def split_double(x):
-    """double tensor -> (hi, lo) float32 pair with hi + lo == x to ~1e-14 relative: lets fp64 statistics ride an fp32 all-reduce."""
+    """fp64 statistics riding an fp32 all-reduce(sum) EXACTLY: x (|x| < 2^60) -> 5 float32 digit planes of 18 bits each (base 2^18
+    fixed point, least significant digit = 2^-30).  Every digit is an integer below 2^18 in magnitude, so the fp32 sum over up to 32 ranks is
+    exact; join_double rebuilds sum_ranks(x) to 2^-30 absolute.  Returns a [5, n] float32 tensor."""
     import torch
-    hi = x.to(torch.float32)
-    lo = (x - hi.to(torch.float64)).to(torch.float32)
-    return hi, lo
+    r = x.to(torch.float64).clone()
+    planes = []
+    for k in range(SPLIT_CHUNKS):
+        scale = 2.0 ** (SPLIT_TOP - SPLIT_BITS * (k + 1))
+        c = torch.trunc(r / scale)
+        r = r - c * scale
+        planes.append(c.to(torch.float32))
+    return torch.stack(planes)
 
 
-def join_double(hi, lo):
+def join_double(planes):
     import torch
-    return hi.to(torch.float64) + lo.to(torch.float64)
+    out = torch.zeros(planes.shape[1], dtype=torch.float64, device=planes.device)
+    for k in range(SPLIT_CHUNKS):
+        out = out + planes[k].to(torch.float64) * (2.0 ** (SPLIT_TOP - SPLIT_BITS * (k + 1)))
+    return out
 
 
 def zfilter_to_sums(stats, D):
