@@ -52,8 +52,10 @@ typedef struct {
     double w[5], k[5], newton_tol;
     /* in-kernel re-seeding of finished episodes (agent_copycat.py:503-512 + dataset_amass_single.py:172-253): when auto_reset != 0,
      * an env whose step ends its episode samples a new (clip, start) slice and is reset inside uhc_env_step; obs = reset obs. */
-    int auto_reset, t_min, t_max, reserved;
+    int auto_reset, t_min, t_max;
+    int reactive_v;         /* cfg.reactive_v (copycat_config.py:97): 1 = train-mode episodes start from the standing-neutral pose with probability reactive_rate */
     unsigned long long reset_seed;
+    double reactive_rate;   /* cfg.reactive_rate (copycat_config.py:99, default 0.3) */
 } UhcEnvCfg;
 
 const char *uhc_last_error(void);
@@ -69,6 +71,9 @@ int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *
 /* body-shape variant of every clip (index into the model's shape variants); the reference rebuilds the robot per clip from
  * its beta/gender (humanoid_im.py:154-180).  Call after uhc_load_clips; default = variant 0 for every clip. */
 int uhc_set_clip_models(UhcEngine *e, int nclips, const int *clip_model);
+
+/* standing-neutral pose of the reactive starts (sample_data/standing_neutral.pkl: qpos[76], qvel[75]; humanoid_im.py:66,86,1269-1271). */
+int uhc_set_neutral_pose(UhcEngine *e, const double *qpos76, const double *qvel75);
 
 /* Clip sampling weights of the in-kernel re-seeding.  Default (weights_host == NULL, and after every uhc_load_clips) = the
  * sample_keys rule used when no success history exists (len // t_max + 1 copies per clip, dataset_amass_single.py:138-142,180-182).

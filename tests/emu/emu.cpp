@@ -25,7 +25,7 @@ static void set_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) {
     c.meta_pd = h->meta_pd; c.env_episode_len = h->env_episode_len; c.trail_steps = h->trail_steps; c.newton_max_iter = h->newton_max_iter;
     for (int i = 0; i < 5; i++) { c.w[i] = (Real)h->w[i]; c.k[i] = (Real)h->k[i]; }
     c.newton_tol = (Real)h->newton_tol;
-    c.auto_reset = 0; c.t_min = h->t_min; c.t_max = h->t_max; c.reset_seed = h->reset_seed; c.num_clips = 0;
+    c.reactive_v = 0; c.reactive_rate = 0; c.auto_reset = 0; c.t_min = h->t_min; c.t_max = h->t_max; c.reset_seed = h->reset_seed; c.num_clips = 0;
 }
 
 template <class Real>
@@ -45,7 +45,7 @@ static Emu<Real> *create(const UhcModelHost *m, const UhcEnvCfg *cfg, int E) {
     M.simp0 = (Real)m->solimp[0]; M.simp1 = (Real)m->solimp[1]; M.simp2 = (Real)m->solimp[2]; M.simp3 = (Real)m->solimp[3]; M.simp4 = (Real)m->solimp[4];
     M.gravz = (Real)m->gravz; M.nshape = 1; M.nvert = m->nvert;
     set_cfg(e->ev.cfg, cfg);
-    e->ev.clip_model = nullptr; e->ev.clip_cdf = nullptr; e->ev.counters = nullptr; e->ev.ep_log = nullptr;
+    e->ev.clip_model = nullptr; e->ev.clip_cdf = nullptr; e->ev.counters = nullptr; e->ev.ep_log = nullptr; e->ev.neutral = nullptr;
     e->state.assign((size_t)E * ST_SIZE, 0); e->istate.assign((size_t)E * SI_SIZE, 0);
     e->ev.num_envs = E; e->ev.state = e->state.data(); e->ev.istate = e->istate.data();
     return e;

@@ -17,7 +17,8 @@ class UhcEnvCfg(C.Structure):
     _fields_ = [("base_rot", C.c_double * 4), ("rfc_scale", C.c_double), ("rfc_lim", C.c_double), ("rfc_rate", C.c_double),
                 ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
                 ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double),
-                ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reserved", C.c_int), ("reset_seed", C.c_ulonglong)]
+                ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reactive_v", C.c_int), ("reset_seed", C.c_ulonglong),
+                ("reactive_rate", C.c_double)]
 
 
 def default_cfg(precision=32, **kw):

@@ -387,3 +387,48 @@ def test_c_rollout_graph_matches_python_step_loop_bit_for_bit(golden_dir):
     lp = buf.logp.cpu().numpy()
     assert np.abs(lp[ex == 0] - lp_mean).max() < 1e-3 and (lp[ex == 1] < lp_mean - 1.0).all()
     ag.engine.close()
+
+
+def test_reactive_starts_match_reference_reset(golden_dir):
+    """cfg.reactive_v = 1 (released config uhc_implicit): a train-mode episode starts, with probability reactive_rate, from the standing-neutral
+    pose turned to the expert's heading at the expert's x, y with the neutral velocities (humanoid_im.py:1255-1271, :1312-1320).
+    Golden = the unmodified reference's env.reset() with reactive_rate = 1 on the sway clip (tools/make_golden.py gen_reactive).
+    rate 1: every reset (host-initiated and in-kernel) is a reactive start and equals the golden; rate 0.3: the fraction is ~0.3 and the
+    others are plain expert starts; test mode (auto_reset = 0) never uses it."""
+    import torch
+    from uhc_b200.engine import Engine
+    g = np.load(os.path.join(golden_dir, "reactive_sway.npz"))
+    ex, so = _expert(golden_dir, "sway")
+    ex = {k: ex[k][:90] for k in KEYS}
+    E = 64
+    eng = Engine(E, auto_reset=1, reactive_v=1, reactive_rate=1.0, t_min=4, t_max=300, reset_seed=3)
+    eng.set_neutral_pose(g["neutral_qpos"], g["neutral_qvel"])
+    eng.load_clips([ex], [so])
+    obs = eng.reset().cpu().numpy().copy()
+    st = eng.get_states()
+    assert np.abs(st["qpos"] - g["qpos0"]).max() < 1e-6 and np.abs(st["qvel"] - g["qvel0"]).max() < 1e-6
+    assert np.abs(obs - g["obs0"]).max() < 1e-4
+    for t in range(3):
+        _, r, _, fail, _, _ = eng.step(torch.zeros(E, 105, device="cuda"))
+        assert np.abs(eng.get_states([0, E - 1])["qpos"] - g["qpos"][t]).max() < 1e-3
+        assert abs(float(r[0]) - g["reward"][t]) < 1e-3
+    eng.close()
+    # rate 0.3 through the in-kernel re-seeding: env_episode_len = 1 ends every episode after one step
+    E = 4096
+    eng = Engine(E, auto_reset=1, reactive_v=1, reactive_rate=0.3, t_min=4, t_max=300, reset_seed=9, env_episode_len=1)
+    eng.load_clips([ex], [so])                       # default neutral pose = the bundled copy of standing_neutral.pkl
+    eng.reset()
+    eng.step(torch.zeros(E, 105, device="cuda"))
+    st = eng.get_states()
+    reactive = np.abs(st["qpos"][:, 7:] - g["neutral_qpos"][7:]).max(1) < 1e-6
+    plain = np.abs(st["qpos"][:, 7:] - ex["qpos"][st["start"], 7:]).max(1) < 1e-6
+    assert (reactive ^ plain).all()
+    assert abs(reactive.mean() - 0.3) < 4 * np.sqrt(0.3 * 0.7 / E), reactive.mean()
+    assert np.abs(st["qpos"][reactive][:, :2] - ex["qpos"][st["start"][reactive], :2]).max() < 1e-6      # x, y of the expert frame
+    assert np.abs(st["qpos"][reactive][:, 2] - g["neutral_qpos"][2]).max() < 1e-6
+    eng.close()
+    eng = Engine(8, auto_reset=0, reactive_v=1, reactive_rate=1.0)                                      # test mode: never reactive
+    eng.load_clips([ex], [so])
+    eng.reset()
+    assert np.abs(eng.get_states()["qpos"] - ex["qpos"][0]).max() < 1e-6
+    eng.close()

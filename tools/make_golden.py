@@ -262,6 +262,29 @@ def gen_metrics():
     print("metrics golden:", {k: np.mean(v) for k, v in m.items()})
 
 
+def gen_reactive(cfg, dl):
+    """reset_model's reactive_v = 1 branch (humanoid_im.py:1255-1271, match_heading_and_pos :1312-1320) on the sway clip: reactive_rate = 1
+    forces the standing-neutral start; the state / observation after env.reset() and three zero-action steps are recorded."""
+    from uhc.losses.reward_function import world_rfc_implicit_reward
+    key = "0-ACCAD_Male2General_c3d_A2- Sway_poses"
+    seq = dl.get_sample_from_key(key, full_sample=False, fr_start=0)
+    seq = {k: (v[:90] if hasattr(v, "shape") and len(v) > 90 else v) for k, v in seq.items()}
+    cfg.reactive_v, cfg.reactive_rate = 1, 1.0
+    env = H.make_env(cfg, seq, mode="train")
+    env.seed(1)
+    obs0 = env.reset()
+    rec = dict(obs0=obs0, qpos0=env.data.qpos.copy(), qvel0=env.data.qvel.copy(), neutral_qpos=np.array(env.netural_data["qpos"]),
+               neutral_qvel=np.array(env.netural_data["qvel"]), qpos=[], reward=[])
+    for t in range(3):
+        a = np.zeros(env.action_dim)
+        ob, _, done, info = env.step(a)
+        r, _ = world_rfc_implicit_reward(env, None, a, info)
+        rec["qpos"].append(env.data.qpos.copy()); rec["reward"].append(r)
+    cfg.reactive_v = 0
+    np.savez_compressed(os.path.join(OUT, "reactive_sway.npz"), **{k: np.array(v) for k, v in rec.items()})
+    print("reactive golden: z", rec["qpos0"][2], "joints == neutral", np.abs(rec["qpos0"][7:] - rec["neutral_qpos"][7:]).max())
+
+
 def gen_math():
     from uhc.utils import transformation as T
     from uhc.utils import math_utils as MU
@@ -301,6 +324,10 @@ def main():
         gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 60, "zero")
         gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 60, "noise")
         gen_env(cfg, dl, "0-BioMotionLab_NTroje_rub008_0025_kicking1_poses", "kick", 70, 69, "noise")
+    if "reactive" in what:
+        cfg = H.make_cfg()
+        from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
+        gen_reactive(cfg, DatasetAMASSSingle(cfg.data_specs, data_mode="train"))
     if "ppo" in what:
         gen_ppo()
     if "ppo_real" in what:

@@ -86,7 +86,7 @@ class HumanoidEnv:
         self.prev_bquat = None
         self.cur_t, self.start_ind, self.end_reward, self.rfc_rate = 0, 0, 0.0, 1.0
         self.last_reward, self.last_cinfo = 0.0, np.zeros(5)
-        self._act = torch.zeros(1, ACT_DIM, device=self.engine.obs.device)
+        self._act = torch.zeros(1, ACT_DIM, device=self.engine.obs.device, dtype=torch.float32)
         self.load_expert(init_expert)
 
     def seed(self, seed=None):

@@ -120,8 +120,8 @@ class BatchedAgent:
         self.noise_rate, self.grad_sync, self.update_tc = noise_rate, grad_sync, update_tc
         self.global_step = 0
         self.obs = None
-        self.ep_len = torch.zeros(num_envs, device=self.dev)
-        self.ep_ret = torch.zeros(num_envs, device=self.dev)
+        self.ep_len = torch.zeros(num_envs, device=self.dev, dtype=torch.float32)
+        self.ep_ret = torch.zeros(num_envs, device=self.dev, dtype=torch.float32)
         self.nn_launches = 0
         self._notdone = torch.zeros(num_envs, device=self.dev, dtype=torch.bool)
 
@@ -146,7 +146,7 @@ class BatchedAgent:
         t = self.torch
         mean_action = None
         if self.noise_rate < 1.0:
-            mean_action = (t.rand(self.E, device=self.dev) < (1.0 - self.noise_rate)).to(t.uint8)
+            mean_action = (t.rand(self.E, device=self.dev, dtype=t.float32) < (1.0 - self.noise_rate)).to(t.uint8)
         s, a, lp = self.policy_step(self.obs, True, mean_action, use_tc, buf.states[k], buf.actions[k], buf.logp[k])
         if mean_action is not None:
             buf.exps[k].copy_(1.0 - mean_action.float())
@@ -209,9 +209,9 @@ class BatchedAgent:
         m, r = buf.masks[:T], buf.rewards[:T]
         done = m == 0
         n_eps = int(done.sum())
-        run_len = t.zeros(self.E, device=self.dev); run_ret = t.zeros(self.E, device=self.dev)
+        run_len = t.zeros(self.E, device=self.dev, dtype=t.float32); run_ret = t.zeros(self.E, device=self.dev, dtype=t.float32)
         run_len += len0; run_ret += ret0
-        tot_len = t.zeros((), device=self.dev); tot_ret = t.zeros((), device=self.dev)
+        tot_len = t.zeros((), device=self.dev, dtype=t.float32); tot_ret = t.zeros((), device=self.dev, dtype=t.float32)
         for k in range(T):
             run_len += 1; run_ret += r[k]
             d = done[k]

@@ -20,6 +20,7 @@ struct EngineView {
     const Real *clip_shape; // [C][17] beta[16], gender
     const int *clip_model;  // [C] body-shape (model variant) of each clip: the reference rebuilds the robot per clip (humanoid_im.py:154-180)
     const float *clip_cdf;  // [C] cumulative sampling weights (len // t_max + 1 copies per clip, sample_keys of the reference)
+    const Real *neutral;    // [76 + 75] standing_neutral qpos / qvel (sample_data/standing_neutral.pkl; humanoid_im.py:66,86), null = reactive starts off
     int *ep_log;            // [E][2] per env: clip index of the episode that ended in the last step (-1: none ended) and its completed fraction (float bits)
                             //   -- the training loop's per-clip success history (agent_copycat.py:561) is built from it
     int *counters;          // [4] device counters: 0 = env-steps failed because a body's contacts did not fit MAXCON, 1 = env-steps skipped on an invalid env record
@@ -161,6 +162,22 @@ UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, 
     for (int i = lane; i < NV; i += 32) { w.v[i] = qvel_override ? qvel_override[i] : e0[EX_QVEL + i]; w.aw[i] = 0; }
     for (int i = lane; i < ACT_DIM; i += 32) w.act[i] = 0;
     LANES_END
+    // reactive_v = 1, train mode (humanoid_im.py:1255-1271): with probability reactive_rate the episode starts from the standing-neutral pose,
+    // turned to the expert's heading and moved to its x, y (match_heading_and_pos, :1312-1320), with the neutral velocities
+    if (ev.cfg.reactive_v == 1 && ev.cfg.auto_reset && !qpos_override && ev.neutral) {
+        const unsigned long long h = mix64(ev.cfg.reset_seed ^ mix64(0x5EAC71FEull + (unsigned long long)env * 0x100000001B3ull + (unsigned long long)(ev.istate[(size_t)env * SI_SIZE + SI_EPISODE] + 1)));
+        if ((Real)((float)(h >> 40) * (1.0f / 16777216.0f)) < ev.cfg.reactive_rate) {
+            Real q1[4], hq[4], nq[4], nh[4], nhi[4], dq[4], out[4];
+            remove_base_rot(ev.cfg, e0 + EX_QPOS + 3, q1); heading_q(q1, hq);                        // heading of the expert's first frame
+            for (int i = 0; i < 4; i++) nq[i] = ev.neutral[3 + i];
+            heading_q(nq, nh); qinv(nh, nhi); qmul(nhi, nq, dq);                                      // de_heading of the neutral root quaternion (as stored: no base-rotation removal, :1317)
+            qmul(hq, dq, out);
+            LANES_BEGIN
+            for (int i = lane; i < NQ; i += 32) w.q[i] = i < 2 ? e0[EX_QPOS + i] : (i >= 3 && i < 7 ? out[i - 3] : ev.neutral[i]);
+            for (int i = lane; i < NV; i += 32) w.v[i] = ev.neutral[NQ + i];
+            LANES_END
+        }
+    }
     LANES_BEGIN
     if (lane == 0) { w.mdl = model_for_clip(ev, clip); w.cfg = ev.cfg; w.con_overflow = 0; }
     LANES_END

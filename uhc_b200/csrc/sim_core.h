@@ -100,6 +100,7 @@ struct EnvCfg {
     Real w[5], k[5], newton_tol;
     int auto_reset, t_min, t_max, num_clips;      // in-kernel re-seeding of finished episodes (dataset_amass_single.py:172-253)
     unsigned long long reset_seed;
+    int reactive_v; Real reactive_rate;           // reset_model's reactive_v = 1 branch (humanoid_im.py:1255-1271): start from the standing pose w.p. reactive_rate
 };
 
 // per-environment working set (lives in shared memory on the GPU)

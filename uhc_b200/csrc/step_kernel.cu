@@ -155,6 +155,7 @@ template <class Real> static void fill_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) 
     for (int i = 0; i < 5; i++) { c.w[i] = (Real)h->w[i]; c.k[i] = (Real)h->k[i]; }
     c.newton_tol = (Real)h->newton_tol;
     c.auto_reset = h->auto_reset; c.t_min = h->t_min; c.t_max = h->t_max; c.reset_seed = h->reset_seed;
+    c.reactive_v = h->reactive_v; c.reactive_rate = (Real)h->reactive_rate;
 }
 template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, const UhcModelHost *m, const UhcEnvCfg *cfg) {
     Model<Real> &M = ev.model;
@@ -177,7 +178,7 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     int *is; CK(cudaMalloc((void **)&is, (size_t)e->E * SI_SIZE * sizeof(int))); e->allocs.push_back(is);
     CK(cudaMemset(is, 0, (size_t)e->E * SI_SIZE * sizeof(int)));
     int *cn; CK(cudaMalloc((void **)&cn, 4 * sizeof(int))); e->allocs.push_back(cn); CK(cudaMemset(cn, 0, 4 * sizeof(int)));
-    ev.counters = cn;
+    ev.counters = cn; ev.neutral = nullptr;
     int *el; CK(cudaMalloc((void **)&el, (size_t)e->E * 2 * sizeof(int))); e->allocs.push_back(el); CK(cudaMemset(el, 0xFF, (size_t)e->E * 2 * sizeof(int)));
     ev.ep_log = el;
     ev.state = st; ev.istate = is; ev.expert = nullptr; ev.clip_adr = nullptr; ev.clip_shape = nullptr; ev.clip_model = nullptr; ev.clip_cdf = nullptr;
@@ -294,6 +295,17 @@ int uhc_load_clips(UhcEngine *e, int nclips, const int *clip_len, const double *
         CK(cudaMemcpy(e->d_expert, frames_host, nf * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(e->d_shape, shape_host, ns * 8, cudaMemcpyHostToDevice));
         e->evd.expert = (const double *)e->d_expert; e->evd.clip_shape = (const double *)e->d_shape; e->evd.clip_adr = e->d_clip_adr;
     }
+    return 0;
+}
+
+int uhc_set_neutral_pose(UhcEngine *e, const double *qpos76, const double *qvel75) {
+    if (!e || !qpos76 || !qvel75) { g_err = "uhc_set_neutral_pose: bad argument"; return -2; }
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<double> h(NQ + NV);
+    memcpy(h.data(), qpos76, NQ * 8); memcpy(h.data() + NQ, qvel75, NV * 8);
+    if (e->precision == 32) { const float *d; if (dev_copy_real<float>(e, &d, h.data(), NQ + NV)) return -1; e->evf.neutral = d; }
+    else { const double *d; if (dev_copy_real<double>(e, &d, h.data(), NQ + NV)) return -1; e->evd.neutral = d; }
     return 0;
 }
 

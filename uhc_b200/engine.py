@@ -20,12 +20,13 @@ class UhcEnvCfg(C.Structure):
     _fields_ = [("base_rot", C.c_double * 4), ("rfc_scale", C.c_double), ("rfc_lim", C.c_double), ("rfc_rate", C.c_double),
                 ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
                 ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double),
-                ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reserved", C.c_int), ("reset_seed", C.c_ulonglong)]
+                ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reactive_v", C.c_int), ("reset_seed", C.c_ulonglong),
+                ("reactive_rate", C.c_double)]
 
 
 def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0, rfc_lim=100.0, rfc_rate=1.0, body_diff_thresh=0.5,
              meta_pd=1, env_episode_len=100000, trail_steps=0, w=(0.3, 0.1, 0.45, 0.1, 0.05), k=(2.0, 0.005, 5.0, 100.0, 1.0),
-             newton_max_iter=None, newton_tol=None, auto_reset=0, t_min=5, t_max=300, reset_seed=1):
+             newton_max_iter=None, newton_tol=None, auto_reset=0, t_min=5, t_max=300, reset_seed=1, reactive_v=0, reactive_rate=0.3):
     """Defaults = config/release/uhc_implicit_shape.yml + copycat_config.py defaults of the reference."""
     c = UhcEnvCfg()
     c.base_rot = (C.c_double * 4)(*base_rot)
@@ -35,6 +36,7 @@ def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0,
     c.newton_tol = newton_tol or (1e-11 if precision == 64 else 1e-5)
     c.w, c.k = (C.c_double * 5)(*w), (C.c_double * 5)(*k)
     c.auto_reset, c.t_min, c.t_max, c.reset_seed = int(auto_reset), int(t_min), int(t_max), int(reset_seed)
+    c.reactive_v, c.reactive_rate = int(reactive_v), float(reactive_rate)
     return c
 
 
@@ -100,6 +102,17 @@ class Engine:
         self.fail = torch.zeros(self.E, device=dev, dtype=torch.int32)
         self.end = torch.zeros(self.E, device=dev, dtype=torch.int32)
         self.clip_len = None
+        if int(cfg.get("reactive_v", 0)) == 1:
+            self.set_neutral_pose()
+
+    def set_neutral_pose(self, qpos=None, qvel=None):
+        """standing-neutral pose of the reactive starts; default = the bundled copy of the reference's sample_data/standing_neutral.pkl"""
+        if qpos is None:
+            z = np.load(os.path.join(_HERE, "assets", "standing_neutral.npz"))
+            qpos, qvel = z["qpos"], z["qvel"]
+        q, v = np.ascontiguousarray(qpos, np.float64), np.ascontiguousarray(qvel, np.float64)
+        _chk(self.lib.uhc_set_neutral_pose(self.h, q.ctypes.data_as(C.POINTER(C.c_double)), v.ctypes.data_as(C.POINTER(C.c_double))))
+        self.neutral = (q.copy(), v.copy())
 
     def close(self):
         if getattr(self, "h", None):

@@ -74,8 +74,9 @@ class MLPNet:
         self.W, self.b = [], []
         for i in range(len(self.dims) - 1):  # nn.Linear default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias
             k = 1.0 / math.sqrt(self.dims[i])
-            w = (torch.rand(self.dims[i + 1], self.dims[i], generator=g) * 2 - 1) * k
-            bb = (torch.rand(self.dims[i + 1], generator=g) * 2 - 1) * k
+            # explicit dtype: the reference's scripts set torch.set_default_dtype(float64) (train_uhc.py:80-81); the seeded stream must not depend on it
+            w = (torch.rand(self.dims[i + 1], self.dims[i], generator=g, dtype=torch.float32) * 2 - 1) * k
+            bb = (torch.rand(self.dims[i + 1], generator=g, dtype=torch.float32) * 2 - 1) * k
             if i == len(self.dims) - 2:  # policy_gaussian.py:20-21 / critic.py:12-13
                 w, bb = w * 0.1, bb * 0.0
             (ow, nw), (ob, nb) = offs[2 * i], offs[2 * i + 1]
@@ -388,13 +389,13 @@ class ZFilter:
         """exact restore from a RunningStat's (n, mean, sum of squared deviations)"""
         import torch
         s = np.concatenate([[float(n)], np.asarray(mean, dtype=np.float64).reshape(-1), np.asarray(S, dtype=np.float64).reshape(-1)])
-        self.stats.copy_(torch.as_tensor(s))
+        self.stats.copy_(torch.as_tensor(s, dtype=torch.float64))
 
     def load(self, n, mean, std):
         import torch
         var = np.asarray(std, dtype=np.float64) ** 2
         s = np.concatenate([[float(n)], np.asarray(mean, dtype=np.float64), var * (max(n, 2) - 1)])
-        self.stats.copy_(torch.as_tensor(s))
+        self.stats.copy_(torch.as_tensor(s, dtype=torch.float64))
 
 
 def gaussian_sample(mean, log_std, seed, step, mean_action=None, out_action=None, out_logp=None):
