@@ -253,22 +253,33 @@ __global__ void k_normalize(float *__restrict__ x, size_t n, const double *__res
 // Batched form: Chan et al. merge of the batch moments into the running (n, mean, S) state, then normalise the batch with the
 // UPDATED statistics (the reference pushes then normalises each sample; sequential-vs-batched order is the documented deviation).
 // stats layout: [0] = n (as double), then mean[D], S[D] (doubles).  One block per 32 dims (column reduction).
-__global__ void k_zfilter_update(const float *__restrict__ X, int M, int D, double *__restrict__ stats) {
+constexpr int ZF_CHUNKS = 16;   // row chunks of the batch-moment pass (deterministic two-stage reduction: partials, then a fixed-order merge)
+// stage 1: block (column tile, row chunk) -> partial (sum, sum of squares) of its rows for 32 columns, into ws[chunk][D][2]
+__global__ void k_zfilter_partial(const float *__restrict__ X, int M, int D, double *__restrict__ ws) {
     __shared__ double rs[32][33], rq[32][33];
-    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int j = blockIdx.x * 32 + threadIdx.x, ch = blockIdx.y;
+    const int r0 = (int)(((long)M * ch) / ZF_CHUNKS), r1 = (int)(((long)M * (ch + 1)) / ZF_CHUNKS);
     double s = 0.0, q = 0.0;
-    if (j < D) for (int i = threadIdx.y; i < M; i += blockDim.y) { const double v = X[(size_t)i * D + j]; s += v; q += v * v; }
+    if (j < D) for (int i = r0 + threadIdx.y; i < r1; i += blockDim.y) { const double v = X[(size_t)i * D + j]; s += v; q += v * v; }
     rs[threadIdx.y][threadIdx.x] = s; rq[threadIdx.y][threadIdx.x] = q;
     __syncthreads();
     if (threadIdx.y == 0 && j < D) {
         double S1 = 0.0, S2 = 0.0;
         for (int k = 0; k < 32; k++) { S1 += rs[k][threadIdx.x]; S2 += rq[k][threadIdx.x]; }
-        const double nb = (double)M, mb = S1 / nb, Sb = S2 - nb * mb * mb;
-        const double na = stats[0], ma = stats[1 + j], Sa = stats[1 + D + j];
-        const double n = na + nb, dlt = mb - ma;
-        stats[1 + j] = ma + dlt * nb / n;
-        stats[1 + D + j] = Sa + Sb + dlt * dlt * na * nb / n;
+        ws[((size_t)ch * D + j) * 2] = S1; ws[((size_t)ch * D + j) * 2 + 1] = S2;
     }
+}
+// stage 2: fixed-order sum of the chunk partials, Chan merge into the running (n, mean, S); thread D bumps the count last
+__global__ void k_zfilter_merge(int M, int D, double *__restrict__ stats, const double *__restrict__ ws) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= D) return;
+    double S1 = 0.0, S2 = 0.0;
+    for (int ch = 0; ch < ZF_CHUNKS; ch++) { S1 += ws[((size_t)ch * D + j) * 2]; S2 += ws[((size_t)ch * D + j) * 2 + 1]; }
+    const double nb = (double)M, mb = S1 / nb, Sb = S2 - nb * mb * mb;
+    const double na = stats[0], ma = stats[1 + j], Sa = stats[1 + D + j];
+    const double n = na + nb, dlt = mb - ma;
+    stats[1 + j] = ma + dlt * nb / n;
+    stats[1 + D + j] = Sa + Sb + dlt * dlt * na * nb / n;
 }
 __global__ void k_zfilter_count(double *stats, int M) { stats[0] += (double)M; }
 __global__ void k_zfilter_apply(const float *__restrict__ X, float *__restrict__ Y, int M, int D, const double *__restrict__ stats, float clip) {
@@ -355,10 +366,20 @@ int uhc_adv_normalize(float *adv, long n, const double *mom2_dev, const double *
     k_normalize<<<592, 256, 0, (cudaStream_t)stream>>>(adv, (size_t)n, mom2_dev, ntotal_dev); CKN(cudaGetLastError());
     return 0;
 }
+int uhc_zfilter_workspace_doubles(int D) { return ZF_CHUNKS * D * 2; }
 int uhc_zfilter(const float *x, float *y, int M, int D, double *stats, float clip, int update, void *stream) {
+    // without a caller workspace: one per (thread, D), allocated on first use (not legal inside a stream capture -- the rollout passes its own)
+    static thread_local double *ws = nullptr; static thread_local int ws_d = 0, ws_dev = -1;
+    int dev = 0; cudaGetDevice(&dev);
+    if (update && (!ws || ws_d < D || ws_dev != dev)) { if (ws && ws_dev == dev) cudaFree(ws); CKN(cudaMalloc((void **)&ws, (size_t)uhc_zfilter_workspace_doubles(D) * sizeof(double))); ws_d = D; ws_dev = dev; }
+    return uhc_zfilter_ws(x, y, M, D, stats, clip, update, ws, stream);
+}
+int uhc_zfilter_ws(const float *x, float *y, int M, int D, double *stats, float clip, int update, double *workspace, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (update) {
-        k_zfilter_update<<<(D + 31) / 32, dim3(32, 32), 0, st>>>(x, M, D, stats); CKN(cudaGetLastError());
+        if (!workspace) { g_nn_err = "uhc_zfilter_ws: workspace is null"; return -2; }
+        k_zfilter_partial<<<dim3((D + 31) / 32, ZF_CHUNKS), dim3(32, 32), 0, st>>>(x, M, D, workspace); CKN(cudaGetLastError());
+        k_zfilter_merge<<<(D + 127) / 128, 128, 0, st>>>(M, D, stats, workspace); CKN(cudaGetLastError());
         k_zfilter_count<<<1, 1, 0, st>>>(stats, M); CKN(cudaGetLastError());
     }
     if (y) { k_zfilter_apply<<<592, 256, 0, st>>>(x, y, M, D, stats, clip); CKN(cudaGetLastError()); }

@@ -3,7 +3,7 @@
 // Replaces the reference's per-process Python loop  Agent.sample_worker  (uhc/agents/agent_copycat.py:496-571:
 //   state -> running_state -> policy_net.select_action -> env.step -> custom_reward -> memory.push(state, action, mask, reward, exp))
 // by T lock-step control steps of all E device-resident environments.  One control step is
-//   k_zfilter_update, k_zfilter_count, k_zfilter_apply_bf16   obs -> normalised state (buffer row, fp32) + bf16 K-padded copy      (a12)
+//   k_zfilter_partial, _merge, _count, k_zfilter_apply_bf16   obs -> normalised state (buffer row, fp32) + bf16 K-padded copy      (a12)
 //   4 x k_linear_tc                                           policy MLP on tensor cores (tcgen05 / TMEM / TMA, mlp_tcgen05.cu)      (a13)
 //   k_gauss_sample_dev                                        action + log-prob into the buffer row                                  (a13)
 //   k_env_step                                                15 physics substeps + obs + reward + termination + in-kernel re-seeding (a1-a10)
@@ -108,6 +108,7 @@ struct RolloutCtx {
     UhcEngine *eng = nullptr; int E = 0, device = 0;
     unsigned long long *d_step = nullptr;
     void *acts[9] = {nullptr}; int act_ld[9] = {0}; float *d_mean = nullptr; int mean_cap = 0;
+    double *d_zws = nullptr; int zws_d = 0;
     unsigned char *d_mean_action = nullptr; float *d_cinfo = nullptr, *d_pct = nullptr; int *d_fail = nullptr, *d_end = nullptr;
     std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
     int launches_per_step = 0;
@@ -131,6 +132,12 @@ int ensure_scratch(RolloutCtx *c, const UhcMlp *m) {
         CKR(cudaMalloc((void **)&c->d_fail, E * 4)); CKR(cudaMalloc((void **)&c->d_end, E * 4));
     }
     if (m->nlayers < 1 || m->nlayers > 8) { g_ro_err = "UhcMlp: 1..8 layers"; return -2; }
+    if (c->zws_d < m->dims[0]) {
+        if (c->d_zws) cudaFree(c->d_zws);
+        CKR(cudaMalloc((void **)&c->d_zws, (size_t)uhc_zfilter_workspace_doubles(m->dims[0]) * sizeof(double))); c->zws_d = m->dims[0];
+        for (auto &g : c->graphs) cudaGraphExecDestroy(g.second);
+        c->graphs.clear();
+    }
     for (int i = 0; i < m->nlayers; i++) {   // bf16 activations, K padded to 64 and zero filled once (the GEMMs write the first N columns only)
         const int ld = pad64(m->dims[i]);
         if (m->kp[i] != ld) { g_ro_err = "UhcMlp: kp[i] must be dims[i] rounded up to 64"; return -2; }
@@ -151,7 +158,7 @@ int ensure_scratch(RolloutCtx *c, const UhcMlp *m) {
 int enqueue_policy(RolloutCtx *c, const float *obs, const UhcMlp *m, double *zstats, float zclip, int update_filter, float *state_out, cudaStream_t st) {
     const int E = c->E, D = m->dims[0];
     int n = 0;
-    if (update_filter) { CKC(uhc_zfilter(obs, nullptr, E, D, zstats, zclip, 1, st), "zfilter update"); n += 2; }
+    if (update_filter) { CKC(uhc_zfilter_ws(obs, nullptr, E, D, zstats, zclip, 1, c->d_zws, st), "zfilter update"); n += 3; }
     k_zfilter_apply_bf16<<<1184, 256, 0, st>>>(obs, state_out, (unsigned short *)c->acts[0], E, D, m->kp[0], zstats, zclip);
     CKR(cudaGetLastError()); n++;
     for (int i = 0; i < m->nlayers; i++) {
@@ -296,7 +303,7 @@ void uhc_rollout_release(UhcEngine *e) {   // called by the binding before uhc_e
         for (cudaEvent_t ev : c->ev0) cudaEventDestroy(ev);
         for (cudaEvent_t ev : c->ev1) cudaEventDestroy(ev);
         for (void *p : c->acts) if (p) cudaFree(p);
-        for (void *p : {(void *)c->d_step, (void *)c->d_mean, (void *)c->d_mean_action, (void *)c->d_cinfo, (void *)c->d_pct, (void *)c->d_fail, (void *)c->d_end}) if (p) cudaFree(p);
+        for (void *p : {(void *)c->d_zws, (void *)c->d_step, (void *)c->d_mean, (void *)c->d_mean_action, (void *)c->d_cinfo, (void *)c->d_pct, (void *)c->d_fail, (void *)c->d_end}) if (p) cudaFree(p);
         delete c; g_ctx.erase(g_ctx.begin() + i); return;
     }
 }
