@@ -311,6 +311,9 @@ def run_gpu(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = E * world * Ke / float(te.item())
     counters = agent.engine.counters
+    st = agent.engine.get_states()        # solver work of the last control step (what the step time is made of)
+    counters.update(newton_iters_per_env_step=float(st["newton_iters"].mean()), newton_iters_max=int(st["newton_iters"].max()),
+                    max_contacts_per_env_step_mean=float(st["ncon"].mean()))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -68,12 +68,13 @@ static int emu_forward_given_tau(const Model<Real> &m, const EnvCfg<Real> &cfg, 
     for (int i = 0; i < NV; i++) { Real f = -w.C[i] + (i < 6 ? (Real)fapp_d[i] : w.tau[i - 6]); w.fs[i] = f; w.as_[i] = f; }
     if (w.ncon == 0) { aba_solve(m, w, Real(0), false, w.as_); for (int i = 0; i < NV; i++) w.a[i] = w.as_[i]; return 0; }
     constraint_setup(m, w);
-    Real scale = newton_init(m, w, tp);
+    Real gn2 = 0;
+    const Real scale = newton_init(m, w, tp, &gn2);
     int iters = 0;
-    while (iters < cfg.newton_max_iter && newton_prepare(m, cfg, w, scale, tp)) {
+    while (iters < cfg.newton_max_iter && gn2 > cfg.newton_tol * cfg.newton_tol * scale * scale) {
         ++iters;
         aba_solve(m, w, Real(0), true, w.p);
-        if (newton_advance(m, w, tp)) break;
+        if (newton_advance(m, w, tp, &gn2)) break;
     }
     return iters;
 }

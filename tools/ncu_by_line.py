@@ -6,7 +6,7 @@ import csv, io, re, subprocess, sys, collections, os, tempfile
 
 rep, ksub = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-so = os.path.join(os.path.dirname(__file__), "..", "uhc_b200", "libuhc_b200.so")
+so = os.environ.get("UHC_PROF_SO") or os.path.join(os.path.dirname(__file__), "..", "uhc_b200", "libuhc_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
 offs = {}

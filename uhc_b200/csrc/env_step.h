@@ -127,7 +127,7 @@ UHC_DEV void load_state(const EngineView<Real> &ev, int env, Work<Real> &w, int 
     __syncwarp();
 #else
     (void)parity;
-    for (int i = 0; i < ST_BLOCK; i++) w.q[i] = st[i];       // q v aw C Ib S are contiguous in Work exactly as in the record
+    { Real *head = reinterpret_cast<Real *>(&w); for (int i = 0; i < ST_BLOCK; i++) head[i] = st[i]; }       // q v aw C Ib S are contiguous in Work exactly as in the record
 #endif
 }
 template <class Real>
@@ -145,7 +145,7 @@ UHC_DEV void store_state(const EngineView<Real> &ev, int env, Work<Real> &w) {
     }
     __syncwarp();
 #else
-    for (int i = 0; i < ST_BLOCK; i++) st[i] = w.q[i];
+    { const Real *head = reinterpret_cast<const Real *>(&w); for (int i = 0; i < ST_BLOCK; i++) st[i] = head[i]; }
     for (int i = 0; i < 72; i++) { st[ST_XPOS + i] = (&w.xpos[0][0])[i]; st[ST_XIPOS + i] = (&w.xipos[0][0])[i]; }
     for (int i = 0; i < 96; i++) st[ST_XQUAT + i] = (&w.xquat[0][0])[i];
 #endif

@@ -115,7 +115,7 @@ struct Work {
     Real act[ACT_DIM + 3];
     alignas(16) Real aU[NV + 6][6];   // articulated-body sweep: columns of  U D^-1  per 3-dof block (U = IA S, D = S^T U + arm)
     Real au[NV + 6];                // D^-1 u per block
-    Real fs[NV + 1], as_[NV + 1], a[NV + 1], Ma[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];
+    Real fs[NV + 1], as_[NV + 1], a[NV + 1], g[NV + 1], p[NV + 1], Mp[NV + 1], tau[NV + 1];   // Mp: the solve's joint-space diagonal
     alignas(16) Real Vb[NB][6], Ab[NB][6], Fb[NB][6];
     // contacts
     int cbody[MAXCON]; Real cr[MAXCON][3], cdist[MAXCON], cD[MAXCON], caref[MAXCON][4], cres[MAXCON][4], cjp[MAXCON][4];
@@ -278,12 +278,15 @@ template <class R, int K> UHC_DEV void subtree_sum(R (&x)[K], int sub_end, int l
         x[i] = hi - (lane > 0 ? lo : R(0));
     }
 }
-// root -> leaves accumulation along the tree: x_b <- x_b + x_parent(b), level by level
-template <class R, int K> UHC_DEV void ancestor_sum(R (&x)[K], int parent, int depth) {
-#pragma unroll 1
-    for (int lvl = 1; lvl <= MAXLEVEL; ++lvl) {
+// root -> leaves accumulation along the tree, x_b <- sum over the chain root .. b, by pointer jumping: after round k every lane holds the sum of
+// its 2^(k+1) nearest ancestors-or-self (chains are at most MAXLEVEL + 1 = 9 bodies long -> 4 rounds instead of one per level)
+template <class R, int K> UHC_DEV void ancestor_sum(R (&x)[K], int a1, int a2, int a4, int a8) {
+    static_assert(MAXLEVEL + 1 <= 16, "four pointer-jumping rounds cover chains of 16 bodies");
 #pragma unroll
-        for (int i = 0; i < K; i++) { const R t = __shfl_sync(0xffffffffu, x[i], parent < 0 ? 0 : parent); if (depth == lvl) x[i] += t; }
+    for (int rnd = 0; rnd < 4; ++rnd) {
+        const int src = rnd == 0 ? a1 : (rnd == 1 ? a2 : (rnd == 2 ? a4 : a8));
+#pragma unroll
+        for (int i = 0; i < K; i++) { const R t = __shfl_sync(0xffffffffu, x[i], src < 0 ? 0 : src); if (src >= 0) x[i] += t; }
     }
 }
 #define WSUBTREE(n, K, tp) subtree_sum<Real, K>(n, tp.sub_end, tp.lane)
@@ -297,7 +300,7 @@ template <class R, int K> UHC_DEV void prefix_sum(R (&x)[K], int lane) {   // in
     }
 }
 #define WPREFIX(n, K) prefix_sum<Real, K>(n, (int)(threadIdx.x & 31))
-#define WANCESTOR(n, K, tp) ancestor_sum<Real, K>(n, tp.parent, tp.depth)
+#define WANCESTOR(n, K, tp) ancestor_sum<Real, K>(n, tp.parent, tp.anc2, tp.anc4, tp.anc8)
 #else
 template <class R> static R emu_sum(const R *x) { R s = 0; for (int i = 0; i < 32; i++) s += x[i]; return s; }
 template <class R> static R emu_max(const R *x) { R s = x[0]; for (int i = 1; i < 32; i++) s = x[i] > s ? x[i] : s; return s; }
@@ -329,7 +332,7 @@ UHC_DEV int popc_(unsigned x) { int c = 0; while (x) { x &= x - 1; c++; } return
 // so one O(n) articulated-body sweep solves all three without ever forming the joint-space matrix: lane = body, articulated
 // inertia (sym 6x6) / bias wrench in registers, leaves -> root then root -> leaves, children/parent exchange by warp shuffles.
 // World-aligned spatial quantities about the common point O need no frame transforms between bodies.
-struct LaneTopo { int lane, parent, depth, sub_end, ch0, ch1, ch2, hadr, hnum; };   // lane = body: tree links, hull vertex range
+struct LaneTopo { signed char lane, parent, depth, sub_end, ch0, ch1, ch2, anc2, anc4, anc8; short hnum; int hadr; };   // lane = body: tree links (anc_k: ancestor k levels up, -1 = none), hull vertex range
 template <class Real>
 UHC_DEV LaneTopo lane_topo(const Model<Real> &m, int lane) {
     LaneTopo t; t.lane = lane;
@@ -340,6 +343,10 @@ UHC_DEV LaneTopo lane_topo(const Model<Real> &m, int lane) {
     t.ch1 = (lane < NB && c0 + 1 < c1) ? UHC_LDG(m.child + c0 + 1) : -1;
     t.ch2 = (lane < NB && c0 + 2 < c1) ? UHC_LDG(m.child + c0 + 2) : -1;
     t.hadr = UHC_LDG(m.hull_adr + b); t.hnum = lane < NB ? UHC_LDG(m.hull_num + b) : 0;
+    int a = lane < NB ? b : -1;
+    t.anc2 = t.anc4 = t.anc8 = -1;
+    for (int k = 1; k <= 8 && a >= 0; ++k) { a = a > 0 ? UHC_LDG(m.parent + a) : -1; if (k == 2) t.anc2 = a; if (k == 4) t.anc4 = a; if (k == 8) t.anc8 = a; }
+    if (lane >= NB) t.parent = -1;
     return t;
 }
 #ifndef UHC_EMU
@@ -446,7 +453,7 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
     typedef Pr<Real> P;
     LVARA(P, row, 3); LVARA(P, pA, 3); LVARA(P, nrow, 3); LVARA(P, npA, 3); LVARA(Real, trow, 6); LVARA(Real, tpA, 6);
     LVARA(Real, Ur, 3);
-    Real *arm = w.Mp;     // joint-space diagonal (armature + arm_scale kd); Mp is only live inside newton_advance
+    Real *arm = w.Mp;     // joint-space diagonal (armature + arm_scale kd)
     LVAR(int, body); LVAR(int, src); LVAR(int, act); LVAR(int, rr); LVAR(int, ent); LVAR(int, entn);
     const int nlvl = (UHC_LDT(m.lvl_pack) >> 26) & 15;
     LANES_BEGIN
@@ -578,6 +585,10 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
             }
         }
         for (int i = 0; i < 3; i++) { LVA(pacc)[2 * i] = a[i].x; LVA(pacc)[2 * i + 1] = a[i].y; }
+        if (use_contacts && b >= 0) {   // the body's spatial acceleration J_b x for the Newton step's contact rows (lane r of the group stores component r)
+            const P t = r < 2 ? a[0] : (r < 4 ? a[1] : a[2]);
+            w.Ab[b][r] = (r & 1) ? t.y : t.x;
+        }
         LANES_END
     }
 }
@@ -857,7 +868,7 @@ UHC_DEVNI void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)
     LANES_END
 }
 // body wrenches from per-row multipliers (force on the body along d_e at the contact point), then subtree sums.
-// mode 0: lam = D r_-  (gradient term J^T D r_-) ; mode 1: lam = D [r<0] jp  (J^T D_act J p)
+// mode 0: lam = D r_-  (gradient term J^T D r_-) ; mode 2: lam = the multipliers the caller left in cjp
 // lane = contact: wrench of each contact about O; contacts are ordered by body and bodies depth-first, so the wrench of
 // subtree(b) is a contiguous range of contacts = a difference of two inclusive prefix sums (second 32-chunk only when needed).
 template <class Real, class TPT>
@@ -874,7 +885,7 @@ UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real
             const Real D = w.cD[c];
             Real l[4];
 #pragma unroll
-            for (int e = 0; e < 4; e++) { const Real r = w.cres[c][e]; l[e] = r < 0 ? D * (mode ? w.cjp[c][e] : r) : Real(0); }
+            for (int e = 0; e < 4; e++) { const Real r = w.cres[c][e]; l[e] = mode == 2 ? w.cjp[c][e] : (r < 0 ? D * r : Real(0)); }
             const Real f[3] = {m.mu * (l[3] - l[2]), m.mu * (l[0] - l[1]), (l[0] + l[1]) + (l[2] + l[3])};
             Real t[3];
             cross3(w.cr[c], f, t);
@@ -917,74 +928,62 @@ UHC_DEVNI void contact_force(const Model<Real> &m, Work<Real> &w, int mode, Real
 }
 
 // ================================================================================================ constraint solve
-// min_a 1/2 (a-a_s)^T M (a-a_s) + sum_rows 1/2 D min(0, J a - aref)^2 ; primal Newton.  The Hessian M + J^T D_act J is never formed:
-// the Newton direction is one articulated-body solve with contact-augmented body inertias (aba_solve, use_contacts).
-// newton_init: start from the warm start (previous qacc, as MuJoCo's warmstart): residuals J a - aref and M a by O(n) passes.
-// The problem is strictly convex, so the minimiser does not depend on the start; starting from the warm start makes the
-// unconstrained solve a_s = M^-1 f_s unnecessary whenever contacts are present.  Returns the gradient-norm scale.
+// min_a 1/2 (a-a_s)^T M (a-a_s) + sum_rows 1/2 D min(0, J a - aref)^2 ; primal Newton.  The Hessian H = M + J^T D_act J is never formed:
+// the Newton direction is one articulated-body solve with contact-augmented body inertias (aba_solve, use_contacts), and that solve's
+// centre -> leaves sweep leaves the body accelerations J_b p of its solution in w.Ab (what the contact rows J p need).
+//
+// The gradient is carried from iteration to iteration instead of being rebuilt: with r(al) = r + al J p and H p = -g,
+//     g(a + al p) = (1 - al) g + J^T D delta,    delta_row = r(al)_- - r_- - al [r < 0] (J p)_row = -|r(al)|  on rows whose active state
+// switched between 0 and al, and 0 on every other row -- so an iteration costs one solve, one pass over the contact rows and (only when
+// some row switched) one wrench pass; M a, M p and the smooth part of the gradient never appear.  The same identity gives the line search
+//     f'(al) = (1 - al) g.p + sum_switched D (J p) delta ,   f''(al) = -g.p + sum_switched (+-) D (J p)^2
+// exactly zero at al = 1 when no row switches: the full step is then the minimiser of the (locally quadratic) cost and the solve stops
+// without a confirming gradient evaluation.
+//
+// newton_init: start from the warm start (previous qacc, as MuJoCo's warmstart): residuals r = J a - aref, gradient g = M a - f_s + J^T D r_-
+// by O(n) passes, -g in w.p.  The problem is strictly convex, so the minimiser does not depend on the start; starting from the warm start
+// makes the unconstrained solve a_s = M^-1 f_s unnecessary whenever contacts are present.  Returns the gradient-norm scale, |g|^2 in *gn2.
 template <class Real, class TPT>
-UHC_DEV Real newton_init(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
+UHC_DEV Real newton_init(const Model<Real> &m, Work<Real> &w, const TPT &tp, Real *gn2) {
     tree_vel(m, w, w.aw, w.Ab, tp);
     contact_rows(m, w, w.Ab, w.cres, w.caref);
+    contact_force(m, w, 0, w.Fb, tp);
     LVARA(Real, Fm, 6);
     LANES_BEGIN
     for (int i = 0; i < 6; i++) LVA(Fm)[i] = 0;
     if (lane < NB) rigid_mul(w.Ib[lane], w.Ab[lane], LVA(Fm));
-    LANES_END
+    LANES_END_R
     WSUBTREE(Fm, 6, tp);
     LANES_BEGIN
-    if (lane < NB) for (int i = 0; i < 6; i++) w.Fb[lane][i] = LVA(Fm)[i];
+    if (lane < NB) for (int i = 0; i < 6; i++) w.Fb[lane][i] += LVA(Fm)[i];
     LANES_END
-    LVAR(Real, part);
-    LANES_BEGIN
-    for (int i = lane; i < NV; i += 32) {
-        const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        w.Ma[i] = pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b])) + UHC_LDT(m.dof_f + 4 * i) * w.aw[i];
-        w.a[i] = w.aw[i];
-    }
-    LV(part) = lane < NB ? 3 * w.Ib[lane][0] : Real(0);   // gradient tolerance scale ~ trace of the translational block of M
-    LANES_END
-    return WSUM(part);
-}
-// newton_prepare: gradient at the current point; returns false when converged, else leaves -g in w.p
-template <class Real, class TPT>
-UHC_DEV bool newton_prepare(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, Real scale, const TPT &tp) {
-    contact_force(m, w, 0, w.Fb, tp);
-    LVAR(Real, part);
+    LVAR(Real, part); LVAR(Real, gs);
     LANES_BEGIN
     Real s = 0;
     for (int i = lane; i < NV; i += 32) {
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        const Real gi = w.Ma[i] - w.fs[i] + pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b]));
-        w.g[i] = gi; w.p[i] = -gi; s += gi * gi;
+        const Real gi = pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b])) + UHC_LDT(m.dof_f + 4 * i) * w.aw[i] - w.fs[i];
+        w.g[i] = gi; w.p[i] = -gi; w.a[i] = w.aw[i]; s += gi * gi;
     }
-    LV(part) = s;
+    LV(gs) = s;
+    LV(part) = lane < NB ? 3 * w.Ib[lane][0] : Real(0);   // gradient tolerance scale ~ trace of the translational block of M
     LANES_END
-    const Real gn = WSUM(part);
-    if (!(gn > cfg.newton_tol * cfg.newton_tol * scale * scale)) return false;
-    return true;
+    *gn2 = WSUM(gs);
+    return WSUM(part);
 }
-// newton_advance: given the Newton direction in w.p: J p, M p, exact-ish line search, update a / M a / residuals
-// Returns true when the step was an exact Newton step: the full step (al = 1) zeroed the directional derivative and no constraint row
-// changed its active state on the way -- the cost is then quadratic along the whole step, the new point is its minimiser and the
-// gradient there is zero up to rounding, so the caller can stop without paying another gradient evaluation just to confirm it.
+// newton_advance: given the Newton direction in w.p (and J_b p in w.Ab, left there by the solve): J p, safeguarded 1-D Newton line search,
+// update of a / residuals / gradient (-g again in w.p).  Returns true when the step was an exact Newton step (al = 1, no row switched): the
+// new point is the minimiser and the carried gradient is exactly zero.
 template <class Real, class TPT>
-UHC_DEV bool newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp) {
-    tree_vel(m, w, w.p, w.Ab, tp);
+UHC_DEV bool newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp, Real *gn2) {
     contact_rows(m, w, w.Ab, w.cjp, (const Real (*)[4]) nullptr);
-    contact_force(m, w, 1, w.Fb, tp);
-    LVAR(Real, pa); LVAR(Real, pb);
+    LVAR(Real, pa);
     LANES_BEGIN
-    Real sA = 0, sB = 0;
-    for (int i = lane; i < NV; i += 32) {
-        const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        const Real mp = -w.g[i] - pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b]));
-        w.Mp[i] = mp; sA += (w.Ma[i] - w.fs[i]) * w.p[i]; sB += mp * w.p[i];
-    }
-    LV(pa) = sA; LV(pb) = sB;
-    LANES_END
-    const Real A0 = WSUM(pa), B0 = WSUM(pb);
-    // 1-D safeguarded Newton on f'(al) = A0 + al B0 + sum_rows D (r + al jp)_- jp   (piecewise linear, increasing)
+    Real sA = 0;
+    for (int i = lane; i < NV; i += 32) sA += w.g[i] * w.p[i];
+    LV(pa) = sA;
+    LANES_END_R
+    const Real gp = WSUM(pa);           // directional derivative at al = 0 (negative: p is a descent direction)
     Real lo = 0, hi = -1, al = 1;
     bool exact = false;
     for (int ls = 0; ls < 12; ++ls) {
@@ -992,25 +991,54 @@ UHC_DEV bool newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp) 
         LANES_BEGIN
         Real s1 = 0, s2 = 0; int ch = 0;
         for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) {
-            const Real r0 = w.cres[c][e], r = r0 + al * w.cjp[c][e];
-            if (r < 0) { s1 += w.cD[c] * r * w.cjp[c][e]; s2 += w.cD[c] * w.cjp[c][e] * w.cjp[c][e]; }
-            ch |= (r0 < 0) != (r < 0);
+            const Real r0 = w.cres[c][e], jp = w.cjp[c][e], r = r0 + al * jp;
+            if ((r0 < 0) != (r < 0)) { const Real dj = w.cD[c] * jp; s1 -= dj * abs_(r); s2 += (r < 0) ? dj * jp : -dj * jp; ch = 1; }
         }
         LV(d1) = s1; LV(d2) = s2; LV(chg) = ch;
-        LANES_END
-        const Real f1 = A0 + al * B0 + WSUM(d1), f2 = B0 + WSUM(d2);
+        LANES_END_R
+        const bool any = WBALLOT(chg) != 0;
+        const Real f1 = (1 - al) * gp + (any ? WSUM(d1) : Real(0)), f2 = -gp + (any ? WSUM(d2) : Real(0));
         if (f1 > 0) hi = al; else lo = al;
-        if (abs_(f1) <= Real(1e-6) * abs_(A0) + Real(1e-30)) { exact = ls == 0 && !WBALLOT(chg); break; }
-        Real nx = al - f1 / f2;
+        if (abs_(f1) <= Real(1e-6) * abs_(gp) + Real(1e-30)) { exact = ls == 0 && !any; break; }
+        Real nx = f2 > 0 ? al - f1 / f2 : Real(-1);
         if (!(nx > lo) || (hi > 0 && !(nx < hi))) nx = hi > 0 ? Real(0.5) * (lo + hi) : 2 * al;
         if (nx == al) break;
         al = nx;
     }
+    // a, residuals; multipliers D delta of the rows that switched between 0 and al (the others carry none) into cjp
+    LVAR(int, chg2);
     LANES_BEGIN
-    for (int i = lane; i < NV; i += 32) { w.a[i] += al * w.p[i]; w.Ma[i] += al * w.Mp[i]; }
-    for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) w.cres[c][e] += al * w.cjp[c][e];
+    for (int i = lane; i < NV; i += 32) w.a[i] += al * w.p[i];
+    int ch = 0;
+    for (int c = lane; c < w.ncon; c += 32) for (int e = 0; e < 4; e++) {
+        const Real r0 = w.cres[c][e], r = r0 + al * w.cjp[c][e];
+        const bool sw = (r0 < 0) != (r < 0);
+        w.cres[c][e] = r; w.cjp[c][e] = sw ? -w.cD[c] * abs_(r) : Real(0); ch |= sw;
+    }
+    LV(chg2) = ch;
     LANES_END
-    return exact;
+    const bool any2 = WBALLOT(chg2) != 0;
+    if (exact && !any2) {
+        LANES_BEGIN
+        for (int i = lane; i < NV; i += 32) { w.g[i] = 0; w.p[i] = 0; }
+        LANES_END
+        *gn2 = 0;
+        return true;
+    }
+    if (any2) contact_force(m, w, 2, w.Fb, tp);
+    LVAR(Real, gs);
+    LANES_BEGIN
+    Real s = 0;
+    for (int i = lane; i < NV; i += 32) {
+        const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
+        Real gi = (1 - al) * w.g[i];
+        if (any2) gi += pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b]));
+        w.g[i] = gi; w.p[i] = -gi; s += gi * gi;
+    }
+    LV(gs) = s;
+    LANES_END
+    *gn2 = WSUM(gs);
+    return false;
 }
 
 // ================================================================================================ task layer
@@ -1130,7 +1158,7 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
                              bool with_pd, OutT *torque_out, bool cta_sync = false) {
     int phase = with_pd ? PH_PD : PH_SMOOTH, iters = 0;
     bool done = false;
-    Real scale = 0;
+    Real scale = 0, gn2 = 0;
     for (;;) {
         // ---- phase set-up: right-hand side into the vector the solve runs on
         Real *rhs = w.p;
@@ -1156,7 +1184,7 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
             rhs = w.as_;
         } else {
             // (aligning the Newton iterations across the CTA as well was measured: the waiting costs more than it saves)
-            if (done || iters >= cfg.newton_max_iter || !newton_prepare(m, cfg, w, scale, tp)) break;
+            if (done || iters >= cfg.newton_max_iter || !(gn2 > cfg.newton_tol * cfg.newton_tol * scale * scale)) break;
             ++iters;
         }
         // ---- the one shared O(n) articulated-body solve (not needed for the smooth phase when contacts are present:
@@ -1173,10 +1201,10 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
                 done = true;
             } else {
                 constraint_setup(m, w);
-                scale = newton_init(m, w, tp);
+                scale = newton_init(m, w, tp, &gn2);
             }
             phase = PH_NEWTON;
-        } else if (newton_advance(m, w, tp)) done = true;
+        } else if (newton_advance(m, w, tp, &gn2)) done = true;
     }
     return iters;
 }

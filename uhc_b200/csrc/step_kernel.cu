@@ -91,7 +91,7 @@ k_env_reset(EngineView<Real> ev, int n, const int *__restrict__ ids, const int *
     const int env = ids[i];
     // optional overrides arrive as float; stage them through the work set's scratch vectors
     Real *qo = nullptr, *vo = nullptr;
-    if (qpos) { qo = w.Ma; vo = w.Mp; const int lane = threadIdx.x & 31;   // vectors untouched before the reset copies them out
+    if (qpos) { qo = w.as_; vo = w.Mp; const int lane = threadIdx.x & 31;   // vectors untouched before the reset copies them out
         for (int k = lane; k < NQ; k += 32) qo[k] = (Real)qpos[(size_t)i * NQ + k];
         for (int k = lane; k < NV; k += 32) vo[k] = qvel ? (Real)qvel[(size_t)i * NV + k] : Real(0);
         __syncwarp(); }
@@ -187,6 +187,9 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
 
 constexpr int EPB_F = UHC_EPB_F, EPB_D = 2;
 template <class Real, int EPB> constexpr size_t step_smem() { return EPB * sizeof(Work<Real>) + NV * 4 * sizeof(Real) + (MAXLEVEL + 1) * LVL_G * sizeof(int) + 32 * sizeof(LaneTopo); }  // environments (warps) per block
+// the fp32 step kernel is tuned for UHC_MIN_CTAS resident blocks per SM (sm_100: 228 KiB of shared memory per SM, 1 KiB reserved per block, ~1 KiB static here):
+// a few hundred bytes more in Work / LaneTopo silently halve the residency (measured: 1.27 -> 0.88 M env-steps/s), so it is a compile-time error
+static_assert(EPB_F != 7 || UHC_MIN_CTAS * (step_smem<float, EPB_F>() + 1024 + 1088) <= 228 * 1024, "k_env_step<float>: the work sets of UHC_MIN_CTAS blocks no longer fit one SM");
 
 extern "C" {
 
@@ -207,6 +210,9 @@ int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_e
     if (precision == 32) {
         CK(cudaFuncSetAttribute(k_env_step<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<float, EPB_F>()));
         CK(cudaFuncSetAttribute(k_env_reset<float, EPB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<float, EPB_F>()));
+        int resident = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_env_step<float, EPB_F>, 32 * EPB_F, step_smem<float, EPB_F>()));
+        if (EPB_F == 7 && resident < UHC_MIN_CTAS) { g_err = "uhc_engine_create: k_env_step<float> reaches only " + std::to_string(resident) + " resident block(s) per SM (built for " + std::to_string(UHC_MIN_CTAS) + ")"; delete e; return -3; }
     } else {
         CK(cudaFuncSetAttribute(k_env_step<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<double, EPB_D>()));
         CK(cudaFuncSetAttribute(k_env_reset<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<double, EPB_D>()));
