@@ -230,7 +230,7 @@ def run_gpu(args):
     agent.reset_envs()
     L, h = agent.engine.lib, agent.engine.h
     R = max(1, min(K, 32))                               # buffer rows in use: one CUDA graph (and one pair of kernel events) per row
-    buf = RolloutBuffer(R, E, agent.dev)
+    buf = RolloutBuffer(R, E, agent.dev, agent.act_dim)
     if L.uhc_rollout_time_env_step(h, C.c_int(R)) != 0:  # CUDA events around k_env_step, recorded on the launching stream inside the graph
         raise RuntimeError("uhc_rollout_time_env_step failed")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=agent.dev)
@@ -391,7 +391,7 @@ def run_train(args):
     agent = BatchedAgent(E, clips, shapes, device=local, seed=1, rank=rank, world=world, model=base, variants=variants, clip_models=clip_models,
                          num_optim_epoch=TRAIN_EPOCHS, t_min=15, t_max=300)
     agent.reset_envs()
-    buf = RolloutBuffer(T, E, agent.dev)
+    buf = RolloutBuffer(T, E, agent.dev, agent.act_dim)
     clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(W):
         agent.sample(T, buf); agent.update_params(buf)
@@ -400,7 +400,9 @@ def run_train(args):
         dist.barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 1)]
     phases = dict(gae_ms=0.0, epochs_ms=0.0, allreduce_ms=0.0, allreduce_bytes=0, allreduce_calls=0)
-    l0 = agent.engine.kernel_launches
+    def launches():       # env-step launches (engine) + the rollout's other kernels + the kernels uhc_ppo_update enqueued
+        return agent.engine.kernel_launches + agent.nn_launches + (agent._ctrainer.kernel_launches if agent._ctrainer is not None else 0)
+    l0 = launches()
     t_wall0 = time.time()
     ev[0].record()
     for k in range(K):
@@ -465,7 +467,8 @@ def run_train(args):
                               note="6 x parameters x N flop per epoch over the measured time of the 10 epochs (includes the activation-gradient / transpose / Adam kernels)"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=16,
                          note="the training iteration has no host inputs (observations, rollout buffer and weights are device resident); the host reads back the two loss scalars"),
-                gpu_launches=(agent.engine.kernel_launches - l0), clocks=clk)
+                gpu_launches=(launches() - l0), update_driver="uhc_ppo_update: one C-ABI call per iteration (V(s), GAE, epochs, Adam, gradient all-reduce on the job's ncclComm_t)",
+                clocks=clk)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -20,7 +20,8 @@ extern "C" {
 #define UHC_NV 75
 #define UHC_NU 69
 #define UHC_OBS_DIM 657
-#define UHC_ACT_DIM 105
+#define UHC_ACT_DIM 105       /* action width of the default configuration (implicit residual force + meta-PD) */
+#define UHC_MAX_ACT_DIM 315   /* explicit residual force + meta-PD */
 #define UHC_EX_SIZE 508   /* expert frame record: qpos76 qvel75 wbpos72 wbquat96 bquat96 bangvel72 ee_wpos15 com3 pad3 */
 #define UHC_BODYF 20
 
@@ -56,6 +57,11 @@ typedef struct {
     int reactive_v;         /* cfg.reactive_v (copycat_config.py:97): 1 = train-mode episodes start from the standing-neutral pose with probability reactive_rate */
     unsigned long long reset_seed;
     double reactive_rate;   /* cfg.reactive_rate (copycat_config.py:99, default 0.3) */
+    /* cfg.residual_force_mode (copycat_config.py:105-109, humanoid_im.py:231-243): 0 = "implicit" (root wrench, 6 action dims),
+     * 1 = "explicit" (contact point + force + torque per body through mj_applyFT, 9 x 24 action dims; reward world_rfc_explicit).
+     * The action row is [69 joint targets | residual-force dims | 30 meta-PD scales when meta_pd]: uhc_engine_act_dim() gives its width. */
+    int rfc_mode;
+    int vf_slot[UHC_NB];    /* explicit mode: residual-force slot of body b (the reference orders the slots by SMPL_BONE_ORDER_NAMES, smpl_parser.py:11-36) */
 } UhcEnvCfg;
 
 const char *uhc_last_error(void);
@@ -113,6 +119,7 @@ int uhc_engine_counters(UhcEngine *e, int *out4);
  * fraction `percent` as float bits -- what the reference appends to its per-clip success history (agent_copycat.py:561). */
 const int *uhc_episode_log_dev(const UhcEngine *e);
 int uhc_num_envs(const UhcEngine *e);
+int uhc_engine_act_dim(const UhcEngine *e);      /* env.action_dim (humanoid_im.py:250): 69 + (6 | 216) + (30 if meta_pd) */
 int uhc_kernel_launches(const UhcEngine *e);   /* kernels launched by this engine so far (bench `gpu_launches`) */
 
 #ifdef __cplusplus

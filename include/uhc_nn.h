@@ -12,6 +12,7 @@ extern "C" {
 enum { UHC_ACT_NONE = 0, UHC_ACT_GELU = 1, UHC_ACT_TANH = 2, UHC_ACT_RELU = 3, UHC_ACT_SIGMOID = 4 };  /* mlp.py:9-16 */
 
 const char *uhc_nn_last_error(void);
+const char *uhc_tc_last_error(void);   /* last error of the tensor-core entry points (uhc_linear_forward_tc*, uhc_transpose_bf16, uhc_dact_bf16) */
 
 /* nn.Linear + activation (khrylib/models/mlp.py:24-27):  y[M][N] = act(x[M][K] W[N][K]^T + b[N]); z (optional) = pre-activation. */
 int uhc_linear_forward(const float *x, const float *W, const float *b, float *y, float *z_or_null, int M, int N, int K, int act, void *stream);

@@ -142,6 +142,21 @@ class Env:
                             C.c_double(body_diff_thresh), C.c_int(meta_pd), C.c_int(env_episode_len),
                             C.c_int(trail_steps), _p(w_), _p(k_))
 
+    # residual-force slot order of the explicit mode: vf_bodies = SMPL_BONE_ORDER_NAMES (humanoid_im.py:236-237, smpl_parser.py:11-36)
+    SMPL_BONE_ORDER = ["Pelvis", "L_Hip", "R_Hip", "Torso", "L_Knee", "R_Knee", "Spine", "L_Ankle", "R_Ankle", "Chest", "L_Toe", "R_Toe", "Neck", "L_Thorax",
+                       "R_Thorax", "Head", "L_Shoulder", "R_Shoulder", "L_Elbow", "R_Elbow", "L_Wrist", "R_Wrist", "L_Hand", "R_Hand"]
+
+    def set_rfc_mode(self, explicit):
+        """residual_force_mode "explicit" (per-body contact point / force / torque, action dim 69 + 216 + 30) or "implicit" (root wrench, 105)"""
+        names = [str(n) for n in self.m.z["body_names"]]
+        vf_body = np.array([names.index(n) for n in self.SMPL_BONE_ORDER], dtype=np.int32)
+        lib().or_env_set_rfc_mode(self.h, C.c_int(int(bool(explicit))), vf_body.ctypes.data_as(C.POINTER(C.c_int)))
+        self.vf_body = vf_body
+
+    @property
+    def action_dim(self):
+        return lib().or_env_action_dim(self.h)
+
     def load_expert(self, ex, shape_obs=None):
         keys = ["qpos", "qvel", "wbpos", "wbquat", "bquat", "bangvel", "ee_wpos", "com"]
         self._ex = [np.ascontiguousarray(ex[k], dtype=np.float64) for k in keys]

@@ -421,6 +421,9 @@ typedef struct {
     int meta_pd, env_episode_len, trail_steps;
     double w[5], k[5];
     double torque[15][NU];            /* per-substep applied torque of the last step (curr_torque) */
+    int rfc_mode;                     /* 0 = implicit root wrench (6 action dims), 1 = explicit per-body forces (cfg.residual_force_mode, humanoid_im.py:231-243) */
+    int vf_dim;                       /* action dims of the residual force: 6, or 9 per body x 24 bodies */
+    int vf_body[NB];                  /* explicit: model body of residual-force slot i (vf_bodies = SMPL_BONE_ORDER_NAMES, humanoid_im.py:236-237) */
 } OrEnv;
 
 OrEnv *or_env_create(OrModel *m) {
@@ -430,8 +433,16 @@ OrEnv *or_env_create(OrModel *m) {
     e->env_episode_len = 100000; e->trail_steps = 0; e->mode_train = 1;
     double w[5] = {0.3, 0.1, 0.45, 0.1, 0.05}, k[5] = {2.0, 0.005, 5.0, 100.0, 1.0};
     memcpy(e->w, w, 40); memcpy(e->k, k, 40);
+    e->rfc_mode = 0; e->vf_dim = 6; for (int b = 0; b < NB; b++) e->vf_body[b] = b;
     return e;
 }
+/* residual_force_mode (copycat_config.py:105-109): explicit = contact point + force + torque per body (residual_force_torque = True,
+   residual_force_bodies = "all", residual_force_bodies_num = 1: the released uhc_explicit.yml); action = [69 joint targets | vf | 30 meta-PD] */
+void or_env_set_rfc_mode(OrEnv *e, int explicit_mode, const int *vf_body) {
+    e->rfc_mode = explicit_mode ? 1 : 0; e->vf_dim = explicit_mode ? 9*NB : 6;
+    if (vf_body) memcpy(e->vf_body, vf_body, sizeof e->vf_body);
+}
+int or_env_action_dim(const OrEnv *e) { return NU + e->vf_dim + (e->meta_pd ? 30 : 0); }
 void or_env_free(OrEnv *e) { if (e) { or_data_free(e->d); free(e); } }
 OrData *or_env_data(OrEnv *e) { return e->d; }
 void or_env_set_expert(OrEnv *e, int len, const double *qpos, const double *qvel, const double *wbpos, const double *wbquat,
@@ -484,7 +495,7 @@ static void or_compute_torque(OrEnv *e, const double *ctrl, int it, double *torq
     const double *tq = e->ex.qpos + NQ*ex_index(e, e->cur_t + 1) + 7;
     double kp[NV] = {0}, kd[NV] = {0}, err[NV] = {0}, rhs[NV];
     double sp = 1, sd = 1;
-    if (e->meta_pd) { sp = ctrl[NU+6+it] + 1; sd = ctrl[NU+6+it+15] + 1; if (sp < 0) sp = 0; if (sp > 10) sp = 10; if (sd < 0) sd = 0; if (sd > 10) sd = 10; }
+    if (e->meta_pd) { sp = ctrl[NU+e->vf_dim+it] + 1; sd = ctrl[NU+e->vf_dim+it+15] + 1; if (sp < 0) sp = 0; if (sp > 10) sp = 10; if (sd < 0) sd = 0; if (sd > 10) sd = 10; }
     for (int j = 0; j < NU; j++) {
         double base = tq[j], q = d->qpos[7+j];
         while (base - q > M_PI) base -= 2*M_PI;
@@ -502,6 +513,30 @@ static void or_rfc_implicit(OrEnv *e, const double *ctrl) { /* humanoid_im.py:11
     for (int i = 0; i < 6; i++) vf[i] = ctrl[NU+i]*e->rfc_scale*e->rfc_rate;
     remove_base_rot(e, e->d->qpos+3, crq); heading_q(crq, hq); q2mat(hq, R); mv(R, vf, t); memcpy(vf, t, 24);
     for (int i = 0; i < 6; i++) { if (vf[i] > e->rfc_lim) vf[i] = e->rfc_lim; if (vf[i] < -e->rfc_lim) vf[i] = -e->rfc_lim; e->d->qfrc_applied[i] = vf[i]; }
+}
+
+/* mj_applyFT restated: qfrc += J(point, body)^T [force; torque].  The reference calls it between two sim.step() (humanoid_im.py:1122-1130), so the
+   Jacobian is built from the kinematics of the LAST forward pass (data.xpos / joint axes), not from the integrated qpos. */
+void or_apply_ft(const OrModel *m, const OrData *d, const double *force, const double *torque, const double *point, int body, double *qfrc) {
+    static double Jv[3][NV], Jw[3][NV];
+    or_jac(m, d, body, point, Jv, Jw);
+    for (int i = 0; i < NV; i++)
+        qfrc[i] += Jv[0][i]*force[0] + Jv[1][i]*force[1] + Jv[2][i]*force[2] + Jw[0][i]*torque[0] + Jw[1][i]*torque[1] + Jw[2][i]*torque[2];
+}
+/* humanoid_im.py:1080-1132 with the release settings (no contact gating: residual_contact_only = False; no projection; one point per body):
+   per body a contact point, a force and a torque in the BODY frame of the last forward pass (mujoco_env.py:171-180), scaled by
+   residual_force_scale, applied through mj_applyFT; qfrc_applied is replaced, not accumulated. */
+static void or_rfc_explicit(OrEnv *e, const double *ctrl) {
+    OrData *d = e->d; double qfrc[NV] = {0};
+    for (int i = 0; i < NB; i++) {
+        const int b = e->vf_body[i]; const double *v = ctrl + NU + 9*i, *R = d->xmat[b];
+        double f[3] = {v[3]*e->rfc_scale, v[4]*e->rfc_scale, v[5]*e->rfc_scale}, tq[3] = {v[6]*e->rfc_scale, v[7]*e->rfc_scale, v[8]*e->rfc_scale};
+        double p[3], fw[3], tw[3];
+        mv(R, v, p); mv(R, f, fw); mv(R, tq, tw);
+        for (int k = 0; k < 3; k++) p[k] += d->xpos[b][k];
+        or_apply_ft(e->m, d, fw, tw, p, b, qfrc);
+    }
+    memcpy(d->qfrc_applied, qfrc, sizeof qfrc);
 }
 
 void or_obs_v2(const OrEnv *e, double *obs) { /* humanoid_im.py:419-503, obs_coord = "root" */
@@ -557,11 +592,13 @@ double or_reward(const OrEnv *e, const double *action, double *cinfo) { /* rewar
         double c = dq[0]; if (c > 1) c = 1; if (c < -1) c = -1;
         double a = acos(c)*w; pose2 += a*a;
         qinv(e->prev_bquat+4*b, iq); qmul(cur_bq+4*b, iq, dq); rot_from_quat(dq, rv);
-        for (int k = 0; k < 3; k++) { double dv = (rv[k]/dt - e_bav[3*b+k])*e->m->diffw[b]; vel2 += dv*dv; }
+        /* world_rfc_implicit weights the angular-velocity error by jpos_diffw (reward_function.py:50-51); world_rfc_explicit does not (:253-341) */
+        for (int k = 0; k < 3; k++) { double dv = (rv[k]/dt - e_bav[3*b+k])*(e->rfc_mode ? 1.0 : e->m->diffw[b]); vel2 += dv*dv; }
     }
     for (int i = 0; i < 5; i++) for (int k = 0; k < 3; k++) { double x = d->xpos[e->m->ee[i]][k] - e_ee[3*i+k]; ee2 += x*x; }
     for (int k = 0; k < 3; k++) { double x = d->xipos[0][k] - e_com[k]; com2 += x*x; }
-    for (int i = 0; i < 6; i++) vf2 += action[NU+i]*action[NU+i];
+    if (!e->rfc_mode) for (int i = 0; i < 6; i++) vf2 += action[NU+i]*action[NU+i];
+    else for (int i = 0; i < NB; i++) for (int k = 3; k < 9; k++) vf2 += action[NU+9*i+k]*action[NU+9*i+k];   /* force + torque part of every body's slot (:321-327) */
     cinfo[0] = exp(-e->k[0]*pose2); cinfo[1] = exp(-e->k[1]*vel2); cinfo[2] = exp(-e->k[2]*ee2); cinfo[3] = exp(-e->k[3]*com2); cinfo[4] = exp(-e->k[4]*vf2);
     double r = 0, ws = 0; for (int i = 0; i < 5; i++) { r += e->w[i]*cinfo[i]; ws += e->w[i]; }
     return r/ws;
@@ -589,7 +626,7 @@ int or_env_step(OrEnv *e, const double *action, double *obs, int *fail, int *end
         double tq[NU];
         or_compute_torque(e, action, i, tq);
         for (int j = 0; j < NU; j++) { if (tq[j] > e->m->tlim[j]) tq[j] = e->m->tlim[j]; if (tq[j] < -e->m->tlim[j]) tq[j] = -e->m->tlim[j]; d->ctrl[j] = tq[j]; e->torque[i][j] = tq[j]; }
-        or_rfc_implicit(e, action);
+        if (e->rfc_mode) or_rfc_explicit(e, action); else or_rfc_implicit(e, action);
         or_step(e->m, d);
     }
     e->cur_t += 1;

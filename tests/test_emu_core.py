@@ -104,3 +104,27 @@ def test_env_trace_matches_reference_golden(golden_dir, prec, tol_q, tol_o):
         assert np.abs(obs - g["obs"][t]).max() < tol_o, t
         assert abs(r - g["reward"][t]) < tol_o
         assert info["fail"] == bool(g["fail"][t])
+
+
+@pytest.mark.parametrize("prec,tol_q,tol_o", [(64, 1e-10, 1e-8), (32, 2e-4, 4e-3)])
+def test_explicit_residual_force_trace_matches_reference_golden(golden_dir, prec, tol_q, tol_o):
+    """residual_force_mode = explicit (config/release/uhc_explicit.yml): the kernel source (per-body wrenches about the stale root position,
+    projected through the stale motion subspaces; action = 69 + 216 + 30; world_rfc_explicit reward) against the reference's own Python."""
+    from uhc_b200.model import HumanoidModel
+    g = np.load(os.path.join(golden_dir, "env_sway_explicit_noise.npz"))
+    z = np.load(os.path.join(golden_dir, "expert_sway.npz"))
+    ex = {k: z[k] for k in z.files}
+    so = np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+    import ctypes as C
+    e = Emu(prec, rfc_mode=1, vf_slot=(C.c_int * 24)(*HumanoidModel().vf_slot()))
+    e.load_clips([ex], [so])
+    obs0 = e.reset()
+    assert np.abs(obs0 - g["obs0"]).max() < max(tol_o * 1e-2, 1e-12)
+    first_fail = int(np.argmax(g["fail"]))
+    for t in range(first_fail):
+        obs, r, done, info = e.step(g["action"][t])
+        st, _ = e.state()
+        assert np.abs(st[:76] - g["qpos"][t]).max() < tol_q, t
+        assert np.abs(obs - g["obs"][t]).max() < tol_o, t
+        assert abs(r - g["reward"][t]) < tol_o and np.abs(info["c_info"] - g["c_info"][t]).max() < tol_o
+        assert info["fail"] == bool(g["fail"][t])

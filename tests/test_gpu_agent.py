@@ -53,3 +53,20 @@ def test_deterministic_rollout_given_seed(golden_dir):
     ba, _ = a.sample(6)
     bb, _ = b.sample(6)
     assert (ba.actions == bb.actions).all() and (ba.rewards == bb.rewards).all()
+
+
+def test_explicit_residual_force_train_iteration(golden_dir):
+    """uhc_explicit shape end to end: 315-wide actions through uhc_rollout (CUDA graph) and uhc_ppo_update."""
+    import torch
+    from uhc_b200.agent import BatchedAgent
+    z = np.load(os.path.join(golden_dir, "expert_sway.npz"))
+    ex = {k: z[k] for k in z.files}
+    so = np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+    ag = BatchedAgent(64, [ex], [so], policy_hsize=(128, 64), value_hsize=(128, 64), num_optim_epoch=2, t_min=15, t_max=60, rfc_mode="explicit")
+    assert ag.act_dim == 315 and ag.policy.dims[-1] == 315
+    w0 = ag.policy.flat.clone()
+    log = ag.optimize_policy(8)
+    torch.cuda.synchronize()
+    assert log["num_steps"] == 8 * 64 and np.isfinite(log["avg_reward"]) and np.isfinite(log["surr_loss"]) and np.isfinite(log["value_loss"])
+    assert not torch.equal(w0, ag.policy.flat) and torch.isfinite(ag.policy.flat).all()
+    assert ag.engine.counters["invalid_env_steps"] == 0

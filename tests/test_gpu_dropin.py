@@ -23,11 +23,11 @@ def _float64_default():
     torch.set_default_dtype(old)
 
 
-def _cfg(tmp_path, monkeypatch):
+def _cfg(tmp_path, monkeypatch, cfg_file="uhc_b200_default.yml"):
     import yaml
     monkeypatch.chdir(tmp_path)
     from uhc.utils.config_utils.copycat_config import Config
-    base = yaml.safe_load(open(os.path.join(os.path.dirname(__file__), "..", "config", "uhc_b200_default.yml")))
+    base = yaml.safe_load(open(os.path.join(os.path.dirname(__file__), "..", "config", cfg_file)))
     base.update(policy_hsize=[128, 64], value_hsize=[128, 64], min_batch_size=1024, num_optim_epoch=2, num_envs=64, save_n_epochs=2, num_epoch=2)
     base["data_specs"]["file_path"] = write_synthetic_pkl(str(tmp_path / "sample_data" / "clips.pkl"))
     base["data_specs"]["t_max"] = 40
@@ -37,17 +37,19 @@ def _cfg(tmp_path, monkeypatch):
     return cfg
 
 
-def test_train_script_sequence(tmp_path, monkeypatch):
+@pytest.mark.parametrize("cfg_file", ["uhc_b200_default.yml", "uhc_b200_explicit.yml"])     # release/uhc_implicit_shape.yml, release/uhc_explicit.yml
+def test_train_script_sequence(tmp_path, monkeypatch, cfg_file):
     import torch
     from uhc.agents import agent_dict
     from uhc.utils.flags import flags
-    cfg = _cfg(tmp_path, monkeypatch)
+    cfg = _cfg(tmp_path, monkeypatch, cfg_file)
     flags.debug = False
     dtype = torch.float64
     device = torch.device("cuda", index=0)
     np.random.seed(cfg.seed)
     torch.manual_seed(cfg.seed)
     agent = agent_dict[cfg.agent_name](cfg, dtype, device, training=True, checkpoint_epoch=0)
+    assert agent.action_dim == (315 if "explicit" in cfg_file else 105)
     for i_iter in range(0, cfg.num_epoch):
         info = agent.optimize_policy(i_iter)
         assert info["log"]["num_steps"] >= cfg.min_batch_size and np.isfinite(info["log"]["avg_reward"])

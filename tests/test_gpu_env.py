@@ -296,3 +296,39 @@ def test_ragged_clips_partial_resets_and_clip_end(golden_dir):
     with pytest.raises(RuntimeError):                                    # a slice that leaves its clip is an argument error, not a silent read
         eng.reset(np.array([0], np.int32), clip=np.array([1], np.int32), start=np.array([5], np.int32), length=np.array([9], np.int32))
     eng.close()
+
+
+def _run_explicit(golden_dir, precision, E):
+    import torch
+    from uhc_b200.engine import Engine
+    g = np.load(os.path.join(golden_dir, "env_sway_explicit_noise.npz"))
+    ex, so = _expert(golden_dir, "sway")
+    eng = Engine(E, precision=precision, rfc_mode="explicit")
+    assert eng.act_dim == 315 == g["action"].shape[1]
+    eng.load_clips([ex], [so])
+    obs0 = eng.reset().cpu().numpy()
+    qpos, obs, rew, ci, fail = [], [], [], [], []
+    for t in range(len(g["reward"])):
+        a = torch.tensor(np.tile(g["action"][t], (E, 1)), dtype=torch.float32, device="cuda")
+        o, r, c, f, en, pct = eng.step(a)
+        torch.cuda.synchronize()
+        qpos.append(eng.get_state(E - 1)["qpos"]); obs.append(o[E - 1].cpu().numpy().copy()); rew.append(float(r[E - 1])); ci.append(c[E - 1].cpu().numpy().copy())
+        fail.append(int(f[E - 1]))
+    eng.close()
+    return g, obs0[E - 1], np.array(qpos), np.array(obs), np.array(rew), np.array(ci), np.array(fail)
+
+
+@pytest.mark.parametrize("precision,tol_q,tol_o", [(64, 1e-8, 2e-5), (32, 1e-3, 5e-3)])
+def test_explicit_residual_force_matches_reference_trace(golden_dir, precision, tol_q, tol_o):
+    """residual_force_mode = explicit (config/release/uhc_explicit.yml, humanoid_im.py:1080-1132 + reward_function.py:253-341) through the C ABI:
+    per-body contact point / force / torque from a 315-wide action row, applied with the Jacobian of the last forward pass."""
+    g, obs0, qpos, obs, rew, ci, fail = _run_explicit(golden_dir, precision, 3)
+    first_fail = int(np.argmax(g["fail"]))
+    assert np.abs(obs0 - g["obs0"]).max() < 1e-5
+    # the random per-body forces topple the humanoid at step ~32; the last steps before the fall amplify round-off (fp32: compared up to 8 steps before it)
+    lim = first_fail if precision == 64 else first_fail - 8
+    assert np.abs(qpos[:lim] - g["qpos"][:lim]).max() < tol_q
+    assert np.abs(obs[:lim - 2] - g["obs"][:lim - 2]).max() < tol_o
+    assert np.abs(rew[:lim - 2] - g["reward"][:lim - 2]).max() < tol_o
+    assert np.abs(ci[:lim - 2] - g["c_info"][:lim - 2]).max() < tol_o
+    assert (fail[:first_fail - 1] == 0).all() and fail[first_fail - 1:first_fail + 2].any()

@@ -38,3 +38,26 @@ def test_env_trace_matches_reference_python(golden_dir, tag, act):
         assert abs(info["percent"] - g["percent"][t]) < 1e-12
         worst = max(worst, np.abs(env.d.qpos - g["qpos"][t]).max())
     assert worst < 1e-7
+
+
+def test_explicit_residual_force_trace_matches_reference_python(golden_dir):
+    """config/release/uhc_explicit.yml: per-body contact point / force / torque applied through mj_applyFT from the pose of the last forward
+    pass (humanoid_im.py:1080-1132), action = 69 + 216 + 30, world_rfc_explicit reward (reward_function.py:253-341) -- the reference's own
+    Python over the oracle physics (tools/make_golden.py explicit) against the C restatement."""
+    g = np.load(os.path.join(golden_dir, "env_sway_explicit_noise.npz"))
+    ex, so = load_expert(golden_dir, "sway")
+    env = O.Env(O.Model(), ex, so)
+    env.set_rfc_mode(True)
+    assert env.action_dim == 315 == g["action"].shape[1] and int(g["vf_dim"]) == 216
+    np.testing.assert_allclose(env.reset(), g["obs0"], rtol=0, atol=1e-9)
+    first_fail = int(np.argmax(g["fail"])) if g["fail"].any() else len(g["reward"])
+    assert first_fail >= 20
+    for t in range(len(g["reward"])):
+        obs, r, done, info = env.step(g["action"][t])
+        tol = 1.0 if t < first_fail else 50.0                       # after the fall the trajectory is chaotic: round-off grows
+        np.testing.assert_allclose(env.torque, g["torque"][t], rtol=1e-7, atol=1e-6 * tol, err_msg=f"torque t={t}")
+        np.testing.assert_allclose(env.d.qpos, g["qpos"][t], rtol=0, atol=1e-7 * tol, err_msg=f"qpos t={t}")
+        np.testing.assert_allclose(obs, g["obs"][t], rtol=0, atol=1e-5 * tol, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(info["c_info"], g["c_info"][t], rtol=0, atol=1e-6 * tol, err_msg=f"c_info t={t}")
+        assert abs(r - g["reward"][t]) < 1e-6 * tol
+        assert info["fail"] == bool(g["fail"][t]) and info["end"] == bool(g["end"][t])

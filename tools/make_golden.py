@@ -23,17 +23,19 @@ EXPERT_KEYS = ["qpos", "qvel", "wbpos", "wbquat", "bquat", "body_com", "bangvel"
                "rlinv_local", "rangv"]
 
 
-def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train"):
-    from uhc.losses.reward_function import world_rfc_implicit_reward
+def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train", out_tag=None, save_expert=True):
+    from uhc.losses.reward_function import reward_func
+    reward = reward_func[cfg.reward_id]                       # world_rfc_implicit (uhc_implicit_shape) / world_rfc_explicit (uhc_explicit)
     seq = dl.get_sample_from_key(key, full_sample=False, fr_start=0)
     seq = {k: (v[:nframes] if hasattr(v, "shape") and v.shape[:1] == (300,) or (hasattr(v, "shape") and len(v) > nframes) else v)
            for k, v in seq.items()}
     env = H.make_env(cfg, seq, mode=mode)
     env.seed(seed)
     ex = env.expert
-    np.savez_compressed(os.path.join(OUT, f"expert_{tag}.npz"), pose_aa=seq["pose_aa"][:, :72].copy(),
-                        trans=seq["trans"], beta=seq["beta"], gender=seq["gender"],
-                        height_lb=ex["height_lb"], length=ex["len"], **{k: ex[k] for k in EXPERT_KEYS})
+    if save_expert:
+        np.savez_compressed(os.path.join(OUT, f"expert_{tag}.npz"), pose_aa=seq["pose_aa"][:, :72].copy(),
+                            trans=seq["trans"], beta=seq["beta"], gender=seq["gender"],
+                            height_lb=ex["height_lb"], length=ex["len"], **{k: ex[k] for k in EXPERT_KEYS})
     rng = np.random.RandomState(seed)
     obs0 = env.reset()
     rec = {k: [] for k in ("action", "obs", "reward", "c_info", "fail", "end", "percent", "qpos", "qvel", "torque",
@@ -43,9 +45,13 @@ def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train"):
             a = np.zeros(env.action_dim)
         else:
             a = rng.normal(0.0, 0.1, env.action_dim)
-            a[69:75] *= 0.3
+            if env.vf_dim == 6:
+                a[69:75] *= 0.3
+            else:                                             # explicit residual forces: 24 x (contact point 3, force 3, torque 3)
+                vf = a[69:69 + env.vf_dim].reshape(-1, 9)
+                vf[:, 3:] *= 0.05
         ob, _, done, info = env.step(a.copy())
-        r, ci = world_rfc_implicit_reward(env, None, a, info)
+        r, ci = reward(env, None, a, info)
         rec["action"].append(a); rec["obs"].append(ob); rec["reward"].append(r); rec["c_info"].append(ci)
         rec["fail"].append(bool(info["fail"])); rec["end"].append(bool(info["end"])); rec["percent"].append(info["percent"])
         rec["qpos"].append(env.data.qpos.copy()); rec["qvel"].append(env.data.qvel.copy())
@@ -54,7 +60,7 @@ def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train"):
         rec["prev_bquat"].append(env.prev_bquat.copy()); rec["ncon"].append(env.data.ncon)
         if info["end"]:
             break
-    np.savez_compressed(os.path.join(OUT, f"env_{tag}_{act_mode}.npz"), obs0=obs0, expert=f"expert_{tag}.npz",
+    np.savez_compressed(os.path.join(OUT, f"env_{out_tag or tag}_{act_mode}.npz"), obs0=obs0, expert=f"expert_{tag}.npz", vf_dim=env.vf_dim,
                         **{k: np.array(v) for k, v in rec.items()})
     print(tag, act_mode, "steps", len(rec["reward"]), "fails", int(np.sum(rec["fail"])), "mean r %.4f" % np.mean(rec["reward"]),
           "max ncon", max(rec["ncon"]))
@@ -324,6 +330,11 @@ def main():
         gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 60, "zero")
         gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 60, "noise")
         gen_env(cfg, dl, "0-BioMotionLab_NTroje_rub008_0025_kicking1_poses", "kick", 70, 69, "noise")
+    if "explicit" in what:       # config/release/uhc_explicit.yml: per-body residual forces through mj_applyFT, world_rfc_explicit reward
+        cfg = H.make_cfg("uhc_explicit")
+        from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
+        dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
+        gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 40, "noise", out_tag="sway_explicit", save_expert=False)
     if "reactive" in what:
         cfg = H.make_cfg()
         from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle

@@ -19,6 +19,8 @@ import tempfile
 import types
 from collections import namedtuple
 
+import ctypes as C
+
 import numpy as np
 
 REF = os.environ.get("UHC_REFERENCE", "/root/reference")
@@ -145,6 +147,15 @@ class FakeData:
     def get_body_xquat(self, name):
         return self.body_xquat[self._sim.model._body_name2id[name]]
 
+    def get_body_xmat(self, name):      # pose of the last forward pass, like data.body_xmat
+        return np.array(self._sim.d.xmat).reshape(24, 3, 3)[self._sim.model._body_name2id[name] - 1].copy()
+
+    @property
+    def contact(self):                  # geom 0 = the floor, geom i = body i (FakeModel.geom_bodyid)
+        d = self._sim.d
+        Cn = namedtuple("Contact", ["geom1", "geom2"])
+        return [Cn(0, int(d.con_body(i)) + 1) for i in range(d.ncon)]
+
     @property
     def ncon(self):
         return self._sim.d.ncon
@@ -186,7 +197,14 @@ def _install_fake_mujoco(om):
 
     fn.mj_fullM = mj_fullM
     fn.mj_getTotalmass = lambda model: float(model.body_mass.sum())
-    fn.mj_applyFT = lambda *a, **k: None
+    def mj_applyFT(model, data, force, torque, point, body_id, qfrc):
+        """qfrc += J(point, body)^T [force; torque] from the kinematics of the last forward pass (oracle/uhc_oracle.c or_apply_ft)"""
+        f, t, p = (np.ascontiguousarray(x, dtype=np.float64) for x in (force, torque, point))
+        q = np.ascontiguousarray(qfrc, dtype=np.float64)
+        O.lib().or_apply_ft(model.om.h, data._sim.d.h, O._p(f), O._p(t), O._p(p), C.c_int(int(body_id) - 1), O._p(q))
+        qfrc[:] = q
+
+    fn.mj_applyFT = mj_applyFT
     mp.functions = fn
     mp.load_model_from_xml = lambda xml: FakeModel(om)
     mp.load_model_from_path = lambda path: FakeModel(om)

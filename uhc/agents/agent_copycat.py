@@ -78,7 +78,14 @@ class AgentCopycat:
         # variants the batched engine does not implement must not be accepted silently
         assert cfg.fix_std, "log_std is not a trained parameter in this engine (fix_std: true in every released config)"
         assert cfg.get("env_term_body", "body") == "body", "env_term_body: only 'body' (calc_body_diff) is implemented"
-        assert cfg.residual_force and cfg.get("residual_force_mode", "implicit") == "implicit", "only the implicit residual force is implemented"
+        rfc_mode = cfg.get("residual_force_mode", "implicit")
+        assert cfg.residual_force and rfc_mode in ("implicit", "explicit"), "residual_force_mode: implicit | explicit"
+        if rfc_mode == "explicit":      # the kernel restates the release settings of the explicit mode (config/release/uhc_explicit.yml)
+            assert cfg.get("residual_force_bodies", "all") == "all" and cfg.get("residual_force_torque", True) and int(cfg.get("residual_force_bodies_num", 1)) == 1 \
+                and not cfg.get("residual_contact_only", False) and not cfg.get("residual_contact_projection", False), \
+                "explicit residual force: only residual_force_bodies = all, one point per body, torque on, no contact gating / projection"
+        # the fused reward follows the residual-force mode (world_rfc_implicit :12-88 / world_rfc_explicit :253-341), as the released configs pair them
+        assert cfg.reward_id == ("world_rfc_explicit" if rfc_mode == "explicit" else "world_rfc_implicit"), "reward_id must match residual_force_mode"
         assert float(cfg.get("env_init_noise", 0.0)) == 0.0, "env_init_noise > 0 is not implemented"
         self.agent = BatchedAgent(
             self.num_envs, self.data_loader.experts, self.data_loader.shapes, device=dev_index, seed=cfg.seed, policy_hsize=cfg.policy_hsize,
@@ -87,9 +94,9 @@ class AgentCopycat:
             t_min=cfg.data_specs.get("t_min", 90), t_max=cfg.data_specs.get("t_max", -1), rank=rank, world=world, grad_sync=sync,
             model=self.model_tables, base_rot=cfg.data_specs.get("base_rot", [0.7071, 0.7071, 0.0, 0.0]), rfc_scale=cfg.residual_force_scale,
             rfc_lim=cfg.residual_force_lim, rfc_rate=0.0 if cfg.rfc_decay else 1.0, body_diff_thresh=cfg.get("body_diff_thresh", 0.5),
-            meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=kk)
+            meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=kk, rfc_mode=rfc_mode)
         self.policy_net, self.value_net, self.running_state = self.agent.policy, self.agent.value, self.agent.running_state
-        self.state_dim, self.action_dim = 657, 105
+        self.state_dim, self.action_dim = 657, self.agent.act_dim
         self.expert_reward = reward_func[cfg.reward_id]
         self.env = None   # single-env facade, built lazily (eval_seq / visualisation code paths)
         self.logger = logging.getLogger(f"uhc_b200.{cfg.id}")
@@ -263,6 +270,7 @@ class AgentCopycat:
         return dict(base_rot=cfg.data_specs.get("base_rot", [0.7071, 0.7071, 0.0, 0.0]), rfc_scale=cfg.residual_force_scale, rfc_lim=cfg.residual_force_lim,
                     rfc_rate=0.0 if cfg.rfc_decay else 1.0, body_diff_thresh=cfg.get("body_diff_thresh_test" if test else "body_diff_thresh", 0.5),
                     meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, auto_reset=0 if test else 1,
+                    rfc_mode=cfg.get("residual_force_mode", "implicit"),
                     w=[rw.get(k, d) for k, d in (("w_p", 0.6), ("w_v", 0.1), ("w_e", 0.2), ("w_c", 0.1), ("w_vf", 0.0))],
                     k=[rw.get(k, d) for k, d in (("k_p", 2), ("k_v", 0.005), ("k_e", 20), ("k_c", 1000), ("k_vf", 1))])
 

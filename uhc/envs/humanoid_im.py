@@ -9,7 +9,7 @@ classic gym-style loop; training uses uhc_b200.agent.BatchedAgent (thousands of 
 import numpy as np
 
 from uhc_b200 import motion_lib
-from uhc_b200.engine import ACT_DIM, OBS_DIM, Engine
+from uhc_b200.engine import OBS_DIM, Engine
 from uhc_b200.model import HumanoidModel
 
 
@@ -75,9 +75,15 @@ class HumanoidEnv:
         self.engine = Engine(1, self.model_tables, device=device, precision=precision, base_rot=data_specs.get("base_rot", [0.7071, 0.7071, 0.0, 0.0]),
                              rfc_scale=cfg.residual_force_scale, rfc_lim=cfg.residual_force_lim, rfc_rate=0.0 if cfg.rfc_decay else 1.0,
                              body_diff_thresh=cfg.get("body_diff_thresh", 0.5) if mode == "train" else cfg.get("body_diff_thresh_test", 0.5),
-                             meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=k)
+                             meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=k,
+                             rfc_mode=cfg.get("residual_force_mode", "implicit"))
         self.dt = self.model_tables.dt * 15
-        self.ndof, self.vf_dim, self.meta_pd_dim = 69, 6 if cfg.residual_force else 0, 30 if cfg.meta_pd else 0
+        # set_action_spaces (humanoid_im.py:226-255): implicit = 6 residual-force dims, explicit = 9 per body x 24 bodies
+        explicit = cfg.get("residual_force_mode", "implicit") == "explicit"
+        self.ndof, self.vf_dim, self.meta_pd_dim = 69, (216 if explicit else 6) if cfg.residual_force else 0, 30 if cfg.meta_pd else 0
+        self.body_vf_dim, self.vf_bodies = 9, list(self.model_tables.SMPL_BONE_ORDER)
+        ACT_DIM = self.engine.act_dim
+        assert ACT_DIM == self.ndof + self.vf_dim + self.meta_pd_dim
         self.action_dim, self.obs_dim = ACT_DIM, OBS_DIM
         self.action_space, self.observation_space = _Space(ACT_DIM), _Space(OBS_DIM)
         self.body_diffw, self.jpos_diffw = self.model_tables.diffw[1:], self.model_tables.diffw[:, None]
@@ -118,7 +124,7 @@ class HumanoidEnv:
 
     def step(self, a):
         self.prev_bquat = self.get_body_quat().copy()
-        self._act.copy_(self.torch.as_tensor(np.asarray(a, dtype=np.float32)).reshape(1, ACT_DIM))
+        self._act.copy_(self.torch.as_tensor(np.asarray(a, dtype=np.float32)).reshape(1, self.action_dim))
         obs, rew, cinfo, fail, end, pct = self.engine.step(self._act)
         self.cur_t += 1
         self.last_reward, self.last_cinfo = float(rew[0]), cinfo[0].cpu().numpy()

@@ -15,7 +15,7 @@ import time
 import numpy as np
 
 from . import nn
-from .engine import ACT_DIM, OBS_DIM, Engine
+from .engine import OBS_DIM, Engine
 
 
 class UhcRolloutBuf(C.Structure):
@@ -69,12 +69,12 @@ class ClipSampler:
 
 
 class RolloutBuffer:
-    def __init__(self, T, E, device):
+    def __init__(self, T, E, device, act_dim=105):
         import torch
         f = dict(device=device, dtype=torch.float32)
         self.T, self.E = T, E
         self.states = torch.empty(T, E, OBS_DIM, **f)
-        self.actions = torch.empty(T, E, ACT_DIM, **f)
+        self.actions = torch.empty(T, E, act_dim, **f)
         self.rewards, self.masks, self.exps, self.logp = (torch.empty(T, E, **f) for _ in range(4))
         self.last_obs = torch.empty(E, OBS_DIM, **f)
         self.last_alive = torch.empty(E, **f)
@@ -99,7 +99,7 @@ class BatchedAgent:
     def __init__(self, num_envs, clips, shapes=None, device=0, seed=1, precision=32, policy_hsize=(2048, 1024, 512),
                  value_hsize=(2048, 1024, 512), htype="gelu", log_std=-2.3, policy_lr=5e-5, value_lr=3e-4, gamma=0.95, tau=0.95,
                  clip_epsilon=0.2, num_optim_epoch=10, grad_clip=40.0, t_min=5, t_max=300, noise_rate=1.0, rank=0, world=1,
-                 grad_sync=None, model=None, update_tc=True, variants=None, clip_models=None, **env_cfg):
+                 grad_sync=None, model=None, update_tc=True, variants=None, clip_models=None, c_update=True, **env_cfg):
         import torch
         self.torch = torch
         self.dev = torch.device("cuda", device)
@@ -110,14 +110,16 @@ class BatchedAgent:
                              reset_seed=seed * 7919 + rank * 104729 + 1, **env_cfg)
         self.engine.load_clips(clips, shapes, clip_models)   # clip_models: body-shape variant per clip (the reference rebuilds the robot per clip)
         self.sampler = ClipSampler(self.engine.clip_len, t_min, t_max, seed=seed * 9973 + rank)
-        self.policy = nn.MLPNet(OBS_DIM, policy_hsize, ACT_DIM, htype, device=self.dev, head_name="action_mean", seed=seed)
+        A = self.act_dim = self.engine.act_dim          # env.action_dim (humanoid_im.py:250): 69 + (6 | 216) + (30 if meta_pd)
+        self.policy = nn.MLPNet(OBS_DIM, policy_hsize, A, htype, device=self.dev, head_name="action_mean", seed=seed)
         self.value = nn.MLPNet(OBS_DIM, value_hsize, 1, htype, device=self.dev, head_name="value_head", seed=seed + 1)
-        self.log_std = torch.full((ACT_DIM,), float(log_std), device=self.dev, dtype=torch.float32)
+        self.log_std = torch.full((A,), float(log_std), device=self.dev, dtype=torch.float32)
         self.running_state = nn.ZFilter(OBS_DIM, clip=5.0, device=self.dev)
         self.opt_p, self.opt_v = nn.Adam(self.policy.params(), policy_lr, net=self.policy), nn.Adam(self.value.params(), value_lr, net=self.value)
         self.comm = nn.GradComm(world)
         self.gamma, self.tau, self.clip_epsilon, self.epochs, self.grad_clip = gamma, tau, clip_epsilon, num_optim_epoch, grad_clip
         self.noise_rate, self.grad_sync, self.update_tc = noise_rate, grad_sync, update_tc
+        self.c_update, self._ctrainer, self._nccl = c_update, None, None      # uhc_ppo_update (include/uhc_ppo.h): the update behind one C-ABI call
         self.global_step = 0
         self.obs = None
         self.ep_len = torch.zeros(num_envs, device=self.dev, dtype=torch.float32)
@@ -194,7 +196,7 @@ class BatchedAgent:
         t = self.torch
         if self.obs is None:
             self.reset_envs()
-        buf = buf or RolloutBuffer(T, self.E, self.dev)
+        buf = buf or RolloutBuffer(T, self.E, self.dev, self.act_dim)
         t0 = time.time()
         len0, ret0 = self.ep_len.clone(), self.ep_ret.clone()
         if c_loop is None:
@@ -246,6 +248,8 @@ class BatchedAgent:
             t.cuda.synchronize()
             self._mlp_c = None
             return dict(update_time=time.time() - t0, surr_loss=float(losses[0]), value_loss=float(losses[1]))
+        if self.c_update:
+            return self._update_params_c(buf, ev)
         tp = getattr(self.policy, "_tc_trainer", None) or nn.TCTrainer(self.policy)
         tv = getattr(self.value, "_tc_trainer", None) or nn.TCTrainer(self.value)
         self.policy._tc_trainer, self.value._tc_trainer = tp, tv
@@ -297,6 +301,38 @@ class BatchedAgent:
         if self.world > 1:
             out.update(allreduce_ms=self.comm.pop_ms(), allreduce_bytes=self.comm.bytes, allreduce_calls=self.comm.calls)
             self.comm.bytes = self.comm.calls = 0
+        return out
+
+    def _update_params_c(self, buf, ev):
+        """the production update: ONE call of uhc_ppo_update (include/uhc_ppo.h) -- V(s) and V(s_T), GAE, global advantage normalisation, the
+        epochs of both nets, Adam, and (world > 1) the gradient all-reduces on this job's ncclComm_t with the statistics tail."""
+        t = self.torch
+        T, E = buf.T, buf.E
+        if self._ctrainer is None or self._ctrainer.max_rows < T * E or self._ctrainer.max_envs < E:
+            if self._ctrainer is not None:
+                self._ctrainer.close()
+            self._ctrainer = nn.CPpoTrainer(self.policy, self.value, self.opt_p, self.opt_v, T * E, E, self.dev)
+        zs = zsync = None
+        if self.world > 1:
+            if self._nccl is None:
+                self._nccl = nn.make_nccl_comm(self.rank, self.world, self.dev)
+            zs = self.running_state.stats
+            if getattr(self, "_z_sync", None) is None:
+                self._z_sync = t.zeros_like(zs)
+            zsync = self._z_sync
+        last_s = self.running_state(buf.last_obs, update=False)
+        if getattr(self, "_losses", None) is None:
+            self._losses = t.zeros(2, device=self.dev, dtype=t.float32)
+        ev[1].record()
+        self._ctrainer.update(buf.flat("states"), last_s, buf.flat("actions"), buf.rewards, buf.masks, buf.flat("exps"), self.log_std, T, E, self.gamma,
+                              self.tau, self.clip_epsilon, self.epochs, self.grad_clip, self._losses, zfilter=zs, z_sync=zsync, comm=self._nccl, world=self.world)
+        ev[2].record()
+        t.cuda.synchronize()
+        out = dict(update_time=1e-3 * ev[0].elapsed_time(ev[2]), gae_ms=0.0, epochs_ms=ev[1].elapsed_time(ev[2]),      # GAE runs inside the call
+                   surr_loss=float(self._losses[0]), value_loss=float(self._losses[1]))
+        if self.world > 1:
+            ms, by, calls = self._ctrainer.comm_stats()
+            out.update(allreduce_ms=ms, allreduce_bytes=by, allreduce_calls=calls)
         return out
 
     def optimize_policy(self, T):

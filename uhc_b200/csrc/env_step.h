@@ -207,9 +207,15 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     const int clip = is[SI_CLIP], start = is[SI_START], len = is[SI_LEN];
     int cur_t = is[SI_CUR_T];
     load_state(ev, env, w, 0);     // the warp's mbarrier completes exactly one phase per kernel launch
+    // action = [NU joint targets | vf_dim residual-force dims | 30 meta-PD scales]: the work set keeps the joint targets, the implicit root
+    // wrench and the meta-PD scales at the fixed slots the PD code reads; the explicit per-body forces are read from global memory where used
+    const bool explicit_rf = ev.cfg.rfc_mode == 1;
     LANES_BEGIN
-    for (int i = lane; i < ACT_DIM; i += 32) w.act[i] = (Real)action[i];
+    for (int i = lane; i < NU; i += 32) w.act[i] = (Real)action[i];
+    if (lane < 6) w.act[NU + lane] = explicit_rf ? Real(0) : (Real)action[NU + lane];
+    if (lane < 2 * NSUB) w.act[NU + 6 + lane] = ev.cfg.meta_pd ? (Real)action[NU + ev.cfg.vf_dim + lane] : Real(0);
     LANES_END
+    if (explicit_rf) restore_stale_pose(w, st + ST_XPOS, st + ST_XQUAT);
     const Real *target = expert_frame(ev, clip, start, len, cur_t + 1) + EX_QPOS + 7;
     int iters = 0, maxcon = 0;
     LANES_BEGIN
@@ -220,7 +226,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
 #pragma unroll 1
     for (int it = 0; it < NSUB; ++it) {
         UHC_CTA_SYNC(true);   // see substep_dynamics: the CTA's warps run each substep's straight-line code together
-        iters += substep_dynamics<Real, ObsT>(mdl, w.cfg, w, tp, target, it, true, torque_out, true);
+        iters += substep_dynamics<Real, ObsT>(mdl, w.cfg, w, tp, target, it, true, torque_out, true, action);
         if (w.ncon > maxcon) maxcon = w.ncon;
         if (it == NSUB - 1) world_quat(mdl, w.q, w);  // pose of the last forward pass (what data.body_xquat holds)
         integrate(mdl, w);
@@ -233,7 +239,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     LANES_END
     body_quat(w, bq);
     Real bd, rew, ci[5];
-    diff_and_reward(mdl, w.cfg, w, expert_frame(ev, clip, start, len, cur_t), bq, pbq, &bd, &rew, ci);
+    diff_and_reward(mdl, w.cfg, w, expert_frame(ev, clip, start, len, cur_t), bq, pbq, &bd, &rew, ci, action);
     int fail = bd > ev.cfg.body_diff_thresh;
     {   // a non-finite state can never pass "bd > thresh": flag it as a failure (mirrors the try/except at :1207-1211)
         LVAR(int, bad);

@@ -223,6 +223,7 @@ int uhc_policy_forward(UhcEngine *e, const float *obs_dev, const UhcMlp *mlp, co
                        unsigned long long seed, const unsigned char *mean_action_or_null, float *state_out_or_null, float *action_out, float *logp_out_or_null,
                        void *stream) {
     if (!e || !obs_dev || !mlp || !log_std || !zfilter_stats || !action_out) { g_ro_err = "uhc_policy_forward: bad argument"; return -2; }
+    if (mlp->nlayers >= 1 && mlp->nlayers <= 8 && mlp->dims[mlp->nlayers] != uhc_engine_act_dim(e)) { g_ro_err = "uhc_policy_forward: the policy's output width is not the engine's action dim"; return -2; }
     RolloutCtx *c = ctx_of(e);
     int rc = ensure_scratch(c, mlp);
     if (rc) return rc;
@@ -237,6 +238,7 @@ int uhc_rollout(UhcEngine *e, int T, int row0, const UhcMlp *mlp, const float *l
                 unsigned long long seed, float noise_rate, const UhcRolloutBuf *buf, int use_graph, void *stream) {
     if (!e || !mlp || !log_std || !zfilter_stats || !buf || T <= 0 || row0 < 0 || row0 + T > buf->T_cap) { g_ro_err = "uhc_rollout: bad argument"; return -2; }
     if (!buf->states || !buf->actions || !buf->rewards || !buf->masks || !buf->exps || !buf->obs_cur) { g_ro_err = "uhc_rollout: missing buffer"; return -2; }
+    if (mlp->nlayers >= 1 && mlp->nlayers <= 8 && mlp->dims[mlp->nlayers] != uhc_engine_act_dim(e)) { g_ro_err = "uhc_rollout: the policy's output width is not the engine's action dim"; return -2; }
     RolloutCtx *c = ctx_of(e);
     int rc = ensure_scratch(c, mlp);
     if (rc) return rc;

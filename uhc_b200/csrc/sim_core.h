@@ -101,7 +101,12 @@ struct EnvCfg {
     int auto_reset, t_min, t_max, num_clips;      // in-kernel re-seeding of finished episodes (dataset_amass_single.py:172-253)
     unsigned long long reset_seed;
     int reactive_v; Real reactive_rate;           // reset_model's reactive_v = 1 branch (humanoid_im.py:1255-1271): start from the standing pose w.p. reactive_rate
+    // residual-force mode (cfg.residual_force_mode, humanoid_im.py:231-243): 0 = implicit root wrench (6 action dims), 1 = explicit per-body contact
+    // point / force / torque (9 dims x 24 bodies).  Action layout: [NU joint targets | vf_dim residual-force dims | 30 meta-PD scales if meta_pd]
+    int rfc_mode, vf_dim, act_dim;
+    signed char vf_slot[NB];                      // explicit: residual-force slot of body b (vf_bodies = SMPL_BONE_ORDER_NAMES, humanoid_im.py:236-237)
 };
+constexpr int VF_BODY_DIM = 9, MAX_ACT_DIM = NU + VF_BODY_DIM * NB + 30;
 
 // per-environment working set (lives in shared memory on the GPU)
 template <class Real>
@@ -1116,6 +1121,48 @@ UHC_DEV void rfc_implicit(const EnvCfg<Real> &cfg, const Work<Real> &w, Real *fa
     for (int i = 0; i < 6; i++) fapp[i] = clamp_(vf[i], -cfg.rfc_lim, cfg.rfc_lim);
 }
 
+// explicit residual force: humanoid_im.py:1080-1132 with the release settings (residual_force_bodies = "all", one point per body, torque on, no
+// contact gating / projection).  Per body a contact point, a force and a torque given in the BODY frame of the LAST forward pass
+// (mujoco_env.py:171-180 read data.body_xpos / xmat between two sim.step()), scaled by residual_force_scale and applied through mj_applyFT, whose
+// Jacobian is also the last forward pass' -- i.e. the stale xpos / xmat / S this work set still holds before kin_rne_forward runs.
+// As spatial wrenches about O (the stale root position): F_b = (tau + (p - O) x f, f); qfrc_i = S_i . sum over subtree(body(i)) of F.
+template <class Real, class ActT, class TPT>
+UHC_DEV void rfc_explicit(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const TPT &tp, const ActT *act, Real *qfrc) {
+    LVARA(Real, F, 6);
+    LANES_BEGIN
+    for (int i = 0; i < 6; i++) LVA(F)[i] = 0;
+    if (lane < NB) {
+        const int b = lane;
+        const ActT *v = act + NU + VF_BODY_DIM * (int)cfg.vf_slot[b];
+        const Real *R = w.xmat[b];
+        const Real cp[3] = {(Real)v[0], (Real)v[1], (Real)v[2]}, fl[3] = {(Real)v[3] * cfg.rfc_scale, (Real)v[4] * cfg.rfc_scale, (Real)v[5] * cfg.rfc_scale},
+                   tl[3] = {(Real)v[6] * cfg.rfc_scale, (Real)v[7] * cfg.rfc_scale, (Real)v[8] * cfg.rfc_scale};
+        Real p[3], f[3], tq[3], n[3];
+        mv3(R, cp, p); mv3(R, fl, f); mv3(R, tl, tq);
+        for (int k = 0; k < 3; k++) p[k] += w.xpos[b][k] - w.xpos[0][k];
+        cross3(p, f, n);
+        LVA(F)[0] = tq[0] + n[0]; LVA(F)[1] = tq[1] + n[1]; LVA(F)[2] = tq[2] + n[2]; LVA(F)[3] = f[0]; LVA(F)[4] = f[1]; LVA(F)[5] = f[2];
+    }
+    LANES_END_R
+    WSUBTREE(F, 6, tp);
+    LANES_BEGIN
+    if (lane < NB) for (int i = 0; i < 6; i++) w.Fb[lane][i] = LVA(F)[i];
+    LANES_END
+    project_force(m, w, w.Fb, qfrc, Real(1), (const Real *)nullptr);
+}
+// pose of the last forward pass back into the work set at the start of a control step (only the explicit residual force needs it before the
+// first forward pass of the step): xpos from the record, xmat from the stored body quaternions (what data.body_xmat holds: mju_quat2Mat of xquat)
+template <class Real>
+UHC_DEV void restore_stale_pose(Work<Real> &w, const Real *st_xpos, const Real *st_xquat) {
+    LANES_BEGIN
+    if (lane < NB) {
+        for (int k = 0; k < 3; k++) w.xpos[lane][k] = st_xpos[3 * lane + k];
+        const Real q[4] = {st_xquat[4 * lane], st_xquat[4 * lane + 1], st_xquat[4 * lane + 2], st_xquat[4 * lane + 3]};
+        q2mat(q, w.xmat[lane]);
+    }
+    LANES_END
+}
+
 template <class Real>
 UHC_DEV void integrate(const Model<Real> &m, Work<Real> &w) {
     const Real dt = m.dt;
@@ -1155,7 +1202,7 @@ enum { PH_PD = 0, PH_SMOOTH = 1, PH_NEWTON = 2 };
 #endif
 template <class Real, class OutT, class TPT>
 UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Work<Real> &w, const TPT &tp, const Real *target, int it,
-                             bool with_pd, OutT *torque_out, bool cta_sync = false) {
+                             bool with_pd, OutT *torque_out, bool cta_sync = false, const OutT *act_global = nullptr) {
     int phase = with_pd ? PH_PD : PH_SMOOTH, iters = 0;
     bool done = false;
     Real scale = 0, gn2 = 0;
@@ -1169,15 +1216,18 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
             arm_scale = sd * m.dt;
         } else if (phase == PH_SMOOTH) {
             Real fapp[6] = {0, 0, 0, 0, 0, 0};
-            if (with_pd) rfc_implicit(cfg, w, fapp);
+            const bool explicit_rf = with_pd && cfg.rfc_mode == 1 && act_global != nullptr;
+            if (explicit_rf) rfc_explicit(m, cfg, w, tp, act_global, w.as_);        // generalized force of the per-body residual forces (stale Jacobian) -> as_
+            else if (with_pd) rfc_implicit(cfg, w, fapp);
             kin_rne_forward(m, w, tp);
             project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
             collide(m, w, tp);
             LANES_BEGIN
             for (int i = lane; i < NV; i += 32) {  // smooth acceleration a_s = M^-1 (tau + f_applied - C)
                 Real f = -w.C[i];
-                if (i < 6) { const Real fa = i == 0 ? fapp[0] : i == 1 ? fapp[1] : i == 2 ? fapp[2] : i == 3 ? fapp[3] : i == 4 ? fapp[4] : fapp[5]; f += fa; }
-                else if (with_pd) f += w.tau[i - 6];
+                if (explicit_rf) f += w.as_[i];
+                else if (i < 6) { const Real fa = i == 0 ? fapp[0] : i == 1 ? fapp[1] : i == 2 ? fapp[2] : i == 3 ? fapp[3] : i == 4 ? fapp[4] : fapp[5]; f += fa; }
+                if (i >= 6 && with_pd) f += w.tau[i - 6];
                 w.fs[i] = f; w.as_[i] = f;
             }
             LANES_END
@@ -1305,13 +1355,16 @@ template <class Real> UHC_DEV void rot_from_quat(const Real *q, Real *rv) {  // 
 
 // termination metric (humanoid_im.py:1408-1415) and world_rfc_implicit reward (reward_function.py:12-88);
 // ext = expert frame at the NEW cur_t; bquat/pbquat = current / previous body quats
-template <class Real>
+// rfc_mode 1: world_rfc_explicit (reward_function.py:253-341) -- angular-velocity error NOT weighted by jpos_diffw, residual-force term = sum over the
+// bodies' slots of |force|^2 + |torque|^2 of the raw action (:321-327)
+template <class Real, class ActT>
 UHC_DEVNI void diff_and_reward(const Model<Real> &m, const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *ext, const Real *bquat,
-                             const Real *pbquat, Real *body_diff, Real *reward, Real *cinfo) {
-    LVAR(Real, s_bd); LVAR(Real, s_n); LVAR(Real, s_pose); LVAR(Real, s_vel); LVAR(Real, s_ee);
+                             const Real *pbquat, Real *body_diff, Real *reward, Real *cinfo, const ActT *act_global) {
+    LVAR(Real, s_bd); LVAR(Real, s_n); LVAR(Real, s_pose); LVAR(Real, s_vel); LVAR(Real, s_ee); LVAR(Real, s_vf);
+    const bool explicit_rf = cfg.rfc_mode == 1 && act_global != nullptr;
     const Real dtc = m.dt * NSUB;
     LANES_BEGIN
-    Real bd = 0, nn = 0, pose = 0, vel = 0, ee = 0;
+    Real bd = 0, nn = 0, pose = 0, vel = 0, ee = 0, vfs = 0;
     if (lane < NB) {
         const int b = lane; const Real dw = UHC_LDG(m.body_f + b * BODYF + 18);
         if (dw != 0) { Real dx[3]; for (int k = 0; k < 3; k++) dx[k] = (w.xpos[b][k] - ext[EX_WBPOS + 3 * b + k]) * dw; bd = sqrt(dot3(dx, dx)); nn = 1; }
@@ -1320,16 +1373,19 @@ UHC_DEVNI void diff_and_reward(const Model<Real> &m, const EnvCfg<Real> &cfg, co
         const Real a = acos_(clamp_(dq[0], Real(-1), Real(1))) * (b == 0 ? Real(1) : dw);
         pose = a * a;
         qinv(pbquat + 4 * b, iq); qmul(bquat + 4 * b, iq, dq); rot_from_quat(dq, rv);
-        for (int k = 0; k < 3; k++) { const Real dv = (rv[k] / dtc - ext[EX_BANGVEL + 3 * b + k]) * dw; vel += dv * dv; }
+        const Real vw = explicit_rf ? Real(1) : dw;
+        for (int k = 0; k < 3; k++) { const Real dv = (rv[k] / dtc - ext[EX_BANGVEL + 3 * b + k]) * vw; vel += dv * dv; }
+        if (explicit_rf) for (int k = 3; k < VF_BODY_DIM; k++) { const Real x = (Real)act_global[NU + VF_BODY_DIM * b + k]; vfs += x * x; }
     }
     if (lane < 5) { const int eb = UHC_LDG(m.ee + lane); for (int k = 0; k < 3; k++) { const Real x = w.xpos[eb][k] - ext[EX_EE + 3 * lane + k]; ee += x * x; } }
-    LV(s_bd) = bd; LV(s_n) = nn; LV(s_pose) = pose; LV(s_vel) = vel; LV(s_ee) = ee;
+    LV(s_bd) = bd; LV(s_n) = nn; LV(s_pose) = pose; LV(s_vel) = vel; LV(s_ee) = ee; LV(s_vf) = vfs;
     LANES_END
     const Real bdsum = WSUM(s_bd), nsum = WSUM(s_n), pose2 = WSUM(s_pose), vel2 = WSUM(s_vel), ee2 = WSUM(s_ee);
     *body_diff = bdsum / nsum;
     Real com2 = 0, vf2 = 0;
     for (int k = 0; k < 3; k++) { const Real x = w.xipos[0][k] - ext[EX_COM + k]; com2 += x * x; }
-    for (int i = 0; i < 6; i++) vf2 += w.act[NU + i] * w.act[NU + i];
+    if (explicit_rf) vf2 = WSUM(s_vf);
+    else for (int i = 0; i < 6; i++) vf2 += w.act[NU + i] * w.act[NU + i];
     cinfo[0] = exp_(-cfg.k[0] * pose2); cinfo[1] = exp_(-cfg.k[1] * vel2); cinfo[2] = exp_(-cfg.k[2] * ee2);
     cinfo[3] = exp_(-cfg.k[3] * com2); cinfo[4] = exp_(-cfg.k[4] * vf2);
     Real r = 0, ws = 0;

@@ -21,12 +21,13 @@ class UhcEnvCfg(C.Structure):
                 ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
                 ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double),
                 ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reactive_v", C.c_int), ("reset_seed", C.c_ulonglong),
-                ("reactive_rate", C.c_double)]
+                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24)]
 
 
 def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0, rfc_lim=100.0, rfc_rate=1.0, body_diff_thresh=0.5,
              meta_pd=1, env_episode_len=100000, trail_steps=0, w=(0.3, 0.1, 0.45, 0.1, 0.05), k=(2.0, 0.005, 5.0, 100.0, 1.0),
-             newton_max_iter=None, newton_tol=None, auto_reset=0, t_min=5, t_max=300, reset_seed=1, reactive_v=0, reactive_rate=0.3):
+             newton_max_iter=None, newton_tol=None, auto_reset=0, t_min=5, t_max=300, reset_seed=1, reactive_v=0, reactive_rate=0.3,
+             rfc_mode="implicit", vf_slot=None):
     """Defaults = config/release/uhc_implicit_shape.yml + copycat_config.py defaults of the reference."""
     c = UhcEnvCfg()
     c.base_rot = (C.c_double * 4)(*base_rot)
@@ -37,7 +38,15 @@ def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0,
     c.w, c.k = (C.c_double * 5)(*w), (C.c_double * 5)(*k)
     c.auto_reset, c.t_min, c.t_max, c.reset_seed = int(auto_reset), int(t_min), int(t_max), int(reset_seed)
     c.reactive_v, c.reactive_rate = int(reactive_v), float(reactive_rate)
+    # cfg.residual_force_mode: "implicit" (6 action dims: root wrench) | "explicit" (24 x 9: contact point, force, torque per body, mj_applyFT)
+    c.rfc_mode = 1 if rfc_mode in (1, "explicit") else 0
+    c.vf_slot = (C.c_int * 24)(*(list(vf_slot) if vf_slot is not None else range(24)))
     return c
+
+
+def act_dim_of(cfg):
+    """env.action_dim (humanoid_im.py:250)"""
+    return NU + (216 if cfg.rfc_mode == 1 else 6) + (30 if cfg.meta_pd else 0)
 
 
 def pack_expert(ex):
@@ -88,8 +97,11 @@ class Engine:
         self.model = model or HumanoidModel()
         self.variants = variants
         self._ms = self.model.host_struct(variants)
+        if cfg.get("rfc_mode") in (1, "explicit") and cfg.get("vf_slot") is None:
+            cfg["vf_slot"] = self.model.vf_slot()                 # slot order of the reference: SMPL_BONE_ORDER_NAMES
         self._cfg_kw = dict(cfg)
         self._cfg = make_cfg(precision, **cfg)
+        self.act_dim = act_dim_of(self._cfg)
         h = C.c_void_p()
         _chk(self.lib.uhc_engine_create(C.byref(self._ms), C.byref(self._cfg), C.c_int(self.E), C.c_int(self.device), C.c_int(precision), C.byref(h)))
         self.h = h
@@ -129,6 +141,7 @@ class Engine:
     def set_cfg(self, **cfg):
         self._cfg_kw = dict(getattr(self, "_cfg_kw", {}), **cfg)
         self._cfg = make_cfg(self.precision, **self._cfg_kw)
+        self.act_dim = act_dim_of(self._cfg)
         _chk(self.lib.uhc_engine_set_cfg(self.h, C.byref(self._cfg)))
 
     def load_clips(self, experts, shapes=None, clip_models=None):
@@ -167,7 +180,7 @@ class Engine:
         """env.step(a) + custom_reward for all envs.  actions: float32 cuda tensor [E,105].  Returns views of the engine's
         output tensors (obs, reward, cinfo, fail, end, percent)."""
         t = self.torch
-        assert actions.is_cuda and actions.dtype == t.float32 and actions.is_contiguous() and tuple(actions.shape) == (self.E, ACT_DIM)
+        assert actions.is_cuda and actions.dtype == t.float32 and actions.is_contiguous() and tuple(actions.shape) == (self.E, self.act_dim)
         rew = self.reward if reward_out is None else reward_out
         _chk(self.lib.uhc_env_step(self.h, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()), C.c_void_p(rew.data_ptr()),
                                    C.c_void_p(self.cinfo.data_ptr()), C.c_void_p(self.fail.data_ptr()), C.c_void_p(self.end.data_ptr()),
@@ -177,7 +190,7 @@ class Engine:
 
     def step_host(self, actions, obs=None, reward=None, cinfo=None, fail=None, end=None, percent=None):
         """Host-buffer entry (H2D of actions and D2H of every requested output inside the call)."""
-        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.E, ACT_DIM)
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.E, self.act_dim)
         obs = np.empty((self.E, OBS_DIM), np.float32) if obs is None else obs
         reward = np.empty(self.E, np.float32) if reward is None else reward
         cinfo = np.empty((self.E, 5), np.float32) if cinfo is None else cinfo

@@ -165,6 +165,14 @@ class HumanoidModel:
         df[6:, 1], df[6:, 2], df[6:, 3] = self.jkp, self.jkd, self.torque_lim
         self.body_f, self.dof_f = np.ascontiguousarray(bf), np.ascontiguousarray(df)
 
+    # residual-force slot order of the explicit mode: vf_bodies = SMPL_BONE_ORDER_NAMES (humanoid_im.py:236-237, smpl_parser.py:11-36)
+    SMPL_BONE_ORDER = ("Pelvis", "L_Hip", "R_Hip", "Torso", "L_Knee", "R_Knee", "Spine", "L_Ankle", "R_Ankle", "Chest", "L_Toe", "R_Toe", "Neck", "L_Thorax",
+                       "R_Thorax", "Head", "L_Shoulder", "R_Shoulder", "L_Elbow", "R_Elbow", "L_Wrist", "R_Wrist", "L_Hand", "R_Hand")
+
+    def vf_slot(self):
+        """residual-force slot of every model body (bodies are numbered depth-first, the slots follow the SMPL joint order)"""
+        return [self.SMPL_BONE_ORDER.index(n) for n in self.body_names]
+
     def host_struct(self, variants=None):
         """ctypes struct of host pointers for uhc_engine_create / the emulation (arrays kept alive on self).
         variants: optional list of HumanoidModel shape variants (same topology); variant 0 must be `self`."""

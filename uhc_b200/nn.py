@@ -577,6 +577,119 @@ def ppo_epochs_tc(policy, value, log_std, opt_p, opt_v, xb, xT, actions, returns
     return losses
 
 
+class UhcNetDesc(C.Structure):
+    """include/uhc_ppo.h UhcNetDesc"""
+    _fields_ = [("nlayers", C.c_int), ("act", C.c_int), ("dims", C.c_int * 10), ("flat", C.c_void_p), ("gfull", C.c_void_p), ("nflat", C.c_long), ("gtail", C.c_long),
+                ("w_off", C.c_long * 8), ("b_off", C.c_long * 8), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("lr", C.c_float), ("W_bf16", C.c_void_p * 8),
+                ("kp", C.c_int * 8)]
+
+
+class UhcPpoCfg(C.Structure):
+    """include/uhc_ppo.h UhcPpoCfg"""
+    _fields_ = [("gamma", C.c_float), ("tau", C.c_float), ("clip_eps", C.c_float), ("grad_clip", C.c_float), ("clip_first_step_only", C.c_int), ("epochs", C.c_int)]
+
+
+def net_desc(net, opt):
+    """UhcNetDesc of an MLPNet + its flat Adam state (all pointers stay valid for the life of the net: the bf16 copies are refreshed in place)."""
+    if getattr(net, "_bf16_store", None) is None or net._bf16 is None:
+        net._prep_bf16()
+    assert opt.net is net, "the optimiser must be built on the net's flat tensors (nn.Adam(net.params(), lr, net=net))"
+    d = UhcNetDesc()
+    d.nlayers, d.act = len(net.W), ACT[net.htype]
+    for i, v in enumerate(net.dims):
+        d.dims[i] = v
+    d.flat, d.gfull, d.nflat, d.gtail = net.flat.data_ptr(), net.gfull.data_ptr(), net.nflat, net.GRAD_TAIL
+    for i in range(len(net.W)):
+        d.w_off[i], d.b_off[i] = net._offs[2 * i][0], net._offs[2 * i + 1][0]
+        d.W_bf16[i], d.kp[i] = net._bf16_store[i].data_ptr(), net._bf16_store[i].shape[1]
+    d.adam_m, d.adam_v, d.lr = opt.mflat.data_ptr(), opt.vflat.data_ptr(), opt.lr
+    d._keep = (net, opt, list(net._bf16_store))
+    return d
+
+
+def make_nccl_comm(rank, world, device):
+    """An ncclComm_t of this process group for the C-side update (uhc_ppo_update takes the communicator, include/uhc_ppo.h): the unique id is
+    made on rank 0 by the libnccl torch has loaded and broadcast through torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    lib = C.CDLL("libnccl.so.2")
+
+    class UniqueId(C.Structure):
+        _fields_ = [("internal", C.c_byte * 128)]
+    uid = UniqueId()
+    if rank == 0 and lib.ncclGetUniqueId(C.byref(uid)) != 0:
+        raise RuntimeError("ncclGetUniqueId failed")
+    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=device)
+    dist.broadcast(t, 0)
+    C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+    comm = C.c_void_p()
+    torch.cuda.set_device(device)
+    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    if lib.ncclCommInitRank(C.byref(comm), world, uid, rank) != 0:
+        raise RuntimeError("ncclCommInitRank failed")
+    return comm
+
+
+class CPpoTrainer:
+    """uhc_ppo_update (include/uhc_ppo.h): V(s), GAE, advantage normalisation and the PPO epochs of both nets behind ONE C-ABI call, with the
+    gradient all-reduce on the given ncclComm_t."""
+
+    def __init__(self, policy, value, opt_p, opt_v, max_rows, max_envs, device):
+        L = _lib()
+        L.uhc_ppo_last_error.restype = C.c_char_p
+        L.uhc_ppo_advantages.restype = C.c_void_p
+        L.uhc_ppo_returns.restype = C.c_void_p
+        L.uhc_ppo_kernel_launches.restype = C.c_long
+        self.L, self.policy, self.value, self.opt_p, self.opt_v = L, policy, value, opt_p, opt_v
+        self.dp, self.dv = net_desc(policy, opt_p), net_desc(value, opt_v)
+        self.h = C.c_void_p()
+        dev = device.index if hasattr(device, "index") else int(device)
+        if L.uhc_ppo_trainer_create(C.byref(self.dp), C.byref(self.dv), C.c_long(max_rows), C.c_int(max_envs), C.c_int(dev or 0), C.byref(self.h)) != 0:
+            raise RuntimeError("uhc_ppo_trainer_create: " + L.uhc_ppo_last_error().decode())
+        self.max_rows, self.max_envs = max_rows, max_envs
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.uhc_ppo_trainer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update(self, states, last_states, actions, rewards, masks, exps, log_std, T, E, gamma, tau, clip_eps, epochs, grad_clip, losses, zfilter=None,
+               z_sync=None, comm=None, world=1):
+        cfg = UhcPpoCfg(gamma, tau, clip_eps, float(grad_clip or 0.0), 1, epochs)
+        sp, sv = C.c_int(self.opt_p.step_n), C.c_int(self.opt_v.step_n)
+        done = C.c_int(1 if getattr(self.opt_p, "_clip_consumed", False) else 0)
+        rc = self.L.uhc_ppo_update(self.h, _p(states), _p(last_states), _p(actions), _p(rewards), _p(masks), _p(exps), _p(log_std), C.c_int(T), C.c_int(E),
+                                   C.byref(cfg), C.byref(sp), C.byref(sv), C.byref(done), _p(zfilter), _p(z_sync), comm, C.c_int(world), _p(losses), _stream(states))
+        if rc != 0:
+            raise RuntimeError("uhc_ppo_update: " + self.L.uhc_ppo_last_error().decode())
+        self.opt_p.step_n, self.opt_v.step_n = sp.value, sv.value
+        self.opt_p._clip_consumed = done.value > 0
+        # the C side refreshed the bf16 weight copies in place after every optimiser step
+        self.policy._bf16, self.value._bf16 = self.policy._bf16_store, self.value._bf16_store
+
+    @property
+    def kernel_launches(self):
+        return int(self.L.uhc_ppo_kernel_launches(self.h))
+
+    def comm_stats(self):
+        ms, by, calls = C.c_double(0), C.c_long(0), C.c_int(0)
+        if self.L.uhc_ppo_comm_stats(self.h, C.byref(ms), C.byref(by), C.byref(calls)) != 0:
+            raise RuntimeError("uhc_ppo_comm_stats: " + self.L.uhc_ppo_last_error().decode())
+        return ms.value, by.value, calls.value
+
+    def advantages(self, M):
+        import torch
+        out = torch.empty(M, device=self.policy.flat.device, dtype=torch.float32)
+        C.cdll.LoadLibrary("libcudart.so").cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(self.L.uhc_ppo_advantages(self.h)), C.c_size_t(4 * M), C.c_int(3))
+        return out
+
+
 def _ppo_update_fp32(policy, value, log_std, opt_p, opt_v, states, actions, returns, advantages, exps, clip_eps=0.2, epochs=10, grad_clip=40.0):
     import torch
     L = _lib()
