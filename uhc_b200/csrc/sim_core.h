@@ -446,7 +446,7 @@ UHC_DEV void rigid_row(const Real *I, const Real *u, bool ang, Real *row) {
 // <= 5 bodies instead of the 9 of the kinematic tree.  A joint on the path centre -> Pelvis is crossed against its kinematic
 // direction: with y = -qacc_j it reads a_child = a_parent + S_j y like every other joint, so its right-hand side and solution
 // just change sign.  The free joint (no armature) turns into the wrench  S_0^-T b_0  applied to the Pelvis body, and the centre
-// body is solved for its own spatial acceleration through six virtual dofs NV .. NV+5 with unit motion vectors.
+// body's own spatial acceleration solves the 6 x 6 system  IA a = -pA  directly (Gauss-Jordan across the six lanes holding its rows).
 //
 // Lane layout: the <= 5 bodies of one level are processed together, 6 lanes per body (lane = 6 g + r owns ROW r of that body's
 // articulated inertia; the bias wrench is replicated in the group).  The three dofs of a body's joint are eliminated as ONE block:
@@ -466,7 +466,6 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
     LV(rr) = lane - 6 * (lane / 6);
     LV(entn) = lane < 6 * LVL_G ? UHC_LDT(m.lvl_pack + (nlvl - 1) * LVL_G + lane / 6) : 0;
     for (int i = lane; i < NV; i += 32) arm[i] = UHC_LDT(m.dof_f + 4 * i) + arm_scale * UHC_LDT(m.dof_f + 4 * i + 2);   // joint-space diagonal
-    if (lane < 6) for (int c = 0; c < 6; c++) w.S[NV + lane][c] = c == lane ? Real(1) : Real(0);                       // virtual dofs of the centre body
     LANES_END
 #pragma unroll 1
     for (int lvl = nlvl - 1; lvl >= 0; --lvl) {
@@ -509,10 +508,10 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
         LANES_BEGIN
         for (int i = 0; i < 3; i++) { LVA(row)[i] = LVA(nrow)[i]; LVA(pA)[i] = LVA(npA)[i]; }
         LANES_END_R
-#pragma unroll 1
-        for (int blk = lvl == 0 ? 1 : 0; blk >= 0; --blk) {   // the centre body (level 0) has two blocks of virtual dofs
+        if (lvl == 0) break;               // the centre body: solved directly below
+        {
             LANES_BEGIN   // this lane's entries of U = IA S
-            const int b = LV(body), d0 = 3 * ((LV(ent) >> 20) & 31) + 3 * blk;
+            const int b = LV(body), d0 = 3 * ((LV(ent) >> 20) & 31);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const Real u = pdot6(LVA(row), as_pairs(w.S[d0 + k]));
@@ -521,19 +520,16 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
             }
             LANES_END
             LANES_BEGIN
-            const int b = LV(body), d0 = 3 * ((LV(ent) >> 20) & 31) + 3 * blk, r = LV(rr);
-            const bool real_dofs = d0 < NV;                              // virtual dofs: no armature, zero right-hand side
+            const int b = LV(body), d0 = 3 * ((LV(ent) >> 20) & 31), r = LV(rr);
             const Real sg = ((LV(ent) >> 25) & 1) ? Real(-1) : Real(1);   // joint crossed against its kinematic direction
             P U0[3], U1[3], U2[3];
             const P *S0 = as_pairs(w.S[d0]), *S1 = as_pairs(w.S[d0 + 1]), *S2 = as_pairs(w.S[d0 + 2]);
 #pragma unroll
             for (int i = 0; i < 3; i++) { U0[i] = as_pairs(w.aU[d0])[i]; U1[i] = as_pairs(w.aU[d0 + 1])[i]; U2[i] = as_pairs(w.aU[d0 + 2])[i]; }
             // D = S^T U + arm (symmetric), u = b - S^T pA
-            const Real D00 = pdot6(S0, U0) + (real_dofs ? arm[d0] : Real(0)), D11 = pdot6(S1, U1) + (real_dofs ? arm[d0 + 1] : Real(0)),
-                       D22 = pdot6(S2, U2) + (real_dofs ? arm[d0 + 2] : Real(0));
+            const Real D00 = pdot6(S0, U0) + arm[d0], D11 = pdot6(S1, U1) + arm[d0 + 1], D22 = pdot6(S2, U2) + arm[d0 + 2];
             const Real D01 = pdot6(S0, U1), D02 = pdot6(S0, U2), D12 = pdot6(S1, U2);
-            const Real u0 = (real_dofs ? sg * x[d0] : Real(0)) - pdot6(S0, LVA(pA)), u1 = (real_dofs ? sg * x[d0 + 1] : Real(0)) - pdot6(S1, LVA(pA)),
-                       u2 = (real_dofs ? sg * x[d0 + 2] : Real(0)) - pdot6(S2, LVA(pA));
+            const Real u0 = sg * x[d0] - pdot6(S0, LVA(pA)), u1 = sg * x[d0 + 1] - pdot6(S1, LVA(pA)), u2 = sg * x[d0 + 2] - pdot6(S2, LVA(pA));
             // inverse by the adjugate (D is symmetric positive definite and small)
             const Real c00 = D11 * D22 - D12 * D12, c01 = D02 * D12 - D01 * D22, c02 = D01 * D12 - D02 * D11;
             const Real c11 = D00 * D22 - D02 * D02, c12 = D01 * D02 - D00 * D12, c22 = D00 * D11 - D01 * D01;
@@ -548,42 +544,67 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
             if (b >= 0 && r == 0) { w.au[d0] = v0; w.au[d0 + 1] = v1; w.au[d0 + 2] = v2; }
             LANES_END
             LANES_BEGIN   // U D^-1 replaces U (after every lane of the group has read U)
-            const int b = LV(body), d0 = 3 * ((LV(ent) >> 20) & 31) + 3 * blk;
+            const int b = LV(body), d0 = 3 * ((LV(ent) >> 20) & 31);
             if (b >= 0) { w.aU[d0][LV(rr)] = LVA(Ur)[0]; w.aU[d0 + 1][LV(rr)] = LVA(Ur)[1]; w.aU[d0 + 2][LV(rr)] = LVA(Ur)[2]; }
             LANES_END
         }
     }
-    // centre -> leaves (the spatial acceleration a is replicated in the 6 lanes of a group)
-    LVARA(Real, acc, 6); LVARA(Real, pacc, 6);
+    // ---- the centre body (no joint above it): IA a = -pA, a 6 x 6 symmetric positive definite system whose row r sits in lane r --
+    // Gauss-Jordan elimination across the six lanes (one broadcast of the pivot row per step), no pivoting needed
+    LVARA(Real, Mx, 7); LVARA(Real, Pk, 7); LVAR(Real, sol); LVARA(Real, acc, 6); LVARA(Real, pacc, 6);
     LANES_BEGIN
-    for (int i = 0; i < 6; i++) LVA(pacc)[i] = 0;
-    LV(entn) = lane < 6 * LVL_G ? UHC_LDT(m.lvl_pack + lane / 6) : 0;
+    for (int i = 0; i < 3; i++) { LVA(Mx)[2 * i] = LVA(row)[i].x; LVA(Mx)[2 * i + 1] = LVA(row)[i].y; }
+    const P t = LV(rr) < 2 ? LVA(pA)[0] : (LV(rr) < 4 ? LVA(pA)[1] : LVA(pA)[2]);
+    LVA(Mx)[6] = -((LV(rr) & 1) ? t.y : t.x);
+    LANES_END_R
+#pragma unroll
+    for (int kk = 0; kk < 6; ++kk) {
+        const int k = kk < 3 ? kk + 3 : kk - 3;   // linear rows first: their block is m 1 (large, diagonal), and what is left for the angular rows is the
+                                                  // inertia about the centre of mass -- eliminating the angular rows first cancels instead
+        WSHFL(Pk, Mx, 7, k);
+        LANES_BEGIN
+        if (lane != k && lane < 6) {
+            const Real f = LVA(Mx)[k] * rcp_(LVA(Pk)[k]);
+#pragma unroll
+            for (int j = 0; j < 7; j++) LVA(Mx)[j] -= f * LVA(Pk)[j];
+        }
+        LANES_END_R
+    }
+    LANES_BEGIN
+    const int r = LV(rr);
+    const Real d = r == 0 ? LVA(Mx)[0] : r == 1 ? LVA(Mx)[1] : r == 2 ? LVA(Mx)[2] : r == 3 ? LVA(Mx)[3] : r == 4 ? LVA(Mx)[4] : LVA(Mx)[5];
+    LV(sol) = lane < 6 ? LVA(Mx)[6] * rcp_(d) : Real(0);
+    LANES_END_R
+    WSHFL1(LVA(pacc)[0], sol, 0); WSHFL1(LVA(pacc)[1], sol, 1); WSHFL1(LVA(pacc)[2], sol, 2);
+    WSHFL1(LVA(pacc)[3], sol, 3); WSHFL1(LVA(pacc)[4], sol, 4); WSHFL1(LVA(pacc)[5], sol, 5);
+    // centre -> leaves (the spatial acceleration a is replicated in the 6 lanes of a group; every lane starts from the centre body's)
+    LANES_BEGIN
+    const int bc = (UHC_LDT(m.lvl_pack) & 63) - 1;
+    if (use_contacts && lane < 6) w.Ab[bc][lane] = LV(sol);
+    LV(entn) = (lane < 6 * LVL_G && nlvl > 1) ? UHC_LDT(m.lvl_pack + LVL_G + lane / 6) : 0;
     LANES_END
 #pragma unroll 1
-    for (int lvl = 0; lvl < nlvl; ++lvl) {
+    for (int lvl = 1; lvl < nlvl; ++lvl) {
         LANES_BEGIN
         const int g = lane / 6;
         const int e = LV(entn);
         LV(entn) = (g < LVL_G && lvl + 1 < nlvl) ? UHC_LDT(m.lvl_pack + (lvl + 1) * LVL_G + g) : 0;
         const int b = (e & 63) - 1;
         LV(body) = b; LV(ent) = e;
-        LV(src) = (b >= 0 && lvl > 0) ? ((e >> 6) & 7) * 6 : lane;
+        LV(src) = b >= 0 ? ((e >> 6) & 7) * 6 : lane;
         LANES_END_R
         WSHFL(acc, pacc, 6, LV(src));
         LANES_BEGIN
         const int b = LV(body), r = LV(rr);
         P a[3];
-        for (int i = 0; i < 3; i++) { a[i].x = lvl == 0 ? Real(0) : LVA(acc)[2 * i]; a[i].y = lvl == 0 ? Real(0) : LVA(acc)[2 * i + 1]; }
+        for (int i = 0; i < 3; i++) { a[i].x = LVA(acc)[2 * i]; a[i].y = LVA(acc)[2 * i + 1]; }
         if (b >= 0) {
             const Real sg = ((LV(ent) >> 25) & 1) ? Real(-1) : Real(1);
-#pragma unroll 1
-            for (int blk = 0; blk < (lvl == 0 ? 2 : 1); ++blk) {   // uniform trip count (only the centre body sits on level 0)
-                const int d0 = 3 * ((LV(ent) >> 20) & 31) + 3 * blk;
-                const Real x0 = w.au[d0] - pdot6(as_pairs(w.aU[d0]), a), x1 = w.au[d0 + 1] - pdot6(as_pairs(w.aU[d0 + 1]), a),
-                           x2 = w.au[d0 + 2] - pdot6(as_pairs(w.aU[d0 + 2]), a);
-                if (r == 0 && d0 < NV) { x[d0] = sg * x0; x[d0 + 1] = sg * x1; x[d0 + 2] = sg * x2; }
-                paxpy6(x0, as_pairs(w.S[d0]), a); paxpy6(x1, as_pairs(w.S[d0 + 1]), a); paxpy6(x2, as_pairs(w.S[d0 + 2]), a);
-            }
+            const int d0 = 3 * ((LV(ent) >> 20) & 31);
+            const Real x0 = w.au[d0] - pdot6(as_pairs(w.aU[d0]), a), x1 = w.au[d0 + 1] - pdot6(as_pairs(w.aU[d0 + 1]), a),
+                       x2 = w.au[d0 + 2] - pdot6(as_pairs(w.aU[d0 + 2]), a);
+            if (r == 0) { x[d0] = sg * x0; x[d0 + 1] = sg * x1; x[d0 + 2] = sg * x2; }
+            paxpy6(x0, as_pairs(w.S[d0]), a); paxpy6(x1, as_pairs(w.S[d0 + 1]), a); paxpy6(x2, as_pairs(w.S[d0 + 2]), a);
             if (b == 0 && r == 0) {   // free-joint accelerations from the Pelvis spatial acceleration: qacc_0 = S_0^-1 a = S_0^T a
                 x[0] = a[1].y; x[1] = a[2].x; x[2] = a[2].y;
                 for (int k = 0; k < 3; k++) x[3 + k] = w.S[3 + k][0] * a[0].x + w.S[3 + k][1] * a[0].y + w.S[3 + k][2] * a[1].x;
