@@ -230,7 +230,7 @@ def run_gpu(args):
     agent.reset_envs()
     L, h = agent.engine.lib, agent.engine.h
     R = max(1, min(K, 32))                               # buffer rows in use: one CUDA graph (and one pair of kernel events) per row
-    buf = RolloutBuffer(R, E, agent.dev, agent.act_dim)
+    buf = RolloutBuffer(R, E, agent.dev, agent.act_dim, agent.obs_dim)
     if L.uhc_rollout_time_env_step(h, C.c_int(R)) != 0:  # CUDA events around k_env_step, recorded on the launching stream inside the graph
         raise RuntimeError("uhc_rollout_time_env_step failed")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=agent.dev)
@@ -391,7 +391,7 @@ def run_train(args):
     agent = BatchedAgent(E, clips, shapes, device=local, seed=1, rank=rank, world=world, model=base, variants=variants, clip_models=clip_models,
                          num_optim_epoch=TRAIN_EPOCHS, t_min=15, t_max=300)
     agent.reset_envs()
-    buf = RolloutBuffer(T, E, agent.dev, agent.act_dim)
+    buf = RolloutBuffer(T, E, agent.dev, agent.act_dim, agent.obs_dim)
     clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(W):
         agent.sample(T, buf); agent.update_params(buf)

@@ -22,7 +22,8 @@ extern "C" {
 #define UHC_OBS_DIM 657
 #define UHC_ACT_DIM 105       /* action width of the default configuration (implicit residual force + meta-PD) */
 #define UHC_MAX_ACT_DIM 315   /* explicit residual force + meta-PD */
-#define UHC_EX_SIZE 508   /* expert frame record: qpos76 qvel75 wbpos72 wbquat96 bquat96 bangvel72 ee_wpos15 com3 pad3 */
+#define UHC_MAX_OBS_DIM 784   /* obs_v 1 (get_full_obs_v1) */
+#define UHC_EX_SIZE 576   /* expert frame record: qpos76 qvel75 wbpos72 wbquat96 bquat96 bangvel72 ee_wpos15 body_com72 (com = its first 3) pad2 */
 #define UHC_BODYF 20
 
 typedef struct UhcEngine UhcEngine;
@@ -62,6 +63,8 @@ typedef struct {
      * The action row is [69 joint targets | residual-force dims | 30 meta-PD scales when meta_pd]: uhc_engine_act_dim() gives its width. */
     int rfc_mode;
     int vf_slot[UHC_NB];    /* explicit mode: residual-force slot of body b (the reference orders the slots by SMPL_BONE_ORDER_NAMES, smpl_parser.py:11-36) */
+    int obs_v;              /* cfg.obs_v (copycat_config.py:88): 2 = get_full_obs_v2 (657 dims, humanoid_im.py:419-503), 1 = get_full_obs_v1 (784 dims, :323-417);
+                             * 0 is read as 2.  uhc_engine_obs_dim() gives the row width of every obs buffer. */
 } UhcEnvCfg;
 
 const char *uhc_last_error(void);
@@ -119,6 +122,7 @@ int uhc_engine_counters(UhcEngine *e, int *out4);
  * fraction `percent` as float bits -- what the reference appends to its per-clip success history (agent_copycat.py:561). */
 const int *uhc_episode_log_dev(const UhcEngine *e);
 int uhc_num_envs(const UhcEngine *e);
+int uhc_engine_obs_dim(const UhcEngine *e);      /* env.obs_dim (humanoid_im.py:256-258) */
 int uhc_engine_act_dim(const UhcEngine *e);      /* env.action_dim (humanoid_im.py:250): 69 + (6 | 216) + (30 if meta_pd) */
 int uhc_kernel_launches(const UhcEngine *e);   /* kernels launched by this engine so far (bench `gpu_launches`) */
 

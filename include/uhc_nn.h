@@ -40,6 +40,12 @@ int uhc_gaussian_sample(const float *mean, const float *log_std, const unsigned 
                         unsigned long long seed, unsigned long long step, void *stream);
 int uhc_gaussian_logprob(const float *mean, const float *log_std, const float *action, float *logp, int M, int A, void *stream);
 
+/* PolicyMCP mixture head (uhc/models/policy_mcp.py:28-36): mean = sum_k softmax(c)_k xall_k ; xall = [P][M][A] primitive outputs, c = [M][P] composer
+ * outputs (after the composer MLP's last activation); weight [M][P] = the softmax, kept for uhc_mcp_backward, which returns the gradients wrt
+ * the primitive outputs (dxall [P][M][A]) and wrt c (dc [M][P]) given dmean. */
+int uhc_mcp_combine(const float *xall, const float *c, float *weight_or_null, float *mean, int M, int A, int P, void *stream);
+int uhc_mcp_backward(const float *xall, const float *weight, const float *dmean, float *dxall, float *dc, int M, int A, int P, void *stream);
+
 /* PPO clipped surrogate gradient wrt the mean head (agent_ppo.py:58-65; rows with exps == 0 are excluded, :45);
  * inv_count = 1 / #selected rows; loss_acc (optional) accumulates the surrogate loss. */
 int uhc_ppo_policy_grad(const float *mean, const float *log_std, const float *action, const float *adv, const float *fixed_logp, const float *exps,

@@ -31,6 +31,7 @@ typedef struct UhcNetDesc {
     float lr;
     void *W_bf16[8];           /* bf16 copies of W[i] with K padded to kp[i] = dims[i] rounded up to 64: refreshed IN PLACE after every step */
     int kp[8];
+    int head_act;              /* activation after the OUTPUT layer: UHC_ACT_NONE for policy / value heads, the trunk's activation for a PolicyMCP composer */
 } UhcNetDesc;
 
 typedef struct UhcPpoCfg {
@@ -47,6 +48,10 @@ const char *uhc_ppo_last_error(void);
 
 /* workspace for updates of up to max_rows transitions from up to max_envs environments (both nets, shared backward scratch) */
 int uhc_ppo_trainer_create(const UhcNetDesc *policy, const UhcNetDesc *value, long max_rows, int max_envs, int device, UhcPpoTrainer **out);
+/* PolicyMCP (uhc/models/policy_mcp.py:9-37): policy_nets = nprim primitive nets followed by the composer (head_act = its activation).  Every
+ * entry shares ONE flat parameter / gradient / Adam tensor (flat, gfull, adam_m, adam_v, nflat identical; w_off / b_off are offsets into it), so the
+ * mixture is still one all-reduce and one Adam launch per step. */
+int uhc_ppo_trainer_create_mcp(const UhcNetDesc *policy_nets, int nprim, const UhcNetDesc *value, long max_rows, int max_envs, int device, UhcPpoTrainer **out);
 void uhc_ppo_trainer_destroy(UhcPpoTrainer *t);
 
 /* One PPO iteration's update on a time-major [T][E] rollout (M = T*E rows, row = t*E + e):
@@ -60,6 +65,11 @@ void uhc_ppo_trainer_destroy(UhcPpoTrainer *t);
 int uhc_ppo_update(UhcPpoTrainer *t, const float *states, const float *last_states, const float *actions, const float *rewards, const float *masks,
                    const float *exps, const float *log_std, int T, int E, const UhcPpoCfg *cfg, int *adam_step_policy, int *adam_step_value,
                    int *policy_steps_done, double *zfilter_stats, double *zfilter_sync, void *nccl_comm, int world, float *losses_out, void *stream);
+
+/* AgentPPO.update_policy (agent_ppo.py:16-51) alone: the epochs on caller-provided returns and (already normalised) advantages, M rows. */
+int uhc_ppo_update_policy(UhcPpoTrainer *t, const float *states, const float *actions, const float *returns, const float *advantages, const float *exps,
+                          const float *log_std, long M, const UhcPpoCfg *cfg, int *adam_step_policy, int *adam_step_value, int *policy_steps_done,
+                          void *nccl_comm, int world, float *losses_out, void *stream);
 
 /* advantages / returns of the last update (device, M floats each; valid until the next call) -- parity hooks */
 const float *uhc_ppo_advantages(const UhcPpoTrainer *t);

@@ -26,12 +26,22 @@ typedef struct {
     const float *bias[8];
 } UhcMlp;
 
+/* PolicyMCP (uhc/models/policy_mcp.py:9-37, actor_type "mcp" of config/release/uhc_implicit.yml): nprim primitive MLPs (same widths as a
+ * PolicyGaussian trunk + action_mean head) and a composer MLP obs -> composer_dim -> nprim whose EVERY layer is followed by the activation
+ * (mlp.py:24-27) before the softmax; action_mean = sum_k softmax(composer(x))_k * prim_k(x). */
+#define UHC_MCP_MAX_PRIM 8
+typedef struct {
+    int nprim, reserved;
+    UhcMlp prim[UHC_MCP_MAX_PRIM];
+    UhcMlp composer;
+} UhcMcp;
+
 /* Time-major rollout buffer [T_cap][E][...] (the device-resident TrajBatch, khrylib/rl/core/trajbatch.py:4-15) and the current
  * observation of every env (written by uhc_env_reset / the step kernel). logp / fails may be NULL. */
 typedef struct {
     float *states, *actions, *rewards, *masks, *exps, *logp;
     int *fails;
-    float *obs_cur;       /* [E][657] raw observation before the step; overwritten with the next one */
+    float *obs_cur;       /* [E][uhc_engine_obs_dim] raw observation before the step; overwritten with the next one */
     int *ep_clip;         /* optional [T_cap][E]: clip index of the episode that ended at this step (-1: none) ... */
     float *ep_pct;        /* ... and its completed fraction: the per-clip success history of agent_copycat.py:561 */
     int T_cap, reserved;
@@ -50,11 +60,18 @@ int uhc_policy_forward(UhcEngine *e, const float *obs_dev, const UhcMlp *mlp, co
                        unsigned long long seed, const unsigned char *mean_action_or_null, float *state_out_or_null, float *action_out, float *logp_out_or_null,
                        void *stream);
 
+/* the same with a PolicyMCP mixture in place of the single MLP */
+int uhc_policy_forward_mcp(UhcEngine *e, const float *obs_dev, const UhcMcp *mcp, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
+                           unsigned long long seed, const unsigned char *mean_action_or_null, float *state_out_or_null, float *action_out, float *logp_out_or_null,
+                           void *stream);
+
 /* T lock-step control steps of every env into rows row0 .. row0+T-1 of the buffer.  noise_rate: P(sampled action) per env and step
  * (agent_copycat.py:530; exp = 1 for sampled rows).  use_graph != 0: the kernel sequence is captured once per argument set into a
  * CUDA graph and replayed (no host work between kernels); 0: plain stream launches of the same kernels (bit-identical results). */
 int uhc_rollout(UhcEngine *e, int T, int row0, const UhcMlp *mlp, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
                 unsigned long long seed, float noise_rate, const UhcRolloutBuf *buf, int use_graph, void *stream);
+int uhc_rollout_mcp(UhcEngine *e, int T, int row0, const UhcMcp *mcp, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
+                    unsigned long long seed, float noise_rate, const UhcRolloutBuf *buf, int use_graph, void *stream);
 /* measurement hook: CUDA events around the env-step kernel of buffer rows 0 .. nrows-1, recorded on the launching stream (also inside
  * graph replays); uhc_rollout_env_step_ms returns the duration of the last step written to `row`.  nrows = 0 disables. */
 int uhc_rollout_time_env_step(UhcEngine *e, int nrows);

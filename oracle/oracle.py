@@ -157,15 +157,29 @@ class Env:
     def action_dim(self):
         return lib().or_env_action_dim(self.h)
 
+    def set_obs_v(self, obs_v):
+        """cfg.obs_v: 2 (default, 657 dims) or 1 (get_full_obs_v1, 784 dims; needs expert["body_com"])"""
+        self._obs_v = int(obs_v)
+        bc = getattr(self, "_body_com", None)
+        assert self._obs_v != 1 or bc is not None, "obs_v 1 needs expert['body_com']"
+        lib().or_env_set_obs_v(self.h, C.c_int(self._obs_v), _p(bc) if bc is not None else None)
+
+    @property
+    def obs_dim(self):
+        return lib().or_env_obs_dim(self.h)
+
     def load_expert(self, ex, shape_obs=None):
         keys = ["qpos", "qvel", "wbpos", "wbquat", "bquat", "bangvel", "ee_wpos", "com"]
+        self._body_com = np.ascontiguousarray(np.asarray(ex["body_com"], dtype=np.float64).reshape(len(ex["qpos"]), 72)) if "body_com" in ex else None
+        if getattr(self, "_obs_v", 2) == 1:
+            self.set_obs_v(1)
         self._ex = [np.ascontiguousarray(ex[k], dtype=np.float64) for k in keys]
         so = np.zeros(17) if shape_obs is None else np.asarray(shape_obs, dtype=np.float64)
         self._so = np.ascontiguousarray(so)
         lib().or_env_set_expert(self.h, C.c_int(len(self._ex[0])), *[_p(a) for a in self._ex], _p(self._so))
 
     def reset(self, qpos=None, qvel=None):
-        obs = np.zeros(OBS_DIM)
+        obs = np.zeros(self.obs_dim)
         qp = None if qpos is None else _p(np.ascontiguousarray(qpos, dtype=np.float64))
         qv = None if qvel is None else _p(np.ascontiguousarray(qvel, dtype=np.float64))
         lib().or_env_reset(self.h, qp, qv, _p(obs))
@@ -173,7 +187,7 @@ class Env:
 
     def step(self, action):
         a = np.ascontiguousarray(action, dtype=np.float64)
-        obs = np.zeros(OBS_DIM)
+        obs = np.zeros(self.obs_dim)
         fail, end, pct = C.c_int(0), C.c_int(0), C.c_double(0)
         done = lib().or_env_step(self.h, _p(a), _p(obs), C.byref(fail), C.byref(end), C.byref(pct))
         cinfo = np.zeros(5)

@@ -410,6 +410,7 @@ void or_step(const OrModel *m, OrData *d) { or_forward(m, d); or_integrate(m, d)
 typedef struct {
     int len;                          /* frames in the clip slice */
     const double *qpos, *qvel, *wbpos, *wbquat, *bquat, *bangvel, *ee_wpos, *com; /* T x {76,75,72,96,96,72,15,3} */
+    const double *body_com;           /* T x 72 per-body centre-of-mass positions (expert["body_com"], obs v1 only); may be NULL */
     double shape_obs[17];             /* beta[16], gender */
 } OrExpert;
 
@@ -424,6 +425,7 @@ typedef struct {
     int rfc_mode;                     /* 0 = implicit root wrench (6 action dims), 1 = explicit per-body forces (cfg.residual_force_mode, humanoid_im.py:231-243) */
     int vf_dim;                       /* action dims of the residual force: 6, or 9 per body x 24 bodies */
     int vf_body[NB];                  /* explicit: model body of residual-force slot i (vf_bodies = SMPL_BONE_ORDER_NAMES, humanoid_im.py:236-237) */
+    int obs_v;                        /* cfg.obs_v: 2 = get_full_obs_v2 (657 with the shape vector), 1 = get_full_obs_v1 (784: + per-body COM blocks, no shape) */
 } OrEnv;
 
 OrEnv *or_env_create(OrModel *m) {
@@ -434,6 +436,7 @@ OrEnv *or_env_create(OrModel *m) {
     double w[5] = {0.3, 0.1, 0.45, 0.1, 0.05}, k[5] = {2.0, 0.005, 5.0, 100.0, 1.0};
     memcpy(e->w, w, 40); memcpy(e->k, k, 40);
     e->rfc_mode = 0; e->vf_dim = 6; for (int b = 0; b < NB; b++) e->vf_body[b] = b;
+    e->obs_v = 2;
     return e;
 }
 /* residual_force_mode (copycat_config.py:105-109): explicit = contact point + force + torque per body (residual_force_torque = True,
@@ -443,6 +446,8 @@ void or_env_set_rfc_mode(OrEnv *e, int explicit_mode, const int *vf_body) {
     if (vf_body) memcpy(e->vf_body, vf_body, sizeof e->vf_body);
 }
 int or_env_action_dim(const OrEnv *e) { return NU + e->vf_dim + (e->meta_pd ? 30 : 0); }
+void or_env_set_obs_v(OrEnv *e, int obs_v, const double *body_com) { e->obs_v = obs_v == 1 ? 1 : 2; e->ex.body_com = body_com; }
+int or_env_obs_dim(const OrEnv *e) { return e->obs_v == 1 ? 784 : 657; }
 void or_env_free(OrEnv *e) { if (e) { or_data_free(e->d); free(e); } }
 OrData *or_env_data(OrEnv *e) { return e->d; }
 void or_env_set_expert(OrEnv *e, int len, const double *qpos, const double *qvel, const double *wbpos, const double *wbquat,
@@ -539,7 +544,9 @@ static void or_rfc_explicit(OrEnv *e, const double *ctrl) {
     memcpy(d->qfrc_applied, qfrc, sizeof qfrc);
 }
 
-void or_obs_v2(const OrEnv *e, double *obs) { /* humanoid_im.py:419-503, obs_coord = "root" */
+/* get_full_obs_v2 (humanoid_im.py:419-503) and get_full_obs_v1 (:323-417), obs_coord = "root", obs_vel = "full".  v1 = v2 with two more blocks
+   (per-body COM relative to the root, COM difference to the expert's body_com) between the joint-position blocks and the quaternions, and no shape vector. */
+void or_obs_v2(const OrEnv *e, double *obs) {
     const OrData *d = e->d; double qpos[NQ], qvel[NV], R[9], t[3];
     memcpy(qpos, d->qpos, sizeof qpos); memcpy(qvel, d->qvel, sizeof qvel);
     q2mat(qpos+3, R); mtv(R, qvel, t); memcpy(qvel, t, 24);                       /* :425 */
@@ -568,12 +575,19 @@ void or_obs_v2(const OrEnv *e, double *obs) { /* humanoid_im.py:419-503, obs_coo
     o += 72;
     for (int b = 0; b < NB; b++) { double r[3] = {tjp[3*b]-d->xpos[b][0], tjp[3*b+1]-d->xpos[b][1], tjp[3*b+2]-d->xpos[b][2]}; mtv(R, r, t); for (int k = 0; k < 3; k++) obs[o+24*k+b] = t[k]; }
     o += 72;
+    if (e->obs_v == 1) {                                                           /* :383-393 */
+        const double *tcom = e->ex.body_com + 72*ind;
+        for (int b = 0; b < NB; b++) { double r[3] = {d->xipos[b][0]-qpos[0], d->xipos[b][1]-qpos[1], d->xipos[b][2]-qpos[2]}; mtv(R, r, t); for (int k = 0; k < 3; k++) obs[o+24*k+b] = t[k]; }
+        o += 72;
+        for (int b = 0; b < NB; b++) { double r[3] = {tcom[3*b]-d->xipos[b][0], tcom[3*b+1]-d->xipos[b][1], tcom[3*b+2]-d->xipos[b][2]}; mtv(R, r, t); for (int k = 0; k < 3; k++) obs[o+24*k+b] = t[k]; }
+        o += 72;
+    }
     int use_target = (d->xquat[0][0] == 0);                                        /* :485 */
     for (int b = 0; b < NB; b++) { const double *cq = use_target ? twq+4*b : d->xquat[b]; qmul(hqi, cq, obs+o+4*b); }
     o += 96;
-    for (int b = 0; b < NB; b++) { const double *cq = use_target ? twq+4*b : d->xquat[b]; double iq[4]; qinv(cq, iq); double n = sqrt(cq[0]*cq[0]+cq[1]*cq[1]+cq[2]*cq[2]+cq[3]*cq[3]); for (int k = 0; k < 4; k++) iq[k] *= n; /* inverse_batch divides by |q|, not |q|^2 */ qmul(iq, twq+4*b, obs+o+4*b); }
+    for (int b = 0; b < NB; b++) { const double *cq = use_target ? twq+4*b : d->xquat[b]; double iq[4]; qinv(cq, iq); double n = e->obs_v == 1 ? 1.0 : sqrt(cq[0]*cq[0]+cq[1]*cq[1]+cq[2]*cq[2]+cq[3]*cq[3]); for (int k = 0; k < 4; k++) iq[k] *= n; /* v2: inverse_batch divides by |q|, not |q|^2; v1: quaternion_inverse (:411) */ qmul(iq, twq+4*b, obs+o+4*b); }
     o += 96;
-    memcpy(obs+o, e->ex.shape_obs, 17*8); o += 17;
+    if (e->obs_v != 1) { memcpy(obs+o, e->ex.shape_obs, 17*8); o += 17; }
 }
 
 static void rot_from_quat(const double *q, double *rv) { /* transformation.py:362-372 */

@@ -28,6 +28,7 @@ static void set_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) {
     c.reactive_v = 0; c.reactive_rate = 0; c.auto_reset = 0; c.t_min = h->t_min; c.t_max = h->t_max; c.reset_seed = h->reset_seed; c.num_clips = 0;
     c.rfc_mode = h->rfc_mode == 1 ? 1 : 0; c.vf_dim = c.rfc_mode ? VF_BODY_DIM * NB : 6; c.act_dim = NU + c.vf_dim + (h->meta_pd ? 2 * NSUB : 0);
     for (int b = 0; b < NB; b++) c.vf_slot[b] = (signed char)h->vf_slot[b];
+    c.obs_v = h->obs_v == 1 ? 1 : 2; c.obs_dim = c.obs_v == 1 ? OBS_DIM_V1 : OBS_DIM;
 }
 
 template <class Real>

@@ -10,7 +10,7 @@ from uhc_b200.model import HumanoidModel
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libuhc_emu.so")
 ST = dict(Q=0, V=76, AW=152, C=228, IB=304, S=544, XPOS=996, XQUAT=1068, XIPOS=1164, BQUAT=1236, PBQUAT=1332, SIZE=1428)
-EX_SIZE = 508
+EX_SIZE = 576
 
 
 class UhcEnvCfg(C.Structure):
@@ -18,7 +18,7 @@ class UhcEnvCfg(C.Structure):
                 ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
                 ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double),
                 ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reactive_v", C.c_int), ("reset_seed", C.c_ulonglong),
-                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24)]
+                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24), ("obs_v", C.c_int)]
 
 
 def default_cfg(precision=32, **kw):
@@ -31,6 +31,7 @@ def default_cfg(precision=32, **kw):
     c.k = (C.c_double * 5)(2.0, 0.005, 5.0, 100.0, 1.0)
     c.newton_tol = 1e-11 if precision == 64 else 1e-5
     c.vf_slot = (C.c_int * 24)(*range(24))
+    c.obs_v = 2
     for k, v in kw.items():
         setattr(c, k, v)
     return c
@@ -44,6 +45,8 @@ def pack_expert(ex):
     for k, n in (("qpos", 76), ("qvel", 75), ("wbpos", 72), ("wbquat", 96), ("bquat", 96), ("bangvel", 72), ("ee_wpos", 15), ("com", 3)):
         out[:, o:o + n] = np.asarray(ex[k]).reshape(T, n)
         o += n
+    if "body_com" in ex:
+        out[:, 502:574] = np.asarray(ex["body_com"]).reshape(T, 72)
     return out
 
 
@@ -67,6 +70,7 @@ class Emu:
         self.model = model or HumanoidModel()
         self._ms = self.model.host_struct()
         self._cfg = default_cfg(precision, **cfg)
+        self.obs_dim = 784 if self._cfg.obs_v == 1 else 657
         self.h = C.c_void_p(self.lib.emu_create(C.byref(self._ms), C.byref(self._cfg), C.c_int(num_envs), C.c_int(precision)))
 
     def load_clips(self, experts, shapes):
@@ -77,7 +81,7 @@ class Emu:
         self.lib.emu_load_clips(self.h, self.prec, len(experts), _p(lens, C.c_int), _p(frames), _p(shp))
 
     def reset(self, env=0, clip=0, start=0, length=None, qpos=None, qvel=None):
-        obs = np.zeros(657)
+        obs = np.zeros(self.obs_dim)
         L = int(self.lens[clip]) - start if length is None else length      # Engine.reset: the rest of the clip from `start`
         q = None if qpos is None else np.ascontiguousarray(qpos, dtype=np.float64)
         v = None if qvel is None else np.ascontiguousarray(qvel, dtype=np.float64)
@@ -86,7 +90,7 @@ class Emu:
 
     def step(self, action, env=0):
         a = np.ascontiguousarray(action, dtype=np.float64)
-        obs, rew, ci, pct, tq = np.zeros(657), np.zeros(1), np.zeros(5), np.zeros(1), np.zeros((15, 69))
+        obs, rew, ci, pct, tq = np.zeros(self.obs_dim), np.zeros(1), np.zeros(5), np.zeros(1), np.zeros((15, 69))
         fail, end = C.c_int(0), C.c_int(0)
         done = self.lib.emu_step(self.h, self.prec, env, _p(a), _p(obs), _p(rew), _p(ci), C.byref(fail), C.byref(end), _p(pct), _p(tq))
         return obs, float(rew[0]), bool(done), {"fail": bool(fail.value), "end": bool(end.value), "percent": float(pct[0]), "c_info": ci, "torque": tq}

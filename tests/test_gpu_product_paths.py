@@ -298,9 +298,10 @@ def _ppo_real_inputs(N=8192, S=657, A=105, hs=(2048, 1024, 512), seed=11):
     return pol, val, states, actions, returns, adv, exps, probe
 
 
-@pytest.mark.parametrize("use_tc", [True, False])
+@pytest.mark.parametrize("use_tc", ["c_abi", True, False])
 def test_ppo_update_at_production_sizes_matches_khrylib(golden_dir, use_tc):
-    """ppo_update (use_tc=True is what BatchedAgent.update_params runs) against AgentPPO.update_policy of the unmodified reference in
+    """The PPO epochs -- "c_abi": uhc_ppo_update_policy, the C-ABI path BatchedAgent.update_params runs (through uhc_ppo_update); True / False: the
+    Python-orchestrated tensor-core / fp32 SIMT sequences of the same kernels -- against AgentPPO.update_policy of the unmodified reference in
     fp64 (tools/make_golden.py gen_ppo_real): nets 657-2048-1024-512-{105,1}, N = 8192 rows, 3 epochs (value step, then clipped
     surrogate step with the first-step grad-norm clip), Adam.  Compared: the change of the policy mean / value on a 256-row probe batch
     and 4096 sampled entries of every parameter tensor.
@@ -324,7 +325,14 @@ def test_ppo_update_at_production_sizes_matches_khrylib(golden_dir, use_tc):
     log_std = torch.full((105,), -2.3, device=dev)
     opt_p, opt_v = nn.Adam(pol.params(), 5e-5), nn.Adam(val.params(), 3e-4)
     t = lambda x: torch.tensor(x, device=dev)
-    nn.ppo_update(pol, val, log_std, opt_p, opt_v, t(states), t(actions), t(returns), t(adv), t(exps), 0.2, 3, 40.0, use_tc=use_tc)
+    if use_tc == "c_abi":
+        tr = nn.CPpoTrainer(pol, val, opt_p, opt_v, len(states), 1, torch.device(dev, 0))
+        tr.update_policy(t(states), t(actions), t(returns), t(adv), t(exps), log_std, 0.2, 3, 40.0, torch.zeros(2, device=dev))
+        torch.cuda.synchronize()
+        tr.close()
+        use_tc = True
+    else:
+        nn.ppo_update(pol, val, log_std, opt_p, opt_v, t(states), t(actions), t(returns), t(adv), t(exps), 0.2, 3, 40.0, use_tc=use_tc)
     mean1, v1 = pol.forward(pr).cpu().numpy().astype(np.float64), val.forward(pr).cpu().numpy().astype(np.float64)
     tol_out, tol_par = (0.08, 0.10) if use_tc else (0.02, 0.02)
     for name, ours, ref0, ref1 in (("mean", mean1 - mean0, g["mean0"], g["mean1"]), ("value", v1 - v0, g["v0"], g["v1"])):

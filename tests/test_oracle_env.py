@@ -61,3 +61,24 @@ def test_explicit_residual_force_trace_matches_reference_python(golden_dir):
         np.testing.assert_allclose(info["c_info"], g["c_info"][t], rtol=0, atol=1e-6 * tol, err_msg=f"c_info t={t}")
         assert abs(r - g["reward"][t]) < 1e-6 * tol
         assert info["fail"] == bool(g["fail"][t]) and info["end"] == bool(g["end"][t])
+
+
+def test_obs_v1_no_meta_pd_trace_matches_reference_python(golden_dir):
+    """config/release/uhc_implicit.yml at the env level: obs_v 1 (get_full_obs_v1, humanoid_im.py:323-417: 784 dims = v2 without the shape vector plus
+    the per-body COM blocks), no meta-PD (75-wide actions), the yaml's joint gains -- the reference's own Python over the oracle physics against the C restatement."""
+    g = np.load(os.path.join(golden_dir, "env_sway_implicit_noise.npz"))
+    ex, so = load_expert(golden_dir, "sway")
+    env = O.Env(O.Model(), ex, so, meta_pd=0)
+    env.set_obs_v(1)
+    assert env.action_dim == 75 == g["action"].shape[1] and env.obs_dim == 784 == g["obs"].shape[1]
+    np.testing.assert_allclose(env.reset(), g["obs0"], rtol=0, atol=1e-9)
+    first_fail = int(np.argmax(g["fail"])) if g["fail"].any() else len(g["reward"])
+    assert first_fail >= 20
+    for t in range(len(g["reward"])):
+        obs, r, done, info = env.step(g["action"][t])
+        tol = 1.0 if t < first_fail else 50.0
+        np.testing.assert_allclose(env.torque, g["torque"][t], rtol=1e-7, atol=1e-6 * tol, err_msg=f"torque t={t}")
+        np.testing.assert_allclose(env.d.qpos, g["qpos"][t], rtol=0, atol=1e-7 * tol, err_msg=f"qpos t={t}")
+        np.testing.assert_allclose(obs, g["obs"][t], rtol=0, atol=1e-5 * tol, err_msg=f"obs t={t}")
+        assert abs(r - g["reward"][t]) < 1e-6 * tol
+        assert info["fail"] == bool(g["fail"][t]) and info["end"] == bool(g["end"][t])

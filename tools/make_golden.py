@@ -132,6 +132,63 @@ def gen_ppo():
     print("ppo_small: N", N, "adv mean/std", adv.mean().item(), adv.std().item())
 
 
+def gen_mcp():
+    """PolicyMCP (uhc/models/policy_mcp.py:9-37, the actor of config/release/uhc_implicit.yml) forward and AgentPPO.update_policy with it, in the
+    reference's fp64 torch, at fixture size: 160 -> [128, 96] relu primitives x 4, composer 160 -> [48, 32] -> 4, 75 actions, N = 512 rows, 2 epochs."""
+    import torch
+    from uhc.khrylib.models.mlp import MLP
+    from uhc.models.policy_mcp import PolicyMCP
+    from uhc.khrylib.rl.core.critic import Value
+    from uhc.khrylib.rl.agents.agent_ppo import AgentPPO
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(5)
+    rng = np.random.RandomState(5)
+    S, A, N, hs, P, cdim = 160, 75, 512, [128, 96], 4, [48, 32]
+
+    class Cfg(dict):
+        policy_hsize, policy_htype, fix_std, log_std, num_primitive = hs, "relu", True, -2.3, P
+    pol = PolicyMCP(Cfg(composer_dim=cdim), action_dim=A, state_dim=S)
+    val = Value(MLP(S, hs, "relu"))
+    states = rng.normal(0, 1, (N, S)).clip(-5, 5)
+    st = torch.tensor(states)
+    with torch.no_grad():
+        mean = pol.forward(st).loc.numpy()
+        weight = pol.composer(st).numpy()
+        actions_t = pol.select_action(st, False)
+        logp = pol.get_log_prob(st, actions_t).numpy()
+        values = val(st).numpy()
+    ret = torch.tensor(values + rng.normal(0, 0.5, values.shape))
+    adv = torch.tensor(rng.normal(0, 1, (N, 1)))
+    exps = (rng.uniform(0, 1, N) > 0.1).astype(np.float64)
+    p0 = {k: v.detach().numpy().copy() for k, v in pol.state_dict().items()}
+    v0 = {k: v.detach().numpy().copy() for k, v in val.state_dict().items()}
+    agent = AgentPPO.__new__(AgentPPO)
+    agent.policy_net, agent.value_net = pol, val
+    agent.optimizer_policy = torch.optim.Adam(pol.parameters(), lr=5e-5)
+    agent.optimizer_value = torch.optim.Adam(val.parameters(), lr=3e-4)
+    agent.clip_epsilon, agent.opt_num_epochs, agent.use_mini_batch = 0.2, 2, False
+    agent.policy_grad_clip = [(pol.parameters(), 40)]
+    agent.update_modules = [pol, val]
+    agent.value_opt_niter = 1
+    agent.update_policy(st, actions_t, ret, adv, torch.tensor(exps))
+    with torch.no_grad():
+        mean1 = pol.forward(st[:64]).loc.numpy()
+    out = dict(hsize=np.array(hs), nprim=P, composer_dim=np.array(cdim), states=states.astype(np.float32), actions=actions_t.numpy(), mean=mean, weight=weight, logp=logp, values=values,
+               returns=ret.numpy(), advantages=adv.numpy(), exps=exps, mean_after=mean1, epochs=2)
+    # weights: p0 only for the layers (fp32 is enough to rebuild the fp64 init to 1e-8 relative); after the update the probe output and the head deltas
+    for k, v in p0.items():
+        out["p0." + k] = v.astype(np.float32)
+    for k, v in v0.items():
+        out["v0." + k] = v.astype(np.float32)
+    p1 = pol.state_dict()
+    for k, v in p1.items():
+        out["p1." + k] = v.detach().numpy().astype(np.float32)
+    for k, v in val.state_dict().items():
+        out["v1." + k] = v.detach().numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "mcp_ppo.npz"), **out)
+    print("mcp_ppo: mean abs", np.abs(mean).mean(), "weight row", weight[0])
+
+
 def ppo_real_inputs(N=8192, S=657, A=105, hs=(2048, 1024, 512), seed=11):
     """Seeded inputs of the real-size PPO parity case, regenerated identically by tests/test_gpu_product_paths.py (numpy and torch CPU
     generators only): initial weights (nn.Linear rule, head x0.1 / bias 0), states, actions, returns, advantages, exps."""
@@ -335,12 +392,19 @@ def main():
         from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
         dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
         gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 40, "noise", out_tag="sway_explicit", save_expert=False)
+    if "implicit" in what:       # config/release/uhc_implicit.yml: obs_v 1 (784 dims, per-body COM blocks, no shape), no meta-PD (75-wide actions), joint gains from the yaml
+        cfg = H.make_cfg("uhc_implicit")
+        from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
+        dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
+        gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 40, "noise", out_tag="sway_implicit", save_expert=False)
     if "reactive" in what:
         cfg = H.make_cfg()
         from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
         gen_reactive(cfg, DatasetAMASSSingle(cfg.data_specs, data_mode="train"))
     if "ppo" in what:
         gen_ppo()
+    if "mcp" in what:
+        gen_mcp()
     if "ppo_real" in what:
         gen_ppo_real()
     if "metrics" in what:

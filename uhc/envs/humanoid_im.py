@@ -9,7 +9,7 @@ classic gym-style loop; training uses uhc_b200.agent.BatchedAgent (thousands of 
 import numpy as np
 
 from uhc_b200 import motion_lib
-from uhc_b200.engine import OBS_DIM, Engine
+from uhc_b200.engine import Engine
 from uhc_b200.model import HumanoidModel
 
 
@@ -76,7 +76,7 @@ class HumanoidEnv:
                              rfc_scale=cfg.residual_force_scale, rfc_lim=cfg.residual_force_lim, rfc_rate=0.0 if cfg.rfc_decay else 1.0,
                              body_diff_thresh=cfg.get("body_diff_thresh", 0.5) if mode == "train" else cfg.get("body_diff_thresh_test", 0.5),
                              meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=k,
-                             rfc_mode=cfg.get("residual_force_mode", "implicit"))
+                             rfc_mode=cfg.get("residual_force_mode", "implicit"), obs_v=int(cfg.get("obs_v", 2)))
         self.dt = self.model_tables.dt * 15
         # set_action_spaces (humanoid_im.py:226-255): implicit = 6 residual-force dims, explicit = 9 per body x 24 bodies
         explicit = cfg.get("residual_force_mode", "implicit") == "explicit"
@@ -84,6 +84,7 @@ class HumanoidEnv:
         self.body_vf_dim, self.vf_bodies = 9, list(self.model_tables.SMPL_BONE_ORDER)
         ACT_DIM = self.engine.act_dim
         assert ACT_DIM == self.ndof + self.vf_dim + self.meta_pd_dim
+        OBS_DIM = self.engine.obs_dim
         self.action_dim, self.obs_dim = ACT_DIM, OBS_DIM
         self.action_space, self.observation_space = _Space(ACT_DIM), _Space(OBS_DIM)
         self.body_diffw, self.jpos_diffw = self.model_tables.diffw[1:], self.model_tables.diffw[:, None]

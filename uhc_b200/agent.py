@@ -15,7 +15,7 @@ import time
 import numpy as np
 
 from . import nn
-from .engine import OBS_DIM, Engine
+from .engine import Engine
 
 
 class UhcRolloutBuf(C.Structure):
@@ -69,14 +69,14 @@ class ClipSampler:
 
 
 class RolloutBuffer:
-    def __init__(self, T, E, device, act_dim=105):
+    def __init__(self, T, E, device, act_dim=105, obs_dim=657):
         import torch
         f = dict(device=device, dtype=torch.float32)
         self.T, self.E = T, E
-        self.states = torch.empty(T, E, OBS_DIM, **f)
+        self.states = torch.empty(T, E, obs_dim, **f)
         self.actions = torch.empty(T, E, act_dim, **f)
         self.rewards, self.masks, self.exps, self.logp = (torch.empty(T, E, **f) for _ in range(4))
-        self.last_obs = torch.empty(E, OBS_DIM, **f)
+        self.last_obs = torch.empty(E, obs_dim, **f)
         self.last_alive = torch.empty(E, **f)
         self.fails = torch.zeros(T, E, device=device, dtype=torch.int32)
         self.ep_clip = torch.full((T, E), -1, device=device, dtype=torch.int32)      # clip of the episode that ended at (t, e), -1 = none
@@ -99,7 +99,8 @@ class BatchedAgent:
     def __init__(self, num_envs, clips, shapes=None, device=0, seed=1, precision=32, policy_hsize=(2048, 1024, 512),
                  value_hsize=(2048, 1024, 512), htype="gelu", log_std=-2.3, policy_lr=5e-5, value_lr=3e-4, gamma=0.95, tau=0.95,
                  clip_epsilon=0.2, num_optim_epoch=10, grad_clip=40.0, t_min=5, t_max=300, noise_rate=1.0, rank=0, world=1,
-                 grad_sync=None, model=None, update_tc=True, variants=None, clip_models=None, c_update=True, **env_cfg):
+                 grad_sync=None, model=None, update_tc=True, variants=None, clip_models=None, c_update=True, actor_type="gauss", num_primitive=8,
+                 composer_dim=(300, 200), **env_cfg):
         import torch
         self.torch = torch
         self.dev = torch.device("cuda", device)
@@ -111,10 +112,17 @@ class BatchedAgent:
         self.engine.load_clips(clips, shapes, clip_models)   # clip_models: body-shape variant per clip (the reference rebuilds the robot per clip)
         self.sampler = ClipSampler(self.engine.clip_len, t_min, t_max, seed=seed * 9973 + rank)
         A = self.act_dim = self.engine.act_dim          # env.action_dim (humanoid_im.py:250): 69 + (6 | 216) + (30 if meta_pd)
-        self.policy = nn.MLPNet(OBS_DIM, policy_hsize, A, htype, device=self.dev, head_name="action_mean", seed=seed)
-        self.value = nn.MLPNet(OBS_DIM, value_hsize, 1, htype, device=self.dev, head_name="value_head", seed=seed + 1)
+        D = self.obs_dim = self.engine.obs_dim          # env.obs_dim: 657 (obs v2) or 784 (obs v1)
+        assert actor_type in ("gauss", "mcp"), "actor_type: gauss (PolicyGaussian) | mcp (PolicyMCP)"
+        self.actor_type = actor_type
+        if actor_type == "mcp":        # policy_mcp.py:9-37 (config/release/uhc_implicit.yml): runs through uhc_rollout_mcp / uhc_ppo_trainer_create_mcp only
+            assert c_update and update_tc and bool(env_cfg.get("auto_reset", True)), "the PolicyMCP actor runs on the C-side rollout / update paths"
+            self.policy = nn.MCPNet(D, policy_hsize, A, htype, num_primitive=num_primitive, composer_dim=composer_dim, device=self.dev, seed=seed)
+        else:
+            self.policy = nn.MLPNet(D, policy_hsize, A, htype, device=self.dev, head_name="action_mean", seed=seed)
+        self.value = nn.MLPNet(D, value_hsize, 1, htype, device=self.dev, head_name="value_head", seed=seed + 1)
         self.log_std = torch.full((A,), float(log_std), device=self.dev, dtype=torch.float32)
-        self.running_state = nn.ZFilter(OBS_DIM, clip=5.0, device=self.dev)
+        self.running_state = nn.ZFilter(D, clip=5.0, device=self.dev)
         self.opt_p, self.opt_v = nn.Adam(self.policy.params(), policy_lr, net=self.policy), nn.Adam(self.value.params(), value_lr, net=self.value)
         self.comm = nn.GradComm(world)
         self.gamma, self.tau, self.clip_epsilon, self.epochs, self.grad_clip = gamma, tau, clip_epsilon, num_optim_epoch, grad_clip
@@ -175,13 +183,14 @@ class BatchedAgent:
         if not getattr(self, "_ro_ready", False):
             L.uhc_rollout_last_error.restype = C.c_char_p
             self._ro_ready = True
+        mcp = self.actor_type == "mcp"
         if self.policy._bf16 is None or getattr(self, "_mlp_c", None) is None:
-            self._mlp_c = nn.mlp_struct(self.policy)
+            self._mlp_c = nn.mcp_struct(self.policy) if mcp else nn.mlp_struct(self.policy)
         if getattr(self, "_ro_step", None) != self.global_step:
             L.uhc_rollout_set_step(self.engine.h, C.c_ulonglong(self.global_step))
         bs = buf.c_struct(self.obs)
         st = C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
-        rc = L.uhc_rollout(self.engine.h, C.c_int(T), C.c_int(row0), C.byref(self._mlp_c), C.c_void_p(self.log_std.data_ptr()),
+        rc = (L.uhc_rollout_mcp if mcp else L.uhc_rollout)(self.engine.h, C.c_int(T), C.c_int(row0), C.byref(self._mlp_c), C.c_void_p(self.log_std.data_ptr()),
                            C.c_void_p(self.running_state.stats.data_ptr()), C.c_float(self.running_state.clip), C.c_int(1),
                            C.c_ulonglong(self.seed * 1000003 + self.rank), C.c_float(self.noise_rate), C.byref(bs), C.c_int(int(use_graph)), st)
         if rc != 0:
@@ -196,7 +205,7 @@ class BatchedAgent:
         t = self.torch
         if self.obs is None:
             self.reset_envs()
-        buf = buf or RolloutBuffer(T, self.E, self.dev, self.act_dim)
+        buf = buf or RolloutBuffer(T, self.E, self.dev, self.act_dim, self.obs_dim)
         t0 = time.time()
         len0, ret0 = self.ep_len.clone(), self.ep_ret.clone()
         if c_loop is None:
@@ -268,7 +277,7 @@ class BatchedAgent:
             nn._chk(L.uhc_adv_normalize(nn._p(adv), C.c_long(N), nn._p(mom), None, nn._stream(adv)))
             inv_count.copy_(1.0 / t.clamp(cnt, min=1.0))
         else:
-            D = OBS_DIM
+            D = self.obs_dim
             zs = self.running_state.stats
             if getattr(self, "_z_sync", None) is None:                               # fresh agent: every rank starts from empty statistics
                 self._z_sync = t.zeros_like(zs)                                      # additive form of the statistics every rank agreed on last

@@ -38,7 +38,7 @@ UHC_DEV bool env_record_valid(const EngineView<Real> &ev, int env) {
 template <class Real, class ObsT>
 UHC_DEV void env_step_invalid(const EngineView<Real> &ev, ObsT *obs, ObsT *reward, ObsT *cinfo_out, int *fail_out, int *end_out, ObsT *percent_out) {
     LANES_BEGIN
-    if (obs) for (int i = lane; i < OBS_DIM; i += 32) obs[i] = (ObsT)0;
+    if (obs) for (int i = lane; i < ev.cfg.obs_dim; i += 32) obs[i] = (ObsT)0;
     if (cinfo_out && lane < 5) cinfo_out[lane] = (ObsT)0;
     if (lane == 0) {
         if (reward) *reward = (ObsT)0;

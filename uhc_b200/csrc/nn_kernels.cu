@@ -294,6 +294,44 @@ __global__ void k_zfilter_apply(const float *__restrict__ X, float *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
+// ---- PolicyMCP (uhc/models/policy_mcp.py:28-36): action_mean = sum_k softmax(composer(x))_k * primitive_k(x).  One warp per row.
+// xall = [P][M][A] primitive outputs, c = [M][P] composer outputs (after its last activation), weight = softmax(c) kept for the backward pass.
+constexpr int MCP_MAX_PRIM = 16;
+__global__ void __launch_bounds__(256) k_mcp_combine(const float *__restrict__ xall, const float *__restrict__ c, float *__restrict__ weight, float *__restrict__ mean,
+                                                     int M, int A, int P) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float w[MCP_MAX_PRIM]; float mx = -3.0e38f, den = 0.f;
+    for (int k = 0; k < P; k++) { w[k] = c[(size_t)row * P + k]; mx = fmaxf(mx, w[k]); }
+    for (int k = 0; k < P; k++) { w[k] = expf(w[k] - mx); den += w[k]; }
+    const float inv = 1.0f / den;
+    for (int k = 0; k < P; k++) { w[k] *= inv; if (weight && lane == 0) weight[(size_t)row * P + k] = w[k]; }
+    for (int a = lane; a < A; a += 32) {
+        float s = 0.f;
+        for (int k = 0; k < P; k++) s += w[k] * xall[((size_t)k * M + row) * A + a];
+        mean[(size_t)row * A + a] = s;
+    }
+}
+// d xall_k = w_k dmean ; d w_k = sum_a dmean_a xall_k,a ; softmax backward d c_k = w_k (d w_k - sum_j w_j d w_j)
+__global__ void __launch_bounds__(256) k_mcp_backward(const float *__restrict__ xall, const float *__restrict__ weight, const float *__restrict__ dmean,
+                                                      float *__restrict__ dxall, float *__restrict__ dc, int M, int A, int P) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    float w[MCP_MAX_PRIM], dw[MCP_MAX_PRIM];
+    for (int k = 0; k < P; k++) { w[k] = weight[(size_t)row * P + k]; dw[k] = 0.f; }
+    for (int a = lane; a < A; a += 32) {
+        const float g = dmean[(size_t)row * A + a];
+        for (int k = 0; k < P; k++) {
+            const size_t i = ((size_t)k * M + row) * A + a;
+            dw[k] += g * xall[i];
+            dxall[i] = w[k] * g;
+        }
+    }
+    float dot = 0.f;
+    for (int k = 0; k < P; k++) { for (int o = 16; o; o >>= 1) dw[k] += __shfl_xor_sync(0xffffffffu, dw[k], o); dot += w[k] * dw[k]; }
+    if (lane == 0) for (int k = 0; k < P; k++) dc[(size_t)row * P + k] = w[k] * (dw[k] - dot);
+}
+
 extern "C" {
 const char *uhc_nn_last_error(void) { return g_nn_err.c_str(); }
 
@@ -365,6 +403,14 @@ int uhc_adv_moments(const float *adv, long n, double *out2, void *stream) {
 int uhc_adv_normalize(float *adv, long n, const double *mom2_dev, const double *ntotal_dev, void *stream) {
     k_normalize<<<592, 256, 0, (cudaStream_t)stream>>>(adv, (size_t)n, mom2_dev, ntotal_dev); CKN(cudaGetLastError());
     return 0;
+}
+int uhc_mcp_combine(const float *xall, const float *c, float *weight_or_null, float *mean, int M, int A, int P, void *stream) {
+    if (P < 1 || P > MCP_MAX_PRIM) { g_nn_err = "uhc_mcp_combine: 1..16 primitives"; return -2; }
+    k_mcp_combine<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(xall, c, weight_or_null, mean, M, A, P); CKN(cudaGetLastError()); return 0;
+}
+int uhc_mcp_backward(const float *xall, const float *weight, const float *dmean, float *dxall, float *dc, int M, int A, int P, void *stream) {
+    if (P < 1 || P > MCP_MAX_PRIM) { g_nn_err = "uhc_mcp_backward: 1..16 primitives"; return -2; }
+    k_mcp_backward<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(xall, weight, dmean, dxall, dc, M, A, P); CKN(cudaGetLastError()); return 0;
 }
 int uhc_zfilter_workspace_doubles(int D) { return ZF_CHUNKS * D * 2; }
 int uhc_zfilter(const float *x, float *y, int M, int D, double *stats, float clip, int update, void *stream) {

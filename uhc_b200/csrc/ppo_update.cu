@@ -111,8 +111,12 @@ struct NetBuf { void *acts[9] = {nullptr}; float *z[8] = {nullptr}; float *out =
 
 struct UhcPpoTrainer {
     int device = 0; long cap = 0; int cap_envs = 0;
-    UhcNetDesc pol{}, val{};
-    NetBuf pb, vb;
+    std::vector<UhcNetDesc> pnets;     // the policy: one MLP (nprim = 0) or nprim primitives followed by the composer (PolicyMCP); all share pnets[0]'s flat storage
+    std::vector<NetBuf> pbufs;
+    int nprim = 0;
+    float *xall = nullptr, *mixw = nullptr, *dxall = nullptr, *dcomp = nullptr, *mean = nullptr;   // PolicyMCP: primitive outputs [P][M][A], softmax weights [M][P], their gradients, the mixture mean
+    UhcNetDesc val{};
+    NetBuf vb;
     void *xb = nullptr, *xT = nullptr, *lb = nullptr;                   // bf16 states [M][Dp], transpose [D][Mp], last states [E][Dp]
     void *dz = nullptr, *dzT = nullptr, *hT = nullptr, *WT = nullptr;   // shared backward scratch (the nets run back to back on one stream)
     float *dh = nullptr, *dmean = nullptr, *dv = nullptr, *fixed = nullptr, *adv = nullptr, *ret = nullptr, *last_v = nullptr, *inv_count = nullptr;
@@ -138,12 +142,13 @@ template <class T> int dalloc(UhcPpoTrainer *t, T **p, size_t bytes, bool zero) 
     if (zero) CKP(cudaMemset(*p, 0, bytes ? bytes : 16));
     return 0;
 }
-int alloc_net(UhcPpoTrainer *t, const UhcNetDesc &n, NetBuf &nb, long cap) {
+int alloc_net(UhcPpoTrainer *t, const UhcNetDesc &n, NetBuf &nb, long cap, bool own_out) {
     for (int i = 0; i < n.nlayers - 1; i++) {
         if (dalloc(t, &nb.acts[i + 1], (size_t)cap * pad64(n.dims[i + 1]) * 2, true)) return -1;    // bf16, zero padded once (the GEMMs write the first N columns)
         if (dalloc(t, &nb.z[i], (size_t)cap * n.dims[i + 1] * 4, false)) return -1;
     }
-    return dalloc(t, &nb.out, (size_t)cap * n.dims[n.nlayers] * 4, false);
+    if (n.head_act != UHC_ACT_NONE && dalloc(t, &nb.z[n.nlayers - 1], (size_t)cap * n.dims[n.nlayers] * 4, false)) return -1;   // activated output layer (MCP composer)
+    return own_out ? dalloc(t, &nb.out, (size_t)cap * n.dims[n.nlayers] * 4, false) : 0;
 }
 // forward keeping what the backward pass needs (bf16 activations, fp32 pre-activations); train = false: plain inference chain on `rows` rows
 int net_forward(const UhcNetDesc &n, NetBuf &nb, const void *x, long rows, bool train, cudaStream_t st) {
@@ -151,8 +156,9 @@ int net_forward(const UhcNetDesc &n, NetBuf &nb, const void *x, long rows, bool 
     for (int i = 0; i < n.nlayers; i++) {
         const bool last = i == n.nlayers - 1;
         const int N = n.dims[i + 1];
+        const int act = last ? n.head_act : n.act;
         CKU(uhc_linear_forward_tc_train(h, n.W_bf16[i], n.flat + n.b_off[i], last ? nullptr : nb.acts[i + 1], last ? nb.out : nullptr,
-                                        (last || !train) ? nullptr : nb.z[i], (int)rows, N, n.kp[i], last ? 0 : (int)pad64(N), last ? UHC_ACT_NONE : n.act, st), "forward GEMM");
+                                        (!train || act == UHC_ACT_NONE) ? nullptr : nb.z[i], (int)rows, N, n.kp[i], last ? 0 : (int)pad64(N), act, st), "forward GEMM");
         h = nb.acts[i + 1];
     }
     return 0;
@@ -164,7 +170,8 @@ int net_backward(UhcPpoTrainer *t, const UhcNetDesc &n, NetBuf &nb, const float 
     for (int i = n.nlayers - 1; i >= 0; --i) {
         const int N = n.dims[i + 1], K = n.dims[i];
         const long Np = pad64(N);
-        CKU(uhc_dact_bf16(dh, i < n.nlayers - 1 ? nb.z[i] : nullptr, t->dz, t->dzT, n.gfull + n.b_off[i], (int)M, N, (int)Np, (int)Mp, n.act, st), "activation backward");
+        const int act = i < n.nlayers - 1 ? n.act : n.head_act;
+        CKU(uhc_dact_bf16(dh, act != UHC_ACT_NONE ? nb.z[i] : nullptr, t->dz, t->dzT, n.gfull + n.b_off[i], (int)M, N, (int)Np, (int)Mp, act, st), "activation backward");
         const void *hT = t->xT;
         if (i > 0) { CKU(uhc_transpose_bf16(nb.acts[i], t->hT, (int)M, K, (int)pad64(K), (int)Mp, st), "transpose h"); hT = t->hT; }
         CKU(uhc_linear_forward_tc(t->dzT, hT, nullptr, nullptr, n.gfull + n.w_off[i], N, K, (int)Mp, 0, UHC_ACT_NONE, st), "dW GEMM");           // dW = dz^T h
@@ -179,6 +186,23 @@ int net_backward(UhcPpoTrainer *t, const UhcNetDesc &n, NetBuf &nb, const float 
 int refresh_bf16(const UhcNetDesc &n, cudaStream_t st) {
     for (int i = 0; i < n.nlayers; i++) CKU(uhc_f32_to_bf16_padded(n.flat + n.w_off[i], n.W_bf16[i], n.dims[i + 1], n.dims[i], n.kp[i], st), "bf16 weight refresh");
     return 0;
+}
+// the policy's mean for every row: the single MLP's output, or the PolicyMCP mixture (policy_mcp.py:28-36)
+int policy_forward(UhcPpoTrainer *t, long M, const float **mean_out, cudaStream_t st) {
+    const int P = t->nprim, A = t->pnets[0].dims[t->pnets[0].nlayers];
+    for (int k = 0; k < P; k++) t->pbufs[k].out = t->xall + (size_t)k * M * A;       // [P][M][A], contiguous for this M
+    for (size_t j = 0; j < t->pnets.size(); j++) if (net_forward(t->pnets[j], t->pbufs[j], t->xb, M, true, st)) return -1;
+    if (P == 0) { *mean_out = t->pbufs[0].out; return 0; }
+    CKU(uhc_mcp_combine(t->xall, t->pbufs[P].out, t->mixw, t->mean, (int)M, A, P, st), "mixture head");
+    *mean_out = t->mean;
+    return 0;
+}
+int policy_backward(UhcPpoTrainer *t, const float *dmean, long M, cudaStream_t st) {
+    const int P = t->nprim, A = t->pnets[0].dims[t->pnets[0].nlayers];
+    if (P == 0) return net_backward(t, t->pnets[0], t->pbufs[0], dmean, M, st);
+    CKU(uhc_mcp_backward(t->xall, t->mixw, dmean, t->dxall, t->dcomp, (int)M, A, P, st), "mixture head backward");
+    for (int k = 0; k < P; k++) if (net_backward(t, t->pnets[k], t->pbufs[k], t->dxall + (size_t)k * M * A, M, st)) return -1;
+    return net_backward(t, t->pnets[P], t->pbufs[P], t->dcomp, M, st);
 }
 int start_all_reduce(UhcPpoTrainer *t, void *comm, float *buf, size_t n, cudaEvent_t done, cudaStream_t st) {
     AllReduceFn ar = nccl_all_reduce();
@@ -200,26 +224,89 @@ int start_all_reduce(UhcPpoTrainer *t, void *comm, float *buf, size_t n, cudaEve
 }
 }  // namespace
 
+// the PPO epochs on t->xb / t->xT / t->adv / t->ret: per epoch one value step then one clipped-surrogate policy step (agent_ppo.py:46-51), see the file header
+// for the order of the collectives.  stats_tail: the first value all-reduce carries the statistics planes (uhc_ppo_update with world > 1).
+static int run_epochs(UhcPpoTrainer *t, const float *actions, const float *exps, const float *log_std, long M, const UhcPpoCfg *cfg, int *adam_step_policy,
+                      int *adam_step_value, int *policy_steps_done, double *zfilter_stats, double *zfilter_sync, void *comm, int world, bool stats_tail,
+                      bool value_forward_done, float *losses_out, cudaStream_t st) {
+    const UhcNetDesc &pol = t->pnets[0], &val = t->val;
+    const int D = pol.dims[0], A = pol.dims[pol.nlayers];
+    const int nd = 4 + 1 + 2 * D;
+    float *tail = val.gfull + val.nflat;
+    // ---- old-policy mean: the fixed log-probabilities and epoch 0's policy forward (same weights)
+    const float *pmean = nullptr;
+    if (policy_forward(t, M, &pmean, st)) return -1;
+    CKU(uhc_gaussian_logprob(pmean, log_std, actions, t->fixed, (int)M, A, st), "fixed log-probabilities");
+
+    for (int ep = 0; ep < cfg->epochs; ++ep) {
+        if ((ep > 0 || !value_forward_done) && net_forward(val, t->vb, t->xb, M, true, st)) return -1;
+        CKP(cudaMemsetAsync(losses_out, 0, 2 * sizeof(float), st));
+        CKU(uhc_value_grad_n(t->vb.out, t->ret, t->dv, losses_out + 1, (int)M, M * world, st), "value gradient");
+        if (net_backward(t, val, t->vb, t->dv, M, st)) return -1;
+        const bool with_tail = stats_tail && ep == 0;
+        if (comm && start_all_reduce(t, comm, val.gfull, (size_t)val.nflat + (with_tail ? (size_t)PLANES * nd : 0), t->ev_v, st)) return -1;
+        if (with_tail) {    // the global statistics are needed before the first policy gradient
+            CKP(cudaStreamWaitEvent(st, t->ev_v, 0));
+            ++g_launches; k_stats_join<<<(nd + 255) / 256, 256, 0, st>>>(tail, D, t->mom, t->ntot, t->inv_count, zfilter_sync); CKP(cudaGetLastError());
+            CKU(uhc_adv_normalize(t->adv, M, t->mom, t->ntot, st), "advantage normalisation (global)");
+            ++g_launches; k_zfilter_from_sums<<<(2 * D + 1 + 255) / 256, 256, 0, st>>>(zfilter_sync, D, zfilter_stats); CKP(cudaGetLastError());
+        }
+        if (ep > 0 && policy_forward(t, M, &pmean, st)) return -1;
+        CKU(uhc_ppo_policy_grad_dev(pmean, log_std, actions, t->adv, t->fixed, exps, cfg->clip_eps, t->inv_count, t->dmean, losses_out, (int)M, A, st), "policy gradient");
+        if (policy_backward(t, t->dmean, M, st)) return -1;
+        if (comm && start_all_reduce(t, comm, pol.gfull, (size_t)pol.nflat, t->ev_p, st)) return -1;
+        // value step first, as the reference; the policy collective is still in flight
+        if (comm) CKP(cudaStreamWaitEvent(st, t->ev_v, 0));
+        *adam_step_value += 1;
+        CKU(uhc_adam_step(val.flat, val.gfull, val.adam_m, val.adam_v, val.nflat, val.lr, 0.9f, 0.999f, 1e-8f, *adam_step_value, nullptr, 0.f, st), "value Adam");
+        if (refresh_bf16(val, st)) return -1;
+        if (comm) CKP(cudaStreamWaitEvent(st, t->ev_p, 0));
+        const bool clip = cfg->grad_clip > 0.f && (!cfg->clip_first_step_only || *policy_steps_done == 0);
+        if (clip) {
+            CKP(cudaMemsetAsync(t->sq, 0, sizeof(double), st));
+            CKU(uhc_sqsum(pol.gfull, pol.nflat, t->sq, st), "gradient norm");
+        }
+        *adam_step_policy += 1; *policy_steps_done += 1;
+        CKU(uhc_adam_step(pol.flat, pol.gfull, pol.adam_m, pol.adam_v, pol.nflat, pol.lr, 0.9f, 0.999f, 1e-8f, *adam_step_policy, clip ? t->sq : nullptr, clip ? cfg->grad_clip : 0.f, st), "policy Adam");
+        for (const UhcNetDesc &n : t->pnets) if (refresh_bf16(n, st)) return -1;
+    }
+    return 0;
+}
+
 extern "C" {
 const char *uhc_ppo_last_error(void) { return g_ppo_err.c_str(); }
 
-int uhc_ppo_trainer_create(const UhcNetDesc *policy, const UhcNetDesc *value, long max_rows, int max_envs, int device, UhcPpoTrainer **out) {
-    if (!policy || !value || !out || max_rows <= 0 || max_envs <= 0) { g_ppo_err = "uhc_ppo_trainer_create: bad argument"; return -2; }
-    if (check_net(*policy, "policy") || check_net(*value, "value")) return -2;
-    if (policy->dims[0] != value->dims[0] || value->dims[value->nlayers] != 1) { g_ppo_err = "uhc_ppo_trainer_create: the nets must share the input width and the value head must be scalar"; return -2; }
+static int trainer_create(const UhcNetDesc *pnets, int nprim, const UhcNetDesc *value, long max_rows, int max_envs, int device, UhcPpoTrainer **out) {
+    const int npn = nprim > 0 ? nprim + 1 : 1;
+    if (!pnets || !value || !out || max_rows <= 0 || max_envs <= 0 || nprim < 0 || nprim > 8) { g_ppo_err = "uhc_ppo_trainer_create: bad argument"; return -2; }
+    for (int j = 0; j < npn; j++) if (check_net(pnets[j], "policy")) return -2;
+    if (check_net(*value, "value")) return -2;
+    const int D = pnets[0].dims[0], A = pnets[0].dims[pnets[0].nlayers];
+    if (D != value->dims[0] || value->dims[value->nlayers] != 1) { g_ppo_err = "uhc_ppo_trainer_create: the nets must share the input width and the value head must be scalar"; return -2; }
+    for (int j = 0; j < npn; j++) {
+        const UhcNetDesc &n = pnets[j];
+        if (n.dims[0] != D || n.flat != pnets[0].flat || n.gfull != pnets[0].gfull || n.nflat != pnets[0].nflat) { g_ppo_err = "uhc_ppo_trainer_create: the policy's nets must share one flat parameter / gradient tensor and the observation"; return -2; }
+        if (nprim > 0 && j < nprim && n.dims[n.nlayers] != A) { g_ppo_err = "uhc_ppo_trainer_create: the primitives must share the action width"; return -2; }
+        if (nprim > 0 && j == nprim && n.dims[n.nlayers] != nprim) { g_ppo_err = "uhc_ppo_trainer_create: the composer's output width must be the number of primitives"; return -2; }
+    }
     CKP(cudaSetDevice(device));
     UhcPpoTrainer *t = new UhcPpoTrainer();
-    t->device = device; t->cap = max_rows; t->cap_envs = max_envs; t->pol = *policy; t->val = *value;
+    t->device = device; t->cap = max_rows; t->cap_envs = max_envs; t->val = *value; t->nprim = nprim;
+    t->pnets.assign(pnets, pnets + npn); t->pbufs.resize(npn);
     const long cap = max_rows, capp = pad64(max_rows);
-    const int D = policy->dims[0];
     long maxN = 1, maxKh = 1;       // widest layer output; widest hidden input (layers i > 0)
-    for (const UhcNetDesc *n : {policy, value})
-        for (int i = 0; i < n->nlayers; i++) { if (n->dims[i + 1] > maxN) maxN = n->dims[i + 1]; if (i > 0 && n->dims[i] > maxKh) maxKh = n->dims[i]; }
-    int rc = alloc_net(t, t->pol, t->pb, cap) || alloc_net(t, t->val, t->vb, cap);
+    auto widths = [&](const UhcNetDesc &n) { for (int i = 0; i < n.nlayers; i++) { if (n.dims[i + 1] > maxN) maxN = n.dims[i + 1]; if (i > 0 && n.dims[i] > maxKh) maxKh = n.dims[i]; } };
+    for (const UhcNetDesc &n : t->pnets) widths(n);
+    widths(*value);
+    int rc = 0;
+    for (int j = 0; j < npn && !rc; j++) rc = alloc_net(t, t->pnets[j], t->pbufs[j], cap, !(nprim > 0 && j < nprim));
+    rc = rc || alloc_net(t, t->val, t->vb, cap, true);
+    if (nprim > 0) rc = rc || dalloc(t, &t->xall, (size_t)nprim * cap * A * 4, false) || dalloc(t, &t->dxall, (size_t)nprim * cap * A * 4, false) ||
+                         dalloc(t, &t->mixw, (size_t)cap * nprim * 4, false) || dalloc(t, &t->dcomp, (size_t)cap * nprim * 4, false) || dalloc(t, &t->mean, (size_t)cap * A * 4, false);
     rc = rc || dalloc(t, &t->xb, (size_t)cap * pad64(D) * 2, true) || dalloc(t, &t->xT, (size_t)D * capp * 2, true) || dalloc(t, &t->lb, (size_t)max_envs * pad64(D) * 2, true);
     rc = rc || dalloc(t, &t->dz, (size_t)cap * pad64(maxN) * 2, true) || dalloc(t, &t->dzT, (size_t)maxN * capp * 2, true) || dalloc(t, &t->hT, (size_t)maxKh * capp * 2, true) ||
          dalloc(t, &t->WT, (size_t)maxKh * pad64(maxN) * 2, true) || dalloc(t, &t->dh, (size_t)cap * maxKh * 4, false);
-    rc = rc || dalloc(t, &t->dmean, (size_t)cap * policy->dims[policy->nlayers] * 4, false) || dalloc(t, &t->dv, (size_t)cap * 4, false) || dalloc(t, &t->fixed, (size_t)cap * 4, false) ||
+    rc = rc || dalloc(t, &t->dmean, (size_t)cap * A * 4, false) || dalloc(t, &t->dv, (size_t)cap * 4, false) || dalloc(t, &t->fixed, (size_t)cap * 4, false) ||
          dalloc(t, &t->adv, (size_t)cap * 4, false) || dalloc(t, &t->ret, (size_t)cap * 4, false) || dalloc(t, &t->last_v, (size_t)max_envs * 4, false) ||
          dalloc(t, &t->inv_count, 4, true) || dalloc(t, &t->mom, 16, true) || dalloc(t, &t->cnt, 8, true) || dalloc(t, &t->ntot, 8, true) || dalloc(t, &t->sq, 8, true);
     if (rc) { uhc_ppo_trainer_destroy(t); return -1; }
@@ -227,6 +314,13 @@ int uhc_ppo_trainer_create(const UhcNetDesc *policy, const UhcNetDesc *value, lo
     CKP(cudaEventCreateWithFlags(&t->ev_ready, cudaEventDisableTiming)); CKP(cudaEventCreateWithFlags(&t->ev_v, cudaEventDisableTiming)); CKP(cudaEventCreateWithFlags(&t->ev_p, cudaEventDisableTiming));
     *out = t;
     return 0;
+}
+int uhc_ppo_trainer_create(const UhcNetDesc *policy, const UhcNetDesc *value, long max_rows, int max_envs, int device, UhcPpoTrainer **out) {
+    return trainer_create(policy, 0, value, max_rows, max_envs, device, out);
+}
+int uhc_ppo_trainer_create_mcp(const UhcNetDesc *policy_nets, int nprim, const UhcNetDesc *value, long max_rows, int max_envs, int device, UhcPpoTrainer **out) {
+    if (nprim < 1) { g_ppo_err = "uhc_ppo_trainer_create_mcp: nprim >= 1"; return -2; }
+    return trainer_create(policy_nets, nprim, value, max_rows, max_envs, device, out);
 }
 
 void uhc_ppo_trainer_destroy(UhcPpoTrainer *t) {
@@ -269,7 +363,7 @@ int uhc_ppo_update(UhcPpoTrainer *t, const float *states, const float *last_stat
     cudaStream_t st = (cudaStream_t)stream;
     g_launches = 0;
     struct Tally { UhcPpoTrainer *t; ~Tally() { t->launches += g_launches; } } tally{t};
-    const UhcNetDesc &pol = t->pol, &val = t->val;
+    const UhcNetDesc &pol = t->pnets[0], &val = t->val;      // pnets[0] carries the policy's flat parameter / gradient / Adam tensors
     const int D = pol.dims[0], A = pol.dims[pol.nlayers];
     const long Dp = pad64(D), Mp = pad64(M);
     void *comm = world > 1 ? nccl_comm : nullptr;
@@ -295,42 +389,31 @@ int uhc_ppo_update(UhcPpoTrainer *t, const float *states, const float *last_stat
         CKP(cudaMemsetAsync(tail, 0, (size_t)val.gtail * sizeof(float), st));
         ++g_launches; k_stats_pack<<<(nd + 255) / 256, 256, 0, st>>>(t->mom, (double)M, t->cnt, zfilter_stats, zfilter_sync, D, tail); CKP(cudaGetLastError());
     }
-    // ---- old-policy mean: the fixed log-probabilities and epoch 0's policy forward (same weights)
-    if (net_forward(pol, t->pb, t->xb, M, true, st)) return -1;
-    CKU(uhc_gaussian_logprob(t->pb.out, log_std, actions, t->fixed, (int)M, A, st), "fixed log-probabilities");
+    return run_epochs(t, actions, exps, log_std, M, cfg, adam_step_policy, adam_step_value, policy_steps_done, zfilter_stats, zfilter_sync, comm, world, comm != nullptr,
+                      true, losses_out, st);
+}
 
-    for (int ep = 0; ep < cfg->epochs; ++ep) {
-        if (ep > 0 && net_forward(val, t->vb, t->xb, M, true, st)) return -1;
-        CKP(cudaMemsetAsync(losses_out, 0, 2 * sizeof(float), st));
-        CKU(uhc_value_grad_n(t->vb.out, t->ret, t->dv, losses_out + 1, (int)M, M * world, st), "value gradient");
-        if (net_backward(t, val, t->vb, t->dv, M, st)) return -1;
-        const bool with_tail = comm && ep == 0;
-        if (comm && start_all_reduce(t, comm, val.gfull, (size_t)val.nflat + (with_tail ? (size_t)PLANES * nd : 0), t->ev_v, st)) return -1;
-        if (with_tail) {    // the global statistics are needed before the first policy gradient
-            CKP(cudaStreamWaitEvent(st, t->ev_v, 0));
-            ++g_launches; k_stats_join<<<(nd + 255) / 256, 256, 0, st>>>(tail, D, t->mom, t->ntot, t->inv_count, zfilter_sync); CKP(cudaGetLastError());
-            CKU(uhc_adv_normalize(t->adv, M, t->mom, t->ntot, st), "advantage normalisation (global)");
-            ++g_launches; k_zfilter_from_sums<<<(2 * D + 1 + 255) / 256, 256, 0, st>>>(zfilter_sync, D, zfilter_stats); CKP(cudaGetLastError());
-        }
-        if (ep > 0 && net_forward(pol, t->pb, t->xb, M, true, st)) return -1;
-        CKU(uhc_ppo_policy_grad_dev(t->pb.out, log_std, actions, t->adv, t->fixed, exps, cfg->clip_eps, t->inv_count, t->dmean, losses_out, (int)M, A, st), "policy gradient");
-        if (net_backward(t, pol, t->pb, t->dmean, M, st)) return -1;
-        if (comm && start_all_reduce(t, comm, pol.gfull, (size_t)pol.nflat, t->ev_p, st)) return -1;
-        // value step first, as the reference; the policy collective is still in flight
-        if (comm) CKP(cudaStreamWaitEvent(st, t->ev_v, 0));
-        *adam_step_value += 1;
-        CKU(uhc_adam_step(val.flat, val.gfull, val.adam_m, val.adam_v, val.nflat, val.lr, 0.9f, 0.999f, 1e-8f, *adam_step_value, nullptr, 0.f, st), "value Adam");
-        if (refresh_bf16(val, st)) return -1;
-        if (comm) CKP(cudaStreamWaitEvent(st, t->ev_p, 0));
-        const bool clip = cfg->grad_clip > 0.f && (!cfg->clip_first_step_only || *policy_steps_done == 0);
-        if (clip) {
-            CKP(cudaMemsetAsync(t->sq, 0, sizeof(double), st));
-            CKU(uhc_sqsum(pol.gfull, pol.nflat, t->sq, st), "gradient norm");
-        }
-        *adam_step_policy += 1; *policy_steps_done += 1;
-        CKU(uhc_adam_step(pol.flat, pol.gfull, pol.adam_m, pol.adam_v, pol.nflat, pol.lr, 0.9f, 0.999f, 1e-8f, *adam_step_policy, clip ? t->sq : nullptr, clip ? cfg->grad_clip : 0.f, st), "policy Adam");
-        if (refresh_bf16(pol, st)) return -1;
-    }
-    return 0;
+/* AgentPPO.update_policy (agent_ppo.py:16-51) alone: the epochs on caller-provided returns / (already normalised) advantages. */
+int uhc_ppo_update_policy(UhcPpoTrainer *t, const float *states, const float *actions, const float *returns, const float *advantages, const float *exps,
+                          const float *log_std, long M, const UhcPpoCfg *cfg, int *adam_step_policy, int *adam_step_value, int *policy_steps_done,
+                          void *nccl_comm, int world, float *losses_out, void *stream) {
+    if (!t || !states || !actions || !returns || !advantages || !exps || !log_std || !cfg || !adam_step_policy || !adam_step_value || !policy_steps_done || !losses_out ||
+        M <= 0 || world < 1) { g_ppo_err = "uhc_ppo_update_policy: bad argument"; return -2; }
+    if (M > t->cap) { g_ppo_err = "uhc_ppo_update_policy: the batch exceeds the trainer's capacity"; return -2; }
+    if (world > 1 && !nccl_comm) { g_ppo_err = "uhc_ppo_update_policy: world > 1 needs an ncclComm_t"; return -2; }
+    CKP(cudaSetDevice(t->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    g_launches = 0;
+    struct Tally { UhcPpoTrainer *t; ~Tally() { t->launches += g_launches; } } tally{t};
+    const int D = t->pnets[0].dims[0];
+    CKU(uhc_f32_to_bf16_padded(states, t->xb, (int)M, D, (int)pad64(D), st), "bf16 states");
+    CKU(uhc_transpose_bf16(t->xb, t->xT, (int)M, D, (int)pad64(D), (int)pad64(M), st), "transpose states");
+    CKP(cudaMemcpyAsync(t->adv, advantages, (size_t)M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CKP(cudaMemcpyAsync(t->ret, returns, (size_t)M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CKP(cudaMemsetAsync(t->cnt, 0, sizeof(double), st));
+    ++g_launches; k_count_selected<<<296, 256, 0, st>>>(exps, (size_t)M, t->cnt); CKP(cudaGetLastError());
+    ++g_launches; k_inv_count<<<1, 1, 0, st>>>(t->cnt, t->inv_count); CKP(cudaGetLastError());      // (a sharded caller passes world = 1 per shard or pre-scales exps)
+    return run_epochs(t, actions, exps, log_std, M, cfg, adam_step_policy, adam_step_value, policy_steps_done, nullptr, nullptr, world > 1 ? nccl_comm : nullptr, world, false,
+                      false, losses_out, st);
 }
 }  // extern "C"

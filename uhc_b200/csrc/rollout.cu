@@ -100,14 +100,19 @@ __global__ void k_rollout_post(const int *__restrict__ fail, const int *__restri
     if (e == 0) *step_ptr += 1ull;   // ordered after every reader of this step's counter by the stream / graph dependencies
 }
 
+// the policy of a rollout: one MLP (PolicyGaussian, nprim = 0: nets[0]) or a PolicyMCP mixture (nets[0 .. nprim-1] = primitives, nets[nprim] = composer)
+struct Policy { int nprim; int pad; UhcMlp nets[UHC_MCP_MAX_PRIM + 1]; };
 struct GraphKey {
-    int T, row0, update_filter; float noise_rate, zclip; unsigned long long seed; UhcMlp mlp; UhcRolloutBuf buf; const float *log_std; double *zstats;
+    int T, row0, update_filter; float noise_rate, zclip; unsigned long long seed; Policy pol; UhcRolloutBuf buf; const float *log_std; double *zstats;
     bool operator==(const GraphKey &o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 struct RolloutCtx {
     UhcEngine *eng = nullptr; int E = 0, device = 0;
     unsigned long long *d_step = nullptr;
-    void *acts[9] = {nullptr}; int act_ld[9] = {0}; float *d_mean = nullptr; int mean_cap = 0;
+    struct NetScratch { void *acts[9] = {nullptr}; int ld[9] = {0}; };
+    NetScratch ns[UHC_MCP_MAX_PRIM + 1];     // bf16 activations per net of the policy; ns[0].acts[0] (the normalised observation) feeds every net
+    float *d_mean = nullptr; int mean_cap = 0;
+    float *d_xall = nullptr, *d_comp = nullptr; size_t xall_cap = 0;   // PolicyMCP: primitive outputs [P][E][A], composer outputs [E][P]
     double *d_zws = nullptr; int zws_d = 0;
     unsigned char *d_mean_action = nullptr; float *d_cinfo = nullptr, *d_pct = nullptr; int *d_fail = nullptr, *d_end = nullptr;
     std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;
@@ -124,59 +129,85 @@ RolloutCtx *ctx_of(UhcEngine *e) {
 }
 int pad64(int n) { return (n + 63) / 64 * 64; }
 
-int ensure_scratch(RolloutCtx *c, const UhcMlp *m) {
+int ensure_scratch(RolloutCtx *c, const Policy *pol) {
     const size_t E = c->E;
     if (!c->d_step) { CKR(cudaMalloc((void **)&c->d_step, sizeof(unsigned long long))); CKR(cudaMemset(c->d_step, 0, sizeof(unsigned long long))); }
     if (!c->d_mean_action) {
         CKR(cudaMalloc((void **)&c->d_mean_action, E)); CKR(cudaMalloc((void **)&c->d_cinfo, E * 5 * 4)); CKR(cudaMalloc((void **)&c->d_pct, E * 4));
         CKR(cudaMalloc((void **)&c->d_fail, E * 4)); CKR(cudaMalloc((void **)&c->d_end, E * 4));
     }
-    if (m->nlayers < 1 || m->nlayers > 8) { g_ro_err = "UhcMlp: 1..8 layers"; return -2; }
-    if (c->zws_d < m->dims[0]) {
-        if (c->d_zws) cudaFree(c->d_zws);
-        CKR(cudaMalloc((void **)&c->d_zws, (size_t)uhc_zfilter_workspace_doubles(m->dims[0]) * sizeof(double))); c->zws_d = m->dims[0];
-        for (auto &g : c->graphs) cudaGraphExecDestroy(g.second);
-        c->graphs.clear();
-    }
-    for (int i = 0; i < m->nlayers; i++) {   // bf16 activations, K padded to 64 and zero filled once (the GEMMs write the first N columns only)
-        const int ld = pad64(m->dims[i]);
-        if (m->kp[i] != ld) { g_ro_err = "UhcMlp: kp[i] must be dims[i] rounded up to 64"; return -2; }
-        if (c->act_ld[i] != ld) {
-            if (c->acts[i]) cudaFree(c->acts[i]);
-            CKR(cudaMalloc(&c->acts[i], E * ld * 2)); CKR(cudaMemset(c->acts[i], 0, E * ld * 2));
-            c->act_ld[i] = ld;
-            for (auto &g : c->graphs) cudaGraphExecDestroy(g.second);
-            c->graphs.clear();
+    const int P = pol->nprim, nnets = P > 0 ? P + 1 : 1;
+    if (P < 0 || P > UHC_MCP_MAX_PRIM) { g_ro_err = "UhcMcp: 1..8 primitives"; return -2; }
+    const UhcMlp *m0 = &pol->nets[0];
+    auto drop_graphs = [&]() { for (auto &g : c->graphs) cudaGraphExecDestroy(g.second); c->graphs.clear(); };
+    for (int j = 0; j < nnets; j++) {
+        const UhcMlp *m = &pol->nets[j];
+        if (m->nlayers < 1 || m->nlayers > 8) { g_ro_err = "UhcMlp: 1..8 layers"; return -2; }
+        if (m->dims[0] != m0->dims[0]) { g_ro_err = "UhcMcp: every net reads the same observation"; return -2; }
+        if (j < P && m->dims[m->nlayers] != m0->dims[m0->nlayers]) { g_ro_err = "UhcMcp: the primitives must share the action width"; return -2; }
+        if (P > 0 && j == P && m->dims[m->nlayers] != P) { g_ro_err = "UhcMcp: the composer's output width must be the number of primitives"; return -2; }
+        for (int i = 0; i < m->nlayers; i++) {   // bf16 activations, K padded to 64 and zero filled once (the GEMMs write the first N columns only)
+            const int ld = pad64(m->dims[i]);
+            if (m->kp[i] != ld) { g_ro_err = "UhcMlp: kp[i] must be dims[i] rounded up to 64"; return -2; }
+            if (i == 0 && j > 0) continue;       // the input is shared
+            if (c->ns[j].ld[i] != ld) {
+                if (c->ns[j].acts[i]) cudaFree(c->ns[j].acts[i]);
+                CKR(cudaMalloc(&c->ns[j].acts[i], E * ld * 2)); CKR(cudaMemset(c->ns[j].acts[i], 0, E * ld * 2));
+                c->ns[j].ld[i] = ld;
+                drop_graphs();
+            }
         }
     }
-    const int A = m->dims[m->nlayers];
-    if (c->mean_cap < A) { if (c->d_mean) cudaFree(c->d_mean); CKR(cudaMalloc((void **)&c->d_mean, E * A * 4)); c->mean_cap = A; }
+    if (c->zws_d < m0->dims[0]) {
+        if (c->d_zws) cudaFree(c->d_zws);
+        CKR(cudaMalloc((void **)&c->d_zws, (size_t)uhc_zfilter_workspace_doubles(m0->dims[0]) * sizeof(double))); c->zws_d = m0->dims[0];
+        drop_graphs();
+    }
+    const int A = m0->dims[m0->nlayers];
+    if (c->mean_cap < A) { if (c->d_mean) cudaFree(c->d_mean); CKR(cudaMalloc((void **)&c->d_mean, E * A * 4)); c->mean_cap = A; drop_graphs(); }
+    if (P > 0 && c->xall_cap < (size_t)P * E * A) {
+        if (c->d_xall) cudaFree(c->d_xall);
+        if (c->d_comp) cudaFree(c->d_comp);
+        CKR(cudaMalloc((void **)&c->d_xall, (size_t)P * E * A * 4)); CKR(cudaMalloc((void **)&c->d_comp, E * UHC_MCP_MAX_PRIM * 4)); c->xall_cap = (size_t)P * E * A;
+        drop_graphs();
+    }
     return 0;
 }
 
-// obs -> (state row, bf16 copy) -> MLP -> mean (ctx scratch).  Returns the number of kernels enqueued (or < 0).
-int enqueue_policy(RolloutCtx *c, const float *obs, const UhcMlp *m, double *zstats, float zclip, int update_filter, float *state_out, cudaStream_t st) {
-    const int E = c->E, D = m->dims[0];
+// obs -> (state row, bf16 copy) -> MLP (or the PolicyMCP mixture: primitives, composer + softmax, weighted sum) -> mean (ctx scratch).
+// Returns the number of kernels enqueued (or < 0).
+int enqueue_policy(RolloutCtx *c, const float *obs, const Policy *pol, double *zstats, float zclip, int update_filter, float *state_out, cudaStream_t st) {
+    const UhcMlp *m0 = &pol->nets[0];
+    const int E = c->E, D = m0->dims[0], P = pol->nprim, A = m0->dims[m0->nlayers];
     int n = 0;
     if (update_filter) { CKC(uhc_zfilter_ws(obs, nullptr, E, D, zstats, zclip, 1, c->d_zws, st), "zfilter update"); n += 3; }
-    k_zfilter_apply_bf16<<<1184, 256, 0, st>>>(obs, state_out, (unsigned short *)c->acts[0], E, D, m->kp[0], zstats, zclip);
+    k_zfilter_apply_bf16<<<1184, 256, 0, st>>>(obs, state_out, (unsigned short *)c->ns[0].acts[0], E, D, m0->kp[0], zstats, zclip);
     CKR(cudaGetLastError()); n++;
-    for (int i = 0; i < m->nlayers; i++) {
-        const bool last = i == m->nlayers - 1;
-        CKC(uhc_linear_forward_tc(c->acts[i], m->W_bf16[i], m->bias[i], last ? nullptr : c->acts[i + 1], last ? c->d_mean : nullptr, E, m->dims[i + 1], m->kp[i],
-                                  last ? 0 : c->act_ld[i + 1], last ? UHC_ACT_NONE : m->act, st), "policy GEMM");
-        n++;
+    for (int j = 0; j < (P > 0 ? P + 1 : 1); j++) {
+        const UhcMlp *m = &pol->nets[j];
+        const bool composer = P > 0 && j == P;
+        float *out = P == 0 ? c->d_mean : (composer ? c->d_comp : c->d_xall + (size_t)j * E * A);
+        for (int i = 0; i < m->nlayers; i++) {
+            const bool last = i == m->nlayers - 1;
+            const void *in = i == 0 ? c->ns[0].acts[0] : c->ns[j].acts[i];
+            // the composer is a plain MLP (mlp.py:24-27): its last affine layer is followed by the activation too, then the softmax (policy_mcp.py:26)
+            CKC(uhc_linear_forward_tc(in, m->W_bf16[i], m->bias[i], last ? nullptr : c->ns[j].acts[i + 1], last ? out : nullptr, E, m->dims[i + 1], m->kp[i],
+                                      last ? 0 : c->ns[j].ld[i + 1], (last && !composer) ? UHC_ACT_NONE : m->act, st), "policy GEMM");
+            n++;
+        }
     }
+    if (P > 0) { CKC(uhc_mcp_combine(c->d_xall, c->d_comp, nullptr, c->d_mean, E, A, P, st), "mixture head"); n++; }
     return n;
 }
 
-int enqueue_step(RolloutCtx *c, int row, const UhcMlp *m, const float *log_std, double *zstats, float zclip, int update_filter, unsigned long long seed,
+int enqueue_step(RolloutCtx *c, int row, const Policy *pol, const float *log_std, double *zstats, float zclip, int update_filter, unsigned long long seed,
                  float noise_rate, const UhcRolloutBuf *b, cudaStream_t st) {
+    const UhcMlp *m = &pol->nets[0];
     const size_t E = c->E; const int D = m->dims[0], A = m->dims[m->nlayers];
     float *state_row = b->states + (size_t)row * E * D, *act_row = b->actions + (size_t)row * E * A;
     float *rew_row = b->rewards + (size_t)row * E, *mask_row = b->masks + (size_t)row * E, *exps_row = b->exps + (size_t)row * E;
     float *logp_row = b->logp ? b->logp + (size_t)row * E : nullptr; int *fail_row = b->fails ? b->fails + (size_t)row * E : nullptr;
-    int n = enqueue_policy(c, b->obs_cur, m, zstats, zclip, update_filter, state_row, st);
+    int n = enqueue_policy(c, b->obs_cur, pol, zstats, zclip, update_filter, state_row, st);
     if (n < 0) return n;
     const bool mixed = noise_rate < 1.0f;
     if (mixed) { k_mean_action<<<(c->E + 255) / 256, 256, 0, st>>>(c->d_mean_action, exps_row, c->E, 1.0f - noise_rate, seed, c->d_step); CKR(cudaGetLastError()); n++; }
@@ -219,36 +250,45 @@ int uhc_rollout_get_step(UhcEngine *e, unsigned long long *step) {
     return 0;
 }
 
-int uhc_policy_forward(UhcEngine *e, const float *obs_dev, const UhcMlp *mlp, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
-                       unsigned long long seed, const unsigned char *mean_action_or_null, float *state_out_or_null, float *action_out, float *logp_out_or_null,
-                       void *stream) {
-    if (!e || !obs_dev || !mlp || !log_std || !zfilter_stats || !action_out) { g_ro_err = "uhc_policy_forward: bad argument"; return -2; }
-    if (mlp->nlayers >= 1 && mlp->nlayers <= 8 && mlp->dims[mlp->nlayers] != uhc_engine_act_dim(e)) { g_ro_err = "uhc_policy_forward: the policy's output width is not the engine's action dim"; return -2; }
+static int make_policy(Policy *pol, const UhcMlp *mlp, const UhcMcp *mcp, UhcEngine *e, const char *who) {
+    memset(pol, 0, sizeof *pol);
+    if (mcp) {
+        if (mcp->nprim < 1 || mcp->nprim > UHC_MCP_MAX_PRIM) { g_ro_err = std::string(who) + ": 1..8 primitives"; return -2; }
+        pol->nprim = mcp->nprim;
+        for (int k = 0; k < mcp->nprim; k++) pol->nets[k] = mcp->prim[k];
+        pol->nets[mcp->nprim] = mcp->composer;
+    } else pol->nets[0] = *mlp;
+    const UhcMlp *m = &pol->nets[0];
+    if (m->nlayers >= 1 && m->nlayers <= 8 && (m->dims[m->nlayers] != uhc_engine_act_dim(e) || m->dims[0] != uhc_engine_obs_dim(e))) {
+        g_ro_err = std::string(who) + ": the policy's input / output widths are not the engine's obs / action dims"; return -2;
+    }
+    return 0;
+}
+static int policy_forward_impl(UhcEngine *e, const float *obs_dev, const Policy *pol, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
+                               unsigned long long seed, const unsigned char *mean_action_or_null, float *state_out_or_null, float *action_out, float *logp_out_or_null,
+                               void *stream) {
     RolloutCtx *c = ctx_of(e);
-    int rc = ensure_scratch(c, mlp);
+    int rc = ensure_scratch(c, pol);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (enqueue_policy(c, obs_dev, mlp, zfilter_stats, zclip, update_filter, state_out_or_null, st) < 0) return -1;
-    k_gauss_sample_dev<<<(c->E + 7) / 8, 256, 0, st>>>(c->d_mean, log_std, mean_action_or_null, action_out, logp_out_or_null, c->E, mlp->dims[mlp->nlayers], seed, c->d_step);
+    if (enqueue_policy(c, obs_dev, pol, zfilter_stats, zclip, update_filter, state_out_or_null, st) < 0) return -1;
+    const UhcMlp *m = &pol->nets[0];
+    k_gauss_sample_dev<<<(c->E + 7) / 8, 256, 0, st>>>(c->d_mean, log_std, mean_action_or_null, action_out, logp_out_or_null, c->E, m->dims[m->nlayers], seed, c->d_step);
     CKR(cudaGetLastError());
     return 0;
 }
-
-int uhc_rollout(UhcEngine *e, int T, int row0, const UhcMlp *mlp, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
-                unsigned long long seed, float noise_rate, const UhcRolloutBuf *buf, int use_graph, void *stream) {
-    if (!e || !mlp || !log_std || !zfilter_stats || !buf || T <= 0 || row0 < 0 || row0 + T > buf->T_cap) { g_ro_err = "uhc_rollout: bad argument"; return -2; }
-    if (!buf->states || !buf->actions || !buf->rewards || !buf->masks || !buf->exps || !buf->obs_cur) { g_ro_err = "uhc_rollout: missing buffer"; return -2; }
-    if (mlp->nlayers >= 1 && mlp->nlayers <= 8 && mlp->dims[mlp->nlayers] != uhc_engine_act_dim(e)) { g_ro_err = "uhc_rollout: the policy's output width is not the engine's action dim"; return -2; }
+static int rollout_impl(UhcEngine *e, int T, int row0, const Policy *pol, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
+                        unsigned long long seed, float noise_rate, const UhcRolloutBuf *buf, int use_graph, void *stream) {
     RolloutCtx *c = ctx_of(e);
-    int rc = ensure_scratch(c, mlp);
+    int rc = ensure_scratch(c, pol);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (!use_graph) {
-        for (int k = 0; k < T; k++) { const int n = enqueue_step(c, row0 + k, mlp, log_std, zfilter_stats, zclip, update_filter, seed, noise_rate, buf, st); if (n < 0) return -1; c->launches_per_step = n; }
+        for (int k = 0; k < T; k++) { const int n = enqueue_step(c, row0 + k, pol, log_std, zfilter_stats, zclip, update_filter, seed, noise_rate, buf, st); if (n < 0) return -1; c->launches_per_step = n; }
         return 0;
     }
     GraphKey key; memset(&key, 0, sizeof key);
-    key.T = T; key.row0 = row0; key.update_filter = update_filter; key.noise_rate = noise_rate; key.zclip = zclip; key.seed = seed; key.mlp = *mlp; key.buf = *buf;
+    key.T = T; key.row0 = row0; key.update_filter = update_filter; key.noise_rate = noise_rate; key.zclip = zclip; key.seed = seed; key.pol = *pol; key.buf = *buf;
     key.log_std = log_std; key.zstats = zfilter_stats;
     cudaGraphExec_t exec = nullptr;
     for (auto &g : c->graphs) if (g.first == key) { exec = g.second; break; }
@@ -258,7 +298,7 @@ int uhc_rollout(UhcEngine *e, int T, int row0, const UhcMlp *mlp, const float *l
         cudaGraph_t graph = nullptr;
         CKR(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         int n = 0;
-        for (int k = 0; k < T && n >= 0; k++) n = enqueue_step(c, row0 + k, mlp, log_std, zfilter_stats, zclip, update_filter, seed, noise_rate, buf, cs);
+        for (int k = 0; k < T && n >= 0; k++) n = enqueue_step(c, row0 + k, pol, log_std, zfilter_stats, zclip, update_filter, seed, noise_rate, buf, cs);
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         cudaStreamDestroy(cs);
         if (n < 0) { if (graph) cudaGraphDestroy(graph); return -1; }
@@ -271,6 +311,36 @@ int uhc_rollout(UhcEngine *e, int T, int row0, const UhcMlp *mlp, const float *l
     }
     CKR(cudaGraphLaunch(exec, st));
     return 0;
+}
+
+int uhc_policy_forward(UhcEngine *e, const float *obs_dev, const UhcMlp *mlp, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
+                       unsigned long long seed, const unsigned char *mean_action_or_null, float *state_out_or_null, float *action_out, float *logp_out_or_null,
+                       void *stream) {
+    if (!e || !obs_dev || !mlp || !log_std || !zfilter_stats || !action_out) { g_ro_err = "uhc_policy_forward: bad argument"; return -2; }
+    Policy pol; if (make_policy(&pol, mlp, nullptr, e, "uhc_policy_forward")) return -2;
+    return policy_forward_impl(e, obs_dev, &pol, log_std, zfilter_stats, zclip, update_filter, seed, mean_action_or_null, state_out_or_null, action_out, logp_out_or_null, stream);
+}
+int uhc_policy_forward_mcp(UhcEngine *e, const float *obs_dev, const UhcMcp *mcp, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
+                           unsigned long long seed, const unsigned char *mean_action_or_null, float *state_out_or_null, float *action_out, float *logp_out_or_null,
+                           void *stream) {
+    if (!e || !obs_dev || !mcp || !log_std || !zfilter_stats || !action_out) { g_ro_err = "uhc_policy_forward_mcp: bad argument"; return -2; }
+    Policy pol; if (make_policy(&pol, nullptr, mcp, e, "uhc_policy_forward_mcp")) return -2;
+    return policy_forward_impl(e, obs_dev, &pol, log_std, zfilter_stats, zclip, update_filter, seed, mean_action_or_null, state_out_or_null, action_out, logp_out_or_null, stream);
+}
+
+int uhc_rollout(UhcEngine *e, int T, int row0, const UhcMlp *mlp, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
+                unsigned long long seed, float noise_rate, const UhcRolloutBuf *buf, int use_graph, void *stream) {
+    if (!e || !mlp || !log_std || !zfilter_stats || !buf || T <= 0 || row0 < 0 || row0 + T > buf->T_cap) { g_ro_err = "uhc_rollout: bad argument"; return -2; }
+    if (!buf->states || !buf->actions || !buf->rewards || !buf->masks || !buf->exps || !buf->obs_cur) { g_ro_err = "uhc_rollout: missing buffer"; return -2; }
+    Policy pol; if (make_policy(&pol, mlp, nullptr, e, "uhc_rollout")) return -2;
+    return rollout_impl(e, T, row0, &pol, log_std, zfilter_stats, zclip, update_filter, seed, noise_rate, buf, use_graph, stream);
+}
+int uhc_rollout_mcp(UhcEngine *e, int T, int row0, const UhcMcp *mcp, const float *log_std, double *zfilter_stats, float zclip, int update_filter,
+                    unsigned long long seed, float noise_rate, const UhcRolloutBuf *buf, int use_graph, void *stream) {
+    if (!e || !mcp || !log_std || !zfilter_stats || !buf || T <= 0 || row0 < 0 || row0 + T > buf->T_cap) { g_ro_err = "uhc_rollout_mcp: bad argument"; return -2; }
+    if (!buf->states || !buf->actions || !buf->rewards || !buf->masks || !buf->exps || !buf->obs_cur) { g_ro_err = "uhc_rollout_mcp: missing buffer"; return -2; }
+    Policy pol; if (make_policy(&pol, nullptr, mcp, e, "uhc_rollout_mcp")) return -2;
+    return rollout_impl(e, T, row0, &pol, log_std, zfilter_stats, zclip, update_filter, seed, noise_rate, buf, use_graph, stream);
 }
 
 // events around the env-step kernel of rows 0 .. nrows-1 (recorded on the launching stream, also inside graph replays); 0 disables.
@@ -304,8 +374,8 @@ void uhc_rollout_release(UhcEngine *e) {   // called by the binding before uhc_e
         for (auto &g : c->graphs) cudaGraphExecDestroy(g.second);
         for (cudaEvent_t ev : c->ev0) cudaEventDestroy(ev);
         for (cudaEvent_t ev : c->ev1) cudaEventDestroy(ev);
-        for (void *p : c->acts) if (p) cudaFree(p);
-        for (void *p : {(void *)c->d_zws, (void *)c->d_step, (void *)c->d_mean, (void *)c->d_mean_action, (void *)c->d_cinfo, (void *)c->d_pct, (void *)c->d_fail, (void *)c->d_end}) if (p) cudaFree(p);
+        for (auto &nsj : c->ns) for (void *p : nsj.acts) if (p) cudaFree(p);
+        for (void *p : {(void *)c->d_xall, (void *)c->d_comp, (void *)c->d_zws, (void *)c->d_step, (void *)c->d_mean, (void *)c->d_mean_action, (void *)c->d_cinfo, (void *)c->d_pct, (void *)c->d_fail, (void *)c->d_end}) if (p) cudaFree(p);
         delete c; g_ctx.erase(g_ctx.begin() + i); return;
     }
 }

@@ -73,9 +73,10 @@ constexpr int ST_Q = 0, ST_V = 76, ST_AW = 152, ST_C = 228, ST_IB = 304, ST_S = 
               ST_XPOS = 996, ST_XQUAT = 1068, ST_XIPOS = 1164, ST_BQUAT = 1236, ST_PBQUAT = 1332, ST_SIZE = 1428;
 // per-env integer record
 constexpr int SI_CUR_T = 0, SI_CLIP = 1, SI_START = 2, SI_LEN = 3, SI_EPISODE = 4, SI_FLAGS = 5, SI_NEWTON = 6, SI_NCON = 7, SI_SIZE = 8;
-// expert frame record (Real units): qpos 76 | qvel 75 | wbpos 72 | wbquat 96 | bquat 96 | bangvel 72 | ee_wpos 15 | com 3 | pad
+// expert frame record (Real units): qpos 76 | qvel 75 | wbpos 72 | wbquat 96 | bquat 96 | bangvel 72 | ee_wpos 15 | body_com 72 (com = its first 3) | pad
 constexpr int EX_QPOS = 0, EX_QVEL = 76, EX_WBPOS = 151, EX_WBQUAT = 223, EX_BQUAT = 319, EX_BANGVEL = 415, EX_EE = 487,
-              EX_COM = 502, EX_SIZE = 508;
+              EX_COM = 502, EX_BCOM = 502, EX_SIZE = 576;
+constexpr int OBS_DIM_V1 = 784, MAX_OBS_DIM = 784;   // get_full_obs_v1: v2 without the 17 shape dims plus two 72-wide per-body COM blocks
 
 template <class Real>
 struct Model {
@@ -104,6 +105,7 @@ struct EnvCfg {
     // residual-force mode (cfg.residual_force_mode, humanoid_im.py:231-243): 0 = implicit root wrench (6 action dims), 1 = explicit per-body contact
     // point / force / torque (9 dims x 24 bodies).  Action layout: [NU joint targets | vf_dim residual-force dims | 30 meta-PD scales if meta_pd]
     int rfc_mode, vf_dim, act_dim;
+    int obs_v, obs_dim;                           // cfg.obs_v: 2 = get_full_obs_v2 (657), 1 = get_full_obs_v1 (784; config/release/uhc_implicit.yml)
     signed char vf_slot[NB];                      // explicit: residual-force slot of body b (vf_bodies = SMPL_BONE_ORDER_NAMES, humanoid_im.py:236-237)
 };
 constexpr int VF_BODY_DIM = 9, MAX_ACT_DIM = NU + VF_BODY_DIM * NB + 30;
@@ -1313,7 +1315,8 @@ UHC_DEVNI void world_quat(const Model<Real> &m, const Real *qfk, Work<Real> &w) 
     LANES_END
 }
 
-// observation v2 (humanoid_im.py:419-503, obs_coord "root"); ex1 = expert frame at cur_t + 1
+// observation v2 (humanoid_im.py:419-503, obs_coord "root") and, with cfg.obs_v == 1, v1 (:323-417: the same blocks, then the per-body centres of
+// mass relative to the root and their difference to the expert's body_com, the quaternion blocks after those, no shape vector); ex1 = expert frame at cur_t + 1
 template <class Real, class OutT>
 UHC_DEVNI void obs_v2(const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *ex1, const Real *shape_obs, OutT *obs) {
     Real crq[4], hq[4], hqi[4], trq[4], dh[4], ci[4], dq[4], Rq[9], Rc[9];
@@ -1352,16 +1355,29 @@ UHC_DEVNI void obs_v2(const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *
         for (int k = 0; k < 3; k++) r[k] = ex1[EX_WBPOS + 3 * b + k] - w.xpos[b][k];
         mtv(Rc, r, t);
         for (int k = 0; k < 3; k++) obs[376 + 24 * k + b] = (OutT)t[k];
+        const bool v1 = cfg.obs_v == 1;
+        const int oq = v1 ? 592 : 448;
+        if (v1) {
+            for (int k = 0; k < 3; k++) r[k] = w.xipos[b][k] - w.q[k];
+            mtv(Rc, r, t);
+            for (int k = 0; k < 3; k++) obs[448 + 24 * k + b] = (OutT)t[k];
+            for (int k = 0; k < 3; k++) r[k] = ex1[EX_BCOM + 3 * b + k] - w.xipos[b][k];
+            mtv(Rc, r, t);
+            for (int k = 0; k < 3; k++) obs[520 + 24 * k + b] = (OutT)t[k];
+        }
         const bool use_t = (w.xquat[0][0] == 0);
         const Real *cq = use_t ? ex1 + EX_WBQUAT + 4 * b : w.xquat[b];
         Real o1[4], iq[4], o2[4];
         qmul(hqi, cq, o1);
-        const Real nn = rsqrt_(cq[0] * cq[0] + cq[1] * cq[1] + cq[2] * cq[2] + cq[3] * cq[3]);  // inverse_batch: conj / |q|
-        iq[0] = cq[0] * nn; iq[1] = -cq[1] * nn; iq[2] = -cq[2] * nn; iq[3] = -cq[3] * nn;
+        if (v1) qinv(cq, iq);                                                                  // v1: quaternion_inverse = conj / |q|^2 (:411)
+        else {
+            const Real nn = rsqrt_(cq[0] * cq[0] + cq[1] * cq[1] + cq[2] * cq[2] + cq[3] * cq[3]);  // v2: inverse_batch = conj / |q|
+            iq[0] = cq[0] * nn; iq[1] = -cq[1] * nn; iq[2] = -cq[2] * nn; iq[3] = -cq[3] * nn;
+        }
         qmul(iq, ex1 + EX_WBQUAT + 4 * b, o2);
-        for (int k = 0; k < 4; k++) { obs[448 + 4 * b + k] = (OutT)o1[k]; obs[544 + 4 * b + k] = (OutT)o2[k]; }
+        for (int k = 0; k < 4; k++) { obs[oq + 4 * b + k] = (OutT)o1[k]; obs[oq + 96 + 4 * b + k] = (OutT)o2[k]; }
     }
-    if (lane < 17) obs[640 + lane] = (OutT)shape_obs[lane];
+    if (cfg.obs_v != 1 && lane < 17) obs[640 + lane] = (OutT)shape_obs[lane];
     LANES_END
 }
 

@@ -55,14 +55,14 @@ k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict
     if (valid && (threadIdx.x & 31) == 0) atomicAdd(&s_nvalid, 1);
     __syncthreads();
     if (!valid) {   // no work (grid tail) or a stale / never-reset env record: flagged outputs, and the warp is not counted in the substep barrier
-        if (env >= 0) env_step_invalid<Real, float>(ev, obs ? obs + (size_t)env * OBS_DIM : nullptr, rew ? rew + env : nullptr, cinfo ? cinfo + (size_t)env * 5 : nullptr,
+        if (env >= 0) env_step_invalid<Real, float>(ev, obs ? obs + (size_t)env * ev.cfg.obs_dim : nullptr, rew ? rew + env : nullptr, cinfo ? cinfo + (size_t)env * 5 : nullptr,
                                                     fail ? fail + env : nullptr, end ? end + env : nullptr, pct ? pct + env : nullptr);
         return;
     }
     Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
     if ((threadIdx.x & 31) == 0) w.sync_threads = 32 * s_nvalid;
     state_mbar_init(w);            // mbarrier of this warp's bulk-async (TMA) state load
-    env_step_warp<Real, float>(ev, env, w, act + (size_t)env * ev.cfg.act_dim, obs ? obs + (size_t)env * OBS_DIM : nullptr, rew ? rew + env : nullptr,
+    env_step_warp<Real, float>(ev, env, w, act + (size_t)env * ev.cfg.act_dim, obs ? obs + (size_t)env * ev.cfg.obs_dim : nullptr, rew ? rew + env : nullptr,
                                cinfo ? cinfo + (size_t)env * 5 : nullptr, fail ? fail + env : nullptr, end ? end + env : nullptr,
                                pct ? pct + env : nullptr, torque ? torque + (size_t)env * NSUB * NU : nullptr);
 }
@@ -95,7 +95,7 @@ k_env_reset(EngineView<Real> ev, int n, const int *__restrict__ ids, const int *
         for (int k = lane; k < NQ; k += 32) qo[k] = (Real)qpos[(size_t)i * NQ + k];
         for (int k = lane; k < NV; k += 32) vo[k] = qvel ? (Real)qvel[(size_t)i * NV + k] : Real(0);
         __syncwarp(); }
-    env_reset_warp<Real, float>(ev, env, w, clip[i], start[i], len[i], qo, vo, obs ? obs + (size_t)env * OBS_DIM : nullptr);
+    env_reset_warp<Real, float>(ev, env, w, clip[i], start[i], len[i], qo, vo, obs ? obs + (size_t)env * ev.cfg.obs_dim : nullptr);
 }
 
 // parity / evaluation hook: gather q, v, xpos, bquat (+ the integer record) of the listed envs into one staging array
@@ -158,6 +158,7 @@ template <class Real> static void fill_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) 
     c.reactive_v = h->reactive_v; c.reactive_rate = (Real)h->reactive_rate;
     c.rfc_mode = h->rfc_mode == 1 ? 1 : 0; c.vf_dim = c.rfc_mode ? VF_BODY_DIM * NB : 6; c.act_dim = NU + c.vf_dim + (h->meta_pd ? 2 * NSUB : 0);
     for (int b = 0; b < NB; b++) c.vf_slot[b] = (signed char)((h->vf_slot[b] >= 0 && h->vf_slot[b] < NB) ? h->vf_slot[b] : b);
+    c.obs_v = h->obs_v == 1 ? 1 : 2; c.obs_dim = c.obs_v == 1 ? OBS_DIM_V1 : OBS_DIM;
 }
 template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, const UhcModelHost *m, const UhcEnvCfg *cfg) {
     Model<Real> &M = ev.model;
@@ -220,7 +221,7 @@ int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_e
         CK(cudaFuncSetAttribute(k_env_reset<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<double, EPB_D>()));
     }
     const size_t E = num_envs;
-    CK(cudaMalloc((void **)&e->d_act, E * MAX_ACT_DIM * 4)); CK(cudaMalloc((void **)&e->d_obs, E * OBS_DIM * 4)); CK(cudaMalloc((void **)&e->d_rew, E * 4));
+    CK(cudaMalloc((void **)&e->d_act, E * MAX_ACT_DIM * 4)); CK(cudaMalloc((void **)&e->d_obs, E * MAX_OBS_DIM * 4)); CK(cudaMalloc((void **)&e->d_rew, E * 4));
     CK(cudaMalloc((void **)&e->d_cinfo, E * 5 * 4)); CK(cudaMalloc((void **)&e->d_pct, E * 4)); CK(cudaMalloc((void **)&e->d_fail, E * 4)); CK(cudaMalloc((void **)&e->d_end, E * 4));
     for (void *p : {(void *)e->d_act, (void *)e->d_obs, (void *)e->d_rew, (void *)e->d_cinfo, (void *)e->d_pct, (void *)e->d_fail, (void *)e->d_end}) e->allocs.push_back(p);
     *out = e;
@@ -401,7 +402,7 @@ int uhc_env_step_host(UhcEngine *e, const float *actions_host, float *obs_host, 
     CK(cudaMemcpyAsync(e->d_act, actions_host, E * (size_t)uhc_engine_act_dim(e) * 4, cudaMemcpyHostToDevice, 0));
     int rc = uhc_env_step(e, e->d_act, e->d_obs, e->d_rew, e->d_cinfo, e->d_fail, e->d_end, e->d_pct, nullptr, nullptr);
     if (rc) return rc;
-    if (obs_host) CK(cudaMemcpyAsync(obs_host, e->d_obs, E * OBS_DIM * 4, cudaMemcpyDeviceToHost, 0));
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, e->d_obs, E * (size_t)uhc_engine_obs_dim(e) * 4, cudaMemcpyDeviceToHost, 0));
     if (reward_host) CK(cudaMemcpyAsync(reward_host, e->d_rew, E * 4, cudaMemcpyDeviceToHost, 0));
     if (cinfo_host) CK(cudaMemcpyAsync(cinfo_host, e->d_cinfo, E * 5 * 4, cudaMemcpyDeviceToHost, 0));
     if (fail_host) CK(cudaMemcpyAsync(fail_host, e->d_fail, E * 4, cudaMemcpyDeviceToHost, 0));
@@ -499,6 +500,7 @@ int uhc_engine_counters(UhcEngine *e, int *out4) {
 
 const int *uhc_episode_log_dev(const UhcEngine *e) { return e ? (e->precision == 32 ? e->evf.ep_log : e->evd.ep_log) : nullptr; }
 int uhc_num_envs(const UhcEngine *e) { return e ? e->E : -1; }
+int uhc_engine_obs_dim(const UhcEngine *e) { return e ? (e->precision == 32 ? e->evf.cfg.obs_dim : e->evd.cfg.obs_dim) : -1; }
 int uhc_engine_act_dim(const UhcEngine *e) { return e ? (e->precision == 32 ? e->evf.cfg.act_dim : e->evd.cfg.act_dim) : -1; }
 int uhc_kernel_launches(const UhcEngine *e) { return e ? e->launches : -1; }
 

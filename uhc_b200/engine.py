@@ -12,7 +12,7 @@ from .model import HumanoidModel, UhcModelHost
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.environ.get("UHC_B200_SO") or os.path.join(_HERE, "libuhc_b200.so")   # override: scratch builds of kernel variants
-OBS_DIM, ACT_DIM, NQ, NV, NU, EX_SIZE = 657, 105, 76, 75, 69, 508
+OBS_DIM, ACT_DIM, NQ, NV, NU, EX_SIZE = 657, 105, 76, 75, 69, 576
 EXPERT_FIELDS = (("qpos", 76), ("qvel", 75), ("wbpos", 72), ("wbquat", 96), ("bquat", 96), ("bangvel", 72), ("ee_wpos", 15), ("com", 3))
 
 
@@ -21,13 +21,13 @@ class UhcEnvCfg(C.Structure):
                 ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
                 ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double),
                 ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reactive_v", C.c_int), ("reset_seed", C.c_ulonglong),
-                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24)]
+                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24), ("obs_v", C.c_int)]
 
 
 def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0, rfc_lim=100.0, rfc_rate=1.0, body_diff_thresh=0.5,
              meta_pd=1, env_episode_len=100000, trail_steps=0, w=(0.3, 0.1, 0.45, 0.1, 0.05), k=(2.0, 0.005, 5.0, 100.0, 1.0),
              newton_max_iter=None, newton_tol=None, auto_reset=0, t_min=5, t_max=300, reset_seed=1, reactive_v=0, reactive_rate=0.3,
-             rfc_mode="implicit", vf_slot=None):
+             rfc_mode="implicit", vf_slot=None, obs_v=2):
     """Defaults = config/release/uhc_implicit_shape.yml + copycat_config.py defaults of the reference."""
     c = UhcEnvCfg()
     c.base_rot = (C.c_double * 4)(*base_rot)
@@ -41,7 +41,14 @@ def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0,
     # cfg.residual_force_mode: "implicit" (6 action dims: root wrench) | "explicit" (24 x 9: contact point, force, torque per body, mj_applyFT)
     c.rfc_mode = 1 if rfc_mode in (1, "explicit") else 0
     c.vf_slot = (C.c_int * 24)(*(list(vf_slot) if vf_slot is not None else range(24)))
+    assert int(obs_v) in (1, 2), "obs_v: 1 (get_full_obs_v1) or 2 (get_full_obs_v2)"
+    c.obs_v = int(obs_v)
     return c
+
+
+def obs_dim_of(cfg):
+    """env.obs_dim: 657 (obs v2 with the shape vector) or 784 (obs v1)"""
+    return 784 if cfg.obs_v == 1 else OBS_DIM
 
 
 def act_dim_of(cfg):
@@ -50,13 +57,18 @@ def act_dim_of(cfg):
 
 
 def pack_expert(ex):
-    """expert dict -> [T][508] frame records (layout: include/uhc_b200.h UHC_EX_SIZE)."""
+    """expert dict -> [T][576] frame records (layout: include/uhc_b200.h UHC_EX_SIZE).  body_com (72, obs v1) starts where com (its first 3
+    values: the root body's centre of mass) sits; an expert dict without body_com (obs v2 only) leaves the rest zero."""
     T = len(ex["qpos"])
     out = np.zeros((T, EX_SIZE))
     o = 0
     for k, n in EXPERT_FIELDS:
         out[:, o:o + n] = np.asarray(ex[k], dtype=np.float64).reshape(T, n)
         o += n
+    if "body_com" in ex:
+        bc = np.asarray(ex["body_com"], dtype=np.float64).reshape(T, 72)
+        assert np.abs(bc[:, :3] - out[:, 502:505]).max() < 1e-9, "expert['com'] must be the root body's body_com"
+        out[:, 502:574] = bc
     return out
 
 
@@ -101,13 +113,13 @@ class Engine:
             cfg["vf_slot"] = self.model.vf_slot()                 # slot order of the reference: SMPL_BONE_ORDER_NAMES
         self._cfg_kw = dict(cfg)
         self._cfg = make_cfg(precision, **cfg)
-        self.act_dim = act_dim_of(self._cfg)
+        self.act_dim, self.obs_dim = act_dim_of(self._cfg), obs_dim_of(self._cfg)
         h = C.c_void_p()
         _chk(self.lib.uhc_engine_create(C.byref(self._ms), C.byref(self._cfg), C.c_int(self.E), C.c_int(self.device), C.c_int(precision), C.byref(h)))
         self.h = h
         dev = torch.device("cuda", self.device)
         f = dict(device=dev, dtype=torch.float32)
-        self.obs = torch.zeros(self.E, OBS_DIM, **f)
+        self.obs = torch.zeros(self.E, self.obs_dim, **f)
         self.reward = torch.zeros(self.E, **f)
         self.cinfo = torch.zeros(self.E, 5, **f)
         self.percent = torch.zeros(self.E, **f)
@@ -141,6 +153,7 @@ class Engine:
     def set_cfg(self, **cfg):
         self._cfg_kw = dict(getattr(self, "_cfg_kw", {}), **cfg)
         self._cfg = make_cfg(self.precision, **self._cfg_kw)
+        assert obs_dim_of(self._cfg) == self.obs_dim, "obs_v cannot change on a live engine (buffers are sized at creation)"
         self.act_dim = act_dim_of(self._cfg)
         _chk(self.lib.uhc_engine_set_cfg(self.h, C.byref(self._cfg)))
 
@@ -191,7 +204,7 @@ class Engine:
     def step_host(self, actions, obs=None, reward=None, cinfo=None, fail=None, end=None, percent=None):
         """Host-buffer entry (H2D of actions and D2H of every requested output inside the call)."""
         a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.E, self.act_dim)
-        obs = np.empty((self.E, OBS_DIM), np.float32) if obs is None else obs
+        obs = np.empty((self.E, self.obs_dim), np.float32) if obs is None else obs
         reward = np.empty(self.E, np.float32) if reward is None else reward
         cinfo = np.empty((self.E, 5), np.float32) if cinfo is None else cinfo
         fail = np.empty(self.E, np.int32) if fail is None else fail

@@ -56,29 +56,45 @@ class ParamList(list):
 class MLPNet:
     """MLP trunk + linear head (khrylib/models/mlp.py:5-27 with PolicyGaussian.action_mean or Value.value_head)."""
 
-    def __init__(self, in_dim, hsize, out_dim, htype="gelu", device="cuda", head_name="action_mean", seed=None):
+    @staticmethod
+    def flat_layout(dims):
+        """offsets (start, count) of W[0], b[0], W[1], ... in the flat tensor (every tensor starts on a 256-byte boundary) and the total length"""
+        offs, o = [], 0
+        for i in range(len(dims) - 1):
+            nW, nb = dims[i + 1] * dims[i], dims[i + 1]
+            offs.append((o, nW)); o += (nW + 63) // 64 * 64
+            offs.append((o, nb)); o += (nb + 63) // 64 * 64
+        return offs, o
+
+    def __init__(self, in_dim, hsize, out_dim, htype="gelu", device="cuda", head_name="action_mean", seed=None, storage=None, head_act="none",
+                 head_scale=(0.1, 0.0), generator=None):
+        """storage = (flat, gfull, base): this net's parameters / gradients are the slice [base, base + nflat) of a shared flat tensor (PolicyMCP: all
+        primitives and the composer live in one tensor -> one all-reduce, one Adam launch); head_act: activation after the output layer (the MCP
+        composer is a plain MLP whose last layer is activated too, mlp.py:24-27); head_scale: (weight, bias) factors of the output layer's init."""
         import torch
         self.torch, self.dims, self.htype, self.head_name = torch, [in_dim] + list(hsize) + [out_dim], htype, head_name
-        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        self.head_act = head_act
+        g = generator if generator is not None else (torch.Generator().manual_seed(seed) if seed is not None else None)
         # ONE flat fp32 tensor holds every parameter (each tensor starts on a 256-byte boundary), W[i] / b[i] are views of it; the
         # gradients live in an identically laid out flat tensor (`gflat`) with a small tail for the scalar statistics that ride the
         # gradient all-reduce (SURVEY.md section 8e) -- so Adam is one launch per net and the collective needs no flatten / copy.
-        offs, o = [], 0
-        for i in range(len(self.dims) - 1):
-            nW, nb = self.dims[i + 1] * self.dims[i], self.dims[i + 1]
-            offs.append((o, nW)); o += (nW + 63) // 64 * 64
-            offs.append((o, nb)); o += (nb + 63) // 64 * 64
+        offs, o = self.flat_layout(self.dims)
         self._offs, self.nflat = offs, o
-        self.flat = torch.zeros(o, device=device, dtype=torch.float32)
-        self._gfull = None
+        self._storage = storage
+        if storage is None:
+            self.flat = torch.zeros(o, device=device, dtype=torch.float32)
+            self._gfull = None
+        else:
+            sflat, sgfull, base = storage
+            self.flat, self._gfull, self._base = sflat[base:base + o], sgfull[base:base + o], base
         self.W, self.b = [], []
         for i in range(len(self.dims) - 1):  # nn.Linear default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias
             k = 1.0 / math.sqrt(self.dims[i])
             # explicit dtype: the reference's scripts set torch.set_default_dtype(float64) (train_uhc.py:80-81); the seeded stream must not depend on it
             w = (torch.rand(self.dims[i + 1], self.dims[i], generator=g, dtype=torch.float32) * 2 - 1) * k
             bb = (torch.rand(self.dims[i + 1], generator=g, dtype=torch.float32) * 2 - 1) * k
-            if i == len(self.dims) - 2:  # policy_gaussian.py:20-21 / critic.py:12-13
-                w, bb = w * 0.1, bb * 0.0
+            if i == len(self.dims) - 2 and head_scale is not None:  # policy_gaussian.py:20-21 / critic.py:12-13 / policy_mcp.py:20-22
+                w, bb = w * head_scale[0], bb * head_scale[1]
             (ow, nw), (ob, nb) = offs[2 * i], offs[2 * i + 1]
             W, B = self.flat[ow:ow + nw].view(self.dims[i + 1], self.dims[i]), self.flat[ob:ob + nb]
             W.copy_(w.float()); B.copy_(bb.float())
@@ -116,7 +132,7 @@ class MLPNet:
 
     @property
     def gfull(self):
-        """flat gradients + tail, allocated on first use"""
+        """flat gradients + tail, allocated on first use (a net living in shared storage sees its slice of the owner's gradient tensor, no tail)"""
         if self._gfull is None:
             self._gfull = self.torch.zeros(self.nflat + self.GRAD_TAIL, device=self.flat.device, dtype=self.torch.float32)
         return self._gfull
@@ -124,6 +140,9 @@ class MLPNet:
     @property
     def gflat(self):
         return self.gfull[:self.nflat]
+
+    def _act_of(self, i):
+        return self.htype if i < len(self.W) - 1 else self.head_act
 
     def grad_views(self):
         """gradient tensors (views of gflat) in params() order"""
@@ -138,7 +157,7 @@ class MLPNet:
         n = len(self.W)
         zs = []
         for i in range(n):
-            act = self.htype if i < n - 1 else "none"
+            act = self._act_of(i)
             if save and i < n - 1:
                 h, z = linear_forward(h, self.W[i], self.b[i], act, save_z=True)
                 zs.append(z)
@@ -204,7 +223,7 @@ class MLPNet:
             ybf = None if last else self._acts[i + 1]
             _chk(L.uhc_linear_forward_tc(_p(self._acts[i]), _p(self._bf16[i]), _p(self.b[i]), _p(ybf), _p(self._out if last else None), M,
                                          self.W[i].shape[0], self._bf16[i].shape[1], 0 if last else ybf.shape[1],
-                                         ACT["none" if last else self.htype], _stream(x)))
+                                         ACT[self._act_of(i)], _stream(x)))
         return self._out
 
 
@@ -226,6 +245,116 @@ def mlp_struct(net):
         m.W_bf16[i] = wb.data_ptr()
         m.bias[i] = b.data_ptr()
     m._keep = (list(net._bf16), list(net.b))
+    return m
+
+
+class UhcMcp(C.Structure):
+    """include/uhc_rollout.h UhcMcp"""
+    _fields_ = [("nprim", C.c_int), ("reserved", C.c_int), ("prim", UhcMlp * 8), ("composer", UhcMlp)]
+
+
+class MCPNet:
+    """PolicyMCP (uhc/models/policy_mcp.py:9-37, actor_type "mcp"): num_primitive MLPs state -> policy_hsize -> action (head weight x 0.1, bias 0) and a
+    composer MLP state -> composer_dim -> num_primitive whose every layer is activated, then a softmax; action_mean = sum_k w_k prim_k(x).
+    All parameters live in ONE flat tensor (and the gradients in one), the sub-nets are views: Adam and the gradient all-reduce see a single net."""
+    GRAD_TAIL = MLPNet.GRAD_TAIL
+
+    def __init__(self, in_dim, hsize, out_dim, htype="relu", num_primitive=8, composer_dim=(300, 200), device="cuda", seed=None):
+        import torch
+        self.torch, self.htype, self.num_primitive, self.head_name = torch, htype, num_primitive, "mcp"
+        self.dims = [in_dim] + list(hsize) + [out_dim]
+        pd, cd = [in_dim] + list(hsize) + [out_dim], [in_dim] + list(composer_dim) + [num_primitive]
+        n_p, n_c = MLPNet.flat_layout(pd)[1], MLPNet.flat_layout(cd)[1]
+        self.nflat = num_primitive * n_p + n_c
+        self.flat = torch.zeros(self.nflat, device=device, dtype=torch.float32)
+        self.gfull = torch.zeros(self.nflat + self.GRAD_TAIL, device=device, dtype=torch.float32)
+        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        self.prims = [MLPNet(in_dim, hsize, out_dim, htype, device=device, storage=(self.flat, self.gfull, k * n_p), generator=g) for k in range(num_primitive)]
+        self.composer = MLPNet(in_dim, composer_dim, num_primitive, htype, device=device, storage=(self.flat, self.gfull, num_primitive * n_p), head_act=htype,
+                               head_scale=None, generator=g)
+        self.nets = self.prims + [self.composer]
+        self._offs = [(n._base + o, cnt) for n in self.nets for (o, cnt) in n._offs]      # params() order, offsets into the shared flat tensor
+        self.W = [w for n in self.nets for w in n.W]           # every weight matrix (parameter counts, bf16 refresh checks)
+        self.b = [b for n in self.nets for b in n.b]
+        self.device, self.opt = device, None
+
+    @property
+    def gflat(self):
+        return self.gfull[:self.nflat]
+
+    @property
+    def _bf16(self):
+        return None if any(n._bf16 is None for n in self.nets) else [w for n in self.nets for w in n._bf16]
+
+    @_bf16.setter
+    def _bf16(self, v):
+        for n in self.nets:
+            n._bf16 = n._bf16_store if v is not None else None
+
+    def _prep_bf16(self):
+        for n in self.nets:
+            n._prep_bf16()
+
+    def invalidate_bf16(self):
+        for n in self.nets:
+            n.invalidate_bf16()
+
+    def params(self):
+        out = ParamList(p for n in self.nets for wb in zip(n.W, n.b) for p in wb)
+        out.net = self
+        return out
+
+    # ---- state_dict in the reference's key layout: nets.{k}.0.affine_layers.{i}.* (MLP), nets.{k}.1.* (action_mean), composer.0.affine_layers.{i}.*
+    def state_dict(self):
+        sd = {}
+        for k, n in enumerate(self.prims):
+            for i in range(len(n.W) - 1):
+                sd[f"nets.{k}.0.affine_layers.{i}.weight"], sd[f"nets.{k}.0.affine_layers.{i}.bias"] = n.W[i].detach().cpu(), n.b[i].detach().cpu()
+            sd[f"nets.{k}.1.weight"], sd[f"nets.{k}.1.bias"] = n.W[-1].detach().cpu(), n.b[-1].detach().cpu()
+        for i in range(len(self.composer.W)):
+            sd[f"composer.0.affine_layers.{i}.weight"], sd[f"composer.0.affine_layers.{i}.bias"] = self.composer.W[i].detach().cpu(), self.composer.b[i].detach().cpu()
+        return sd
+
+    def load_state_dict(self, sd):
+        t = self.torch
+        cp = lambda dst, src: dst.copy_(t.as_tensor(np.asarray(src), dtype=t.float32))
+        for k, n in enumerate(self.prims):
+            for i in range(len(n.W) - 1):
+                cp(n.W[i], sd[f"nets.{k}.0.affine_layers.{i}.weight"]); cp(n.b[i], sd[f"nets.{k}.0.affine_layers.{i}.bias"])
+            cp(n.W[-1], sd[f"nets.{k}.1.weight"]); cp(n.b[-1], sd[f"nets.{k}.1.bias"])
+        for i in range(len(self.composer.W)):
+            cp(self.composer.W[i], sd[f"composer.0.affine_layers.{i}.weight"]); cp(self.composer.b[i], sd[f"composer.0.affine_layers.{i}.bias"])
+        self.invalidate_bf16()
+
+    def _mix(self, xall, c):
+        t = self.torch
+        M, A, P = c.shape[0], self.dims[-1], self.num_primitive
+        mean = t.empty(M, A, device=c.device, dtype=t.float32)
+        _chk(_lib().uhc_mcp_combine(_p(xall), _p(c), None, _p(mean), M, A, P, _stream(c)))
+        return mean
+
+    def forward(self, x):
+        """fp32 SIMT GEMMs (the parity path against the reference's fp64 torch)"""
+        xall = self.torch.stack([n.forward(x) for n in self.prims]).contiguous()
+        return self._mix(xall, self.composer.forward(x).contiguous())
+
+    def forward_tc(self, x):
+        """tensor-core path (what uhc_rollout_mcp / uhc_policy_forward_mcp run)"""
+        xall = self.torch.stack([n.forward_tc(x).clone() for n in self.prims]).contiguous()
+        return self._mix(xall, self.composer.forward_tc(x).contiguous())
+
+
+def mcp_struct(net):
+    """UhcMcp view of an MCPNet's current bf16 weights"""
+    m = UhcMcp()
+    m.nprim = net.num_primitive
+    keep = []
+    for k, n in enumerate(net.prims):
+        s_ = mlp_struct(n); keep.append(s_)
+        m.prim[k] = s_
+    sc = mlp_struct(net.composer); keep.append(sc)
+    m.composer = sc
+    m._keep = keep
     return m
 
 
@@ -581,7 +710,7 @@ class UhcNetDesc(C.Structure):
     """include/uhc_ppo.h UhcNetDesc"""
     _fields_ = [("nlayers", C.c_int), ("act", C.c_int), ("dims", C.c_int * 10), ("flat", C.c_void_p), ("gfull", C.c_void_p), ("nflat", C.c_long), ("gtail", C.c_long),
                 ("w_off", C.c_long * 8), ("b_off", C.c_long * 8), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("lr", C.c_float), ("W_bf16", C.c_void_p * 8),
-                ("kp", C.c_int * 8)]
+                ("kp", C.c_int * 8), ("head_act", C.c_int)]
 
 
 class UhcPpoCfg(C.Structure):
@@ -589,18 +718,21 @@ class UhcPpoCfg(C.Structure):
     _fields_ = [("gamma", C.c_float), ("tau", C.c_float), ("clip_eps", C.c_float), ("grad_clip", C.c_float), ("clip_first_step_only", C.c_int), ("epochs", C.c_int)]
 
 
-def net_desc(net, opt):
-    """UhcNetDesc of an MLPNet + its flat Adam state (all pointers stay valid for the life of the net: the bf16 copies are refreshed in place)."""
+def net_desc(net, opt, owner=None):
+    """UhcNetDesc of an MLPNet + its flat Adam state (all pointers stay valid for the life of the net: the bf16 copies are refreshed in place).
+    owner: the MCPNet whose flat tensors this sub-net lives in (offsets are then relative to the owner's tensors)."""
     if getattr(net, "_bf16_store", None) is None or net._bf16 is None:
         net._prep_bf16()
-    assert opt.net is net, "the optimiser must be built on the net's flat tensors (nn.Adam(net.params(), lr, net=net))"
+    top = owner if owner is not None else net
+    assert opt.net is top, "the optimiser must be built on the net's flat tensors (nn.Adam(net.params(), lr, net=net))"
+    base = net._base if owner is not None else 0
     d = UhcNetDesc()
-    d.nlayers, d.act = len(net.W), ACT[net.htype]
+    d.nlayers, d.act, d.head_act = len(net.W), ACT[net.htype], ACT[net.head_act]
     for i, v in enumerate(net.dims):
         d.dims[i] = v
-    d.flat, d.gfull, d.nflat, d.gtail = net.flat.data_ptr(), net.gfull.data_ptr(), net.nflat, net.GRAD_TAIL
+    d.flat, d.gfull, d.nflat, d.gtail = top.flat.data_ptr(), top.gfull.data_ptr(), top.nflat, top.GRAD_TAIL
     for i in range(len(net.W)):
-        d.w_off[i], d.b_off[i] = net._offs[2 * i][0], net._offs[2 * i + 1][0]
+        d.w_off[i], d.b_off[i] = base + net._offs[2 * i][0], base + net._offs[2 * i + 1][0]
         d.W_bf16[i], d.kp[i] = net._bf16_store[i].data_ptr(), net._bf16_store[i].shape[1]
     d.adam_m, d.adam_v, d.lr = opt.mflat.data_ptr(), opt.vflat.data_ptr(), opt.lr
     d._keep = (net, opt, list(net._bf16_store))
@@ -641,10 +773,20 @@ class CPpoTrainer:
         L.uhc_ppo_returns.restype = C.c_void_p
         L.uhc_ppo_kernel_launches.restype = C.c_long
         self.L, self.policy, self.value, self.opt_p, self.opt_v = L, policy, value, opt_p, opt_v
-        self.dp, self.dv = net_desc(policy, opt_p), net_desc(value, opt_v)
+        self.dv = net_desc(value, opt_v)
         self.h = C.c_void_p()
         dev = device.index if hasattr(device, "index") else int(device)
-        if L.uhc_ppo_trainer_create(C.byref(self.dp), C.byref(self.dv), C.c_long(max_rows), C.c_int(max_envs), C.c_int(dev or 0), C.byref(self.h)) != 0:
+        if isinstance(policy, MCPNet):
+            arr = (UhcNetDesc * len(policy.nets))()
+            self._keep = [net_desc(n, opt_p, owner=policy) for n in policy.nets]
+            for i, d in enumerate(self._keep):
+                arr[i] = d
+            self.dp = arr
+            rc = L.uhc_ppo_trainer_create_mcp(arr, C.c_int(policy.num_primitive), C.byref(self.dv), C.c_long(max_rows), C.c_int(max_envs), C.c_int(dev or 0), C.byref(self.h))
+        else:
+            self.dp = net_desc(policy, opt_p)
+            rc = L.uhc_ppo_trainer_create(C.byref(self.dp), C.byref(self.dv), C.c_long(max_rows), C.c_int(max_envs), C.c_int(dev or 0), C.byref(self.h))
+        if rc != 0:
             raise RuntimeError("uhc_ppo_trainer_create: " + L.uhc_ppo_last_error().decode())
         self.max_rows, self.max_envs = max_rows, max_envs
 
@@ -671,7 +813,22 @@ class CPpoTrainer:
         self.opt_p.step_n, self.opt_v.step_n = sp.value, sv.value
         self.opt_p._clip_consumed = done.value > 0
         # the C side refreshed the bf16 weight copies in place after every optimiser step
-        self.policy._bf16, self.value._bf16 = self.policy._bf16_store, self.value._bf16_store
+        self.policy._bf16 = getattr(self.policy, "_bf16_store", True)
+        self.value._bf16 = self.value._bf16_store
+
+    def update_policy(self, states, actions, returns, advantages, exps, log_std, clip_eps, epochs, grad_clip, losses, comm=None, world=1):
+        """AgentPPO.update_policy (agent_ppo.py:16-51) on given returns / normalised advantages: uhc_ppo_update_policy"""
+        cfg = UhcPpoCfg(0.0, 0.0, clip_eps, float(grad_clip or 0.0), 1, epochs)
+        sp, sv = C.c_int(self.opt_p.step_n), C.c_int(self.opt_v.step_n)
+        done = C.c_int(1 if getattr(self.opt_p, "_clip_consumed", False) else 0)
+        rc = self.L.uhc_ppo_update_policy(self.h, _p(states), _p(actions), _p(returns), _p(advantages), _p(exps), _p(log_std), C.c_long(states.shape[0]), C.byref(cfg),
+                                          C.byref(sp), C.byref(sv), C.byref(done), comm, C.c_int(world), _p(losses), _stream(states))
+        if rc != 0:
+            raise RuntimeError("uhc_ppo_update_policy: " + self.L.uhc_ppo_last_error().decode())
+        self.opt_p.step_n, self.opt_v.step_n = sp.value, sv.value
+        self.opt_p._clip_consumed = done.value > 0
+        self.policy._bf16 = getattr(self.policy, "_bf16_store", True)
+        self.value._bf16 = self.value._bf16_store
 
     @property
     def kernel_launches(self):
