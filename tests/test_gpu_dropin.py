@@ -37,7 +37,7 @@ def _cfg(tmp_path, monkeypatch, cfg_file="uhc_b200_default.yml"):
     return cfg
 
 
-@pytest.mark.parametrize("cfg_file", ["uhc_b200_default.yml", "uhc_b200_explicit.yml"])     # release/uhc_implicit_shape.yml, release/uhc_explicit.yml
+@pytest.mark.parametrize("cfg_file", ["uhc_b200_default.yml", "uhc_b200_explicit.yml", "uhc_b200_implicit.yml"])     # the three configs of config/release/
 def test_train_script_sequence(tmp_path, monkeypatch, cfg_file):
     import torch
     from uhc.agents import agent_dict
@@ -49,7 +49,8 @@ def test_train_script_sequence(tmp_path, monkeypatch, cfg_file):
     np.random.seed(cfg.seed)
     torch.manual_seed(cfg.seed)
     agent = agent_dict[cfg.agent_name](cfg, dtype, device, training=True, checkpoint_epoch=0)
-    assert agent.action_dim == (315 if "explicit" in cfg_file else 105)
+    assert agent.action_dim == {"uhc_b200_default.yml": 105, "uhc_b200_explicit.yml": 315, "uhc_b200_implicit.yml": 75}[cfg_file]
+    assert agent.state_dim == (784 if "implicit.yml" in cfg_file else 657)
     for i_iter in range(0, cfg.num_epoch):
         info = agent.optimize_policy(i_iter)
         assert info["log"]["num_steps"] >= cfg.min_batch_size and np.isfinite(info["log"]["avg_reward"])
@@ -57,7 +58,7 @@ def test_train_script_sequence(tmp_path, monkeypatch, cfg_file):
     assert os.path.exists(ck)
     cp = pickle.load(open(ck, "rb"))
     assert set(cp) == {"policy_dict", "value_dict", "running_state"}
-    assert "net.affine_layers.0.weight" in cp["policy_dict"] and "value_head.bias" in cp["value_dict"]
+    assert ("nets.0.0.affine_layers.0.weight" if "implicit.yml" in cfg_file else "net.affine_layers.0.weight") in cp["policy_dict"] and "value_head.bias" in cp["value_dict"]
     # eval_uhc.py --mode stats: resume from the checkpoint and evaluate every clip deterministically
     agent2 = agent_dict[cfg.agent_name](cfg, dtype, device, training=True, checkpoint_epoch=2)
     res = agent2.eval_policy(epoch=2, dump=True)

@@ -73,8 +73,11 @@ class AgentCopycat:
             if not dist.is_initialized():
                 dist.init_process_group("nccl")
             sync = make_nccl_grad_sync(world)
-        assert cfg.obs_v == 2 and cfg.actor_type == "gauss" and cfg.reward_id in reward_func, \
-            "the B200 engine implements obs_v 2 / gauss actor / world_rfc_implicit (SURVEY.md section 8f lists the other variants as next)"
+        assert cfg.obs_v in (1, 2) and cfg.actor_type in ("gauss", "mcp") and cfg.reward_id in reward_func, \
+            "the B200 engine implements obs_v 1 | 2, the gauss and mcp actors, world_rfc_implicit / world_rfc_explicit (obs_v 3/5/6 etc.: SURVEY.md section 8f, next)"
+        assert cfg.get("obs_vel", "full") == "full" and cfg.get("obs_coord", "root") == "root" and not cfg.get("obs_phase", False), "obs_vel full / obs_coord root / no phase only"
+        if cfg.obs_v == 1:
+            assert not cfg.get("has_shape", False), "obs_v 1 carries no shape vector (has_shape: false in config/release/uhc_implicit.yml)"
         # variants the batched engine does not implement must not be accepted silently
         assert cfg.fix_std, "log_std is not a trained parameter in this engine (fix_std: true in every released config)"
         assert cfg.get("env_term_body", "body") == "body", "env_term_body: only 'body' (calc_body_diff) is implemented"
@@ -94,9 +97,11 @@ class AgentCopycat:
             t_min=cfg.data_specs.get("t_min", 90), t_max=cfg.data_specs.get("t_max", -1), rank=rank, world=world, grad_sync=sync,
             model=self.model_tables, base_rot=cfg.data_specs.get("base_rot", [0.7071, 0.7071, 0.0, 0.0]), rfc_scale=cfg.residual_force_scale,
             rfc_lim=cfg.residual_force_lim, rfc_rate=0.0 if cfg.rfc_decay else 1.0, body_diff_thresh=cfg.get("body_diff_thresh", 0.5),
-            meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=kk, rfc_mode=rfc_mode)
+            meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=kk, rfc_mode=rfc_mode,
+            obs_v=int(cfg.obs_v), actor_type=cfg.actor_type, num_primitive=int(cfg.get("num_primitive", 8)), composer_dim=tuple(cfg.get("composer_dim", [300, 200])),
+            reactive_v=int(cfg.get("reactive_v", 0)), reactive_rate=float(cfg.get("reactive_rate", 0.3)))
         self.policy_net, self.value_net, self.running_state = self.agent.policy, self.agent.value, self.agent.running_state
-        self.state_dim, self.action_dim = 657, self.agent.act_dim
+        self.state_dim, self.action_dim = self.agent.obs_dim, self.agent.act_dim
         self.expert_reward = reward_func[cfg.reward_id]
         self.env = None   # single-env facade, built lazily (eval_seq / visualisation code paths)
         self.logger = logging.getLogger(f"uhc_b200.{cfg.id}")
@@ -270,7 +275,7 @@ class AgentCopycat:
         return dict(base_rot=cfg.data_specs.get("base_rot", [0.7071, 0.7071, 0.0, 0.0]), rfc_scale=cfg.residual_force_scale, rfc_lim=cfg.residual_force_lim,
                     rfc_rate=0.0 if cfg.rfc_decay else 1.0, body_diff_thresh=cfg.get("body_diff_thresh_test" if test else "body_diff_thresh", 0.5),
                     meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, auto_reset=0 if test else 1,
-                    rfc_mode=cfg.get("residual_force_mode", "implicit"),
+                    rfc_mode=cfg.get("residual_force_mode", "implicit"), obs_v=int(cfg.obs_v),
                     w=[rw.get(k, d) for k, d in (("w_p", 0.6), ("w_v", 0.1), ("w_e", 0.2), ("w_c", 0.1), ("w_vf", 0.0))],
                     k=[rw.get(k, d) for k, d in (("k_p", 2), ("k_v", 0.005), ("k_e", 20), ("k_c", 1000), ("k_vf", 1))])
 

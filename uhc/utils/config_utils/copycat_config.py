@@ -29,7 +29,7 @@ class Config(Base_Config):
         self.reward_id, self.reward_weights = g("reward_id", "quat"), g("reward_weights", None)
         self.end_reward, self.actor_type = g("end_reward", False), g("actor_type", "gauss")
         if self.actor_type == "mcp":
-            self.num_primitive, self.composer_dim = g("num_primitive", 8), g("composer_dim", [[300, 200]])
+            self.num_primitive, self.composer_dim = g("num_primitive", 8), g("composer_dim", [300, 200])
         self.adp_iter_cp = np.array(g("adp_iter_cp", [0]))
         pad = lambda a: np.pad(np.array(a, dtype=np.float64), (0, self.adp_iter_cp.size - len(a)), "edge")
         self.adp_noise_rate_cp = pad(g("adp_noise_rate_cp", [1.0]))
