@@ -44,6 +44,7 @@ typedef struct {
                                | (first dof of the connecting joint / 3)<<20 | joint crossed backwards<<25 | number of levels<<26 */
     double dt, margin, mu, solref[2], solimp[5], gravz;
     int nshape;             /* number of body-shape variants: body_f = [nshape][24][20], hull = [nshape][nvert][3] (same topology / hull graph) */
+    const double *dof_lim;  /* [75][4] joint limits: lower, upper (rad; the xml's default is limited="true"), dof_invweight0, pad.  NULL = no limits */
 } UhcModelHost;
 
 /* Task configuration: the cfg attributes HumanoidEnv / world_rfc_implicit_reward read

@@ -80,6 +80,10 @@ class Model:
             _p(k[10]), _p(k[11], C.c_int), C.c_int(len(k[12])), _p(k[12]), _p(k[13], C.c_int), _p(k[14], C.c_int),
             _p(k[15], C.c_int), _p(k[16], C.c_int), C.c_double(float(z["timestep"])), C.c_double(float(z["margin"])),
             C.c_double(float(z["friction"])), _p(k[17]), _p(k[18]), _p(k[19])))
+        # joint limits: ranges from the model (xml: every hinge +-180 deg), overridable (tables["jnt_range"]) as smpl_robot.py:1087-1110 tightens them per shape
+        if "jnt_range" in z and "dof_invweight0" in z:
+            self._lim = (f("jnt_range"), f("dof_invweight0"))
+            lib().or_model_set_limits(self.h, _p(self._lim[0]), _p(self._lim[1]))
         self.dt = float(z["timestep"])
         self.qpos0 = np.zeros(NQ)
         self.qpos0[:3] = z["body_gpos"][0]

@@ -43,7 +43,7 @@
 #define NV 75
 #define NU 69
 #define MAXCON 96
-#define MAXROW (4 * MAXCON)
+#define MAXROW (4 * MAXCON + NU)   /* pyramid rows + one joint-limit row per hinge */
 #define OBS_DIM 657
 #define ACT_DIM 105
 
@@ -55,6 +55,7 @@ typedef struct {
     int nvert, vadr[NB], vnum[NB];
     double *vert; int *nbr, *nbradr;
     double dt, margin, mu, solref[2], solimp[5], gravity[3];
+    double jnt_range[NU][2], dof_invw[NV];   /* hinge limits (the model's default is limited="true", humanoid_smpl_neutral_mesh.xml:9) and dof_invweight0 */
 } OrModel;
 
 typedef struct {
@@ -152,7 +153,12 @@ OrModel *or_model_create(const int *parent, const double *offset, const double *
     m->dt = dt; m->margin = margin; m->mu = mu;
     memcpy(m->solref, solref, sizeof m->solref); memcpy(m->solimp, solimp, sizeof m->solimp);
     memcpy(m->gravity, gravity, sizeof m->gravity);
+    for (int j = 0; j < NU; j++) { m->jnt_range[j][0] = -M_PI; m->jnt_range[j][1] = M_PI; }
+    for (int i = 0; i < NV; i++) m->dof_invw[i] = 1.0;
     return m;
+}
+void or_model_set_limits(OrModel *m, const double *jnt_range, const double *dof_invw) {
+    memcpy(m->jnt_range, jnt_range, sizeof m->jnt_range); memcpy(m->dof_invw, dof_invw, sizeof m->dof_invw);
 }
 void or_model_free(OrModel *m) { if (m) { free(m->vert); free(m->nbr); free(m->nbradr); free(m); } }
 OrData *or_data_create(void) { OrData *d = (OrData *)calloc(1, sizeof(OrData)); d->qpos[3] = 1; return d; }
@@ -332,6 +338,19 @@ static void or_constraint_solve(const OrModel *m, OrData *d) {
             for (int i = 0; i < NV; i++) { J[nrow][i] = Jv[2][i] + sg*(t[0]*Jv[0][i] + t[1]*Jv[1][i] + t[2]*Jv[2][i]); vel += J[nrow][i]*d->qvel[i]; }
             aref[nrow] = -bb*vel - kk*imp*pos; D[nrow] = 1.0/Rpy; nrow++;
         }
+    }
+    /* joint limits (mj_instantiateLimit, margin 0): a hinge past its range gets one unilateral row J = +-e_dof, pos = distance to the limit (< 0),
+       default solref / solimp, diagApprox = dof_invweight0; frictionless, so R = (1 - d)/d * diagApprox without the pyramid factor */
+    for (int j = 0; j < NU; j++) {
+        const double q = d->qpos[7+j], lo = m->jnt_range[j][0], hi = m->jnt_range[j][1];
+        double dist, sg;
+        if (q - lo < 0) { dist = q - lo; sg = 1; } else if (hi - q < 0) { dist = hi - q; sg = -1; } else continue;
+        double x = fabs(dist)/width; if (x > 1) x = 1;
+        double y = (x < mid) ? pow(x/mid, power)*mid : 1 - pow((1-x)/(1-mid), power)*(1-mid);
+        double imp = dmin + y*(dmax-dmin);
+        double R = (1-imp)*m->dof_invw[6+j]/imp; if (R < 1e-15) R = 1e-15;
+        memset(J[nrow], 0, sizeof J[nrow]); J[nrow][6+j] = sg;
+        aref[nrow] = -bb*sg*d->qvel[6+j] - kk*imp*dist; D[nrow] = 1.0/R; nrow++;
     }
     d->nrow = nrow; d->newton_iters = 0;
     if (nrow == 0) { memcpy(d->qacc, d->qacc_smooth, sizeof d->qacc); return; }

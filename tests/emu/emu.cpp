@@ -11,7 +11,7 @@ using namespace uhc;
 
 template <class Real>
 struct Emu {
-    std::vector<Real> body_f, dof_f, hull, state, expert, shape;
+    std::vector<Real> body_f, dof_f, dof_lim, hull, state, expert, shape;
     std::vector<int> lvl_tab, lvl_pack, hull_adr, hull_num, nbr, nbradr, parent, depth, child_adr, child, body_sub_end, ee, istate, clip_adr;
     EngineView<Real> ev; Work<Real> w; int E;
 };
@@ -40,6 +40,7 @@ static Emu<Real> *create(const UhcModelHost *m, const UhcEnvCfg *cfg, int E) {
     cp(e->parent, m->parent, NB); cp(e->depth, m->depth, NB); cp(e->child_adr, m->child_adr, NB + 1); cp(e->child, m->child, NB - 1);
     cp(e->body_sub_end, m->body_sub_end, NB); cp(e->ee, m->ee, 5); cp(e->lvl_tab, m->lvl_tab, (MAXLEVEL + 1) * LVL_G * 5); cp(e->lvl_pack, m->lvl_pack, (MAXLEVEL + 1) * LVL_G);
     Model<Real> &M = e->ev.model;
+    cp(e->dof_lim, m->dof_lim, NV * 4); M.dof_lim = e->dof_lim.data();
     M.body_f = e->body_f.data(); M.dof_f = e->dof_f.data(); M.hull = e->hull.data(); M.hull_adr = e->hull_adr.data(); M.hull_num = e->hull_num.data();
     M.nbr = e->nbr.data(); M.nbradr = e->nbradr.data(); M.parent = e->parent.data(); M.depth = e->depth.data(); M.child_adr = e->child_adr.data();
     M.child = e->child.data(); M.body_sub_end = e->body_sub_end.data();
@@ -69,7 +70,8 @@ static int emu_forward_given_tau(const Model<Real> &m, const EnvCfg<Real> &cfg, 
     project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
     collide(m, w, tp);
     for (int i = 0; i < NV; i++) { Real f = -w.C[i] + (i < 6 ? (Real)fapp_d[i] : w.tau[i - 6]); w.fs[i] = f; w.as_[i] = f; }
-    if (w.ncon == 0) { aba_solve(m, w, Real(0), false, w.as_); for (int i = 0; i < NV; i++) w.a[i] = w.as_[i]; return 0; }
+    limit_setup(m, w);
+    if (w.ncon == 0 && w.nlim == 0) { aba_solve(m, w, Real(0), false, w.as_); for (int i = 0; i < NV; i++) w.a[i] = w.as_[i]; return 0; }
     constraint_setup(m, w);
     Real gn2 = 0;
     const Real scale = newton_init(m, w, tp, &gn2);

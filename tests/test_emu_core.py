@@ -150,3 +150,37 @@ def test_obs_v1_no_meta_pd_trace_matches_reference_golden(golden_dir, prec, tol_
         assert np.abs(obs - g["obs"][t]).max() < tol_o, t
         assert abs(r - g["reward"][t]) < tol_o
         assert info["fail"] == bool(g["fail"][t])
+
+
+@pytest.mark.parametrize("with_contacts", [False, True])
+def test_joint_limit_rows_match_oracle_fp64(with_contacts):
+    """Tightened hinge ranges (as smpl_robot.py:1087-1110 does per shape) with several joints past them, airborne and standing on the floor: the
+    kernel's limit rows (unit-Jacobian soft rows folded into the solve's joint-space diagonal and the carried gradient) against the oracle's dense rows."""
+    from uhc_b200.model import HumanoidModel
+    z = np.load(O.MODEL_NPZ)
+    jr = np.tile(np.array([[-0.4, 0.5]]), (69, 1))
+    om, d = O.Model(tables={"jnt_range": jr}), O.Data()
+    e = Emu(64, model=HumanoidModel(jnt_range=jr))
+    rng = np.random.default_rng(17)
+    nviol = []
+    for case in range(6):
+        q = om.qpos0.copy()
+        q[2] = rng.uniform(0.88, 0.93) if with_contacts else 3.0
+        q[3:7] = [0.7071068, 0.7071068, 0, 0]
+        q[7:] = rng.uniform(-0.7, 0.8, 69) if not with_contacts else rng.uniform(-0.05, 0.05, 69)
+        if with_contacts:
+            idx = rng.choice(np.arange(24, 69), 6, replace=False)        # upper-body joints past the range, feet on the ground
+            q[7 + idx] = rng.choice([-0.55, 0.65], 6)
+        v = rng.normal(size=75) * 0.5
+        tau, fapp, aw = rng.normal(size=69) * 20, rng.normal(size=6) * 10, rng.normal(size=75) * 3
+        d.qpos[:], d.qvel[:], d.ctrl[:] = q, v, tau
+        d.qfrc_applied[:] = 0; d.qfrc_applied[:6] = fapp; d.qacc_warm[:] = aw
+        O.forward(om, d)
+        if d.ncon > 40:
+            continue
+        assert (d.ncon > 0) == with_contacts
+        r = e.forward(q, v, tau, fapp, aw)
+        nviol.append(int(((q[7:] < jr[:, 0]) | (q[7:] > jr[:, 1])).sum()))
+        assert r["ncon"] == d.ncon
+        assert np.abs(r["qacc"] - d.qacc).max() < 2e-6 * max(1.0, np.abs(d.qacc).max()), (case, d.ncon, nviol[-1], np.abs(r["qacc"] - d.qacc).max())
+    assert len(nviol) >= 4 and min(nviol) >= 4

@@ -332,3 +332,34 @@ def test_explicit_residual_force_matches_reference_trace(golden_dir, precision, 
     assert np.abs(rew[:lim - 2] - g["reward"][:lim - 2]).max() < tol_o
     assert np.abs(ci[:lim - 2] - g["c_info"][:lim - 2]).max() < tol_o
     assert (fail[:first_fail - 1] == 0).all() and fail[first_fail - 1:first_fail + 2].any()
+
+
+@pytest.mark.parametrize("precision,tol_q", [(64, 1e-7), (32, 1e-3)])
+def test_joint_limit_rows_match_oracle(golden_dir, precision, tol_q):
+    """Hinge ranges tightened to +-0.3 rad (smpl_robot.py:1087-1110 tightens knee / ankle ranges per shape; the shipped neutral model has +-180 deg on every
+    hinge): the sway clip then drives many joints past their limits, so the limit rows act in every substep.  Kernel against the oracle env on the
+    same tables, 12 control steps."""
+    import torch
+    from oracle import oracle as O
+    from uhc_b200.engine import Engine
+    from uhc_b200.model import HumanoidModel
+    ex, so = _expert(golden_dir, "sway")
+    jr = np.tile(np.array([[-0.3, 0.3]]), (69, 1))
+    eng = Engine(2, model=HumanoidModel(jnt_range=jr), precision=precision)
+    eng.load_clips([ex], [so])
+    obs0 = eng.reset().cpu().numpy()
+    oe = O.Env(O.Model(tables={"jnt_range": jr}), ex, so)
+    assert np.abs(oe.reset() - obs0[1]).max() < 1e-4
+    assert ((ex["qpos"][0, 7:] < -0.3) | (ex["qpos"][0, 7:] > 0.3)).sum() >= 3          # the clip's first frame already violates several limits
+    rng = np.random.RandomState(3)
+    worst = 0.0
+    for t in range(12):
+        a = rng.normal(0, 0.1, 105); a[69:75] *= 0.3
+        eng.step(torch.tensor(np.tile(a, (2, 1)), dtype=torch.float32, device="cuda"))
+        torch.cuda.synchronize()
+        oo, ro, done, info = oe.step(a)
+        worst = max(worst, np.abs(eng.get_state(1)["qpos"] - oe.d.qpos).max())
+        if done:
+            break
+    assert t >= 5 and worst < tol_q, (t, worst)
+    eng.close()

@@ -99,3 +99,42 @@ def test_contact_solution_is_consistent_with_its_forces():
         assert np.abs(lhs - total).max() < 1e-6 * max(1.0, np.abs(total).max()), (case, lhs, total)
         assert total[2] > 0                                       # the floor only pushes
     assert seen >= 5
+
+
+def test_joint_limit_row_matches_closed_form():
+    """One hinge past a tightened limit, no contacts: the constrained acceleration has the closed form of a single soft unilateral row
+    (min 1/2 (a - a_s)^T M (a - a_s) + 1/2 D (sg a_i - aref)_-^2  =>  r = (sg a_s,i - aref) / (1 + (M^-1)_ii D), a = a_s - M^-1 e_i sg D r), with
+    MuJoCo's default solref / solimp and diagApprox = dof_invweight0; inside the range nothing changes."""
+    z = np.load(O.MODEL_NPZ)
+    rng = np.random.default_rng(5)
+    jr = z["jnt_range"].copy()
+    knee_x = 3 * 1 + 2                      # hinge index of L_Knee_x (body 2 = L_Knee: hinges 3..5, order z, y, x)
+    jr[knee_x] = [-0.1, 2.0]
+    om, d = O.Model(tables={"jnt_range": jr}), O.Data()
+    for q_knee, sg in ((-0.3, 1.0), (2.25, -1.0), (0.7, 0.0)):
+        q = om.qpos0.copy(); q[2] = 3.0
+        q[7:] = rng.uniform(-0.2, 0.2, 69); q[7 + knee_x] = q_knee
+        v = rng.normal(size=75) * 0.3
+        d.qpos[:], d.qvel[:], d.ctrl[:] = q, v, rng.normal(size=69) * 5
+        d.qfrc_applied[:] = 0; d.qacc_warm[:] = 0
+        O.forward(om, d)
+        assert d.ncon == 0
+        a_s, M = np.array(d.qacc_smooth), np.array(d.M).reshape(75, 75)
+        if sg == 0:
+            np.testing.assert_allclose(d.qacc, a_s, atol=1e-12)
+            continue
+        i = 6 + knee_x
+        dist = (q_knee - jr[knee_x, 0]) if sg > 0 else (jr[knee_x, 1] - q_knee)
+        assert dist < 0
+        dmin, dmax, width, mid, power = z["solimp"]; tc, dr = z["solref"]
+        x = min(abs(dist) / width, 1.0)
+        y = (x / mid) ** power * mid if x < mid else 1 - ((1 - x) / (1 - mid)) ** power * (1 - mid)
+        imp = dmin + y * (dmax - dmin)
+        D = 1.0 / ((1 - imp) * z["dof_invweight0"][i] / imp)
+        kk, bb = 1.0 / (dmax * dmax * tc * tc * dr * dr), 2.0 / (dmax * tc)
+        aref = -bb * sg * v[i] - kk * imp * dist
+        Minv_i = np.linalg.solve(M, np.eye(75)[i])
+        r = (sg * a_s[i] - aref) / (1 + Minv_i[i] * D)
+        assert r < 0                                                        # the row is active: the limit pushes the joint back
+        np.testing.assert_allclose(d.qacc, a_s - Minv_i * sg * D * r, rtol=0, atol=1e-8 * max(1.0, np.abs(d.qacc).max()))
+        assert sg * (d.qacc[i] - a_s[i]) > 0

@@ -83,6 +83,7 @@ def main():
 
     root = ET.parse(XML).getroot()
     names, parent, gpos = [], [], []
+    jrange = []          # hinge ranges in radians, dof order (xml default: limited="true", angle unit degree)
 
     def walk(el, par):
         for b in el.findall("body"):
@@ -95,6 +96,9 @@ def main():
                 assert len(js) == 1 and js[0].get("type") == "free"
             else:
                 assert [j.get("axis").split()[k] for k, j in zip((2, 1, 0), js)] == ["1.0000"] * 3, "hinge order z,y,x"
+                for j in js:
+                    assert j.get("limited", "true") == "true"
+                    jrange.append([np.deg2rad(float(x)) for x in j.get("range").split()])
             walk(b, idx)
 
     walk(root.find("worldbody"), -1)
@@ -179,12 +183,15 @@ def main():
     for b in range(nb):
         invw[b, 0] = np.trace(Jv[b] @ Minv @ Jv[b].T) / 3
         invw[b, 1] = np.trace(Jw[b] @ Minv @ Jw[b].T) / 3
+    # dof_invweight0 (diagApprox of the joint-limit rows): diagonal of M^-1 at qpos0; the free joint's translational / rotational dofs share their means
+    dof_invw = np.diag(Minv).copy()
+    dof_invw[0:3], dof_invw[3:6] = dof_invw[0:3].mean(), dof_invw[3:6].mean()
 
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     np.savez_compressed(
         OUT, body_names=np.array(names), parent=parent, body_gpos=gpos, body_offset=offset, body_mass=mass,
         body_ipos=ipos, body_inertia=inertia, body_invweight0=invw, dof_body=dof_body, armature=armature,
-        jkp=jkp, jkd=jkd, torque_lim=tlim, diffw=diffw,
+        jkp=jkp, jkd=jkd, torque_lim=tlim, diffw=diffw, jnt_range=np.array(jrange), dof_invweight0=dof_invw,
         ee_body=np.array([names.index(n) for n in EE_NAMES], dtype=np.int32),
         hull_vert=verts, hull_vadr=np.array(vadr, dtype=np.int32), hull_vnum=np.array(vnum, dtype=np.int32),
         hull_nbr=np.array(nbr, dtype=np.int32), hull_nbradr=np.array(nbradr, dtype=np.int32),

@@ -82,6 +82,7 @@ template <class Real>
 struct Model {
     const Real *body_f;   // [NB][BODYF]: offset3 ipos3 mass inertia6(xx,yy,zz,xy,xz,yz) invw bsphere4 diffw pad
     const Real *dof_f;    // [NV][4]: armature, kp, kd, torque_lim
+    const Real *dof_lim;  // [NV][4]: joint limit lower, upper (rad), dof_invweight0, pad
     const Real *hull;     // [nvert][3] body-local
     const int *hull_adr, *hull_num, *nbr, *nbradr;
     const int *parent, *depth, *child_adr, *child, *body_sub_end;
@@ -128,6 +129,7 @@ struct Work {
     int cbody[MAXCON]; Real cr[MAXCON][3], cdist[MAXCON], cD[MAXCON], caref[MAXCON][4], cres[MAXCON][4], cjp[MAXCON][4];
     int bcon_adr[NB + 1];
     int ncon, upper_contact;
+    int nlim;                     // joint-limit rows of this substep (hinges past their range); their data rides in tau (sign * D) and as_ (residual)
     int con_overflow;             // a candidate body's contacts did not fit MAXCON in some substep of this step (the env is failed, never silently truncated)
     alignas(8) unsigned long long mbar;   // mbarrier of this warp's bulk-async state load
     int sync_threads;             // threads taking part in the CTA-level substep alignment barrier (32 x warps that own a valid env)
@@ -467,7 +469,12 @@ UHC_DEVNI void aba_solve(const Model<Real> &m, Work<Real> &w, Real arm_scale, bo
     for (int i = 0; i < 3; i++) { LVA(row)[i] = pbc(Real(0)); LVA(pA)[i] = pbc(Real(0)); }
     LV(rr) = lane - 6 * (lane / 6);
     LV(entn) = lane < 6 * LVL_G ? UHC_LDT(m.lvl_pack + (nlvl - 1) * LVL_G + lane / 6) : 0;
-    for (int i = lane; i < NV; i += 32) arm[i] = UHC_LDT(m.dof_f + 4 * i) + arm_scale * UHC_LDT(m.dof_f + 4 * i + 2);   // joint-space diagonal
+    const bool limits = use_contacts && w.nlim > 0;     // an active joint-limit row (J = +-e_i) adds its D to the joint-space diagonal of the Hessian
+    for (int i = lane; i < NV; i += 32) {
+        Real d = UHC_LDT(m.dof_f + 4 * i) + arm_scale * UHC_LDT(m.dof_f + 4 * i + 2);   // joint-space diagonal
+        if (limits && w.tau[i] != 0 && w.as_[i] < 0) d += abs_(w.tau[i]);
+        arm[i] = d;
+    }
     LANES_END
 #pragma unroll 1
     for (int lvl = nlvl - 1; lvl >= 0; --lvl) {
@@ -883,6 +890,49 @@ UHC_DEV void constraint_setup(const Model<Real> &m, Work<Real> &w) {
     LANES_END
 }
 
+// joint limits (mj_instantiateLimit with margin 0): a hinge past its range gets ONE unilateral row J = sg e_dof (sg = +1 at the lower, -1 at the upper
+// limit), pos = distance to the limit (< 0), default solref / solimp, R = (1 - d)/d * dof_invweight0 (no pyramid factor).  lane = dof.  The row's data
+// ride in vectors that are dead during the constraint solve: tau[i] = sg * D (0 = no row), as_[i] = -aref (newton_init turns it into the residual).
+template <class Real>
+UHC_DEV void limit_setup(const Model<Real> &m, Work<Real> &w) {
+    // cheap test first (the ranges sit in shared memory next to the joint gains): in the common case no hinge is past its range and nothing else happens
+    LVAR(int, viol);
+    LANES_BEGIN
+    int f = 0;
+    for (int i = 6 + lane; i < NV; i += 32) { const Real q = w.q[i + 1]; f |= (q < UHC_LDT(m.dof_lim + 4 * i)) | (q > UHC_LDT(m.dof_lim + 4 * i + 1)); }
+    LV(viol) = f;
+    LANES_END_R
+    if (!WBALLOT(viol)) { w.nlim = 0; return; }
+    const Real kk = Real(1) / (m.simp1 * m.simp1 * m.solref0 * m.solref0 * m.solref1 * m.solref1), bb = Real(2) / (m.simp1 * m.solref0);
+    LANES_BEGIN
+    for (int i = lane; i < NV; i += 32) {
+        Real sD = 0;
+        if (i >= 6) {
+            const Real q = w.q[i + 1], lo = UHC_LDT(m.dof_lim + 4 * i), hi = UHC_LDT(m.dof_lim + 4 * i + 1);
+            Real dist = 0, sg = 0;
+            if (q - lo < 0) { dist = q - lo; sg = 1; } else if (hi - q < 0) { dist = hi - q; sg = -1; }
+            if (sg != 0) {
+                Real x = abs_(dist) / m.simp2; if (x > 1) x = 1;
+                Real y;
+                if (m.simp4 == Real(2)) y = x < m.simp3 ? x * x / m.simp3 : 1 - (1 - x) * (1 - x) / (1 - m.simp3);
+                else if (x < m.simp3) y = pow_(x / m.simp3, m.simp4) * m.simp3;
+                else y = 1 - pow_((1 - x) / (1 - m.simp3), m.simp4) * (1 - m.simp3);
+                const Real imp = m.simp0 + y * (m.simp1 - m.simp0);
+                Real R = (1 - imp) * UHC_LDT(m.dof_lim + 4 * i + 2) / imp;
+                if (R < Real(1e-15)) R = Real(1e-15);
+                sD = sg / R;
+                w.as_[i] = bb * sg * w.v[i] + kk * imp * dist;       // -aref
+            }
+        }
+        w.tau[i] = sD;
+    }
+    LANES_END
+    w.nlim = 1;
+#ifndef UHC_EMU
+    __syncwarp();
+#endif
+}
+
 // rows: out[c][e] = d_e . (point velocity of body spatial vector X at contact c), lane = contact
 template <class Real>
 UHC_DEVNI void contact_rows(const Model<Real> &m, Work<Real> &w, const Real (*X)[6], Real (*out)[4], const Real (*sub)[4]) {
@@ -990,7 +1040,12 @@ UHC_DEV Real newton_init(const Model<Real> &m, Work<Real> &w, const TPT &tp, Rea
     Real s = 0;
     for (int i = lane; i < NV; i += 32) {
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
-        const Real gi = pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b])) + UHC_LDT(m.dof_f + 4 * i) * w.aw[i] - w.fs[i];
+        Real gi = pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b])) + UHC_LDT(m.dof_f + 4 * i) * w.aw[i] - w.fs[i];
+        if (w.nlim > 0 && w.tau[i] != 0) {      // joint-limit row: residual r = sg a_i - aref, gradient term J^T D r_- = sg D r_-
+            const Real sD = w.tau[i], r = (sD > 0 ? w.aw[i] : -w.aw[i]) + w.as_[i];
+            w.as_[i] = r;
+            if (r < 0) gi += sD * r;
+        }
         w.g[i] = gi; w.p[i] = -gi; w.a[i] = w.aw[i]; s += gi * gi;
     }
     LV(gs) = s;
@@ -1022,6 +1077,10 @@ UHC_DEV bool newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp, 
             const Real r0 = w.cres[c][e], jp = w.cjp[c][e], r = r0 + al * jp;
             if ((r0 < 0) != (r < 0)) { const Real dj = w.cD[c] * jp; s1 -= dj * abs_(r); s2 += (r < 0) ? dj * jp : -dj * jp; ch = 1; }
         }
+        if (w.nlim > 0) for (int i = lane; i < NV; i += 32) if (w.tau[i] != 0) {     // joint-limit rows: J p = sg p_i
+            const Real sD = w.tau[i], r0 = w.as_[i], jp = sD > 0 ? w.p[i] : -w.p[i], r = r0 + al * jp;
+            if ((r0 < 0) != (r < 0)) { const Real dj = abs_(sD) * jp; s1 -= dj * abs_(r); s2 += (r < 0) ? dj * jp : -dj * jp; ch = 1; }
+        }
         LV(d1) = s1; LV(d2) = s2; LV(chg) = ch;
         LANES_END_R
         const bool any = WBALLOT(chg) != 0;
@@ -1043,6 +1102,15 @@ UHC_DEV bool newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp, 
         const bool sw = (r0 < 0) != (r < 0);
         w.cres[c][e] = r; w.cjp[c][e] = sw ? -w.cD[c] * abs_(r) : Real(0); ch |= sw;
     }
+    if (w.nlim > 0) for (int i = lane; i < NV; i += 32) {       // joint-limit rows: new residual, multiplier sg D delta of a switched row into Mp (free between solves)
+        Real mult = 0;
+        if (w.tau[i] != 0) {
+            const Real sD = w.tau[i], r0 = w.as_[i], r = r0 + al * (sD > 0 ? w.p[i] : -w.p[i]);   // p is still the direction here (a is updated above from it)
+            w.as_[i] = r;
+            if ((r0 < 0) != (r < 0)) { mult = -sD * abs_(r); ch = 1; }
+        }
+        w.Mp[i] = mult;
+    }
     LV(chg2) = ch;
     LANES_END
     const bool any2 = WBALLOT(chg2) != 0;
@@ -1061,6 +1129,7 @@ UHC_DEV bool newton_advance(const Model<Real> &m, Work<Real> &w, const TPT &tp, 
         const int b = i < 6 ? 0 : 1 + (i - 6) / 3;
         Real gi = (1 - al) * w.g[i];
         if (any2) gi += pdot6(as_pairs(w.S[i]), as_pairs(w.Fb[b]));
+        if (any2 && w.nlim > 0) gi += w.Mp[i];
         w.g[i] = gi; w.p[i] = -gi; s += gi * gi;
     }
     LV(gs) = s;
@@ -1255,6 +1324,7 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
             }
             LANES_END
             rhs = w.as_;
+            limit_setup(m, w);                         // after the loop above consumed tau; touches as_ only on dofs that get a limit row (then no smooth solve runs)
         } else {
             // (aligning the Newton iterations across the CTA as well was measured: the waiting costs more than it saves)
             if (done || iters >= cfg.newton_max_iter || !(gn2 > cfg.newton_tol * cfg.newton_tol * scale * scale)) break;
@@ -1262,12 +1332,12 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
         }
         // ---- the one shared O(n) articulated-body solve (not needed for the smooth phase when contacts are present:
         //      Newton starts from the warm start and only needs f_s, not a_s = M^-1 f_s)
-        if (!(phase == PH_SMOOTH && w.ncon > 0)) aba_solve(m, w, arm_scale, phase == PH_NEWTON, rhs);
+        if (!(phase == PH_SMOOTH && (w.ncon > 0 || w.nlim > 0))) aba_solve(m, w, arm_scale, phase == PH_NEWTON, rhs);
         // ---- phase post-processing
         if (phase == PH_PD) { pd_finish(m, cfg, w, it, torque_out); phase = PH_SMOOTH; UHC_CTA_SYNC(cta_sync); }
         else if (phase == PH_SMOOTH) {
             UHC_CTA_SYNC(cta_sync);
-            if (w.ncon == 0) {
+            if (w.ncon == 0 && w.nlim == 0) {
                 LANES_BEGIN
                 for (int i = lane; i < NV; i += 32) w.a[i] = w.as_[i];
                 LANES_END

@@ -22,13 +22,14 @@ static thread_local std::string g_err;
 template <class Real, int EPB>
 __device__ __forceinline__ void stage_tables(EngineView<Real> &ev, unsigned char *smem) {
     Real *s_dof = reinterpret_cast<Real *>(smem + EPB * sizeof(Work<Real>));
-    int *s_lvl = reinterpret_cast<int *>(s_dof + NV * 4);
-    for (int i = threadIdx.x; i < NV * 4; i += blockDim.x) s_dof[i] = ev.model.dof_f[i];
+    Real *s_lim = s_dof + NV * 4;
+    int *s_lvl = reinterpret_cast<int *>(s_lim + NV * 4);
+    for (int i = threadIdx.x; i < NV * 4; i += blockDim.x) { s_dof[i] = ev.model.dof_f[i]; s_lim[i] = ev.model.dof_lim[i]; }
     for (int i = threadIdx.x; i < (MAXLEVEL + 1) * LVL_G; i += blockDim.x) s_lvl[i] = ev.model.lvl_pack[i];
     LaneTopo *s_topo = reinterpret_cast<LaneTopo *>(s_lvl + (MAXLEVEL + 1) * LVL_G);
     if (threadIdx.x < 32) s_topo[threadIdx.x] = lane_topo(ev.model, (int)threadIdx.x);
     __syncthreads();
-    ev.model.dof_f = s_dof; ev.model.lvl_pack = s_lvl; ev.model.topo_s = s_topo;
+    ev.model.dof_f = s_dof; ev.model.dof_lim = s_lim; ev.model.lvl_pack = s_lvl; ev.model.topo_s = s_topo;
 }
 
 #ifndef UHC_MIN_CTAS
@@ -166,6 +167,11 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
     if (dev_copy_real<Real>(e, &M.body_f, m->body_f, (size_t)nshape * NB * BODYF) || dev_copy_real<Real>(e, &M.dof_f, m->dof_f, NV * 4) ||
         dev_copy_real<Real>(e, &M.hull, m->hull, (size_t)nshape * m->nvert * 3)) return -1;
     M.nshape = nshape; M.nvert = m->nvert; M.topo_s = nullptr;
+    {   // joint limits: without a table every hinge is unlimited
+        std::vector<double> lim(NV * 4, 0.0);
+        for (int i = 0; i < NV; i++) { lim[4 * i] = -1e30; lim[4 * i + 1] = 1e30; lim[4 * i + 2] = 1.0; }
+        if (dev_copy_real<Real>(e, &M.dof_lim, m->dof_lim ? m->dof_lim : lim.data(), NV * 4)) return -1;
+    }
     int *p;
 #define CPI(field, n) do { if (dev_copy(e, &p, m->field, (size_t)(n))) return -1; M.field = p; } while (0)
     CPI(hull_adr, NB); CPI(hull_num, NB); CPI(nbr, m->nnbr); CPI(nbradr, m->nvert + 1); CPI(parent, NB); CPI(depth, NB); CPI(child_adr, NB + 1);
@@ -189,7 +195,7 @@ template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, 
 }
 
 constexpr int EPB_F = UHC_EPB_F, EPB_D = 2;
-template <class Real, int EPB> constexpr size_t step_smem() { return EPB * sizeof(Work<Real>) + NV * 4 * sizeof(Real) + (MAXLEVEL + 1) * LVL_G * sizeof(int) + 32 * sizeof(LaneTopo); }  // environments (warps) per block
+template <class Real, int EPB> constexpr size_t step_smem() { return EPB * sizeof(Work<Real>) + 2 * NV * 4 * sizeof(Real) + (MAXLEVEL + 1) * LVL_G * sizeof(int) + 32 * sizeof(LaneTopo); }  // environments (warps) per block
 // the fp32 step kernel is tuned for UHC_MIN_CTAS resident blocks per SM (sm_100: 228 KiB of shared memory per SM, 1 KiB reserved per block, ~1 KiB static here):
 // a few hundred bytes more in Work / LaneTopo silently halve the residency (measured: 1.27 -> 0.88 M env-steps/s), so it is a compile-time error
 static_assert(EPB_F != 7 || UHC_MIN_CTAS * (step_smem<float, EPB_F>() + 1024 + 1088) <= 228 * 1024, "k_env_step<float>: the work sets of UHC_MIN_CTAS blocks no longer fit one SM");

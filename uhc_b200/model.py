@@ -26,11 +26,13 @@ class UhcModelHost(C.Structure):
                 ("ee", C.POINTER(C.c_int)),
                 ("lvl_tab", C.POINTER(C.c_int)), ("lvl_pack", C.POINTER(C.c_int)),
                 ("dt", C.c_double), ("margin", C.c_double), ("mu", C.c_double), ("solref", C.c_double * 2),
-                ("solimp", C.c_double * 5), ("gravz", C.c_double), ("nshape", C.c_int)]
+                ("solimp", C.c_double * 5), ("gravz", C.c_double), ("nshape", C.c_int), ("dof_lim", C.POINTER(C.c_double))]
 
 
 class HumanoidModel:
-    def __init__(self, npz=ASSET, scale=None):
+    def __init__(self, npz=ASSET, scale=None, jnt_range=None):
+        """jnt_range: optional [69][2] hinge limits in radians overriding the model's (xml: +-180 deg on every hinge; smpl_robot.py:1087-1110 tightens
+        knee / ankle ranges per shape)."""
         z = np.load(npz)
         self.z = {k: z[k] for k in z.files}
         self.body_names = [str(n) for n in z["body_names"]]
@@ -61,6 +63,8 @@ class HumanoidModel:
         self.qpos0[:3] = z["body_gpos"][0]
         self.qpos0[3] = 1.0
         self.root_offset = z["body_gpos"][0].copy()  # mj_model.body_pos[1] in smpl_to_qpose (count_offset)
+        self.jnt_range = np.asarray(jnt_range if jnt_range is not None else z["jnt_range"], dtype=np.float64).reshape(NV - 6, 2)
+        self.dof_invweight0 = z["dof_invweight0"].astype(np.float64)
         self._topology()
         if self.invw is None:
             self.invw = self._invweight0()
@@ -164,6 +168,12 @@ class HumanoidModel:
         df[:, 0] = self.armature
         df[6:, 1], df[6:, 2], df[6:, 3] = self.jkp, self.jkd, self.torque_lim
         self.body_f, self.dof_f = np.ascontiguousarray(bf), np.ascontiguousarray(df)
+        # joint-limit table [NV][4]: lower, upper (rad), dof_invweight0 (diagApprox of a limit row), pad; the free joint has no limits
+        dl = np.zeros((NV, 4))
+        dl[:6, 0], dl[:6, 1] = -1e30, 1e30
+        dl[6:, 0:2] = self.jnt_range
+        dl[:, 2] = self.dof_invweight0
+        self.dof_lim = np.ascontiguousarray(dl)
 
     # residual-force slot order of the explicit mode: vf_bodies = SMPL_BONE_ORDER_NAMES (humanoid_im.py:236-237, smpl_parser.py:11-36)
     SMPL_BONE_ORDER = ("Pelvis", "L_Hip", "R_Hip", "Torso", "L_Knee", "R_Knee", "Spine", "L_Ankle", "R_Ankle", "Chest", "L_Toe", "R_Toe", "Neck", "L_Thorax",
@@ -191,6 +201,7 @@ class HumanoidModel:
         h.nvert, h.nnbr = len(self.hull), len(self.nbr)
         h.body_f, h.dof_f, h.hull = ptr("bf", body_f, C.c_double), ptr("df", self.dof_f, C.c_double), ptr("hull", hull, C.c_double)
         h.nshape = len(models)
+        h.dof_lim = ptr("dof_lim", self.dof_lim, C.c_double)
         for n in ("hull_adr", "hull_num", "nbr", "nbradr", "parent", "depth", "child_adr", "child", "body_sub_end", "ee", "lvl_tab", "lvl_pack"):
             setattr(h, n, ptr(n, getattr(self, n).astype(np.int32), C.c_int))
         h.dt, h.margin, h.mu, h.gravz = self.dt, self.margin, self.mu, self.gravz
