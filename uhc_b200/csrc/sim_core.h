@@ -133,6 +133,7 @@ struct Work {
     int con_overflow;             // a candidate body's contacts did not fit MAXCON in some substep of this step (the env is failed, never silently truncated)
     alignas(8) unsigned long long mbar;   // mbarrier of this warp's bulk-async state load
     int sync_threads;             // threads taking part in the CTA-level substep alignment barrier (32 x warps that own a valid env)
+    int sync_id;                  // named barrier of this warp's alignment group (1 = the whole CTA; UHC_SYNC_SPLIT builds use one barrier per group)
     // this env's model view (shape variant) and config: kept here so that the non-inlined phases read them from shared memory
     // instead of a per-thread local-memory copy
     alignas(8) Model<Real> mdl;
@@ -1285,10 +1286,11 @@ enum { PH_PD = 0, PH_SMOOTH = 1, PH_NEWTON = 2 };
 // Measured (E = 4096): whole-CTA alignment 1.25 M env-steps/s, groups of 4 / 3 / 2 warps 1.23 / 1.20 / 1.16 M, none 0.95 M;
 // every 2nd / 3rd substep only 1.06 / 1.00 M; aligning each Newton iteration too 1.06 M.  Re-measured on the final kernel (1.57 M):
 // without the barrier before the Newton phase 1.53 M, without the one at the substep start 1.57 M (neutral), without both 1.52 M.
+// Round-2 kernel (profiles/r02_env_step_sync_groups.txt): groups of 2 / 3 / 4 warps 1.46 / 1.53 / 1.64 M, the whole 7-warp CTA 1.74 M, one 14-warp CTA per SM 1.70 M.
 // The barrier is a NAMED barrier with an explicit thread count (w.sync_threads = 32 x the warps of the CTA that own a valid
 // environment): warps without work leave the kernel before the substep loop and are simply not counted.
 #if !defined(UHC_EMU) && !defined(UHC_NO_CTA_SYNC)
-#define UHC_CTA_SYNC(on) do { if (on) asm volatile("bar.sync 1, %0;" :: "r"(w.sync_threads) : "memory"); } while (0)
+#define UHC_CTA_SYNC(on) do { if (on) asm volatile("bar.sync %0, %1;" :: "r"(w.sync_id), "r"(w.sync_threads) : "memory"); } while (0)
 #else
 #define UHC_CTA_SYNC(on) do { (void)(on); } while (0)
 #endif

@@ -45,15 +45,18 @@ __global__ void UHC_STEP_BOUNDS(EPB, Real)
 k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict__ obs, float *__restrict__ rew, float *__restrict__ cinfo,
            int *__restrict__ fail, int *__restrict__ end, float *__restrict__ pct, float *__restrict__ torque, const int *__restrict__ order) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_nvalid;
-    const int warp = threadIdx.x >> 5, slot = blockIdx.x * EPB + warp;
-    if (threadIdx.x == 0) s_nvalid = 0;
+#ifndef UHC_SYNC_SPLIT
+#define UHC_SYNC_SPLIT EPB            /* warps per alignment group (experiment knob; measured: the whole CTA is best) */
+#endif
+    __shared__ int s_nvalid[8];
+    const int warp = threadIdx.x >> 5, slot = blockIdx.x * EPB + warp, grp = warp / (UHC_SYNC_SPLIT);
+    if (threadIdx.x < 8) s_nvalid[threadIdx.x] = 0;
     stage_tables<Real, EPB>(ev, smem);
     // the warps of a CTA wait for each other every substep: `order` groups environments that needed a similar number of solver
     // iterations in the previous step into the same CTA (k_order_envs), outputs stay indexed by the environment id
     const int env = slot < ev.num_envs ? (order ? order[slot] : slot) : -1;
     const bool valid = env >= 0 && env_record_valid(ev, env);
-    if (valid && (threadIdx.x & 31) == 0) atomicAdd(&s_nvalid, 1);
+    if (valid && (threadIdx.x & 31) == 0) atomicAdd(&s_nvalid[grp], 1);
     __syncthreads();
     if (!valid) {   // no work (grid tail) or a stale / never-reset env record: flagged outputs, and the warp is not counted in the substep barrier
         if (env >= 0) env_step_invalid<Real, float>(ev, obs ? obs + (size_t)env * ev.cfg.obs_dim : nullptr, rew ? rew + env : nullptr, cinfo ? cinfo + (size_t)env * 5 : nullptr,
@@ -61,7 +64,7 @@ k_env_step(EngineView<Real> ev, const float *__restrict__ act, float *__restrict
         return;
     }
     Work<Real> &w = reinterpret_cast<Work<Real> *>(smem)[warp];
-    if ((threadIdx.x & 31) == 0) w.sync_threads = 32 * s_nvalid;
+    if ((threadIdx.x & 31) == 0) { w.sync_threads = 32 * s_nvalid[grp]; w.sync_id = 1 + grp; }
     state_mbar_init(w);            // mbarrier of this warp's bulk-async (TMA) state load
     env_step_warp<Real, float>(ev, env, w, act + (size_t)env * ev.cfg.act_dim, obs ? obs + (size_t)env * ev.cfg.obs_dim : nullptr, rew ? rew + env : nullptr,
                                cinfo ? cinfo + (size_t)env * 5 : nullptr, fail ? fail + env : nullptr, end ? end + env : nullptr,
