@@ -93,7 +93,10 @@ __device__ __forceinline__ void stage_store(float *stg, float *__restrict__ dst,
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, STAGES * STAGE_BYTES <= 100 * 1024 ? 2 : 1)
+#ifndef UHC_TC_MINB
+#define UHC_TC_MINB (STAGES * STAGE_BYTES <= 100 * 1024 ? 2 : 1)     /* resident CTAs per SM the register budget is cut for (experiment knob) */
+#endif
+__global__ void __launch_bounds__(NTHREADS, UHC_TC_MINB)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
             __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act, int ksplit) {
     extern __shared__ uint8_t smem_raw[];
