@@ -22,7 +22,7 @@ extern "C" {
 #define UHC_OBS_DIM 657
 #define UHC_ACT_DIM 105       /* action width of the default configuration (implicit residual force + meta-PD) */
 #define UHC_MAX_ACT_DIM 315   /* explicit residual force + meta-PD */
-#define UHC_MAX_OBS_DIM 784   /* obs_v 1 (get_full_obs_v1) */
+#define UHC_OBS_DIM_V1 784    /* obs_v 1 (get_full_obs_v1); obs_v 3 is UHC_OBS_DIM * fut_frames */
 #define UHC_EX_SIZE 576   /* expert frame record: qpos76 qvel75 wbpos72 wbquat96 bquat96 bangvel72 ee_wpos15 body_com72 (com = its first 3) pad2 */
 #define UHC_BODYF 20
 
@@ -60,12 +60,16 @@ typedef struct {
     unsigned long long reset_seed;
     double reactive_rate;   /* cfg.reactive_rate (copycat_config.py:99, default 0.3) */
     /* cfg.residual_force_mode (copycat_config.py:105-109, humanoid_im.py:231-243): 0 = "implicit" (root wrench, 6 action dims),
-     * 1 = "explicit" (contact point + force + torque per body through mj_applyFT, 9 x 24 action dims; reward world_rfc_explicit).
+     * 1 = "explicit" (contact point + force + torque per body through mj_applyFT, 9 x 24 action dims; reward world_rfc_explicit),
+     * 2 = cfg.residual_force false (no residual-force dims in the action, nothing applied, the reward's residual-force term is 0).
      * The action row is [69 joint targets | residual-force dims | 30 meta-PD scales when meta_pd]: uhc_engine_act_dim() gives its width. */
     int rfc_mode;
     int vf_slot[UHC_NB];    /* explicit mode: residual-force slot of body b (the reference orders the slots by SMPL_BONE_ORDER_NAMES, smpl_parser.py:11-36) */
     int obs_v;              /* cfg.obs_v (copycat_config.py:88): 2 = get_full_obs_v2 (657 dims, humanoid_im.py:419-503), 1 = get_full_obs_v1 (784 dims, :323-417);
+                             * 3 = get_full_obs_v3 (:505-513): fut_frames v2 blocks against the expert frames cur_t + 1 + i * fut_skip (657 * fut_frames dims);
                              * 0 is read as 2.  uhc_engine_obs_dim() gives the row width of every obs buffer. */
+    int fut_frames, fut_skip;   /* cfg.fut_frames / cfg.skip of obs_v 3 (both default to 10 when <= 0, as cc_cfg.get does) */
+    int no_shape;               /* != 0: cfg.has_shape false -- the v2 block carries no shape vector (640 dims instead of 657, humanoid_im.py:499-500) */
 } UhcEnvCfg;
 
 const char *uhc_last_error(void);

@@ -154,16 +154,21 @@ class Env:
         """residual_force_mode "explicit" (per-body contact point / force / torque, action dim 69 + 216 + 30) or "implicit" (root wrench, 105)"""
         names = [str(n) for n in self.m.z["body_names"]]
         vf_body = np.array([names.index(n) for n in self.SMPL_BONE_ORDER], dtype=np.int32)
-        lib().or_env_set_rfc_mode(self.h, C.c_int(int(bool(explicit))), vf_body.ctypes.data_as(C.POINTER(C.c_int)))
+        mode = 2 if explicit in (2, "none", None) else int(bool(explicit))         # "none": cfg.residual_force false (no residual-force dims)
+        lib().or_env_set_rfc_mode(self.h, C.c_int(mode), vf_body.ctypes.data_as(C.POINTER(C.c_int)))
         self.vf_body = vf_body
+
+    def set_has_shape(self, has_shape):
+        lib().or_env_set_has_shape(self.h, C.c_int(int(bool(has_shape))))
 
     @property
     def action_dim(self):
         return lib().or_env_action_dim(self.h)
 
-    def set_obs_v(self, obs_v):
-        """cfg.obs_v: 2 (default, 657 dims) or 1 (get_full_obs_v1, 784 dims; needs expert["body_com"])"""
+    def set_obs_v(self, obs_v, fut_frames=10, skip=10):
+        """cfg.obs_v: 2 (default, 657 dims), 1 (get_full_obs_v1, 784 dims; needs expert["body_com"]) or 3 (get_full_obs_v3: fut_frames v2 blocks)"""
         self._obs_v = int(obs_v)
+        lib().or_env_set_future(self.h, C.c_int(int(fut_frames)), C.c_int(int(skip)))
         bc = getattr(self, "_body_com", None)
         assert self._obs_v != 1 or bc is not None, "obs_v 1 needs expert['body_com']"
         lib().or_env_set_obs_v(self.h, C.c_int(self._obs_v), _p(bc) if bc is not None else None)

@@ -444,7 +444,10 @@ typedef struct {
     int rfc_mode;                     /* 0 = implicit root wrench (6 action dims), 1 = explicit per-body forces (cfg.residual_force_mode, humanoid_im.py:231-243) */
     int vf_dim;                       /* action dims of the residual force: 6, or 9 per body x 24 bodies */
     int vf_body[NB];                  /* explicit: model body of residual-force slot i (vf_bodies = SMPL_BONE_ORDER_NAMES, humanoid_im.py:236-237) */
-    int obs_v;                        /* cfg.obs_v: 2 = get_full_obs_v2 (657 with the shape vector), 1 = get_full_obs_v1 (784: + per-body COM blocks, no shape) */
+    int obs_v;                        /* cfg.obs_v: 2 = get_full_obs_v2 (657 with the shape vector), 1 = get_full_obs_v1 (784: + per-body COM blocks, no shape),
+                                         3 = get_full_obs_v3 (fut_frames v2 blocks against the expert frames cur_t + 1 + i * skip, humanoid_im.py:505-513) */
+    int fut_frames, fut_skip, obs_dt; /* obs_dt: the delta_t of the v2 block being written */
+    int no_shape;                     /* cfg.has_shape false: the v2 block has no shape vector (640 dims) */
 } OrEnv;
 
 OrEnv *or_env_create(OrModel *m) {
@@ -455,18 +458,21 @@ OrEnv *or_env_create(OrModel *m) {
     double w[5] = {0.3, 0.1, 0.45, 0.1, 0.05}, k[5] = {2.0, 0.005, 5.0, 100.0, 1.0};
     memcpy(e->w, w, 40); memcpy(e->k, k, 40);
     e->rfc_mode = 0; e->vf_dim = 6; for (int b = 0; b < NB; b++) e->vf_body[b] = b;
-    e->obs_v = 2;
+    e->obs_v = 2; e->fut_frames = 10; e->fut_skip = 10; e->obs_dt = 0;
     return e;
 }
 /* residual_force_mode (copycat_config.py:105-109): explicit = contact point + force + torque per body (residual_force_torque = True,
    residual_force_bodies = "all", residual_force_bodies_num = 1: the released uhc_explicit.yml); action = [69 joint targets | vf | 30 meta-PD] */
 void or_env_set_rfc_mode(OrEnv *e, int explicit_mode, const int *vf_body) {
-    e->rfc_mode = explicit_mode ? 1 : 0; e->vf_dim = explicit_mode ? 9*NB : 6;
+    e->rfc_mode = explicit_mode == 1 ? 1 : (explicit_mode == 2 ? 2 : 0); e->vf_dim = e->rfc_mode == 1 ? 9*NB : (e->rfc_mode == 2 ? 0 : 6);   /* 2: cfg.residual_force false */
     if (vf_body) memcpy(e->vf_body, vf_body, sizeof e->vf_body);
 }
 int or_env_action_dim(const OrEnv *e) { return NU + e->vf_dim + (e->meta_pd ? 30 : 0); }
-void or_env_set_obs_v(OrEnv *e, int obs_v, const double *body_com) { e->obs_v = obs_v == 1 ? 1 : 2; e->ex.body_com = body_com; }
-int or_env_obs_dim(const OrEnv *e) { return e->obs_v == 1 ? 784 : 657; }
+void or_env_set_obs_v(OrEnv *e, int obs_v, const double *body_com) { e->obs_v = (obs_v == 1 || obs_v == 3) ? obs_v : 2; e->ex.body_com = body_com; }
+void or_env_set_future(OrEnv *e, int fut_frames, int skip) { e->fut_frames = fut_frames > 0 ? fut_frames : 10; e->fut_skip = skip > 0 ? skip : 10; }
+void or_env_set_has_shape(OrEnv *e, int has_shape) { e->no_shape = !has_shape; }
+static int obs_block_dim(const OrEnv *e) { return e->no_shape ? 640 : 657; }
+int or_env_obs_dim(const OrEnv *e) { return e->obs_v == 1 ? 784 : (e->obs_v == 3 ? obs_block_dim(e)*e->fut_frames : obs_block_dim(e)); }
 void or_env_free(OrEnv *e) { if (e) { or_data_free(e->d); free(e); } }
 OrData *or_env_data(OrEnv *e) { return e->d; }
 void or_env_set_expert(OrEnv *e, int len, const double *qpos, const double *qvel, const double *wbpos, const double *wbquat,
@@ -565,14 +571,21 @@ static void or_rfc_explicit(OrEnv *e, const double *ctrl) {
 
 /* get_full_obs_v2 (humanoid_im.py:419-503) and get_full_obs_v1 (:323-417), obs_coord = "root", obs_vel = "full".  v1 = v2 with two more blocks
    (per-body COM relative to the root, COM difference to the expert's body_com) between the joint-position blocks and the quaternions, and no shape vector. */
-void or_obs_v2(const OrEnv *e, double *obs) {
+static void or_obs_block(const OrEnv *e, double *obs);
+void or_obs_v2(const OrEnv *ec, double *obs) {     /* get_obs: one block, or the v3 stack of v2 blocks */
+    OrEnv *e = (OrEnv *)ec;
+    if (e->obs_v != 3) { e->obs_dt = 0; or_obs_block(e, obs); return; }
+    for (int f = 0; f < e->fut_frames; f++) { e->obs_dt = f*e->fut_skip; or_obs_block(e, obs + obs_block_dim(e)*f); }
+    e->obs_dt = 0;
+}
+static void or_obs_block(const OrEnv *e, double *obs) {
     const OrData *d = e->d; double qpos[NQ], qvel[NV], R[9], t[3];
     memcpy(qpos, d->qpos, sizeof qpos); memcpy(qvel, d->qvel, sizeof qvel);
     q2mat(qpos+3, R); mtv(R, qvel, t); memcpy(qvel, t, 24);                       /* :425 */
     double crq[4], hq[4], hqi[4];
     remove_base_rot(e, qpos+3, crq); heading_q(crq, hq);
     int o = 0; memcpy(obs+o, hq, 32); o += 4;
-    int ind = ex_index(e, e->cur_t + 1);
+    int ind = ex_index(e, e->cur_t + 1 + e->obs_dt);
     const double *tq = e->ex.qpos + NQ*ind, *twq = e->ex.wbquat + 96*ind, *tjp = e->ex.wbpos + 72*ind;
     double trq[4], dh[4], diff[NQ], ci[4];
     remove_base_rot(e, tq+3, trq);
@@ -606,7 +619,7 @@ void or_obs_v2(const OrEnv *e, double *obs) {
     o += 96;
     for (int b = 0; b < NB; b++) { const double *cq = use_target ? twq+4*b : d->xquat[b]; double iq[4]; qinv(cq, iq); double n = e->obs_v == 1 ? 1.0 : sqrt(cq[0]*cq[0]+cq[1]*cq[1]+cq[2]*cq[2]+cq[3]*cq[3]); for (int k = 0; k < 4; k++) iq[k] *= n; /* v2: inverse_batch divides by |q|, not |q|^2; v1: quaternion_inverse (:411) */ qmul(iq, twq+4*b, obs+o+4*b); }
     o += 96;
-    if (e->obs_v != 1) { memcpy(obs+o, e->ex.shape_obs, 17*8); o += 17; }
+    if (e->obs_v != 1 && !e->no_shape) { memcpy(obs+o, e->ex.shape_obs, 17*8); o += 17; }
 }
 
 static void rot_from_quat(const double *q, double *rv) { /* transformation.py:362-372 */
@@ -626,13 +639,13 @@ double or_reward(const OrEnv *e, const double *action, double *cinfo) { /* rewar
         double a = acos(c)*w; pose2 += a*a;
         qinv(e->prev_bquat+4*b, iq); qmul(cur_bq+4*b, iq, dq); rot_from_quat(dq, rv);
         /* world_rfc_implicit weights the angular-velocity error by jpos_diffw (reward_function.py:50-51); world_rfc_explicit does not (:253-341) */
-        for (int k = 0; k < 3; k++) { double dv = (rv[k]/dt - e_bav[3*b+k])*(e->rfc_mode ? 1.0 : e->m->diffw[b]); vel2 += dv*dv; }
+        for (int k = 0; k < 3; k++) { double dv = (rv[k]/dt - e_bav[3*b+k])*(e->rfc_mode == 1 ? 1.0 : e->m->diffw[b]); vel2 += dv*dv; }
     }
     for (int i = 0; i < 5; i++) for (int k = 0; k < 3; k++) { double x = d->xpos[e->m->ee[i]][k] - e_ee[3*i+k]; ee2 += x*x; }
     for (int k = 0; k < 3; k++) { double x = d->xipos[0][k] - e_com[k]; com2 += x*x; }
-    if (!e->rfc_mode) for (int i = 0; i < 6; i++) vf2 += action[NU+i]*action[NU+i];
-    else for (int i = 0; i < NB; i++) for (int k = 3; k < 9; k++) vf2 += action[NU+9*i+k]*action[NU+9*i+k];   /* force + torque part of every body's slot (:321-327) */
-    cinfo[0] = exp(-e->k[0]*pose2); cinfo[1] = exp(-e->k[1]*vel2); cinfo[2] = exp(-e->k[2]*ee2); cinfo[3] = exp(-e->k[3]*com2); cinfo[4] = exp(-e->k[4]*vf2);
+    if (e->rfc_mode == 0) for (int i = 0; i < 6; i++) vf2 += action[NU+i]*action[NU+i];
+    else if (e->rfc_mode == 1) for (int i = 0; i < NB; i++) for (int k = 3; k < 9; k++) vf2 += action[NU+9*i+k]*action[NU+9*i+k];   /* force + torque part of every body's slot (:321-327) */
+    cinfo[0] = exp(-e->k[0]*pose2); cinfo[1] = exp(-e->k[1]*vel2); cinfo[2] = exp(-e->k[2]*ee2); cinfo[3] = exp(-e->k[3]*com2); cinfo[4] = e->rfc_mode == 2 ? 0.0 : exp(-e->k[4]*vf2);   /* residual_force off: vf_reward = 0.0 (reward_function.py:68-72) */
     double r = 0, ws = 0; for (int i = 0; i < 5; i++) { r += e->w[i]*cinfo[i]; ws += e->w[i]; }
     return r/ws;
 }
@@ -659,7 +672,7 @@ int or_env_step(OrEnv *e, const double *action, double *obs, int *fail, int *end
         double tq[NU];
         or_compute_torque(e, action, i, tq);
         for (int j = 0; j < NU; j++) { if (tq[j] > e->m->tlim[j]) tq[j] = e->m->tlim[j]; if (tq[j] < -e->m->tlim[j]) tq[j] = -e->m->tlim[j]; d->ctrl[j] = tq[j]; e->torque[i][j] = tq[j]; }
-        if (e->rfc_mode) or_rfc_explicit(e, action); else or_rfc_implicit(e, action);
+        if (e->rfc_mode == 1) or_rfc_explicit(e, action); else if (e->rfc_mode == 0) or_rfc_implicit(e, action);
         or_step(e->m, d);
     }
     e->cur_t += 1;

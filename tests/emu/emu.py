@@ -18,7 +18,7 @@ class UhcEnvCfg(C.Structure):
                 ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
                 ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double),
                 ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reactive_v", C.c_int), ("reset_seed", C.c_ulonglong),
-                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24), ("obs_v", C.c_int)]
+                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24), ("obs_v", C.c_int), ("fut_frames", C.c_int), ("fut_skip", C.c_int), ("no_shape", C.c_int)]
 
 
 def default_cfg(precision=32, **kw):
@@ -70,7 +70,8 @@ class Emu:
         self.model = model or HumanoidModel()
         self._ms = self.model.host_struct()
         self._cfg = default_cfg(precision, **cfg)
-        self.obs_dim = 784 if self._cfg.obs_v == 1 else 657
+        blk = 640 if self._cfg.no_shape else 657
+        self.obs_dim = 784 if self._cfg.obs_v == 1 else (blk * (self._cfg.fut_frames or 10) if self._cfg.obs_v == 3 else blk)
         self.h = C.c_void_p(self.lib.emu_create(C.byref(self._ms), C.byref(self._cfg), C.c_int(num_envs), C.c_int(precision)))
 
     def load_clips(self, experts, shapes):

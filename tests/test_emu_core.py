@@ -184,3 +184,22 @@ def test_joint_limit_rows_match_oracle_fp64(with_contacts):
         assert r["ncon"] == d.ncon
         assert np.abs(r["qacc"] - d.qacc).max() < 2e-6 * max(1.0, np.abs(d.qacc).max()), (case, d.ncon, nviol[-1], np.abs(r["qacc"] - d.qacc).max())
     assert len(nviol) >= 4 and min(nviol) >= 4
+
+
+@pytest.mark.parametrize("prec,tol_q,tol_o", [(64, 1e-10, 1e-8), (32, 1e-4, 2e-3)])
+def test_obs_v3_no_shape_no_residual_force_matches_reference_golden(golden_dir, prec, tol_q, tol_o):
+    """config/meta_pd/copycat_35.yml at the env level (obs_v 3 = 5 x 640, 99-wide actions without residual force): kernel source vs the reference's Python"""
+    g = np.load(os.path.join(golden_dir, "env_sway_obsv3_noise.npz"))
+    z = np.load(os.path.join(golden_dir, "expert_sway.npz"))
+    ex = {k: z[k] for k in z.files}
+    so = np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+    e = Emu(prec, obs_v=3, fut_frames=5, fut_skip=10, no_shape=1, rfc_mode=2)
+    e.load_clips([ex], [so])
+    obs0 = e.reset()
+    assert obs0.shape == (3200,) and np.abs(obs0 - g["obs0"]).max() < max(tol_o * 1e-2, 1e-12)
+    for t in range(len(g["reward"])):
+        obs, r, done, info = e.step(g["action"][t])
+        st, _ = e.state()
+        assert np.abs(st[:76] - g["qpos"][t]).max() < tol_q, t
+        assert np.abs(obs - g["obs"][t]).max() < tol_o, t
+        assert abs(r - g["reward"][t]) < tol_o and info["c_info"][4] == 0.0

@@ -70,3 +70,20 @@ def test_explicit_residual_force_train_iteration(golden_dir):
     assert log["num_steps"] == 8 * 64 and np.isfinite(log["avg_reward"]) and np.isfinite(log["surr_loss"]) and np.isfinite(log["value_loss"])
     assert not torch.equal(w0, ag.policy.flat) and torch.isfinite(ag.policy.flat).all()
     assert ag.engine.counters["invalid_env_steps"] == 0
+
+
+def test_obs_v3_train_iteration(golden_dir):
+    """obs_v 3 (3 future frames -> 1920-wide observations without the shape vector), no residual force (99-wide actions) through uhc_rollout / uhc_ppo_update"""
+    import torch
+    from uhc_b200.agent import BatchedAgent
+    z = np.load(os.path.join(golden_dir, "expert_sway.npz"))
+    ex = {k: z[k] for k in z.files}
+    so = np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+    ag = BatchedAgent(64, [ex], [so], policy_hsize=(128, 64), value_hsize=(128, 64), htype="relu", num_optim_epoch=2, t_min=15, t_max=60, obs_v=3, fut_frames=3,
+                      fut_skip=10, has_shape=False, rfc_mode="none")
+    assert ag.obs_dim == 1920 and ag.act_dim == 99
+    w0 = ag.policy.flat.clone()
+    log = ag.optimize_policy(8)
+    torch.cuda.synchronize()
+    assert log["num_steps"] == 8 * 64 and np.isfinite(log["avg_reward"]) and np.isfinite(log["surr_loss"]) and np.isfinite(log["value_loss"])
+    assert not torch.equal(w0, ag.policy.flat) and torch.isfinite(ag.policy.flat).all()

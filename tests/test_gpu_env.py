@@ -363,3 +363,26 @@ def test_joint_limit_rows_match_oracle(golden_dir, precision, tol_q):
             break
     assert t >= 5 and worst < tol_q, (t, worst)
     eng.close()
+
+
+@pytest.mark.parametrize("precision,tol_q,tol_o", [(64, 1e-8, 2e-5), (32, 1e-3, 5e-3)])
+def test_obs_v3_no_shape_no_residual_force_matches_reference_trace(golden_dir, precision, tol_q, tol_o):
+    """config/meta_pd/copycat_35.yml at the env level through the C ABI: obs_v 3 (five 640-wide v2 blocks ten frames apart, humanoid_im.py:505-513), has_shape
+    false, residual_force false (99-wide actions, residual-force reward term 0)."""
+    import torch
+    from uhc_b200.engine import Engine
+    g = np.load(os.path.join(golden_dir, "env_sway_obsv3_noise.npz"))
+    ex, so = _expert(golden_dir, "sway")
+    eng = Engine(2, precision=precision, obs_v=3, fut_frames=5, fut_skip=10, has_shape=False, rfc_mode="none")
+    assert eng.obs_dim == 3200 == g["obs"].shape[1] and eng.act_dim == 99 == g["action"].shape[1]
+    eng.load_clips([ex], [so])
+    obs0 = eng.reset().cpu().numpy()
+    assert np.abs(obs0[1] - g["obs0"]).max() < 1e-5
+    for t in range(len(g["reward"])):
+        a = torch.tensor(np.tile(g["action"][t], (2, 1)), dtype=torch.float32, device="cuda")
+        o, r, c, f, en, pct = eng.step(a)
+        torch.cuda.synchronize()
+        assert np.abs(eng.get_state(1)["qpos"] - g["qpos"][t]).max() < tol_q, t
+        assert np.abs(o[1].cpu().numpy() - g["obs"][t]).max() < tol_o, t
+        assert abs(float(r[1]) - g["reward"][t]) < tol_o and float(c[1, 4]) == 0.0
+    eng.close()

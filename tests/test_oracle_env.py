@@ -82,3 +82,20 @@ def test_obs_v1_no_meta_pd_trace_matches_reference_python(golden_dir):
         np.testing.assert_allclose(obs, g["obs"][t], rtol=0, atol=1e-5 * tol, err_msg=f"obs t={t}")
         assert abs(r - g["reward"][t]) < 1e-6 * tol
         assert info["fail"] == bool(g["fail"][t]) and info["end"] == bool(g["end"][t])
+
+
+def test_obs_v3_no_shape_no_residual_force_trace_matches_reference_python(golden_dir):
+    """config/meta_pd/copycat_35.yml at the env level: obs_v 3 (get_full_obs_v3, humanoid_im.py:505-513: five v2 blocks ten frames apart (no `skip` key: cc_cfg.get("skip", 10))), has_shape false
+    (640-wide blocks), residual_force false (99-wide actions: 69 joint targets + 30 meta-PD; the reward's residual-force term is 0)."""
+    g = np.load(os.path.join(golden_dir, "env_sway_obsv3_noise.npz"))
+    ex, so = load_expert(golden_dir, "sway")
+    env = O.Env(O.Model(), ex, so)
+    env.set_rfc_mode("none"); env.set_has_shape(False); env.set_obs_v(3, fut_frames=5, skip=10)
+    assert env.action_dim == 99 == g["action"].shape[1] and env.obs_dim == 3200 == g["obs"].shape[1]
+    np.testing.assert_allclose(env.reset(), g["obs0"], rtol=0, atol=1e-9)
+    for t in range(len(g["reward"])):
+        obs, r, done, info = env.step(g["action"][t])
+        np.testing.assert_allclose(env.d.qpos, g["qpos"][t], rtol=0, atol=1e-7, err_msg=f"qpos t={t}")
+        np.testing.assert_allclose(obs, g["obs"][t], rtol=0, atol=1e-5, err_msg=f"obs t={t}")
+        np.testing.assert_allclose(info["c_info"], g["c_info"][t], rtol=0, atol=1e-6)
+        assert abs(r - g["reward"][t]) < 1e-6 and info["c_info"][4] == 0.0

@@ -397,6 +397,11 @@ def main():
         from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
         dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
         gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 40, "noise", out_tag="sway_implicit", save_expert=False)
+    if "obsv3" in what:          # config/meta_pd/copycat_35.yml: obs_v 3 = five v2 blocks, ten frames apart (the yaml has no `skip` key) (humanoid_im.py:505-513); relu nets, meta-PD, implicit RFC
+        cfg = H.make_cfg("copycat_35")
+        from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
+        dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
+        gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 12, "noise", out_tag="sway_obsv3", save_expert=False)
     if "reactive" in what:
         cfg = H.make_cfg()
         from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle

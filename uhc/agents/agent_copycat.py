@@ -73,16 +73,16 @@ class AgentCopycat:
             if not dist.is_initialized():
                 dist.init_process_group("nccl")
             sync = make_nccl_grad_sync(world)
-        assert cfg.obs_v in (1, 2) and cfg.actor_type in ("gauss", "mcp") and cfg.reward_id in reward_func, \
-            "the B200 engine implements obs_v 1 | 2, the gauss and mcp actors, world_rfc_implicit / world_rfc_explicit (obs_v 3/5/6 etc.: SURVEY.md section 8f, next)"
+        assert cfg.obs_v in (1, 2, 3) and cfg.actor_type in ("gauss", "mcp") and cfg.reward_id in reward_func, \
+            "the B200 engine implements obs_v 1 | 2 | 3, the gauss and mcp actors, world_rfc_implicit / world_rfc_explicit (obs_v 5/6 etc.: SURVEY.md section 8f, next)"
         assert cfg.get("obs_vel", "full") == "full" and cfg.get("obs_coord", "root") == "root" and not cfg.get("obs_phase", False), "obs_vel full / obs_coord root / no phase only"
         if cfg.obs_v == 1:
             assert not cfg.get("has_shape", False), "obs_v 1 carries no shape vector (has_shape: false in config/release/uhc_implicit.yml)"
         # variants the batched engine does not implement must not be accepted silently
         assert cfg.fix_std, "log_std is not a trained parameter in this engine (fix_std: true in every released config)"
         assert cfg.get("env_term_body", "body") == "body", "env_term_body: only 'body' (calc_body_diff) is implemented"
-        rfc_mode = cfg.get("residual_force_mode", "implicit")
-        assert cfg.residual_force and rfc_mode in ("implicit", "explicit"), "residual_force_mode: implicit | explicit"
+        rfc_mode = cfg.get("residual_force_mode", "implicit") if cfg.residual_force else "none"     # residual_force: false -> no residual-force dims (humanoid_im.py:231-243)
+        assert rfc_mode in ("implicit", "explicit", "none"), "residual_force_mode: implicit | explicit"
         if rfc_mode == "explicit":      # the kernel restates the release settings of the explicit mode (config/release/uhc_explicit.yml)
             assert cfg.get("residual_force_bodies", "all") == "all" and cfg.get("residual_force_torque", True) and int(cfg.get("residual_force_bodies_num", 1)) == 1 \
                 and not cfg.get("residual_contact_only", False) and not cfg.get("residual_contact_projection", False), \
@@ -98,7 +98,8 @@ class AgentCopycat:
             model=self.model_tables, base_rot=cfg.data_specs.get("base_rot", [0.7071, 0.7071, 0.0, 0.0]), rfc_scale=cfg.residual_force_scale,
             rfc_lim=cfg.residual_force_lim, rfc_rate=0.0 if cfg.rfc_decay else 1.0, body_diff_thresh=cfg.get("body_diff_thresh", 0.5),
             meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=kk, rfc_mode=rfc_mode,
-            obs_v=int(cfg.obs_v), actor_type=cfg.actor_type, num_primitive=int(cfg.get("num_primitive", 8)), composer_dim=tuple(cfg.get("composer_dim", [300, 200])),
+            obs_v=int(cfg.obs_v), fut_frames=int(cfg.get("fut_frames", 10)), fut_skip=int(cfg.get("skip", 10)),
+            has_shape=bool(cfg.get("has_shape", False)) and bool(cfg.get("has_shape_obs", True)), actor_type=cfg.actor_type, num_primitive=int(cfg.get("num_primitive", 8)), composer_dim=tuple(cfg.get("composer_dim", [300, 200])),
             reactive_v=int(cfg.get("reactive_v", 0)), reactive_rate=float(cfg.get("reactive_rate", 0.3)))
         self.policy_net, self.value_net, self.running_state = self.agent.policy, self.agent.value, self.agent.running_state
         self.state_dim, self.action_dim = self.agent.obs_dim, self.agent.act_dim
@@ -275,7 +276,9 @@ class AgentCopycat:
         return dict(base_rot=cfg.data_specs.get("base_rot", [0.7071, 0.7071, 0.0, 0.0]), rfc_scale=cfg.residual_force_scale, rfc_lim=cfg.residual_force_lim,
                     rfc_rate=0.0 if cfg.rfc_decay else 1.0, body_diff_thresh=cfg.get("body_diff_thresh_test" if test else "body_diff_thresh", 0.5),
                     meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, auto_reset=0 if test else 1,
-                    rfc_mode=cfg.get("residual_force_mode", "implicit"), obs_v=int(cfg.obs_v),
+                    rfc_mode=cfg.get("residual_force_mode", "implicit") if cfg.residual_force else "none", obs_v=int(cfg.obs_v),
+                    fut_frames=int(cfg.get("fut_frames", 10)), fut_skip=int(cfg.get("skip", 10)),
+                    has_shape=bool(cfg.get("has_shape", False)) and bool(cfg.get("has_shape_obs", True)),
                     w=[rw.get(k, d) for k, d in (("w_p", 0.6), ("w_v", 0.1), ("w_e", 0.2), ("w_c", 0.1), ("w_vf", 0.0))],
                     k=[rw.get(k, d) for k, d in (("k_p", 2), ("k_v", 0.005), ("k_e", 20), ("k_c", 1000), ("k_vf", 1))])
 

@@ -76,7 +76,9 @@ class HumanoidEnv:
                              rfc_scale=cfg.residual_force_scale, rfc_lim=cfg.residual_force_lim, rfc_rate=0.0 if cfg.rfc_decay else 1.0,
                              body_diff_thresh=cfg.get("body_diff_thresh", 0.5) if mode == "train" else cfg.get("body_diff_thresh_test", 0.5),
                              meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=k,
-                             rfc_mode=cfg.get("residual_force_mode", "implicit"), obs_v=int(cfg.get("obs_v", 2)))
+                             rfc_mode=cfg.get("residual_force_mode", "implicit") if cfg.residual_force else "none", obs_v=int(cfg.get("obs_v", 2)),
+                             fut_frames=int(cfg.get("fut_frames", 10)), fut_skip=int(cfg.get("skip", 10)),
+                             has_shape=bool(cfg.get("has_shape", False)) and bool(cfg.get("has_shape_obs", True)))
         self.dt = self.model_tables.dt * 15
         # set_action_spaces (humanoid_im.py:226-255): implicit = 6 residual-force dims, explicit = 9 per body x 24 bodies
         explicit = cfg.get("residual_force_mode", "implicit") == "explicit"

@@ -88,6 +88,16 @@ UHC_DEV Model<Real> model_for_clip(const EngineView<Real> &ev, int clip) {
     return m;
 }
 
+// get_obs (humanoid_im.py:269-288): obs v1 / v2 against the expert frame t_next, or v3 = the v2 block repeated for fut_frames future frames
+// t_next + i * skip (:505-513; expert_frame clamps past the end of the slice like get_expert_index)
+template <class Real, class ObsT>
+UHC_DEV void write_obs(const EngineView<Real> &ev, const Work<Real> &w, int clip, int start, int len, int t_next, ObsT *obs) {
+    const Real *shape = ev.clip_shape + 17 * clip;
+    if (w.cfg.obs_v == 3) {
+        for (int f = 0; f < w.cfg.fut_frames; ++f) obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, t_next + f * w.cfg.fut_skip), shape, obs + (size_t)f * w.cfg.obs_block);
+    } else obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, t_next), shape, obs);
+}
+
 // ---- state record <-> work set.  GPU: the head block (q v aw C Ib S, ST_BLOCK Reals) travels as ONE bulk-async copy (TMA engine:
 // cp.async.bulk global -> shared completing on this warp's mbarrier; shared -> global as a bulk group), the pose arrays as 16-byte
 // vector stores.  Host emulation: plain copies.
@@ -191,7 +201,7 @@ UHC_DEV void env_reset_warp(const EngineView<Real> &ev, int env, Work<Real> &w, 
     for (int i = lane; i < 96; i += 32) { const Real v = (i & 3) == 0 ? Real(1) : Real(0); st[ST_BQUAT + i] = v; st[ST_PBQUAT + i] = v; }
     if (lane == 0) { is[SI_CUR_T] = 0; is[SI_CLIP] = clip; is[SI_START] = start; is[SI_LEN] = len; is[SI_NEWTON] = iters; is[SI_NCON] = w.ncon; }
     LANES_END
-    if (obs) obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, 1), ev.clip_shape + 17 * clip, obs);
+    if (obs) write_obs(ev, w, clip, start, len, 1, obs);
     LANES_BEGIN
     for (int i = lane; i < NV; i += 32) w.aw[i] = 0;
     LANES_END
@@ -212,7 +222,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     const bool explicit_rf = ev.cfg.rfc_mode == 1;
     LANES_BEGIN
     for (int i = lane; i < NU; i += 32) w.act[i] = (Real)action[i];
-    if (lane < 6) w.act[NU + lane] = explicit_rf ? Real(0) : (Real)action[NU + lane];
+    if (lane < 6) w.act[NU + lane] = ev.cfg.rfc_mode == 0 ? (Real)action[NU + lane] : Real(0);
     if (lane < 2 * NSUB) w.act[NU + 6 + lane] = ev.cfg.meta_pd ? (Real)action[NU + ev.cfg.vf_dim + lane] : Real(0);
     LANES_END
     if (explicit_rf) restore_stale_pose(w, st + ST_XPOS, st + ST_XQUAT);
@@ -254,7 +264,7 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     const int overflow = w.con_overflow;
     if (overflow) fail = 1;
     const int end = (cur_t >= ev.cfg.env_episode_len) || (cur_t >= len + ev.cfg.trail_steps - 1);
-    if (obs) obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, cur_t + 1), ev.clip_shape + 17 * clip, obs);
+    if (obs) write_obs(ev, w, clip, start, len, cur_t + 1, obs);
     LANES_BEGIN
     if (lane == 0) {
         is[SI_CUR_T] = cur_t; is[SI_NEWTON] = iters; is[SI_NCON] = maxcon; is[SI_FLAGS] = overflow ? 1 : 0;

@@ -103,10 +103,12 @@ struct EnvCfg {
     int auto_reset, t_min, t_max, num_clips;      // in-kernel re-seeding of finished episodes (dataset_amass_single.py:172-253)
     unsigned long long reset_seed;
     int reactive_v; Real reactive_rate;           // reset_model's reactive_v = 1 branch (humanoid_im.py:1255-1271): start from the standing pose w.p. reactive_rate
-    // residual-force mode (cfg.residual_force_mode, humanoid_im.py:231-243): 0 = implicit root wrench (6 action dims), 1 = explicit per-body contact
-    // point / force / torque (9 dims x 24 bodies).  Action layout: [NU joint targets | vf_dim residual-force dims | 30 meta-PD scales if meta_pd]
+    // residual-force mode (cfg.residual_force / residual_force_mode, humanoid_im.py:231-243): 0 = implicit root wrench (6 action dims), 1 = explicit per-body
+    // contact point / force / torque (9 dims x 24 bodies), 2 = residual_force: false (no residual-force dims, no applied force, reward term 0).  Action layout: [NU joint targets | vf_dim residual-force dims | 30 meta-PD scales if meta_pd]
     int rfc_mode, vf_dim, act_dim;
-    int obs_v, obs_dim;                           // cfg.obs_v: 2 = get_full_obs_v2 (657), 1 = get_full_obs_v1 (784; config/release/uhc_implicit.yml)
+    int obs_v, obs_dim;                           // cfg.obs_v: 2 = get_full_obs_v2 (657), 1 = get_full_obs_v1 (784; config/release/uhc_implicit.yml),
+    int fut_frames, fut_skip;                     //   3 = get_full_obs_v3 (:505-513): fut_frames v2 blocks against the expert frames cur_t + 1 + i * skip
+    int has_shape, obs_block;                     // cfg.has_shape (:499-500): the v2 block ends with the 17 shape dims (657) or not (640); obs_block = its width
     signed char vf_slot[NB];                      // explicit: residual-force slot of body b (vf_bodies = SMPL_BONE_ORDER_NAMES, humanoid_im.py:236-237)
 };
 constexpr int VF_BODY_DIM = 9, MAX_ACT_DIM = NU + VF_BODY_DIM * NB + 30;
@@ -1312,7 +1314,7 @@ UHC_DEVNI int substep_dynamics(const Model<Real> &m, const EnvCfg<Real> &cfg, Wo
             Real fapp[6] = {0, 0, 0, 0, 0, 0};
             const bool explicit_rf = with_pd && cfg.rfc_mode == 1 && act_global != nullptr;
             if (explicit_rf) rfc_explicit(m, cfg, w, tp, act_global, w.as_);        // generalized force of the per-body residual forces (stale Jacobian) -> as_
-            else if (with_pd) rfc_implicit(cfg, w, fapp);
+            else if (with_pd && cfg.rfc_mode == 0) rfc_implicit(cfg, w, fapp);
             kin_rne_forward(m, w, tp);
             project_force(m, w, w.Fb, w.C, Real(1), (const Real *)nullptr);
             collide(m, w, tp);
@@ -1449,7 +1451,7 @@ UHC_DEVNI void obs_v2(const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *
         qmul(iq, ex1 + EX_WBQUAT + 4 * b, o2);
         for (int k = 0; k < 4; k++) { obs[oq + 4 * b + k] = (OutT)o1[k]; obs[oq + 96 + 4 * b + k] = (OutT)o2[k]; }
     }
-    if (cfg.obs_v != 1 && lane < 17) obs[640 + lane] = (OutT)shape_obs[lane];
+    if (cfg.obs_v != 1 && cfg.has_shape && lane < 17) obs[640 + lane] = (OutT)shape_obs[lane];
     LANES_END
 }
 
@@ -1496,7 +1498,7 @@ UHC_DEVNI void diff_and_reward(const Model<Real> &m, const EnvCfg<Real> &cfg, co
     if (explicit_rf) vf2 = WSUM(s_vf);
     else for (int i = 0; i < 6; i++) vf2 += w.act[NU + i] * w.act[NU + i];
     cinfo[0] = exp_(-cfg.k[0] * pose2); cinfo[1] = exp_(-cfg.k[1] * vel2); cinfo[2] = exp_(-cfg.k[2] * ee2);
-    cinfo[3] = exp_(-cfg.k[3] * com2); cinfo[4] = exp_(-cfg.k[4] * vf2);
+    cinfo[3] = exp_(-cfg.k[3] * com2); cinfo[4] = cfg.rfc_mode == 2 ? Real(0) : exp_(-cfg.k[4] * vf2);     // residual_force off: vf_reward = 0.0 (reward_function.py:68-72)
     Real r = 0, ws = 0;
     for (int i = 0; i < 5; i++) { r += cfg.w[i] * cinfo[i]; ws += cfg.w[i]; }
     *reward = r / ws;

@@ -160,9 +160,12 @@ template <class Real> static void fill_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) 
     c.newton_tol = (Real)h->newton_tol;
     c.auto_reset = h->auto_reset; c.t_min = h->t_min; c.t_max = h->t_max; c.reset_seed = h->reset_seed;
     c.reactive_v = h->reactive_v; c.reactive_rate = (Real)h->reactive_rate;
-    c.rfc_mode = h->rfc_mode == 1 ? 1 : 0; c.vf_dim = c.rfc_mode ? VF_BODY_DIM * NB : 6; c.act_dim = NU + c.vf_dim + (h->meta_pd ? 2 * NSUB : 0);
+    c.rfc_mode = (h->rfc_mode == 1 || h->rfc_mode == 2) ? h->rfc_mode : 0; c.vf_dim = c.rfc_mode == 1 ? VF_BODY_DIM * NB : (c.rfc_mode == 2 ? 0 : 6); c.act_dim = NU + c.vf_dim + (h->meta_pd ? 2 * NSUB : 0);
     for (int b = 0; b < NB; b++) c.vf_slot[b] = (signed char)((h->vf_slot[b] >= 0 && h->vf_slot[b] < NB) ? h->vf_slot[b] : b);
-    c.obs_v = h->obs_v == 1 ? 1 : 2; c.obs_dim = c.obs_v == 1 ? OBS_DIM_V1 : OBS_DIM;
+    c.obs_v = (h->obs_v == 1 || h->obs_v == 3) ? h->obs_v : 2;
+    c.fut_frames = h->fut_frames > 0 ? h->fut_frames : 10; c.fut_skip = h->fut_skip > 0 ? h->fut_skip : 10;     // cc_cfg.get("fut_frames", 10), get("skip", 10)
+    c.has_shape = h->no_shape ? 0 : 1; c.obs_block = c.has_shape ? OBS_DIM : OBS_DIM - 17;
+    c.obs_dim = c.obs_v == 1 ? OBS_DIM_V1 : (c.obs_v == 3 ? c.obs_block * c.fut_frames : c.obs_block);
 }
 template <class Real> static int build_view(UhcEngine *e, EngineView<Real> &ev, const UhcModelHost *m, const UhcEnvCfg *cfg) {
     Model<Real> &M = ev.model;
@@ -230,7 +233,7 @@ int uhc_engine_create(const UhcModelHost *model, const UhcEnvCfg *cfg, int num_e
         CK(cudaFuncSetAttribute(k_env_reset<double, EPB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem<double, EPB_D>()));
     }
     const size_t E = num_envs;
-    CK(cudaMalloc((void **)&e->d_act, E * MAX_ACT_DIM * 4)); CK(cudaMalloc((void **)&e->d_obs, E * MAX_OBS_DIM * 4)); CK(cudaMalloc((void **)&e->d_rew, E * 4));
+    CK(cudaMalloc((void **)&e->d_act, E * MAX_ACT_DIM * 4)); CK(cudaMalloc((void **)&e->d_obs, E * (size_t)(precision == 32 ? e->evf.cfg.obs_dim : e->evd.cfg.obs_dim) * 4)); CK(cudaMalloc((void **)&e->d_rew, E * 4));
     CK(cudaMalloc((void **)&e->d_cinfo, E * 5 * 4)); CK(cudaMalloc((void **)&e->d_pct, E * 4)); CK(cudaMalloc((void **)&e->d_fail, E * 4)); CK(cudaMalloc((void **)&e->d_end, E * 4));
     for (void *p : {(void *)e->d_act, (void *)e->d_obs, (void *)e->d_rew, (void *)e->d_cinfo, (void *)e->d_pct, (void *)e->d_fail, (void *)e->d_end}) e->allocs.push_back(p);
     *out = e;
@@ -278,7 +281,9 @@ int uhc_engine_set_cfg(UhcEngine *e, const UhcEnvCfg *cfg) {
     if (!e || !cfg) { g_err = "uhc_engine_set_cfg: null"; return -2; }
     CK(cudaSetDevice(e->device));
     const int old_tmax = e->precision == 32 ? e->evf.cfg.t_max : e->evd.cfg.t_max;
+    const int old_obs_dim = uhc_engine_obs_dim(e);
     if (e->precision == 32) { fill_cfg(e->evf.cfg, cfg); e->evf.cfg.num_clips = e->num_clips; } else { fill_cfg(e->evd.cfg, cfg); e->evd.cfg.num_clips = e->num_clips; }
+    if (uhc_engine_obs_dim(e) != old_obs_dim) { g_err = "uhc_engine_set_cfg: the observation width cannot change on a live engine (buffers are sized at creation)"; return -2; }
     if (cfg->t_max != old_tmax && e->clip_w.empty()) { CK(cudaDeviceSynchronize()); return upload_clip_cdf(e); }   // the sample_keys weights depend on t_max
     return 0;
 }

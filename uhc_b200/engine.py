@@ -21,13 +21,13 @@ class UhcEnvCfg(C.Structure):
                 ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
                 ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double),
                 ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reactive_v", C.c_int), ("reset_seed", C.c_ulonglong),
-                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24), ("obs_v", C.c_int)]
+                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24), ("obs_v", C.c_int), ("fut_frames", C.c_int), ("fut_skip", C.c_int), ("no_shape", C.c_int)]
 
 
 def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0, rfc_lim=100.0, rfc_rate=1.0, body_diff_thresh=0.5,
              meta_pd=1, env_episode_len=100000, trail_steps=0, w=(0.3, 0.1, 0.45, 0.1, 0.05), k=(2.0, 0.005, 5.0, 100.0, 1.0),
              newton_max_iter=None, newton_tol=None, auto_reset=0, t_min=5, t_max=300, reset_seed=1, reactive_v=0, reactive_rate=0.3,
-             rfc_mode="implicit", vf_slot=None, obs_v=2):
+             rfc_mode="implicit", vf_slot=None, obs_v=2, fut_frames=10, fut_skip=10, has_shape=True):
     """Defaults = config/release/uhc_implicit_shape.yml + copycat_config.py defaults of the reference."""
     c = UhcEnvCfg()
     c.base_rot = (C.c_double * 4)(*base_rot)
@@ -39,21 +39,22 @@ def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0,
     c.auto_reset, c.t_min, c.t_max, c.reset_seed = int(auto_reset), int(t_min), int(t_max), int(reset_seed)
     c.reactive_v, c.reactive_rate = int(reactive_v), float(reactive_rate)
     # cfg.residual_force_mode: "implicit" (6 action dims: root wrench) | "explicit" (24 x 9: contact point, force, torque per body, mj_applyFT)
-    c.rfc_mode = 1 if rfc_mode in (1, "explicit") else 0
+    c.rfc_mode = 1 if rfc_mode in (1, "explicit") else (2 if rfc_mode in (2, "none", None, False) else 0)      # "none": cfg.residual_force false
     c.vf_slot = (C.c_int * 24)(*(list(vf_slot) if vf_slot is not None else range(24)))
-    assert int(obs_v) in (1, 2), "obs_v: 1 (get_full_obs_v1) or 2 (get_full_obs_v2)"
-    c.obs_v = int(obs_v)
+    assert int(obs_v) in (1, 2, 3), "obs_v: 1 (get_full_obs_v1), 2 (get_full_obs_v2) or 3 (get_full_obs_v3: fut_frames v2 blocks, skip frames apart)"
+    c.obs_v, c.fut_frames, c.fut_skip, c.no_shape = int(obs_v), int(fut_frames), int(fut_skip), int(not has_shape)
     return c
 
 
 def obs_dim_of(cfg):
     """env.obs_dim: 657 (obs v2 with the shape vector) or 784 (obs v1)"""
-    return 784 if cfg.obs_v == 1 else OBS_DIM
+    block = OBS_DIM - (17 if cfg.no_shape else 0)
+    return 784 if cfg.obs_v == 1 else (block * (cfg.fut_frames if cfg.fut_frames > 0 else 10) if cfg.obs_v == 3 else block)
 
 
 def act_dim_of(cfg):
     """env.action_dim (humanoid_im.py:250)"""
-    return NU + (216 if cfg.rfc_mode == 1 else 6) + (30 if cfg.meta_pd else 0)
+    return NU + {0: 6, 1: 216, 2: 0}[cfg.rfc_mode] + (30 if cfg.meta_pd else 0)
 
 
 def pack_expert(ex):
