@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include "../../include/uhc_nn.h"
 
@@ -21,6 +22,12 @@ constexpr int BM = 128, BN = UHC_TC_BN, BK = 64, UK = 16, STAGES = UHC_TC_STAGES
 constexpr int STAGE_BYTES = (BM * BK + BN * BK) * 2;             // 32 KB
 constexpr int NTHREADS = 320;                                    // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue (two per TMEM lane quarter, half the columns each)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;    // + alignment slack + barriers
+// epilogue staging inside the (then idle) operand ring, one block per epilogue warp: [fp32 32x32 tile A | fp32 32x32 tile B | bf16 32x32 tile | bias row]
+constexpr int EPI_F32_A = 0, EPI_F32_B = 4096, EPI_BF16 = 8192, EPI_BIAS = 10240, EPI_BLOCK = 11264;
+static_assert(8 * EPI_BLOCK <= STAGES * STAGE_BYTES, "epilogue staging must fit the operand ring");
+#ifndef UHC_TC_TMA_STORE
+#define UHC_TC_TMA_STORE 1       /* outputs leave through the TMA engine (cp.async.bulk.tensor shared -> global) where their row pitch allows it */
+#endif
 thread_local std::string g_tc_err;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -37,6 +44,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { while
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// one 32 x 32 tile, shared -> global, clipped at the tensor's bounds by the TMA engine
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+// this thread's row of 32 fp32 values into a 32 x 128 B tile laid out for a SWIZZLE_128B tensor map (16-byte chunk j of row r sits at chunk j ^ (r & 7))
+__device__ __forceinline__ void stage_row_f32_sw128(uint32_t tile, int r, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tile + r * 128 + ((j ^ (r & 7)) << 4)), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+}
+// the same as bf16 into a 32 x 64 B tile for a SWIZZLE_64B map (chunk j of row r sits at chunk j ^ ((r >> 1) & 3))
+__device__ __forceinline__ void stage_row_bf16_sw64(uint32_t tile, int r, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)), "r"(*(uint32_t *)&p0), "r"(*(uint32_t *)&p1),
+                     "r"(*(uint32_t *)&p2), "r"(*(uint32_t *)&p3) : "memory");
+    }
 }
 // K-major, 128B-swizzled operand tile: 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -98,7 +125,9 @@ __device__ __forceinline__ void stage_store(float *stg, float *__restrict__ dst,
 #endif
 __global__ void __launch_bounds__(NTHREADS, UHC_TC_MINB)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
-            __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act, int ksplit) {
+            __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act, int ksplit,
+            const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapYf, const __grid_constant__ CUtensorMap mapYb, int tma_mask) {
+    // tma_mask: bit 0 = zf, bit 1 = yf, bit 2 = ybf leave through their tensor map (32 x 32 boxes from swizzled staging tiles) instead of per-thread stores
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], tmem_full
@@ -169,16 +198,24 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                            "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]) :: "memory");   // (operands: the loaded registers may not be read before the wait)
-            // fp32 outputs leave through a warp-private 32 x 33 staging tile in the (now idle) operand ring so that every store
-            // instruction writes one full 128-byte row segment instead of 32 scattered words
+            // every output of this 32 x 32 chunk is staged in the warp's block of the (now idle) operand ring.  Where the output's row pitch allows a tensor map
+            // (tma_mask) the tile is written in the map's swizzled layout and ONE elected lane hands it to the TMA engine (bounds are clipped by the hardware);
+            // otherwise fp32 goes through a 32 x 33 tile so that every store instruction writes one full 128-byte row segment, bf16 as 16-byte stores of the row.
             const int nb = n0 + c * 32;
-            float *stg = reinterpret_cast<float *>(smem) + (warp - 2) * (33 * 33);
+            uint8_t *blk = smem + (warp - 2) * EPI_BLOCK;
+            float *stg = reinterpret_cast<float *>(blk);                      // legacy 32 x 33 tile over the two fp32 areas
+            float *sbias = reinterpret_cast<float *>(blk + EPI_BIAS);
+            const uint32_t blk_s = smem_u32(blk);
+            if (tma_mask) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }      // the previous chunk's tiles have been read
             __syncwarp();
-            stg[32 * 33 + lane] = (bias && blockIdx.z == 0 && nb + lane < N) ? __ldg(bias + nb + lane) : 0.f;   // this chunk's 32 biases, read back as broadcasts
+            sbias[lane] = (bias && blockIdx.z == 0 && nb + lane < N) ? __ldg(bias + nb + lane) : 0.f;   // this chunk's 32 biases, read back as broadcasts
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? v[j] + stg[32 * 33 + j] : 0.f;
-            if (zf) stage_store(stg, zf, v, m0 + 32 * q, nb, M, N, lane, false);       // pre-activation (for the backward pass)
+            for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? v[j] + sbias[j] : 0.f;
+            if (zf) {                                                            // pre-activation (for the backward pass)
+                if (tma_mask & 1) stage_row_f32_sw128(blk_s + EPI_F32_A, lane, v);
+                else stage_store(stg, zf, v, m0 + 32 * q, nb, M, N, lane, false);
+            }
             if (act == UHC_ACT_GELU) {        // act(0) = 0 for every supported activation except sigmoid, so padded entries stay 0
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
@@ -186,22 +223,40 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? act_f(v[j], act) : 0.f;
             }
-            if (yf) stage_store(stg, yf, v, m0 + 32 * q, nb, M, N, lane, ksplit > 1);
-            if (ybf && nb < ldy && row < M) {
-                if (nb + 32 <= ldy) {
-                    uint4 *dst = (uint4 *)(ybf + (size_t)row * ldy + nb);
+            if (yf) {
+                if (tma_mask & 2) stage_row_f32_sw128(blk_s + EPI_F32_B, lane, v);
+                else stage_store(stg, yf, v, m0 + 32 * q, nb, M, N, lane, ksplit > 1);
+            }
+            if (ybf && nb < ldy) {
+                if (tma_mask & 4) stage_row_bf16_sw64(blk_s + EPI_BF16, lane, v);
+                else if (row < M) {
+                    if (nb + 32 <= ldy) {
+                        uint4 *dst = (uint4 *)(ybf + (size_t)row * ldy + nb);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                        uint4 u; u.x = *(uint32_t *)&p0; u.y = *(uint32_t *)&p1; u.z = *(uint32_t *)&p2; u.w = *(uint32_t *)&p3;
-                        dst[j] = u;
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                            uint4 u; u.x = *(uint32_t *)&p0; u.y = *(uint32_t *)&p1; u.z = *(uint32_t *)&p2; u.w = *(uint32_t *)&p3;
+                            dst[j] = u;
+                        }
+                    } else {
+                        for (int j = 0; j < 32 && nb + j < ldy; ++j) ybf[(size_t)row * ldy + nb + j] = __float2bfloat16_rn(v[j]);
                     }
-                } else {
-                    for (int j = 0; j < 32 && nb + j < ldy; ++j) ybf[(size_t)row * ldy + nb + j] = __float2bfloat16_rn(v[j]);
+                }
+            }
+            if (tma_mask) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this lane's tile rows -> visible to the async proxy
+                __syncwarp();
+                if (lane == 0) {
+                    const int r0 = m0 + 32 * q;
+                    if (zf && (tma_mask & 1)) tma_store_2d(&mapZ, blk_s + EPI_F32_A, nb, r0);
+                    if (yf && (tma_mask & 2)) tma_store_2d(&mapYf, blk_s + EPI_F32_B, nb, r0);
+                    if (ybf && (tma_mask & 4) && nb < ldy) tma_store_2d(&mapYb, blk_s + EPI_BF16, nb, r0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         }
+        if (tma_mask && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // complete before the CTA's shared memory goes away
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -361,6 +416,22 @@ int make_map(CUtensorMap *m, const void *base, int rows, int Kp, int box_rows = 
     if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return -1; }
     return 0;
 }
+// output tensor map: row-major [rows][cols] with a row pitch of `pitch` bytes, 32 x 32 boxes; the staging tiles use the 128-byte (fp32) / 64-byte (bf16) swizzle
+int make_map_out(CUtensorMap *m, const void *base, int rows, int cols, size_t pitch, bool bf16) {
+    EncodeFn enc = get_encode();
+    if (!enc) { g_tc_err = "cuTensorMapEncodeTiled unavailable"; return -1; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_tc_err = "cuTensorMapEncodeTiled (output) failed: " + std::to_string((int)r); return -1; }
+    return 0;
+}
+bool tma_store_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("UHC_TC_TMA_STORE"); on = e ? (e[0] != '0') : (UHC_TC_TMA_STORE != 0); }
+    return on != 0;
+}
 }  // namespace
 
 extern "C" {
@@ -393,7 +464,22 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
         if (ksplit > 1 && cudaMemsetAsync(y_f32_or_null, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "memset failed"; return -1; }
     }
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, ksplit);
-    k_linear_tc<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act, ksplit);
+    // outputs through the TMA engine: a tensor map needs a 16-byte aligned base and row pitch.  The fp32 outputs share one staging decision (their legacy
+    // 32 x 33 tile spans both fp32 areas of the warp's block); split-K accumulation keeps the atomic path.
+    CUtensorMap mz = ma, myf = ma, myb = ma;
+    int tma_mask = 0;
+    if (tma_store_enabled()) {
+        auto ok = [](const void *p, size_t pitch) { return p && ((uintptr_t)p & 15) == 0 && pitch % 16 == 0; };
+        const size_t pf = (size_t)N * sizeof(float), pb = (size_t)ldy_bf16 * 2;
+        const bool f32_ok = ksplit == 1 && (z_f32_or_null || y_f32_or_null) && (!z_f32_or_null || ok(z_f32_or_null, pf)) && (!y_f32_or_null || ok(y_f32_or_null, pf));
+        if (f32_ok) {
+            if (z_f32_or_null) { if (make_map_out(&mz, z_f32_or_null, M, N, pf, false)) return -1; tma_mask |= 1; }
+            if (y_f32_or_null) { if (make_map_out(&myf, y_f32_or_null, M, N, pf, false)) return -1; tma_mask |= 2; }
+        }
+        if (y_bf16_or_null && ok(y_bf16_or_null, pb)) { if (make_map_out(&myb, y_bf16_or_null, M, ldy_bf16, pb, true)) return -1; tma_mask |= 4; }
+    }
+    k_linear_tc<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act, ksplit,
+                                                                     mz, myf, myb, tma_mask);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
     return 0;
