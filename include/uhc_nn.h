@@ -30,6 +30,11 @@ int uhc_f32_to_bf16_padded(const float *x, void *y_bf16, int M, int K, int Kp, v
  *   transposed bf16 copies ; uhc_dact_bf16 fuses dz = dh * act'(z) -> bf16 dz, bf16 dz^T and the bias gradient. */
 int uhc_linear_forward_tc_train(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null, float *z_f32,
                                 int M, int N, int Kp, int ldy_bf16, int act, void *stream);
+/* the same, also emitting the transposed bf16 activation yT [N][ld_yT] (ld_yT >= M, multiple of 8, zero padded): the dW GEMM's K-major operand, stored by the
+ * epilogue through the TMA engine.  Needs the TMA-store path (uhc_tc_tma_store_enabled(); UHC_TC_TMA_STORE=0 in the environment turns it off). */
+int uhc_linear_forward_tc_train_t(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16, void *yT_bf16, int ld_yT, float *z_f32_or_null,
+                                  int M, int N, int Kp, int ldy_bf16, int act, void *stream);
+int uhc_tc_tma_store_enabled(void);
 int uhc_transpose_bf16(const void *in, void *out, int R, int C, int ld_in, int ld_out, void *stream);
 int uhc_dact_bf16(const float *dh, const float *z_or_null, void *dz_bf16, void *dzT_bf16, float *db_or_null, int M, int N, int ld_dz, int ld_dzT, int act,
                   void *stream);

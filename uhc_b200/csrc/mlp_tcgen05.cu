@@ -65,6 +65,14 @@ __device__ __forceinline__ void stage_row_bf16_sw64(uint32_t tile, int r, const 
                      "r"(*(uint32_t *)&p2), "r"(*(uint32_t *)&p3) : "memory");
     }
 }
+// this thread's row m (= lane) of 32 values as COLUMN m of the transposed 32 x 64 B bf16 tile (row j = output column nb + j), SWIZZLE_64B layout
+__device__ __forceinline__ void stage_col_bf16_sw64(uint32_t tile, int m, const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(v[j]));
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(tile + j * 64 + ((((m >> 3) ^ ((j >> 1) & 3))) << 4) + ((m & 7) << 1)), "h"(h) : "memory");
+    }
+}
 // K-major, 128B-swizzled operand tile: 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -126,8 +134,10 @@ __device__ __forceinline__ void stage_store(float *stg, float *__restrict__ dst,
 __global__ void __launch_bounds__(NTHREADS, UHC_TC_MINB)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
             __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act, int ksplit,
-            const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapYf, const __grid_constant__ CUtensorMap mapYb, int tma_mask) {
-    // tma_mask: bit 0 = zf, bit 1 = yf, bit 2 = ybf leave through their tensor map (32 x 32 boxes from swizzled staging tiles) instead of per-thread stores
+            const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapYf, const __grid_constant__ CUtensorMap mapYb, int tma_mask,
+            const __grid_constant__ CUtensorMap mapYT) {
+    // tma_mask: bit 0 = zf, bit 1 = yf, bit 2 = ybf leave through their tensor map (32 x 32 boxes from swizzled staging tiles) instead of per-thread stores;
+    // bit 3 = the TRANSPOSE of the bf16 activation ([N][M pitch], what the backward pass' dW = dz^T h GEMM reads as its K-major operand) is emitted as well
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], tmem_full
@@ -227,6 +237,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 if (tma_mask & 2) stage_row_f32_sw128(blk_s + EPI_F32_B, lane, v);
                 else stage_store(stg, yf, v, m0 + 32 * q, nb, M, N, lane, ksplit > 1);
             }
+            if ((tma_mask & 8) && nb < N) stage_col_bf16_sw64(blk_s + EPI_F32_B, lane, v);     // (the second fp32 area is free: a transposed copy is only asked for next to a bf16 y)
             if (ybf && nb < ldy) {
                 if (tma_mask & 4) stage_row_bf16_sw64(blk_s + EPI_BF16, lane, v);
                 else if (row < M) {
@@ -252,6 +263,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     if (zf && (tma_mask & 1)) tma_store_2d(&mapZ, blk_s + EPI_F32_A, nb, r0);
                     if (yf && (tma_mask & 2)) tma_store_2d(&mapYf, blk_s + EPI_F32_B, nb, r0);
                     if (ybf && (tma_mask & 4) && nb < ldy) tma_store_2d(&mapYb, blk_s + EPI_BF16, nb, r0);
+                    if ((tma_mask & 8) && nb < N) tma_store_2d(&mapYT, blk_s + EPI_F32_B, r0, nb);          // box = 32 rows (n) x 32 m-values
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -443,7 +455,7 @@ int uhc_f32_to_bf16_padded(const float *x, void *y_bf16, int M, int K, int Kp, v
 }
 
 static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null, float *z_f32_or_null,
-                          int M, int N, int Kp, int ldy_bf16, int act, void *stream) {
+                          int M, int N, int Kp, int ldy_bf16, int act, void *stream, void *yT_bf16_or_null = nullptr, int ld_yT = 0) {
     if (Kp % BK != 0 || M <= 0 || N <= 0) { g_tc_err = "uhc_linear_forward_tc: Kp must be a positive multiple of 64"; return -2; }
     if (y_bf16_or_null && (ldy_bf16 % 8 != 0)) { g_tc_err = "uhc_linear_forward_tc: ldy must be a multiple of 8"; return -2; }
     static bool attr_set[64] = {false};   // per device: the attribute belongs to the function on the CURRENT device
@@ -478,8 +490,14 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
         }
         if (y_bf16_or_null && ok(y_bf16_or_null, pb)) { if (make_map_out(&myb, y_bf16_or_null, M, ldy_bf16, pb, true)) return -1; tma_mask |= 4; }
     }
+    CUtensorMap myt = ma;
+    if (yT_bf16_or_null) {      // transposed activation [N][ld_yT] (ld_yT >= M rounded up to 64, the padding columns receive the tile's zero rows)
+        if (!tma_store_enabled() || y_f32_or_null || ((uintptr_t)yT_bf16_or_null & 15) || ld_yT % 8 != 0 || ld_yT < M) { g_tc_err = "uhc_linear_forward_tc_train_t: the transposed output needs the TMA store path, no fp32 y, and a pitch >= M that is a multiple of 8"; return -2; }
+        if (make_map_out(&myt, yT_bf16_or_null, N, ld_yT, (size_t)ld_yT * 2, true)) return -1;
+        tma_mask |= 8;
+    }
     k_linear_tc<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act, ksplit,
-                                                                     mz, myf, myb, tma_mask);
+                                                                     mz, myf, myb, tma_mask, myt);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
     return 0;
@@ -493,6 +511,14 @@ int uhc_linear_forward_tc_train(const void *x_bf16, const void *W_bf16, const fl
                                 int M, int N, int Kp, int ldy_bf16, int act, void *stream) {
     return linear_tc_impl(x_bf16, W_bf16, b, y_bf16_or_null, y_f32_or_null, z_f32, M, N, Kp, ldy_bf16, act, stream);
 }
+/* training forward that also emits the transpose of the bf16 activation, yT [N][ld_yT] (zero padded to ld_yT): the K-major operand of the backward pass' dW GEMM,
+ * written by the same epilogue through the TMA engine instead of by a separate transpose kernel */
+int uhc_linear_forward_tc_train_t(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16, void *yT_bf16, int ld_yT, float *z_f32_or_null,
+                                  int M, int N, int Kp, int ldy_bf16, int act, void *stream) {
+    if (!y_bf16 || !yT_bf16) { g_tc_err = "uhc_linear_forward_tc_train_t: y and yT are required"; return -2; }
+    return linear_tc_impl(x_bf16, W_bf16, b, y_bf16, nullptr, z_f32_or_null, M, N, Kp, ldy_bf16, act, stream, yT_bf16, ld_yT);
+}
+int uhc_tc_tma_store_enabled(void) { return tma_store_enabled() ? 1 : 0; }
 int uhc_transpose_bf16(const void *in, void *out, int R, int Cc, int ld_in, int ld_out, void *stream) {
     dim3 grid((Cc + 63) / 64, (R + 63) / 64);
     if (Cc % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && ((uintptr_t)in & 7) == 0 && ((uintptr_t)out & 7) == 0)

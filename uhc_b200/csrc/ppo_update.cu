@@ -106,7 +106,7 @@ AllReduceFn nccl_all_reduce() {
 }
 constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0;
 
-struct NetBuf { void *acts[9] = {nullptr}; float *z[8] = {nullptr}; float *out = nullptr; };
+struct NetBuf { void *acts[9] = {nullptr}; void *actsT[9] = {nullptr}; float *z[8] = {nullptr}; float *out = nullptr; };   // actsT[i]: [dims[i]][rows rounded up to 64] bf16, written by the forward epilogue
 }  // namespace
 
 struct UhcPpoTrainer {
@@ -145,6 +145,7 @@ template <class T> int dalloc(UhcPpoTrainer *t, T **p, size_t bytes, bool zero) 
 int alloc_net(UhcPpoTrainer *t, const UhcNetDesc &n, NetBuf &nb, long cap, bool own_out) {
     for (int i = 0; i < n.nlayers - 1; i++) {
         if (dalloc(t, &nb.acts[i + 1], (size_t)cap * pad64(n.dims[i + 1]) * 2, true)) return -1;    // bf16, zero padded once (the GEMMs write the first N columns)
+        if (uhc_tc_tma_store_enabled() && dalloc(t, &nb.actsT[i + 1], (size_t)n.dims[i + 1] * pad64(cap) * 2, true)) return -1;
         if (dalloc(t, &nb.z[i], (size_t)cap * n.dims[i + 1] * 4, false)) return -1;
     }
     if (n.head_act != UHC_ACT_NONE && dalloc(t, &nb.z[n.nlayers - 1], (size_t)cap * n.dims[n.nlayers] * 4, false)) return -1;   // activated output layer (MCP composer)
@@ -157,6 +158,12 @@ int net_forward(const UhcNetDesc &n, NetBuf &nb, const void *x, long rows, bool 
         const bool last = i == n.nlayers - 1;
         const int N = n.dims[i + 1];
         const int act = last ? n.head_act : n.act;
+        if (train && !last && nb.actsT[i + 1]) {      // hidden layer of a training forward: the epilogue also writes the transposed activation the dW GEMM needs
+            CKU(uhc_linear_forward_tc_train_t(h, n.W_bf16[i], n.flat + n.b_off[i], nb.acts[i + 1], nb.actsT[i + 1], (int)pad64(rows), act == UHC_ACT_NONE ? nullptr : nb.z[i],
+                                              (int)rows, N, n.kp[i], (int)pad64(N), act, st), "forward GEMM");
+            h = nb.acts[i + 1];
+            continue;
+        }
         CKU(uhc_linear_forward_tc_train(h, n.W_bf16[i], n.flat + n.b_off[i], last ? nullptr : nb.acts[i + 1], last ? nb.out : nullptr,
                                         (!train || act == UHC_ACT_NONE) ? nullptr : nb.z[i], (int)rows, N, n.kp[i], last ? 0 : (int)pad64(N), act, st), "forward GEMM");
         h = nb.acts[i + 1];
@@ -173,7 +180,10 @@ int net_backward(UhcPpoTrainer *t, const UhcNetDesc &n, NetBuf &nb, const float 
         const int act = i < n.nlayers - 1 ? n.act : n.head_act;
         CKU(uhc_dact_bf16(dh, act != UHC_ACT_NONE ? nb.z[i] : nullptr, t->dz, t->dzT, n.gfull + n.b_off[i], (int)M, N, (int)Np, (int)Mp, act, st), "activation backward");
         const void *hT = t->xT;
-        if (i > 0) { CKU(uhc_transpose_bf16(nb.acts[i], t->hT, (int)M, K, (int)pad64(K), (int)Mp, st), "transpose h"); hT = t->hT; }
+        if (i > 0) {
+            if (nb.actsT[i]) hT = nb.actsT[i];           // written by the forward pass' epilogue with pitch pad64(M)
+            else { CKU(uhc_transpose_bf16(nb.acts[i], t->hT, (int)M, K, (int)pad64(K), (int)Mp, st), "transpose h"); hT = t->hT; }
+        }
         CKU(uhc_linear_forward_tc(t->dzT, hT, nullptr, nullptr, n.gfull + n.w_off[i], N, K, (int)Mp, 0, UHC_ACT_NONE, st), "dW GEMM");           // dW = dz^T h
         if (i > 0) {
             CKU(uhc_transpose_bf16(n.W_bf16[i], t->WT, N, K, n.kp[i], (int)Np, st), "transpose W");

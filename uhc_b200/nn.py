@@ -403,8 +403,15 @@ class TCTrainer:
             N = net.W[i].shape[0]
             ybf = None if last else _buf(self.cache, f"a{i}", (M, _pad64(N)), torch.bfloat16, xb.device)
             z = None if last else _buf(self.cache, f"z{i}", (M, N), torch.float32, xb.device, zero=False)
-            _chk(L.uhc_linear_forward_tc_train(_p(acts[i]), _p(net._bf16[i]), _p(net.b[i]), _p(ybf), _p(out if last else None), _p(z), M, N,
-                                               net._bf16[i].shape[1], 0 if last else ybf.shape[1], ACT["none" if last else net.htype], _stream(xb)))
+            if not last and L.uhc_tc_tma_store_enabled():      # the epilogue also stores the transposed activation the dW GEMM of the backward pass reads
+                yT = _buf(self.cache, f"hT{i + 1}", (N, _pad64(M)), torch.bfloat16, xb.device)
+                _chk(L.uhc_linear_forward_tc_train_t(_p(acts[i]), _p(net._bf16[i]), _p(net.b[i]), _p(ybf), _p(yT), yT.shape[1], _p(z), M, N,
+                                                     net._bf16[i].shape[1], ybf.shape[1], ACT[net.htype], _stream(xb)))
+                self.cache[f"hT_fresh{i + 1}"] = True
+            else:
+                _chk(L.uhc_linear_forward_tc_train(_p(acts[i]), _p(net._bf16[i]), _p(net.b[i]), _p(ybf), _p(out if last else None), _p(z), M, N,
+                                                   net._bf16[i].shape[1], 0 if last else ybf.shape[1], ACT["none" if last else net.htype], _stream(xb)))
+                self.cache[f"hT_fresh{i + 1}"] = False
             if not last:
                 acts.append(ybf)
                 zs.append(z)
@@ -431,7 +438,8 @@ class TCTrainer:
                 hT = xT
             else:
                 hT = _buf(self.cache, f"hT{i}", (K, Mp), torch.bfloat16, dev)
-                _chk(L.uhc_transpose_bf16(_p(acts[i]), _p(hT), M, K, acts[i].shape[1], Mp, _stream(dy)))
+                if not self.cache.get(f"hT_fresh{i}"):
+                    _chk(L.uhc_transpose_bf16(_p(acts[i]), _p(hT), M, K, acts[i].shape[1], Mp, _stream(dy)))
             dW = grads[2 * i]
             _chk(L.uhc_linear_forward_tc(_p(dzT), _p(hT), None, None, _p(dW), N, K, Mp, 0, 0, _stream(dy)))      # dW = dz^T h
             if i > 0:
