@@ -35,6 +35,11 @@ int uhc_linear_forward_tc_train(const void *x_bf16, const void *W_bf16, const fl
 int uhc_linear_forward_tc_train_t(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16, void *yT_bf16, int ld_yT, float *z_f32_or_null,
                                   int M, int N, int Kp, int ldy_bf16, int act, void *stream);
 int uhc_tc_tma_store_enabled(void);
+/* backward through one Linear and the PREVIOUS layer's activation in one kernel: dz_prev = (dz W) * act'(z_prev), emitted as bf16 [M][ld_dz] and transposed
+ * [K][ld_dzT] (zero padded), db_prev[k] = sum_m dz_prev[m][k]; no fp32 dh is written.  dz [M][Np], WT [K][Np] bf16 K-major.  Returns -2 when the shapes
+ * do not allow the TMA path (K % 4 != 0, unaligned buffers, UHC_TC_TMA_STORE=0): use uhc_linear_forward_tc + uhc_dact_bf16 then. */
+int uhc_linear_dx_dact_tc(const void *dz_bf16, const void *WT_bf16, const float *z_prev, void *dzp_bf16, void *dzpT_bf16, float *db_prev_or_null,
+                          int M, int K, int Np, int ld_dz, int ld_dzT, int act, void *stream);
 int uhc_transpose_bf16(const void *in, void *out, int R, int C, int ld_in, int ld_out, void *stream);
 int uhc_dact_bf16(const float *dh, const float *z_or_null, void *dz_bf16, void *dzT_bf16, float *db_or_null, int M, int N, int ld_dz, int ld_dzT, int act,
                   void *stream);

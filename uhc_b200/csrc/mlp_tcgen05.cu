@@ -109,6 +109,23 @@ __device__ __forceinline__ float act_f(float z, int act) {
     return z;
 }
 
+// act'(z) for the fused activation backward; GELU through the same erf approximation (one exp shared by the erf tail and the density)
+__device__ __forceinline__ float act_b_fast(float z, int act) {
+    switch (act) {
+    case UHC_ACT_GELU: {
+        const float x = fabsf(z) * 0.70710678118654752f;
+        const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+        const float E = __expf(-x * x);                                   // exp(-z^2 / 2)
+        const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+        const float e = 1.0f - poly * E;                                  // erf(|z| / sqrt 2)
+        return 0.5f + copysignf(0.5f * e, z) + z * E * 0.3989422804014327f;
+    }
+    case UHC_ACT_TANH: { const float th = tanhf(z); return 1.0f - th * th; }
+    case UHC_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case UHC_ACT_SIGMOID: { const float sg = 1.0f / (1.0f + __expf(-z)); return sg * (1.0f - sg); }
+    }
+    return 1.f;
+}
 // one warp writes its 32 x 32 block (thread = row, vals = that row's 32 columns) to dst[row0 + rr][col0 + lane], rows in order
 __device__ __forceinline__ void stage_store(float *stg, float *__restrict__ dst, const float (&vals)[32], int row0, int col0, int M, int N, int lane, bool atomic) {
     __syncwarp();
@@ -131,17 +148,22 @@ __device__ __forceinline__ void stage_store(float *stg, float *__restrict__ dst,
 #ifndef UHC_TC_MINB
 #define UHC_TC_MINB (STAGES * STAGE_BYTES <= 100 * 1024 ? 2 : 1)     /* resident CTAs per SM the register budget is cut for (experiment knob) */
 #endif
+// DACT = the backward pass' dX GEMM with the activation backward fused into its epilogue: the accumulator (dh of the previous layer) is multiplied by act'(z_prev)
+// (z tile fetched by TMA through mapZ) and leaves as bf16 dz (mapYb), its transpose (mapYT) and 32-row partial column sums added to dbias (the bias gradient);
+// no fp32 dh is ever written.
+template <bool DACT>
 __global__ void __launch_bounds__(NTHREADS, UHC_TC_MINB)
 k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias,
             __nv_bfloat16 *__restrict__ ybf, float *__restrict__ yf, float *__restrict__ zf, int M, int N, int Kp, int ldy, int act, int ksplit,
             const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapYf, const __grid_constant__ CUtensorMap mapYb, int tma_mask,
-            const __grid_constant__ CUtensorMap mapYT) {
+            const __grid_constant__ CUtensorMap mapYT, float *__restrict__ dbias) {
     // tma_mask: bit 0 = zf, bit 1 = yf, bit 2 = ybf leave through their tensor map (32 x 32 boxes from swizzled staging tiles) instead of per-thread stores;
     // bit 3 = the TRANSPOSE of the bf16 activation ([N][M pitch], what the backward pass' dW = dz^T h GEMM reads as its K-major operand) is emitted as well
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(smem + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], tmem_full
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * STAGES + 1);
+    uint64_t *zbars = bars + 16;                                   // DACT: one barrier per epilogue warp for its z tiles
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     // split-K (gridDim.z slices of the reduction, fp32 atomic accumulation into yf): used for dW = dZ^T X whose output has few tiles
@@ -153,6 +175,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB));
         for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(tfull, 1);
+        if (DACT) for (int w = 0; w < 8; w++) mbar_init(smem_u32(zbars + w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -197,6 +220,68 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         mbar_wait(tfull, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + 32 * q + lane;
+        if constexpr (DACT) {
+            uint8_t *blk = smem + (warp - 2) * EPI_BLOCK;
+            const uint32_t blk_s = smem_u32(blk), zbar = smem_u32(zbars + (warp - 2));
+            const int r0 = m0 + 32 * q, cfirst = half * (BN / 64);
+            static_assert(BN / 64 == 2, "the z tiles of a warp's two chunks live in the two fp32 staging areas");
+            const bool zl0 = r0 < M && n0 + cfirst * 32 < N, zl1 = r0 < M && n0 + cfirst * 32 + 32 < N;
+            if (lane == 0 && zl0) {      // the operand ring is idle now: fetch this warp's z tiles while the accumulator is read from TMEM
+                mbar_expect_tx(zbar, (zl1 ? 2u : 1u) * 4096u);
+                tma_load_2d(blk_s + EPI_F32_A, &mapZ, zbar, n0 + cfirst * 32, r0);
+                if (zl1) tma_load_2d(blk_s + EPI_F32_B, &mapZ, zbar, n0 + cfirst * 32 + 32, r0);
+            }
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[32];
+                const int c = cfirst + cc, nb = n0 + c * 32;
+                const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+                               "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]),
+                               "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]) :: "memory");
+                if (cc == 0 && zl0) mbar_wait(zbar, 0);
+                if (cc == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the bf16 tile of the first chunk has been read
+                __syncwarp();
+                const uint32_t zarea = blk_s + (cc ? EPI_F32_B : EPI_F32_A);
+                if (cc ? zl1 : zl0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {        // this thread's row of the 128B-swizzled z tile
+                        float a, b, cq, d;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(cq), "=f"(d) : "r"(zarea + lane * 128 + ((j ^ (lane & 7)) << 4)) : "memory");
+                        v[4 * j] *= act_b_fast(a, act); v[4 * j + 1] *= act_b_fast(b, act); v[4 * j + 2] *= act_b_fast(cq, act); v[4 * j + 3] *= act_b_fast(d, act);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? v[j] : 0.f;
+                __syncwarp();                             // every lane has read its z row: the area now stages the transposed tile
+                if (nb < ldy) stage_row_bf16_sw64(blk_s + EPI_BF16, lane, v);
+                if (nb < N) stage_col_bf16_sw64(zarea, lane, v);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (nb < ldy) tma_store_2d(&mapYb, blk_s + EPI_BF16, nb, r0);
+                    if (nb < N) tma_store_2d(&mapYT, zarea, r0, nb);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (dbias && nb < N) {                    // column sums over the warp's 32 rows: transpose-reduce (31 shuffles), lane l ends with column l
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) {
+                        const bool up = (lane & o) != 0;
+#pragma unroll
+                        for (int k = 0; k < o; ++k) {
+                            const float send = up ? v[k] : v[k + o], keep = up ? v[k + o] : v[k];
+                            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    if (nb + lane < N) atomicAdd(dbias + nb + lane, v[0]);
+                }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else {
 #pragma unroll 1
         for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
             float v[32];
@@ -251,7 +336,8 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                             dst[j] = u;
                         }
                     } else {
-                        for (int j = 0; j < 32 && nb + j < ldy; ++j) ybf[(size_t)row * ldy + nb + j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (nb + j < ldy) ybf[(size_t)row * ldy + nb + j] = __float2bfloat16_rn(v[j]);      // (static indices: v stays in registers)
                     }
                 }
             }
@@ -269,6 +355,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             }
         }
         if (tma_mask && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // complete before the CTA's shared memory goes away
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -461,7 +548,8 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
     static bool attr_set[64] = {false};   // per device: the attribute belongs to the function on the CURRENT device
     int dev = 0; cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        if (cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute failed"; return -1; }
+        if (cudaFuncSetAttribute(k_linear_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_linear_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute failed"; return -1; }
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     CUtensorMap ma, mb;
@@ -496,8 +584,8 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
         if (make_map_out(&myt, yT_bf16_or_null, N, ld_yT, (size_t)ld_yT * 2, true)) return -1;
         tma_mask |= 8;
     }
-    k_linear_tc<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act, ksplit,
-                                                                     mz, myf, myb, tma_mask, myt);
+    k_linear_tc<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act, ksplit,
+                                                                            mz, myf, myb, tma_mask, myt, nullptr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
     return 0;
@@ -519,6 +607,33 @@ int uhc_linear_forward_tc_train_t(const void *x_bf16, const void *W_bf16, const 
     return linear_tc_impl(x_bf16, W_bf16, b, y_bf16, nullptr, z_f32_or_null, M, N, Kp, ldy_bf16, act, stream, yT_bf16, ld_yT);
 }
 int uhc_tc_tma_store_enabled(void) { return tma_store_enabled() ? 1 : 0; }
+/* backward through one Linear + the previous layer's activation in ONE kernel:  dz_prev = (dz W) * act'(z_prev)  as bf16 [M][ld_dz] and transposed [K][ld_dzT],
+ * db_prev[k] += sum_m dz_prev[m][k].  dz [M][Np] and WT [K][Np] are the K-major bf16 operands (Np = N rounded up to 64).  Needs the TMA-store path, K % 4 == 0
+ * and 16-byte aligned buffers (returns -2 otherwise: run uhc_linear_forward_tc + uhc_dact_bf16 instead). */
+int uhc_linear_dx_dact_tc(const void *dz_bf16, const void *WT_bf16, const float *z_prev, void *dzp_bf16, void *dzpT_bf16, float *db_prev_or_null,
+                          int M, int K, int Np, int ld_dz, int ld_dzT, int act, void *stream) {
+    if (Np % BK != 0 || M <= 0 || K <= 0) { g_tc_err = "uhc_linear_dx_dact_tc: Np must be a positive multiple of 64"; return -2; }
+    auto al = [](const void *p) { return p && ((uintptr_t)p & 15) == 0; };
+    if (!tma_store_enabled() || K % 4 != 0 || ld_dz % 8 != 0 || ld_dzT % 8 != 0 || ld_dz < K || ld_dzT < M || !al(z_prev) || !al(dzp_bf16) || !al(dzpT_bf16)) {
+        g_tc_err = "uhc_linear_dx_dact_tc: needs the TMA store path, K % 4 == 0, pitches that are multiples of 8 elements and 16-byte aligned buffers"; return -2;
+    }
+    int dev = 0; cudaGetDevice(&dev);
+    static bool attr_set[64] = {false};
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(k_linear_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute failed"; return -1; }
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    CUtensorMap ma, mb, mz, mdz, mdzT;
+    if (make_map(&ma, dz_bf16, M, Np, BM) || make_map(&mb, WT_bf16, K, Np, BN)) return -1;
+    if (make_map_out(&mz, z_prev, M, K, (size_t)K * 4, false) || make_map_out(&mdz, dzp_bf16, M, ld_dz, (size_t)ld_dz * 2, true) ||
+        make_map_out(&mdzT, dzpT_bf16, K, ld_dzT, (size_t)ld_dzT * 2, true)) return -1;
+    if (db_prev_or_null && cudaMemsetAsync(db_prev_or_null, 0, (size_t)K * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "uhc_linear_dx_dact_tc: memset failed"; return -1; }
+    dim3 grid((K + BN - 1) / BN, (M + BM - 1) / BM, 1);
+    k_linear_tc<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, nullptr, nullptr, nullptr, nullptr, M, K, Np, ld_dz, act, 1, mz, mz, mdz, 0, mdzT, db_prev_or_null);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
 int uhc_transpose_bf16(const void *in, void *out, int R, int Cc, int ld_in, int ld_out, void *stream) {
     dim3 grid((Cc + 63) / 64, (R + 63) / 64);
     if (Cc % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0 && ((uintptr_t)in & 7) == 0 && ((uintptr_t)out & 7) == 0)

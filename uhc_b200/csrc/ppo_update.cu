@@ -118,6 +118,7 @@ struct UhcPpoTrainer {
     UhcNetDesc val{};
     NetBuf vb;
     void *xb = nullptr, *xT = nullptr, *lb = nullptr;                   // bf16 states [M][Dp], transpose [D][Mp], last states [E][Dp]
+    void *dz2 = nullptr, *dzT2 = nullptr;                               // second dz / dz^T pair: the fused dX + activation-backward GEMM reads one pair and writes the other
     void *dz = nullptr, *dzT = nullptr, *hT = nullptr, *WT = nullptr;   // shared backward scratch (the nets run back to back on one stream)
     float *dh = nullptr, *dmean = nullptr, *dv = nullptr, *fixed = nullptr, *adv = nullptr, *ret = nullptr, *last_v = nullptr, *inv_count = nullptr;
     double *mom = nullptr, *cnt = nullptr, *ntot = nullptr, *sq = nullptr;
@@ -174,21 +175,32 @@ int net_forward(const UhcNetDesc &n, NetBuf &nb, const void *x, long rows, bool 
 int net_backward(UhcPpoTrainer *t, const UhcNetDesc &n, NetBuf &nb, const float *dy, long M, cudaStream_t st) {
     const long Mp = pad64(M);
     const float *dh = dy;
+    void *dz = t->dz, *dzT = t->dzT, *dz_o = t->dz2, *dzT_o = t->dzT2;
+    bool have_dz = false;        // dz / dz^T / db of this layer were already produced by the layer above's fused dX GEMM
     for (int i = n.nlayers - 1; i >= 0; --i) {
         const int N = n.dims[i + 1], K = n.dims[i];
         const long Np = pad64(N);
         const int act = i < n.nlayers - 1 ? n.act : n.head_act;
-        CKU(uhc_dact_bf16(dh, act != UHC_ACT_NONE ? nb.z[i] : nullptr, t->dz, t->dzT, n.gfull + n.b_off[i], (int)M, N, (int)Np, (int)Mp, act, st), "activation backward");
+        if (!have_dz)
+            CKU(uhc_dact_bf16(dh, act != UHC_ACT_NONE ? nb.z[i] : nullptr, dz, dzT, n.gfull + n.b_off[i], (int)M, N, (int)Np, (int)Mp, act, st), "activation backward");
+        have_dz = false;
         const void *hT = t->xT;
         if (i > 0) {
             if (nb.actsT[i]) hT = nb.actsT[i];           // written by the forward pass' epilogue with pitch pad64(M)
             else { CKU(uhc_transpose_bf16(nb.acts[i], t->hT, (int)M, K, (int)pad64(K), (int)Mp, st), "transpose h"); hT = t->hT; }
         }
-        CKU(uhc_linear_forward_tc(t->dzT, hT, nullptr, nullptr, n.gfull + n.w_off[i], N, K, (int)Mp, 0, UHC_ACT_NONE, st), "dW GEMM");           // dW = dz^T h
+        CKU(uhc_linear_forward_tc(dzT, hT, nullptr, nullptr, n.gfull + n.w_off[i], N, K, (int)Mp, 0, UHC_ACT_NONE, st), "dW GEMM");           // dW = dz^T h
         if (i > 0) {
             CKU(uhc_transpose_bf16(n.W_bf16[i], t->WT, N, K, n.kp[i], (int)Np, st), "transpose W");
-            CKU(uhc_linear_forward_tc(t->dz, t->WT, nullptr, nullptr, t->dh, (int)M, K, (int)Np, 0, UHC_ACT_NONE, st), "dX GEMM");                  // dh_prev = dz W
-            dh = t->dh;
+            if (uhc_tc_tma_store_enabled() && n.act != UHC_ACT_NONE && K % 4 == 0) {
+                // dz_prev = (dz W) * act'(z_prev) with its transpose and the bias gradient, all from the GEMM's epilogue
+                CKU(uhc_linear_dx_dact_tc(dz, t->WT, nb.z[i - 1], dz_o, dzT_o, n.gfull + n.b_off[i - 1], (int)M, K, (int)Np, (int)pad64(K), (int)Mp, n.act, st), "dX + activation backward GEMM");
+                void *s1 = dz; dz = dz_o; dz_o = s1; s1 = dzT; dzT = dzT_o; dzT_o = s1;
+                have_dz = true;
+            } else {
+                CKU(uhc_linear_forward_tc(dz, t->WT, nullptr, nullptr, t->dh, (int)M, K, (int)Np, 0, UHC_ACT_NONE, st), "dX GEMM");                  // dh_prev = dz W
+                dh = t->dh;
+            }
         }
     }
     return 0;
@@ -314,6 +326,7 @@ static int trainer_create(const UhcNetDesc *pnets, int nprim, const UhcNetDesc *
     if (nprim > 0) rc = rc || dalloc(t, &t->xall, (size_t)nprim * cap * A * 4, false) || dalloc(t, &t->dxall, (size_t)nprim * cap * A * 4, false) ||
                          dalloc(t, &t->mixw, (size_t)cap * nprim * 4, false) || dalloc(t, &t->dcomp, (size_t)cap * nprim * 4, false) || dalloc(t, &t->mean, (size_t)cap * A * 4, false);
     rc = rc || dalloc(t, &t->xb, (size_t)cap * pad64(D) * 2, true) || dalloc(t, &t->xT, (size_t)D * capp * 2, true) || dalloc(t, &t->lb, (size_t)max_envs * pad64(D) * 2, true);
+    rc = rc || dalloc(t, &t->dz2, (size_t)cap * pad64(maxN) * 2, true) || dalloc(t, &t->dzT2, (size_t)maxN * capp * 2, true);
     rc = rc || dalloc(t, &t->dz, (size_t)cap * pad64(maxN) * 2, true) || dalloc(t, &t->dzT, (size_t)maxN * capp * 2, true) || dalloc(t, &t->hT, (size_t)maxKh * capp * 2, true) ||
          dalloc(t, &t->WT, (size_t)maxKh * pad64(maxN) * 2, true) || dalloc(t, &t->dh, (size_t)cap * maxKh * 4, false);
     rc = rc || dalloc(t, &t->dmean, (size_t)cap * A * 4, false) || dalloc(t, &t->dv, (size_t)cap * 4, false) || dalloc(t, &t->fixed, (size_t)cap * 4, false) ||

@@ -427,13 +427,19 @@ class TCTrainer:
         dev = dy.device
         grads = net.grad_views()     # dW / db are written straight into the flat gradient tensor the optimiser and the all-reduce use
         dh = dy.contiguous()
+        fuse = bool(L.uhc_tc_tma_store_enabled()) and net.htype != "none"
+        have_dz = False
         for i in range(n - 1, -1, -1):
             N, K = net.W[i].shape
             Np = _pad64(N)
-            dz = _buf(self.cache, f"dz{i}", (M, Np), torch.bfloat16, dev)
-            dzT = _buf(self.cache, f"dzT{i}", (N, Mp), torch.bfloat16, dev)
             db = grads[2 * i + 1]
-            _chk(L.uhc_dact_bf16(_p(dh), _p(zs[i] if i < n - 1 else None), _p(dz), _p(dzT), _p(db), M, N, Np, Mp, ACT[net.htype], _stream(dy)))
+            if have_dz:                      # produced by the layer above's fused dX + activation-backward GEMM
+                dz, dzT = dz_next, dzT_next
+            else:
+                dz = _buf(self.cache, f"dz{i}", (M, Np), torch.bfloat16, dev)
+                dzT = _buf(self.cache, f"dzT{i}", (N, Mp), torch.bfloat16, dev)
+                _chk(L.uhc_dact_bf16(_p(dh), _p(zs[i] if i < n - 1 else None), _p(dz), _p(dzT), _p(db), M, N, Np, Mp, ACT[net.htype], _stream(dy)))
+            have_dz = False
             if i == 0:
                 hT = xT
             else:
@@ -445,9 +451,16 @@ class TCTrainer:
             if i > 0:
                 WT = _buf(self.cache, f"WT{i}", (K, Np), torch.bfloat16, dev)
                 _chk(L.uhc_transpose_bf16(_p(net._bf16[i]), _p(WT), N, K, net._bf16[i].shape[1], Np, _stream(dy)))
-                dhp = _buf(self.cache, f"dh{i}", (M, K), torch.float32, dev, zero=False)
-                _chk(L.uhc_linear_forward_tc(_p(dz), _p(WT), None, None, _p(dhp), M, K, Np, 0, 0, _stream(dy)))    # dh_prev = dz W
-                dh = dhp
+                if fuse and K % 4 == 0:
+                    dz_next = _buf(self.cache, f"dz{i - 1}", (M, _pad64(K)), torch.bfloat16, dev)
+                    dzT_next = _buf(self.cache, f"dzT{i - 1}", (K, Mp), torch.bfloat16, dev)
+                    _chk(L.uhc_linear_dx_dact_tc(_p(dz), _p(WT), _p(zs[i - 1]), _p(dz_next), _p(dzT_next), _p(grads[2 * i - 1]), M, K, Np, _pad64(K), Mp,
+                                                 ACT[net.htype], _stream(dy)))
+                    have_dz = True
+                else:
+                    dhp = _buf(self.cache, f"dh{i}", (M, K), torch.float32, dev, zero=False)
+                    _chk(L.uhc_linear_forward_tc(_p(dz), _p(WT), None, None, _p(dhp), M, K, Np, 0, 0, _stream(dy)))    # dh_prev = dz W
+                    dh = dhp
         return net.gflat
 
 
