@@ -177,6 +177,13 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         mbar_init(tfull, 1);
         if (DACT) for (int w = 0; w < 8; w++) mbar_init(smem_u32(zbars + w), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the first ring fill does not depend on anything the other warps set up: start it before the CTA-wide barrier
+        for (int kb = 0; kb < STAGES && kb < nkb; ++kb) {
+            mbar_expect_tx(full0 + 8 * kb, STAGE_BYTES);
+            const uint32_t a = smem_u32(smem + kb * STAGE_BYTES), b = a + BM * BK * 2;
+            tma_load_2d(a, &mapA, full0 + 8 * kb, (kb0 + kb) * BK, m0);
+            tma_load_2d(b, &mapB, full0 + 8 * kb, (kb0 + kb) * BK, n0);
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
@@ -189,7 +196,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = STAGES; kb < nkb; ++kb) {
                 const int s = kb % STAGES; const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
@@ -280,7 +287,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     if (nb + lane < N) atomicAdd(dbias + nb + lane, v[0]);
                 }
             }
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging tiles have been read (the writes drain after the CTA)
         } else {
 #pragma unroll 1
         for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
@@ -354,7 +361,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                 }
             }
         }
-        if (tma_mask && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // complete before the CTA's shared memory goes away
+        if (tma_mask && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging tiles have been read before the CTA's shared memory goes away (the global writes drain on their own)
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -362,6 +369,266 @@ k_linear_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------------------------------------
+// k_linear_tc2: the same Linear / fused-backward GEMMs on CTA PAIRS (tcgen05 cta_group::2), persistent, with two accumulators in TMEM.
+//   * a cluster of two CTAs (one per SM of a TPC) owns a 256 x 256 output tile: each CTA stages ITS 128 rows of A and ITS 128 of the tile's 256 B rows per k-block
+//     (32 KB / stage / CTA for twice the flops of the single-CTA 128 x 128 tile: the operand traffic L2 -> shared memory per flop halves -- the single-CTA
+//     kernel's main loop is bound by exactly that traffic); the leader CTA's elected thread issues UMMA 256 x 256 x 16 for the pair;
+//   * persistent: each pair walks tiles pair, pair + npairs, ...; the accumulator is double buffered (2 x 256 TMEM columns), so the main loop of tile t + 1 runs
+//     under the epilogue of tile t; the epilogue staging has its own shared memory (the operand ring never idles);
+//   * 16 epilogue warps (four per TMEM lane quarter, 64 of the tile's 256 columns each): the epilogue is instruction-latency bound, so it gets the warps;
+//   * every output leaves through the TMA engine; DACT as in k_linear_tc, with both z tiles of a warp prefetched before the accumulator is ready.
+// Barriers: full[s] (leader's: both CTAs' TMA bytes), empty[s] (each CTA's: multicast commit), tmem_full[a] (each CTA's: multicast commit),
+// tmem_empty[a] (leader's: one arrive per epilogue warp of both CTAs), z[warp] (DACT).
+constexpr int P_STAGES = 5, P_TILE_N = 256, P_EPI_WARPS = 16, P_THREADS = (2 + P_EPI_WARPS) * 32, P_BLOCK = 4096;
+constexpr int P_EPI_OFF = P_STAGES * STAGE_BYTES, P_BARS_OFF = P_EPI_OFF + P_EPI_WARPS * P_BLOCK;
+constexpr int P_SMEM_BYTES = P_BARS_OFF + 512 + 1024;
+// staging block of one epilogue warp: 4 KB = one fp32 32 x 32 tile or two bf16 ones.  Forward: z (fp32), then -- after the TMA engine has read it -- y / y^T
+// (bf16) or the fp32 y.  DACT: the chunk's z tile lands here and, once in registers, makes room for dz^T and dz; the next chunk's z tile follows their store.
+// (the small blocks buy a 5-stage operand ring: 160 KB in flight per CTA is what the TMA latency needs at this tile's consumption rate)
+static_assert(STAGE_BYTES == 32768 && BM == 128 && BN == 128, "the pair kernel reuses the single-CTA operand boxes: 128 rows of A, 128 rows of B per CTA and k-block");
+static_assert(P_SMEM_BYTES <= 227 * 1024, "pair kernel shared memory");
+static_assert((2 * P_STAGES + 4 + P_EPI_WARPS) * 8 + 4 <= 512, "pair kernel barrier area");
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs when the MMAs issued so far retire
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+#define UHC_LDTM32(v, taddr)                                                                                                                                  \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                                                    \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),      \
+                   "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]),          \
+                   "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31]) \
+                 : "r"(taddr));                                                                                                                               \
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]) :: "memory")
+
+template <bool DACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias, int M, int N, int Kp, int ldy, int act,
+             const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapYf, const __grid_constant__ CUtensorMap mapYb,
+             const __grid_constant__ CUtensorMap mapYT, int out_mask, float *__restrict__ dbias) {
+    // out_mask (forward): bit 0 = fp32 pre-activation z (mapZ), bit 1 = fp32 y (mapYf; then no bf16 outputs: the host sends those shapes to k_linear_tc),
+    // bit 2 = bf16 y (mapYb, ldy columns incl. padding), bit 3 = bf16 y^T (mapYT).
+    // DACT: mapZ is the INPUT z_prev; outputs bf16 dz (mapYb), dz^T (mapYT), bias gradient sums (dbias).
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(smem + P_BARS_OFF);              // full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | zbar[warps]
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * P_STAGES + 4 + P_EPI_WARPS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int tiles_n = (N + P_TILE_N - 1) / P_TILE_N, ntiles = ((M + 2 * BM - 1) / (2 * BM)) * tiles_n, nkb = Kp / BK;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + P_STAGES), tfull0 = smem_u32(bars + 2 * P_STAGES), tempty0 = smem_u32(bars + 2 * P_STAGES + 2);
+    const uint32_t zbar0 = smem_u32(bars + 2 * P_STAGES + 4);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB));
+        for (int s = 0; s < P_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * P_EPI_WARPS); }
+        for (int w = 0; w < P_EPI_WARPS; w++) mbar_init(zbar0 + 8 * w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {      // the same warp of both CTAs: one allocation of all 512 columns in each SM of the pair
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                            // the peer's barriers exist before anything can arrive on them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;                                            // k-blocks issued so far (ring position)
+            uint32_t full_leader0;                                 // the leader CTA's full[] in the cluster's shared window
+            asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader0) : "r"(full0));
+            for (int t = pair; t < ntiles; t += npairs) {
+                const int m0 = (t / tiles_n) * 2 * BM + (int)rank * BM, nrow0 = (t % tiles_n) * P_TILE_N + (int)rank * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P_STAGES; const uint32_t ph = (it / P_STAGES) & 1;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * STAGE_BYTES);          // the pair's bytes land on the leader's barrier
+                    const uint32_t a = smem_u32(smem + s * STAGE_BYTES), b = a + BM * BK * 2, lb = full_leader0 + 8 * s;
+                    tma_load_2d_pair(a, &mapA, lb, kb * BK, m0);
+                    tma_load_2d_pair(b, &mapB, lb, kb * BK, nrow0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 256, M = 256 (128 rows per CTA)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P_TILE_N >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            int it = 0, ti = 0;
+            for (int t = pair; t < ntiles; t += npairs, ++ti) {
+                const int acc = ti & 1; const uint32_t aph = (ti >> 1) & 1;
+                mbar_wait(tempty0 + 8 * acc, aph ^ 1);                                      // both CTAs' epilogues have drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem + (uint32_t)(acc * P_TILE_N);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P_STAGES; const uint32_t ph = (it / P_STAGES) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a = smem_u32(smem + s * STAGE_BYTES), b = a + BM * BK * 2;
+                    const uint64_t ad = make_desc(a), bd = make_desc(b);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k) umma_bf16_pair(tacc, ad + (uint64_t)(k * UK * 2 >> 4), bd + (uint64_t)(k * UK * 2 >> 4), idesc, (kb | k) != 0);
+                    umma_commit_pair(empty0 + 8 * s);
+                }
+                umma_commit_pair(tfull0 + 8 * acc);
+            }
+        }
+    } else {
+        const int q = warp & 3, ew = warp - 2, colq = ew >> 2;          // TMEM lane quarter (fixed by the hardware: warp id % 4); which 64 of the tile's 256 columns
+        const uint32_t blk_s = smem_u32(smem + P_EPI_OFF + ew * P_BLOCK), zb = zbar0 + 8 * ew;
+        uint32_t tempty_leader0;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(tempty_leader0) : "r"(tempty0));
+        int ti = 0;
+        uint32_t zuse = 0;                                 // completed uses of this warp's z barrier (a chunk outside the matrix has neither a load nor a wait)
+        if constexpr (DACT) {
+            if (lane == 0 && pair < ntiles) {              // the first chunk's z tile: in flight before the first accumulator exists
+                const int r0 = (pair / tiles_n) * 2 * BM + (int)rank * BM + 32 * q, n0 = (pair % tiles_n) * P_TILE_N + 64 * colq;
+                if (r0 < M && n0 < N) { mbar_expect_tx(zb, 4096u); tma_load_2d(blk_s, &mapZ, zb, n0, r0); }
+            }
+        }
+        for (int t = pair; t < ntiles; t += npairs, ++ti) {
+            const int acc = ti & 1; const uint32_t aph = (ti >> 1) & 1;
+            const int r0 = (t / tiles_n) * 2 * BM + (int)rank * BM + 32 * q, n0 = (t % tiles_n) * P_TILE_N + 64 * colq;
+            const int row = r0 + lane;
+            mbar_wait(tfull0 + 8 * acc, aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[32];
+                const int nb = n0 + 32 * cc;
+                const bool interior = r0 + 32 <= M && nb + 32 <= N;      // (warp uniform) no element of this chunk needs masking
+                const uint32_t taddr = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * P_TILE_N + 64 * colq + 32 * cc);
+                UHC_LDTM32(v, taddr);
+                if (cc == 1) {                          // the accumulator is in registers: hand it back to the MMA warp of the leader
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader0 + 8 * acc) : "memory");
+                }
+                if constexpr (DACT) {
+                    if (r0 < M && nb < N) {
+                        mbar_wait(zb, zuse & 1); ++zuse;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float a, b, cq, d;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(cq), "=f"(d) : "r"(blk_s + lane * 128 + ((j ^ (lane & 7)) << 4)) : "memory");
+                            v[4 * j] *= act_b_fast(a, act); v[4 * j + 1] *= act_b_fast(b, act); v[4 * j + 2] *= act_b_fast(cq, act); v[4 * j + 3] *= act_b_fast(d, act);
+                        }
+                    }
+                    if (!interior) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? v[j] : 0.f;
+                    }
+                    __syncwarp();                       // every lane has its z row in registers: the block now stages this chunk's dz^T and dz
+                    if (nb < N) stage_col_bf16_sw64(blk_s, lane, v);
+                    if (nb < ldy) stage_row_bf16_sw64(blk_s + 2048, lane, v);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (nb < N) tma_store_2d(&mapYT, blk_s, r0, nb);
+                        if (nb < ldy) tma_store_2d(&mapYb, blk_s + 2048, nb, r0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // the block is free again: fetch the NEXT chunk's z tile under this chunk's tail
+                        int nr0 = r0, nnb = nb + 32;
+                        if (cc == 1) { const int tn = t + npairs; nr0 = tn < ntiles ? (tn / tiles_n) * 2 * BM + (int)rank * BM + 32 * q : M; nnb = (tn % tiles_n) * P_TILE_N + 64 * colq; }
+                        if (nr0 < M && nnb < N) { mbar_expect_tx(zb, 4096u); tma_load_2d(blk_s, &mapZ, zb, nnb, nr0); }
+                    }
+                    if (dbias && nb < N) {              // column sums over the warp's 32 rows: transpose-reduce (31 shuffles), lane l ends with column l
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) {
+                            const bool up = (lane & o) != 0;
+#pragma unroll
+                            for (int k = 0; k < o; ++k) {
+                                const float send = up ? v[k] : v[k + o], keep = up ? v[k + o] : v[k];
+                                v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                            }
+                        }
+                        if (nb + lane < N) atomicAdd(dbias + nb + lane, v[0]);
+                    }
+                    __syncwarp();
+                } else {
+                    if (bias) {
+                        if (interior && (((uintptr_t)(bias + nb)) & 15) == 0) {      // 8 uniform 16-byte loads instead of 32 shuffles
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + nb) + j); v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w; }
+                        } else {
+                            const float bl = nb + lane < N ? __ldg(bias + nb + lane) : 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+                        }
+                    }
+                    if (!interior) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? v[j] : 0.f;
+                    }
+                    if ((out_mask & 1) && nb < N) {     // phase 1: the fp32 pre-activation through the warp's 4 KB block
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        stage_row_f32_sw128(blk_s, lane, v);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) { tma_store_2d(&mapZ, blk_s, nb, r0); asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+                    }
+                    if (act == UHC_ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                    } else if (act != UHC_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = act_f(v[j], act);
+                        if (!interior) {                 // (sigmoid(0) != 0)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = (row < M && nb + j < N) ? v[j] : 0.f;
+                        }
+                    }
+                    if (out_mask & 14) {                // phase 2: fp32 y, or bf16 y (first 2 KB) and y^T (second 2 KB), once the block has been read
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        if (out_mask & 2) { if (nb < N) stage_row_f32_sw128(blk_s, lane, v); }
+                        else {
+                            if ((out_mask & 4) && nb < ldy) stage_row_bf16_sw64(blk_s, lane, v);
+                            if ((out_mask & 8) && nb < N) stage_col_bf16_sw64(blk_s + 2048, lane, v);
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (out_mask & 2) { if (nb < N) tma_store_2d(&mapYf, blk_s, nb, r0); }
+                            else {
+                                if ((out_mask & 4) && nb < ldy) tma_store_2d(&mapYb, blk_s, nb, r0);
+                                if ((out_mask & 8) && nb < N) tma_store_2d(&mapYT, blk_s + 2048, r0, nb);
+                            }
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                }
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                            // both CTAs are done with TMEM and with each other's barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
 }
 
@@ -531,6 +798,28 @@ bool tma_store_enabled() {
     if (on < 0) { const char *e = getenv("UHC_TC_TMA_STORE"); on = e ? (e[0] != '0') : (UHC_TC_TMA_STORE != 0); }
     return on != 0;
 }
+// the CTA-pair kernel takes the big training GEMMs (many 256 x 256 tiles, every output through a tensor map); UHC_TC_PAIR=0 keeps everything on k_linear_tc
+bool pair_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("UHC_TC_PAIR"); on = e ? (e[0] != '0') : 1; }
+    return on != 0;
+}
+bool pair_shape(int M, int N) { return pair_enabled() && M >= 16384 && N >= 256; }
+int pair_attr() {
+    static bool attr_set[64] = {false};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        if (cudaFuncSetAttribute(k_linear_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_linear_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES) != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute (pair kernel) failed"; return -1; }
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    return 0;
+}
+int pair_grid(int M, int N) {
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles = ((M + 255) / 256) * ((N + 255) / 256), pairs = sms / 2;
+    return 2 * (tiles < pairs ? tiles : pairs);
+}
 }  // namespace
 
 extern "C" {
@@ -584,6 +873,16 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
         if (make_map_out(&myt, yT_bf16_or_null, N, ld_yT, (size_t)ld_yT * 2, true)) return -1;
         tma_mask |= 8;
     }
+    {   // every requested output has a tensor map and the shape is big: CTA pairs
+        const int want = (z_f32_or_null ? 1 : 0) | (y_f32_or_null ? 2 : 0) | (y_bf16_or_null ? 4 : 0) | (yT_bf16_or_null ? 8 : 0);
+        if (ksplit == 1 && want == tma_mask && !((want & 2) && (want & 12)) && pair_shape(M, N)) {
+            if (pair_attr()) return -1;
+            k_linear_tc2<false><<<pair_grid(M, N), P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, M, N, Kp, ldy_bf16, act, mz, myf, myb, myt, tma_mask, nullptr);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
+            return 0;
+        }
+    }
     k_linear_tc<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, (__nv_bfloat16 *)y_bf16_or_null, y_f32_or_null, z_f32_or_null, M, N, Kp, ldy_bf16, act, ksplit,
                                                                             mz, myf, myb, tma_mask, myt, nullptr);
     cudaError_t e = cudaGetLastError();
@@ -628,6 +927,13 @@ int uhc_linear_dx_dact_tc(const void *dz_bf16, const void *WT_bf16, const float 
     if (make_map_out(&mz, z_prev, M, K, (size_t)K * 4, false) || make_map_out(&mdz, dzp_bf16, M, ld_dz, (size_t)ld_dz * 2, true) ||
         make_map_out(&mdzT, dzpT_bf16, K, ld_dzT, (size_t)ld_dzT * 2, true)) return -1;
     if (db_prev_or_null && cudaMemsetAsync(db_prev_or_null, 0, (size_t)K * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "uhc_linear_dx_dact_tc: memset failed"; return -1; }
+    if (pair_shape(M, K)) {
+        if (pair_attr()) return -1;
+        k_linear_tc2<true><<<pair_grid(M, K), P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, nullptr, M, K, Np, ld_dz, act, mz, mz, mdz, mdzT, 0, db_prev_or_null);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
+        return 0;
+    }
     dim3 grid((K + BN - 1) / BN, (M + BM - 1) / BM, 1);
     k_linear_tc<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, nullptr, nullptr, nullptr, nullptr, M, K, Np, ld_dz, act, 1, mz, mz, mdz, 0, mdzT, db_prev_or_null);
     cudaError_t e = cudaGetLastError();
