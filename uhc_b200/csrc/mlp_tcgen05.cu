@@ -398,6 +398,9 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {      // global[tile] += shared tile (element type from the map: fp32)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
                  ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
@@ -421,7 +424,9 @@ template <bool DACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *__restrict__ bias, int M, int N, int Kp, int ldy, int act,
              const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapYf, const __grid_constant__ CUtensorMap mapYb,
-             const __grid_constant__ CUtensorMap mapYT, int out_mask, float *__restrict__ dbias) {
+             const __grid_constant__ CUtensorMap mapYT, int out_mask, float *__restrict__ dbias, int ksplit) {
+    // ksplit > 1 (dW = dz^T h: few output tiles, a very long reduction): a work item is (tile, slice of the k-blocks); the fp32 y tiles are ADDED to the zeroed
+    // output by the TMA engine (cp.reduce.async.bulk.tensor .add) -- only out_mask == 2 and no activation then.
     // out_mask (forward): bit 0 = fp32 pre-activation z (mapZ), bit 1 = fp32 y (mapYf; then no bf16 outputs: the host sends those shapes to k_linear_tc),
     // bit 2 = bf16 y (mapYb, ldy columns incl. padding), bit 3 = bf16 y^T (mapYT).
     // DACT: mapZ is the INPUT z_prev; outputs bf16 dz (mapYb), dz^T (mapYT), bias gradient sums (dbias).
@@ -433,7 +438,8 @@ k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int tiles_n = (N + P_TILE_N - 1) / P_TILE_N, ntiles = ((M + 2 * BM - 1) / (2 * BM)) * tiles_n, nkb = Kp / BK;
+    // work item w = tile * ksplit + slice; "ntiles" counts work items, w / ksplit is the tile every index computation below uses
+    const int tiles_n = (N + P_TILE_N - 1) / P_TILE_N, ntiles = ((M + 2 * BM - 1) / (2 * BM)) * tiles_n * ksplit, nkb_all = Kp / BK;
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + P_STAGES), tfull0 = smem_u32(bars + 2 * P_STAGES), tempty0 = smem_u32(bars + 2 * P_STAGES + 2);
     const uint32_t zbar0 = smem_u32(bars + 2 * P_STAGES + 4);
 
@@ -459,9 +465,11 @@ k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             int it = 0;                                            // k-blocks issued so far (ring position)
             uint32_t full_leader0;                                 // the leader CTA's full[] in the cluster's shared window
             asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(full_leader0) : "r"(full0));
-            for (int t = pair; t < ntiles; t += npairs) {
+            for (int w = pair; w < ntiles; w += npairs) {
+                const int t = w / ksplit, sl = w - t * ksplit;
+                const int kb0 = (int)(((long)nkb_all * sl) / ksplit), kb1 = (int)(((long)nkb_all * (sl + 1)) / ksplit);
                 const int m0 = (t / tiles_n) * 2 * BM + (int)rank * BM, nrow0 = (t % tiles_n) * P_TILE_N + (int)rank * BN;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % P_STAGES; const uint32_t ph = (it / P_STAGES) & 1;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * STAGE_BYTES);          // the pair's bytes land on the leader's barrier
@@ -476,7 +484,8 @@ k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             // instruction descriptor: D = F32, A = B = BF16, both K-major, N = 256, M = 256 (128 rows per CTA)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P_TILE_N >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
             int it = 0, ti = 0;
-            for (int t = pair; t < ntiles; t += npairs, ++ti) {
+            for (int w = pair; w < ntiles; w += npairs, ++ti) {
+                const int sl = w % ksplit, nkb = (int)(((long)nkb_all * (sl + 1)) / ksplit) - (int)(((long)nkb_all * sl) / ksplit);
                 const int acc = ti & 1; const uint32_t aph = (ti >> 1) & 1;
                 mbar_wait(tempty0 + 8 * acc, aph ^ 1);                                      // both CTAs' epilogues have drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -502,12 +511,14 @@ k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         int ti = 0;
         uint32_t zuse = 0;                                 // completed uses of this warp's z barrier (a chunk outside the matrix has neither a load nor a wait)
         if constexpr (DACT) {
-            if (lane == 0 && pair < ntiles) {              // the first chunk's z tile: in flight before the first accumulator exists
+            if (lane == 0 && pair < ntiles) {              // the first chunk's z tile: in flight before the first accumulator exists (DACT never splits k)
                 const int r0 = (pair / tiles_n) * 2 * BM + (int)rank * BM + 32 * q, n0 = (pair % tiles_n) * P_TILE_N + 64 * colq;
                 if (r0 < M && n0 < N) { mbar_expect_tx(zb, 4096u); tma_load_2d(blk_s, &mapZ, zb, n0, r0); }
             }
         }
-        for (int t = pair; t < ntiles; t += npairs, ++ti) {
+        for (int w = pair; w < ntiles; w += npairs, ++ti) {
+            const int t = w / ksplit;
+            const bool first_slice = w == t * ksplit;
             const int acc = ti & 1; const uint32_t aph = (ti >> 1) & 1;
             const int r0 = (t / tiles_n) * 2 * BM + (int)rank * BM + 32 * q, n0 = (t % tiles_n) * P_TILE_N + 64 * colq;
             const int row = r0 + lane;
@@ -523,7 +534,8 @@ k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 if (cc == 1) {                          // the accumulator is in registers: hand it back to the MMA warp of the leader
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader0 + 8 * acc) : "memory");
+                    // (relaxed: the TMEM reads are ordered by the tcgen05 fence above; a release at cluster scope would drain every outstanding global access of the lane)
+                    if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader0 + 8 * acc) : "memory");
                 }
                 if constexpr (DACT) {
                     if (r0 < M && nb < N) {
@@ -532,7 +544,11 @@ k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         for (int j = 0; j < 8; ++j) {
                             float a, b, cq, d;
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(cq), "=f"(d) : "r"(blk_s + lane * 128 + ((j ^ (lane & 7)) << 4)) : "memory");
-                            v[4 * j] *= act_b_fast(a, act); v[4 * j + 1] *= act_b_fast(b, act); v[4 * j + 2] *= act_b_fast(cq, act); v[4 * j + 3] *= act_b_fast(d, act);
+                            if (act == UHC_ACT_GELU) {       // (the common case without the per-element switch)
+                                v[4 * j] *= act_b_fast(a, UHC_ACT_GELU); v[4 * j + 1] *= act_b_fast(b, UHC_ACT_GELU); v[4 * j + 2] *= act_b_fast(cq, UHC_ACT_GELU); v[4 * j + 3] *= act_b_fast(d, UHC_ACT_GELU);
+                            } else {
+                                v[4 * j] *= act_b_fast(a, act); v[4 * j + 1] *= act_b_fast(b, act); v[4 * j + 2] *= act_b_fast(cq, act); v[4 * j + 3] *= act_b_fast(d, act);
+                            }
                         }
                     }
                     if (!interior) {
@@ -550,7 +566,7 @@ k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");          // the block is free again: fetch the NEXT chunk's z tile under this chunk's tail
                         int nr0 = r0, nnb = nb + 32;
-                        if (cc == 1) { const int tn = t + npairs; nr0 = tn < ntiles ? (tn / tiles_n) * 2 * BM + (int)rank * BM + 32 * q : M; nnb = (tn % tiles_n) * P_TILE_N + 64 * colq; }
+                        if (cc == 1) { const int tn = w + npairs; nr0 = tn < ntiles ? (tn / tiles_n) * 2 * BM + (int)rank * BM + 32 * q : M; nnb = (tn % tiles_n) * P_TILE_N + 64 * colq; }
                         if (nr0 < M && nnb < N) { mbar_expect_tx(zb, 4096u); tma_load_2d(blk_s, &mapZ, zb, nnb, nr0); }
                     }
                     if (dbias && nb < N) {              // column sums over the warp's 32 rows: transpose-reduce (31 shuffles), lane l ends with column l
@@ -567,7 +583,7 @@ k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     }
                     __syncwarp();
                 } else {
-                    if (bias) {
+                    if (bias && first_slice) {
                         if (interior && (((uintptr_t)(bias + nb)) & 15) == 0) {      // 8 uniform 16-byte loads instead of 32 shuffles
 #pragma unroll
                             for (int j = 0; j < 8; ++j) { const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + nb) + j); v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w; }
@@ -611,7 +627,7 @@ k_linear_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) {
-                            if (out_mask & 2) { if (nb < N) tma_store_2d(&mapYf, blk_s, nb, r0); }
+                            if (out_mask & 2) { if (nb < N) { if (ksplit > 1) tma_reduce_add_2d(&mapYf, blk_s, nb, r0); else tma_store_2d(&mapYf, blk_s, nb, r0); } }
                             else {
                                 if ((out_mask & 4) && nb < ldy) tma_store_2d(&mapYb, blk_s, nb, r0);
                                 if ((out_mask & 8) && nb < N) tma_store_2d(&mapYT, blk_s + 2048, r0, nb);
@@ -843,8 +859,28 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
     }
     CUtensorMap ma, mb;
     if (make_map(&ma, x_bf16, M, Kp, BM) || make_map(&mb, W_bf16, N, Kp, BN)) return -1;
-    // split the reduction when the output has too few tiles to fill the GPU (only legal for a plain fp32 accumulate output)
     const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM), nkb = Kp / BK;
+    // a plain fp32 product with a long reduction and few output tiles (dW = dz^T h): CTA pairs, the reduction split into as many slices as fill the pairs evenly,
+    // partial tiles added into the zeroed output by the TMA engine
+    if (pair_enabled() && tma_store_enabled() && !y_bf16_or_null && !z_f32_or_null && !yT_bf16_or_null && act == UHC_ACT_NONE && y_f32_or_null && M >= 256 && N >= 256 &&
+        nkb >= 256 && ((uintptr_t)y_f32_or_null & 15) == 0 && N % 4 == 0) {
+        int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int pairs = sms / 2, pt = ((M + 255) / 256) * ((N + 255) / 256);
+        int ks = 1; double best = 0.0;
+        for (int c = 1; c <= 16 && c <= nkb / 32; ++c) {
+            const int items = pt * c; const double eff = (double)items / (double)(((items + pairs - 1) / pairs) * pairs);
+            if (eff > best + 0.02) { best = eff; ks = c; }
+        }
+        CUtensorMap my;
+        if (make_map_out(&my, y_f32_or_null, M, N, (size_t)N * sizeof(float), false) || pair_attr()) return -1;
+        if (ks > 1 && cudaMemsetAsync(y_f32_or_null, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "memset failed"; return -1; }
+        const int items = pt * ks;
+        k_linear_tc2<false><<<2 * (items < pairs ? items : pairs), P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, M, N, Kp, 0, UHC_ACT_NONE, ma, my, ma, ma, 2, nullptr, ks);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
+        return 0;
+    }
+    // split the reduction when the output has too few tiles to fill the GPU (only legal for a plain fp32 accumulate output)
     int ksplit = 1;
     if (!y_bf16_or_null && !z_f32_or_null && act == UHC_ACT_NONE && y_f32_or_null && tiles < 148 && nkb >= 32) {
         ksplit = (296 + tiles - 1) / tiles;
@@ -877,7 +913,7 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
         const int want = (z_f32_or_null ? 1 : 0) | (y_f32_or_null ? 2 : 0) | (y_bf16_or_null ? 4 : 0) | (yT_bf16_or_null ? 8 : 0);
         if (ksplit == 1 && want == tma_mask && !((want & 2) && (want & 12)) && pair_shape(M, N)) {
             if (pair_attr()) return -1;
-            k_linear_tc2<false><<<pair_grid(M, N), P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, M, N, Kp, ldy_bf16, act, mz, myf, myb, myt, tma_mask, nullptr);
+            k_linear_tc2<false><<<pair_grid(M, N), P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, M, N, Kp, ldy_bf16, act, mz, myf, myb, myt, tma_mask, nullptr, 1);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
             return 0;
@@ -929,7 +965,7 @@ int uhc_linear_dx_dact_tc(const void *dz_bf16, const void *WT_bf16, const float 
     if (db_prev_or_null && cudaMemsetAsync(db_prev_or_null, 0, (size_t)K * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "uhc_linear_dx_dact_tc: memset failed"; return -1; }
     if (pair_shape(M, K)) {
         if (pair_attr()) return -1;
-        k_linear_tc2<true><<<pair_grid(M, K), P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, nullptr, M, K, Np, ld_dz, act, mz, mz, mdz, mdzT, 0, db_prev_or_null);
+        k_linear_tc2<true><<<pair_grid(M, K), P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, nullptr, M, K, Np, ld_dz, act, mz, mz, mdz, mdzT, 0, db_prev_or_null, 1);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
         return 0;
