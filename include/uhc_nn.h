@@ -34,6 +34,9 @@ int uhc_linear_forward_tc_train(const void *x_bf16, const void *W_bf16, const fl
  * epilogue through the TMA engine.  Needs the TMA-store path (uhc_tc_tma_store_enabled(); UHC_TC_TMA_STORE=0 in the environment turns it off). */
 int uhc_linear_forward_tc_train_t(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16, void *yT_bf16, int ld_yT, float *z_f32_or_null,
                                   int M, int N, int Kp, int ldy_bf16, int act, void *stream);
+/* plain fp32 product y[M][ld_y] = x W^T with an explicit row pitch ld_y >= N (floats, multiple of 4) on the CTA-pair split-K path; -2 when the shape is not
+ * eligible (M, N >= 256 and Kp >= 16384 are required) */
+int uhc_linear_forward_tc_f32_pitched(const void *x_bf16, const void *W_bf16, float *y_f32, int ld_y, int M, int N, int Kp, void *stream);
 int uhc_tc_tma_store_enabled(void);
 /* backward through one Linear and the PREVIOUS layer's activation in one kernel: dz_prev = (dz W) * act'(z_prev), emitted as bf16 [M][ld_dz] and transposed
  * [K][ld_dzT] (zero padded), db_prev[k] = sum_m dz_prev[m][k]; no fp32 dh is written.  dz [M][Np], WT [K][Np] bf16 K-major.  Returns -2 when the shapes

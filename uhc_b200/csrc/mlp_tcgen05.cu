@@ -847,7 +847,8 @@ int uhc_f32_to_bf16_padded(const float *x, void *y_bf16, int M, int K, int Kp, v
 }
 
 static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b, void *y_bf16_or_null, float *y_f32_or_null, float *z_f32_or_null,
-                          int M, int N, int Kp, int ldy_bf16, int act, void *stream, void *yT_bf16_or_null = nullptr, int ld_yT = 0) {
+                          int M, int N, int Kp, int ldy_bf16, int act, void *stream, void *yT_bf16_or_null = nullptr, int ld_yT = 0, int ld_yf = 0) {
+    if (ld_yf <= 0) ld_yf = N;      // row pitch of the fp32 y in floats (only the long-reduction pair path takes a pitch other than N)
     if (Kp % BK != 0 || M <= 0 || N <= 0) { g_tc_err = "uhc_linear_forward_tc: Kp must be a positive multiple of 64"; return -2; }
     if (y_bf16_or_null && (ldy_bf16 % 8 != 0)) { g_tc_err = "uhc_linear_forward_tc: ldy must be a multiple of 8"; return -2; }
     static bool attr_set[64] = {false};   // per device: the attribute belongs to the function on the CURRENT device
@@ -863,7 +864,7 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
     // a plain fp32 product with a long reduction and few output tiles (dW = dz^T h): CTA pairs, the reduction split into as many slices as fill the pairs evenly,
     // partial tiles added into the zeroed output by the TMA engine
     if (pair_enabled() && tma_store_enabled() && !y_bf16_or_null && !z_f32_or_null && !yT_bf16_or_null && act == UHC_ACT_NONE && y_f32_or_null && M >= 256 && N >= 256 &&
-        nkb >= 256 && ((uintptr_t)y_f32_or_null & 15) == 0 && N % 4 == 0) {
+        nkb >= 256 && ((uintptr_t)y_f32_or_null & 15) == 0 && ld_yf % 4 == 0 && ld_yf >= N) {
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int pairs = sms / 2, pt = ((M + 255) / 256) * ((N + 255) / 256);
         int ks = 1; double best = 0.0;
@@ -872,14 +873,15 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
             if (eff > best + 0.02) { best = eff; ks = c; }
         }
         CUtensorMap my;
-        if (make_map_out(&my, y_f32_or_null, M, N, (size_t)N * sizeof(float), false) || pair_attr()) return -1;
-        if (ks > 1 && cudaMemsetAsync(y_f32_or_null, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "memset failed"; return -1; }
+        if (make_map_out(&my, y_f32_or_null, M, N, (size_t)ld_yf * sizeof(float), false) || pair_attr()) return -1;
+        if (ks > 1 && cudaMemsetAsync(y_f32_or_null, 0, (size_t)M * ld_yf * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "memset failed"; return -1; }
         const int items = pt * ks;
         k_linear_tc2<false><<<2 * (items < pairs ? items : pairs), P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, M, N, Kp, 0, UHC_ACT_NONE, ma, my, ma, ma, 2, nullptr, ks);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { g_tc_err = cudaGetErrorString(e); return -1; }
         return 0;
     }
+    if (ld_yf != N) { g_tc_err = "uhc_linear_forward_tc_f32_pitched: this shape does not run on the CTA-pair path (needs M, N >= 256, Kp >= 16384, a pitch that is a multiple of 4)"; return -2; }
     // split the reduction when the output has too few tiles to fill the GPU (only legal for a plain fp32 accumulate output)
     int ksplit = 1;
     if (!y_bf16_or_null && !z_f32_or_null && act == UHC_ACT_NONE && y_f32_or_null && tiles < 148 && nkb >= 32) {
@@ -940,6 +942,12 @@ int uhc_linear_forward_tc_train_t(const void *x_bf16, const void *W_bf16, const 
                                   int M, int N, int Kp, int ldy_bf16, int act, void *stream) {
     if (!y_bf16 || !yT_bf16) { g_tc_err = "uhc_linear_forward_tc_train_t: y and yT are required"; return -2; }
     return linear_tc_impl(x_bf16, W_bf16, b, y_bf16, nullptr, z_f32_or_null, M, N, Kp, ldy_bf16, act, stream, yT_bf16, ld_yT);
+}
+/* plain fp32 product y[M][ld_y] = x W^T with a row pitch ld_y >= N (floats, multiple of 4): lets an output whose own pitch no tensor map accepts (N % 4 != 0) be
+ * computed on the CTA-pair path into a padded scratch.  Returns -2 when the shape does not qualify (then use uhc_linear_forward_tc). */
+int uhc_linear_forward_tc_f32_pitched(const void *x_bf16, const void *W_bf16, float *y_f32, int ld_y, int M, int N, int Kp, void *stream) {
+    if (!y_f32 || ld_y < N || ld_y % 4 != 0 || !pair_enabled() || !tma_store_enabled() || M < 256 || N < 256 || Kp / BK < 256) { g_tc_err = "uhc_linear_forward_tc_f32_pitched: shape not eligible"; return -2; }
+    return linear_tc_impl(x_bf16, W_bf16, nullptr, nullptr, y_f32, nullptr, M, N, Kp, 0, UHC_ACT_NONE, stream, nullptr, 0, ld_y);
 }
 int uhc_tc_tma_store_enabled(void) { return tma_store_enabled() ? 1 : 0; }
 /* backward through one Linear + the previous layer's activation in ONE kernel:  dz_prev = (dz W) * act'(z_prev)  as bf16 [M][ld_dz] and transposed [K][ld_dzT],

@@ -118,6 +118,7 @@ struct UhcPpoTrainer {
     UhcNetDesc val{};
     NetBuf vb;
     void *xb = nullptr, *xT = nullptr, *lb = nullptr;                   // bf16 states [M][Dp], transpose [D][Mp], last states [E][Dp]
+    float *dWpad = nullptr; long dWpad_n = 0;                          // dW of a layer whose input width is not a multiple of 4, at a pitch the TMA engine accepts
     void *dz2 = nullptr, *dzT2 = nullptr;                               // second dz / dz^T pair: the fused dX + activation-backward GEMM reads one pair and writes the other
     void *dz = nullptr, *dzT = nullptr, *hT = nullptr, *WT = nullptr;   // shared backward scratch (the nets run back to back on one stream)
     float *dh = nullptr, *dmean = nullptr, *dv = nullptr, *fixed = nullptr, *adv = nullptr, *ret = nullptr, *last_v = nullptr, *inv_count = nullptr;
@@ -189,7 +190,13 @@ int net_backward(UhcPpoTrainer *t, const UhcNetDesc &n, NetBuf &nb, const float 
             if (nb.actsT[i]) hT = nb.actsT[i];           // written by the forward pass' epilogue with pitch pad64(M)
             else { CKU(uhc_transpose_bf16(nb.acts[i], t->hT, (int)M, K, (int)pad64(K), (int)Mp, st), "transpose h"); hT = t->hT; }
         }
-        CKU(uhc_linear_forward_tc(dzT, hT, nullptr, nullptr, n.gfull + n.w_off[i], N, K, (int)Mp, 0, UHC_ACT_NONE, st), "dW GEMM");           // dW = dz^T h
+        // dW = dz^T h.  A row length that is not a multiple of 4 floats (657 inputs) has no tensor map: that product runs at a padded pitch, then the rows are copied
+        const int Kq = (K + 3) & ~3;
+        if (K != Kq && t->dWpad && (long)N * Kq <= t->dWpad_n && uhc_linear_forward_tc_f32_pitched(dzT, hT, t->dWpad, Kq, N, K, (int)Mp, st) == 0) {
+            g_launches += 2;          // the GEMM and the row copy
+            CKP(cudaMemcpy2DAsync(n.gfull + n.w_off[i], (size_t)K * 4, t->dWpad, (size_t)Kq * 4, (size_t)K * 4, N, cudaMemcpyDeviceToDevice, st));
+        } else
+            CKU(uhc_linear_forward_tc(dzT, hT, nullptr, nullptr, n.gfull + n.w_off[i], N, K, (int)Mp, 0, UHC_ACT_NONE, st), "dW GEMM");
         if (i > 0) {
             CKU(uhc_transpose_bf16(n.W_bf16[i], t->WT, N, K, n.kp[i], (int)Np, st), "transpose W");
             if (uhc_tc_tma_store_enabled() && n.act != UHC_ACT_NONE && K % 4 == 0) {
@@ -326,6 +333,13 @@ static int trainer_create(const UhcNetDesc *pnets, int nprim, const UhcNetDesc *
     if (nprim > 0) rc = rc || dalloc(t, &t->xall, (size_t)nprim * cap * A * 4, false) || dalloc(t, &t->dxall, (size_t)nprim * cap * A * 4, false) ||
                          dalloc(t, &t->mixw, (size_t)cap * nprim * 4, false) || dalloc(t, &t->dcomp, (size_t)cap * nprim * 4, false) || dalloc(t, &t->mean, (size_t)cap * A * 4, false);
     rc = rc || dalloc(t, &t->xb, (size_t)cap * pad64(D) * 2, true) || dalloc(t, &t->xT, (size_t)D * capp * 2, true) || dalloc(t, &t->lb, (size_t)max_envs * pad64(D) * 2, true);
+    {   // scratch for the dW of layers with K % 4 != 0
+        long need = 0;
+        auto scan = [&](const UhcNetDesc &n) { for (int i = 0; i < n.nlayers; i++) if (n.dims[i] % 4) { const long v = (long)n.dims[i + 1] * ((n.dims[i] + 3) & ~3); if (v > need) need = v; } };
+        for (auto &n : t->pnets) scan(n);
+        scan(t->val);
+        if (need) { void *p = nullptr; rc = rc || dalloc(t, &p, (size_t)need * 4, false); t->dWpad = (float *)p; t->dWpad_n = need; }
+    }
     rc = rc || dalloc(t, &t->dz2, (size_t)cap * pad64(maxN) * 2, true) || dalloc(t, &t->dzT2, (size_t)maxN * capp * 2, true);
     rc = rc || dalloc(t, &t->dz, (size_t)cap * pad64(maxN) * 2, true) || dalloc(t, &t->dzT, (size_t)maxN * capp * 2, true) || dalloc(t, &t->hT, (size_t)maxKh * capp * 2, true) ||
          dalloc(t, &t->WT, (size_t)maxKh * pad64(maxN) * 2, true) || dalloc(t, &t->dh, (size_t)cap * maxKh * 4, false);
