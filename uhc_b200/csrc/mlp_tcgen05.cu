@@ -820,7 +820,12 @@ bool pair_enabled() {
     if (on < 0) { const char *e = getenv("UHC_TC_PAIR"); on = e ? (e[0] != '0') : 1; }
     return on != 0;
 }
-bool pair_shape(int M, int N) { return pair_enabled() && M >= 16384 && N >= 256; }
+int pair_min_rows() {      // smallest M the pair kernel takes (UHC_TC_PAIR_MINM): below it the 128 x 128 tiles of k_linear_tc spread over more SMs
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("UHC_TC_PAIR_MINM"); v = e ? atoi(e) : 16384; if (v < 256) v = 256; }
+    return v;
+}
+bool pair_shape(int M, int N) { return pair_enabled() && M >= pair_min_rows() && N >= 256; }
 int pair_attr() {
     static bool attr_set[64] = {false};
     int dev = 0; cudaGetDevice(&dev);
