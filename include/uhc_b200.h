@@ -23,7 +23,7 @@ extern "C" {
 #define UHC_ACT_DIM 105       /* action width of the default configuration (implicit residual force + meta-PD) */
 #define UHC_MAX_ACT_DIM 315   /* explicit residual force + meta-PD */
 #define UHC_OBS_DIM_V1 784    /* obs_v 1 (get_full_obs_v1); obs_v 3 is UHC_OBS_DIM * fut_frames */
-#define UHC_EX_SIZE 576   /* expert frame record: qpos76 qvel75 wbpos72 wbquat96 bquat96 bangvel72 ee_wpos15 body_com72 (com = its first 3) pad2 */
+#define UHC_EX_SIZE 576       /* expert frame record: qpos76 qvel75 wbpos72 wbquat96 bquat96 bangvel72 ee_wpos15 body_com72 (com = its first 3) pad2 */
 #define UHC_BODYF 20
 
 typedef struct UhcEngine UhcEngine;
@@ -70,6 +70,10 @@ typedef struct {
                              * 0 is read as 2.  uhc_engine_obs_dim() gives the row width of every obs buffer. */
     int fut_frames, fut_skip;   /* cfg.fut_frames / cfg.skip of obs_v 3 (both default to 10 when <= 0, as cc_cfg.get does) */
     int no_shape;               /* != 0: cfg.has_shape false -- the v2 block carries no shape vector (640 dims instead of 657, humanoid_im.py:499-500) */
+    /* cfg.env_term_body (humanoid_im.py:1223-1229): 0 = "body" (mean body-position error above body_diff_thresh), 1 = "root" (root height more than 0.1 m below the
+     * lowest of the episode's window of the clip, expert["height_lb"]), 2 = "Head" (height of body head_body below expert["head_height_lb"] - 0.1).  The kernel
+     * takes the minimum over the window [start, start + len) itself: the reference's expert IS that slice (dataset_amass_single.py:238-244, tools.py:94-95). */
+    int term_body, head_body;
 } UhcEnvCfg;
 
 const char *uhc_last_error(void);

@@ -448,6 +448,8 @@ typedef struct {
                                          3 = get_full_obs_v3 (fut_frames v2 blocks against the expert frames cur_t + 1 + i * skip, humanoid_im.py:505-513) */
     int fut_frames, fut_skip, obs_dt; /* obs_dt: the delta_t of the v2 block being written */
     int no_shape;                     /* cfg.has_shape false: the v2 block has no shape vector (640 dims) */
+    int term_body, head_body;         /* cfg.env_term_body (humanoid_im.py:1223-1229): 0 "body", 1 "root", 2 "Head" (head_body = its model body) */
+    double height_lb, head_height_lb; /* expert["height_lb"], ["head_height_lb"] (uhc/utils/tools.py:94-95): lowest root / head height of the loaded expert */
 } OrEnv;
 
 OrEnv *or_env_create(OrModel *m) {
@@ -471,6 +473,15 @@ int or_env_action_dim(const OrEnv *e) { return NU + e->vf_dim + (e->meta_pd ? 30
 void or_env_set_obs_v(OrEnv *e, int obs_v, const double *body_com) { e->obs_v = (obs_v == 1 || obs_v == 3) ? obs_v : 2; e->ex.body_com = body_com; }
 void or_env_set_future(OrEnv *e, int fut_frames, int skip) { e->fut_frames = fut_frames > 0 ? fut_frames : 10; e->fut_skip = skip > 0 ? skip : 10; }
 void or_env_set_has_shape(OrEnv *e, int has_shape) { e->no_shape = !has_shape; }
+/* call after or_env_set_expert: the bounds are minima over the loaded expert (tools.py:94-95; torch_smpl_humanoid.py:250 for height_lb) */
+void or_env_set_term_body(OrEnv *e, int mode, int head_body) {
+    e->term_body = (mode == 1 || mode == 2) ? mode : 0; e->head_body = (head_body >= 0 && head_body < NB) ? head_body : 13;
+    e->height_lb = e->head_height_lb = 1e30;
+    for (int t = 0; t < e->ex.len; t++) {
+        if (e->ex.qpos[(size_t)t*NQ + 2] < e->height_lb) e->height_lb = e->ex.qpos[(size_t)t*NQ + 2];
+        if (e->ex.wbpos[(size_t)t*3*NB + 3*e->head_body + 2] < e->head_height_lb) e->head_height_lb = e->ex.wbpos[(size_t)t*3*NB + 3*e->head_body + 2];
+    }
+}
 static int obs_block_dim(const OrEnv *e) { return e->no_shape ? 640 : 657; }
 int or_env_obs_dim(const OrEnv *e) { return e->obs_v == 1 ? 784 : (e->obs_v == 3 ? obs_block_dim(e)*e->fut_frames : obs_block_dim(e)); }
 void or_env_free(OrEnv *e) { if (e) { or_data_free(e->d); free(e); } }
@@ -678,7 +689,9 @@ int or_env_step(OrEnv *e, const double *action, double *obs, int *fail, int *end
     e->cur_t += 1;
     or_body_quat(e, e->bquat);
     double bd = or_body_diff(e);
-    *fail = bd > e->body_diff_thresh;
+    if (e->term_body == 1) *fail = d->qpos[2] < e->height_lb - 0.1;                              /* humanoid_im.py:1226 */
+    else if (e->term_body == 2) *fail = d->xpos[e->head_body][2] < e->head_height_lb - 0.1;     /* :1221-1224: data.body_xpos of the last forward pass */
+    else *fail = bd > e->body_diff_thresh;
     for (int i = 0; i < NQ; i++) if (!isfinite(d->qpos[i])) *fail = 1;
     *end = (e->cur_t >= e->env_episode_len) || (e->cur_t + e->start_ind >= e->ex.len + e->trail_steps - 1);
     *percent = (double)e->cur_t/(e->ex.len - 1);

@@ -203,3 +203,20 @@ def test_obs_v3_no_shape_no_residual_force_matches_reference_golden(golden_dir, 
         assert np.abs(st[:76] - g["qpos"][t]).max() < tol_q, t
         assert np.abs(obs - g["obs"][t]).max() < tol_o, t
         assert abs(r - g["reward"][t]) < tol_o and info["c_info"][4] == 0.0
+
+
+@pytest.mark.parametrize("term", ["root", "Head"])
+def test_env_term_body_root_and_head_flags_match_reference_golden(golden_dir, term):
+    """env_term_body root / Head in the kernel source (host emulation, fp64): the reference's own fail flags, the window minimum taken in the kernel"""
+    g = np.load(os.path.join(golden_dir, f"env_sway_term{term.lower()}_noise.npz"))
+    z = np.load(os.path.join(golden_dir, "expert_sway.npz"))
+    ex = {k: z[k] for k in z.files}
+    so = np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+    e = Emu(64, term_body={"root": 1, "Head": 2}[term], head_body=int(g["head_idx"]) if term == "Head" else 13)
+    e.load_clips([ex], [so])
+    e.reset()
+    fails = []
+    for t in range(34):
+        _, _, _, info = e.step(g["action"][t])
+        fails.append(info["fail"])
+    assert fails == [bool(f) for f in g["fail"][:34]] and any(fails)

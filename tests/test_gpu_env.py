@@ -386,3 +386,25 @@ def test_obs_v3_no_shape_no_residual_force_matches_reference_trace(golden_dir, p
         assert np.abs(o[1].cpu().numpy() - g["obs"][t]).max() < tol_o, t
         assert abs(float(r[1]) - g["reward"][t]) < tol_o and float(c[1, 4]) == 0.0
     eng.close()
+
+
+@pytest.mark.parametrize("term", ["root", "Head"])
+def test_env_term_body_root_and_head_match_reference_flags(golden_dir, term):
+    """env_term_body root / Head through the C ABI (fp64 kernels, so that the crossing step is the reference's): the fail flags of the reference's own step()"""
+    import torch
+    from uhc_b200.engine import Engine
+    g = np.load(os.path.join(golden_dir, f"env_sway_term{term.lower()}_noise.npz"))
+    ex, so = _expert(golden_dir, "sway")
+    E = 3
+    eng = Engine(E, precision=64, term_body=term, head_body=int(g["head_idx"]) if term == "Head" else 13)
+    eng.load_clips([ex], [so])
+    eng.reset()
+    fails = []
+    for t in range(len(g["fail"])):
+        a = torch.tensor(np.tile(g["action"][t], (E, 1)), dtype=torch.float32, device="cuda")
+        o, r, c, f, en, pct = eng.step(a)
+        torch.cuda.synchronize()
+        fails.append(bool(int(f[E - 1])))
+        assert abs(eng.get_state(E - 1)["qpos"][2] - g["root_z"][t]) < 1e-6
+    eng.close()
+    assert fails == [bool(x) for x in g["fail"]]

@@ -99,3 +99,21 @@ def test_obs_v3_no_shape_no_residual_force_trace_matches_reference_python(golden
         np.testing.assert_allclose(obs, g["obs"][t], rtol=0, atol=1e-5, err_msg=f"obs t={t}")
         np.testing.assert_allclose(info["c_info"], g["c_info"][t], rtol=0, atol=1e-6)
         assert abs(r - g["reward"][t]) < 1e-6 and info["c_info"][4] == 0.0
+
+
+@pytest.mark.parametrize("term", ["root", "Head"])
+def test_env_term_body_root_and_head_flags_match_reference_python(golden_dir, term):
+    """cfg.env_term_body "root" / "Head" (humanoid_im.py:1223-1226): the fail flags of the reference's own step() over the noise trajectory of env_sway_noise
+    (root below expert["height_lb"] - 0.1 from step 26, head below expert["head_height_lb"] - 0.1 from step 23, the default body criterion from step 31)."""
+    g = np.load(os.path.join(golden_dir, f"env_sway_term{term.lower()}_noise.npz"))
+    ex, so = load_expert(golden_dir, "sway")
+    env = O.Env(O.Model(), ex, so)
+    env.set_term_body(term, head_body=int(g["head_idx"]) if term == "Head" else 13)
+    env.reset()
+    fails = []
+    for t in range(len(g["fail"])):
+        _, _, _, info = env.step(g["action"][t])
+        fails.append(info["fail"])
+        assert abs(env.d.qpos[2] - g["root_z"][t]) < 1e-7 and info["end"] == bool(g["end"][t])
+    assert fails == [bool(f) for f in g["fail"]]
+    assert 20 < int(np.argmax(fails)) < 31           # (a different step than the body-position criterion's 31)

@@ -23,7 +23,7 @@ EXPERT_KEYS = ["qpos", "qvel", "wbpos", "wbquat", "bquat", "body_com", "bangvel"
                "rlinv_local", "rangv"]
 
 
-def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train", out_tag=None, save_expert=True):
+def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train", out_tag=None, save_expert=True, term_body=None):
     from uhc.losses.reward_function import reward_func
     reward = reward_func[cfg.reward_id]                       # world_rfc_implicit (uhc_implicit_shape) / world_rfc_explicit (uhc_explicit)
     seq = dl.get_sample_from_key(key, full_sample=False, fr_start=0)
@@ -32,6 +32,8 @@ def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train", 
     env = H.make_env(cfg, seq, mode=mode)
     env.seed(seed)
     ex = env.expert
+    if term_body == "Head" and "head_height_lb" not in ex:      # the AMASS loader's expert carries height_lb only (torch_smpl_humanoid.py:250); uhc/utils/tools.py:95 defines the head bound
+        ex["head_height_lb"] = ex["wbpos"].reshape(ex["wbpos"].shape[0], -1, 3)[:, env.get_head_idx(), 2].min()
     if save_expert:
         np.savez_compressed(os.path.join(OUT, f"expert_{tag}.npz"), pose_aa=seq["pose_aa"][:, :72].copy(),
                             trans=seq["trans"], beta=seq["beta"], gender=seq["gender"],
@@ -60,7 +62,14 @@ def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train", 
         rec["prev_bquat"].append(env.prev_bquat.copy()); rec["ncon"].append(env.data.ncon)
         if info["end"]:
             break
-    np.savez_compressed(os.path.join(OUT, f"env_{out_tag or tag}_{act_mode}.npz"), obs0=obs0, expert=f"expert_{tag}.npz", vf_dim=env.vf_dim,
+    extra = {"head_idx": env.get_head_idx(), "head_height_lb": ex["head_height_lb"]} if term_body == "Head" else {}
+    if term_body:       # same trajectory as the env_<tag>_<act_mode> golden (the actions do not depend on the flags): keep the flags and the heights they are decided on
+        np.savez_compressed(os.path.join(OUT, f"env_{out_tag}_{act_mode}.npz"), base=f"env_{tag}_{act_mode}.npz", term_body=term_body, height_lb=ex["height_lb"],
+                            fail=np.array(rec["fail"]), end=np.array(rec["end"]), percent=np.array(rec["percent"]), action=np.array(rec["action"]),
+                            root_z=np.array(rec["qpos"])[:, 2], head_z=np.array(rec["xpos"])[:, env.get_head_idx(), 2], **extra)
+        print(out_tag, "fail from step", int(np.argmax(rec["fail"])))
+        return
+    np.savez_compressed(os.path.join(OUT, f"env_{out_tag or tag}_{act_mode}.npz"), obs0=obs0, expert=f"expert_{tag}.npz", vf_dim=env.vf_dim, **extra,
                         **{k: np.array(v) for k, v in rec.items()})
     print(tag, act_mode, "steps", len(rec["reward"]), "fails", int(np.sum(rec["fail"])), "mean r %.4f" % np.mean(rec["reward"]),
           "max ncon", max(rec["ncon"]))
@@ -402,6 +411,13 @@ def main():
         from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
         dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
         gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 12, "noise", out_tag="sway_obsv3", save_expert=False)
+    if "term" in what:           # cfg.env_term_body "root" / "Head" (humanoid_im.py:1223-1226): the episode fails when the root / the head drops 0.1 m below the clip's lowest
+        from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
+        for tb in ("root", "Head"):
+            cfg = H.make_cfg()
+            cfg.env_term_body = tb
+            dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
+            gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 45, "noise", out_tag="sway_term" + tb.lower(), save_expert=False, term_body=tb)
     if "reactive" in what:
         cfg = H.make_cfg()
         from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle

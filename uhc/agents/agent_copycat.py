@@ -80,7 +80,7 @@ class AgentCopycat:
             assert not cfg.get("has_shape", False), "obs_v 1 carries no shape vector (has_shape: false in config/release/uhc_implicit.yml)"
         # variants the batched engine does not implement must not be accepted silently
         assert cfg.fix_std, "log_std is not a trained parameter in this engine (fix_std: true in every released config)"
-        assert cfg.get("env_term_body", "body") == "body", "env_term_body: only 'body' (calc_body_diff) is implemented"
+        assert cfg.get("env_term_body", "body") in ("body", "root", "Head"), "env_term_body: 'body' (calc_body_diff), 'root' or 'Head' (humanoid_im.py:1223-1229)"
         rfc_mode = cfg.get("residual_force_mode", "implicit") if cfg.residual_force else "none"     # residual_force: false -> no residual-force dims (humanoid_im.py:231-243)
         assert rfc_mode in ("implicit", "explicit", "none"), "residual_force_mode: implicit | explicit"
         if rfc_mode == "explicit":      # the kernel restates the release settings of the explicit mode (config/release/uhc_explicit.yml)
@@ -100,7 +100,8 @@ class AgentCopycat:
             meta_pd=int(cfg.meta_pd), env_episode_len=cfg.env_episode_len, trail_steps=cfg.env_expert_trail_steps, w=w, k=kk, rfc_mode=rfc_mode,
             obs_v=int(cfg.obs_v), fut_frames=int(cfg.get("fut_frames", 10)), fut_skip=int(cfg.get("skip", 10)),
             has_shape=bool(cfg.get("has_shape", False)) and bool(cfg.get("has_shape_obs", True)), actor_type=cfg.actor_type, num_primitive=int(cfg.get("num_primitive", 8)), composer_dim=tuple(cfg.get("composer_dim", [300, 200])),
-            reactive_v=int(cfg.get("reactive_v", 0)), reactive_rate=float(cfg.get("reactive_rate", 0.3)))
+            reactive_v=int(cfg.get("reactive_v", 0)), reactive_rate=float(cfg.get("reactive_rate", 0.3)),
+            term_body=cfg.get("env_term_body", "body"), head_body=self.model_tables.body_names.index("Head"))
         self.policy_net, self.value_net, self.running_state = self.agent.policy, self.agent.value, self.agent.running_state
         self.state_dim, self.action_dim = self.agent.obs_dim, self.agent.act_dim
         self.expert_reward = reward_func[cfg.reward_id]
@@ -279,6 +280,7 @@ class AgentCopycat:
                     rfc_mode=cfg.get("residual_force_mode", "implicit") if cfg.residual_force else "none", obs_v=int(cfg.obs_v),
                     fut_frames=int(cfg.get("fut_frames", 10)), fut_skip=int(cfg.get("skip", 10)),
                     has_shape=bool(cfg.get("has_shape", False)) and bool(cfg.get("has_shape_obs", True)),
+                    term_body=cfg.get("env_term_body", "body"), head_body=self.model_tables.body_names.index("Head"),
                     w=[rw.get(k, d) for k, d in (("w_p", 0.6), ("w_v", 0.1), ("w_e", 0.2), ("w_c", 0.1), ("w_vf", 0.0))],
                     k=[rw.get(k, d) for k, d in (("k_p", 2), ("k_v", 0.005), ("k_e", 20), ("k_c", 1000), ("k_vf", 1))])
 

@@ -249,8 +249,24 @@ UHC_DEV int env_step_warp(const EngineView<Real> &ev, int env, Work<Real> &w, co
     LANES_END
     body_quat(w, bq);
     Real bd, rew, ci[5];
-    diff_and_reward(mdl, w.cfg, w, expert_frame(ev, clip, start, len, cur_t), bq, pbq, &bd, &rew, ci, action);
-    int fail = bd > ev.cfg.body_diff_thresh;
+    const Real *exf = expert_frame(ev, clip, start, len, cur_t);
+    diff_and_reward(mdl, w.cfg, w, exf, bq, pbq, &bd, &rew, ci, action);
+    // cfg.env_term_body (humanoid_im.py:1223-1229): the mean body-position error; or the new root height / the head height of the last forward pass (data.body_xpos)
+    // against the lowest of the episode's expert window - 0.1 m (expert["height_lb"], ["head_height_lb"]: tools.py:94-95 on the slice the loader handed out)
+    int fail;
+    if (ev.cfg.term_body == 0) fail = bd > ev.cfg.body_diff_thresh;
+    else {
+        const Real *f0 = ev.expert + (size_t)(UHC_LDG(ev.clip_adr + clip) + start) * EX_SIZE;
+        const int off = ev.cfg.term_body == 1 ? EX_QPOS + 2 : EX_WBPOS + 3 * ev.cfg.head_body + 2;
+        LVAR(Real, neg);
+        LANES_BEGIN
+        Real mx = Real(-1e30);
+        for (int i = lane; i < len; i += 32) { const Real z = -(Real)UHC_LDG(f0 + (size_t)i * EX_SIZE + off); mx = z > mx ? z : mx; }
+        LV(neg) = mx;
+        LANES_END
+        const Real lb = -WMAX(neg);
+        fail = (ev.cfg.term_body == 1 ? w.q[2] : w.xpos[ev.cfg.head_body][2]) < lb - Real(0.1);
+    }
     {   // a non-finite state can never pass "bd > thresh": flag it as a failure (mirrors the try/except at :1207-1211)
         LVAR(int, bad);
         LANES_BEGIN

@@ -825,17 +825,31 @@ int pair_min_rows() {      // smallest M the pair kernel takes (UHC_TC_PAIR_MINM
     if (v < 0) { const char *e = getenv("UHC_TC_PAIR_MINM"); v = e ? atoi(e) : 16384; if (v < 256) v = 256; }
     return v;
 }
-bool pair_shape(int M, int N) { return pair_enabled() && M >= pair_min_rows() && N >= 256; }
-int pair_attr() {
-    static bool attr_set[64] = {false};
+int pair_probe();
+bool pair_shape(int M, int N) { return pair_enabled() && M >= pair_min_rows() && N >= 256 && pair_probe() == 1; }
+// per device: 0 = not probed, 1 = the pair kernel can run (attribute set, at least one 2-CTA cluster with its shared memory fits), 2 = it cannot (then every shape
+// stays on k_linear_tc: a partitioned or smaller GPU is a slower path, not an error)
+int g_pair_state[64] = {0};
+int pair_probe() {
     int dev = 0; cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        if (cudaFuncSetAttribute(k_linear_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_linear_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES) != cudaSuccess) { g_tc_err = "cudaFuncSetAttribute (pair kernel) failed"; return -1; }
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    if (dev < 0 || dev >= 64) return 2;
+    if (g_pair_state[dev]) return g_pair_state[dev];
+    int st = 1;
+    if (cudaFuncSetAttribute(k_linear_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_linear_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES) != cudaSuccess) st = 2;
+    if (st == 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2, 1, 1); cfg.blockDim = dim3(P_THREADS, 1, 1); cfg.dynamicSmemBytes = P_SMEM_BYTES;
+        cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, k_linear_tc2<false>, &cfg) != cudaSuccess || nclusters < 1) st = 2;
     }
-    return 0;
+    (void)cudaGetLastError();
+    g_pair_state[dev] = st;
+    return st;
 }
+int pair_attr() { if (pair_probe() != 1) { g_tc_err = "the CTA-pair kernel cannot run on this device"; return -1; } return 0; }
 int pair_grid(int M, int N) {
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = ((M + 255) / 256) * ((N + 255) / 256), pairs = sms / 2;
@@ -868,7 +882,7 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
     const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM), nkb = Kp / BK;
     // a plain fp32 product with a long reduction and few output tiles (dW = dz^T h): CTA pairs, the reduction split into as many slices as fill the pairs evenly,
     // partial tiles added into the zeroed output by the TMA engine
-    if (pair_enabled() && tma_store_enabled() && !y_bf16_or_null && !z_f32_or_null && !yT_bf16_or_null && act == UHC_ACT_NONE && y_f32_or_null && M >= 256 && N >= 256 &&
+    if (pair_enabled() && pair_probe() == 1 && tma_store_enabled() && !y_bf16_or_null && !z_f32_or_null && !yT_bf16_or_null && act == UHC_ACT_NONE && y_f32_or_null && M >= 256 && N >= 256 &&
         nkb >= 256 && ((uintptr_t)y_f32_or_null & 15) == 0 && ld_yf % 4 == 0 && ld_yf >= N) {
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int pairs = sms / 2, pt = ((M + 255) / 256) * ((N + 255) / 256);
@@ -951,7 +965,7 @@ int uhc_linear_forward_tc_train_t(const void *x_bf16, const void *W_bf16, const 
 /* plain fp32 product y[M][ld_y] = x W^T with a row pitch ld_y >= N (floats, multiple of 4): lets an output whose own pitch no tensor map accepts (N % 4 != 0) be
  * computed on the CTA-pair path into a padded scratch.  Returns -2 when the shape does not qualify (then use uhc_linear_forward_tc). */
 int uhc_linear_forward_tc_f32_pitched(const void *x_bf16, const void *W_bf16, float *y_f32, int ld_y, int M, int N, int Kp, void *stream) {
-    if (!y_f32 || ld_y < N || ld_y % 4 != 0 || !pair_enabled() || !tma_store_enabled() || M < 256 || N < 256 || Kp / BK < 256) { g_tc_err = "uhc_linear_forward_tc_f32_pitched: shape not eligible"; return -2; }
+    if (!y_f32 || ld_y < N || ld_y % 4 != 0 || !pair_enabled() || pair_probe() != 1 || !tma_store_enabled() || M < 256 || N < 256 || Kp / BK < 256) { g_tc_err = "uhc_linear_forward_tc_f32_pitched: shape not eligible"; return -2; }
     return linear_tc_impl(x_bf16, W_bf16, nullptr, nullptr, y_f32, nullptr, M, N, Kp, 0, UHC_ACT_NONE, stream, nullptr, 0, ld_y);
 }
 int uhc_tc_tma_store_enabled(void) { return tma_store_enabled() ? 1 : 0; }

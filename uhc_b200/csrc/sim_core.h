@@ -110,6 +110,7 @@ struct EnvCfg {
     int fut_frames, fut_skip;                     //   3 = get_full_obs_v3 (:505-513): fut_frames v2 blocks against the expert frames cur_t + 1 + i * skip
     int has_shape, obs_block;                     // cfg.has_shape (:499-500): the v2 block ends with the 17 shape dims (657) or not (640); obs_block = its width
     signed char vf_slot[NB];                      // explicit: residual-force slot of body b (vf_bodies = SMPL_BONE_ORDER_NAMES, humanoid_im.py:236-237)
+    int term_body, head_body;                     // cfg.env_term_body (humanoid_im.py:1223-1229): 0 body-position error, 1 root height, 2 height of body head_body
 };
 constexpr int VF_BODY_DIM = 9, MAX_ACT_DIM = NU + VF_BODY_DIM * NB + 30;
 
