@@ -74,6 +74,7 @@ typedef struct {
      * lowest of the episode's window of the clip, expert["height_lb"]), 2 = "Head" (height of body head_body below expert["head_height_lb"] - 0.1).  The kernel
      * takes the minimum over the window [start, start + len) itself: the reference's expert IS that slice (dataset_amass_single.py:238-244, tools.py:94-95). */
     int term_body, head_body;
+    int reward_mul;             /* != 0: reward_id world_rfc_implicit_v1_mul (reward_function.py:174-250): pose * vel * ee * com * (vf if w[4] != 0), same five c_info terms */
 } UhcEnvCfg;
 
 const char *uhc_last_error(void);

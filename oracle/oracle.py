@@ -161,6 +161,10 @@ class Env:
     def set_has_shape(self, has_shape):
         lib().or_env_set_has_shape(self.h, C.c_int(int(bool(has_shape))))
 
+    def set_reward_mul(self, on=True):
+        """reward_id world_rfc_implicit_v1_mul: the product of the five terms (reward_function.py:174-250)"""
+        lib().or_env_set_reward_mul(self.h, C.c_int(int(bool(on))))
+
     def set_term_body(self, term_body, head_body=13):
         """cfg.env_term_body (humanoid_im.py:1223-1229): "body" (default), "root" or "Head"; the height bounds are minima over the loaded expert"""
         lib().or_env_set_term_body(self.h, C.c_int({"body": 0, "root": 1, "Head": 2}[term_body]), C.c_int(int(head_body)))

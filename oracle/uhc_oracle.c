@@ -449,6 +449,7 @@ typedef struct {
     int fut_frames, fut_skip, obs_dt; /* obs_dt: the delta_t of the v2 block being written */
     int no_shape;                     /* cfg.has_shape false: the v2 block has no shape vector (640 dims) */
     int term_body, head_body;         /* cfg.env_term_body (humanoid_im.py:1223-1229): 0 "body", 1 "root", 2 "Head" (head_body = its model body) */
+    int reward_mul;                   /* reward_id world_rfc_implicit_v1_mul (reward_function.py:174-250) */
     double height_lb, head_height_lb; /* expert["height_lb"], ["head_height_lb"] (uhc/utils/tools.py:94-95): lowest root / head height of the loaded expert */
 } OrEnv;
 
@@ -473,6 +474,7 @@ int or_env_action_dim(const OrEnv *e) { return NU + e->vf_dim + (e->meta_pd ? 30
 void or_env_set_obs_v(OrEnv *e, int obs_v, const double *body_com) { e->obs_v = (obs_v == 1 || obs_v == 3) ? obs_v : 2; e->ex.body_com = body_com; }
 void or_env_set_future(OrEnv *e, int fut_frames, int skip) { e->fut_frames = fut_frames > 0 ? fut_frames : 10; e->fut_skip = skip > 0 ? skip : 10; }
 void or_env_set_has_shape(OrEnv *e, int has_shape) { e->no_shape = !has_shape; }
+void or_env_set_reward_mul(OrEnv *e, int on) { e->reward_mul = on ? 1 : 0; }
 /* call after or_env_set_expert: the bounds are minima over the loaded expert (tools.py:94-95; torch_smpl_humanoid.py:250 for height_lb) */
 void or_env_set_term_body(OrEnv *e, int mode, int head_body) {
     e->term_body = (mode == 1 || mode == 2) ? mode : 0; e->head_body = (head_body >= 0 && head_body < NB) ? head_body : 13;
@@ -657,6 +659,7 @@ double or_reward(const OrEnv *e, const double *action, double *cinfo) { /* rewar
     if (e->rfc_mode == 0) for (int i = 0; i < 6; i++) vf2 += action[NU+i]*action[NU+i];
     else if (e->rfc_mode == 1) for (int i = 0; i < NB; i++) for (int k = 3; k < 9; k++) vf2 += action[NU+9*i+k]*action[NU+9*i+k];   /* force + torque part of every body's slot (:321-327) */
     cinfo[0] = exp(-e->k[0]*pose2); cinfo[1] = exp(-e->k[1]*vel2); cinfo[2] = exp(-e->k[2]*ee2); cinfo[3] = exp(-e->k[3]*com2); cinfo[4] = e->rfc_mode == 2 ? 0.0 : exp(-e->k[4]*vf2);   /* residual_force off: vf_reward = 0.0 (reward_function.py:68-72) */
+    if (e->reward_mul) return cinfo[0]*cinfo[1]*cinfo[2]*cinfo[3]*(e->w[4] != 0.0 ? cinfo[4] : 1.0);   /* :243-245 */
     double r = 0, ws = 0; for (int i = 0; i < 5; i++) { r += e->w[i]*cinfo[i]; ws += e->w[i]; }
     return r/ws;
 }

@@ -408,3 +408,23 @@ def test_env_term_body_root_and_head_match_reference_flags(golden_dir, term):
         assert abs(eng.get_state(E - 1)["qpos"][2] - g["root_z"][t]) < 1e-6
     eng.close()
     assert fails == [bool(x) for x in g["fail"]]
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-6), (32, 5e-3)])
+def test_multiplicative_reward_matches_reference_trace(golden_dir, precision, tol):
+    """reward_id world_rfc_implicit_v1_mul through the C ABI: the reference's reward / c_info over the noise trajectory (before the fall)"""
+    import torch
+    from uhc_b200.engine import Engine
+    g = np.load(os.path.join(golden_dir, "env_sway_rewmul_noise.npz"))
+    ex, so = _expert(golden_dir, "sway")
+    E = 2
+    eng = Engine(E, precision=precision, reward_mul=True)
+    eng.load_clips([ex], [so])
+    eng.reset()
+    for t in range(20):
+        a = torch.tensor(np.tile(g["action"][t], (E, 1)), dtype=torch.float32, device="cuda")
+        o, r, c, f, en, pct = eng.step(a)
+        torch.cuda.synchronize()
+        assert abs(float(r[E - 1]) - g["reward"][t]) < tol, t
+        assert np.abs(c[E - 1].cpu().numpy() - g["c_info"][t]).max() < tol, t
+    eng.close()

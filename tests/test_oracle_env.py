@@ -117,3 +117,17 @@ def test_env_term_body_root_and_head_flags_match_reference_python(golden_dir, te
         assert abs(env.d.qpos[2] - g["root_z"][t]) < 1e-7 and info["end"] == bool(g["end"][t])
     assert fails == [bool(f) for f in g["fail"]]
     assert 20 < int(np.argmax(fails)) < 31           # (a different step than the body-position criterion's 31)
+
+
+def test_multiplicative_reward_matches_reference_python(golden_dir):
+    """reward_id world_rfc_implicit_v1_mul (reward_function.py:174-250) over the env_sway_noise trajectory: the reference's own reward and c_info"""
+    g = np.load(os.path.join(golden_dir, "env_sway_rewmul_noise.npz"))
+    ex, so = load_expert(golden_dir, "sway")
+    env = O.Env(O.Model(), ex, so)
+    env.set_reward_mul(True)
+    env.reset()
+    for t in range(len(g["reward"])):
+        _, r, _, info = env.step(g["action"][t])
+        assert abs(r - g["reward"][t]) < 1e-7, t
+        np.testing.assert_allclose(info["c_info"], g["c_info"][t], rtol=0, atol=1e-6)
+    assert float(g["reward_weights"][4]) != 0.0 and g["reward"].min() < 0.2 < g["reward"].max()      # (w_vf = 0.05: the residual-force term is part of the product)

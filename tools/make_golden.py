@@ -23,7 +23,7 @@ EXPERT_KEYS = ["qpos", "qvel", "wbpos", "wbquat", "bquat", "body_com", "bangvel"
                "rlinv_local", "rangv"]
 
 
-def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train", out_tag=None, save_expert=True, term_body=None):
+def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train", out_tag=None, save_expert=True, term_body=None, reward_only=False):
     from uhc.losses.reward_function import reward_func
     reward = reward_func[cfg.reward_id]                       # world_rfc_implicit (uhc_implicit_shape) / world_rfc_explicit (uhc_explicit)
     seq = dl.get_sample_from_key(key, full_sample=False, fr_start=0)
@@ -63,6 +63,12 @@ def gen_env(cfg, dl, key, tag, nframes, nsteps, act_mode, seed=1, mode="train", 
         if info["end"]:
             break
     extra = {"head_idx": env.get_head_idx(), "head_height_lb": ex["head_height_lb"]} if term_body == "Head" else {}
+    if reward_only:     # same trajectory as the env_<tag>_<act_mode> golden: keep what the reward function returned
+        np.savez_compressed(os.path.join(OUT, f"env_{out_tag}_{act_mode}.npz"), base=f"env_{tag}_{act_mode}.npz", reward_id=cfg.reward_id, reward=np.array(rec["reward"]),
+                            c_info=np.array(rec["c_info"]), action=np.array(rec["action"]), reward_weights=np.array([cfg.reward_weights.get(k, d) for k, d in
+                            (("w_p", 0.6), ("w_v", 0.1), ("w_e", 0.2), ("w_c", 0.1), ("w_vf", 0.0))]))
+        print(out_tag, "mean r %.4f" % np.mean(rec["reward"]))
+        return
     if term_body:       # same trajectory as the env_<tag>_<act_mode> golden (the actions do not depend on the flags): keep the flags and the heights they are decided on
         np.savez_compressed(os.path.join(OUT, f"env_{out_tag}_{act_mode}.npz"), base=f"env_{tag}_{act_mode}.npz", term_body=term_body, height_lb=ex["height_lb"],
                             fail=np.array(rec["fail"]), end=np.array(rec["end"]), percent=np.array(rec["percent"]), action=np.array(rec["action"]),
@@ -418,6 +424,12 @@ def main():
             cfg.env_term_body = tb
             dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
             gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 45, "noise", out_tag="sway_term" + tb.lower(), save_expert=False, term_body=tb)
+    if "rewmul" in what:         # reward_id world_rfc_implicit_v1_mul (reward_function.py:174-250): the five terms of world_rfc_implicit multiplied instead of averaged
+        from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
+        cfg = H.make_cfg()
+        cfg.reward_id = "world_rfc_implicit_v1_mul"
+        dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
+        gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 30, "noise", out_tag="sway_rewmul", save_expert=False, reward_only=True)
     if "reactive" in what:
         cfg = H.make_cfg()
         from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle

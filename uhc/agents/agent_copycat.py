@@ -88,7 +88,7 @@ class AgentCopycat:
                 and not cfg.get("residual_contact_only", False) and not cfg.get("residual_contact_projection", False), \
                 "explicit residual force: only residual_force_bodies = all, one point per body, torque on, no contact gating / projection"
         # the fused reward follows the residual-force mode (world_rfc_implicit :12-88 / world_rfc_explicit :253-341), as the released configs pair them
-        assert cfg.reward_id == ("world_rfc_explicit" if rfc_mode == "explicit" else "world_rfc_implicit"), "reward_id must match residual_force_mode"
+        assert cfg.reward_id in (("world_rfc_explicit",) if rfc_mode == "explicit" else ("world_rfc_implicit", "world_rfc_implicit_v1_mul")), "reward_id must match residual_force_mode"
         assert float(cfg.get("env_init_noise", 0.0)) == 0.0, "env_init_noise > 0 is not implemented"
         self.agent = BatchedAgent(
             self.num_envs, self.data_loader.experts, self.data_loader.shapes, device=dev_index, seed=cfg.seed, policy_hsize=cfg.policy_hsize,
@@ -101,7 +101,7 @@ class AgentCopycat:
             obs_v=int(cfg.obs_v), fut_frames=int(cfg.get("fut_frames", 10)), fut_skip=int(cfg.get("skip", 10)),
             has_shape=bool(cfg.get("has_shape", False)) and bool(cfg.get("has_shape_obs", True)), actor_type=cfg.actor_type, num_primitive=int(cfg.get("num_primitive", 8)), composer_dim=tuple(cfg.get("composer_dim", [300, 200])),
             reactive_v=int(cfg.get("reactive_v", 0)), reactive_rate=float(cfg.get("reactive_rate", 0.3)),
-            term_body=cfg.get("env_term_body", "body"), head_body=self.model_tables.body_names.index("Head"))
+            term_body=cfg.get("env_term_body", "body"), head_body=self.model_tables.body_names.index("Head"), reward_mul=cfg.reward_id == "world_rfc_implicit_v1_mul")
         self.policy_net, self.value_net, self.running_state = self.agent.policy, self.agent.value, self.agent.running_state
         self.state_dim, self.action_dim = self.agent.obs_dim, self.agent.act_dim
         self.expert_reward = reward_func[cfg.reward_id]
@@ -280,7 +280,7 @@ class AgentCopycat:
                     rfc_mode=cfg.get("residual_force_mode", "implicit") if cfg.residual_force else "none", obs_v=int(cfg.obs_v),
                     fut_frames=int(cfg.get("fut_frames", 10)), fut_skip=int(cfg.get("skip", 10)),
                     has_shape=bool(cfg.get("has_shape", False)) and bool(cfg.get("has_shape_obs", True)),
-                    term_body=cfg.get("env_term_body", "body"), head_body=self.model_tables.body_names.index("Head"),
+                    term_body=cfg.get("env_term_body", "body"), head_body=self.model_tables.body_names.index("Head"), reward_mul=cfg.reward_id == "world_rfc_implicit_v1_mul",
                     w=[rw.get(k, d) for k, d in (("w_p", 0.6), ("w_v", 0.1), ("w_e", 0.2), ("w_c", 0.1), ("w_vf", 0.0))],
                     k=[rw.get(k, d) for k, d in (("k_p", 2), ("k_v", 0.005), ("k_e", 20), ("k_c", 1000), ("k_vf", 1))])
 

@@ -80,7 +80,7 @@ class HumanoidEnv:
                              fut_frames=int(cfg.get("fut_frames", 10)), fut_skip=int(cfg.get("skip", 10)),
                              has_shape=bool(cfg.get("has_shape", False)) and bool(cfg.get("has_shape_obs", True)),
                              term_body=cfg.get("env_term_body", "body") if cfg.get("env_term_body", "body") in ("root", "Head") else "body",
-                             head_body=self.model_tables.body_names.index("Head"))
+                             head_body=self.model_tables.body_names.index("Head"), reward_mul=cfg.get("reward_id", "") == "world_rfc_implicit_v1_mul")
         self.dt = self.model_tables.dt * 15
         # set_action_spaces (humanoid_im.py:226-255): implicit = 6 residual-force dims, explicit = 9 per body x 24 bodies
         explicit = cfg.get("residual_force_mode", "implicit") == "explicit"

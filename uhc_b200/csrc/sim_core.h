@@ -111,6 +111,7 @@ struct EnvCfg {
     int has_shape, obs_block;                     // cfg.has_shape (:499-500): the v2 block ends with the 17 shape dims (657) or not (640); obs_block = its width
     signed char vf_slot[NB];                      // explicit: residual-force slot of body b (vf_bodies = SMPL_BONE_ORDER_NAMES, humanoid_im.py:236-237)
     int term_body, head_body;                     // cfg.env_term_body (humanoid_im.py:1223-1229): 0 body-position error, 1 root height, 2 height of body head_body
+    int reward_mul;                               // world_rfc_implicit_v1_mul (reward_function.py:174-250): the product of the terms instead of their weighted mean
 };
 constexpr int VF_BODY_DIM = 9, MAX_ACT_DIM = NU + VF_BODY_DIM * NB + 30;
 
@@ -1500,6 +1501,7 @@ UHC_DEVNI void diff_and_reward(const Model<Real> &m, const EnvCfg<Real> &cfg, co
     else for (int i = 0; i < 6; i++) vf2 += w.act[NU + i] * w.act[NU + i];
     cinfo[0] = exp_(-cfg.k[0] * pose2); cinfo[1] = exp_(-cfg.k[1] * vel2); cinfo[2] = exp_(-cfg.k[2] * ee2);
     cinfo[3] = exp_(-cfg.k[3] * com2); cinfo[4] = cfg.rfc_mode == 2 ? Real(0) : exp_(-cfg.k[4] * vf2);     // residual_force off: vf_reward = 0.0 (reward_function.py:68-72)
+    if (cfg.reward_mul) { *reward = cinfo[0] * cinfo[1] * cinfo[2] * cinfo[3] * (cfg.w[4] != Real(0) ? cinfo[4] : Real(1)); return; }      // reward_function.py:243-245
     Real r = 0, ws = 0;
     for (int i = 0; i < 5; i++) { r += cfg.w[i] * cinfo[i]; ws += cfg.w[i]; }
     *reward = r / ws;

@@ -21,13 +21,13 @@ class UhcEnvCfg(C.Structure):
                 ("body_diff_thresh", C.c_double), ("meta_pd", C.c_int), ("env_episode_len", C.c_int), ("trail_steps", C.c_int),
                 ("newton_max_iter", C.c_int), ("w", C.c_double * 5), ("k", C.c_double * 5), ("newton_tol", C.c_double),
                 ("auto_reset", C.c_int), ("t_min", C.c_int), ("t_max", C.c_int), ("reactive_v", C.c_int), ("reset_seed", C.c_ulonglong),
-                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24), ("obs_v", C.c_int), ("fut_frames", C.c_int), ("fut_skip", C.c_int), ("no_shape", C.c_int), ("term_body", C.c_int), ("head_body", C.c_int)]
+                ("reactive_rate", C.c_double), ("rfc_mode", C.c_int), ("vf_slot", C.c_int * 24), ("obs_v", C.c_int), ("fut_frames", C.c_int), ("fut_skip", C.c_int), ("no_shape", C.c_int), ("term_body", C.c_int), ("head_body", C.c_int), ("reward_mul", C.c_int)]
 
 
 def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0, rfc_lim=100.0, rfc_rate=1.0, body_diff_thresh=0.5,
              meta_pd=1, env_episode_len=100000, trail_steps=0, w=(0.3, 0.1, 0.45, 0.1, 0.05), k=(2.0, 0.005, 5.0, 100.0, 1.0),
              newton_max_iter=None, newton_tol=None, auto_reset=0, t_min=5, t_max=300, reset_seed=1, reactive_v=0, reactive_rate=0.3,
-             rfc_mode="implicit", vf_slot=None, obs_v=2, fut_frames=10, fut_skip=10, has_shape=True, term_body="body", head_body=13):
+             rfc_mode="implicit", vf_slot=None, obs_v=2, fut_frames=10, fut_skip=10, has_shape=True, term_body="body", head_body=13, reward_mul=False):
     """Defaults = config/release/uhc_implicit_shape.yml + copycat_config.py defaults of the reference."""
     c = UhcEnvCfg()
     c.base_rot = (C.c_double * 4)(*base_rot)
@@ -46,6 +46,7 @@ def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0,
     # cfg.env_term_body: "body" | "root" | "Head" (humanoid_im.py:1223-1229); head_body = model body of "Head" (13 in the SMPL humanoid)
     c.term_body = {"body": 0, "root": 1, "Head": 2, "head": 2, 0: 0, 1: 1, 2: 2}[term_body]
     c.head_body = int(head_body)
+    c.reward_mul = int(bool(reward_mul))          # reward_id world_rfc_implicit_v1_mul
     return c
 
 
