@@ -1,3 +1,3 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -3
+timeout 300 python -m pytest tests/test_gpu_nn.py -q 2>&1 | tail -3

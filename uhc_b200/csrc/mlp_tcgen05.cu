@@ -893,7 +893,7 @@ static int linear_tc_impl(const void *x_bf16, const void *W_bf16, const float *b
         }
         CUtensorMap my;
         if (make_map_out(&my, y_f32_or_null, M, N, (size_t)ld_yf * sizeof(float), false) || pair_attr()) return -1;
-        if (ks > 1 && cudaMemsetAsync(y_f32_or_null, 0, (size_t)M * ld_yf * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "memset failed"; return -1; }
+        if ((ks > 1 || ld_yf != N) && cudaMemsetAsync(y_f32_or_null, 0, (size_t)M * ld_yf * sizeof(float), (cudaStream_t)stream) != cudaSuccess) { g_tc_err = "memset failed"; return -1; }   // (a padded pitch: the padding columns read as zeros)
         const int items = pt * ks;
         k_linear_tc2<false><<<2 * (items < pairs ? items : pairs), P_THREADS, P_SMEM_BYTES, (cudaStream_t)stream>>>(ma, mb, b, M, N, Kp, 0, UHC_ACT_NONE, ma, my, ma, ma, 2, nullptr, ks);
         cudaError_t e = cudaGetLastError();
