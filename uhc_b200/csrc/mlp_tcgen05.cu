@@ -1,8 +1,14 @@
-// mlp_tcgen05.cu -- tensor-core Linear(+bias+activation) for the rollout-time policy/value forward:
-//   y[M][N] = act(x[M][Kp] W[N][Kp]^T + b),  bf16 operands (K-major, zero padded to Kp % 64 == 0), fp32 accumulation in TMEM.
-// sm_100a only: TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring -> tcgen05.mma (one elected thread, UMMA 128x128x16,
-// cta_group::1, 128 TMEM columns per CTA, 2 CTAs/SM) -> tcgen05.ld epilogue (bias + activation fused, bf16 and/or fp32 store).  Warp roles: 0 = TMA producer,
-// 1 = MMA issuer + TMEM allocator, 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// mlp_tcgen05.cu -- tensor-core Linear layers for the policy / value nets: rollout-time forward and the whole autograd of the PPO update.
+//   y[M][N] = act(x[M][Kp] W[N][Kp]^T + b),  bf16 operands (K-major, zero padded to Kp % 64 == 0), fp32 accumulation in TMEM.  sm_100a only.
+// Two kernels share the TMA maps, the operand layout (128-byte swizzle) and the epilogue building blocks:
+//   k_linear_tc   one CTA per 128 x 128 tile: TMA (cp.async.bulk.tensor) -> 3-stage smem ring -> tcgen05.mma cta_group::1 (one elected thread, UMMA 128x128x16,
+//                 128 TMEM columns, 2 CTAs/SM so that one CTA's epilogue overlaps the other's MMAs) -> tcgen05.ld epilogue in 8 warps.  Rollout-time forward
+//                 (M = 4096), small shapes, split-K by fp32 atomics, and the fallback of every fused path.
+//   k_linear_tc2  CTA pairs (cta_group::2, 256 x 256 tiles), persistent, two TMEM accumulators, 5-stage ring, 16 epilogue warps, split-K work items whose
+//                 partial tiles the TMA engine adds into the output: the training GEMMs (M >= 16384 rows, or a reduction over >= 16384 rows).
+// Epilogues (both kernels): bias + activation; outputs staged in swizzled shared-memory tiles and stored by the TMA engine (fp32 pre-activation z, bf16 / fp32 y,
+// the TRANSPOSED bf16 y for the backward pass' dW GEMM); DACT variant = the backward pass' dX GEMM with the previous layer's activation backward fused in
+// (z tile fetched by TMA, dz / dz^T stored by TMA, bias gradient by a warp transpose-reduce).  Host entry points at the end of the file (C ABI: include/uhc_nn.h).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
