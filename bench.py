@@ -462,9 +462,9 @@ def run_train(args):
                             allreduce_calls_per_iter=phases["allreduce_calls"] / K,
                             allreduce_busbw_GBps=(phases["allreduce_bytes"] * 2 * (world - 1) / world / (phases["allreduce_ms"] * 1e-3) / 1e9) if phases["allreduce_ms"] > 0 else None),
                 replicas_identical=same, parameters=npar,
-                roofline=dict(bound="tensor", kernel="k_linear_tc (forward, dX, dW of both nets)", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                roofline=dict(bound="tensor", kernel="k_linear_tc2 (CTA-pair tcgen05 GEMMs: forward, dX with the activation backward fused, split-K dW of both nets)", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
                               peak_source="MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 TFLOP/s",
-                              note="6 x parameters x N flop per epoch over the measured time of the 10 epochs (includes the activation-gradient / transpose / Adam kernels)"),
+                              note="6 x parameters x N flop per epoch over the measured time of the 10 epochs (includes the loss, head activation-gradient, weight-transpose, Adam and bf16 weight-refresh kernels)"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=16,
                          note="the training iteration has no host inputs (observations, rollout buffer and weights are device resident); the host reads back the two loss scalars"),
                 gpu_launches=(launches() - l0), update_driver="uhc_ppo_update: one C-ABI call per iteration (V(s), GAE, epochs, Adam, gradient all-reduce on the job's ncclComm_t)",
