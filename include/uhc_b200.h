@@ -67,6 +67,7 @@ typedef struct {
     int vf_slot[UHC_NB];    /* explicit mode: residual-force slot of body b (the reference orders the slots by SMPL_BONE_ORDER_NAMES, smpl_parser.py:11-36) */
     int obs_v;              /* cfg.obs_v (copycat_config.py:88): 2 = get_full_obs_v2 (657 dims, humanoid_im.py:419-503), 1 = get_full_obs_v1 (784 dims, :323-417);
                              * 3 = get_full_obs_v3 (:505-513): fut_frames v2 blocks against the expert frames cur_t + 1 + i * fut_skip (657 * fut_frames dims);
+                             * 5 = get_full_obs_v5 (:505-594, 636 + 17 dims), 6 = get_full_obs_v6 (:596-666, 384 + 17 dims; the 17 shape dims only without no_shape);
                              * 0 is read as 2.  uhc_engine_obs_dim() gives the row width of every obs buffer. */
     int fut_frames, fut_skip;   /* cfg.fut_frames / cfg.skip of obs_v 3 (both default to 10 when <= 0, as cc_cfg.get does) */
     int no_shape;               /* != 0: cfg.has_shape false -- the v2 block carries no shape vector (640 dims instead of 657, humanoid_im.py:499-500) */

@@ -471,7 +471,7 @@ void or_env_set_rfc_mode(OrEnv *e, int explicit_mode, const int *vf_body) {
     if (vf_body) memcpy(e->vf_body, vf_body, sizeof e->vf_body);
 }
 int or_env_action_dim(const OrEnv *e) { return NU + e->vf_dim + (e->meta_pd ? 30 : 0); }
-void or_env_set_obs_v(OrEnv *e, int obs_v, const double *body_com) { e->obs_v = (obs_v == 1 || obs_v == 3) ? obs_v : 2; e->ex.body_com = body_com; }
+void or_env_set_obs_v(OrEnv *e, int obs_v, const double *body_com) { e->obs_v = (obs_v == 1 || obs_v == 3 || obs_v == 5 || obs_v == 6) ? obs_v : 2; e->ex.body_com = body_com; }
 void or_env_set_future(OrEnv *e, int fut_frames, int skip) { e->fut_frames = fut_frames > 0 ? fut_frames : 10; e->fut_skip = skip > 0 ? skip : 10; }
 void or_env_set_has_shape(OrEnv *e, int has_shape) { e->no_shape = !has_shape; }
 void or_env_set_reward_mul(OrEnv *e, int on) { e->reward_mul = on ? 1 : 0; }
@@ -485,7 +485,11 @@ void or_env_set_term_body(OrEnv *e, int mode, int head_body) {
     }
 }
 static int obs_block_dim(const OrEnv *e) { return e->no_shape ? 640 : 657; }
-int or_env_obs_dim(const OrEnv *e) { return e->obs_v == 1 ? 784 : (e->obs_v == 3 ? obs_block_dim(e)*e->fut_frames : obs_block_dim(e)); }
+int or_env_obs_dim(const OrEnv *e) {
+    if (e->obs_v == 5) return 636 + (e->no_shape ? 0 : 17);       /* get_full_obs_v5 */
+    if (e->obs_v == 6) return 384 + (e->no_shape ? 0 : 17);       /* get_full_obs_v6 */
+    return e->obs_v == 1 ? 784 : (e->obs_v == 3 ? obs_block_dim(e)*e->fut_frames : obs_block_dim(e));
+}
 void or_env_free(OrEnv *e) { if (e) { or_data_free(e->d); free(e); } }
 OrData *or_env_data(OrEnv *e) { return e->d; }
 void or_env_set_expert(OrEnv *e, int len, const double *qpos, const double *qvel, const double *wbpos, const double *wbquat,
@@ -585,8 +589,10 @@ static void or_rfc_explicit(OrEnv *e, const double *ctrl) {
 /* get_full_obs_v2 (humanoid_im.py:419-503) and get_full_obs_v1 (:323-417), obs_coord = "root", obs_vel = "full".  v1 = v2 with two more blocks
    (per-body COM relative to the root, COM difference to the expert's body_com) between the joint-position blocks and the quaternions, and no shape vector. */
 static void or_obs_block(const OrEnv *e, double *obs);
+static void or_obs_v56(const OrEnv *e, double *obs);
 void or_obs_v2(const OrEnv *ec, double *obs) {     /* get_obs: one block, or the v3 stack of v2 blocks */
     OrEnv *e = (OrEnv *)ec;
+    if (e->obs_v == 5 || e->obs_v == 6) { or_obs_v56(e, obs); return; }
     if (e->obs_v != 3) { e->obs_dt = 0; or_obs_block(e, obs); return; }
     for (int f = 0; f < e->fut_frames; f++) { e->obs_dt = f*e->fut_skip; or_obs_block(e, obs + obs_block_dim(e)*f); }
     e->obs_dt = 0;
@@ -633,6 +639,67 @@ static void or_obs_block(const OrEnv *e, double *obs) {
     for (int b = 0; b < NB; b++) { const double *cq = use_target ? twq+4*b : d->xquat[b]; double iq[4]; qinv(cq, iq); double n = e->obs_v == 1 ? 1.0 : sqrt(cq[0]*cq[0]+cq[1]*cq[1]+cq[2]*cq[2]+cq[3]*cq[3]); for (int k = 0; k < 4; k++) iq[k] *= n; /* v2: inverse_batch divides by |q|, not |q|^2; v1: quaternion_inverse (:411) */ qmul(iq, twq+4*b, obs+o+4*b); }
     o += 96;
     if (e->obs_v != 1 && !e->no_shape) { memcpy(obs+o, e->ex.shape_obs, 17*8); o += 17; }
+}
+
+/* the "_new" heading helpers (uhc/utils/math_utils.py:169-207): yaw from the full quaternion, heading quaternion about z */
+static double heading_new(const double *q) { return atan2(2*(q[0]*q[3] + q[1]*q[2]), 1 - 2*(q[2]*q[2] + q[3]*q[3])); }
+static void heading_q_new(const double *q, double *hq) { double y = heading_new(q); hq[0] = cos(y/2); hq[1] = 0; hq[2] = 0; hq[3] = sin(y/2); }
+/* get_full_obs_v5 (humanoid_im.py:505-594: "no diff, no heading" ablation of v2 on the _new heading helpers, velocity rotated ONCE) and get_full_obs_v6
+   (:596-666: the concise one -- root offset / heading / relative root rotation, qvel, joint positions and their differences in the heading frame, local joint
+   quaternions and their differences).  obs_coord = "root", obs_vel = "full".  Kept as the reference computes them: in v6 `transform_vec_batch_new(...)[1:]` slices
+   the (3, 24) result, i.e. drops the x ROW (48 values remain), while the difference block drops the root BODY before the transform (3 x 23 = 69 values). */
+static void or_obs_v56(const OrEnv *e, double *obs) {
+    const OrData *d = e->d; double qpos[NQ], qvel[NV], R[9], t[3];
+    memcpy(qpos, d->qpos, sizeof qpos); memcpy(qvel, d->qvel, sizeof qvel);
+    const int ind = ex_index(e, e->cur_t + 1);
+    const double *tq = e->ex.qpos + NQ*ind, *twq = e->ex.wbquat + 96*ind, *tjp = e->ex.wbpos + 72*ind, *tbq = e->ex.bquat + 96*ind;
+    double crq[4], trq[4], hq[4], hqi[4], ci[4], relq[4];
+    remove_base_rot(e, qpos+3, crq); remove_base_rot(e, tq+3, trq); heading_q_new(crq, hq); qinv(hq, hqi);
+    qinv(crq, ci); qmul(trq, ci, relq);
+    double rel_h = heading_new(trq) - heading_new(crq);
+    if (rel_h > M_PI) rel_h -= 2*M_PI;
+    if (rel_h < -M_PI) rel_h += 2*M_PI;
+    int o = 0;
+    if (e->obs_v == 5) {
+        double dh[4], diff[NQ];
+        qmul(hqi, crq, dh);                                                          /* de_heading_new(curr_root_quat) :528 */
+        memcpy(diff, tq, sizeof diff); diff[2] -= qpos[2];
+        memcpy(qpos+3, dh, 32);
+        for (int i = 7; i < NQ; i++) diff[i] -= qpos[i];
+        memcpy(diff+3, relq, 32);
+        memcpy(obs+o, tq+2, 74*8); o += 74; memcpy(obs+o, qpos+2, 74*8); o += 74; memcpy(obs+o, diff+2, 74*8); o += 74;
+        q2mat(crq, R); mtv(R, qvel, t); memcpy(qvel, t, 24);                          /* transform_vec_new(qvel[:3], curr_root_quat, "root") = v . R :540 */
+        memcpy(obs+o, qvel, 75*8); o += 75;
+        obs[o++] = rel_h;
+        double rp[3] = {tq[0]-qpos[0], tq[1]-qpos[1], tq[2]-qpos[2]};
+        mtv(R, rp, t); obs[o++] = t[0]; obs[o++] = t[1];
+        for (int b = 0; b < NB; b++) { double r[3] = {d->xpos[b][0]-qpos[0], d->xpos[b][1]-qpos[1], d->xpos[b][2]-qpos[2]}; mtv(R, r, t); for (int k = 0; k < 3; k++) obs[o+24*k+b] = t[k]; }
+        o += 72;
+        for (int b = 0; b < NB; b++) { double r[3] = {tjp[3*b]-d->xpos[b][0], tjp[3*b+1]-d->xpos[b][1], tjp[3*b+2]-d->xpos[b][2]}; mtv(R, r, t); for (int k = 0; k < 3; k++) obs[o+24*k+b] = t[k]; }
+        o += 72;
+        int use_target = (d->xquat[0][0] == 0);
+        for (int b = 0; b < NB; b++) { const double *cq = use_target ? twq+4*b : d->xquat[b]; qmul(hqi, cq, obs+o+4*b); }
+        o += 96;
+        for (int b = 0; b < NB; b++) { const double *cq = use_target ? twq+4*b : d->xquat[b]; double iq[4]; qinv(cq, iq); double n = sqrt(cq[0]*cq[0]+cq[1]*cq[1]+cq[2]*cq[2]+cq[3]*cq[3]); for (int k = 0; k < 4; k++) iq[k] *= n; qmul(iq, twq+4*b, obs+o+4*b); }
+        o += 96;
+    } else {
+        q2mat(hq, R);
+        double rp[3] = {tq[0]-qpos[0], tq[1]-qpos[1], tq[2]-qpos[2]};
+        mtv(R, rp, t); memcpy(obs+o, t, 24); o += 3;                                  /* :623-626 */
+        obs[o++] = rel_h;
+        memcpy(obs+o, relq, 32); o += 4;
+        mtv(R, qvel, t); memcpy(qvel, t, 24);
+        memcpy(obs+o, qvel, 75*8); o += 75;
+        for (int b = 0; b < NB; b++) { double r[3] = {d->xpos[b][0]-qpos[0], d->xpos[b][1]-qpos[1], d->xpos[b][2]-qpos[2]}; mtv(R, r, t); for (int k = 1; k < 3; k++) obs[o+24*(k-1)+b] = t[k]; }
+        o += 48;                                                                      /* [1:] of the (3, 24) array: the y and z rows (:645) */
+        for (int b = 1; b < NB; b++) { double r[3] = {tjp[3*b]-d->xpos[b][0], tjp[3*b+1]-d->xpos[b][1], tjp[3*b+2]-d->xpos[b][2]}; mtv(R, r, t); for (int k = 0; k < 3; k++) obs[o+23*k+(b-1)] = t[k]; }
+        o += 69;
+        double bq[96]; or_body_quat(e, bq);
+        memcpy(obs+o, bq+4, 92*8); o += 92;
+        for (int b = 1; b < NB; b++) { const double *cq = bq+4*b; double iq[4]; qinv(cq, iq); double n = sqrt(cq[0]*cq[0]+cq[1]*cq[1]+cq[2]*cq[2]+cq[3]*cq[3]); for (int k = 0; k < 4; k++) iq[k] *= n; qmul(iq, tbq+4*b, obs+o+4*(b-1)); }
+        o += 92;
+    }
+    if (!e->no_shape) { memcpy(obs+o, e->ex.shape_obs, 17*8); o += 17; }
 }
 
 static void rot_from_quat(const double *q, double *rv) { /* transformation.py:362-372 */

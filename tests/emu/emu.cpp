@@ -28,10 +28,11 @@ static void set_cfg(EnvCfg<Real> &c, const UhcEnvCfg *h) {
     c.reactive_v = 0; c.reactive_rate = 0; c.auto_reset = 0; c.t_min = h->t_min; c.t_max = h->t_max; c.reset_seed = h->reset_seed; c.num_clips = 0;
     c.rfc_mode = (h->rfc_mode == 1 || h->rfc_mode == 2) ? h->rfc_mode : 0; c.vf_dim = c.rfc_mode == 1 ? VF_BODY_DIM * NB : (c.rfc_mode == 2 ? 0 : 6); c.act_dim = NU + c.vf_dim + (h->meta_pd ? 2 * NSUB : 0);
     for (int b = 0; b < NB; b++) c.vf_slot[b] = (signed char)h->vf_slot[b];
-    c.obs_v = (h->obs_v == 1 || h->obs_v == 3) ? h->obs_v : 2;
+    c.obs_v = (h->obs_v == 1 || h->obs_v == 3 || h->obs_v == 5 || h->obs_v == 6) ? h->obs_v : 2;
     c.fut_frames = h->fut_frames > 0 ? h->fut_frames : 10; c.fut_skip = h->fut_skip > 0 ? h->fut_skip : 10;
     c.has_shape = h->no_shape ? 0 : 1; c.obs_block = c.has_shape ? OBS_DIM : OBS_DIM - 17;
     c.obs_dim = c.obs_v == 1 ? OBS_DIM_V1 : (c.obs_v == 3 ? c.obs_block * c.fut_frames : c.obs_block);
+    if (c.obs_v == 5 || c.obs_v == 6) c.obs_dim = (c.obs_v == 5 ? 636 : 384) + (c.has_shape ? 17 : 0);      // get_full_obs_v5 / v6
     c.term_body = (h->term_body == 1 || h->term_body == 2) ? h->term_body : 0; c.head_body = (h->head_body >= 0 && h->head_body < NB) ? h->head_body : 13;
     c.reward_mul = h->reward_mul ? 1 : 0;
 }

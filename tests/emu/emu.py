@@ -73,6 +73,8 @@ class Emu:
         self._cfg = default_cfg(precision, **cfg)
         blk = 640 if self._cfg.no_shape else 657
         self.obs_dim = 784 if self._cfg.obs_v == 1 else (blk * (self._cfg.fut_frames or 10) if self._cfg.obs_v == 3 else blk)
+        if self._cfg.obs_v in (5, 6):
+            self.obs_dim = (636 if self._cfg.obs_v == 5 else 384) + (0 if self._cfg.no_shape else 17)
         self.h = C.c_void_p(self.lib.emu_create(C.byref(self._ms), C.byref(self._cfg), C.c_int(num_envs), C.c_int(precision)))
 
     def load_clips(self, experts, shapes):

@@ -220,3 +220,22 @@ def test_env_term_body_root_and_head_flags_match_reference_golden(golden_dir, te
         _, _, _, info = e.step(g["action"][t])
         fails.append(info["fail"])
     assert fails == [bool(f) for f in g["fail"][:34]] and any(fails)
+
+
+@pytest.mark.parametrize("v,prec,tol_q,tol_o", [(5, 64, 1e-10, 1e-8), (6, 64, 1e-10, 1e-8), (5, 32, 2e-4, 4e-3), (6, 32, 2e-4, 4e-3)])
+def test_obs_v5_v6_match_reference_golden(golden_dir, v, prec, tol_q, tol_o):
+    """obs_v 5 / 6 in the kernel source (host emulation): the reference's own get_full_obs_v5 / get_full_obs_v6 over the noise trajectory"""
+    g = np.load(os.path.join(golden_dir, f"env_sway_obsv{v}_noise.npz"))
+    z = np.load(os.path.join(golden_dir, "expert_sway.npz"))
+    ex = {k: z[k] for k in z.files}
+    so = np.concatenate([ex["beta"][0], [ex["gender"][0]]])
+    e = Emu(prec, obs_v=v)
+    assert e.obs_dim == g["obs"].shape[1]
+    e.load_clips([ex], [so])
+    obs0 = e.reset()
+    assert np.abs(obs0 - g["obs0"]).max() < max(tol_o * 1e-2, 1e-12)
+    for t in range(len(g["reward"])):
+        obs, r, done, info = e.step(g["action"][t])
+        st, _ = e.state()
+        assert np.abs(st[:76] - g["qpos"][t]).max() < tol_q, t
+        assert np.abs(obs - g["obs"][t]).max() < tol_o, (t, int(np.abs(obs - g["obs"][t]).argmax()))

@@ -428,3 +428,25 @@ def test_multiplicative_reward_matches_reference_trace(golden_dir, precision, to
         assert abs(float(r[E - 1]) - g["reward"][t]) < tol, t
         assert np.abs(c[E - 1].cpu().numpy() - g["c_info"][t]).max() < tol, t
     eng.close()
+
+
+@pytest.mark.parametrize("v,precision,tol_q,tol_o", [(5, 64, 1e-8, 2e-5), (6, 64, 1e-8, 2e-5), (5, 32, 1e-3, 5e-3), (6, 32, 1e-3, 5e-3)])
+def test_obs_v5_v6_match_reference_trace(golden_dir, v, precision, tol_q, tol_o):
+    """obs_v 5 / 6 (get_full_obs_v5 / get_full_obs_v6, humanoid_im.py:505-666) through the C ABI against the reference's own observations"""
+    import torch
+    from uhc_b200.engine import Engine
+    g = np.load(os.path.join(golden_dir, f"env_sway_obsv{v}_noise.npz"))
+    ex, so = _expert(golden_dir, "sway")
+    E = 3
+    eng = Engine(E, precision=precision, obs_v=v)
+    assert eng.obs_dim == g["obs"].shape[1]
+    eng.load_clips([ex], [so])
+    obs0 = eng.reset().cpu().numpy()
+    assert np.abs(obs0[E - 1] - g["obs0"]).max() < 1e-5
+    for t in range(len(g["reward"])):
+        a = torch.tensor(np.tile(g["action"][t], (E, 1)), dtype=torch.float32, device="cuda")
+        o, r, c, f, en, pct = eng.step(a)
+        torch.cuda.synchronize()
+        assert np.abs(eng.get_state(E - 1)["qpos"] - g["qpos"][t]).max() < tol_q, t
+        assert np.abs(o[E - 1].cpu().numpy() - g["obs"][t]).max() < tol_o, t
+    eng.close()

@@ -131,3 +131,21 @@ def test_multiplicative_reward_matches_reference_python(golden_dir):
         assert abs(r - g["reward"][t]) < 1e-7, t
         np.testing.assert_allclose(info["c_info"], g["c_info"][t], rtol=0, atol=1e-6)
     assert float(g["reward_weights"][4]) != 0.0 and g["reward"].min() < 0.2 < g["reward"].max()      # (w_vf = 0.05: the residual-force term is part of the product)
+
+
+@pytest.mark.parametrize("v,dim", [(5, 653), (6, 401)])
+def test_obs_v5_v6_traces_match_reference_python(golden_dir, v, dim):
+    """obs_v 5 / 6 (get_full_obs_v5 humanoid_im.py:505-594, get_full_obs_v6 :596-666, the _new heading helpers of math_utils.py:142-207): the reference's own
+    observations over the noise trajectory, bug for bug (v6 drops the x ROW of the transformed joint positions)"""
+    g = np.load(os.path.join(golden_dir, f"env_sway_obsv{v}_noise.npz"))
+    ex, so = load_expert(golden_dir, "sway")
+    env = O.Env(O.Model(), ex, so)
+    env.set_obs_v(v)
+    assert env.obs_dim == dim == g["obs"].shape[1]
+    obs0 = env.reset()
+    np.testing.assert_allclose(obs0, g["obs0"], rtol=0, atol=1e-9)
+    for t in range(len(g["reward"])):
+        obs, r, done, info = env.step(g["action"][t])
+        np.testing.assert_allclose(env.d.qpos, g["qpos"][t], rtol=0, atol=1e-7, err_msg=f"qpos t={t}")
+        np.testing.assert_allclose(obs, g["obs"][t], rtol=0, atol=1e-5, err_msg=f"obs t={t}")
+        assert abs(r - g["reward"][t]) < 1e-6

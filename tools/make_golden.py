@@ -424,6 +424,13 @@ def main():
             cfg.env_term_body = tb
             dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
             gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 45, "noise", out_tag="sway_term" + tb.lower(), save_expert=False, term_body=tb)
+    if "obsv56" in what:         # obs_v 5 / 6 (get_full_obs_v5 :505-594, get_full_obs_v6 :596-666) on the default implicit-RFC, shape-conditioned configuration
+        from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
+        for v in (5, 6):
+            cfg = H.make_cfg()
+            cfg.obs_v = v
+            dl = DatasetAMASSSingle(cfg.data_specs, data_mode="train")
+            gen_env(cfg, dl, "0-ACCAD_Male2General_c3d_A2- Sway_poses", "sway", 90, 14, "noise", out_tag=f"sway_obsv{v}", save_expert=False)
     if "rewmul" in what:         # reward_id world_rfc_implicit_v1_mul (reward_function.py:174-250): the five terms of world_rfc_implicit multiplied instead of averaged
         from uhc.data_loaders.dataset_amass_single import DatasetAMASSSingle
         cfg = H.make_cfg()

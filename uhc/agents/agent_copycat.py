@@ -73,8 +73,8 @@ class AgentCopycat:
             if not dist.is_initialized():
                 dist.init_process_group("nccl")
             sync = make_nccl_grad_sync(world)
-        assert cfg.obs_v in (1, 2, 3) and cfg.actor_type in ("gauss", "mcp") and cfg.reward_id in reward_func, \
-            "the B200 engine implements obs_v 1 | 2 | 3, the gauss and mcp actors, world_rfc_implicit / world_rfc_explicit (obs_v 5/6 etc.: SURVEY.md section 8f, next)"
+        assert cfg.obs_v in (1, 2, 3, 5, 6) and cfg.actor_type in ("gauss", "mcp") and cfg.reward_id in reward_func, \
+            "the B200 engine implements obs_v 1 | 2 | 3 | 5 | 6, the gauss and mcp actors, world_rfc_implicit (_v1_mul) / world_rfc_explicit (obs_v 0/4, reward v2/v3: SURVEY.md section 8f, next)"
         assert cfg.get("obs_vel", "full") == "full" and cfg.get("obs_coord", "root") == "root" and not cfg.get("obs_phase", False), "obs_vel full / obs_coord root / no phase only"
         if cfg.obs_v == 1:
             assert not cfg.get("has_shape", False), "obs_v 1 carries no shape vector (has_shape: false in config/release/uhc_implicit.yml)"

@@ -93,7 +93,8 @@ UHC_DEV Model<Real> model_for_clip(const EngineView<Real> &ev, int clip) {
 template <class Real, class ObsT>
 UHC_DEV void write_obs(const EngineView<Real> &ev, const Work<Real> &w, int clip, int start, int len, int t_next, ObsT *obs) {
     const Real *shape = ev.clip_shape + 17 * clip;
-    if (w.cfg.obs_v == 3) {
+    if (w.cfg.obs_v == 5 || w.cfg.obs_v == 6) obs_v56(w.cfg, w, expert_frame(ev, clip, start, len, t_next), shape, obs);
+    else if (w.cfg.obs_v == 3) {
         for (int f = 0; f < w.cfg.fut_frames; ++f) obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, t_next + f * w.cfg.fut_skip), shape, obs + (size_t)f * w.cfg.obs_block);
     } else obs_v2(w.cfg, w, expert_frame(ev, clip, start, len, t_next), shape, obs);
 }

@@ -106,7 +106,7 @@ struct EnvCfg {
     // residual-force mode (cfg.residual_force / residual_force_mode, humanoid_im.py:231-243): 0 = implicit root wrench (6 action dims), 1 = explicit per-body
     // contact point / force / torque (9 dims x 24 bodies), 2 = residual_force: false (no residual-force dims, no applied force, reward term 0).  Action layout: [NU joint targets | vf_dim residual-force dims | 30 meta-PD scales if meta_pd]
     int rfc_mode, vf_dim, act_dim;
-    int obs_v, obs_dim;                           // cfg.obs_v: 2 = get_full_obs_v2 (657), 1 = get_full_obs_v1 (784; config/release/uhc_implicit.yml),
+    int obs_v, obs_dim;                           // cfg.obs_v: 2 = get_full_obs_v2 (657), 1 = get_full_obs_v1 (784; config/release/uhc_implicit.yml), 5 / 6 = get_full_obs_v5 / v6 (636 / 384 + shape),
     int fut_frames, fut_skip;                     //   3 = get_full_obs_v3 (:505-513): fut_frames v2 blocks against the expert frames cur_t + 1 + i * skip
     int has_shape, obs_block;                     // cfg.has_shape (:499-500): the v2 block ends with the 17 shape dims (657) or not (640); obs_block = its width
     signed char vf_slot[NB];                      // explicit: residual-force slot of body b (vf_bodies = SMPL_BONE_ORDER_NAMES, humanoid_im.py:236-237)
@@ -173,6 +173,8 @@ UHC_DEV void sincos_(float x, float *s, float *c) {
 UHC_DEV void sincos_(double x, double *s, double *c) { *s = sin(x); *c = cos(x); }
 UHC_DEV float acos_(float x) { return acosf(x); }
 UHC_DEV double acos_(double x) { return acos(x); }
+UHC_DEV float atan2_(float y, float x) { return atan2f(y, x); }
+UHC_DEV double atan2_(double y, double x) { return atan2(y, x); }
 UHC_DEV float exp_(float x) { return expf(x); }
 UHC_DEV double exp_(double x) { return exp(x); }
 UHC_DEV float abs_(float x) { return fabsf(x); }
@@ -1454,6 +1456,95 @@ UHC_DEVNI void obs_v2(const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *
         for (int k = 0; k < 4; k++) { obs[oq + 4 * b + k] = (OutT)o1[k]; obs[oq + 96 + 4 * b + k] = (OutT)o2[k]; }
     }
     if (cfg.obs_v != 1 && cfg.has_shape && lane < 17) obs[640 + lane] = (OutT)shape_obs[lane];
+    LANES_END
+}
+
+// the "_new" heading helpers (uhc/utils/math_utils.py:169-207): yaw from the full quaternion, heading quaternion about z
+template <class Real> UHC_DEV Real heading_new(const Real *q) { return atan2_(2 * (q[0] * q[3] + q[1] * q[2]), 1 - 2 * (q[2] * q[2] + q[3] * q[3])); }
+template <class Real> UHC_DEV void heading_q_new(const Real *q, Real *hq) { Real sn, cs; sincos_(heading_new(q) * Real(0.5), &sn, &cs); hq[0] = cs; hq[1] = 0; hq[2] = 0; hq[3] = sn; }
+// observation v5 (humanoid_im.py:505-594: the v2 blocks on the _new heading helpers, no heading quaternion block, the root velocity rotated once, the true root
+// offset) and v6 (:596-666: root offset in the heading frame, relative heading, relative root rotation, qvel, joint positions (the y and z ROWS of the
+// transformed (3, 24) array: the reference slices `[1:]` after the transform) and joint-position differences of bodies 1..23 in the heading frame, local joint
+// quaternions of bodies 1..23 and their differences to the expert's); ex1 = expert frame at cur_t + 1; obs_coord "root", obs_vel "full"
+template <class Real, class OutT>
+UHC_DEVNI void obs_v56(const EnvCfg<Real> &cfg, const Work<Real> &w, const Real *ex1, const Real *shape_obs, OutT *obs) {
+    Real crq[4], trq[4], hq[4], hqi[4], ci[4], relq[4], dh[4], R[9];
+    remove_base_rot(cfg, w.q + 3, crq); remove_base_rot(cfg, ex1 + EX_QPOS + 3, trq);
+    heading_q_new(crq, hq); qinv(hq, hqi); qinv(crq, ci); qmul(trq, ci, relq); qmul(hqi, crq, dh);
+    Real rel_h = heading_new(trq) - heading_new(crq);
+    if (rel_h > Real(PI_D)) rel_h -= Real(2 * PI_D);
+    if (rel_h < -Real(PI_D)) rel_h += Real(2 * PI_D);
+    const bool v5 = cfg.obs_v == 5;
+    q2mat(v5 ? crq : hq, R);
+    LANES_BEGIN
+    if (v5) {
+        for (int i = lane; i < 74; i += 32) {
+            const Real tq = ex1[EX_QPOS + 2 + i];
+            Real cur, df;
+            if (i == 0) { cur = w.q[2]; df = tq - cur; }
+            else if (i < 5) { cur = dh[i - 1]; df = relq[i - 1]; }
+            else { cur = w.q[2 + i]; df = tq - cur; }
+            obs[i] = (OutT)tq; obs[74 + i] = (OutT)cur; obs[148 + i] = (OutT)df;
+        }
+        if (lane == 0) {
+            Real t[3];
+            mtv(R, w.v, t);                                                       // rotated once (:540)
+            obs[222] = (OutT)t[0]; obs[223] = (OutT)t[1]; obs[224] = (OutT)t[2];
+            obs[297] = (OutT)rel_h;
+            const Real rp[3] = {ex1[EX_QPOS] - w.q[0], ex1[EX_QPOS + 1] - w.q[1], ex1[EX_QPOS + 2] - w.q[2]};
+            mtv(R, rp, t);
+            obs[298] = (OutT)t[0]; obs[299] = (OutT)t[1];
+        }
+        for (int i = 3 + lane; i < NV; i += 32) obs[222 + i] = (OutT)w.v[i];
+        if (lane < NB) {
+            const int b = lane; Real r[3], t[3];
+            for (int k = 0; k < 3; k++) r[k] = w.xpos[b][k] - w.q[k];
+            mtv(R, r, t);
+            for (int k = 0; k < 3; k++) obs[300 + 24 * k + b] = (OutT)t[k];
+            for (int k = 0; k < 3; k++) r[k] = ex1[EX_WBPOS + 3 * b + k] - w.xpos[b][k];
+            mtv(R, r, t);
+            for (int k = 0; k < 3; k++) obs[372 + 24 * k + b] = (OutT)t[k];
+            const bool use_t = (w.xquat[0][0] == 0);
+            const Real *cq = use_t ? ex1 + EX_WBQUAT + 4 * b : w.xquat[b];
+            Real o1[4], iq[4], o2[4];
+            qmul(hqi, cq, o1);
+            const Real nn = rsqrt_(cq[0] * cq[0] + cq[1] * cq[1] + cq[2] * cq[2] + cq[3] * cq[3]);      // inverse_batch = conj / |q|
+            iq[0] = cq[0] * nn; iq[1] = -cq[1] * nn; iq[2] = -cq[2] * nn; iq[3] = -cq[3] * nn;
+            qmul(iq, ex1 + EX_WBQUAT + 4 * b, o2);
+            for (int k = 0; k < 4; k++) { obs[444 + 4 * b + k] = (OutT)o1[k]; obs[540 + 4 * b + k] = (OutT)o2[k]; }
+        }
+        if (cfg.has_shape && lane < 17) obs[636 + lane] = (OutT)shape_obs[lane];
+    } else {
+        if (lane == 0) {
+            Real t[3];
+            const Real rp[3] = {ex1[EX_QPOS] - w.q[0], ex1[EX_QPOS + 1] - w.q[1], ex1[EX_QPOS + 2] - w.q[2]};
+            mtv(R, rp, t);
+            obs[0] = (OutT)t[0]; obs[1] = (OutT)t[1]; obs[2] = (OutT)t[2];
+            obs[3] = (OutT)rel_h;
+            for (int k = 0; k < 4; k++) obs[4 + k] = (OutT)relq[k];
+            mtv(R, w.v, t);
+            obs[8] = (OutT)t[0]; obs[9] = (OutT)t[1]; obs[10] = (OutT)t[2];
+        }
+        for (int i = 3 + lane; i < NV; i += 32) obs[8 + i] = (OutT)w.v[i];
+        if (lane < NB) {
+            const int b = lane; Real r[3], t[3];
+            for (int k = 0; k < 3; k++) r[k] = w.xpos[b][k] - w.q[k];
+            mtv(R, r, t);
+            obs[83 + b] = (OutT)t[1]; obs[107 + b] = (OutT)t[2];                 // rows 1.. of the (3, 24) array (:645)
+            if (b >= 1) {
+                for (int k = 0; k < 3; k++) r[k] = ex1[EX_WBPOS + 3 * b + k] - w.xpos[b][k];
+                mtv(R, r, t);
+                for (int k = 0; k < 3; k++) obs[131 + 23 * k + (b - 1)] = (OutT)t[k];
+                Real bq[4], iq[4], o2[4];
+                euler_zyx_quat(w.q[7 + 3 * (b - 1)], w.q[8 + 3 * (b - 1)], w.q[9 + 3 * (b - 1)], bq);      // get_body_quat() of the current qpos (:925-947)
+                const Real nn = rsqrt_(bq[0] * bq[0] + bq[1] * bq[1] + bq[2] * bq[2] + bq[3] * bq[3]);
+                iq[0] = bq[0] * nn; iq[1] = -bq[1] * nn; iq[2] = -bq[2] * nn; iq[3] = -bq[3] * nn;
+                qmul(iq, ex1 + EX_BQUAT + 4 * b, o2);
+                for (int k = 0; k < 4; k++) { obs[200 + 4 * (b - 1) + k] = (OutT)bq[k]; obs[292 + 4 * (b - 1) + k] = (OutT)o2[k]; }
+            }
+        }
+        if (cfg.has_shape && lane < 17) obs[384 + lane] = (OutT)shape_obs[lane];
+    }
     LANES_END
 }
 

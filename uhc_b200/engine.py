@@ -41,7 +41,7 @@ def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0,
     # cfg.residual_force_mode: "implicit" (6 action dims: root wrench) | "explicit" (24 x 9: contact point, force, torque per body, mj_applyFT)
     c.rfc_mode = 1 if rfc_mode in (1, "explicit") else (2 if rfc_mode in (2, "none", None, False) else 0)      # "none": cfg.residual_force false
     c.vf_slot = (C.c_int * 24)(*(list(vf_slot) if vf_slot is not None else range(24)))
-    assert int(obs_v) in (1, 2, 3), "obs_v: 1 (get_full_obs_v1), 2 (get_full_obs_v2) or 3 (get_full_obs_v3: fut_frames v2 blocks, skip frames apart)"
+    assert int(obs_v) in (1, 2, 3, 5, 6), "obs_v: 1 (get_full_obs_v1), 2 (get_full_obs_v2), 3 (get_full_obs_v3: fut_frames v2 blocks, skip frames apart), 5 / 6 (get_full_obs_v5 / v6)"
     c.obs_v, c.fut_frames, c.fut_skip, c.no_shape = int(obs_v), int(fut_frames), int(fut_skip), int(not has_shape)
     # cfg.env_term_body: "body" | "root" | "Head" (humanoid_im.py:1223-1229); head_body = model body of "Head" (13 in the SMPL humanoid)
     c.term_body = {"body": 0, "root": 1, "Head": 2, "head": 2, 0: 0, 1: 1, 2: 2}[term_body]
@@ -53,6 +53,8 @@ def make_cfg(precision=32, base_rot=(0.7071, 0.7071, 0.0, 0.0), rfc_scale=100.0,
 def obs_dim_of(cfg):
     """env.obs_dim: 657 (obs v2 with the shape vector) or 784 (obs v1)"""
     block = OBS_DIM - (17 if cfg.no_shape else 0)
+    if cfg.obs_v in (5, 6):
+        return (636 if cfg.obs_v == 5 else 384) + (0 if cfg.no_shape else 17)
     return 784 if cfg.obs_v == 1 else (block * (cfg.fut_frames if cfg.fut_frames > 0 else 10) if cfg.obs_v == 3 else block)
 
 
