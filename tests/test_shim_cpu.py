@@ -50,3 +50,56 @@ def test_dataset_schema_and_sampling(tmp_path):
     assert s["pose_aa"].shape[0] <= 60 and s["beta"].shape[1] == 16 and s["seq_name"] in ds.data_keys
     full = ds.get_sample_from_key(ds.data_keys[1], full_sample=True)
     assert full["pose_aa"].shape[0] == ds.get_sample_len_from_key(ds.data_keys[1]) and full["gender"][0] == 1
+
+
+def _cfg_view(d):
+    """what supported_variant reads from a Config, built from a yaml dict with copycat_config.py's defaults"""
+    import types
+    return types.SimpleNamespace(get=d.get, obs_v=d.get("obs_v", 0), actor_type=d.get("actor_type", "gauss"), reward_id=d.get("reward_id", "quat"),
+                                 fix_std=d.get("fix_std", False), residual_force=d.get("residual_force", False))
+
+
+def test_supported_variant_accepts_the_shipped_configs_and_names_what_it_refuses():
+    import glob
+    import yaml
+    from uhc.agents.agent_copycat import supported_variant
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "config")
+    modes = {}
+    for f in sorted(glob.glob(os.path.join(here, "*.yml"))):
+        modes[os.path.basename(f)] = supported_variant(_cfg_view(yaml.safe_load(open(f))))
+    assert modes["uhc_b200_default.yml"] == "implicit" and modes["uhc_b200_explicit.yml"] == "explicit" and modes["uhc_b200_implicit.yml"] == "implicit"
+    base = yaml.safe_load(open(os.path.join(here, "uhc_b200_default.yml")))
+    for key, val, word in (("obs_v", 4, "obs_v"), ("fix_std", False, "log_std"), ("env_term_body", "head", "env_term_body"), ("reward_id", "world_rfc_implicit_v2", "obs_v"),
+                           ("env_init_noise", 0.1, "env_init_noise"), ("obs_coord", "heading", "obs_coord")):
+        d = dict(base); d[key] = val
+        try:
+            supported_variant(_cfg_view(d))
+        except AssertionError as e:
+            assert word in str(e), (key, str(e))
+        else:
+            raise AssertionError(f"{key} = {val!r} must be refused")
+    for key, val in (("obs_v", 5), ("obs_v", 6), ("env_term_body", "root"), ("env_term_body", "Head"), ("reward_id", "world_rfc_implicit_v1_mul"), ("actor_type", "mcp")):
+        d = dict(base); d[key] = val
+        assert supported_variant(_cfg_view(d)) == "implicit"
+
+
+def test_reference_yaml_coverage():
+    """how many of the reference's own config files the drop-in accepts (needs the reference checkout; the count is what DESIGN.md section 5 quotes)"""
+    import glob
+    import pytest
+    import yaml
+    from uhc.agents.agent_copycat import supported_variant
+    root = os.environ.get("UHC_REFERENCE", "/root/reference")
+    files = sorted(glob.glob(os.path.join(root, "config", "**", "*.yml"), recursive=True))
+    if not files:
+        pytest.skip("reference checkout not present")
+    accepted = 0
+    for f in files:
+        d = yaml.safe_load(open(f)) or {}
+        if d.get("agent_name", "agent_copycat") != "agent_copycat":
+            continue
+        try:
+            supported_variant(_cfg_view(d)); accepted += 1
+        except AssertionError:
+            pass
+    assert len(files) == 115 and accepted == 86, (len(files), accepted)

@@ -45,6 +45,31 @@ class _Log(dict):
     __getattr__ = dict.get
 
 
+def supported_variant(cfg):
+    """The reference configuration keys this engine implements; returns the residual-force mode ("implicit" | "explicit" | "none").  `cfg` needs `.get(key, default)`
+    and the attributes obs_v, actor_type, reward_id, fix_std, residual_force (uhc/utils/config_utils/copycat_config.py).  Everything else raises an AssertionError
+    naming the key: of the reference's 115 yaml files 86 pass (tests/test_shim_cpu.py counts them); the others use explicit residual forces with contact gating /
+    projection / body subsets (10), the six-term world_rfc_implicit_v2 / _v3 rewards (8), obs_v 0 / 4 (6), a trained log_std (2), ..."""
+    assert cfg.obs_v in (1, 2, 3, 5, 6) and cfg.actor_type in ("gauss", "mcp") and cfg.reward_id in reward_func, \
+        "the B200 engine implements obs_v 1 | 2 | 3 | 5 | 6, the gauss and mcp actors, world_rfc_implicit (_v1_mul) / world_rfc_explicit (obs_v 0/4, reward v2/v3: SURVEY.md section 8f, next)"
+    assert cfg.get("obs_vel", "full") == "full" and cfg.get("obs_coord", "root") == "root" and not cfg.get("obs_phase", False), "obs_vel full / obs_coord root / no phase only"
+    if cfg.obs_v == 1:
+        assert not cfg.get("has_shape", False), "obs_v 1 carries no shape vector (has_shape: false in config/release/uhc_implicit.yml)"
+    # variants the batched engine does not implement must not be accepted silently (ADVICE r1)
+    assert cfg.fix_std, "log_std is not a trained parameter in this engine (fix_std: true in every released config)"
+    assert cfg.get("env_term_body", "body") in ("body", "root", "Head"), "env_term_body: 'body' (calc_body_diff), 'root' or 'Head' (humanoid_im.py:1223-1229)"
+    rfc_mode = cfg.get("residual_force_mode", "implicit") if cfg.residual_force else "none"     # residual_force: false -> no residual-force dims (humanoid_im.py:231-243)
+    assert rfc_mode in ("implicit", "explicit", "none"), "residual_force_mode: implicit | explicit"
+    if rfc_mode == "explicit":      # the kernel restates the release settings of the explicit mode (config/release/uhc_explicit.yml)
+        assert cfg.get("residual_force_bodies", "all") == "all" and cfg.get("residual_force_torque", True) and int(cfg.get("residual_force_bodies_num", 1)) == 1 \
+            and not cfg.get("residual_contact_only", False) and not cfg.get("residual_contact_projection", False), \
+            "explicit residual force: only residual_force_bodies = all, one point per body, torque on, no contact gating / projection"
+    # the fused reward follows the residual-force mode (world_rfc_implicit :12-88 / world_rfc_explicit :253-341), as the released configs pair them
+    assert cfg.reward_id in (("world_rfc_explicit",) if rfc_mode == "explicit" else ("world_rfc_implicit", "world_rfc_implicit_v1_mul")), "reward_id must match residual_force_mode"
+    assert float(cfg.get("env_init_noise", 0.0)) == 0.0, "env_init_noise > 0 is not implemented"
+    return rfc_mode
+
+
 class AgentCopycat:
     def __init__(self, cfg, dtype, device, training=True, checkpoint_epoch=0):
         import torch
@@ -73,23 +98,7 @@ class AgentCopycat:
             if not dist.is_initialized():
                 dist.init_process_group("nccl")
             sync = make_nccl_grad_sync(world)
-        assert cfg.obs_v in (1, 2, 3, 5, 6) and cfg.actor_type in ("gauss", "mcp") and cfg.reward_id in reward_func, \
-            "the B200 engine implements obs_v 1 | 2 | 3 | 5 | 6, the gauss and mcp actors, world_rfc_implicit (_v1_mul) / world_rfc_explicit (obs_v 0/4, reward v2/v3: SURVEY.md section 8f, next)"
-        assert cfg.get("obs_vel", "full") == "full" and cfg.get("obs_coord", "root") == "root" and not cfg.get("obs_phase", False), "obs_vel full / obs_coord root / no phase only"
-        if cfg.obs_v == 1:
-            assert not cfg.get("has_shape", False), "obs_v 1 carries no shape vector (has_shape: false in config/release/uhc_implicit.yml)"
-        # variants the batched engine does not implement must not be accepted silently
-        assert cfg.fix_std, "log_std is not a trained parameter in this engine (fix_std: true in every released config)"
-        assert cfg.get("env_term_body", "body") in ("body", "root", "Head"), "env_term_body: 'body' (calc_body_diff), 'root' or 'Head' (humanoid_im.py:1223-1229)"
-        rfc_mode = cfg.get("residual_force_mode", "implicit") if cfg.residual_force else "none"     # residual_force: false -> no residual-force dims (humanoid_im.py:231-243)
-        assert rfc_mode in ("implicit", "explicit", "none"), "residual_force_mode: implicit | explicit"
-        if rfc_mode == "explicit":      # the kernel restates the release settings of the explicit mode (config/release/uhc_explicit.yml)
-            assert cfg.get("residual_force_bodies", "all") == "all" and cfg.get("residual_force_torque", True) and int(cfg.get("residual_force_bodies_num", 1)) == 1 \
-                and not cfg.get("residual_contact_only", False) and not cfg.get("residual_contact_projection", False), \
-                "explicit residual force: only residual_force_bodies = all, one point per body, torque on, no contact gating / projection"
-        # the fused reward follows the residual-force mode (world_rfc_implicit :12-88 / world_rfc_explicit :253-341), as the released configs pair them
-        assert cfg.reward_id in (("world_rfc_explicit",) if rfc_mode == "explicit" else ("world_rfc_implicit", "world_rfc_implicit_v1_mul")), "reward_id must match residual_force_mode"
-        assert float(cfg.get("env_init_noise", 0.0)) == 0.0, "env_init_noise > 0 is not implemented"
+        rfc_mode = supported_variant(cfg)       # refuses (AssertionError) what the batched engine does not implement instead of accepting it silently
         self.agent = BatchedAgent(
             self.num_envs, self.data_loader.experts, self.data_loader.shapes, device=dev_index, seed=cfg.seed, policy_hsize=cfg.policy_hsize,
             value_hsize=cfg.value_hsize, htype=cfg.policy_htype, log_std=cfg.log_std, policy_lr=cfg.policy_lr, value_lr=cfg.value_lr,
